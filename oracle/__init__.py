@@ -1,0 +1,327 @@
+"""ctypes binding of the CPU oracle (oracle/qd_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (quickdna_b200/) never imports this.
+
+Parity status: pinned -- see the header of oracle/qd_oracle.h.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libqd_oracle.so")
+
+KIND_NAMES = {
+    0: "Ok",
+    1: "NonAsciiByte",
+    2: "BadNucleotide",
+    3: "UnexpectedAmbiguousNucleotide",
+    4: "BadTranslationTable",
+}
+
+
+class OracleError(ValueError):
+    """Mirrors the ValueError the reference's PyO3 layer raises (src/python_api.rs:15-19)."""
+
+    def __init__(self, kind: int, byte: int, pos: int, message: str):
+        super().__init__(message)
+        self.kind = kind
+        self.byte = byte
+        self.pos = pos
+
+
+class _Err(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("byte", C.c_uint8), ("pos", C.c_uint64)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (oracle/Makefile).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "qd_oracle.c")
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("qd_oracle.c", "qd_oracle.h", "ncbi_codes.h")
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "libqd_oracle.so"], check=True, capture_output=True)
+    assert os.path.exists(src)
+    return _LIB_PATH
+
+
+_lib: Optional[C.CDLL] = None
+
+_u8p = C.POINTER(C.c_uint8)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.qdo_tables.restype = _u8p
+        L.qdo_table_slot.argtypes = [C.c_int]
+        L.qdo_err_message.argtypes = [C.POINTER(_Err), C.c_char_p, C.c_size_t]
+        L.qdo_translate_bytes.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(_Err)]
+        L.qdo_translate_masks.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.qdo_translate_masks.restype = None
+        L.qdo_revcomp_bytes.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(_Err)]
+        L.qdo_revcomp_masks.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.qdo_revcomp_masks.restype = None
+        L.qdo_self_frames_masks.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.qdo_all_frames_masks.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        for f in (L.qdo_py_self_frames, L.qdo_py_all_frames):
+            f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t),
+                          C.POINTER(C.c_int), C.POINTER(_Err)]
+        L.qdo_parse.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(_Err)]
+        L.qdo_forward_canonical.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.qdo_forward_canonical.restype = None
+        L.qdo_canonical.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.qdo_canonical.restype = None
+        L.qdo_canonical_windows.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.qdo_canonical_windows.restype = C.c_size_t
+        L.qdo_expansions_size_hint.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+        L.qdo_expansions.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.qdo_expansions.restype = C.c_size_t
+        L.qdo_windows.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.qdo_windows.restype = C.c_size_t
+        L.qdo_windows_all.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.POINTER(C.c_size_t)]
+        L.qdo_windows_all.restype = C.c_size_t
+        L.qdo_bench_all_frames_batch.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+        L.qdo_bench_all_frames_batch.restype = C.c_double
+        L.qdo_bench_revcomp.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+        L.qdo_bench_revcomp.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+# --------------------------------------------------------------------------- helpers
+
+
+def _as_u8(x) -> np.ndarray:
+    if isinstance(x, str):
+        x = x.encode("latin-1")
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _raise(err: _Err):
+    buf = C.create_string_buffer(128)
+    lib().qdo_err_message(C.byref(err), buf, 128)
+    raise OracleError(err.kind, err.byte, err.pos, buf.value.decode("ascii"))
+
+
+ASCII_OF_MASK = b"?ATWCMYHGRKDSVBN"
+_MASK_OF_ASCII = np.zeros(256, dtype=np.uint8)
+for _m, _c in enumerate(ASCII_OF_MASK):
+    if _m:
+        _MASK_OF_ASCII[_c] = _m
+        _MASK_OF_ASCII[ord(chr(_c).lower())] = _m
+
+
+def masks_of(ascii_seq) -> np.ndarray:
+    """Plain table decode of already-valid ASCII (test convenience, no whitespace handling)."""
+    m = _MASK_OF_ASCII[_as_u8(ascii_seq)]
+    assert (m != 0).all()
+    return m
+
+
+def ascii_of(masks) -> bytes:
+    return bytes(np.frombuffer(ASCII_OF_MASK, dtype=np.uint8)[_as_u8(masks)])
+
+
+# --------------------------------------------------------------------------- API
+
+
+def tables() -> bytes:
+    return C.string_at(lib().qdo_tables(), 27 * 4096)
+
+
+def table_slot(ncbi_id: int) -> int:
+    return lib().qdo_table_slot(int(ncbi_id))
+
+
+def err_message(kind: int, byte: int) -> str:
+    e = _Err(kind, byte, 0)
+    buf = C.create_string_buffer(128)
+    lib().qdo_err_message(C.byref(e), buf, 128)
+    return buf.value.decode("ascii")
+
+
+def translate_bytes(table: int, dna, strict: bool = False) -> bytes:
+    a = _as_u8(dna)
+    out = np.empty(len(a) // 3, dtype=np.uint8)
+    err = _Err()
+    if lib().qdo_translate_bytes(int(table), int(strict), _ptr(a), len(a), _ptr(out), C.byref(err)) != 0:
+        _raise(err)
+    return out.tobytes()
+
+
+def translate_masks(slot: int, masks) -> bytes:
+    a = _as_u8(masks)
+    out = np.empty(len(a) // 3, dtype=np.uint8)
+    lib().qdo_translate_masks(int(slot), _ptr(a), len(a), _ptr(out))
+    return out.tobytes()
+
+
+def revcomp_bytes(dna, strict: bool = False) -> bytes:
+    a = _as_u8(dna)
+    out = np.empty(len(a), dtype=np.uint8)
+    err = _Err()
+    if lib().qdo_revcomp_bytes(int(strict), _ptr(a), len(a), _ptr(out), C.byref(err)) != 0:
+        _raise(err)
+    return out.tobytes()
+
+
+def revcomp_masks(masks) -> np.ndarray:
+    a = _as_u8(masks)
+    out = np.empty(len(a), dtype=np.uint8)
+    lib().qdo_revcomp_masks(_ptr(a), len(a), _ptr(out))
+    return out
+
+
+def _split(out: np.ndarray, lens, n_frames_total: int) -> List[bytes]:
+    frames, off = [], 0
+    for ln in lens:
+        if ln > 0:
+            frames.append(out[off:off + ln].tobytes())
+        off += ln
+    assert len(frames) == n_frames_total
+    return frames
+
+
+def self_frames_masks(slot: int, masks) -> List[bytes]:
+    a = _as_u8(masks)
+    out = np.empty(len(a) + 8, dtype=np.uint8)
+    lens = (C.c_size_t * 3)()
+    nf = lib().qdo_self_frames_masks(int(slot), _ptr(a), len(a), _ptr(out), lens)
+    return _split(out, list(lens), nf)
+
+
+def all_frames_masks(slot: int, masks) -> List[bytes]:
+    a = _as_u8(masks)
+    out = np.empty(2 * len(a) + 8, dtype=np.uint8)
+    lens = (C.c_size_t * 6)()
+    nf = lib().qdo_all_frames_masks(int(slot), _ptr(a), len(a), _ptr(out), lens)
+    return _split(out, list(lens), nf)
+
+
+def py_self_frames(table: int, dna, strict: bool = False) -> List[bytes]:
+    a = _as_u8(dna)
+    out = np.empty(len(a) + 8, dtype=np.uint8)
+    lens = (C.c_size_t * 3)()
+    nf = C.c_int()
+    err = _Err()
+    if lib().qdo_py_self_frames(int(table), int(strict), _ptr(a), len(a), _ptr(out), lens, C.byref(nf), C.byref(err)) != 0:
+        _raise(err)
+    return _split(out, list(lens), nf.value)
+
+
+def py_all_frames(table: int, dna, strict: bool = False) -> List[bytes]:
+    a = _as_u8(dna)
+    out = np.empty(2 * len(a) + 8, dtype=np.uint8)
+    lens = (C.c_size_t * 6)()
+    nf = C.c_int()
+    err = _Err()
+    if lib().qdo_py_all_frames(int(table), int(strict), _ptr(a), len(a), _ptr(out), lens, C.byref(nf), C.byref(err)) != 0:
+        _raise(err)
+    return _split(out, list(lens), nf.value)
+
+
+def parse(ascii_seq, strict: bool = False) -> np.ndarray:
+    a = _as_u8(ascii_seq)
+    out = np.empty(len(a), dtype=np.uint8)
+    n = C.c_size_t()
+    err = _Err()
+    if lib().qdo_parse(int(strict), _ptr(a), len(a), _ptr(out), C.byref(n), C.byref(err)) != 0:
+        _raise(err)
+    return out[: n.value].copy()
+
+
+def forward_canonical(masks) -> np.ndarray:
+    a = _as_u8(masks)
+    out = np.empty(len(a), dtype=np.uint8)
+    lib().qdo_forward_canonical(_ptr(a), len(a), _ptr(out))
+    return out
+
+
+def canonical(masks) -> np.ndarray:
+    a = _as_u8(masks)
+    out = np.empty(len(a), dtype=np.uint8)
+    lib().qdo_canonical(_ptr(a), len(a), _ptr(out))
+    return out
+
+
+def canonical_windows(masks, w: int) -> np.ndarray:
+    a = _as_u8(masks)
+    count = max(0, len(a) - w + 1) if w > 0 else 0
+    out = np.empty((count, w), dtype=np.uint8)
+    got = lib().qdo_canonical_windows(_ptr(a), len(a), w, _ptr(out))
+    assert got == count
+    return out
+
+
+def expansions_size_hint(masks) -> Optional[int]:
+    a = _as_u8(masks)
+    c = C.c_uint64()
+    ok = lib().qdo_expansions_size_hint(_ptr(a), len(a), C.byref(c))
+    return c.value if ok else None
+
+
+def expansions(masks, max_out: int = 1 << 20) -> np.ndarray:
+    a = _as_u8(masks)
+    hint = expansions_size_hint(a)
+    cap = max_out if hint is None else min(max_out, hint)
+    out = np.empty((cap, len(a)), dtype=np.uint8)
+    got = lib().qdo_expansions(_ptr(a), len(a), _ptr(out), cap)
+    return out[:got]
+
+
+def windows(seq, w: int) -> np.ndarray:
+    a = _as_u8(seq)
+    count = max(0, len(a) - w + 1) if w > 0 else 0
+    out = np.empty((count, w), dtype=np.uint8)
+    got = lib().qdo_windows(_ptr(a), len(a), w, _ptr(out))
+    assert got == count
+    return out
+
+
+def windows_all(masks, w_dna: int = 42, w_aa: int = 20) -> Tuple[np.ndarray, np.ndarray, np.ndarray, List[int]]:
+    """(dna windows [fwd then rc], aa windows [frames 0..5], origin indices, counts[8])."""
+    a = _as_u8(masks)
+    counts = (C.c_size_t * 8)()
+    total = lib().qdo_windows_all(_ptr(a), len(a), w_dna, w_aa, None, None, None, counts)
+    cs = list(counts)
+    dna = np.empty((cs[0] + cs[1], w_dna), dtype=np.uint8)
+    aa = np.empty((sum(cs[2:]), w_aa), dtype=np.uint8)
+    origin = np.empty(total, dtype=np.uint64)
+    lib().qdo_windows_all(_ptr(a), len(a), w_dna, w_aa, _ptr(dna), _ptr(aa), _ptr(origin), counts)
+    return dna, aa, origin, cs
+
+
+def bench_all_frames_batch(slot: int, dna: np.ndarray, n_reads: int, read_len: int, threads: int, reps: int = 1,
+                           out: Optional[np.ndarray] = None) -> Tuple[float, np.ndarray]:
+    a = _as_u8(dna)
+    assert a.size == n_reads * read_len
+    if out is None:
+        out = np.empty(n_reads * 2 * max(read_len - 2, 0), dtype=np.uint8)
+    secs = lib().qdo_bench_all_frames_batch(int(slot), _ptr(a), n_reads, read_len, _ptr(out), threads, reps)
+    return secs, out
+
+
+def bench_revcomp(dna: np.ndarray, threads: int, reps: int = 1) -> Tuple[float, np.ndarray]:
+    a = _as_u8(dna)
+    out = np.empty(a.size, dtype=np.uint8)
+    secs = lib().qdo_bench_revcomp(_ptr(a), a.size, _ptr(out), threads, reps)
+    return secs, out
