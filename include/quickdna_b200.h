@@ -1,0 +1,225 @@
+/* quickdna_b200 -- C ABI of the B200-native quickdna sequence hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / CUDA types in the
+ * signatures (a CUDA stream crosses as `void*`).  Each entry point names the reference
+ * interface whose body it replaces (paths relative to the SecureDNA/quickdna checkout).
+ * INTEGRATION.md shows the Rust `extern "C"` block and the PyO3 shims that bind it.
+ *
+ * Conventions kept from the reference:
+ *   - inputs are borrowed; outputs are caller-allocated (every size is a closed form of n);
+ *   - the translation table id is validated BEFORE any DNA byte (src/python_api.rs:35,48);
+ *   - errors carry the offending byte exactly as src/errors.rs:17-29 does (`kind` + `byte`
+ *     rebuild the reference's message, see qd_err_message); `pos` / `seq_index` are the
+ *     extra "first error position" the north star asks for;
+ *   - on error the output contents are unspecified (the reference drops its Vec).
+ *
+ * There is NO CPU fallback: every compute entry point runs sm_100a kernels and returns
+ * QD_ERR_CUDA if no usable device / kernel image is present.
+ */
+#ifndef QUICKDNA_B200_H
+#define QUICKDNA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QD_ABI_VERSION 1
+
+/* ---- status codes (return value of every int-returning entry point) ------------------ */
+enum {
+    QD_OK = 0,
+    QD_ERR_NON_ASCII_BYTE = 1,       /* TranslationError::NonAsciiByte(u8)                    */
+    QD_ERR_BAD_NUCLEOTIDE = 2,       /* TranslationError::BadNucleotide(char)                 */
+    QD_ERR_UNEXPECTED_AMBIGUOUS = 3, /* TranslationError::UnexpectedAmbiguousNucleotide(char) */
+    QD_ERR_BAD_TABLE = 4,            /* TranslationError::BadTranslationTable(u8)             */
+    QD_ERR_BAD_MASK = 5,             /* MASK encoding only: byte is not a valid IUPAC mask     */
+    QD_ERR_INVALID_ARGUMENT = 90,
+    QD_ERR_CUDA = 100                /* CUDA runtime failure; qd_last_cuda_error() has text   */
+};
+
+/* ---- encodings ------------------------------------------------------------------------ */
+enum {
+    QD_ENC_ASCII = 0, /* one ASCII letter per nucleotide (PyO3 path, src/python_api.rs)        */
+    QD_ENC_MASK = 1   /* one byte holding the 4-bit IUPAC set A=1,T=2,C=4,G=8 -- the in-memory
+                         value of `Nucleotide` / `NucleotideAmbiguous` (src/nucleotide.rs:20-53),
+                         i.e. a `&[T]` of the typed Rust API reinterpreted as bytes             */
+};
+
+/* ---- frame selection -------------------------------------------------------------------- */
+enum {
+    QD_FRAMES_ONE = 1,  /* translate:               src/rust_api.rs:216-219                    */
+    QD_FRAMES_SELF = 3, /* translate_self_frames:   src/rust_api.rs:227-255                    */
+    QD_FRAMES_ALL = 6   /* translate_all_frames:    src/rust_api.rs:263-270                    */
+};
+
+typedef struct qd_ctx qd_ctx;
+
+typedef struct qd_err {
+    int32_t kind;       /* QD_OK or one of QD_ERR_* above                                      */
+    uint8_t byte;       /* payload of the reference's error variant (offending byte; upper-case
+                           letter for kind 3; table id for kind 4)                              */
+    uint64_t pos;       /* index of the first offending byte within its sequence               */
+    uint64_t seq_index; /* sequence index within a batch (0 for single-sequence calls)         */
+} qd_err;
+
+/* ---- context ----------------------------------------------------------------------------
+ * One context owns one device, one stream, the device-resident LUTs and grow-only scratch
+ * buffers.  Entry points taking a context are serialised on an internal mutex (the
+ * reference's functions are pure and re-entrant; use one context per thread to run in
+ * parallel). */
+int qd_ctx_create(qd_ctx **out, int device);
+void qd_ctx_destroy(qd_ctx *ctx);
+int qd_ctx_device(const qd_ctx *ctx);
+void *qd_ctx_stream(const qd_ctx *ctx); /* the context's cudaStream_t */
+int qd_ctx_sm_count(const qd_ctx *ctx);
+const char *qd_last_cuda_error(const qd_ctx *ctx);
+int qd_abi_version(void);
+/* input bytes per chunk of the host batch pipeline (default 256 MiB) */
+int qd_ctx_set_chunk_bytes(qd_ctx *ctx, size_t bytes);
+
+/* ---- tables / errors (host-only helpers) --------------------------------------------------
+ * qd_table_slot:  TranslationTable::try_from(u8) + table_index(), src/trans_table.rs:114-146,
+ *                 230-267.  Returns the LUT slot 0..26 or -1 (=> BadTranslationTable).
+ * qd_table_data:  the 4096-byte LUT of a slot in the reference's layout, index
+ *                 (m0<<8)|(m1<<4)|m2 (src/trans_table.rs:78-85); all 27 are contiguous, so
+ *                 qd_table_data(0) addresses a byte-for-byte image of src/tables.dat.
+ * qd_err_message: Display of TranslationError, src/errors.rs:19-28 (what PyO3 puts into the
+ *                 ValueError, src/python_api.rs:15-19).  Returns the text length. */
+int qd_table_slot(int ncbi_id);
+const uint8_t *qd_table_data(int slot);
+int qd_err_message(const qd_err *err, char *buf, size_t cap);
+
+/* ---- output geometry -----------------------------------------------------------------------
+ * Frame k (0..2, either strand) of an n-nt sequence has floor((n-k)/3) residues when n > k
+ * (src/rust_api.rs:227-255); the reference returns only non-empty frames.
+ *
+ * Device / batch layout ("slots"): a sequence is cut into runs of 48 nt; with
+ * R = ceil(n/48) each of the F frames (F = 1, 3 or 6) owns a slot of 16*R bytes, slots back to
+ * back, so one sequence occupies 16*R*F bytes and every kernel store is an aligned 128-bit
+ * store.  Forward frame k starts at the beginning of slot k; reverse-complement frame k ENDS at
+ * the end of slot 3+k (it is produced back to front).  Bytes of a slot outside its frame are 0.
+ */
+size_t qd_frame_len(size_t n, int k);
+size_t qd_runs(size_t n);                                           /* R = ceil(n/48)        */
+size_t qd_slots_bytes(size_t n, int frames);                        /* 16*R*frames           */
+size_t qd_slot_frame_offset(size_t n, int frames, int frame_index); /* first residue's offset */
+
+/* ======================= host-pointer entry points (synchronous) =========================== */
+
+/* translate_dna_bytes::<T> / translate_dna::<T>: src/trans_table.rs:176-203, 205-227
+ * (PyO3 _translate/_translate_strict, src/python_api.rs:33-51; DnaSequence::translate,
+ * src/rust_api.rs:216-219).  out: floor(n/3) bytes.  ASCII: validates the first 3*floor(n/3)
+ * bytes; strict rejects ambiguity codes. */
+int qd_translate(qd_ctx *ctx, int table, int enc, int strict, const uint8_t *dna, size_t n,
+                 uint8_t *out, qd_err *err);
+
+/* translate_self_frames / translate_all_frames: src/rust_api.rs:227-255, 263-270 (the Python
+ * wrappers at quickdna/__init__.py:128-185 make 3 / 7 native calls for the same result).
+ * frames = QD_FRAMES_SELF or QD_FRAMES_ALL.  out: frames written back to back, tightly
+ * (f0|f1|f2[|r0|r1|r2]); out_len[k] = residues of frame k (0 when the reference omits it);
+ * *n_frames = number of frames the reference returns (6/4/2/0 or 3/2/1/0).  Capacity needed:
+ * sum of qd_frame_len(n,k) over the frames.  ASCII: all n bytes are validated when n >= 3,
+ * none when n < 3. */
+int qd_translate_frames(qd_ctx *ctx, int table, int enc, int strict, int frames,
+                        const uint8_t *dna, size_t n, uint8_t *out, size_t out_len[6],
+                        int *n_frames, qd_err *err);
+
+/* reverse_complement_bytes::<T> / reverse_complement::<T>: src/trans_table.rs:269-278, 284-286
+ * (PyO3 _reverse_complement[_strict], src/python_api.rs:58-74; DnaSequence::reverse_complement,
+ * src/rust_api.rs:273-275).  out: n bytes, same encoding as the input; ASCII output is upper
+ * case.  Every byte is validated. */
+int qd_revcomp(qd_ctx *ctx, int enc, int strict, const uint8_t *dna, size_t n, uint8_t *out,
+               qd_err *err);
+
+/* Batch of n_seq sequences stored back to back in `dna` with CSR offsets[n_seq+1]
+ * (offsets[0] = 0): what a caller looping DnaSequence::translate* over a Vec of reads does,
+ * in one call.  out: slot layout above, sequence i at out_offsets[i] = 16*frames*sum_{j<i}R_j;
+ * out_offsets (n_seq+1 entries) is filled when non-NULL.  Capacity: qd_batch_out_bytes().
+ * Work is pipelined in chunks of whole sequences (H2D, kernel, D2H overlap). */
+size_t qd_batch_out_bytes(const uint64_t *offsets, size_t n_seq, int frames);
+int qd_translate_frames_batch(qd_ctx *ctx, int table, int enc, int strict, int frames,
+                              const uint8_t *dna, const uint64_t *offsets, size_t n_seq,
+                              uint8_t *out, uint64_t *out_offsets, qd_err *err);
+/* Same for n_seq sequences of identical length (no offsets array; closed-form geometry:
+ * sequence i at dna + i*seq_len and out + i*qd_slots_bytes(seq_len, frames)). */
+int qd_translate_frames_batch_uniform(qd_ctx *ctx, int table, int enc, int strict, int frames,
+                                      const uint8_t *dna, size_t n_seq, size_t seq_len,
+                                      uint8_t *out, qd_err *err);
+
+/* DnaSequence::<Nucleotide>::canonical over every length-w window: src/canonical.rs:17-55,
+ * 71-118, 129-179 applied as in benches/canonical.rs:29-34.  Strict alphabet only.
+ * forward_only != 0 gives ForwardCanonical.  out: (n-w+1)*w bytes (0 windows if n < w),
+ * window i at out + i*w, same encoding as the input (ASCII output upper case). 1 <= w <= 64. */
+int qd_canonical_windows(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna, size_t n,
+                         size_t w, uint8_t *out, qd_err *err);
+
+/* DnaSequence::<NucleotideAmbiguous>::expansions over a batch of n_win windows of w nt each
+ * (benches/expansions.rs:126-130 shape): src/expansions.rs:35-108.
+ *   counts[i]      = Expansions::size_hint() of window i (UINT64_MAX on overflow == (usize::MAX, None))
+ *   out_index[i]   = index of window i's first expansion in `out`, or UINT64_MAX when
+ *                    counts[i] > max_expansions (such windows are skipped, as
+ *                    benches/expansions.rs:57-66 does); out_index[n_win] = total expansions
+ *   out            = expansions in iteration order, w bytes each (strict alphabet, input encoding)
+ * Call with out == NULL to get counts / out_index only.  out capacity:
+ * out_index[n_win]*w, at most n_win*max_expansions*w.  1 <= w <= 64. */
+int qd_expansion_windows(qd_ctx *ctx, int enc, const uint8_t *windows, size_t n_win, size_t w,
+                         uint64_t max_expansions, uint64_t *counts, uint64_t *out_index,
+                         uint8_t *out, qd_err *err);
+
+/* DnaSequence::windows / ProteinSequence::windows, src/rust_api.rs:100-104, 277-279:
+ * out + i*w holds seq[i..i+w); returns the window count through *n_windows. */
+int qd_windows(qd_ctx *ctx, const uint8_t *seq, size_t n, size_t w, uint8_t *out,
+               size_t *n_windows);
+
+/* benches/all_windows.rs:78-102 (SequenceWindows::from_dna, table Ncbi1) + :39-75 (enumerate)
+ * for one strict sequence: forward DNA windows, reverse-complement DNA windows (ASCII), then the
+ * aa windows of the frames the reference returns, each with its origin index.
+ *   counts[0..1] = DNA / RC-DNA window counts, counts[2..7] = aa windows per returned frame
+ *   dna_out: (counts[0]+counts[1])*w_dna bytes; aa_out: sum(counts[2..7])*w_aa bytes;
+ *   origin: one uint64 per window in enumerate() order.  Any of the three may be NULL. */
+int qd_windows_all(qd_ctx *ctx, int enc, const uint8_t *dna, size_t n, size_t w_dna, size_t w_aa,
+                   uint8_t *dna_out, uint8_t *aa_out, uint64_t *origin, size_t counts[8],
+                   qd_err *err);
+
+/* =================== device-pointer entry points (asynchronous) ============================
+ * Same arithmetic on buffers already resident in HBM; launched on `stream` (NULL = the
+ * context's stream) and NOT synchronised.  `dna` may have any alignment; kernels read whole
+ * 16-byte granules, so the granules containing the first and last byte must be readable (true
+ * for any cudaMalloc / torch allocation).  `out` must be 16-byte aligned and sized by the slot
+ * layout (qd_slots_bytes / qd_batch_out_bytes).  Errors are reported through a device-side
+ * key: call qd_dev_error_reset before a launch sequence and qd_dev_error_fetch (which
+ * synchronises the stream) after it. */
+int qd_dev_error_reset(qd_ctx *ctx, void *stream);
+/* dna/offsets: the device buffers the launches ran on (offsets NULL for a single sequence or
+ * uniform batch with seq_len given); fills err like the host entry points do. */
+int qd_dev_error_fetch(qd_ctx *ctx, void *stream, int enc, int strict, const uint8_t *dna_dev,
+                       const uint64_t *offsets_dev, size_t n_seq, size_t uniform_len, qd_err *err);
+
+int qd_revcomp_dev(qd_ctx *ctx, int enc, int strict, const uint8_t *dna_dev, size_t n,
+                   uint8_t *out_dev, void *stream);
+/* single sequence, slot layout */
+int qd_translate_frames_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
+                            const uint8_t *dna_dev, size_t n, uint8_t *out_dev, void *stream);
+int qd_translate_frames_batch_uniform_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
+                                          const uint8_t *dna_dev, size_t n_seq, size_t seq_len,
+                                          uint8_t *out_dev, void *stream);
+/* variable lengths: CSR offsets on the device (absolute, offsets_dev[0] corresponds to dna_dev[0]);
+ * the run prefix / tile map the kernel needs are built on `stream` in context-owned scratch. */
+int qd_translate_frames_batch_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
+                                  const uint8_t *dna_dev, const uint64_t *offsets_dev,
+                                  size_t n_seq, size_t total_nt, uint8_t *out_dev, void *stream);
+int qd_canonical_windows_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev,
+                             size_t n, size_t w, uint8_t *out_dev, void *stream);
+int qd_windows_dev(qd_ctx *ctx, const uint8_t *seq_dev, size_t n, size_t w, uint8_t *out_dev,
+                   void *stream);
+
+/* Number of kernel launches this context has issued (bench.py's gpu_launches claim). */
+uint64_t qd_launch_count(const qd_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUICKDNA_B200_H */

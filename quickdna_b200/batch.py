@@ -1,0 +1,262 @@
+"""Batch and device-resident entry points (numpy / torch plumbing over the C ABI).
+
+This is the SURVEY 8(f) rank-4 "Python batch API": what a caller looping
+`DnaSequence.translate_all_frames` over many reads does (quickdna/__init__.py:163-185), in one
+native call.  torch is used only for device memory and streams.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _native as N
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        return np.frombuffer(a, dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def frame_len(n: int, k: int) -> int:
+    return (n - k) // 3 if n > k else 0
+
+
+def runs(n: int) -> int:
+    return (n + 47) // 48
+
+
+def slot_frame_offset(n: int, frames: int, f: int) -> int:
+    """Offset of frame f's first residue inside a sequence's slot block (include/quickdna_b200.h)."""
+    slot = 16 * runs(n)
+    if f < 3 or frames != N.FRAMES_ALL:
+        return f * slot
+    return (f + 1) * slot - frame_len(n, f - 3)
+
+
+@dataclass
+class FramesBatch:
+    """Result of a batched frame translation in the slot layout."""
+
+    data: np.ndarray  # uint8, slot layout
+    out_offsets: np.ndarray  # uint64 [n_seq+1]
+    lengths: np.ndarray  # uint64 [n_seq]
+    frames: int
+
+    def frame(self, i: int, f: int) -> bytes:
+        n = int(self.lengths[i])
+        ln = frame_len(n, f % 3)
+        base = int(self.out_offsets[i]) + slot_frame_offset(n, self.frames, f)
+        return self.data[base:base + ln].tobytes()
+
+    def sequence_frames(self, i: int) -> List[bytes]:
+        """The frames the reference returns for sequence i (empty frames omitted)."""
+        n_slots = 1 if self.frames == N.FRAMES_ONE else self.frames
+        out = [self.frame(i, f) for f in range(n_slots)]
+        return [x for x in out if len(x)]
+
+
+def translate_frames_batch(
+    reads: Union[np.ndarray, Sequence[bytes], Tuple[np.ndarray, np.ndarray]],
+    table: int = 1,
+    strict: bool = False,
+    frames: int = N.FRAMES_ALL,
+    enc: int = N.ENC_ASCII,
+    ctx: Optional[N.Context] = None,
+) -> FramesBatch:
+    """Translate every read of a batch.
+
+    reads: a 2-D uint8 array (n_reads x read_len, uniform batch), a (flat, offsets) pair
+    (CSR, offsets uint64 [n+1]), or a sequence of bytes objects.
+    """
+    ctx = ctx or N.default_context()
+    L = N.lib()
+    err = N.QdErr()
+    if isinstance(reads, np.ndarray) and reads.ndim == 2:
+        a = _u8(reads)
+        n_seq, seq_len = a.shape
+        per = 16 * runs(seq_len) * frames
+        out = np.empty(n_seq * per, dtype=np.uint8)
+        rc = L.qd_translate_frames_batch_uniform(ctx.handle, table, enc, int(strict), frames, _p(a), n_seq, seq_len, _p(out),
+                                                 C.byref(err))
+        ctx.check(rc, err)
+        return FramesBatch(out, np.arange(n_seq + 1, dtype=np.uint64) * np.uint64(per),
+                           np.full(n_seq, seq_len, dtype=np.uint64), frames)
+    if isinstance(reads, tuple):
+        flat, offsets = _u8(reads[0]), np.ascontiguousarray(reads[1], dtype=np.uint64)
+    else:
+        lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
+        offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offsets[1:])
+        flat = _u8(b"".join(bytes(r) for r in reads))
+    n_seq = len(offsets) - 1
+    total = int(L.qd_batch_out_bytes(_p(offsets), n_seq, frames))
+    out = np.empty(max(total, 1), dtype=np.uint8)
+    out_offsets = np.empty(n_seq + 1, dtype=np.uint64)
+    if flat.size == 0:
+        flat = np.zeros(1, dtype=np.uint8)
+    rc = L.qd_translate_frames_batch(ctx.handle, table, enc, int(strict), frames, _p(flat), _p(offsets), n_seq, _p(out),
+                                     _p(out_offsets), C.byref(err))
+    ctx.check(rc, err)
+    return FramesBatch(out[:total], out_offsets, np.diff(offsets), frames)
+
+
+def canonical_windows(dna, w: int = 42, forward_only: bool = False, enc: int = N.ENC_ASCII,
+                      ctx: Optional[N.Context] = None) -> np.ndarray:
+    """Every length-w window of a strict sequence, canonicalised (src/canonical.rs; benches/canonical.rs:29-34)."""
+    ctx = ctx or N.default_context()
+    a = _u8(dna)
+    count = max(0, a.size - w + 1)
+    out = np.empty((count, w), dtype=np.uint8)
+    err = N.QdErr()
+    rc = N.lib().qd_canonical_windows(ctx.handle, enc, int(forward_only), _p(a if a.size else np.zeros(1, np.uint8)), a.size, w,
+                                      _p(out if count else np.zeros(1, np.uint8)), C.byref(err))
+    ctx.check(rc, err)
+    return out
+
+
+def expansion_windows(windows, max_expansions: int = 16, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    """Expansions of a batch of equal-length ambiguous windows (src/expansions.rs; benches/expansions.rs:126-130).
+
+    Returns (counts, out_index, rows): counts[i] = size_hint (2**64-1 on overflow), out_index[i] = first row of
+    window i or 2**64-1 if it was skipped (more than max_expansions), rows = uint8 [total, w].
+    """
+    ctx = ctx or N.default_context()
+    a = _u8(windows)
+    assert a.ndim == 2
+    n_win, w = a.shape
+    counts = np.empty(n_win, dtype=np.uint64)
+    out_index = np.empty(n_win + 1, dtype=np.uint64)
+    err = N.QdErr()
+    L = N.lib()
+    rc = L.qd_expansion_windows(ctx.handle, enc, _p(a), n_win, w, max_expansions, _p(counts), _p(out_index), None, C.byref(err))
+    ctx.check(rc, err)
+    total = int(out_index[n_win])
+    rows = np.empty((total, w), dtype=np.uint8)
+    if total:
+        rc = L.qd_expansion_windows(ctx.handle, enc, _p(a), n_win, w, max_expansions, _p(counts), _p(out_index), _p(rows),
+                                    C.byref(err))
+        ctx.check(rc, err)
+    return counts, out_index, rows
+
+
+def windows(seq, w: int, ctx: Optional[N.Context] = None) -> np.ndarray:
+    """DnaSequence::windows / ProteinSequence::windows (src/rust_api.rs:100-104, 277-279)."""
+    ctx = ctx or N.default_context()
+    a = _u8(seq)
+    count = max(0, a.size - w + 1)
+    out = np.empty((count, w), dtype=np.uint8)
+    n_windows = C.c_size_t()
+    rc = N.lib().qd_windows(ctx.handle, _p(a if a.size else np.zeros(1, np.uint8)), a.size, w,
+                            _p(out if count else np.zeros(1, np.uint8)), C.byref(n_windows))
+    ctx.check(rc)
+    assert n_windows.value == count
+    return out
+
+
+def windows_all(dna, w_dna: int = 42, w_aa: int = 20, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    """benches/all_windows.rs SequenceWindows::from_dna + enumerate for one strict sequence.
+
+    Returns (dna_windows [fwd then rc], aa_windows [returned frames in order], origin, counts[8]).
+    """
+    ctx = ctx or N.default_context()
+    a = _u8(dna)
+    n = a.size
+
+    def nwin(length, w):
+        return length + 1 - min(w, length + 1)
+
+    n_dna = nwin(n, w_dna) if n else 0
+    lens = [frame_len(n, f % 3) for f in range(6)]
+    n_aa = sum(nwin(ln, w_aa) for ln in lens if ln)
+    dna_out = np.empty((2 * n_dna, w_dna), dtype=np.uint8)
+    aa_out = np.empty((n_aa, w_aa), dtype=np.uint8)
+    origin = np.empty(2 * n_dna + n_aa, dtype=np.uint64)
+    counts = (C.c_size_t * 8)()
+    err = N.QdErr()
+    dummy = np.zeros(1, np.uint8)
+    rc = N.lib().qd_windows_all(ctx.handle, enc, _p(a if n else dummy), n, w_dna, w_aa, _p(dna_out if dna_out.size else dummy),
+                                _p(aa_out if aa_out.size else dummy), _p(origin if origin.size else np.zeros(1, np.uint64)),
+                                counts, C.byref(err))
+    ctx.check(rc, err)
+    return dna_out, aa_out, origin, list(counts)
+
+
+# ----------------------------------------------------------------------------------------------
+# device-resident (torch tensors on the context's GPU); asynchronous on torch's current stream
+# ----------------------------------------------------------------------------------------------
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def revcomp_dev(dna, out=None, strict: bool = False, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    if out is None:
+        out = torch.empty_like(dna)
+    rc = N.lib().qd_revcomp_dev(ctx.handle, enc, int(strict), C.c_void_p(dna.data_ptr()), dna.numel(),
+                                C.c_void_p(out.data_ptr()), _stream_ptr(torch))
+    ctx.check(rc)
+    return out
+
+
+def translate_frames_uniform_dev(dna, n_seq: int, seq_len: int, out=None, table: int = 1, strict: bool = False,
+                                 frames: int = N.FRAMES_ALL, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    if out is None:
+        out = torch.empty(n_seq * 16 * runs(seq_len) * frames, dtype=torch.uint8, device=dna.device)
+    rc = N.lib().qd_translate_frames_batch_uniform_dev(ctx.handle, table, enc, int(strict), frames, C.c_void_p(dna.data_ptr()),
+                                                       n_seq, seq_len, C.c_void_p(out.data_ptr()), _stream_ptr(torch))
+    ctx.check(rc)
+    return out
+
+
+def translate_frames_csr_dev(dna, offsets, out=None, table: int = 1, strict: bool = False, frames: int = N.FRAMES_ALL,
+                             enc: int = N.ENC_ASCII, total_runs: Optional[int] = None, ctx: Optional[N.Context] = None):
+    """dna: uint8 device tensor; offsets: int64 device tensor [n_seq+1] starting at 0."""
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    n_seq = offsets.numel() - 1
+    if out is None:
+        if total_runs is None:
+            lens = offsets[1:] - offsets[:-1]
+            total_runs = int(((lens + 47) // 48).sum().item())
+        out = torch.empty(total_runs * 16 * frames, dtype=torch.uint8, device=dna.device)
+    rc = N.lib().qd_translate_frames_batch_dev(ctx.handle, table, enc, int(strict), frames, C.c_void_p(dna.data_ptr()),
+                                               C.c_void_p(offsets.data_ptr()), n_seq, dna.numel(), C.c_void_p(out.data_ptr()),
+                                               _stream_ptr(torch))
+    ctx.check(rc)
+    return out
+
+
+def dev_error_reset(ctx: Optional[N.Context] = None):
+    import torch
+
+    ctx = ctx or N.default_context()
+    ctx.check(N.lib().qd_dev_error_reset(ctx.handle, _stream_ptr(torch)))
+
+
+def dev_error_fetch(dna, offsets=None, n_seq: int = 0, uniform_len: int = 0, strict: bool = False, enc: int = N.ENC_ASCII,
+                    ctx: Optional[N.Context] = None) -> Optional[N.TranslationError]:
+    """Synchronises; returns None when the launches since dev_error_reset saw only valid input."""
+    import torch
+
+    ctx = ctx or N.default_context()
+    err = N.QdErr()
+    rc = N.lib().qd_dev_error_fetch(ctx.handle, _stream_ptr(torch), enc, int(strict), C.c_void_p(dna.data_ptr()),
+                                    None if offsets is None else C.c_void_p(offsets.data_ptr()), n_seq, uniform_len, C.byref(err))
+    if rc in (N.QD_ERR_CUDA, N.QD_ERR_INVALID_ARGUMENT):
+        ctx.check(rc)
+    return None if rc == N.QD_OK else N.make_error(err)

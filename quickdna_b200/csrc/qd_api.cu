@@ -1,0 +1,974 @@
+// quickdna_b200 -- C ABI implementation (include/quickdna_b200.h) over the sm_100a kernels.
+//
+// No CPU fallback: every compute entry point launches kernels and returns QD_ERR_CUDA when that
+// is impossible.  Host code here only moves bytes, sizes buffers and classifies the one offending
+// byte of an error the way src/nucleotide.rs:268-315 does.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/quickdna_b200.h"
+#include "qd_kernels.cuh"
+#include "qd_tables.hpp"
+
+using namespace qd;
+
+namespace {
+
+const HostTables& host_tables() {
+    static HostTables* T = [] {
+        auto* t = new HostTables();
+        build_host_tables(*t);
+        return t;
+    }();
+    return *T;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);  // 1 MiB granules, >= 16 B slack
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int N_PIPE = 3;  // streams / buffer sets of the chunked host pipeline
+
+struct Pipe {
+    cudaStream_t stream = nullptr;
+    DevBuf in, out, offsets, run_prefix, tile_first, block_sums;
+};
+
+}  // namespace
+
+struct qd_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string last_error;
+    uint64_t launches = 0;
+    // device-resident tables
+    uint16_t* d_lut = nullptr;  // 27 * 4096
+    uint8_t* d_tables = nullptr;  // 256-byte tables, see TAB_* offsets
+    unsigned long long* d_err = nullptr;
+    unsigned long long* h_err = nullptr;  // pinned
+    uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
+    DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums;
+    Pipe pipe[N_PIPE];
+    size_t chunk_bytes = size_t(256) << 20;  // input bytes per pipeline chunk
+    int occ_frames[3] = {0, 0, 0};
+};
+
+namespace {
+
+enum {
+    TAB_DECODE_ASCII = 0,
+    TAB_DECODE_MASK,
+    TAB_RC_ASCII,
+    TAB_RC_ASCII_STRICT,
+    TAB_RC_MASK,
+    TAB_RC_MASK_STRICT,
+    TAB_RC_MASK_TO_ASCII,
+    TAB_RC_MASK_TO_ASCII_STRICT,
+    TAB_UPPER_ASCII,
+    TAB_UPPER_ASCII_STRICT,
+    TAB_MASK_TO_ASCII,
+    TAB_MASK_TO_ASCII_STRICT,
+    TAB_TO_MASK_ASCII,
+    TAB_TO_MASK_MASK,
+    TAB_COUNT
+};
+
+#define QD_CUDA(ctx, expr)                                                                    \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);          \
+            return QD_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+inline const uint8_t* tab(const qd_ctx* c, int which) { return c->d_tables + 256 * which; }
+
+void clear_err(qd_err* e) {
+    if (e) {
+        e->kind = QD_OK;
+        e->byte = 0;
+        e->pos = 0;
+        e->seq_index = 0;
+    }
+}
+
+int set_err(qd_err* e, int kind, uint8_t byte, uint64_t pos, uint64_t seq) {
+    if (e) {
+        e->kind = kind;
+        e->byte = byte;
+        e->pos = pos;
+        e->seq_index = seq;
+    }
+    return kind;
+}
+
+// src/nucleotide.rs:285-315 + :268-283 for the one byte the kernels singled out
+int classify_byte(int enc, int strict, uint8_t b, uint8_t* payload) {
+    if (enc == QD_ENC_ASCII) {
+        if (b >= 128) {
+            *payload = b;
+            return QD_ERR_NON_ASCII_BYTE;
+        }
+        const uint8_t m = mask_of_ascii(b);
+        if (!m) {
+            *payload = b;
+            return QD_ERR_BAD_NUCLEOTIDE;
+        }
+        if (strict && popcount4(m) > 1) {
+            *payload = ascii_of_mask(m);
+            return QD_ERR_UNEXPECTED_AMBIGUOUS;
+        }
+    } else {
+        if (b < 1 || b > 15) {
+            *payload = b;
+            return QD_ERR_BAD_MASK;
+        }
+        if (strict && popcount4(b) > 1) {
+            *payload = ascii_of_mask(b);
+            return QD_ERR_UNEXPECTED_AMBIGUOUS;
+        }
+    }
+    *payload = b;
+    return QD_OK;
+}
+
+int check_table(int table, qd_err* err, int* slot) {
+    *slot = (table < 0 || table > 255) ? -1 : qd_table_slot(table);
+    if (*slot < 0) return set_err(err, QD_ERR_BAD_TABLE, (uint8_t)table, 0, 0);
+    return QD_OK;
+}
+
+bool valid_frames(int f) { return f == QD_FRAMES_ONE || f == QD_FRAMES_SELF || f == QD_FRAMES_ALL; }
+
+size_t frames_smem_bytes() { return sizeof(FramesSmem<6, false>); }
+
+template <int FRAMES>
+int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_slot) {
+    auto kern = translate_frames_kernel<FRAMES, false>;
+    const size_t smem = frames_smem_bytes();
+    if (c->occ_frames[occ_slot] == 0) {
+        QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_THREADS, smem));
+        c->occ_frames[occ_slot] = std::max(1, occ);
+    }
+    if (p.n_tiles == 0) return QD_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>(p.n_tiles, (uint64_t)c->sm_count * c->occ_frames[occ_slot]);
+    kern<<<grid, TILE_THREADS, smem, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s) {
+    switch (frames) {
+        case QD_FRAMES_ONE: return launch_frames_t<1>(c, p, s, 0);
+        case QD_FRAMES_SELF: return launch_frames_t<3>(c, p, s, 1);
+        default: return launch_frames_t<6>(c, p, s, 2);
+    }
+}
+
+// uniform batch (also the single-sequence case n_seq = 1) on device buffers
+int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna_dev, size_t n_seq,
+                       size_t seq_len, uint8_t* out_dev, cudaStream_t s, uint64_t key_base = 0) {
+    if (n_seq == 0 || seq_len == 0) return QD_OK;
+    const uint64_t runs = (seq_len + RUN_NT - 1) / RUN_NT;
+    const uint64_t total_runs = runs * n_seq;
+    if (runs > 0xffffffffull || total_runs > 0xffffff00ull) {
+        c->last_error = "batch too large for one launch (more than 2^32 runs)";
+        return QD_ERR_INVALID_ARGUMENT;
+    }
+    FramesParams p{};
+    p.dna = dna_dev;
+    p.total_nt = (uint64_t)n_seq * seq_len;
+    p.offsets = nullptr;
+    p.run_prefix = nullptr;
+    p.tile_first = nullptr;
+    p.n_seq = n_seq;
+    p.uniform_len = seq_len;
+    p.uniform_runs = (uint32_t)runs;
+    p.total_runs = total_runs;
+    p.n_tiles = (uint32_t)((total_runs + TILE_RUNS - 1) / TILE_RUNS);
+    p.out = out_dev;
+    p.lut = c->d_lut + (size_t)slot * CODONS;
+    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    p.err_key = c->d_err;
+    p.key_base = key_base;
+    p.strict = strict;
+    return launch_frames(c, frames, p, s);
+}
+
+template <int MODE>
+int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* dst, DevBuf& block_sums, cudaStream_t s) {
+    const uint64_t n_blocks = std::max<uint64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
+    scan_block_sums_kernel<MODE><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>());
+    scan_spine_kernel<<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks);
+    scan_finish_kernel<MODE><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst);
+    c->launches += 3;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+size_t tiles_upper_bound(uint64_t total_nt, uint64_t n_seq) {
+    const uint64_t runs = total_nt / RUN_NT + n_seq;
+    return (size_t)((runs + TILE_RUNS - 1) / TILE_RUNS);
+}
+
+// variable-length batch on device buffers; offsets_dev are absolute, `flat_base` = offsets[0]
+int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna_dev, uint64_t total_nt,
+                   const uint64_t* offsets_dev, size_t n_seq, DevBuf& run_prefix, DevBuf& tile_first, DevBuf& block_sums,
+                   uint8_t* out_dev, cudaStream_t s, uint64_t flat_base = 0, uint64_t key_base = 0) {
+    if (n_seq == 0) return QD_OK;
+    if (n_seq >= 0xffffffffull || total_nt / RUN_NT + n_seq > 0xffffff00ull) {
+        c->last_error = "batch too large for one launch";
+        return QD_ERR_INVALID_ARGUMENT;
+    }
+    const size_t n_tiles = tiles_upper_bound(total_nt, n_seq);
+    QD_CUDA(c, run_prefix.reserve((n_seq + 1) * sizeof(uint64_t)));
+    QD_CUDA(c, tile_first.reserve((n_tiles + 1) * sizeof(uint32_t)));
+    int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, run_prefix.as<uint64_t>(), block_sums, s);
+    if (rc) return rc;
+    const unsigned g = (unsigned)std::min<uint64_t>((n_seq + 255) / 256, (uint64_t)c->sm_count * 8);
+    tile_first_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), n_seq, tile_first.as<uint32_t>(), n_tiles);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    FramesParams p{};
+    p.dna = dna_dev;
+    p.total_nt = total_nt;
+    p.offsets = offsets_dev;
+    p.run_prefix = run_prefix.as<uint64_t>();
+    p.tile_first = tile_first.as<uint32_t>();
+    p.n_seq = n_seq;
+    p.n_tiles = (uint32_t)n_tiles;
+    p.out = out_dev;
+    p.lut = c->d_lut + (size_t)slot * CODONS;
+    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    p.err_key = c->d_err;
+    p.flat_base = flat_base;
+    p.key_base = key_base;
+    p.strict = strict;
+    return launch_frames(c, frames, p, s);
+}
+
+int revcomp_dev_table(qd_ctx* c, const uint8_t* table_dev, const uint8_t* dna_dev, size_t n, uint8_t* out_dev,
+                      cudaStream_t s) {
+    if (n == 0) return QD_OK;
+    RevcompParams p{dna_dev, (uint64_t)n, out_dev, table_dev, c->d_err};
+    const uint64_t chunks = n >> 4;
+    const uint64_t per_block = (uint64_t)RC_THREADS * RC_UNROLL;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + per_block - 1) / per_block, (uint64_t)c->sm_count * 16));
+    revcomp_kernel<<<grid, RC_THREADS, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+int reset_err_key(qd_ctx* c, cudaStream_t s) {
+    QD_CUDA(c, cudaMemsetAsync(c->d_err, 0xff, sizeof(unsigned long long), s));
+    return QD_OK;
+}
+
+// returns QD_OK and *key (NO_ERROR_KEY when clean); synchronises `s`
+int fetch_err_key(qd_ctx* c, cudaStream_t s, unsigned long long* key) {
+    QD_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    *key = *c->h_err;
+    return QD_OK;
+}
+
+int report_single(int enc, int strict, const uint8_t* dna_host, unsigned long long key, qd_err* err) {
+    uint8_t payload = 0;
+    const int kind = classify_byte(enc, strict, dna_host[key], &payload);
+    return set_err(err, kind == QD_OK ? QD_ERR_BAD_NUCLEOTIDE : kind, payload, key, 0);
+}
+
+}  // namespace
+
+// =================================================================================================
+// context
+// =================================================================================================
+extern "C" int qd_abi_version(void) { return QD_ABI_VERSION; }
+
+extern "C" int qd_ctx_create(qd_ctx** out, int device) {
+    if (!out) return QD_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return QD_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return QD_ERR_CUDA;
+    qd_ctx* c = new qd_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete c;
+        return QD_ERR_CUDA;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    const HostTables& T = host_tables();
+    bool ok = true;
+    ok &= cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < N_PIPE; i++) ok &= cudaStreamCreateWithFlags(&c->pipe[i].stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_lut, T.folded.size() * sizeof(uint16_t)) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_tables, 256 * TAB_COUNT) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
+    ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+    ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
+    if (ok) {
+        std::vector<uint8_t> tabs(256 * TAB_COUNT);
+        auto put = [&](int which, const uint8_t* src) { memcpy(tabs.data() + 256 * which, src, 256); };
+        put(TAB_DECODE_ASCII, T.decode_ascii);
+        put(TAB_DECODE_MASK, T.decode_mask);
+        put(TAB_RC_ASCII, T.rc_ascii[0]);
+        put(TAB_RC_ASCII_STRICT, T.rc_ascii[1]);
+        put(TAB_RC_MASK, T.rc_mask[0]);
+        put(TAB_RC_MASK_STRICT, T.rc_mask[1]);
+        put(TAB_RC_MASK_TO_ASCII, T.rc_mask_to_ascii[0]);
+        put(TAB_RC_MASK_TO_ASCII_STRICT, T.rc_mask_to_ascii[1]);
+        put(TAB_UPPER_ASCII, T.upper_ascii[0]);
+        put(TAB_UPPER_ASCII_STRICT, T.upper_ascii[1]);
+        put(TAB_MASK_TO_ASCII, T.mask_to_ascii[0]);
+        put(TAB_MASK_TO_ASCII_STRICT, T.mask_to_ascii[1]);
+        put(TAB_TO_MASK_ASCII, T.to_mask_ascii);
+        put(TAB_TO_MASK_MASK, T.to_mask_mask);
+        ok &= cudaMemcpy(c->d_tables, tabs.data(), tabs.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(c->d_lut, T.folded.data(), T.folded.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemset(c->d_err, 0xff, sizeof(unsigned long long)) == cudaSuccess;
+    }
+    if (!ok) {
+        qd_ctx_destroy(c);
+        return QD_ERR_CUDA;
+    }
+    *out = c;
+    return QD_OK;
+}
+
+extern "C" void qd_ctx_destroy(qd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&c->in, &c->out, &c->aux0, &c->aux1, &c->aux2, &c->aux3, &c->run_prefix, &c->tile_first, &c->block_sums}) b->release();
+    for (int i = 0; i < N_PIPE; i++) {
+        Pipe& P = c->pipe[i];
+        for (DevBuf* b : {&P.in, &P.out, &P.offsets, &P.run_prefix, &P.tile_first, &P.block_sums}) b->release();
+        if (P.stream) cudaStreamDestroy(P.stream);
+    }
+    if (c->d_lut) cudaFree(c->d_lut);
+    if (c->d_tables) cudaFree(c->d_tables);
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int qd_ctx_device(const qd_ctx* c) { return c ? c->device : -1; }
+extern "C" void* qd_ctx_stream(const qd_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int qd_ctx_sm_count(const qd_ctx* c) { return c ? c->sm_count : 0; }
+extern "C" const char* qd_last_cuda_error(const qd_ctx* c) { return c ? c->last_error.c_str() : "no context"; }
+extern "C" uint64_t qd_launch_count(const qd_ctx* c) { return c ? c->launches : 0; }
+extern "C" int qd_ctx_set_chunk_bytes(qd_ctx* c, size_t bytes) {
+    if (!c || bytes < (size_t(1) << 16)) return QD_ERR_INVALID_ARGUMENT;
+    c->chunk_bytes = bytes;
+    return QD_OK;
+}
+
+// =================================================================================================
+// host-only helpers
+// =================================================================================================
+extern "C" int qd_table_slot(int id) {
+    if (id == 8) return 0;  // alias of 1, src/trans_table.rs:118
+    if (id == 7) return 3;  // alias of 4, src/trans_table.rs:122
+    for (int s = 0; s < N_SLOTS; s++)
+        if (SLOT_NCBI_ID[s] == id) return s;
+    return -1;
+}
+
+extern "C" const uint8_t* qd_table_data(int slot) {
+    if (slot < 0 || slot >= N_SLOTS) return nullptr;
+    return host_tables().ref.data() + (size_t)slot * CODONS;
+}
+
+static int fmt_char_debug(uint8_t ch, char* buf, size_t cap) {  // Rust `{:?}` of an ASCII char
+    switch (ch) {
+        case 0: return snprintf(buf, cap, "'\\0'");
+        case 9: return snprintf(buf, cap, "'\\t'");
+        case 10: return snprintf(buf, cap, "'\\n'");
+        case 13: return snprintf(buf, cap, "'\\r'");
+        case 39: return snprintf(buf, cap, "'\\''");
+        case 92: return snprintf(buf, cap, "'\\\\'");
+        default: break;
+    }
+    if (ch < 32 || ch == 127) return snprintf(buf, cap, "'\\u{%x}'", (unsigned)ch);
+    return snprintf(buf, cap, "'%c'", (char)ch);
+}
+
+extern "C" int qd_err_message(const qd_err* e, char* buf, size_t cap) {
+    if (!e || !buf || !cap) return 0;
+    char q[16];
+    switch (e->kind) {
+        case QD_OK: return snprintf(buf, cap, "ok");
+        case QD_ERR_NON_ASCII_BYTE: return snprintf(buf, cap, "non-ascii byte: %x", (unsigned)e->byte);
+        case QD_ERR_BAD_NUCLEOTIDE:
+            fmt_char_debug(e->byte, q, sizeof q);
+            return snprintf(buf, cap, "bad nucleotide: %s", q);
+        case QD_ERR_UNEXPECTED_AMBIGUOUS:
+            fmt_char_debug(e->byte, q, sizeof q);
+            return snprintf(buf, cap, "unexpected ambiguous nucleotide: %s", q);
+        case QD_ERR_BAD_TABLE: return snprintf(buf, cap, "not a ncbi translation table: %u", (unsigned)e->byte);
+        case QD_ERR_BAD_MASK: return snprintf(buf, cap, "not a nucleotide mask: %u", (unsigned)e->byte);
+        case QD_ERR_INVALID_ARGUMENT: return snprintf(buf, cap, "invalid argument");
+        default: return snprintf(buf, cap, "cuda error");
+    }
+}
+
+extern "C" size_t qd_frame_len(size_t n, int k) { return (k >= 0 && k < 3 && n > (size_t)k) ? (n - k) / 3 : 0; }
+extern "C" size_t qd_runs(size_t n) { return (n + RUN_NT - 1) / RUN_NT; }
+extern "C" size_t qd_slots_bytes(size_t n, int frames) { return 16 * qd_runs(n) * (size_t)frames; }
+extern "C" size_t qd_slot_frame_offset(size_t n, int frames, int f) {
+    const size_t slot = 16 * qd_runs(n);
+    if (f < 3 || frames != QD_FRAMES_ALL) return (size_t)f * slot;
+    return (size_t)(f + 1) * slot - qd_frame_len(n, f - 3);
+}
+
+extern "C" size_t qd_batch_out_bytes(const uint64_t* offsets, size_t n_seq, int frames) {
+    size_t runs = 0;
+    for (size_t i = 0; i < n_seq; i++) runs += qd_runs((size_t)(offsets[i + 1] - offsets[i]));
+    return runs * 16 * (size_t)frames;
+}
+
+// =================================================================================================
+// device-pointer entry points
+// =================================================================================================
+static cudaStream_t pick_stream(qd_ctx* c, void* s) { return s ? (cudaStream_t)s : c->stream; }
+
+extern "C" int qd_dev_error_reset(qd_ctx* c, void* stream) {
+    if (!c) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return reset_err_key(c, pick_stream(c, stream));
+}
+
+extern "C" int qd_dev_error_fetch(qd_ctx* c, void* stream, int enc, int strict, const uint8_t* dna_dev,
+                                  const uint64_t* offsets_dev, size_t n_seq, size_t uniform_len, qd_err* err) {
+    if (!c) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    clear_err(err);
+    cudaStream_t s = pick_stream(c, stream);
+    unsigned long long key = 0;
+    int rc = fetch_err_key(c, s, &key);
+    if (rc) return rc;
+    if (key == NO_ERROR_KEY) return QD_OK;
+    uint8_t b = 0;
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, dna_dev + key, 1, cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    b = *reinterpret_cast<uint8_t*>(c->h_scratch);
+    uint64_t seq = 0, pos = key;
+    if (offsets_dev && n_seq) {
+        // upper_bound over the device offsets by bisection with single-element copies (error path only)
+        uint64_t lo = 0, hi = n_seq - 1;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi + 1) >> 1, v = 0;
+            QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, offsets_dev + mid, 8, cudaMemcpyDeviceToHost, s));
+            QD_CUDA(c, cudaStreamSynchronize(s));
+            v = c->h_scratch[0];
+            if (v <= key) lo = mid; else hi = mid - 1;
+        }
+        QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, offsets_dev + lo, 8, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        seq = lo;
+        pos = key - c->h_scratch[0];
+    } else if (uniform_len) {
+        seq = key / uniform_len;
+        pos = key % uniform_len;
+    }
+    uint8_t payload = 0;
+    int kind = classify_byte(enc, strict, b, &payload);
+    if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+    return set_err(err, kind, payload, pos, seq);
+}
+
+extern "C" int qd_revcomp_dev(qd_ctx* c, int enc, int strict, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, void* stream) {
+    if (!c || (n && (!dna_dev || !out_dev)) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    const int which = enc == QD_ENC_ASCII ? (strict ? TAB_RC_ASCII_STRICT : TAB_RC_ASCII) : (strict ? TAB_RC_MASK_STRICT : TAB_RC_MASK);
+    return revcomp_dev_table(c, tab(c, which), dna_dev, n, out_dev, pick_stream(c, stream));
+}
+
+extern "C" int qd_translate_frames_dev(qd_ctx* c, int table, int enc, int strict, int frames, const uint8_t* dna_dev, size_t n,
+                                       uint8_t* out_dev, void* stream) {
+    return qd_translate_frames_batch_uniform_dev(c, table, enc, strict, frames, dna_dev, n ? 1 : 0, n, out_dev, stream);
+}
+
+extern "C" int qd_translate_frames_batch_uniform_dev(qd_ctx* c, int table, int enc, int strict, int frames, const uint8_t* dna_dev,
+                                                     size_t n_seq, size_t seq_len, uint8_t* out_dev, void* stream) {
+    if (!c || !valid_frames(frames) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (check_table(table, nullptr, &slot)) return QD_ERR_BAD_TABLE;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return frames_uniform_dev(c, slot, enc, strict, frames, dna_dev, n_seq, seq_len, out_dev, pick_stream(c, stream));
+}
+
+extern "C" int qd_translate_frames_batch_dev(qd_ctx* c, int table, int enc, int strict, int frames, const uint8_t* dna_dev,
+                                             const uint64_t* offsets_dev, size_t n_seq, size_t total_nt, uint8_t* out_dev,
+                                             void* stream) {
+    if (!c || !valid_frames(frames) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (check_table(table, nullptr, &slot)) return QD_ERR_BAD_TABLE;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return frames_csr_dev(c, slot, enc, strict, frames, dna_dev, total_nt, offsets_dev, n_seq, c->run_prefix, c->tile_first,
+                          c->block_sums, out_dev, pick_stream(c, stream));
+}
+
+static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, size_t w, uint8_t* out_dev,
+                         cudaStream_t s) {
+    if (w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
+    if (n < w) return QD_OK;
+    CanonParams p{};
+    p.dna = dna_dev;
+    p.n = n;
+    p.w = (uint32_t)w;
+    p.forward_only = forward_only;
+    p.out = out_dev;
+    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
+    p.err_key = c->d_err;
+    const size_t smem = ((CANON_THREADS + CANON_MAX_W + 15) & ~15) + 16 + (size_t)CANON_THREADS * w;
+    const uint64_t blocks = ((n - w + 1) + CANON_THREADS - 1) / CANON_THREADS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 16);
+    canonical_windows_kernel<<<grid, CANON_THREADS, smem, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_canonical_windows_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, size_t w,
+                                        uint8_t* out_dev, void* stream) {
+    if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return canonical_dev(c, enc, forward_only, dna_dev, n, w, out_dev, pick_stream(c, stream));
+}
+
+static int windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, uint8_t* out_dev, cudaStream_t s) {
+    if (w == 0 || w > 0xffffffffull) return QD_ERR_INVALID_ARGUMENT;
+    if (n < w) return QD_OK;
+    const uint64_t n_windows = n - w + 1;
+    const uint64_t chunks = (n_windows * w + 15) >> 4;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + 255) / 256, (uint64_t)c->sm_count * 16));
+    windows_kernel<<<grid, 256, 0, s>>>(seq_dev, n_windows, (uint32_t)w, out_dev);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, uint8_t* out_dev, void* stream) {
+    if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return windows_dev(c, seq_dev, n, w, out_dev, pick_stream(c, stream));
+}
+
+// =================================================================================================
+// host-pointer entry points
+// =================================================================================================
+extern "C" int qd_translate(qd_ctx* c, int table, int enc, int strict, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
+    size_t lens[6];
+    int nf = 0;
+    if (!c) return QD_ERR_INVALID_ARGUMENT;
+    // same path as the frames entry point with one frame; the reference returns an empty Vec for n < 3
+    return qd_translate_frames(c, table, enc, strict, QD_FRAMES_ONE, dna, n, out, lens, &nf, err);
+}
+
+extern "C" int qd_translate_frames(qd_ctx* c, int table, int enc, int strict, int frames, const uint8_t* dna, size_t n, uint8_t* out,
+                                   size_t out_len[6], int* n_frames, qd_err* err) {
+    clear_err(err);
+    if (!c || !valid_frames(frames) || (n && !dna)) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (int rc = check_table(table, err, &slot)) return rc;  // table first: src/python_api.rs:35,48
+    for (int k = 0; k < 6; k++)
+        if (out_len) out_len[k] = 0;
+    if (n_frames) *n_frames = 0;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(qd_slots_bytes(n, frames)));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    if (int rc = frames_uniform_dev(c, slot, enc, strict, frames, c->in.as<uint8_t>(), 1, n, c->out.as<uint8_t>(), s)) return rc;
+    // gather the frames tightly: f0|f1|f2[|r0|r1|r2]
+    size_t off = 0;
+    int nf = 0;
+    const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
+    for (int f = 0; f < n_slots; f++) {
+        const size_t len = qd_frame_len(n, f % 3);
+        if (out_len) out_len[f] = len;
+        if (len) {
+            QD_CUDA(c, cudaMemcpyAsync(out + off, c->out.as<uint8_t>() + qd_slot_frame_offset(n, frames, f), len, cudaMemcpyDeviceToHost, s));
+            off += len;
+            nf++;
+        }
+    }
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;
+    if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+    if (n_frames) *n_frames = nf;
+    return QD_OK;
+}
+
+extern "C" int qd_revcomp(qd_ctx* c, int enc, int strict, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
+    clear_err(err);
+    if (!c || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(n + 16));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    const int which = enc == QD_ENC_ASCII ? (strict ? TAB_RC_ASCII_STRICT : TAB_RC_ASCII) : (strict ? TAB_RC_MASK_STRICT : TAB_RC_MASK);
+    if (int rc = revcomp_dev_table(c, tab(c, which), c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, n, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;
+    if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+    return QD_OK;
+}
+
+// chunked H2D -> kernel -> D2H pipeline over whole sequences, N_PIPE streams deep
+static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna, const uint64_t* offsets,
+                          size_t n_seq, size_t uniform_len, uint8_t* out, uint64_t* out_offsets, qd_err* err) {
+    const bool uniform = offsets == nullptr;
+    const uint64_t total_nt = uniform ? (uint64_t)n_seq * uniform_len : offsets[n_seq] - offsets[0];
+    if (n_seq == 0) return QD_OK;
+    const uint64_t stride = 16 * (uint64_t)frames;
+    // out_offsets (host) for the CSR form: 16*frames*prefix(runs)
+    std::vector<uint64_t> own_offsets;
+    const uint64_t* oo = out_offsets;
+    if (!uniform) {
+        if (!out_offsets) {
+            own_offsets.resize(n_seq + 1);
+            out_offsets = own_offsets.data();
+        }
+        uint64_t acc = 0;
+        for (size_t i = 0; i < n_seq; i++) {
+            out_offsets[i] = acc;
+            acc += stride * qd_runs((size_t)(offsets[i + 1] - offsets[i]));
+        }
+        out_offsets[n_seq] = acc;
+        oo = out_offsets;
+    }
+    for (int i = 0; i < N_PIPE; i++) QD_CUDA(c, cudaStreamSynchronize(c->pipe[i].stream));
+    if (int rc = reset_err_key(c, c->stream)) return rc;
+    QD_CUDA(c, cudaStreamSynchronize(c->stream));
+
+    size_t r0 = 0;
+    int turn = 0;
+    const uint64_t uni_out = uniform ? stride * qd_runs(uniform_len) : 0;
+    while (r0 < n_seq) {
+        // pick [r0, r1): whole sequences, about chunk_bytes of input (at least one sequence)
+        size_t r1;
+        if (uniform) {
+            const size_t per = std::max<size_t>(1, uniform_len ? c->chunk_bytes / uniform_len : n_seq);
+            r1 = std::min(n_seq, r0 + per);
+        } else {
+            const uint64_t target = offsets[r0] + c->chunk_bytes;
+            r1 = (size_t)(std::upper_bound(offsets + r0 + 1, offsets + n_seq + 1, target) - offsets) - 1;
+            r1 = std::min(n_seq, std::max(r1, r0 + 1));
+        }
+        const size_t cnt = r1 - r0;
+        const uint64_t in0 = uniform ? (uint64_t)r0 * uniform_len : offsets[r0];
+        const uint64_t in_bytes = uniform ? (uint64_t)cnt * uniform_len : offsets[r1] - offsets[r0];
+        const uint64_t out0 = uniform ? (uint64_t)r0 * uni_out : oo[r0];
+        const uint64_t out_bytes = uniform ? (uint64_t)cnt * uni_out : oo[r1] - oo[r0];
+        Pipe& P = c->pipe[turn % N_PIPE];
+        turn++;
+        cudaStream_t s = P.stream;
+        if (in_bytes > P.in.cap || out_bytes > P.out.cap) QD_CUDA(c, cudaStreamSynchronize(s));  // about to reallocate
+        QD_CUDA(c, P.in.reserve(in_bytes + 16));
+        QD_CUDA(c, P.out.reserve(out_bytes + 16));
+        if (in_bytes) QD_CUDA(c, cudaMemcpyAsync(P.in.p, dna + (uniform ? in0 : in0 - offsets[0]), in_bytes, cudaMemcpyHostToDevice, s));
+        int rc;
+        if (uniform) {
+            rc = frames_uniform_dev(c, slot, enc, strict, frames, P.in.as<uint8_t>(), cnt, uniform_len, P.out.as<uint8_t>(), s, in0);
+        } else {
+            if ((cnt + 1) * 8 > P.offsets.cap) QD_CUDA(c, cudaStreamSynchronize(s));
+            QD_CUDA(c, P.offsets.reserve((cnt + 1) * sizeof(uint64_t)));
+            QD_CUDA(c, cudaMemcpyAsync(P.offsets.p, offsets + r0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+            // the chunk's device buffer starts at the sequence whose offset is in0
+            rc = frames_csr_dev(c, slot, enc, strict, frames, P.in.as<uint8_t>(), in_bytes, P.offsets.as<uint64_t>(), cnt, P.run_prefix,
+                                P.tile_first, P.block_sums, P.out.as<uint8_t>(), s, in0, in0 - offsets[0]);
+        }
+        if (rc) return rc;
+        if (out_bytes) QD_CUDA(c, cudaMemcpyAsync(out + out0, P.out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+        r0 = r1;
+    }
+    for (int i = 0; i < N_PIPE; i++) QD_CUDA(c, cudaStreamSynchronize(c->pipe[i].stream));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, c->stream, &key)) return rc;
+    if (key != NO_ERROR_KEY) {
+        uint64_t seq, pos;
+        if (uniform) {
+            seq = key / uniform_len;
+            pos = key % uniform_len;
+        } else {
+            seq = (uint64_t)(std::upper_bound(offsets, offsets + n_seq + 1, (uint64_t)key + offsets[0]) - offsets) - 1;
+            pos = key + offsets[0] - offsets[seq];
+        }
+        uint8_t payload = 0;
+        int kind = classify_byte(enc, strict, dna[key], &payload);
+        if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+        return set_err(err, kind, payload, pos, seq);
+    }
+    (void)total_nt;
+    return QD_OK;
+}
+
+extern "C" int qd_translate_frames_batch(qd_ctx* c, int table, int enc, int strict, int frames, const uint8_t* dna,
+                                         const uint64_t* offsets, size_t n_seq, uint8_t* out, uint64_t* out_offsets, qd_err* err) {
+    clear_err(err);
+    if (!c || !valid_frames(frames) || !offsets) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (int rc = check_table(table, err, &slot)) return rc;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return batch_pipeline(c, slot, enc, strict, frames, dna, offsets, n_seq, 0, out, out_offsets, err);
+}
+
+extern "C" int qd_translate_frames_batch_uniform(qd_ctx* c, int table, int enc, int strict, int frames, const uint8_t* dna,
+                                                 size_t n_seq, size_t seq_len, uint8_t* out, qd_err* err) {
+    clear_err(err);
+    if (!c || !valid_frames(frames)) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (int rc = check_table(table, err, &slot)) return rc;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (seq_len == 0) return QD_OK;
+    return batch_pipeline(c, slot, enc, strict, frames, dna, nullptr, n_seq, seq_len, out, nullptr, err);
+}
+
+extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const uint8_t* dna, size_t n, size_t w, uint8_t* out,
+                                    qd_err* err) {
+    clear_err(err);
+    if (!c || w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n < w) return QD_OK;
+    cudaStream_t s = c->stream;
+    const size_t out_bytes = (n - w + 1) * w;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(out_bytes + 16));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    if (int rc = canonical_dev(c, enc, forward_only, c->in.as<uint8_t>(), n, w, c->out.as<uint8_t>(), s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;
+    if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+    return QD_OK;
+}
+
+extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, size_t n_win, size_t w, uint64_t max_expansions,
+                                    uint64_t* counts, uint64_t* out_index, uint8_t* out, qd_err* err) {
+    clear_err(err);
+    if (!c || w < 1 || w > 64) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n_win == 0) {
+        if (out_index) out_index[0] = 0;
+        return QD_OK;
+    }
+    cudaStream_t s = c->stream;
+    const size_t in_bytes = n_win * w;
+    QD_CUDA(c, c->in.reserve(in_bytes + 16));
+    QD_CUDA(c, c->aux0.reserve(n_win * 8));        // counts
+    QD_CUDA(c, c->aux1.reserve(n_win * 8));        // emit
+    QD_CUDA(c, c->aux2.reserve((n_win + 1) * 8));  // out_index
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, windows, in_bytes, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    ExpandParams p{};
+    p.windows = c->in.as<uint8_t>();
+    p.n_win = n_win;
+    p.w = (uint32_t)w;
+    p.max_expansions = max_expansions;
+    p.to_mask = tab(c, enc == QD_ENC_ASCII ? TAB_TO_MASK_ASCII : TAB_TO_MASK_MASK);
+    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
+    p.counts = c->aux0.as<uint64_t>();
+    p.emit = c->aux1.as<uint64_t>();
+    p.out_index = c->aux2.as<uint64_t>();
+    p.err_key = c->d_err;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_win + 255) / 256, (uint64_t)c->sm_count * 16);
+    expansion_count_kernel<<<grid, 256, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    if (int rc = device_exclusive_scan<1>(c, c->aux1.as<uint64_t>(), n_win, c->aux2.as<uint64_t>(), c->block_sums, s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->aux2.as<uint64_t>() + n_win, 8, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
+    if (key != NO_ERROR_KEY) {
+        uint8_t payload = 0;
+        int kind = classify_byte(enc, 0, windows[key], &payload);
+        if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+        return set_err(err, kind, payload, key % w, key / w);
+    }
+    const uint64_t total_rows = c->h_scratch[0];
+    std::vector<uint64_t> own_counts;
+    if (!counts) {
+        own_counts.resize(n_win);
+        counts = own_counts.data();
+    }
+    QD_CUDA(c, cudaMemcpyAsync(counts, c->aux0.p, n_win * 8, cudaMemcpyDeviceToHost, s));
+    if (out_index) QD_CUDA(c, cudaMemcpyAsync(out_index, c->aux2.p, (n_win + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (out && total_rows) {
+        QD_CUDA(c, c->out.reserve(total_rows * w + 16));
+        p.out = c->out.as<uint8_t>();
+        const unsigned g2 = (unsigned)std::min<uint64_t>((total_rows + 255) / 256, (uint64_t)c->sm_count * 16);
+        expansion_write_kernel<<<g2, 256, 0, s>>>(p, total_rows);
+        c->launches++;
+        QD_CUDA(c, cudaGetLastError());
+        QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, total_rows * w, cudaMemcpyDeviceToHost, s));
+    }
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    if (out_index) {
+        // skipped windows are marked, as the header documents
+        // (their device-side index equals the next window's; the mark is host-side only)
+        for (size_t i = 0; i < n_win; i++)
+            if (counts[i] > max_expansions) out_index[i] = ~0ull;
+    }
+    return QD_OK;
+}
+
+extern "C" int qd_windows(qd_ctx* c, const uint8_t* seq, size_t n, size_t w, uint8_t* out, size_t* n_windows) {
+    if (n_windows) *n_windows = 0;
+    if (!c || w == 0) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n < w) return QD_OK;
+    cudaStream_t s = c->stream;
+    const size_t count = n - w + 1;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(count * w + 16));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, seq, n, cudaMemcpyHostToDevice, s));
+    if (int rc = windows_dev(c, c->in.as<uint8_t>(), n, w, c->out.as<uint8_t>(), s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, count * w, cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    if (n_windows) *n_windows = count;
+    return QD_OK;
+}
+
+extern "C" int qd_windows_all(qd_ctx* c, int enc, const uint8_t* dna, size_t n, size_t w_dna, size_t w_aa, uint8_t* dna_out,
+                              uint8_t* aa_out, uint64_t* origin, size_t counts[8], qd_err* err) {
+    clear_err(err);
+    if (!c || !counts || w_dna == 0 || w_aa == 0) return QD_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < 8; i++) counts[i] = 0;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    auto nwin = [](size_t len, size_t w) { return len + 1 - std::min(w, len + 1); };  // benches/all_windows.rs:209-211
+    const size_t n_dna = nwin(n, w_dna);
+    counts[0] = counts[1] = n_dna;
+    // frames the reference returns, in list order (`operation` = list index, benches/all_windows.rs:52-72)
+    size_t list_len[6];
+    int list_frame[6];
+    int n_list = 0;
+    for (int f = 0; f < 6; f++)
+        if (qd_frame_len(n, f % 3)) {
+            list_len[n_list] = qd_frame_len(n, f % 3);
+            list_frame[n_list] = f;
+            n_list++;
+        }
+    size_t n_aa = 0;
+    for (int op = 0; op < n_list; op++) {
+        counts[2 + op] = nwin(list_len[op], w_aa);
+        n_aa += counts[2 + op];
+    }
+    const size_t total = 2 * n_dna + n_aa;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->aux0.reserve(n + 16));                       // forward ASCII
+    QD_CUDA(c, c->aux1.reserve(n + 16));                       // reverse-complement ASCII
+    QD_CUDA(c, c->aux2.reserve(qd_slots_bytes(n, 6) + 16));    // six frames
+    QD_CUDA(c, c->out.reserve(std::max(2 * n_dna * w_dna, n_aa * w_aa) + 16));
+    QD_CUDA(c, c->aux3.reserve(total * 8 + 16));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    // strict alphabet (DnaSequence<Nucleotide>): the strict tables reject everything else
+    const uint8_t* t_rc = tab(c, enc == QD_ENC_ASCII ? TAB_RC_ASCII_STRICT : TAB_RC_MASK_TO_ASCII_STRICT);
+    if (int rc = revcomp_dev_table(c, t_rc, c->in.as<uint8_t>(), n, c->aux1.as<uint8_t>(), s)) return rc;
+    // forward ASCII (upper case) = reverse complement of the reverse complement
+    if (int rc = revcomp_dev_table(c, tab(c, TAB_RC_ASCII_STRICT), c->aux1.as<uint8_t>(), n, c->aux0.as<uint8_t>(), s)) return rc;
+    if (int rc = frames_uniform_dev(c, 0 /* Ncbi1 */, enc, 1, QD_FRAMES_ALL, c->in.as<uint8_t>(), 1, n, c->aux2.as<uint8_t>(), s)) return rc;
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;
+    if (key != NO_ERROR_KEY) return report_single(enc, 1, dna, key, err);
+    if (dna_out && n_dna) {
+        // the two DNA segments are written to separately aligned buffers, then copied out back to back
+        if (int rc = windows_dev(c, c->aux0.as<uint8_t>(), n, w_dna, c->out.as<uint8_t>(), s)) return rc;
+        QD_CUDA(c, cudaMemcpyAsync(dna_out, c->out.p, n_dna * w_dna, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        if (int rc = windows_dev(c, c->aux1.as<uint8_t>(), n, w_dna, c->out.as<uint8_t>(), s)) return rc;
+        QD_CUDA(c, cudaMemcpyAsync(dna_out + n_dna * w_dna, c->out.p, n_dna * w_dna, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+    }
+    if (aa_out) {
+        size_t written = 0;
+        for (int op = 0; op < n_list; op++) {
+            if (!counts[2 + op]) continue;
+            const uint8_t* frame = c->aux2.as<uint8_t>() + qd_slot_frame_offset(n, 6, list_frame[op]);
+            if (int rc = windows_dev(c, frame, list_len[op], w_aa, c->out.as<uint8_t>(), s)) return rc;
+            QD_CUDA(c, cudaMemcpyAsync(aa_out + written * w_aa, c->out.p, counts[2 + op] * w_aa, cudaMemcpyDeviceToHost, s));
+            QD_CUDA(c, cudaStreamSynchronize(s));
+            written += counts[2 + op];
+        }
+    }
+    if (origin && total) {
+        uint64_t* o = c->aux3.as<uint64_t>();
+        size_t at = 0;
+        auto fill = [&](size_t count, int kind, uint64_t f) {
+            if (!count) return;
+            const unsigned grid = (unsigned)std::min<uint64_t>((count + 255) / 256, (uint64_t)c->sm_count * 8);
+            origin_kernel<<<grid, 256, 0, s>>>(o + at, count, kind, f, (uint64_t)n, (uint64_t)w_aa);
+            c->launches++;
+            at += count;
+        };
+        fill(n_dna, 0, 0);
+        fill(n_dna, 1, 0);
+        for (int op = 0; op < n_list; op++) fill(counts[2 + op], op <= 2 ? 2 : 3, (uint64_t)(op % 3));
+        QD_CUDA(c, cudaGetLastError());
+        QD_CUDA(c, cudaMemcpyAsync(origin, o, total * 8, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+    }
+    return QD_OK;
+}

@@ -1,0 +1,513 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: -m gpu.
+
+Bit-exact bar: every output byte, every frame count, every error (kind, byte, position).
+"""
+
+import ctypes as C
+import hashlib
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import vectors as V
+
+pytestmark = pytest.mark.gpu
+
+IUPAC = b"ACGTacgtWMRYSKBVDHNwmryskbvdhn"
+
+
+@pytest.fixture(scope="module")
+def qd():
+    import quickdna_b200
+
+    return quickdna_b200
+
+
+@pytest.fixture(scope="module")
+def N():
+    from quickdna_b200 import _native
+
+    return _native
+
+
+@pytest.fixture(scope="module")
+def B():
+    from quickdna_b200 import batch
+
+    return batch
+
+
+def _rand(rng, n, alphabet=b"ACGT"):
+    return bytes(np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)])
+
+
+# ------------------------------------------------------------------ golden vectors, Python surface
+
+
+@pytest.mark.parametrize("table,dna,protein", V.TRANSLATE)
+def test_translate_vectors(qd, table, dna, protein):
+    assert qd.DnaSequence(dna).translate(table=table) == qd.ProteinSequence(protein)
+    if all(c in "ACGTacgt" for c in dna):
+        assert qd.DnaSequence(dna).translate(table=table, strict=True) == qd.ProteinSequence(protein)
+
+
+@pytest.mark.parametrize("dna,frames", V.SELF_FRAMES)
+def test_self_frames_vectors(qd, dna, frames):
+    want = [qd.ProteinSequence(f) for f in frames]
+    assert qd.DnaSequence(dna).translate_self_frames(table=1) == want
+    assert qd.DnaSequence(dna).translate_self_frames(table=1, strict=True) == want
+
+
+@pytest.mark.parametrize("dna,frames", V.ALL_FRAMES)
+def test_all_frames_vectors(qd, dna, frames):
+    want = [qd.ProteinSequence(f) for f in frames]
+    assert qd.DnaSequence(dna).translate_all_frames(table=1) == want
+    assert qd.DnaSequence(dna).translate_all_frames(table=1, strict=True) == want
+
+
+@pytest.mark.parametrize("dna,rc", V.REVCOMP)
+def test_revcomp_vectors(qd, dna, rc):
+    assert qd.DnaSequence(dna).reverse_complement() == qd.DnaSequence(rc)
+
+
+def test_wrapper_behaviour_like_reference(qd):
+    # tests/test_wrapper.py of the reference, restated
+    D, P = qd.DnaSequence, qd.ProteinSequence
+    assert D("aaa") == D("aaa") and D("aaa") != P("aaa") and hash(D("aaa")) != hash(P("aaa"))
+    d = D("aaa")
+    assert d[1] == ord("a") and d[:] == D("aaa") and d[1:] == D("aa") and d[1:] != P("aa")
+    assert len(D("a" * 20)) == 20
+    assert D("at") + D("cg") == D("atcg") and P("KG") + P("GK") == P("KGGK")
+    with pytest.raises(TypeError):
+        D("at") + P("KG")
+    assert D("a") * 20 == D("a" * 20)
+    assert list(D("atcg" * 20)) == list("atcg" * 20)
+    with pytest.raises(ValueError):
+        D("AAABBBGGG").reverse_complement(strict=True)
+    assert D("AAAGGGAAA").translate(table=1, strict=True) == P("KGK")
+    with pytest.raises(ValueError):
+        D("AAABBBAAA").translate(table=1, strict=True)
+    assert repr(D("A" * 40)) == "DnaSequence(seq='" + "A" * 30 + "...')"
+
+
+@pytest.mark.parametrize("fn,dna,kind,byte,msg", V.ERRORS)
+def test_error_vectors(qd, fn, dna, kind, byte, msg):
+    from quickdna_b200 import quickdna as native
+
+    raw = dna.encode("latin-1")
+    call = {
+        "translate": lambda: native._translate(1, raw),
+        "translate_strict": lambda: native._translate_strict(1, raw),
+        "revcomp": lambda: native._reverse_complement(raw),
+        "revcomp_strict": lambda: native._reverse_complement_strict(raw),
+    }[fn]
+    with pytest.raises(ValueError) as ei:
+        call()
+    assert (ei.value.kind, ei.value.byte, str(ei.value)) == (kind, byte, msg)
+    # and the oracle agrees on the position
+    ocall = {
+        "translate": lambda: oracle.translate_bytes(1, raw),
+        "translate_strict": lambda: oracle.translate_bytes(1, raw, strict=True),
+        "revcomp": lambda: oracle.revcomp_bytes(raw),
+        "revcomp_strict": lambda: oracle.revcomp_bytes(raw, strict=True),
+    }[fn]
+    with pytest.raises(oracle.OracleError) as oi:
+        ocall()
+    assert ei.value.pos == oi.value.pos
+
+
+def test_table_errors(qd):
+    from quickdna_b200 import quickdna as native
+
+    with pytest.raises(ValueError) as ei:
+        native._translate(17, b"QQQ")  # table is checked before the DNA
+    assert str(ei.value) == V.BAD_TABLE_MESSAGE
+    for t in (0, 17, 18, 19, 20, 34, 200):
+        with pytest.raises(ValueError):
+            native._check_table(t)
+        with pytest.raises(ValueError):
+            native._translate_strict(t, b"")
+    for t in V.ALL_ACCEPTED_TABLES:
+        native._check_table(t)
+
+
+def test_all_frames_short_input_quirk(qd):
+    # quickdna/__init__.py:182: len < 3 still validates through the NON-strict reverse complement
+    with pytest.raises(ValueError):
+        qd.DnaSequence("Q").translate_all_frames()
+    assert qd.DnaSequence("NN").translate_all_frames(strict=True) == []
+    assert qd.DnaSequence("QQ").translate_self_frames() == []
+
+
+# ------------------------------------------------------------------ exhaustive / random parity
+
+
+def test_exhaustive_codons_all_tables(qd):
+    # tests/test_exhaustive.py shape, against the oracle (whose LUT is sha-pinned to tables.dat)
+    letters = "ATCGWMRYSKBVDHN"
+    dna = "".join(a + b + c for a, b, c in itertools.product(letters, repeat=3))
+    for table in V.ALL_ACCEPTED_TABLES:
+        got = qd.DnaSequence(dna).translate(table=table).seq
+        assert got == oracle.translate_bytes(table, dna), table
+        assert qd.DnaSequence(dna.lower()).translate(table=table).seq == got
+
+
+def test_device_lut_image_matches_tables_dat(N):
+    img = C.string_at(N.lib().qd_table_data(0), 27 * 4096)
+    assert hashlib.sha256(img).hexdigest() == V.TABLES_DAT_SHA256
+    assert img == oracle.tables()
+
+
+def test_every_length_0_to_400(qd):
+    rng = np.random.default_rng(1)
+    for n in range(0, 401):
+        dna = _rand(rng, n, IUPAC)
+        d = qd.DnaSequence(dna)
+        assert d.translate(table=1 + n % 6).seq == oracle.translate_bytes(1 + n % 6, dna), n
+        assert d.reverse_complement().seq == oracle.revcomp_bytes(dna), n
+        assert [f.seq for f in d.translate_all_frames(table=11)] == oracle.py_all_frames(11, dna), n
+        assert [f.seq for f in d.translate_self_frames(table=2)] == oracle.py_self_frames(2, dna), n
+
+
+def test_revcomp_alignments_and_sizes(N):
+    # every (source misalignment, length mod 16) combination of the shifted-granule path
+    rng = np.random.default_rng(2)
+    ctx = N.default_context()
+    L = N.lib()
+    base = np.frombuffer(_rand(rng, 5000, IUPAC), dtype=np.uint8)
+    for n in list(range(0, 70)) + [255, 256, 257, 1023, 4095, 4096, 4097, 4999]:
+        for shift in (0, 1, 3, 7, 8, 15):
+            src = base[shift:shift + n].copy()  # host alignment does not matter; device copy is aligned
+            out = np.empty(max(n, 1), dtype=np.uint8)
+            err = N.QdErr()
+            rc = L.qd_revcomp(ctx.handle, 0, 0, src.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), C.byref(err))
+            assert rc == 0
+            assert out[:n].tobytes() == oracle.revcomp_bytes(src.tobytes())
+
+
+def test_mask_encoding(N):
+    # typed Rust API: &[Nucleotide] / &[NucleotideAmbiguous] reinterpreted as bytes
+    rng = np.random.default_rng(3)
+    ctx = N.default_context()
+    L = N.lib()
+    for n in (0, 1, 2, 3, 4, 5, 47, 48, 49, 50, 51, 95, 96, 97, 1000, 5003):
+        for ambiguous in (False, True):
+            m = (rng.integers(1, 16, n) if ambiguous else np.array([1, 2, 4, 8])[rng.integers(0, 4, n)]).astype(np.uint8)
+            src = m if n else np.zeros(1, np.uint8)
+            out = np.zeros(2 * n + 16, dtype=np.uint8)
+            lens = (C.c_size_t * 6)()
+            nf = C.c_int()
+            err = N.QdErr()
+            rc = L.qd_translate_frames(ctx.handle, 1, 1, int(not ambiguous), 6, src.ctypes.data_as(C.c_void_p), n,
+                                       out.ctypes.data_as(C.c_void_p), lens, C.byref(nf), C.byref(err))
+            assert rc == 0, (n, ambiguous, err.kind, err.pos)
+            want = oracle.all_frames_masks(0, m)
+            got, off = [], 0
+            for ln in lens:
+                if ln:
+                    got.append(out[off:off + ln].tobytes())
+                off += ln
+            assert got == want and nf.value == len(want)
+            rcout = np.zeros(max(n, 1), dtype=np.uint8)
+            rc = L.qd_revcomp(ctx.handle, 1, int(not ambiguous), src.ctypes.data_as(C.c_void_p), n,
+                              rcout.ctypes.data_as(C.c_void_p), C.byref(err))
+            assert rc == 0
+            assert (rcout[:n] == oracle.revcomp_masks(m)).all()
+    # invalid mask bytes and strictness
+    bad = np.array([1, 2, 0, 4], dtype=np.uint8)
+    err = N.QdErr()
+    out = np.zeros(16, dtype=np.uint8)
+    rc = L.qd_revcomp(ctx.handle, 1, 0, bad.ctypes.data_as(C.c_void_p), 4, out.ctypes.data_as(C.c_void_p), C.byref(err))
+    assert (rc, err.kind, err.pos, err.byte) == (5, 5, 2, 0)
+    amb = np.array([1, 2, 4, 15, 3], dtype=np.uint8)
+    rc = L.qd_revcomp(ctx.handle, 1, 1, amb.ctypes.data_as(C.c_void_p), 5, out.ctypes.data_as(C.c_void_p), C.byref(err))
+    assert (rc, err.kind, err.pos, err.byte) == (3, 3, 3, ord("N"))
+
+
+def test_first_error_position_random(qd):
+    from quickdna_b200 import quickdna as native
+
+    rng = np.random.default_rng(4)
+    for trial in range(120):
+        n = int(rng.integers(1, 3000))
+        dna = bytearray(_rand(rng, n, b"ACGTacgt"))
+        for _ in range(int(rng.integers(1, 4))):
+            dna[int(rng.integers(0, n))] = int(rng.choice(list(b"NRYqZ-\n \x00\xc4\xff*")))
+        dna = bytes(dna)
+        for strict in (False, True):
+            for name, gpu, cpu in (
+                ("translate", lambda: (native._translate_strict if strict else native._translate)(1, dna),
+                 lambda: oracle.translate_bytes(1, dna, strict=strict)),
+                ("revcomp", lambda: (native._reverse_complement_strict if strict else native._reverse_complement)(dna),
+                 lambda: oracle.revcomp_bytes(dna, strict=strict)),
+                ("all_frames", lambda: [f.seq for f in qd.DnaSequence(dna).translate_all_frames(1, strict)],
+                 lambda: oracle.py_all_frames(1, dna, strict=strict)),
+            ):
+                try:
+                    want = cpu()
+                    werr = None
+                except oracle.OracleError as e:
+                    want, werr = None, e
+                if werr is None:
+                    assert gpu() == want, (name, strict, trial)
+                else:
+                    with pytest.raises(ValueError) as ei:
+                        gpu()
+                    assert (ei.value.kind, ei.value.byte, ei.value.pos, str(ei.value)) == (
+                        werr.kind, werr.byte, werr.pos, str(werr)), (name, strict, trial)
+
+
+# ------------------------------------------------------------------ batches
+
+
+def _check_batch(B, reads, table, strict, frames):
+    res = B.translate_frames_batch(reads, table=table, strict=strict, frames=frames)
+    slot = oracle.table_slot(table)
+    for i, r in enumerate(reads):
+        r = bytes(r)
+        if frames == 6:
+            want = oracle.py_all_frames(table, r, strict=strict) if len(r) >= 3 else []
+        elif frames == 3:
+            want = oracle.py_self_frames(table, r, strict=strict)
+        else:
+            want = [oracle.translate_bytes(table, r, strict=strict)] if len(r) >= 3 else []
+        assert res.sequence_frames(i) == want, (i, len(r), frames)
+    # bytes of a slot outside its frame are zero
+    total_frames = sum(len(x) for i in range(len(reads)) for x in res.sequence_frames(i))
+    assert int(np.count_nonzero(res.data)) <= total_frames
+    return res
+
+
+def test_batch_variable_lengths(B):
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 2, 3, 4, 5, 47, 48, 49, 50, 0, 0, 96, 97, 1000, 12287, 12288, 12289, 30000, 7, 0]
+    lens += [int(x) for x in rng.integers(0, 2500, 300)]
+    reads = [_rand(rng, n, IUPAC) for n in lens]
+    for frames in (6, 3, 1):
+        _check_batch(B, reads, 1, False, frames)
+    _check_batch(B, [_rand(rng, n) for n in lens], 4, True, 6)
+
+
+def test_batch_many_tiny_reads(B):
+    # more sequences starting inside one tile than the shared-memory search window holds
+    rng = np.random.default_rng(6)
+    reads = [_rand(rng, int(n), IUPAC) for n in rng.integers(0, 6, 5000)]
+    _check_batch(B, reads, 1, False, 6)
+
+
+def test_batch_uniform(B):
+    rng = np.random.default_rng(7)
+    for n_reads, read_len in ((1, 1000), (37, 1000), (300, 999), (513, 150), (64, 48), (64, 49), (9, 2), (5, 3), (3, 20000)):
+        a = np.frombuffer(_rand(rng, n_reads * read_len, IUPAC), dtype=np.uint8).reshape(n_reads, read_len)
+        for frames in (6, 3, 1):
+            res = B.translate_frames_batch(a, table=11, frames=frames)
+            for i in range(n_reads):
+                r = a[i].tobytes()
+                want = {6: oracle.py_all_frames(11, r) if read_len >= 3 else [],
+                        3: oracle.py_self_frames(11, r),
+                        1: [oracle.translate_bytes(11, r)] if read_len >= 3 else []}[frames]
+                assert res.sequence_frames(i) == want, (n_reads, read_len, frames, i)
+
+
+def test_batch_chunked_pipeline_and_error_index(B, N):
+    rng = np.random.default_rng(8)
+    ctx = N.default_context()
+    assert N.lib().qd_ctx_set_chunk_bytes(ctx.handle, 1 << 16) == 0  # force many chunks
+    try:
+        a = np.frombuffer(_rand(rng, 700 * 1000), dtype=np.uint8).reshape(700, 1000).copy()
+        res = B.translate_frames_batch(a, table=1, frames=6)
+        for i in (0, 65, 66, 131, 699):
+            assert res.sequence_frames(i) == oracle.py_all_frames(1, a[i].tobytes())
+        reads = [a[i, : 400 + i].tobytes() for i in range(600)]
+        _check_batch(B, reads, 1, True, 6)
+        a[501, 777] = ord("n")
+        a[650, 3] = ord("Q")
+        with pytest.raises(ValueError) as ei:
+            B.translate_frames_batch(a, table=1, strict=True, frames=6)
+        assert (ei.value.seq_index, ei.value.pos, ei.value.kind, ei.value.byte) == (501, 777, 3, ord("N"))
+        with pytest.raises(ValueError) as ei:
+            B.translate_frames_batch(a, table=1, strict=False, frames=6)
+        assert (ei.value.seq_index, ei.value.pos, ei.value.kind, ei.value.byte) == (650, 3, 2, ord("Q"))
+        reads[123] = reads[123][:50] + b"-" + reads[123][51:]
+        with pytest.raises(ValueError) as ei:
+            B.translate_frames_batch(reads, table=1, frames=6)
+        assert (ei.value.seq_index, ei.value.pos, str(ei.value)) == (123, 50, "bad nucleotide: '-'")
+    finally:
+        N.lib().qd_ctx_set_chunk_bytes(ctx.handle, 256 << 20)
+
+
+# ------------------------------------------------------------------ windows / canonical / expansions
+
+
+@pytest.mark.parametrize("dna,canon", V.CANONICAL[:-1])
+def test_canonical_vectors(B, dna, canon):
+    got = B.canonical_windows(dna.encode(), w=len(dna))
+    assert got.shape == (1, len(dna)) and got[0].tobytes() == canon.encode()
+
+
+def test_canonical_windows_random(B):
+    rng = np.random.default_rng(9)
+    for n, w in ((10042 - 1, 42), (500, 1), (500, 7), (3000, 33), (1000, 64), (41, 42), (42, 42), (300, 20)):
+        dna = _rand(rng, n, b"ACGTacgt")
+        m = oracle.masks_of(dna)
+        for fwd_only in (False, True):
+            got = B.canonical_windows(dna, w=w, forward_only=fwd_only)
+            if fwd_only:
+                want = np.stack([oracle.forward_canonical(m[i:i + w]) for i in range(max(0, n - w + 1))]) if n >= w else np.empty((0, w), np.uint8)
+            else:
+                want = oracle.canonical_windows(m, w)
+            assert got.shape == want.shape
+            assert got.tobytes() == oracle.ascii_of(want.reshape(-1)), (n, w, fwd_only)
+        gm = B.canonical_windows(m, w=w, enc=1)
+        assert (gm == oracle.canonical_windows(m, w)).all()
+    with pytest.raises(ValueError) as ei:
+        B.canonical_windows(b"ACGTNACGT", w=4)
+    assert (ei.value.kind, ei.value.pos, ei.value.byte) == (3, 4, ord("N"))
+
+
+@pytest.mark.parametrize("dna,exp", V.EXPANSIONS)
+def test_expansion_vectors(B, dna, exp):
+    a = np.frombuffer(dna.encode(), dtype=np.uint8).reshape(1, -1)
+    counts, out_index, rows = B.expansion_windows(a, max_expansions=64)
+    assert int(counts[0]) == len(exp) and int(out_index[1]) == len(exp)
+    assert [r.tobytes().decode() for r in rows] == exp
+
+
+def test_expansion_windows_random(B):
+    # benches/expansions.rs:68-102 shape: 42-nt windows, 2 ambiguities from the 11-code list, cap 16
+    rng = np.random.default_rng(10)
+    n_win, w = 1000, 42
+    a = np.frombuffer(_rand(rng, n_win * w), dtype=np.uint8).reshape(n_win, w).copy()
+    codes = np.frombuffer(b"WMYHRKDSVBN", dtype=np.uint8)
+    for i in range(n_win):
+        for j in rng.choice(w, size=int(rng.integers(0, 4)), replace=False):
+            a[i, j] = codes[rng.integers(0, 11)]
+    counts, out_index, rows = B.expansion_windows(a, max_expansions=16)
+    at = 0
+    for i in range(n_win):
+        m = oracle.masks_of(a[i])
+        hint = oracle.expansions_size_hint(m)
+        assert int(counts[i]) == hint
+        if hint <= 16:
+            assert int(out_index[i]) == at
+            want = oracle.expansions(m)
+            assert rows[at:at + hint].tobytes() == oracle.ascii_of(want.reshape(-1))
+            at += hint
+        else:
+            assert int(out_index[i]) == 2 ** 64 - 1
+    assert at == len(rows) == int(out_index[n_win])
+    big = np.frombuffer((V.SIZE_HINT_OVERFLOW + "A" * 10).encode(), dtype=np.uint8).reshape(1, -1)
+    counts, _, rows = B.expansion_windows(big)
+    assert int(counts[0]) == 2 ** 64 - 1 and len(rows) == 0
+    big = np.frombuffer(V.SIZE_HINT_BIG[0].encode(), dtype=np.uint8).reshape(1, -1)
+    assert int(B.expansion_windows(big)[0][0]) == V.SIZE_HINT_BIG[1]
+
+
+def test_windows(B):
+    seq, wins = V.WINDOWS_10
+    got = B.windows(seq.encode(), 10)
+    assert [w.tobytes().decode() for w in got] == wins
+    assert len(B.windows(b"antg", 10)) == 0
+    rng = np.random.default_rng(11)
+    s = _rand(rng, 3001, b"ACDEFGHIKLMNPQRSTVWY*")
+    for w in (1, 20, 42, 127):
+        assert (B.windows(s, w) == oracle.windows(s, w)).all()
+
+
+def test_windows_all(B):
+    rng = np.random.default_rng(12)
+    for n in (0, 1, 4, 5, 41, 42, 43, 59, 60, 61, 62, 63, 64, 65, 200, 999, 99999):
+        dna = _rand(rng, n, b"ACGTacgt")
+        m = oracle.masks_of(dna) if n else np.zeros(0, np.uint8)
+        d_want, a_want, o_want, c_want = oracle.windows_all(m, 42, 20)
+        d, a, o, c = B.windows_all(dna, 42, 20)
+        assert c == c_want, n
+        assert d.tobytes() == d_want.tobytes() and a.tobytes() == a_want.tobytes()
+        assert (o == o_want).all()
+        if n:
+            d2, a2, o2, c2 = B.windows_all(m, 42, 20, enc=1)
+            assert d2.tobytes() == d_want.tobytes() and a2.tobytes() == a_want.tobytes() and c2 == c_want
+
+
+# ------------------------------------------------------------------ device-resident API at scale (properties)
+
+
+def test_device_api_revcomp_large_properties(B, N):
+    import torch
+
+    from quickdna_b200.synth import synth_np, synth_torch
+
+    dev = torch.device("cuda:0")
+    for n in (250_000_000, 250_000_001, 249_999_999):
+        x = synth_torch(2, 0, n, dev)
+        B.dev_error_reset()
+        y = B.revcomp_dev(x)
+        z = B.revcomp_dev(y)
+        assert B.dev_error_fetch(x) is None
+        assert torch.equal(z, x)  # involution on upper-case ACGT
+        # sampled slices against the oracle
+        for s0 in (0, 12345, n // 2 - 7, n - 4099):
+            sl = x[s0:s0 + 4099].cpu().numpy()
+            assert sl.tobytes() == synth_np(2, s0, 4099).tobytes()
+            want = oracle.revcomp_bytes(sl.tobytes())
+            got = y[n - s0 - 4099:n - s0].cpu().numpy().tobytes()
+            assert got == want
+        # composition: reversed complement histogram
+        hx = torch.bincount(x[: 1 << 24].to(torch.int64), minlength=128)
+        hy = torch.bincount(y[n - (1 << 24):].to(torch.int64), minlength=128)
+        assert hx[ord("A")] == hy[ord("T")] and hx[ord("C")] == hy[ord("G")] and hx[ord("G")] == hy[ord("C")]
+        del x, y, z
+    # strict failure at a known position
+    x = synth_torch(2, 0, 1_000_003, dev)
+    x[777_777] = ord("N")
+    B.dev_error_reset()
+    B.revcomp_dev(x, strict=True)
+    e = B.dev_error_fetch(x, strict=True)
+    assert e is not None and (e.kind, e.pos, e.byte) == (3, 777_777, ord("N"))
+
+
+def test_device_api_six_frames_large_properties(B, N):
+    import torch
+
+    from quickdna_b200.synth import synth_torch
+
+    dev = torch.device("cuda:0")
+    n_reads, L = 1_000_000, 1000
+    x = synth_torch(3, 0, n_reads * L, dev)
+    B.dev_error_reset()
+    out = B.translate_frames_uniform_dev(x, n_reads, L)
+    assert B.dev_error_fetch(x, uniform_len=L) is None
+    per = 16 * B.runs(L) * 6
+    o = out.view(n_reads, per)
+    # sampled reads against the oracle
+    for i in (0, 1, 4242, 500_000, n_reads - 1):
+        r = x[i * L:(i + 1) * L].cpu().numpy().tobytes()
+        want = oracle.py_all_frames(1, r)
+        row = o[i].cpu().numpy()
+        got = [row[B.slot_frame_offset(L, 6, f):B.slot_frame_offset(L, 6, f) + B.frame_len(L, f % 3)].tobytes() for f in range(6)]
+        assert got == want
+    # property over the whole batch: reverse frames of x == forward frames of revcomp(x), read by read
+    xr = torch.empty_like(x)
+    for i0 in range(0, n_reads, 250_000):  # revcomp each read: flip within rows, complement by LUT
+        blk = x[i0 * L:(i0 + 250_000) * L].view(-1, L).flip(1)
+        comp = torch.zeros(256, dtype=torch.uint8, device=dev)
+        for a, b in zip(b"ACGT", b"TGCA"):
+            comp[a] = b
+        xr[i0 * L:(i0 + 250_000) * L] = comp[blk.reshape(-1).to(torch.int64)]
+    out_r = B.translate_frames_uniform_dev(xr, n_reads, L).view(n_reads, per)
+    for f in range(3):
+        ln = B.frame_len(L, f)
+        a0, b0 = B.slot_frame_offset(L, 6, 3 + f), B.slot_frame_offset(L, 6, f)
+        assert torch.equal(o[:, a0:a0 + ln], out_r[:, b0:b0 + ln])
+    # same data through the CSR path gives identical bytes
+    offsets = torch.arange(0, (n_reads + 1) * L, L, dtype=torch.int64, device=dev)
+    out_csr = B.translate_frames_csr_dev(x, offsets, total_runs=n_reads * B.runs(L))
+    assert torch.equal(out_csr, out)
+    # an error deep inside the batch is located exactly
+    x[123_456 * L + 789] = ord("@")
+    B.dev_error_reset()
+    B.translate_frames_uniform_dev(x, n_reads, L, out=out)
+    e = B.dev_error_fetch(x, uniform_len=L)
+    assert e is not None and (e.seq_index, e.pos, str(e)) == (123_456, 789, "bad nucleotide: '@'")
