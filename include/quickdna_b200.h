@@ -186,7 +186,7 @@ int qd_windows_all(qd_ctx *ctx, int enc, const uint8_t *dna, size_t n, size_t w_
 
 /* =================== device-pointer entry points (asynchronous) ============================
  * Same arithmetic on buffers already resident in HBM; launched on `stream` (NULL = the
- * context's stream) and NOT synchronised.  `dna` may have any alignment; kernels read whole
+ * legacy default stream, as in the CUDA runtime) and NOT synchronised.  `dna` may have any alignment; kernels read whole
  * 16-byte granules, so the granules containing the first and last byte must be readable (true
  * for any cudaMalloc / torch allocation).  `out` must be 16-byte aligned and sized by the slot
  * layout (qd_slots_bytes / qd_batch_out_bytes).  Errors are reported through a device-side

@@ -465,7 +465,9 @@ extern "C" size_t qd_batch_out_bytes(const uint64_t* offsets, size_t n_seq, int 
 // =================================================================================================
 // device-pointer entry points
 // =================================================================================================
-static cudaStream_t pick_stream(qd_ctx* c, void* s) { return s ? (cudaStream_t)s : c->stream; }
+// device-pointer entry points run on exactly the stream they are given; NULL is the legacy default
+// stream (what torch.cuda.current_stream() is unless the caller switched streams)
+static cudaStream_t pick_stream(qd_ctx*, void* s) { return (cudaStream_t)s; }
 
 extern "C" int qd_dev_error_reset(qd_ctx* c, void* stream) {
     if (!c) return QD_ERR_INVALID_ARGUMENT;

@@ -141,10 +141,10 @@ struct RunDesc {
 
 template <int FRAMES, bool USE_TMA>
 struct FramesSmem {
-    uint32_t nib[NIB_WORDS];
-    uint16_t lut[4096];
-    uint8_t decode[256];
-    uint64_t span[2];  // flat [start, end) of the tile's input span
+    alignas(16) uint32_t nib[NIB_WORDS];
+    alignas(16) uint16_t lut[4096];
+    alignas(16) uint8_t decode[256];
+    alignas(16) uint64_t span[2];  // flat [start, end) of the tile's input span
     uint32_t search[SEARCH_CAP + 1];
     uint32_t suspicious;
     uint32_t pad_;

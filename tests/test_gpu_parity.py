@@ -176,7 +176,7 @@ def test_revcomp_alignments_and_sizes(N):
     rng = np.random.default_rng(2)
     ctx = N.default_context()
     L = N.lib()
-    base = np.frombuffer(_rand(rng, 5000, IUPAC), dtype=np.uint8)
+    base = np.frombuffer(_rand(rng, 5100, IUPAC), dtype=np.uint8)
     for n in list(range(0, 70)) + [255, 256, 257, 1023, 4095, 4096, 4097, 4999]:
         for shift in (0, 1, 3, 7, 8, 15):
             src = base[shift:shift + n].copy()  # host alignment does not matter; device copy is aligned
