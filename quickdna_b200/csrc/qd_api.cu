@@ -166,14 +166,11 @@ int check_table(int table, qd_err* err, int* slot) {
 
 bool valid_frames(int f) { return f == QD_FRAMES_ONE || f == QD_FRAMES_SELF || f == QD_FRAMES_ALL; }
 
-size_t frames_smem_bytes() { return sizeof(FramesSmem<6, false>); }
-
 template <int FRAMES>
 int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_slot) {
-    auto kern = translate_frames_kernel<FRAMES, false>;
-    const size_t smem = frames_smem_bytes();
+    auto kern = translate_frames_kernel<FRAMES>;
+    const size_t smem = 0;  // all shared memory is static
     if (c->occ_frames[occ_slot] == 0) {
-        QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_THREADS, smem));
         c->occ_frames[occ_slot] = std::max(1, occ);
@@ -213,10 +210,12 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     p.n_seq = n_seq;
     p.uniform_len = seq_len;
     p.uniform_runs = (uint32_t)runs;
+    p.uniform_magic = runs == 1 ? 0 : (~0ull / runs) + 1;  // ceil(2^64 / runs); the kernel special-cases runs == 1
+    p.uniform_mod3 = (uint32_t)(seq_len % 3);
     p.total_runs = total_runs;
     p.n_tiles = (uint32_t)((total_runs + TILE_RUNS - 1) / TILE_RUNS);
     p.out = out_dev;
-    p.lut = c->d_lut + (size_t)slot * CODONS;
+    p.lut = c->d_lut + (size_t)slot * LUT_ENTRIES;
     p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
     p.err_key = c->d_err;
     p.key_base = key_base;
@@ -268,7 +267,7 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     p.n_seq = n_seq;
     p.n_tiles = (uint32_t)n_tiles;
     p.out = out_dev;
-    p.lut = c->d_lut + (size_t)slot * CODONS;
+    p.lut = c->d_lut + (size_t)slot * LUT_ENTRIES;
     p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
     p.err_key = c->d_err;
     p.flat_base = flat_base;

@@ -22,15 +22,22 @@ constexpr int NIB_WORDS = TILE_MAX_CHUNKS * 2 + 16;  // 8 nibble codes per 32-bi
 constexpr int SEARCH_CAP = 512;   // reads of one tile whose run prefix is cached in smem
 
 // Internal 4-bit nucleotide code (NOT the reference's mask): concrete bases are 0..3 in the
-// reference's A<T<C<G order so that the low two bits of each code spread concrete codons over
-// all shared-memory banks; 4..14 are the IUPAC ambiguity codes; 15 = invalid byte / past the end.
+// reference's A<T<C<G order, 4..14 are the IUPAC ambiguity codes, 15 = invalid byte / past the end.
 constexpr int CODE_INVALID = 15;
 
-// LUT index of a codon (c0 first nucleotide): idx = c0 | c1<<4 | c2<<8, then the low bits of c2
-// are folded onto bits 2..3 so that the 64 concrete codons occupy 64 consecutive 16-bit entries
-// (32 words, 32 distinct banks).  Entry = forward aa | (reverse-strand aa << 8); the reverse aa
-// is LUT[comp(c2), comp(c1), comp(c0)] of the reference table, so both strands cost one load.
-__host__ __device__ __forceinline__ uint32_t lut_fold(uint32_t idx) { return idx ^ ((idx >> 6) & 0xCu); }
+// LUT index of a codon (c0 = first nucleotide): idx = c0 + 16*c1 + 244*c2.  It is injective on
+// codes 0..14, a codon whose LAST nucleotide is 15 (anything past the end of a sequence) lands in
+// [3660, 3916) where every entry is 0, and -- found by exhaustive search -- the 64 concrete codons
+// occupy 32 words in 32 distinct shared-memory banks, so random ACGT codons never conflict.
+// The kernel gets 2*idx (the byte offset of a 16-bit entry) from ONE dp4a over four consecutive
+// doubled codes with coefficients (1, 16, 244, 0).  Entry = forward aa | (reverse-strand aa << 8);
+// the reverse aa is LUT[comp(c2), comp(c1), comp(c0)] of the reference table.
+constexpr uint32_t LUT_K1 = 16, LUT_K2 = 244;
+constexpr uint32_t LUT_ENTRIES = 4096;  // 15 + 16*15 + 244*15 = 3915 is the largest index
+constexpr uint32_t LUT_DP4A_COEF = 1u | (LUT_K1 << 8) | (LUT_K2 << 16);
+__host__ __device__ __forceinline__ uint32_t lut_index(uint32_t c0, uint32_t c1, uint32_t c2) {
+    return c0 + LUT_K1 * c1 + LUT_K2 * c2;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Small PTX helpers
@@ -119,11 +126,13 @@ struct FramesParams {
     const uint32_t* tile_first;  // sequence holding the first run of each tile, or nullptr (uniform)
     uint64_t n_seq;
     uint64_t uniform_len;        // sequence length in uniform mode
+    uint64_t uniform_magic;      // ceil(2^64 / uniform_runs): g / uniform_runs == umul64hi(g, magic) for g < 2^32
     uint32_t uniform_runs;       // ceil(uniform_len / 48)
+    uint32_t uniform_mod3;       // uniform_len % 3
     uint64_t total_runs;         // uniform mode; variable mode reads run_prefix[n_seq]
     uint32_t n_tiles;            // upper bound on tiles (tiles past total_runs exit)
     uint8_t* out;                // slot layout, 16-byte aligned
-    const uint16_t* lut;         // 4096 folded entries of the selected table
+    const uint16_t* lut;         // LUT_ENTRIES entries of the selected table, lut_index() layout
     const uint8_t* decode;       // 256-byte ASCII (or mask) -> internal code table
     unsigned long long* err_key;
     uint64_t flat_base;          // value of offsets[] that corresponds to dna[0] (CSR chunks)
@@ -134,24 +143,15 @@ struct FramesParams {
 struct RunDesc {
     uint64_t flat_start;  // flat offset of the run's first nucleotide
     uint64_t out_base;    // byte offset of the sequence's slot block in `out`
-    uint64_t n;           // sequence length
+    uint64_t left_nt;     // nucleotides from the run start to the end of its sequence
     uint32_t m;           // run index within the sequence
     uint32_t runs;        // R = ceil(n/48) of the sequence
-};
-
-template <int FRAMES, bool USE_TMA>
-struct FramesSmem {
-    alignas(16) uint32_t nib[NIB_WORDS];
-    alignas(16) uint16_t lut[4096];
-    alignas(16) uint8_t decode[256];
-    alignas(16) uint64_t span[2];  // flat [start, end) of the tile's input span
-    uint32_t search[SEARCH_CAP + 1];
-    uint32_t suspicious;
-    uint32_t pad_;
+    uint32_t mod3;        // n % 3
+    bool tiny;            // n < 3 (frames modes validate nothing)
 };
 
 // First-error search over one run's window (only on tiles the decode pass flagged).
-__device__ __forceinline__ void validate_run(const uint32_t (&W)[7], int vcnt, int strict, uint64_t flat_start,
+__device__ __forceinline__ void validate_run(const uint32_t (&W)[7], int vcnt, int strict, uint64_t key0,
                                              unsigned long long* err_key) {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -162,31 +162,42 @@ __device__ __forceinline__ void validate_run(const uint32_t (&W)[7], int vcnt, i
         if (left < 8) f &= (1u << (4 * left)) - 1u;
         if (f) {
             uint32_t pos = 8 * k + ((__ffs(f) - 1) >> 2);
-            atomicMin(err_key, (unsigned long long)(flat_start + pos));
+            atomicMin(err_key, (unsigned long long)(key0 + pos));
             break;
         }
     }
 }
 
-template <int FRAMES, bool USE_TMA>
-__global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const FramesParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FramesSmem<FRAMES, USE_TMA>& S = *reinterpret_cast<FramesSmem<FRAMES, USE_TMA>*>(smem_raw);
+// Static shared memory: compile-time addresses, so every table load is [register + immediate].
+struct FramesSmem {
+    alignas(256) uint8_t decode[256];        // input byte -> code; 256-aligned so base | byte is its address
+    alignas(16) uint16_t lut[LUT_ENTRIES];   // codon -> (forward aa, reverse aa)
+    alignas(16) uint32_t nib[NIB_WORDS];     // the tile's nucleotides as 4-bit codes, 8 per word
+    alignas(16) uint64_t span[2];            // flat [start, end) of the tile's input span
+    uint32_t search[SEARCH_CAP + 1];
+    uint32_t suspicious;
+};
+
+template <int FRAMES>
+__global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const FramesParams p) {
+    __shared__ FramesSmem S;
     const int tid = threadIdx.x;
 
     // Per-CTA tables (persistent CTA: loaded once, reused for every tile).
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.lut);
         uint4* dst = reinterpret_cast<uint4*>(S.lut);
-        for (int i = tid; i < 4096 * 2 / 16; i += TILE_THREADS) dst[i] = ldg_cached(src + i);
+        for (int i = tid; i < (int)(LUT_ENTRIES * 2 / 16); i += TILE_THREADS) dst[i] = ldg_cached(src + i);
         if (tid < 16) reinterpret_cast<uint4*>(S.decode)[tid] = ldg_cached(reinterpret_cast<const uint4*>(p.decode) + tid);
     }
     const bool uniform = (p.offsets == nullptr);
     const uint64_t total_runs = uniform ? p.total_runs : p.run_prefix[p.n_seq];
-    const uint32_t lut_base = smem_u32(S.lut);
-    const uint32_t dec_base = smem_u32(S.decode);
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna);
     const uintptr_t dna_hi = dna_lo + p.total_nt;
+    // shared-window addresses of the two tables: folded into the address-forming instruction itself
+    // (dp4a accumulator / byte permute), so a lookup is [extract, load] with no separate add
+    const uint32_t lut_base = smem_u32(S.lut);
+    const uint32_t dec_base = smem_u32(S.decode);
 
     for (uint64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint64_t g0 = tile * TILE_RUNS;
@@ -199,12 +210,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const
         const bool active = tid < (int)cnt;
         if (uniform) {
             const uint32_t g = (uint32_t)g0 + (active ? tid : 0);
-            const uint32_t r = g / p.uniform_runs;
+            const uint32_t r = p.uniform_runs == 1 ? g : (uint32_t)__umul64hi((uint64_t)g, p.uniform_magic);
             rd.m = g - r * p.uniform_runs;
-            rd.n = p.uniform_len;
             rd.runs = p.uniform_runs;
-            rd.flat_start = (uint64_t)r * p.uniform_len + (uint64_t)rd.m * RUN_NT;
-            rd.out_base = (uint64_t)r * p.uniform_runs * (16u * FRAMES);
+            rd.mod3 = p.uniform_mod3;
+            rd.tiny = p.uniform_len < 3;
+            const uint64_t in_seq = (uint64_t)rd.m * RUN_NT;
+            rd.left_nt = p.uniform_len - in_seq;
+            rd.flat_start = (uint64_t)r * p.uniform_len + in_seq;
+            rd.out_base = (uint64_t)r * ((uint64_t)p.uniform_runs * (16u * FRAMES));
         } else {
             // cache the run prefix of the sequences this tile touches, then upper_bound in smem
             const uint32_t r_first = p.tile_first[tile];
@@ -217,8 +231,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const
             }
             __syncthreads();
             const uint32_t gl = active ? tid : 0;  // run index relative to g0
-            // largest i with search[i] <= gl
-            uint32_t lo = 0, hi = SEARCH_CAP;
+            uint32_t lo = 0, hi = SEARCH_CAP;      // largest i with search[i] <= gl
             while (lo < hi) {
                 uint32_t mid = (lo + hi + 1) >> 1;
                 if (S.search[mid] <= gl) lo = mid; else hi = mid - 1;
@@ -235,14 +248,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const
             }
             const uint64_t rp = p.run_prefix[r];
             const uint64_t o0 = p.offsets[r] - p.flat_base;
-            rd.n = p.offsets[r + 1] - p.flat_base - o0;
+            const uint64_t n = p.offsets[r + 1] - p.flat_base - o0;
             rd.m = (uint32_t)(g0 + gl - rp);
-            rd.runs = (uint32_t)((rd.n + RUN_NT - 1) / RUN_NT);
-            rd.flat_start = o0 + (uint64_t)rd.m * RUN_NT;
+            rd.runs = (uint32_t)((n + RUN_NT - 1) / RUN_NT);
+            rd.mod3 = (n >> 32) ? (uint32_t)(n % 3) : ((uint32_t)n % 3u);
+            rd.tiny = n < 3;
+            const uint64_t in_seq = (uint64_t)rd.m * RUN_NT;
+            rd.left_nt = n - in_seq;
+            rd.flat_start = o0 + in_seq;
             rd.out_base = rp * (16u * FRAMES);
         }
-        const uint64_t left_nt = rd.n - (uint64_t)rd.m * RUN_NT;  // nucleotides from the run start to the sequence end
-        const int have = (int)min((uint64_t)(RUN_NT + 2), left_nt);  // nucleotides this run may look at
+        const int have = (int)min((uint64_t)(RUN_NT + 2), rd.left_nt);  // nucleotides this run may look at
         if (tid == 0) S.span[0] = rd.flat_start;
         if (tid == (int)cnt - 1) S.span[1] = rd.flat_start + have;
         __syncthreads();
@@ -276,14 +292,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t wa = w[2 * h], wb = w[2 * h + 1];
-                uint32_t acc = lds_u8(dec_base + (wb >> 24));
-                acc = acc * 16u + lds_u8(dec_base + ((wb >> 16) & 0xffu));
-                acc = acc * 16u + lds_u8(dec_base + ((wb >> 8) & 0xffu));
-                acc = acc * 16u + lds_u8(dec_base + (wb & 0xffu));
-                acc = acc * 16u + lds_u8(dec_base + (wa >> 24));
-                acc = acc * 16u + lds_u8(dec_base + ((wa >> 16) & 0xffu));
-                acc = acc * 16u + lds_u8(dec_base + ((wa >> 8) & 0xffu));
-                acc = acc * 16u + lds_u8(dec_base + (wa & 0xffu));
+                // one permute per nucleotide extracts the byte INTO the table's base address; the *16
+                // chain that packs the codes runs on the FMA pipe
+                uint32_t acc = lds_u8(__byte_perm(wb, dec_base, 0x7653));
+                acc = acc * 16u + lds_u8(__byte_perm(wb, dec_base, 0x7652));
+                acc = acc * 16u + lds_u8(__byte_perm(wb, dec_base, 0x7651));
+                acc = acc * 16u + lds_u8(__byte_perm(wb, dec_base, 0x7650));
+                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7653));
+                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7652));
+                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7651));
+                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7650));
                 nw[h] = acc;
             }
             // conservative filter: strict -> any code >= 4; else any code >= 12 (exact check in phase 2)
@@ -309,9 +327,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const
             if (S.suspicious) {
                 // validated range: translate -> first 3*floor(n/3) bytes (src/trans_table.rs:191);
                 // frames -> every byte when n >= 3 (union of the frames), none otherwise
-                const uint64_t vend = (FRAMES == 1) ? (rd.n / 3) * 3 : (rd.n >= 3 ? rd.n : 0);
-                const uint64_t run0 = (uint64_t)rd.m * RUN_NT;
-                if (vend > run0) validate_run(W, (int)min((uint64_t)RUN_NT, vend - run0), p.strict, p.key_base + rd.flat_start, p.err_key);
+                uint64_t vleft = rd.left_nt;  // validated nucleotides from the run start on
+                if (FRAMES == 1) vleft = vleft >= rd.mod3 ? vleft - rd.mod3 : 0;
+                else if (rd.tiny) vleft = 0;
+                if (vleft) validate_run(W, (int)min((uint64_t)RUN_NT, vleft), p.strict, p.key_base + rd.flat_start, p.err_key);
             }
             if (have < RUN_NT + 2) {  // past the end of the sequence: code 15 -> LUT entry 0
 #pragma unroll
@@ -321,8 +340,19 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const
                     else if (left < 8) W[k] |= 0xffffffffu << (4 * left);
                 }
             }
+            // codes -> doubled codes, one per byte: Bq[q] holds nucleotides 4q..4q+3
+            uint32_t Bq[13];
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                const uint32_t lo2 = (W[k] << 1) & 0x1e1e1e1eu;  // nibbles 0,2,4,6 doubled
+                const uint32_t hi2 = (W[k] >> 3) & 0x1e1e1e1eu;  // nibbles 1,3,5,7 doubled
+                Bq[2 * k] = __byte_perm(lo2, hi2, 0x5140);
+                if (2 * k + 1 < 13) Bq[2 * k + 1] = __byte_perm(lo2, hi2, 0x7362);
+            }
             uint8_t* const out_seq = p.out + rd.out_base;
             const uint32_t slot = rd.runs * 16u;
+            uint8_t* const fwd_dst = out_seq + (size_t)rd.m * 16u;
+            uint8_t* const rc_dst = out_seq + 4 * (size_t)slot - (size_t)(rd.m + 1) * 16u;
 #pragma unroll
             for (int i = 0; i < (FRAMES == 1 ? 1 : 3); i++) {
                 uint32_t F[4], R[4];
@@ -332,29 +362,22 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) translate_frames_kernel(const
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int j = 3 * (4 * q + e) + i;  // codon start within the run
-                        const int bit = 4 * j, k = bit >> 5, s = bit & 31;
-                        // X1 = window << 1 (byte address of a 16-bit entry); T = window >> 5 (fold source)
-                        uint32_t X1, T;
-                        if (s == 0) X1 = W[k] << 1;
-                        else if (s + 12 <= 32) X1 = W[k] >> (s - 1);
-                        else X1 = __funnelshift_r(W[k], W[k + 1], s - 1);
-                        if (s + 10 <= 32) T = W[k] >> (s + 5);
-                        else if (s + 5 >= 32) T = W[k + 1] >> (s + 5 - 32);
-                        else T = __funnelshift_r(W[k], W[k + 1], s + 5);
-                        const uint32_t idx2 = (X1 & 0x1ffeu) ^ (T & 0x18u);
-                        r4[e] = lds_u16(lut_base + idx2);
+                        const int wq = j >> 2, rb = j & 3;
+                        const uint32_t x = rb == 0 ? Bq[wq] : __funnelshift_r(Bq[wq], Bq[wq + 1], 8 * rb);
+                        r4[e] = lds_u16(__dp4a(x, LUT_DP4A_COEF, lut_base));  // base + 2 * lut_index(c0, c1, c2)
                     }
-                    const uint32_t t01 = __byte_perm(r4[0], r4[1], 0x1540);
-                    const uint32_t t23 = __byte_perm(r4[2], r4[3], 0x1540);
-                    F[q] = __byte_perm(t01, t23, 0x5410);
-                    R[q] = __byte_perm(t01, t23, 0x3276);
+                    // r = fwd | rc << 8.  Pack pairs with a multiply-add (FMA pipe), finish with two permutes.
+                    const uint32_t t01 = r4[1] * 65536u + r4[0];  // [f0, r0, f1, r1]
+                    const uint32_t t23 = r4[3] * 65536u + r4[2];  // [f2, r2, f3, r3]
+                    F[q] = __byte_perm(t01, t23, 0x6420);         // f0 f1 f2 f3
+                    R[q] = __byte_perm(t01, t23, 0x1357);         // r3 r2 r1 r0
                 }
-                stg_stream(out_seq + (size_t)i * slot + (size_t)rd.m * 16u, make_uint4(F[0], F[1], F[2], F[3]));
+                stg_stream(fwd_dst + (size_t)i * slot, make_uint4(F[0], F[1], F[2], F[3]));
                 if (FRAMES == 6) {
                     // codon start p = 48m + 3jj + i is reverse frame (n - i) mod 3, residue (n-3-i)/3 - 16m - jj
-                    const uint32_t kq = (uint32_t)((rd.n + 3 - i) % 3);
-                    stg_stream(out_seq + (size_t)(4 + kq) * slot - (size_t)(rd.m + 1) * 16u,
-                               make_uint4(R[3], R[2], R[1], R[0]));
+                    uint32_t kq = rd.mod3 + 3u - i;
+                    kq = kq >= 3u ? kq - 3u : kq;
+                    stg_stream(rc_dst + (size_t)kq * slot, make_uint4(R[3], R[2], R[1], R[0]));
                 }
             }
         }
@@ -378,16 +401,17 @@ constexpr int RC_UNROLL = 4;
 
 __device__ __forceinline__ uint32_t rc_map_word(uint32_t w, uint32_t tab) {
     // input bytes b0..b3 (ascending address) -> output word whose ascending bytes are c(b3)..c(b0)
-    uint32_t r = lds_u8(tab + (w & 0xffu));
-    r = r * 256u + lds_u8(tab + ((w >> 8) & 0xffu));
-    r = r * 256u + lds_u8(tab + ((w >> 16) & 0xffu));
-    r = r * 256u + lds_u8(tab + (w >> 24));
+    // `tab` is 256-byte aligned: one permute extracts a byte straight into the table address
+    uint32_t r = lds_u8(__byte_perm(w, tab, 0x7650));
+    r = r * 256u + lds_u8(__byte_perm(w, tab, 0x7651));
+    r = r * 256u + lds_u8(__byte_perm(w, tab, 0x7652));
+    r = r * 256u + lds_u8(__byte_perm(w, tab, 0x7653));
     return r;
 }
 __device__ __forceinline__ uint32_t has_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
 
 __global__ void __launch_bounds__(RC_THREADS) revcomp_kernel(const RevcompParams p) {
-    __shared__ __align__(16) uint8_t tab_s[256];
+    __shared__ __align__(256) uint8_t tab_s[256];
     const int tid = threadIdx.x;
     if (tid < 16) reinterpret_cast<uint4*>(tab_s)[tid] = ldg_cached(reinterpret_cast<const uint4*>(p.table) + tid);
     __syncthreads();
