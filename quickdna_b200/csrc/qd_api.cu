@@ -206,7 +206,7 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     p.total_nt = (uint64_t)n_seq * seq_len;
     p.offsets = nullptr;
     p.run_prefix = nullptr;
-    p.tile_first = nullptr;
+    p.tiles = nullptr;
     p.n_seq = n_seq;
     p.uniform_len = seq_len;
     p.uniform_runs = (uint32_t)runs;
@@ -251,11 +251,11 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     }
     const size_t n_tiles = tiles_upper_bound(total_nt, n_seq);
     QD_CUDA(c, run_prefix.reserve((n_seq + 1) * sizeof(uint64_t)));
-    QD_CUDA(c, tile_first.reserve((n_tiles + 1) * sizeof(uint32_t)));
+    QD_CUDA(c, tile_first.reserve((n_tiles + 1) * sizeof(TileInfo)));
     int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, run_prefix.as<uint64_t>(), block_sums, s);
     if (rc) return rc;
     const unsigned g = (unsigned)std::min<uint64_t>((n_seq + 255) / 256, (uint64_t)c->sm_count * 8);
-    tile_first_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), n_seq, tile_first.as<uint32_t>(), n_tiles);
+    tile_info_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), offsets_dev, flat_base, n_seq, tile_first.as<TileInfo>(), n_tiles);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     FramesParams p{};
@@ -263,7 +263,7 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     p.total_nt = total_nt;
     p.offsets = offsets_dev;
     p.run_prefix = run_prefix.as<uint64_t>();
-    p.tile_first = tile_first.as<uint32_t>();
+    p.tiles = tile_first.as<TileInfo>();
     p.n_seq = n_seq;
     p.n_tiles = (uint32_t)n_tiles;
     p.out = out_dev;

@@ -19,6 +19,7 @@ constexpr int TILE_THREADS = 256;
 constexpr int TILE_MAX_BYTES = TILE_RUNS * RUN_NT + 2 + 15 + 15;  // span + halo + alignment slack
 constexpr int TILE_MAX_CHUNKS = (TILE_MAX_BYTES + 15) / 16 + 1;
 constexpr int NIB_WORDS = TILE_MAX_CHUNKS * 2 + 16;  // 8 nibble codes per 32-bit word, + window slack
+constexpr int RAW_BYTES = TILE_MAX_CHUNKS * 16;      // one staged tile of raw input bytes
 constexpr int SEARCH_CAP = 512;   // reads of one tile whose run prefix is cached in smem
 
 // Internal 4-bit nucleotide code (NOT the reference's mask): concrete bases are 0..3 in the
@@ -83,6 +84,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -118,12 +122,19 @@ constexpr unsigned long long NO_ERROR_KEY = ~0ull;
 // ------------------------------------------------------------------------------------------------
 // Frame translation (1, 3 or 6 frames from ONE read of the input)
 // ------------------------------------------------------------------------------------------------
+// Where a tile starts: flat offset of its first run, and the sequence that run belongs to.
+struct TileInfo {
+    uint64_t flat;
+    uint32_t first_seq;
+    uint32_t pad_;
+};
+
 struct FramesParams {
     const uint8_t* dna;          // flat input (all sequences back to back)
     uint64_t total_nt;           // bytes in dna
     const uint64_t* offsets;     // CSR offsets [n_seq+1] or nullptr (uniform batch / single sequence)
     const uint64_t* run_prefix;  // exclusive prefix of ceil(len/48) [n_seq+1] or nullptr (uniform)
-    const uint32_t* tile_first;  // sequence holding the first run of each tile, or nullptr (uniform)
+    const TileInfo* tiles;       // per tile (variable mode), or nullptr (uniform: closed form)
     uint64_t n_seq;
     uint64_t uniform_len;        // sequence length in uniform mode
     uint64_t uniform_magic;      // ceil(2^64 / uniform_runs): g / uniform_runs == umul64hi(g, magic) for g < 2^32
@@ -168,42 +179,91 @@ __device__ __forceinline__ void validate_run(const uint32_t (&W)[7], int vcnt, i
     }
 }
 
-// Static shared memory: compile-time addresses, so every table load is [register + immediate].
+// Shared memory of one CTA.  raw[] is the TMA landing zone: while tile T is decoded and translated,
+// the bytes of the CTA's next tile stream into the other buffer (cp.async.bulk + mbarrier), so the
+// DRAM latency of a tile is hidden behind the previous tile's arithmetic.
 struct FramesSmem {
     alignas(256) uint8_t decode[256];        // input byte -> code; 256-aligned so base | byte is its address
     alignas(16) uint16_t lut[LUT_ENTRIES];   // codon -> (forward aa, reverse aa)
     alignas(16) uint32_t nib[NIB_WORDS];     // the tile's nucleotides as 4-bit codes, 8 per word
-    alignas(16) uint64_t span[2];            // flat [start, end) of the tile's input span
+    alignas(128) uint8_t raw[2][RAW_BYTES];  // double-buffered raw input of a tile, 2-nt halo included
+    alignas(8) uint64_t full[2];             // mbarriers: raw[b] has landed
+    uint64_t span[2][2];                     // flat [start, end) of the input span staged in raw[b]
     uint32_t search[SEARCH_CAP + 1];
-    uint32_t suspicious;
+    uint32_t suspicious[2];                  // per buffer: the decode pass saw a code that needs the exact check
 };
+
+// flat offset of the first run of tile t (t * TILE_RUNS < total_runs)
+__device__ __forceinline__ uint64_t tile_flat_start(const FramesParams& p, uint64_t t) {
+    if (p.tiles) return p.tiles[t].flat;
+    const uint32_t g = (uint32_t)(t * TILE_RUNS);
+    const uint32_t r = p.uniform_runs == 1 ? g : (uint32_t)__umul64hi((uint64_t)g, p.uniform_magic);
+    return (uint64_t)r * p.uniform_len + (uint64_t)(g - r * p.uniform_runs) * RUN_NT;
+}
+
+// One thread: publish the span of tile t in S.span[b] and start its bulk copy into S.raw[b].
+// Only whole 16-byte granules inside [dna, dna + total) are copied by TMA; the (at most two) granules
+// that straddle the ends of the whole buffer are read byte-wise by the decode pass instead.
+__device__ __forceinline__ void stage_tile(FramesSmem& S, const FramesParams& p, uint64_t t, uint64_t total_runs, int b) {
+    const uint64_t lo = tile_flat_start(p, t);
+    uint64_t hi = p.total_nt;
+    if ((t + 1) * TILE_RUNS < total_runs) hi = min(p.total_nt, tile_flat_start(p, t + 1) + 2);  // 2-nt halo
+    S.span[b][0] = lo;
+    S.span[b][1] = hi;
+    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.total_nt;
+    const uintptr_t a0 = (dna_lo + lo) & ~(uintptr_t)15;
+    const uintptr_t a1 = (dna_lo + hi + 15) & ~(uintptr_t)15;
+    const uintptr_t t0 = max(a0, (dna_lo + 15) & ~(uintptr_t)15);
+    const uintptr_t t1 = min(a1, dna_hi & ~(uintptr_t)15);
+    if (t1 > t0) {
+        const uint32_t bytes = (uint32_t)(t1 - t0);
+        mbar_expect_tx(&S.full[b], bytes);
+        tma_bulk_g2s(S.raw[b] + (t0 - a0), reinterpret_cast<const void*>(t0), bytes, &S.full[b]);
+    } else {
+        mbar_arrive(&S.full[b]);
+    }
+}
 
 template <int FRAMES>
 __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const FramesParams p) {
     __shared__ FramesSmem S;
     const int tid = threadIdx.x;
+    const bool uniform = (p.offsets == nullptr);
+    const uint64_t total_runs = uniform ? p.total_runs : p.run_prefix[p.n_seq];
+    const uint64_t n_tiles = min((uint64_t)p.n_tiles, (total_runs + TILE_RUNS - 1) / TILE_RUNS);
 
-    // Per-CTA tables (persistent CTA: loaded once, reused for every tile).
+    // Per-CTA tables (persistent CTA: loaded once, reused for every tile) and the first bulk copy.
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        fence_barrier_init();
+        S.suspicious[0] = 0;
+        if (blockIdx.x < n_tiles) stage_tile(S, p, blockIdx.x, total_runs, 0);
+    }
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.lut);
         uint4* dst = reinterpret_cast<uint4*>(S.lut);
         for (int i = tid; i < (int)(LUT_ENTRIES * 2 / 16); i += TILE_THREADS) dst[i] = ldg_cached(src + i);
         if (tid < 16) reinterpret_cast<uint4*>(S.decode)[tid] = ldg_cached(reinterpret_cast<const uint4*>(p.decode) + tid);
     }
-    const bool uniform = (p.offsets == nullptr);
-    const uint64_t total_runs = uniform ? p.total_runs : p.run_prefix[p.n_seq];
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna);
     const uintptr_t dna_hi = dna_lo + p.total_nt;
     // shared-window addresses of the two tables: folded into the address-forming instruction itself
     // (dp4a accumulator / byte permute), so a lookup is [extract, load] with no separate add
     const uint32_t lut_base = smem_u32(S.lut);
     const uint32_t dec_base = smem_u32(S.decode);
+    __syncthreads();
 
-    for (uint64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
         const uint64_t g0 = tile * TILE_RUNS;
-        if (g0 >= total_runs) break;
         const uint32_t cnt = (uint32_t)min((uint64_t)TILE_RUNS, total_runs - g0);
-        if (tid == 0) S.suspicious = 0;
+        if (tid == 0) {
+            S.suspicious[buf ^ 1] = 0;  // last read in the previous iteration, next set in the following one
+            // raw[buf ^ 1] was last read during the previous iteration's decode pass (barrier since)
+            if (tile + gridDim.x < n_tiles) stage_tile(S, p, tile + gridDim.x, total_runs, buf ^ 1);
+        }
 
         // ---- phase 0: which run is mine --------------------------------------------------------
         RunDesc rd;
@@ -221,8 +281,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const
             rd.out_base = (uint64_t)r * ((uint64_t)p.uniform_runs * (16u * FRAMES));
         } else {
             // cache the run prefix of the sequences this tile touches, then upper_bound in smem
-            const uint32_t r_first = p.tile_first[tile];
-            __syncthreads();  // previous tile's readers of S.search are done
+            const uint32_t r_first = p.tiles[tile].first_seq;
             for (uint32_t i = tid; i <= SEARCH_CAP; i += TILE_THREADS) {
                 uint64_t r = (uint64_t)r_first + i;
                 uint64_t v = (r <= p.n_seq) ? p.run_prefix[r] : ~0ull;
@@ -259,21 +318,19 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const
             rd.out_base = rp * (16u * FRAMES);
         }
         const int have = (int)min((uint64_t)(RUN_NT + 2), rd.left_nt);  // nucleotides this run may look at
-        if (tid == 0) S.span[0] = rd.flat_start;
-        if (tid == (int)cnt - 1) S.span[1] = rd.flat_start + have;
-        __syncthreads();
 
-        // ---- phase 1: stream the tile's bytes, decode to 4-bit codes in shared memory ---------------
-        const uintptr_t span_lo = dna_lo + S.span[0];
-        const uintptr_t span_hi = dna_lo + S.span[1];
+        // ---- phase 1: the staged bytes -> 4-bit codes in shared memory --------------------------
+        const uintptr_t span_lo = dna_lo + S.span[buf][0];
+        const uintptr_t span_hi = dna_lo + S.span[buf][1];
         const uintptr_t a0 = span_lo & ~(uintptr_t)15;
         const uint32_t n_chunks = (uint32_t)((span_hi - a0 + 15) >> 4);
+        mbar_wait(&S.full[buf], (it >> 1) & 1);
         uint32_t flagged = 0;
         for (uint32_t c = tid; c < n_chunks; c += TILE_THREADS) {
             const uintptr_t addr = a0 + ((uintptr_t)c << 4);
             uint32_t w[4];
             if (addr >= dna_lo && addr + 16 <= dna_hi) {
-                uint4 v = ldg_stream(reinterpret_cast<const void*>(addr));
+                const uint4 v = *reinterpret_cast<const uint4*>(S.raw[buf] + ((size_t)c << 4));
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
             } else {  // first / last granule of the whole buffer: byte-wise, nothing outside [dna, dna+total)
 #pragma unroll
@@ -309,7 +366,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const
             flagged |= p.strict ? (both & 0xCCCCCCCCu) : ((nw[0] & (nw[0] >> 1) & 0x44444444u) | (nw[1] & (nw[1] >> 1) & 0x44444444u));
             *reinterpret_cast<uint2*>(&S.nib[2 * c]) = make_uint2(nw[0], nw[1]);
         }
-        if (flagged) S.suspicious = 1;
+        if (flagged) S.suspicious[buf] = 1;
         __syncthreads();
 
         // ---- phase 2: one run per thread: 48 codon starts -> 16 residues per frame per strand -----
@@ -324,7 +381,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const
 #pragma unroll
                 for (int k = 0; k < 7; k++) W[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
             }
-            if (S.suspicious) {
+            if (S.suspicious[buf]) {
                 // validated range: translate -> first 3*floor(n/3) bytes (src/trans_table.rs:191);
                 // frames -> every byte when n >= 3 (union of the frames), none otherwise
                 uint64_t vleft = rd.left_nt;  // validated nucleotides from the run start on
@@ -381,7 +438,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const
                 }
             }
         }
-        __syncthreads();  // nib / span are rewritten by the next tile
+        __syncthreads();  // nib / span / search are rewritten by the next tile
     }
 }
 
@@ -796,14 +853,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) dst[0] = 0;
 }
 
-// tile_first[t] = sequence containing run t*TILE_RUNS
-__global__ void __launch_bounds__(256) tile_first_kernel(const uint64_t* __restrict__ run_prefix, uint64_t n_seq,
-                                                         uint32_t* __restrict__ tile_first, uint64_t n_tiles_cap) {
+// tiles[t] = {flat offset of run t*TILE_RUNS, sequence containing it}
+__global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t* __restrict__ run_prefix, const uint64_t* __restrict__ offsets,
+                                                        uint64_t flat_base, uint64_t n_seq, TileInfo* __restrict__ tiles,
+                                                        uint64_t n_tiles_cap) {
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_seq; r += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t a = run_prefix[r], b = run_prefix[r + 1];
         if (b == a) continue;
+        const uint64_t o0 = offsets[r] - flat_base;
         uint64_t t = (a + TILE_RUNS - 1) / TILE_RUNS;
-        for (; t * TILE_RUNS < b && t < n_tiles_cap; t++) tile_first[t] = (uint32_t)r;
+        for (; t * TILE_RUNS < b && t < n_tiles_cap; t++) {
+            TileInfo ti;
+            ti.flat = o0 + (t * TILE_RUNS - a) * RUN_NT;
+            ti.first_seq = (uint32_t)r;
+            ti.pad_ = 0;
+            tiles[t] = ti;
+        }
     }
 }
 
