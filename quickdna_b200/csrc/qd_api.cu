@@ -76,6 +76,7 @@ struct qd_ctx {
     Pipe pipe[N_PIPE];
     size_t chunk_bytes = size_t(256) << 20;  // input bytes per pipeline chunk
     int occ_frames[3] = {0, 0, 0};
+    int occ_revcomp = 0;
 };
 
 namespace {
@@ -280,9 +281,13 @@ int revcomp_dev_table(qd_ctx* c, const uint8_t* table_dev, const uint8_t* dna_de
                       cudaStream_t s) {
     if (n == 0) return QD_OK;
     RevcompParams p{dna_dev, (uint64_t)n, out_dev, table_dev, c->d_err};
-    const uint64_t chunks = n >> 4;
-    const uint64_t per_block = (uint64_t)RC_THREADS * RC_UNROLL;
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + per_block - 1) / per_block, (uint64_t)c->sm_count * 16));
+    const uint64_t tiles = ((n >> 4) + RC_TILE_CHUNKS - 1) / RC_TILE_CHUNKS;
+    if (c->occ_revcomp == 0) {
+        int occ = 0;
+        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, revcomp_kernel, RC_THREADS, 0));
+        c->occ_revcomp = std::max(1, occ);
+    }
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)c->sm_count * c->occ_revcomp));
     revcomp_kernel<<<grid, RC_THREADS, 0, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());

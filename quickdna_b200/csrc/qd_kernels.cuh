@@ -455,6 +455,8 @@ struct RevcompParams {
 
 constexpr int RC_THREADS = 256;
 constexpr int RC_UNROLL = 4;
+constexpr int RC_TILE_CHUNKS = RC_THREADS * RC_UNROLL;  // 16-byte output chunks per tile (16 KiB)
+constexpr int RC_RAW_BYTES = (RC_TILE_CHUNKS + 1) * 16;  // + one granule for the source misalignment
 
 __device__ __forceinline__ uint32_t rc_map_word(uint32_t w, uint32_t tab) {
     // input bytes b0..b3 (ascending address) -> output word whose ascending bytes are c(b3)..c(b0)
@@ -467,61 +469,111 @@ __device__ __forceinline__ uint32_t rc_map_word(uint32_t w, uint32_t tab) {
 }
 __device__ __forceinline__ uint32_t has_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
 
-__global__ void __launch_bounds__(RC_THREADS) revcomp_kernel(const RevcompParams p) {
-    __shared__ __align__(256) uint8_t tab_s[256];
+struct RevcompSmem {
+    alignas(256) uint8_t tab[256];
+    alignas(128) uint8_t raw[2][RC_RAW_BYTES];  // double-buffered source bytes of a tile (TMA landing zone)
+    alignas(8) uint64_t full[2];
+};
+
+// Tile t produces output chunks [t*RC_TILE_CHUNKS, ...): out[16j, 16j+16) = in[n-16j-16, n-16j) reversed and
+// complemented.  Its source is one contiguous span that ends at in_end - 16*j0; `d` (the misalignment of
+// in_end) is the same for every chunk, so the span is staged as whole 16-byte granules starting at a0.
+__device__ __forceinline__ void rc_stage_tile(RevcompSmem& S, const RevcompParams& p, uint64_t t, uint64_t full_chunks, int b) {
+    const uint64_t j0 = t * RC_TILE_CHUNKS;
+    const uint32_t cnt = (uint32_t)min((uint64_t)RC_TILE_CHUNKS, full_chunks - j0);
+    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.n;
+    const uint32_t d = (uint32_t)(dna_hi & 15u);
+    const uintptr_t a0 = dna_hi - 16 * (j0 + cnt) - d;  // granule holding the tile's lowest source byte
+    const uintptr_t a1 = a0 + 16 * (uintptr_t)(cnt + (d ? 1 : 0));
+    const uintptr_t t0 = max(a0, (dna_lo + 15) & ~(uintptr_t)15);
+    const uintptr_t t1 = min(a1, dna_hi & ~(uintptr_t)15);
+    if (t1 > t0) {
+        const uint32_t bytes = (uint32_t)(t1 - t0);
+        mbar_expect_tx(&S.full[b], bytes);
+        tma_bulk_g2s(S.raw[b] + (t0 - a0), reinterpret_cast<const void*>(t0), bytes, &S.full[b]);
+    } else {
+        mbar_arrive(&S.full[b]);
+    }
+}
+
+// granule g of the staged tile; granules that straddle the ends of the whole buffer were not staged
+__device__ __forceinline__ uint4 rc_granule(const RevcompSmem& S, int b, uintptr_t a0, uint32_t g, uintptr_t dna_lo, uintptr_t dna_hi) {
+    const uintptr_t addr = a0 + 16 * (uintptr_t)g;
+    if (addr >= dna_lo && addr + 16 <= dna_hi) return *reinterpret_cast<const uint4*>(S.raw[b] + 16 * (size_t)g);
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uintptr_t a = addr + 4 * q + k;
+            const uint32_t byte = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : 0x41u;  // filler never used
+            x |= byte << (8 * k);
+        }
+        w[q] = x;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(RC_THREADS, 4) revcomp_kernel(const RevcompParams p) {
+    __shared__ RevcompSmem S;
     const int tid = threadIdx.x;
-    if (tid < 16) reinterpret_cast<uint4*>(tab_s)[tid] = ldg_cached(reinterpret_cast<const uint4*>(p.table) + tid);
-    __syncthreads();
-    const uint32_t tab = smem_u32(tab_s);
     const uint64_t n = p.n;
-    const uint64_t full = n >> 4;  // full 16-byte output chunks; chunk j holds out[16j, 16j+16) = in[n-16j-16, n-16j) reversed
-    const uintptr_t in_end = reinterpret_cast<uintptr_t>(p.dna) + n;
-    const uint32_t d = (uint32_t)(in_end & 15u);  // misalignment of every chunk's source
+    const uint64_t full = n >> 4;  // full 16-byte output chunks
+    const uint64_t n_tiles = (full + RC_TILE_CHUNKS - 1) / RC_TILE_CHUNKS;
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        fence_barrier_init();
+        if (blockIdx.x < n_tiles) rc_stage_tile(S, p, blockIdx.x, full, 0);
+    }
+    if (tid < 16) reinterpret_cast<uint4*>(S.tab)[tid] = ldg_cached(reinterpret_cast<const uint4*>(p.table) + tid);
+    __syncthreads();
+    const uint32_t tab = smem_u32(S.tab);
+    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + n;
+    const uint32_t d = (uint32_t)(dna_hi & 15u);  // misalignment of every chunk's source
     const uint32_t ws = d >> 2, bs = (d & 3u) * 8u;
 
-    for (uint64_t base = (uint64_t)blockIdx.x * (RC_THREADS * RC_UNROLL); base < full;
-         base += (uint64_t)gridDim.x * (RC_THREADS * RC_UNROLL)) {
-        uint4 lo[RC_UNROLL], hi[RC_UNROLL];
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && tile + gridDim.x < n_tiles) rc_stage_tile(S, p, tile + gridDim.x, full, buf ^ 1);
+        const uint64_t j0 = tile * RC_TILE_CHUNKS;
+        const uint32_t cnt = (uint32_t)min((uint64_t)RC_TILE_CHUNKS, full - j0);
+        const uintptr_t a0 = dna_hi - 16 * (j0 + cnt) - d;
+        mbar_wait(&S.full[buf], (it >> 1) & 1);
 #pragma unroll
         for (int u = 0; u < RC_UNROLL; u++) {
-            const uint64_t j = base + (uint64_t)u * RC_THREADS + tid;
-            if (j < full) {
-                const uintptr_t src = in_end - 16 * (j + 1);  // address of in[n-16j-16]
-                const uintptr_t q = src - d;
-                // when d != 0 the bytes live in granules q and q+16; both contain valid bytes
-                // except q for the very last chunk when it starts before `dna`
-                if (d == 0) {
-                    lo[u] = ldg_stream(reinterpret_cast<const void*>(q));
-                    hi[u] = lo[u];
-                } else {
-                    hi[u] = ldg_stream(reinterpret_cast<const void*>(q + 16));
-                    lo[u] = (q + 16 > reinterpret_cast<uintptr_t>(p.dna)) ? ldg_stream(reinterpret_cast<const void*>(q)) : make_uint4(0, 0, 0, 0);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < RC_UNROLL; u++) {
-            const uint64_t j = base + (uint64_t)u * RC_THREADS + tid;
-            if (j < full) {
-                const uint32_t w[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+            const uint32_t l = (uint32_t)u * RC_THREADS + tid;  // chunk within the tile
+            if (l < cnt) {
+                const uint64_t j = j0 + l;
+                const uint32_t g = cnt - 1 - l;  // granule holding in[n-16j-16] (at byte offset d)
                 uint32_t x[4];
-                switch (ws) {  // uniform across the grid
-                    case 0:
+                if (d == 0) {
+                    const uint4 v = rc_granule(S, buf, a0, g, dna_lo, dna_hi);
+                    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+                } else {
+                    const uint4 lo = rc_granule(S, buf, a0, g, dna_lo, dna_hi);
+                    const uint4 hi = rc_granule(S, buf, a0, g + 1, dna_lo, dna_hi);
+                    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    switch (ws) {  // uniform across the grid
+                        case 0:
 #pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k], w[k + 1], bs);
-                        break;
-                    case 1:
+                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k], w[k + 1], bs);
+                            break;
+                        case 1:
 #pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 1], w[k + 2], bs);
-                        break;
-                    case 2:
+                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 1], w[k + 2], bs);
+                            break;
+                        case 2:
 #pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 2], w[k + 3], bs);
-                        break;
-                    default:
+                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 2], w[k + 3], bs);
+                            break;
+                        default:
 #pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 3], w[(k + 4) & 7], bs);
-                        break;
+                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 3], w[(k + 4) & 7], bs);
+                            break;
+                    }
                 }
                 // x[0..3] = in[n-16j-16 .. n-16j) ; output ascending = input descending
                 uint4 o;
@@ -541,11 +593,12 @@ __global__ void __launch_bounds__(RC_THREADS) revcomp_kernel(const RevcompParams
                 stg_stream(p.out + 16 * j, o);
             }
         }
+        __syncthreads();  // raw[buf] may be restaged two iterations from now by thread 0
     }
     // tail: out[16*full, n) = in[0, n mod 16) reversed
     if (blockIdx.x == 0 && tid < (int)(n & 15u)) {
         const uint64_t i = tid;
-        const uint32_t v = tab_s[p.dna[i]];
+        const uint32_t v = S.tab[p.dna[i]];
         if (v == 0) atomicMin(p.err_key, (unsigned long long)i);
         p.out[n - 1 - i] = (uint8_t)v;
     }
