@@ -222,11 +222,13 @@ def main():
     sampler.start()
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # `ncu --profile-from-start off` lists exactly the timed region
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = ctx.launch_count - launches0
     clocks = sampler.stop()

@@ -79,6 +79,9 @@ const char *qd_last_cuda_error(const qd_ctx *ctx);
 int qd_abi_version(void);
 /* input bytes per chunk of the host batch pipeline (default 256 MiB) */
 int qd_ctx_set_chunk_bytes(qd_ctx *ctx, size_t bytes);
+/* tuning / test knob: frame launches of at least `runs` 48-nt runs use the 1024-thread tile
+ * (default 2 * 1024 * SM count); 0 = always, UINT64_MAX = never */
+int qd_ctx_set_big_tile_min_runs(qd_ctx *ctx, uint64_t runs);
 
 /* ---- tables / errors (host-only helpers) --------------------------------------------------
  * qd_table_slot:  TranslationTable::try_from(u8) + table_index(), src/trans_table.rs:114-146,

@@ -93,6 +93,7 @@ SIGNATURES = {
     "qd_canonical_windows_dev": (_i, [_vp, _i, _i, _vp, _sz, _sz, _vp, _vp]),
     "qd_windows_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "qd_launch_count": (C.c_uint64, [_vp]),
+    "qd_ctx_set_big_tile_min_runs": (C.c_int, [_vp, C.c_uint64]),
 }
 
 _lib: Optional[C.CDLL] = None

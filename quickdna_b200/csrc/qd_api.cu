@@ -69,13 +69,15 @@ struct qd_ctx {
     // device-resident tables
     uint16_t* d_lut = nullptr;  // 27 * 4096
     uint8_t* d_tables = nullptr;  // 256-byte tables, see TAB_* offsets
+    uint16_t* d_pair = nullptr;   // [encoding][strict][PAIR_ENTRIES]
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
     DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums;
     Pipe pipe[N_PIPE];
     size_t chunk_bytes = size_t(256) << 20;  // input bytes per pipeline chunk
-    int occ_frames[3] = {0, 0, 0};
+    int occ_frames[6] = {0, 0, 0, 0, 0, 0};  // [tile size][frames]
+    uint64_t big_tile_min_runs = 0;           // launches with at least this many runs use 1024-thread tiles
     int occ_revcomp = 0;
 };
 
@@ -167,28 +169,51 @@ int check_table(int table, qd_err* err, int* slot) {
 
 bool valid_frames(int f) { return f == QD_FRAMES_ONE || f == QD_FRAMES_SELF || f == QD_FRAMES_ALL; }
 
-template <int FRAMES>
+void set_encoding(const qd_ctx* c, FramesParams& p, int enc, int strict) {
+    const bool ascii = enc == QD_ENC_ASCII;
+    p.decode = tab(c, ascii ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    p.pair = c->d_pair + ((ascii ? 0 : 2) + (strict ? 1 : 0)) * PAIR_ENTRIES;
+    const uint32_t k1 = ascii ? PAIR_K1_ASCII : PAIR_K1_MASK;
+    p.pair_coef = 2u | ((2u * k1) << 16);
+    p.and_need = ascii ? 0x40404040u : 0u;
+    p.or_forbid = ascii ? 0x80808080u : 0xe0e0e0e0u;
+    p.strict = strict;
+}
+
+// Which CTA size a launch of `total_runs` runs uses: the 1024-thread tile once every SM gets at least two of them.
+bool use_big_tiles(const qd_ctx* c, uint64_t total_runs) { return total_runs >= c->big_tile_min_runs; }
+
+template <int FRAMES, int THREADS>
 int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_slot) {
-    auto kern = translate_frames_kernel<FRAMES>;
-    const size_t smem = 0;  // all shared memory is static
+    auto kern = translate_frames_kernel<FRAMES, THREADS>;
+    const size_t smem = sizeof(FramesSmem<THREADS>);
     if (c->occ_frames[occ_slot] == 0) {
         int occ = 0;
-        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_THREADS, smem));
-        c->occ_frames[occ_slot] = std::max(1, occ);
+        QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+        c->occ_frames[occ_slot] = std::max(1, std::min(occ, TileGeom<THREADS>::CTAS_PER_SM));
     }
     if (p.n_tiles == 0) return QD_OK;
     const unsigned grid = (unsigned)std::min<uint64_t>(p.n_tiles, (uint64_t)c->sm_count * c->occ_frames[occ_slot]);
-    kern<<<grid, TILE_THREADS, smem, s>>>(p);
+    kern<<<grid, THREADS, smem, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
 }
 
-int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s) {
+// p.n_tiles must have been computed with tile_runs_for(c, total_runs)
+int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s, bool big) {
+    if (big) {
+        switch (frames) {
+            case QD_FRAMES_ONE: return launch_frames_t<1, BIG_THREADS>(c, p, s, 3);
+            case QD_FRAMES_SELF: return launch_frames_t<3, BIG_THREADS>(c, p, s, 4);
+            default: return launch_frames_t<6, BIG_THREADS>(c, p, s, 5);
+        }
+    }
     switch (frames) {
-        case QD_FRAMES_ONE: return launch_frames_t<1>(c, p, s, 0);
-        case QD_FRAMES_SELF: return launch_frames_t<3>(c, p, s, 1);
-        default: return launch_frames_t<6>(c, p, s, 2);
+        case QD_FRAMES_ONE: return launch_frames_t<1, SMALL_THREADS>(c, p, s, 0);
+        case QD_FRAMES_SELF: return launch_frames_t<3, SMALL_THREADS>(c, p, s, 1);
+        default: return launch_frames_t<6, SMALL_THREADS>(c, p, s, 2);
     }
 }
 
@@ -214,14 +239,15 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     p.uniform_magic = runs == 1 ? 0 : (~0ull / runs) + 1;  // ceil(2^64 / runs); the kernel special-cases runs == 1
     p.uniform_mod3 = (uint32_t)(seq_len % 3);
     p.total_runs = total_runs;
-    p.n_tiles = (uint32_t)((total_runs + TILE_RUNS - 1) / TILE_RUNS);
+    const bool big = use_big_tiles(c, total_runs);
+    const uint64_t tile_runs = big ? BIG_THREADS : SMALL_THREADS;
+    p.n_tiles = (uint32_t)((total_runs + tile_runs - 1) / tile_runs);
     p.out = out_dev;
     p.lut = c->d_lut + (size_t)slot * LUT_ENTRIES;
-    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    set_encoding(c, p, enc, strict);
     p.err_key = c->d_err;
     p.key_base = key_base;
-    p.strict = strict;
-    return launch_frames(c, frames, p, s);
+    return launch_frames(c, frames, p, s, big);
 }
 
 template <int MODE>
@@ -236,10 +262,7 @@ int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* 
     return QD_OK;
 }
 
-size_t tiles_upper_bound(uint64_t total_nt, uint64_t n_seq) {
-    const uint64_t runs = total_nt / RUN_NT + n_seq;
-    return (size_t)((runs + TILE_RUNS - 1) / TILE_RUNS);
-}
+uint64_t runs_upper_bound(uint64_t total_nt, uint64_t n_seq) { return total_nt / RUN_NT + n_seq; }
 
 // variable-length batch on device buffers; offsets_dev are absolute, `flat_base` = offsets[0]
 int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna_dev, uint64_t total_nt,
@@ -250,13 +273,16 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
         c->last_error = "batch too large for one launch";
         return QD_ERR_INVALID_ARGUMENT;
     }
-    const size_t n_tiles = tiles_upper_bound(total_nt, n_seq);
+    // the exact run count is only known on the device; the tile size is picked from its upper bound
+    const bool big = use_big_tiles(c, total_nt / RUN_NT);
+    const uint64_t tile_runs = big ? BIG_THREADS : SMALL_THREADS;
+    const size_t n_tiles = (size_t)((runs_upper_bound(total_nt, n_seq) + tile_runs - 1) / tile_runs);
     QD_CUDA(c, run_prefix.reserve((n_seq + 1) * sizeof(uint64_t)));
     QD_CUDA(c, tile_first.reserve((n_tiles + 1) * sizeof(TileInfo)));
     int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, run_prefix.as<uint64_t>(), block_sums, s);
     if (rc) return rc;
     const unsigned g = (unsigned)std::min<uint64_t>((n_seq + 255) / 256, (uint64_t)c->sm_count * 8);
-    tile_info_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), offsets_dev, flat_base, n_seq, tile_first.as<TileInfo>(), n_tiles);
+    tile_info_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), offsets_dev, flat_base, n_seq, tile_first.as<TileInfo>(), n_tiles, tile_runs);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     FramesParams p{};
@@ -269,12 +295,11 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     p.n_tiles = (uint32_t)n_tiles;
     p.out = out_dev;
     p.lut = c->d_lut + (size_t)slot * LUT_ENTRIES;
-    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    set_encoding(c, p, enc, strict);
     p.err_key = c->d_err;
     p.flat_base = flat_base;
     p.key_base = key_base;
-    p.strict = strict;
-    return launch_frames(c, frames, p, s);
+    return launch_frames(c, frames, p, s, big);
 }
 
 int revcomp_dev_table(qd_ctx* c, const uint8_t* table_dev, const uint8_t* dna_dev, size_t n, uint8_t* out_dev,
@@ -334,12 +359,14 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         return QD_ERR_CUDA;
     }
     c->sm_count = prop.multiProcessorCount;
+    c->big_tile_min_runs = (uint64_t)2 * BIG_THREADS * (uint64_t)c->sm_count;  // every SM gets two big tiles
     const HostTables& T = host_tables();
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < N_PIPE; i++) ok &= cudaStreamCreateWithFlags(&c->pipe[i].stream, cudaStreamNonBlocking) == cudaSuccess;
     ok &= cudaMalloc(&c->d_lut, T.folded.size() * sizeof(uint16_t)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_tables, 256 * TAB_COUNT) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_pair, sizeof(T.pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
@@ -362,6 +389,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         put(TAB_TO_MASK_MASK, T.to_mask_mask);
         ok &= cudaMemcpy(c->d_tables, tabs.data(), tabs.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_lut, T.folded.data(), T.folded.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(c->d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemset(c->d_err, 0xff, sizeof(unsigned long long)) == cudaSuccess;
     }
     if (!ok) {
@@ -384,6 +412,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     }
     if (c->d_lut) cudaFree(c->d_lut);
     if (c->d_tables) cudaFree(c->d_tables);
+    if (c->d_pair) cudaFree(c->d_pair);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -396,6 +425,11 @@ extern "C" void* qd_ctx_stream(const qd_ctx* c) { return c ? (void*)c->stream : 
 extern "C" int qd_ctx_sm_count(const qd_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" const char* qd_last_cuda_error(const qd_ctx* c) { return c ? c->last_error.c_str() : "no context"; }
 extern "C" uint64_t qd_launch_count(const qd_ctx* c) { return c ? c->launches : 0; }
+extern "C" int qd_ctx_set_big_tile_min_runs(qd_ctx* c, uint64_t runs) {
+    if (!c) return QD_ERR_INVALID_ARGUMENT;
+    c->big_tile_min_runs = runs;
+    return QD_OK;
+}
 extern "C" int qd_ctx_set_chunk_bytes(qd_ctx* c, size_t bytes) {
     if (!c || bytes < (size_t(1) << 16)) return QD_ERR_INVALID_ARGUMENT;
     c->chunk_bytes = bytes;

@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace qd {
@@ -14,13 +15,24 @@ namespace qd {
 // Geometry
 // ------------------------------------------------------------------------------------------------
 constexpr int RUN_NT = 48;        // nucleotides per run: 16 residues per frame = one 128-bit store
-constexpr int TILE_RUNS = 256;    // runs per tile = threads per CTA (one run per thread in phase 2)
-constexpr int TILE_THREADS = 256;
-constexpr int TILE_MAX_BYTES = TILE_RUNS * RUN_NT + 2 + 15 + 15;  // span + halo + alignment slack
-constexpr int TILE_MAX_CHUNKS = (TILE_MAX_BYTES + 15) / 16 + 1;
-constexpr int NIB_WORDS = TILE_MAX_CHUNKS * 2 + 16;  // 8 nibble codes per 32-bit word, + window slack
-constexpr int RAW_BYTES = TILE_MAX_CHUNKS * 16;      // one staged tile of raw input bytes
-constexpr int SEARCH_CAP = 512;   // reads of one tile whose run prefix is cached in smem
+#ifndef QD_ST_HINT
+#define QD_ST_HINT 0  // 0: st.global.L1::no_allocate, 1: st.global.cs, 2: st.global
+#endif
+// A tile = one run per thread of the CTA.  Measured on B200 (tools/kbench.cu): for the 1 read : 2 write mix of the
+// six-frame kernel, ONE 1024-thread CTA per SM (48 KB contiguous in, 96 KB out per tile) reaches 5.75 TB/s where four
+// 256-thread CTAs per SM reach 5.05 TB/s; small inputs use the 256-thread form so they still spread over the SMs.
+constexpr int BIG_THREADS = 1024;
+constexpr int SMALL_THREADS = 256;
+constexpr int STAGES = 2;  // TMA landing buffers per CTA (3 and 4 measured no better)
+template <int THREADS>
+struct TileGeom {
+    static constexpr int RUNS = THREADS;                           // runs per tile
+    static constexpr int MAX_BYTES = RUNS * RUN_NT + 2 + 15 + 15;  // span + halo + alignment slack
+    static constexpr int MAX_CHUNKS = (MAX_BYTES + 15) / 16 + 1;
+    static constexpr int RAW_BYTES = MAX_CHUNKS * 16 + 64;         // one staged tile (+ slack: a run reads 80 B)
+    static constexpr int SEARCH_CAP = 2 * THREADS;                 // sequences of one tile whose run prefix is cached in smem
+    static constexpr int CTAS_PER_SM = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 4);
+};
 
 // Internal 4-bit nucleotide code (NOT the reference's mask): concrete bases are 0..3 in the
 // reference's A<T<C<G order, 4..14 are the IUPAC ambiguity codes, 15 = invalid byte / past the end.
@@ -58,9 +70,15 @@ __device__ __forceinline__ uint4 ldg_cached(const void* p) {
     return r;
 }
 __device__ __forceinline__ void stg_stream(void* p, uint4 v) {
+#if QD_ST_HINT == 1
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#elif QD_ST_HINT == 2
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -74,6 +92,18 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1   (.hi: b.byte2, b.byte3) -- 16-bit coefficients, 8-bit data
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t coef, uint32_t data, uint32_t acc) {
+    uint32_t r;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(data), "r"(acc));
+    return r;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t coef, uint32_t data, uint32_t acc) {
+    uint32_t r;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(coef), "r"(data), "r"(acc));
+    return r;
 }
 
 // mbarrier + TMA bulk copy (global -> shared::cta), used by the TMA-staged tile loader.
@@ -144,7 +174,11 @@ struct FramesParams {
     uint32_t n_tiles;            // upper bound on tiles (tiles past total_runs exit)
     uint8_t* out;                // slot layout, 16-byte aligned
     const uint16_t* lut;         // LUT_ENTRIES entries of the selected table, lut_index() layout
-    const uint8_t* decode;       // 256-byte ASCII (or mask) -> internal code table
+    const uint8_t* decode;       // 256-byte ASCII (or mask) -> internal code table (exact error search only)
+    const uint16_t* pair;        // PAIR_ENTRIES letter-pair entries for (encoding, strict)
+    uint32_t pair_coef;          // dp2a coefficients {2, 2 * k1} of the pair table
+    uint32_t and_need;           // bits every input byte must have (ASCII letters: 0x40 per byte)
+    uint32_t or_forbid;          // bits no input byte may have (ASCII: 0x80, mask: 0xe0 per byte)
     unsigned long long* err_key;
     uint64_t flat_base;          // value of offsets[] that corresponds to dna[0] (CSR chunks)
     uint64_t key_base;           // added to a flat offset to form the error key (chunked host calls)
@@ -161,53 +195,63 @@ struct RunDesc {
     bool tiny;            // n < 3 (frames modes validate nothing)
 };
 
-// First-error search over one run's window (only on tiles the decode pass flagged).
-__device__ __forceinline__ void validate_run(const uint32_t (&W)[7], int vcnt, int strict, uint64_t key0,
-                                             unsigned long long* err_key) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        int left = vcnt - 8 * k;
-        if (left <= 0) break;
-        uint32_t x = W[k];
-        uint32_t f = strict ? ((x | (x >> 1)) & 0x44444444u) >> 2 : (x & (x >> 1) & (x >> 2) & (x >> 3) & 0x11111111u);
-        if (left < 8) f &= (1u << (4 * left)) - 1u;
-        if (f) {
-            uint32_t pos = 8 * k + ((__ffs(f) - 1) >> 2);
-            atomicMin(err_key, (unsigned long long)(key0 + pos));
-            break;
+// Pair table: 5-bit letter pair (u0, u1), u = byte & 31, at index u0 + PAIR_K1 * u1 -> two "doubled code" bytes
+// (2 * code | PAIR_FLAG).  flag = the letter is invalid (or ambiguous in a strict table); the code of a VALID letter is
+// always exact, whatever its neighbour is.  The strides were picked by search so that the 16 concrete pairs fall in
+// 16 distinct shared-memory banks (random ACGT never conflicts); 31 * (1 + k1) + 1 <= PAIR_ENTRIES.
+constexpr uint32_t PAIR_K1_ASCII = 40, PAIR_K1_MASK = 38;
+constexpr uint32_t PAIR_ENTRIES = 1280;
+// The flag sits above the doubled code (bits 1..4) so a flagged letter still forms an even, in-allocation LUT address
+// (its residue is garbage, but a flagged letter inside a validated range always ends in an error).
+constexpr uint32_t PAIR_FLAG = 0x20;
+
+// Exact first-error search over one run (only threads whose conservative flags fired get here).
+__device__ __noinline__ void exact_check_run(const uint8_t* __restrict__ run_bytes /* global */, int vcnt, const uint8_t* __restrict__ decode, int strict,
+                                             uint64_t key0, unsigned long long* err_key) {
+    if ((unsigned long long)key0 >= *reinterpret_cast<volatile unsigned long long*>(err_key)) return;  // cannot lower the minimum
+    for (int i = 0; i < vcnt; i++) {
+        const uint32_t c = __ldg(decode + __ldg(run_bytes + i));
+        if (c == (uint32_t)CODE_INVALID || (strict && c >= 4u)) {
+            atomicMin(err_key, (unsigned long long)(key0 + i));
+            return;
         }
     }
 }
 
-// Shared memory of one CTA.  raw[] is the TMA landing zone: while tile T is decoded and translated,
-// the bytes of the CTA's next tile stream into the other buffer (cp.async.bulk + mbarrier), so the
-// DRAM latency of a tile is hidden behind the previous tile's arithmetic.
+// Shared memory of one CTA.  raw[] is the TMA landing zone: while tile T is translated, the bytes of the CTA's next
+// tiles stream into the other buffer (cp.async.bulk + mbarrier), so DRAM latency hides behind arithmetic.
+template <int THREADS>
 struct FramesSmem {
-    alignas(256) uint8_t decode[256];        // input byte -> code; 256-aligned so base | byte is its address
     alignas(16) uint16_t lut[LUT_ENTRIES];   // codon -> (forward aa, reverse aa)
-    alignas(16) uint32_t nib[NIB_WORDS];     // the tile's nucleotides as 4-bit codes, 8 per word
-    alignas(128) uint8_t raw[2][RAW_BYTES];  // double-buffered raw input of a tile, 2-nt halo included
-    alignas(8) uint64_t full[2];             // mbarriers: raw[b] has landed
-    uint64_t span[2][2];                     // flat [start, end) of the input span staged in raw[b]
-    uint32_t search[SEARCH_CAP + 1];
-    uint32_t suspicious[2];                  // per buffer: the decode pass saw a code that needs the exact check
+    alignas(16) uint16_t pair[PAIR_ENTRIES]; // letter pair -> two doubled codes
+    alignas(16) uint4 lowmask[17];           // lowmask[k]: the first k bytes of a 16-byte vector are 0xff
+    alignas(128) uint8_t raw[STAGES][TileGeom<THREADS>::RAW_BYTES];  // multi-buffered raw input of a tile, 2-nt halo included
+    alignas(8) uint64_t full[STAGES];             // mbarriers: raw[b] has landed
+    uint64_t span[STAGES][2];                     // flat [start, end) of the input span staged in raw[b]
+    uint32_t search[TileGeom<THREADS>::SEARCH_CAP + 1];
 };
 
-// flat offset of the first run of tile t (t * TILE_RUNS < total_runs)
+static_assert(offsetof(FramesSmem<SMALL_THREADS>, lut) == 0 && (2 * 14 + PAIR_FLAG) * (1 + LUT_K1 + LUT_K2) + 2 <= sizeof(FramesSmem<SMALL_THREADS>),
+              "a flagged codon must still address shared memory of this CTA");
+
+// flat offset of the first run of tile t (t * RUNS < total_runs)
+template <int THREADS>
 __device__ __forceinline__ uint64_t tile_flat_start(const FramesParams& p, uint64_t t) {
     if (p.tiles) return p.tiles[t].flat;
-    const uint32_t g = (uint32_t)(t * TILE_RUNS);
+    const uint32_t g = (uint32_t)(t * TileGeom<THREADS>::RUNS);
     const uint32_t r = p.uniform_runs == 1 ? g : (uint32_t)__umul64hi((uint64_t)g, p.uniform_magic);
     return (uint64_t)r * p.uniform_len + (uint64_t)(g - r * p.uniform_runs) * RUN_NT;
 }
 
 // One thread: publish the span of tile t in S.span[b] and start its bulk copy into S.raw[b].
-// Only whole 16-byte granules inside [dna, dna + total) are copied by TMA; the (at most two) granules
-// that straddle the ends of the whole buffer are read byte-wise by the decode pass instead.
-__device__ __forceinline__ void stage_tile(FramesSmem& S, const FramesParams& p, uint64_t t, uint64_t total_runs, int b) {
-    const uint64_t lo = tile_flat_start(p, t);
+// Whole 16-byte granules inside [dna, dna + total) are copied by TMA; the (at most two) granules that straddle the
+// ends of the whole buffer are copied byte-wise by this thread, so nothing outside the buffer is ever read.
+template <int THREADS>
+__device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesParams& p, uint64_t t, uint64_t total_runs, int b) {
+    constexpr int TILE_RUNS = TileGeom<THREADS>::RUNS;
+    const uint64_t lo = tile_flat_start<THREADS>(p, t);
     uint64_t hi = p.total_nt;
-    if ((t + 1) * TILE_RUNS < total_runs) hi = min(p.total_nt, tile_flat_start(p, t + 1) + 2);  // 2-nt halo
+    if ((t + 1) * TILE_RUNS < total_runs) hi = min(p.total_nt, tile_flat_start<THREADS>(p, t + 1) + 2);  // 2-nt halo
     S.span[b][0] = lo;
     S.span[b][1] = hi;
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.total_nt;
@@ -215,55 +259,63 @@ __device__ __forceinline__ void stage_tile(FramesSmem& S, const FramesParams& p,
     const uintptr_t a1 = (dna_lo + hi + 15) & ~(uintptr_t)15;
     const uintptr_t t0 = max(a0, (dna_lo + 15) & ~(uintptr_t)15);
     const uintptr_t t1 = min(a1, dna_hi & ~(uintptr_t)15);
+    if (a0 < t0 || t1 < a1) {  // edge granules of the whole buffer
+#pragma unroll 1
+        for (uintptr_t a = a0; a < min(t0, a1); a++) S.raw[b][a - a0] = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : (uint8_t)0;
+#pragma unroll 1
+        for (uintptr_t a = max(t1, a0); a < a1; a++) S.raw[b][a - a0] = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : (uint8_t)0;
+    }
     if (t1 > t0) {
         const uint32_t bytes = (uint32_t)(t1 - t0);
-        mbar_expect_tx(&S.full[b], bytes);
+        mbar_expect_tx(&S.full[b], bytes);  // release: the byte stores above are visible to whoever observes the phase
         tma_bulk_g2s(S.raw[b] + (t0 - a0), reinterpret_cast<const void*>(t0), bytes, &S.full[b]);
     } else {
         mbar_arrive(&S.full[b]);
     }
 }
 
-template <int FRAMES>
-__global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const FramesParams p) {
-    __shared__ FramesSmem S;
+template <int FRAMES, int THREADS>
+__global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) translate_frames_kernel(const FramesParams p) {
+    constexpr int TILE_THREADS = THREADS, TILE_RUNS = TileGeom<THREADS>::RUNS, SEARCH_CAP = TileGeom<THREADS>::SEARCH_CAP;
+    extern __shared__ __align__(128) unsigned char frames_smem_raw[];  // sizeof(FramesSmem<THREADS>) dynamic bytes
+    FramesSmem<THREADS>& S = *reinterpret_cast<FramesSmem<THREADS>*>(frames_smem_raw);
     const int tid = threadIdx.x;
     const bool uniform = (p.offsets == nullptr);
     const uint64_t total_runs = uniform ? p.total_runs : p.run_prefix[p.n_seq];
     const uint64_t n_tiles = min((uint64_t)p.n_tiles, (total_runs + TILE_RUNS - 1) / TILE_RUNS);
 
-    // Per-CTA tables (persistent CTA: loaded once, reused for every tile) and the first bulk copy.
+    // Per-CTA tables (persistent CTA: loaded once, reused for every tile) and the first two bulk copies.
     if (tid == 0) {
-        mbar_init(&S.full[0], 1);
-        mbar_init(&S.full[1], 1);
+        for (int b = 0; b < STAGES; b++) mbar_init(&S.full[b], 1);
         fence_barrier_init();
-        S.suspicious[0] = 0;
-        if (blockIdx.x < n_tiles) stage_tile(S, p, blockIdx.x, total_runs, 0);
+        for (int b = 0; b < STAGES; b++)
+            if (blockIdx.x + b * (uint64_t)gridDim.x < n_tiles) stage_tile(S, p, blockIdx.x + b * (uint64_t)gridDim.x, total_runs, b);
     }
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.lut);
         uint4* dst = reinterpret_cast<uint4*>(S.lut);
         for (int i = tid; i < (int)(LUT_ENTRIES * 2 / 16); i += TILE_THREADS) dst[i] = ldg_cached(src + i);
-        if (tid < 16) reinterpret_cast<uint4*>(S.decode)[tid] = ldg_cached(reinterpret_cast<const uint4*>(p.decode) + tid);
+        const uint4* psrc = reinterpret_cast<const uint4*>(p.pair);
+        uint4* pdst = reinterpret_cast<uint4*>(S.pair);
+        for (int i = tid; i < (int)(PAIR_ENTRIES * 2 / 16); i += TILE_THREADS) pdst[i] = ldg_cached(psrc + i);
+        if (tid < 17) {
+            auto word = [](int k) { return k >= 4 ? 0xffffffffu : (k <= 0 ? 0u : (1u << (8 * k)) - 1u); };
+            S.lowmask[tid] = make_uint4(word(tid), word(tid - 4), word(tid - 8), word(tid - 12));
+        }
     }
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna);
-    const uintptr_t dna_hi = dna_lo + p.total_nt;
-    // shared-window addresses of the two tables: folded into the address-forming instruction itself
-    // (dp4a accumulator / byte permute), so a lookup is [extract, load] with no separate add
+    // shared-window addresses of the two tables: folded into the address-forming dot products as the accumulator,
+    // so a lookup is [dot product, load] with no separate add
     const uint32_t lut_base = smem_u32(S.lut);
-    const uint32_t dec_base = smem_u32(S.decode);
+    const uint32_t pair_base = smem_u32(S.pair);
+    const uint32_t pair_coef = p.pair_coef;
     __syncthreads();
 
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
+        const int buf = it % STAGES;
         const uint64_t g0 = tile * TILE_RUNS;
         const uint32_t cnt = (uint32_t)min((uint64_t)TILE_RUNS, total_runs - g0);
-        if (tid == 0) {
-            S.suspicious[buf ^ 1] = 0;  // last read in the previous iteration, next set in the following one
-            // raw[buf ^ 1] was last read during the previous iteration's decode pass (barrier since)
-            if (tile + gridDim.x < n_tiles) stage_tile(S, p, tile + gridDim.x, total_runs, buf ^ 1);
-        }
 
         // ---- phase 0: which run is mine --------------------------------------------------------
         RunDesc rd;
@@ -317,99 +369,78 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const
             rd.flat_start = o0 + in_seq;
             rd.out_base = rp * (16u * FRAMES);
         }
-        const int have = (int)min((uint64_t)(RUN_NT + 2), rd.left_nt);  // nucleotides this run may look at
 
-        // ---- phase 1: the staged bytes -> 4-bit codes in shared memory --------------------------
-        const uintptr_t span_lo = dna_lo + S.span[buf][0];
-        const uintptr_t span_hi = dna_lo + S.span[buf][1];
-        const uintptr_t a0 = span_lo & ~(uintptr_t)15;
-        const uint32_t n_chunks = (uint32_t)((span_hi - a0 + 15) >> 4);
-        mbar_wait(&S.full[buf], (it >> 1) & 1);
-        uint32_t flagged = 0;
-        for (uint32_t c = tid; c < n_chunks; c += TILE_THREADS) {
-            const uintptr_t addr = a0 + ((uintptr_t)c << 4);
-            uint32_t w[4];
-            if (addr >= dna_lo && addr + 16 <= dna_hi) {
-                const uint4 v = *reinterpret_cast<const uint4*>(S.raw[buf] + ((size_t)c << 4));
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            } else {  // first / last granule of the whole buffer: byte-wise, nothing outside [dna, dna+total)
+        // ---- phase 1: my run's 52 raw bytes, from the staged tile into registers ------------------
+        mbar_wait(&S.full[buf], (it / STAGES) & 1);
+        const uintptr_t a0 = (dna_lo + S.span[buf][0]) & ~(uintptr_t)15;
+        const uint32_t o = (uint32_t)(dna_lo + rd.flat_start - a0);  // local byte offset of the run
+        uint32_t W[13];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(S.raw[buf] + (o & ~15u));
+            const uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+            const uint32_t w[20] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y,
+                                    v2.z, v2.w, v3.x, v3.y, v3.z, v3.w, v4.x, v4.y, v4.z, v4.w};
+            const uint32_t bs = (o & 3u) * 8u;
+            switch ((o >> 2) & 3u) {  // the same for every run of a sequence (48 = 0 mod 16)
+                case 0:
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uint32_t x = 0;
+                    for (int k = 0; k < 13; k++) W[k] = __funnelshift_r(w[k], w[k + 1], bs);
+                    break;
+                case 1:
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        uintptr_t a = addr + q * 4 + b;
-                        uint32_t byte = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : 0u;
-                        x |= byte << (8 * b);
-                    }
-                    w[q] = x;
-                }
+                    for (int k = 0; k < 13; k++) W[k] = __funnelshift_r(w[k + 1], w[k + 2], bs);
+                    break;
+                case 2:
+#pragma unroll
+                    for (int k = 0; k < 13; k++) W[k] = __funnelshift_r(w[k + 2], w[k + 3], bs);
+                    break;
+                default:
+#pragma unroll
+                    for (int k = 0; k < 13; k++) W[k] = __funnelshift_r(w[k + 3], w[k + 4], bs);
+                    break;
             }
-            uint32_t nw[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t wa = w[2 * h], wb = w[2 * h + 1];
-                // one permute per nucleotide extracts the byte INTO the table's base address; the *16
-                // chain that packs the codes runs on the FMA pipe
-                uint32_t acc = lds_u8(__byte_perm(wb, dec_base, 0x7653));
-                acc = acc * 16u + lds_u8(__byte_perm(wb, dec_base, 0x7652));
-                acc = acc * 16u + lds_u8(__byte_perm(wb, dec_base, 0x7651));
-                acc = acc * 16u + lds_u8(__byte_perm(wb, dec_base, 0x7650));
-                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7653));
-                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7652));
-                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7651));
-                acc = acc * 16u + lds_u8(__byte_perm(wa, dec_base, 0x7650));
-                nw[h] = acc;
-            }
-            // conservative filter: strict -> any code >= 4; else any code >= 12 (exact check in phase 2)
-            const uint32_t both = nw[0] | nw[1];
-            flagged |= p.strict ? (both & 0xCCCCCCCCu) : ((nw[0] & (nw[0] >> 1) & 0x44444444u) | (nw[1] & (nw[1] >> 1) & 0x44444444u));
-            *reinterpret_cast<uint2*>(&S.nib[2 * c]) = make_uint2(nw[0], nw[1]);
         }
-        if (flagged) S.suspicious[buf] = 1;
-        __syncthreads();
+        __syncthreads();  // every thread holds its bytes: raw[buf] can be refilled
+        if (tid == 0 && tile + STAGES * (uint64_t)gridDim.x < n_tiles) stage_tile(S, p, tile + STAGES * (uint64_t)gridDim.x, total_runs, buf);
 
         // ---- phase 2: one run per thread: 48 codon starts -> 16 residues per frame per strand -----
         if (active) {
-            const uint32_t o = (uint32_t)(dna_lo + rd.flat_start - a0);  // local nucleotide offset of the run
-            const uint32_t wi = o >> 3, sh = (o & 7u) * 4u;
-            uint32_t W[7];
-            {
-                uint32_t raw[8];
+            // letters -> doubled codes, two letters per table lookup; Bq[q] holds nucleotides 4q..4q+3
+            uint32_t Bq[13];
+            uint32_t acc_and = 0xffffffffu, acc_or = 0u;
 #pragma unroll
-                for (int k = 0; k < 8; k++) raw[k] = S.nib[wi + k];
-#pragma unroll
-                for (int k = 0; k < 7; k++) W[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
+            for (int k = 0; k < 13; k++) {
+                if (k & 1) {  // one 3-input LOP3 per two words
+                    acc_and &= W[k - 1] & W[k];
+                    acc_or |= W[k - 1] | W[k];
+                } else if (k == 12) {
+                    acc_and &= W[k];
+                    acc_or |= W[k];
+                }
+                const uint32_t m = W[k] & 0x1f1f1f1fu;
+                const uint32_t e_lo = lds_u16(dp2a_lo(pair_coef, m, pair_base));
+                const uint32_t e_hi = lds_u16(dp2a_hi(pair_coef, m, pair_base));
+                Bq[k] = e_hi * 65536u + e_lo;
             }
-            if (S.suspicious[buf]) {
+            uint32_t flags = 0;
+#pragma unroll
+            for (int k = 0; k < 12; k += 2) flags |= Bq[k] | Bq[k + 1];
+            flags |= Bq[12];
+            // conservative: a flagged letter, or a byte outside the letter range of the encoding
+            const bool suspicious = (flags & (PAIR_FLAG * 0x01010101u)) | ((acc_and & p.and_need) ^ p.and_need) | (acc_or & p.or_forbid);
+            if (suspicious) {
                 // validated range: translate -> first 3*floor(n/3) bytes (src/trans_table.rs:191);
                 // frames -> every byte when n >= 3 (union of the frames), none otherwise
                 uint64_t vleft = rd.left_nt;  // validated nucleotides from the run start on
                 if (FRAMES == 1) vleft = vleft >= rd.mod3 ? vleft - rd.mod3 : 0;
                 else if (rd.tiny) vleft = 0;
-                if (vleft) validate_run(W, (int)min((uint64_t)RUN_NT, vleft), p.strict, p.key_base + rd.flat_start, p.err_key);
-            }
-            if (have < RUN_NT + 2) {  // past the end of the sequence: code 15 -> LUT entry 0
-#pragma unroll
-                for (int k = 0; k < 7; k++) {
-                    const int left = have - 8 * k;
-                    if (left <= 0) W[k] = 0xffffffffu;
-                    else if (left < 8) W[k] |= 0xffffffffu << (4 * left);
-                }
-            }
-            // codes -> doubled codes, one per byte: Bq[q] holds nucleotides 4q..4q+3
-            uint32_t Bq[13];
-#pragma unroll
-            for (int k = 0; k < 7; k++) {
-                const uint32_t lo2 = (W[k] << 1) & 0x1e1e1e1eu;  // nibbles 0,2,4,6 doubled
-                const uint32_t hi2 = (W[k] >> 3) & 0x1e1e1e1eu;  // nibbles 1,3,5,7 doubled
-                Bq[2 * k] = __byte_perm(lo2, hi2, 0x5140);
-                if (2 * k + 1 < 13) Bq[2 * k + 1] = __byte_perm(lo2, hi2, 0x7362);
+                if (vleft) exact_check_run(p.dna + rd.flat_start, (int)min((uint64_t)RUN_NT, vleft), p.decode, p.strict, p.key_base + rd.flat_start, p.err_key);
             }
             uint8_t* const out_seq = p.out + rd.out_base;
             const uint32_t slot = rd.runs * 16u;
             uint8_t* const fwd_dst = out_seq + (size_t)rd.m * 16u;
             uint8_t* const rc_dst = out_seq + 4 * (size_t)slot - (size_t)(rd.m + 1) * 16u;
+            const bool partial = rd.left_nt < (uint64_t)(RUN_NT + 2);  // last run of its sequence
 #pragma unroll
             for (int i = 0; i < (FRAMES == 1 ? 1 : 3); i++) {
                 uint32_t F[4], R[4];
@@ -423,22 +454,30 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) translate_frames_kernel(const
                         const uint32_t x = rb == 0 ? Bq[wq] : __funnelshift_r(Bq[wq], Bq[wq + 1], 8 * rb);
                         r4[e] = lds_u16(__dp4a(x, LUT_DP4A_COEF, lut_base));  // base + 2 * lut_index(c0, c1, c2)
                     }
-                    // r = fwd | rc << 8.  Pack pairs with a multiply-add (FMA pipe), finish with two permutes.
-                    const uint32_t t01 = r4[1] * 65536u + r4[0];  // [f0, r0, f1, r1]
-                    const uint32_t t23 = r4[3] * 65536u + r4[2];  // [f2, r2, f3, r3]
-                    F[q] = __byte_perm(t01, t23, 0x6420);         // f0 f1 f2 f3
-                    R[q] = __byte_perm(t01, t23, 0x1357);         // r3 r2 r1 r0
+                    // r = fwd | rc << 8
+                    const uint32_t t01 = __byte_perm(r4[0], r4[1], 0x5410);  // [f0, r0, f1, r1]
+                    const uint32_t t23 = __byte_perm(r4[2], r4[3], 0x5410);  // [f2, r2, f3, r3]
+                    F[q] = __byte_perm(t01, t23, 0x6420);                    // f0 f1 f2 f3
+                    R[q] = __byte_perm(t01, t23, 0x1357);                    // r3 r2 r1 r0
                 }
-                stg_stream(fwd_dst + (size_t)i * slot, make_uint4(F[0], F[1], F[2], F[3]));
+                uint4 fv = make_uint4(F[0], F[1], F[2], F[3]);
+                uint4 rv = make_uint4(R[3], R[2], R[1], R[0]);
+                if (partial) {  // codon starts past the end of the sequence produce nothing: those bytes are 0
+                    const uint32_t left = max((uint32_t)rd.left_nt, (uint32_t)i) - i;  // < 50
+                    const uint32_t keep = min(16u, (left * 171u) >> 9);                // floor(left / 3), exact below 64
+                    const uint4 lm = S.lowmask[keep], hm = S.lowmask[16u - keep];
+                    fv.x &= lm.x; fv.y &= lm.y; fv.z &= lm.z; fv.w &= lm.w;            // forward: the first `keep` residues
+                    rv.x &= ~hm.x; rv.y &= ~hm.y; rv.z &= ~hm.z; rv.w &= ~hm.w;        // reverse: the last `keep` bytes
+                }
+                stg_stream(fwd_dst + (size_t)i * slot, fv);
                 if (FRAMES == 6) {
                     // codon start p = 48m + 3jj + i is reverse frame (n - i) mod 3, residue (n-3-i)/3 - 16m - jj
                     uint32_t kq = rd.mod3 + 3u - i;
                     kq = kq >= 3u ? kq - 3u : kq;
-                    stg_stream(rc_dst + (size_t)kq * slot, make_uint4(R[3], R[2], R[1], R[0]));
+                    stg_stream(rc_dst + (size_t)kq * slot, rv);
                 }
             }
         }
-        __syncthreads();  // nib / span / search are rewritten by the next tile
     }
 }
 
@@ -906,18 +945,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) dst[0] = 0;
 }
 
-// tiles[t] = {flat offset of run t*TILE_RUNS, sequence containing it}
+// tiles[t] = {flat offset of run t*tile_runs, sequence containing it}
 __global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t* __restrict__ run_prefix, const uint64_t* __restrict__ offsets,
                                                         uint64_t flat_base, uint64_t n_seq, TileInfo* __restrict__ tiles,
-                                                        uint64_t n_tiles_cap) {
+                                                        uint64_t n_tiles_cap, uint64_t tile_runs) {
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_seq; r += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t a = run_prefix[r], b = run_prefix[r + 1];
         if (b == a) continue;
         const uint64_t o0 = offsets[r] - flat_base;
-        uint64_t t = (a + TILE_RUNS - 1) / TILE_RUNS;
-        for (; t * TILE_RUNS < b && t < n_tiles_cap; t++) {
+        uint64_t t = (a + tile_runs - 1) / tile_runs;
+        for (; t * tile_runs < b && t < n_tiles_cap; t++) {
             TileInfo ti;
-            ti.flat = o0 + (t * TILE_RUNS - a) * RUN_NT;
+            ti.flat = o0 + (t * tile_runs - a) * RUN_NT;
             ti.first_seq = (uint32_t)r;
             ti.pad_ = 0;
             tiles[t] = ti;

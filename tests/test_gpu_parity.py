@@ -160,7 +160,7 @@ def test_device_lut_image_matches_tables_dat(N):
     assert img == oracle.tables()
 
 
-def test_every_length_0_to_400(qd):
+def test_every_length_0_to_400(qd, tiles):
     rng = np.random.default_rng(1)
     for n in range(0, 401):
         dna = _rand(rng, n, IUPAC)
@@ -226,7 +226,7 @@ def test_mask_encoding(N):
     assert (rc, err.kind, err.pos, err.byte) == (3, 3, 3, ord("N"))
 
 
-def test_first_error_position_random(qd):
+def test_first_error_position_random(qd, tiles):
     from quickdna_b200 import quickdna as native
 
     rng = np.random.default_rng(4)
@@ -262,6 +262,16 @@ def test_first_error_position_random(qd):
 # ------------------------------------------------------------------ batches
 
 
+@pytest.fixture(params=["default-tiles", "big-tiles"])
+def tiles(request, N):
+    """Frame launches pick the 256- or the 1024-thread tile by size; force the big one onto small inputs too."""
+    ctx = N.default_context()
+    if request.param == "big-tiles":
+        assert N.lib().qd_ctx_set_big_tile_min_runs(ctx.handle, 0) == 0
+    yield request.param
+    N.lib().qd_ctx_set_big_tile_min_runs(ctx.handle, 2 * 1024 * N.lib().qd_ctx_sm_count(ctx.handle))
+
+
 def _check_batch(B, reads, table, strict, frames):
     res = B.translate_frames_batch(reads, table=table, strict=strict, frames=frames)
     slot = oracle.table_slot(table)
@@ -280,7 +290,7 @@ def _check_batch(B, reads, table, strict, frames):
     return res
 
 
-def test_batch_variable_lengths(B):
+def test_batch_variable_lengths(B, tiles):
     rng = np.random.default_rng(5)
     lens = [0, 1, 2, 3, 4, 5, 47, 48, 49, 50, 0, 0, 96, 97, 1000, 12287, 12288, 12289, 30000, 7, 0]
     lens += [int(x) for x in rng.integers(0, 2500, 300)]
@@ -290,14 +300,14 @@ def test_batch_variable_lengths(B):
     _check_batch(B, [_rand(rng, n) for n in lens], 4, True, 6)
 
 
-def test_batch_many_tiny_reads(B):
+def test_batch_many_tiny_reads(B, tiles):
     # more sequences starting inside one tile than the shared-memory search window holds
     rng = np.random.default_rng(6)
     reads = [_rand(rng, int(n), IUPAC) for n in rng.integers(0, 6, 5000)]
     _check_batch(B, reads, 1, False, 6)
 
 
-def test_batch_uniform(B):
+def test_batch_uniform(B, tiles):
     rng = np.random.default_rng(7)
     for n_reads, read_len in ((1, 1000), (37, 1000), (300, 999), (513, 150), (64, 48), (64, 49), (9, 2), (5, 3), (3, 20000)):
         a = np.frombuffer(_rand(rng, n_reads * read_len, IUPAC), dtype=np.uint8).reshape(n_reads, read_len)
@@ -311,7 +321,7 @@ def test_batch_uniform(B):
                 assert res.sequence_frames(i) == want, (n_reads, read_len, frames, i)
 
 
-def test_batch_chunked_pipeline_and_error_index(B, N):
+def test_batch_chunked_pipeline_and_error_index(B, N, tiles):
     rng = np.random.default_rng(8)
     ctx = N.default_context()
     assert N.lib().qd_ctx_set_chunk_bytes(ctx.handle, 1 << 16) == 0  # force many chunks

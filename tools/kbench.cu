@@ -1,0 +1,143 @@
+// Kernel-only harness for tuning: runs translate_frames_kernel<6, KB_THREADS> on a uniform batch and revcomp_kernel on one
+// sequence, device-resident, CUDA-event timed.  Not product code, not a parity check (tests/ does that) --
+// it exists so kernel variants (compile-time -D knobs) can be compared back to back on ONE box.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/kbench tools/kbench.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../quickdna_b200/csrc/qd_kernels.cuh"
+#include "../quickdna_b200/csrc/qd_tables.hpp"
+
+using namespace qd;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+__global__ void synth_kernel(uint8_t* out, size_t n, uint64_t seed) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + i + 0x9e3779b97f4a7c15ull;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z ^= z >> 31;
+        out[i] = "ACGT"[z & 3];
+    }
+}
+__global__ void xorsum_kernel(const uint32_t* p, size_t n, unsigned long long* acc) {
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += p[i] * (unsigned long long)(i % 1000003 + 1);
+    atomicAdd(acc, s);
+}
+
+int main(int argc, char** argv) {
+    const size_t n_reads = argc > 1 ? strtoull(argv[1], 0, 10) : 4000000;
+    const size_t L = argc > 2 ? strtoull(argv[2], 0, 10) : 1000;
+    const int reps = argc > 3 ? atoi(argv[3]) : 10;
+    const size_t n_rc = 250000000;
+    static HostTables T;
+    build_host_tables(T);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    const size_t total = n_reads * L, runs = (L + RUN_NT - 1) / RUN_NT, out_bytes = n_reads * runs * 16 * 6;
+    uint8_t *dna, *out, *d_decode;
+    uint16_t *d_lut, *d_pair;
+    unsigned long long *d_err, *d_acc;
+    CK(cudaMalloc(&dna, total + 64));
+    CK(cudaMalloc(&out, out_bytes + 64));
+    CK(cudaMalloc(&d_lut, LUT_ENTRIES * 2));
+    CK(cudaMalloc(&d_pair, sizeof(T.pair)));
+    CK(cudaMalloc(&d_decode, 256));
+    CK(cudaMalloc(&d_err, 8));
+    CK(cudaMalloc(&d_acc, 8));
+    CK(cudaMemcpy(d_lut, T.folded.data(), LUT_ENTRIES * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_decode, T.decode_ascii, 256, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_err, 0xff, 8));
+    CK(cudaMemset(d_acc, 0, 8));
+    synth_kernel<<<sms * 8, 256>>>(dna, total, 3);
+    CK(cudaDeviceSynchronize());
+
+    FramesParams p{};
+    p.dna = dna;
+    p.total_nt = total;
+    p.n_seq = n_reads;
+    p.uniform_len = L;
+    p.uniform_runs = (uint32_t)runs;
+    p.uniform_magic = runs == 1 ? 0 : (~0ull / runs) + 1;
+    p.uniform_mod3 = (uint32_t)(L % 3);
+    p.total_runs = runs * n_reads;
+#ifndef KB_THREADS
+#define KB_THREADS 1024
+#endif
+    constexpr int TILE_THREADS = KB_THREADS, TILE_RUNS = KB_THREADS;
+    p.n_tiles = (uint32_t)((p.total_runs + TILE_RUNS - 1) / TILE_RUNS);
+    p.out = out;
+    p.lut = d_lut;
+    p.decode = d_decode;
+    p.pair = d_pair;
+    p.pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);
+    p.and_need = 0x40404040u;
+    p.or_forbid = 0x80808080u;
+    p.err_key = d_err;
+    int occ = 0;
+    const size_t smem = sizeof(FramesSmem<KB_THREADS>);
+    CK(cudaFuncSetAttribute(translate_frames_kernel<6, KB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, translate_frames_kernel<6, KB_THREADS>, TILE_THREADS, smem));
+#ifdef KB_OCC
+    occ = KB_OCC;
+#endif
+    const unsigned grid = (unsigned)(sms * occ);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; i++) translate_frames_kernel<6, KB_THREADS><<<grid, TILE_THREADS, smem>>>(p);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; i++) translate_frames_kernel<6, KB_THREADS><<<grid, TILE_THREADS, smem>>>(p);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= reps;
+    size_t algo = L;
+    for (int k = 0; k < 3; k++) algo += 2 * ((L - k) / 3);
+    xorsum_kernel<<<sms * 8, 256>>>((const uint32_t*)out, out_bytes / 4, d_acc);
+    unsigned long long acc = 0, err = 0;
+    CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&err, d_err, 8, cudaMemcpyDeviceToHost));
+    printf("frames6  occ %d grid %u  %zu x %zu  %.3f ms  %.1f GB/s algorithmic  %.3f Tnt/s  checksum %016llx err %llx\n", occ, grid, n_reads, L,
+           ms, n_reads * (double)algo / ms / 1e6, total / (double)ms / 1e9, acc, err);
+
+    // reverse complement, rotating 4 buffer sets inside the big allocations
+    if (total >= 4 * n_rc && out_bytes >= 4 * n_rc) {
+        uint8_t* d_tab;
+        CK(cudaMalloc(&d_tab, 256));
+        CK(cudaMemcpy(d_tab, T.rc_ascii[0], 256, cudaMemcpyHostToDevice));
+        int occ_rc = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_rc, revcomp_kernel, RC_THREADS, 0));
+        const uint64_t tiles = ((n_rc >> 4) + RC_TILE_CHUNKS - 1) / RC_TILE_CHUNKS;
+        const unsigned g2 = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * occ_rc);
+        for (int i = 0; i < 4; i++) {
+            RevcompParams q{dna + i * n_rc, n_rc, out + i * n_rc, d_tab, d_err};
+            revcomp_kernel<<<g2, RC_THREADS>>>(q);
+        }
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < 20; i++) {
+            RevcompParams q{dna + (i & 3) * n_rc, n_rc, out + (i & 3) * n_rc, d_tab, d_err};
+            revcomp_kernel<<<g2, RC_THREADS>>>(q);
+        }
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= 20;
+        CK(cudaMemset(d_acc, 0, 8));
+        xorsum_kernel<<<sms * 8, 256>>>((const uint32_t*)out, n_rc / 4, d_acc);
+        CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
+        printf("revcomp  occ %d grid %u  %zu nt  %.4f ms  %.1f GB/s algorithmic  checksum %016llx\n", occ_rc, g2, n_rc, ms, 2.0 * n_rc / ms / 1e6, acc);
+    }
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
