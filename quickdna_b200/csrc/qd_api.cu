@@ -70,6 +70,7 @@ struct qd_ctx {
     uint16_t* d_lut = nullptr;  // 27 * 4096
     uint8_t* d_tables = nullptr;  // 256-byte tables, see TAB_* offsets
     uint16_t* d_pair = nullptr;   // [encoding][strict][PAIR_ENTRIES]
+    uint16_t* d_rc_pair = nullptr;  // [RC_PAIR_COUNT][PAIR_ENTRIES]
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
@@ -78,7 +79,7 @@ struct qd_ctx {
     size_t chunk_bytes = size_t(256) << 20;  // input bytes per pipeline chunk
     int occ_frames[6] = {0, 0, 0, 0, 0, 0};  // [tile size][frames]
     uint64_t big_tile_min_runs = 0;           // launches with at least this many runs use 1024-thread tiles
-    int occ_revcomp = 0;
+    int occ_revcomp[2] = {0, 0};  // [small, big tile]
 };
 
 namespace {
@@ -302,21 +303,45 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     return launch_frames(c, frames, p, s, big);
 }
 
-int revcomp_dev_table(qd_ctx* c, const uint8_t* table_dev, const uint8_t* dna_dev, size_t n, uint8_t* out_dev,
-                      cudaStream_t s) {
-    if (n == 0) return QD_OK;
-    RevcompParams p{dna_dev, (uint64_t)n, out_dev, table_dev, c->d_err};
-    const uint64_t tiles = ((n >> 4) + RC_TILE_CHUNKS - 1) / RC_TILE_CHUNKS;
-    if (c->occ_revcomp == 0) {
+template <int THREADS>
+int launch_revcomp_t(qd_ctx* c, const RevcompParams& p, cudaStream_t s, int occ_slot) {
+    auto kern = revcomp_kernel<THREADS>;
+    const size_t smem = sizeof(RevcompSmem<THREADS>);
+    if (c->occ_revcomp[occ_slot] == 0) {
         int occ = 0;
-        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, revcomp_kernel, RC_THREADS, 0));
-        c->occ_revcomp = std::max(1, occ);
+        QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+        c->occ_revcomp[occ_slot] = std::max(1, occ);
     }
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)c->sm_count * c->occ_revcomp));
-    revcomp_kernel<<<grid, RC_THREADS, 0, s>>>(p);
+    const uint64_t tiles = ((p.n >> 4) + RevcompSmem<THREADS>::TILE_CHUNKS - 1) / RevcompSmem<THREADS>::TILE_CHUNKS;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)c->sm_count * c->occ_revcomp[occ_slot]));
+    kern<<<grid, THREADS, smem, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
+}
+
+// `which` = one of RC_PAIR_*: selects the complement table (256-byte form and letter-pair form)
+int revcomp_dev_table(qd_ctx* c, int which, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, cudaStream_t s) {
+    if (n == 0) return QD_OK;
+    static const int byte_tab[RC_PAIR_COUNT] = {TAB_RC_ASCII, TAB_RC_ASCII_STRICT, TAB_RC_MASK, TAB_RC_MASK_STRICT,
+                                                TAB_RC_MASK_TO_ASCII, TAB_RC_MASK_TO_ASCII_STRICT};
+    const bool ascii_in = which < RC_PAIR_MASK;
+    RevcompParams p{};
+    p.dna = dna_dev;
+    p.n = n;
+    p.out = out_dev;
+    p.table = tab(c, byte_tab[which]);
+    p.pair = c->d_rc_pair + (size_t)which * PAIR_ENTRIES;
+    p.pair_coef = 2u | ((2u * (ascii_in ? PAIR_K1_ASCII : PAIR_K1_MASK)) << 16);
+    p.and_need = ascii_in ? 0x40404040u : 0u;
+    p.or_forbid = ascii_in ? 0x80808080u : 0xe0e0e0e0u;
+    p.filler = ascii_in ? 0x41u : 0x01u;
+    p.err_key = c->d_err;
+    // big tiles once every SM gets two of them
+    const bool big = (n >> 4) >= (uint64_t)2 * RevcompSmem<RC_BIG_THREADS>::TILE_CHUNKS * (uint64_t)c->sm_count && c->big_tile_min_runs != ~0ull;
+    if (big || c->big_tile_min_runs == 0) return launch_revcomp_t<RC_BIG_THREADS>(c, p, s, 1);
+    return launch_revcomp_t<RC_SMALL_THREADS>(c, p, s, 0);
 }
 
 int reset_err_key(qd_ctx* c, cudaStream_t s) {
@@ -367,6 +392,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_lut, T.folded.size() * sizeof(uint16_t)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_tables, 256 * TAB_COUNT) == cudaSuccess;
     ok &= cudaMalloc(&c->d_pair, sizeof(T.pair)) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_rc_pair, sizeof(T.rc_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
@@ -390,6 +416,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         ok &= cudaMemcpy(c->d_tables, tabs.data(), tabs.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_lut, T.folded.data(), T.folded.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(c->d_rc_pair, T.rc_pair, sizeof(T.rc_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemset(c->d_err, 0xff, sizeof(unsigned long long)) == cudaSuccess;
     }
     if (!ok) {
@@ -413,6 +440,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_lut) cudaFree(c->d_lut);
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->d_pair) cudaFree(c->d_pair);
+    if (c->d_rc_pair) cudaFree(c->d_rc_pair);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -558,8 +586,8 @@ extern "C" int qd_revcomp_dev(qd_ctx* c, int enc, int strict, const uint8_t* dna
     if (!c || (n && (!dna_dev || !out_dev)) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(c->mu);
     QD_CUDA(c, cudaSetDevice(c->device));
-    const int which = enc == QD_ENC_ASCII ? (strict ? TAB_RC_ASCII_STRICT : TAB_RC_ASCII) : (strict ? TAB_RC_MASK_STRICT : TAB_RC_MASK);
-    return revcomp_dev_table(c, tab(c, which), dna_dev, n, out_dev, pick_stream(c, stream));
+    const int which = enc == QD_ENC_ASCII ? (strict ? RC_PAIR_ASCII_STRICT : RC_PAIR_ASCII) : (strict ? RC_PAIR_MASK_STRICT : RC_PAIR_MASK);
+    return revcomp_dev_table(c, which, dna_dev, n, out_dev, pick_stream(c, stream));
 }
 
 extern "C" int qd_translate_frames_dev(qd_ctx* c, int table, int enc, int strict, int frames, const uint8_t* dna_dev, size_t n,
@@ -698,8 +726,8 @@ extern "C" int qd_revcomp(qd_ctx* c, int enc, int strict, const uint8_t* dna, si
     QD_CUDA(c, c->out.reserve(n + 16));
     QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
     if (int rc = reset_err_key(c, s)) return rc;
-    const int which = enc == QD_ENC_ASCII ? (strict ? TAB_RC_ASCII_STRICT : TAB_RC_ASCII) : (strict ? TAB_RC_MASK_STRICT : TAB_RC_MASK);
-    if (int rc = revcomp_dev_table(c, tab(c, which), c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s)) return rc;
+    const int which = enc == QD_ENC_ASCII ? (strict ? RC_PAIR_ASCII_STRICT : RC_PAIR_ASCII) : (strict ? RC_PAIR_MASK_STRICT : RC_PAIR_MASK);
+    if (int rc = revcomp_dev_table(c, which, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s)) return rc;
     QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, n, cudaMemcpyDeviceToHost, s));
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;
@@ -965,10 +993,10 @@ extern "C" int qd_windows_all(qd_ctx* c, int enc, const uint8_t* dna, size_t n, 
     QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
     if (int rc = reset_err_key(c, s)) return rc;
     // strict alphabet (DnaSequence<Nucleotide>): the strict tables reject everything else
-    const uint8_t* t_rc = tab(c, enc == QD_ENC_ASCII ? TAB_RC_ASCII_STRICT : TAB_RC_MASK_TO_ASCII_STRICT);
+    const int t_rc = enc == QD_ENC_ASCII ? RC_PAIR_ASCII_STRICT : RC_PAIR_MASK_TO_ASCII_STRICT;
     if (int rc = revcomp_dev_table(c, t_rc, c->in.as<uint8_t>(), n, c->aux1.as<uint8_t>(), s)) return rc;
     // forward ASCII (upper case) = reverse complement of the reverse complement
-    if (int rc = revcomp_dev_table(c, tab(c, TAB_RC_ASCII_STRICT), c->aux1.as<uint8_t>(), n, c->aux0.as<uint8_t>(), s)) return rc;
+    if (int rc = revcomp_dev_table(c, RC_PAIR_ASCII_STRICT, c->aux1.as<uint8_t>(), n, c->aux0.as<uint8_t>(), s)) return rc;
     if (int rc = frames_uniform_dev(c, 0 /* Ncbi1 */, enc, 1, QD_FRAMES_ALL, c->in.as<uint8_t>(), 1, n, c->aux2.as<uint8_t>(), s)) return rc;
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;

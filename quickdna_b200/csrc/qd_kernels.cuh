@@ -488,44 +488,55 @@ struct RevcompParams {
     const uint8_t* dna;
     uint64_t n;
     uint8_t* out;            // 16-byte aligned
-    const uint8_t* table;    // 256-byte complement table, 0 = invalid byte
+    const uint8_t* table;    // 256-byte complement table, 0 = invalid byte (tail bytes and the exact error search)
+    const uint16_t* pair;    // PAIR_ENTRIES entries: letters (u0, u1) at u0 + k1 * u1 -> comp(u1) | comp(u0) << 8, invalid -> 0x80
+    uint32_t pair_coef;      // dp2a coefficients {2, 2 * k1}
+    uint32_t and_need;       // bits every input byte must have
+    uint32_t or_forbid;      // bits no input byte may have
+    uint32_t filler;         // a valid input byte replicated 4x: stands in for bytes outside the buffer in its edge granules
     unsigned long long* err_key;
 };
 
-constexpr int RC_THREADS = 256;
-constexpr int RC_UNROLL = 4;
-constexpr int RC_TILE_CHUNKS = RC_THREADS * RC_UNROLL;  // 16-byte output chunks per tile (16 KiB)
-constexpr int RC_RAW_BYTES = (RC_TILE_CHUNKS + 1) * 16;  // + one granule for the source misalignment
+#ifndef QD_RC_THREADS
+#define QD_RC_THREADS 1024
+#endif
+#ifndef QD_RC_UNROLL
+#define QD_RC_UNROLL 2
+#endif
+constexpr int RC_BIG_THREADS = QD_RC_THREADS, RC_SMALL_THREADS = 256;
+constexpr int RC_UNROLL = QD_RC_UNROLL;  // 16-byte output granules per thread and tile
+constexpr uint32_t RC_INVALID = 0x80;    // complement-table flag (outputs are ASCII letters or masks: bit 7 is free)
 
-__device__ __forceinline__ uint32_t rc_map_word(uint32_t w, uint32_t tab) {
-    // input bytes b0..b3 (ascending address) -> output word whose ascending bytes are c(b3)..c(b0)
-    // `tab` is 256-byte aligned: one permute extracts a byte straight into the table address
-    uint32_t r = lds_u8(__byte_perm(w, tab, 0x7650));
-    r = r * 256u + lds_u8(__byte_perm(w, tab, 0x7651));
-    r = r * 256u + lds_u8(__byte_perm(w, tab, 0x7652));
-    r = r * 256u + lds_u8(__byte_perm(w, tab, 0x7653));
-    return r;
-}
-__device__ __forceinline__ uint32_t has_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
-
+template <int THREADS>
 struct RevcompSmem {
-    alignas(256) uint8_t tab[256];
-    alignas(128) uint8_t raw[2][RC_RAW_BYTES];  // double-buffered source bytes of a tile (TMA landing zone)
-    alignas(8) uint64_t full[2];
+    static constexpr int TILE_CHUNKS = THREADS * RC_UNROLL;        // 16-byte output granules per tile
+    static constexpr int RAW_BYTES = (TILE_CHUNKS + 1) * 16;       // + one granule for the source misalignment
+    alignas(16) uint16_t pair[PAIR_ENTRIES];
+    alignas(128) uint8_t raw[STAGES][RAW_BYTES];  // source bytes of a tile (TMA landing zone)
+    alignas(8) uint64_t full[STAGES];
 };
 
-// Tile t produces output chunks [t*RC_TILE_CHUNKS, ...): out[16j, 16j+16) = in[n-16j-16, n-16j) reversed and
+// Tile t produces output granules [t*TILE_CHUNKS, ...): out[16j, 16j+16) = in[n-16j-16, n-16j) reversed and
 // complemented.  Its source is one contiguous span that ends at in_end - 16*j0; `d` (the misalignment of
-// in_end) is the same for every chunk, so the span is staged as whole 16-byte granules starting at a0.
-__device__ __forceinline__ void rc_stage_tile(RevcompSmem& S, const RevcompParams& p, uint64_t t, uint64_t full_chunks, int b) {
-    const uint64_t j0 = t * RC_TILE_CHUNKS;
-    const uint32_t cnt = (uint32_t)min((uint64_t)RC_TILE_CHUNKS, full_chunks - j0);
+// in_end) is the same for every granule, so the span is staged as whole 16-byte granules starting at a0.
+// Granules that straddle the ends of the whole buffer are filled byte-wise by the staging thread.
+template <int THREADS>
+__device__ __noinline__ void rc_stage_tile(RevcompSmem<THREADS>& S, const RevcompParams& p, uint64_t t, uint64_t full_chunks, int b) {
+    constexpr int TILE_CHUNKS = RevcompSmem<THREADS>::TILE_CHUNKS;
+    const uint64_t j0 = t * TILE_CHUNKS;
+    const uint32_t cnt = (uint32_t)min((uint64_t)TILE_CHUNKS, full_chunks - j0);
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.n;
     const uint32_t d = (uint32_t)(dna_hi & 15u);
     const uintptr_t a0 = dna_hi - 16 * (j0 + cnt) - d;  // granule holding the tile's lowest source byte
     const uintptr_t a1 = a0 + 16 * (uintptr_t)(cnt + (d ? 1 : 0));
     const uintptr_t t0 = max(a0, (dna_lo + 15) & ~(uintptr_t)15);
     const uintptr_t t1 = min(a1, dna_hi & ~(uintptr_t)15);
+    if (a0 < t0 || t1 < a1) {
+#pragma unroll 1
+        for (uintptr_t a = a0; a < min(t0, a1); a++) S.raw[b][a - a0] = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : (uint8_t)p.filler;
+#pragma unroll 1
+        for (uintptr_t a = max(t1, a0); a < a1; a++) S.raw[b][a - a0] = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : (uint8_t)p.filler;
+    }
     if (t1 > t0) {
         const uint32_t bytes = (uint32_t)(t1 - t0);
         mbar_expect_tx(&S.full[b], bytes);
@@ -535,109 +546,114 @@ __device__ __forceinline__ void rc_stage_tile(RevcompSmem& S, const RevcompParam
     }
 }
 
-// granule g of the staged tile; granules that straddle the ends of the whole buffer were not staged
-__device__ __forceinline__ uint4 rc_granule(const RevcompSmem& S, int b, uintptr_t a0, uint32_t g, uintptr_t dna_lo, uintptr_t dna_hi) {
-    const uintptr_t addr = a0 + 16 * (uintptr_t)g;
-    if (addr >= dna_lo && addr + 16 <= dna_hi) return *reinterpret_cast<const uint4*>(S.raw[b] + 16 * (size_t)g);
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uintptr_t a = addr + 4 * q + k;
-            const uint32_t byte = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : 0x41u;  // filler never used
-            x |= byte << (8 * k);
-        }
-        w[q] = x;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+// input word (bytes b0..b3, ascending address) -> output word whose ascending bytes are c(b3) c(b2) c(b1) c(b0):
+// two letter-pair lookups, each returning its two complemented letters already swapped
+__device__ __forceinline__ uint32_t rc_map_word(uint32_t w, uint32_t coef, uint32_t base) {
+    const uint32_t m = w & 0x1f1f1f1fu;
+    const uint32_t e_lo = lds_u16(dp2a_lo(coef, m, base));  // c(b1) | c(b0) << 8
+    const uint32_t e_hi = lds_u16(dp2a_hi(coef, m, base));  // c(b3) | c(b2) << 8
+    return e_lo * 65536u + e_hi;
 }
 
-__global__ void __launch_bounds__(RC_THREADS, 4) revcomp_kernel(const RevcompParams p) {
-    __shared__ RevcompSmem S;
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 4) revcomp_kernel(const RevcompParams p) {
+    constexpr int TILE_CHUNKS = RevcompSmem<THREADS>::TILE_CHUNKS;
+    extern __shared__ __align__(128) unsigned char rc_smem_raw[];
+    RevcompSmem<THREADS>& S = *reinterpret_cast<RevcompSmem<THREADS>*>(rc_smem_raw);
     const int tid = threadIdx.x;
     const uint64_t n = p.n;
-    const uint64_t full = n >> 4;  // full 16-byte output chunks
-    const uint64_t n_tiles = (full + RC_TILE_CHUNKS - 1) / RC_TILE_CHUNKS;
+    const uint64_t full = n >> 4;  // full 16-byte output granules
+    const uint64_t n_tiles = (full + TILE_CHUNKS - 1) / TILE_CHUNKS;
     if (tid == 0) {
-        mbar_init(&S.full[0], 1);
-        mbar_init(&S.full[1], 1);
+        for (int b = 0; b < STAGES; b++) mbar_init(&S.full[b], 1);
         fence_barrier_init();
-        if (blockIdx.x < n_tiles) rc_stage_tile(S, p, blockIdx.x, full, 0);
+        for (int b = 0; b < STAGES; b++)
+            if (blockIdx.x + b * (uint64_t)gridDim.x < n_tiles) rc_stage_tile(S, p, blockIdx.x + b * (uint64_t)gridDim.x, full, b);
     }
-    if (tid < 16) reinterpret_cast<uint4*>(S.tab)[tid] = ldg_cached(reinterpret_cast<const uint4*>(p.table) + tid);
+    {
+        const uint4* psrc = reinterpret_cast<const uint4*>(p.pair);
+        uint4* pdst = reinterpret_cast<uint4*>(S.pair);
+        for (int i = tid; i < (int)(PAIR_ENTRIES * 2 / 16); i += THREADS) pdst[i] = ldg_cached(psrc + i);
+    }
     __syncthreads();
-    const uint32_t tab = smem_u32(S.tab);
-    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + n;
-    const uint32_t d = (uint32_t)(dna_hi & 15u);  // misalignment of every chunk's source
+    const uint32_t pair_base = smem_u32(S.pair), coef = p.pair_coef;
+    const uintptr_t dna_hi = reinterpret_cast<uintptr_t>(p.dna) + n;
+    const uint32_t d = (uint32_t)(dna_hi & 15u);  // misalignment of every granule's source
     const uint32_t ws = d >> 2, bs = (d & 3u) * 8u;
 
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (tid == 0 && tile + gridDim.x < n_tiles) rc_stage_tile(S, p, tile + gridDim.x, full, buf ^ 1);
-        const uint64_t j0 = tile * RC_TILE_CHUNKS;
-        const uint32_t cnt = (uint32_t)min((uint64_t)RC_TILE_CHUNKS, full - j0);
-        const uintptr_t a0 = dna_hi - 16 * (j0 + cnt) - d;
-        mbar_wait(&S.full[buf], (it >> 1) & 1);
+        const int buf = it % STAGES;
+        const uint64_t j0 = tile * TILE_CHUNKS;
+        const uint32_t cnt = (uint32_t)min((uint64_t)TILE_CHUNKS, full - j0);
+        mbar_wait(&S.full[buf], (it / STAGES) & 1);
+        // ---- my granules' 16 source bytes each, into registers ----------------------------------------
+        uint32_t x[RC_UNROLL][4];
 #pragma unroll
         for (int u = 0; u < RC_UNROLL; u++) {
-            const uint32_t l = (uint32_t)u * RC_THREADS + tid;  // chunk within the tile
+            const uint32_t l = (uint32_t)u * THREADS + tid;  // output granule within the tile
+            const uint32_t g = l < cnt ? cnt - 1 - l : 0;    // staged granule holding in[n-16j-16] (at byte offset d)
+            const uint4* src = reinterpret_cast<const uint4*>(S.raw[buf]) + g;
+            const uint4 lo = src[0];
+            if (d == 0) {
+                x[u][0] = lo.x; x[u][1] = lo.y; x[u][2] = lo.z; x[u][3] = lo.w;
+            } else {
+                const uint4 hi = src[1];
+                const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                switch (ws) {  // uniform across the grid
+                    case 0:
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[u][k] = __funnelshift_r(w[k], w[k + 1], bs);
+                        break;
+                    case 1:
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[u][k] = __funnelshift_r(w[k + 1], w[k + 2], bs);
+                        break;
+                    case 2:
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[u][k] = __funnelshift_r(w[k + 2], w[k + 3], bs);
+                        break;
+                    default:
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[u][k] = __funnelshift_r(w[k + 3], w[(k + 4) & 7], bs);
+                        break;
+                }
+            }
+        }
+        __syncthreads();  // every thread holds its bytes: raw[buf] can be refilled
+        if (tid == 0 && tile + STAGES * (uint64_t)gridDim.x < n_tiles) rc_stage_tile(S, p, tile + STAGES * (uint64_t)gridDim.x, full, buf);
+        // ---- complement + reverse + validate + store ----------------------------------------------------
+#pragma unroll
+        for (int u = 0; u < RC_UNROLL; u++) {
+            const uint32_t l = (uint32_t)u * THREADS + tid;
             if (l < cnt) {
                 const uint64_t j = j0 + l;
-                const uint32_t g = cnt - 1 - l;  // granule holding in[n-16j-16] (at byte offset d)
-                uint32_t x[4];
-                if (d == 0) {
-                    const uint4 v = rc_granule(S, buf, a0, g, dna_lo, dna_hi);
-                    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-                } else {
-                    const uint4 lo = rc_granule(S, buf, a0, g, dna_lo, dna_hi);
-                    const uint4 hi = rc_granule(S, buf, a0, g + 1, dna_lo, dna_hi);
-                    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                    switch (ws) {  // uniform across the grid
-                        case 0:
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k], w[k + 1], bs);
-                            break;
-                        case 1:
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 1], w[k + 2], bs);
-                            break;
-                        case 2:
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 2], w[k + 3], bs);
-                            break;
-                        default:
-#pragma unroll
-                            for (int k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k + 3], w[(k + 4) & 7], bs);
-                            break;
-                    }
-                }
-                // x[0..3] = in[n-16j-16 .. n-16j) ; output ascending = input descending
+                // x[u][0..3] = in[n-16j-16 .. n-16j) ; output ascending = input descending
                 uint4 o;
-                o.x = rc_map_word(x[3], tab);
-                o.y = rc_map_word(x[2], tab);
-                o.z = rc_map_word(x[1], tab);
-                o.w = rc_map_word(x[0], tab);
-                if (has_zero_byte(o.x) | has_zero_byte(o.y) | has_zero_byte(o.z) | has_zero_byte(o.w)) {
-                    // lowest failing INPUT index of this chunk = highest failing output byte
-                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-                    for (int t = 15; t >= 0; t--)
-                        if (((ow[t >> 2] >> (8 * (t & 3))) & 0xffu) == 0) {
-                            atomicMin(p.err_key, (unsigned long long)(n - 1 - (16 * j + t)));
-                            break;
-                        }
+                o.x = rc_map_word(x[u][3], coef, pair_base);
+                o.y = rc_map_word(x[u][2], coef, pair_base);
+                o.z = rc_map_word(x[u][1], coef, pair_base);
+                o.w = rc_map_word(x[u][0], coef, pair_base);
+                const uint32_t a = x[u][0] & x[u][1] & x[u][2] & x[u][3], r = x[u][0] | x[u][1] | x[u][2] | x[u][3];
+                const uint32_t bad = ((o.x | o.y | o.z | o.w) & (RC_INVALID * 0x01010101u)) | ((a & p.and_need) ^ p.and_need) | (r & p.or_forbid);
+                if (bad) {  // exact: the lowest failing input index of this granule
+                    const uint64_t i0 = n - 16 * j - 16;
+                    if ((unsigned long long)i0 < *reinterpret_cast<volatile unsigned long long*>(p.err_key)) {
+                        for (int t = 0; t < 16; t++)
+                            if (__ldg(p.table + __ldg(p.dna + i0 + t)) == 0) {
+                                atomicMin(p.err_key, (unsigned long long)(i0 + t));
+                                break;
+                            }
+                    }
                 }
                 stg_stream(p.out + 16 * j, o);
             }
         }
-        __syncthreads();  // raw[buf] may be restaged two iterations from now by thread 0
     }
     // tail: out[16*full, n) = in[0, n mod 16) reversed
     if (blockIdx.x == 0 && tid < (int)(n & 15u)) {
         const uint64_t i = tid;
-        const uint32_t v = S.tab[p.dna[i]];
+        const uint32_t v = __ldg(p.table + __ldg(p.dna + i));
         if (v == 0) atomicMin(p.err_key, (unsigned long long)i);
         p.out[n - 1 - i] = (uint8_t)v;
     }

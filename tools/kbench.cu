@@ -13,6 +13,9 @@
 
 using namespace qd;
 
+#ifndef KB_RC_MISALIGN
+#define KB_RC_MISALIGN 0
+#endif
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 __global__ void synth_kernel(uint8_t* out, size_t n, uint64_t seed) {
@@ -113,21 +116,40 @@ int main(int argc, char** argv) {
     // reverse complement, rotating 4 buffer sets inside the big allocations
     if (total >= 4 * n_rc && out_bytes >= 4 * n_rc) {
         uint8_t* d_tab;
+        uint16_t* d_rcp;
         CK(cudaMalloc(&d_tab, 256));
+        CK(cudaMalloc(&d_rcp, PAIR_ENTRIES * 2));
         CK(cudaMemcpy(d_tab, T.rc_ascii[0], 256, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_rcp, T.rc_pair[RC_PAIR_ASCII], PAIR_ENTRIES * 2, cudaMemcpyHostToDevice));
         int occ_rc = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_rc, revcomp_kernel, RC_THREADS, 0));
-        const uint64_t tiles = ((n_rc >> 4) + RC_TILE_CHUNKS - 1) / RC_TILE_CHUNKS;
+        constexpr int RCT = RC_BIG_THREADS;
+        const size_t rc_smem = sizeof(RevcompSmem<RCT>);
+        CK(cudaFuncSetAttribute(revcomp_kernel<RCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_rc, revcomp_kernel<RCT>, RCT, rc_smem));
+#ifdef KB_RC_OCC
+        occ_rc = KB_RC_OCC;
+#endif
+        const uint64_t tiles = ((n_rc >> 4) + RevcompSmem<RCT>::TILE_CHUNKS - 1) / RevcompSmem<RCT>::TILE_CHUNKS;
         const unsigned g2 = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * occ_rc);
-        for (int i = 0; i < 4; i++) {
-            RevcompParams q{dna + i * n_rc, n_rc, out + i * n_rc, d_tab, d_err};
-            revcomp_kernel<<<g2, RC_THREADS>>>(q);
-        }
+        auto mk = [&](int i) {
+            RevcompParams q{};
+            q.dna = dna + (size_t)i * n_rc + KB_RC_MISALIGN;
+            q.n = n_rc - 16;
+            q.out = out + (size_t)i * n_rc;
+            q.table = d_tab;
+            q.pair = d_rcp;
+            q.pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);
+            q.and_need = 0x40404040u;
+            q.or_forbid = 0x80808080u;
+            q.filler = 0x41u;
+            q.err_key = d_err;
+            return q;
+        };
+        for (int i = 0; i < 4; i++) revcomp_kernel<RCT><<<g2, RCT, rc_smem>>>(mk(i));
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
         for (int i = 0; i < 20; i++) {
-            RevcompParams q{dna + (i & 3) * n_rc, n_rc, out + (i & 3) * n_rc, d_tab, d_err};
-            revcomp_kernel<<<g2, RC_THREADS>>>(q);
+            revcomp_kernel<RCT><<<g2, RCT, rc_smem>>>(mk(i & 3));
         }
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
@@ -136,7 +158,7 @@ int main(int argc, char** argv) {
         CK(cudaMemset(d_acc, 0, 8));
         xorsum_kernel<<<sms * 8, 256>>>((const uint32_t*)out, n_rc / 4, d_acc);
         CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
-        printf("revcomp  occ %d grid %u  %zu nt  %.4f ms  %.1f GB/s algorithmic  checksum %016llx\n", occ_rc, g2, n_rc, ms, 2.0 * n_rc / ms / 1e6, acc);
+        printf("revcomp  thr %d unroll %d occ %d grid %u  %zu nt  %.4f ms  %.1f GB/s algorithmic  checksum %016llx\n", RCT, RC_UNROLL, occ_rc, g2, n_rc, ms, 2.0 * n_rc / ms / 1e6, acc);
     }
     CK(cudaDeviceSynchronize());
     return 0;
