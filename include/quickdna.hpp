@@ -1,0 +1,329 @@
+// quickdna.hpp -- C++17 host mirror of the reference's Rust API for the sequence hot path
+// (src/rust_api.rs, src/trans_table.rs, src/nucleotide.rs, src/errors.rs of SecureDNA/quickdna),
+// header-only, over the C ABI of quickdna_b200.h.
+//
+// The reference is a Rust crate; Rust is not available in this build environment, so this header plays the
+// role the rebound crate would: the same type and method names, argument meaning, frame rules and error
+// vocabulary, every method body one call into libquickdna_b200.so (INTEGRATION.md shows the Rust side).
+// A `DnaSequence<T>` stores one byte per nucleotide whose value IS the 4-bit IUPAC mask, exactly as
+// `Vec<Nucleotide>` / `Vec<NucleotideAmbiguous>` do (src/nucleotide.rs:20-53), so buffers cross the
+// boundary as QD_ENC_MASK without conversion.  There is no CPU fallback: constructing a Context without a
+// usable GPU throws.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <type_traits>
+#include <vector>
+
+#include "quickdna_b200.h"
+
+namespace quickdna {
+
+// src/nucleotide.rs:20-28
+enum class Nucleotide : uint8_t { A = 1, T = 2, C = 4, G = 8 };
+// src/nucleotide.rs:31-53
+enum class NucleotideAmbiguous : uint8_t {
+    A = 1, T = 2, W = 3, C = 4, M = 5, Y = 6, H = 7, G = 8, R = 9, K = 10, D = 11, S = 12, V = 13, B = 14, N = 15
+};
+
+template <class T>
+inline constexpr bool is_nucleotide_like = std::is_same_v<T, Nucleotide> || std::is_same_v<T, NucleotideAmbiguous>;
+template <class T>
+inline constexpr int strict_of = std::is_same_v<T, Nucleotide> ? 1 : 0;
+
+// src/nucleotide.rs:138-145, 219-237
+template <class T>
+inline char to_ascii(T n) { return "?ATWCMYHGRKDSVBN"[static_cast<uint8_t>(n) & 15]; }
+// src/nucleotide.rs:125-132, 195-213
+template <class T>
+inline T complement(T n) {
+    const uint8_t m = static_cast<uint8_t>(n);
+    return static_cast<T>(((m & 5) << 1) | ((m & 10) >> 1));
+}
+
+// src/trans_table.rs:11-73 (ids accepted by TryFrom<u8>, :230-267)
+enum class TranslationTable : uint8_t {
+    Ncbi1 = 1, Ncbi2, Ncbi3, Ncbi4, Ncbi5, Ncbi6, Ncbi7, Ncbi8, Ncbi9, Ncbi10, Ncbi11, Ncbi12, Ncbi13, Ncbi14, Ncbi15, Ncbi16,
+    Ncbi21 = 21, Ncbi22, Ncbi23, Ncbi24, Ncbi25, Ncbi26, Ncbi27, Ncbi28, Ncbi29, Ncbi30, Ncbi31, Ncbi32, Ncbi33
+};
+
+// src/errors.rs:17-29; what() is the reference's Display text
+class TranslationError : public std::runtime_error {
+  public:
+    enum Kind { NonAsciiByte = 1, BadNucleotide = 2, UnexpectedAmbiguousNucleotide = 3, BadTranslationTable = 4 };
+    TranslationError(const qd_err& e, std::string msg) : std::runtime_error(std::move(msg)), kind(static_cast<Kind>(e.kind)), byte(e.byte), pos(e.pos) {}
+    Kind kind;
+    uint8_t byte;   // payload of the variant
+    uint64_t pos;   // extra: index of the offending byte
+};
+
+class RuntimeFailure : public std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// One qd_ctx per thread (the reference's functions are pure and re-entrant).
+class Context {
+  public:
+    explicit Context(int device = 0) {
+        if (qd_ctx_create(&ctx_, device) != QD_OK) throw RuntimeFailure("quickdna_b200: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Context() { qd_ctx_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    qd_ctx* get() const { return ctx_; }
+    static Context& current() {
+        thread_local Context c;
+        return c;
+    }
+    void check(int rc, const qd_err& e) const {
+        if (rc == QD_OK) return;
+        if (rc >= QD_ERR_NON_ASCII_BYTE && rc <= QD_ERR_BAD_TABLE) {
+            char buf[96];
+            qd_err_message(&e, buf, sizeof buf);
+            throw TranslationError(e, buf);
+        }
+        throw RuntimeFailure(std::string("quickdna_b200 status ") + std::to_string(rc) + ": " + qd_last_cuda_error(ctx_));
+    }
+
+  private:
+    qd_ctx* ctx_ = nullptr;
+};
+
+// TranslationTable::try_from(u8), src/trans_table.rs:230-267
+inline TranslationTable table_try_from(uint8_t id) {
+    if (qd_table_slot(id) < 0) {
+        qd_err e{QD_ERR_BAD_TABLE, id, 0, 0};
+        char buf[96];
+        qd_err_message(&e, buf, sizeof buf);
+        throw TranslationError(e, buf);
+    }
+    return static_cast<TranslationTable>(id);
+}
+
+// ---- src/trans_table.rs free functions ----------------------------------------------------------------
+
+// TranslationTable::translate_dna_bytes::<T>, src/trans_table.rs:176-203
+template <class T>
+std::vector<uint8_t> translate_dna_bytes(TranslationTable table, std::string_view dna) {
+    static_assert(is_nucleotide_like<T>);
+    std::vector<uint8_t> out(dna.size() / 3);
+    qd_err e{};
+    Context& c = Context::current();
+    c.check(qd_translate(c.get(), static_cast<int>(table), QD_ENC_ASCII, strict_of<T>, reinterpret_cast<const uint8_t*>(dna.data()),
+                         dna.size(), out.data(), &e), e);
+    return out;
+}
+
+// TranslationTable::translate_dna::<T>, src/trans_table.rs:205-227
+template <class T>
+std::vector<uint8_t> translate_dna(TranslationTable table, const T* dna, size_t n) {
+    static_assert(is_nucleotide_like<T> && sizeof(T) == 1);
+    std::vector<uint8_t> out(n / 3);
+    qd_err e{};
+    Context& c = Context::current();
+    c.check(qd_translate(c.get(), static_cast<int>(table), QD_ENC_MASK, 0, reinterpret_cast<const uint8_t*>(dna), n, out.data(), &e), e);
+    return out;
+}
+
+// reverse_complement_bytes::<T>, src/trans_table.rs:269-278
+template <class T>
+std::vector<uint8_t> reverse_complement_bytes(std::string_view dna) {
+    std::vector<uint8_t> out(dna.size());
+    qd_err e{};
+    Context& c = Context::current();
+    c.check(qd_revcomp(c.get(), QD_ENC_ASCII, strict_of<T>, reinterpret_cast<const uint8_t*>(dna.data()), dna.size(), out.data(), &e), e);
+    return out;
+}
+
+// reverse_complement::<T>, src/trans_table.rs:284-286
+template <class T>
+std::vector<T> reverse_complement(const T* dna, size_t n) {
+    std::vector<T> out(n);
+    qd_err e{};
+    Context& c = Context::current();
+    c.check(qd_revcomp(c.get(), QD_ENC_MASK, 0, reinterpret_cast<const uint8_t*>(dna), n, reinterpret_cast<uint8_t*>(out.data()), &e), e);
+    return out;
+}
+
+// ---- src/rust_api.rs ---------------------------------------------------------------------------------
+
+// src/rust_api.rs:77-161
+class ProteinSequence {
+  public:
+    ProteinSequence() = default;
+    explicit ProteinSequence(std::vector<uint8_t> aa) : amino_acids_(std::move(aa)) {}
+    // TryFrom<&[u8]> / FromStr, :132-161: ASCII only, upper-cased
+    static ProteinSequence from_str(std::string_view s) {
+        std::vector<uint8_t> v(s.begin(), s.end());
+        for (uint8_t& b : v) {
+            if (b >= 128) {
+                qd_err e{QD_ERR_NON_ASCII_BYTE, b, 0, 0};
+                char buf[96];
+                qd_err_message(&e, buf, sizeof buf);
+                throw TranslationError(e, buf);
+            }
+            if (b >= 'a' && b <= 'z') b = static_cast<uint8_t>(b - 32);
+        }
+        return ProteinSequence(std::move(v));
+    }
+    size_t len() const { return amino_acids_.size(); }
+    bool is_empty() const { return amino_acids_.empty(); }
+    const std::vector<uint8_t>& as_slice() const { return amino_acids_; }
+    void push(uint8_t aa) { amino_acids_.push_back(aa); }
+    uint8_t operator[](size_t i) const { return amino_acids_[i]; }
+    std::string to_string() const { return std::string(amino_acids_.begin(), amino_acids_.end()); }
+    bool operator==(const ProteinSequence& o) const { return amino_acids_ == o.amino_acids_; }
+    bool operator!=(const ProteinSequence& o) const { return !(*this == o); }
+    // :100-104 -- every length-`length` window as an owned sequence
+    std::vector<ProteinSequence> windows(size_t length) const {
+        std::vector<ProteinSequence> res;
+        if (length == 0 || amino_acids_.size() < length) return res;
+        const size_t count = amino_acids_.size() - length + 1;
+        std::vector<uint8_t> flat(count * length);
+        size_t got = 0;
+        Context& c = Context::current();
+        c.check(qd_windows(c.get(), amino_acids_.data(), amino_acids_.size(), length, flat.data(), &got), qd_err{});
+        res.reserve(got);
+        for (size_t i = 0; i < got; i++) res.emplace_back(std::vector<uint8_t>(flat.begin() + i * length, flat.begin() + (i + 1) * length));
+        return res;
+    }
+
+  private:
+    std::vector<uint8_t> amino_acids_;
+};
+
+// src/rust_api.rs:163-387
+template <class T>
+class DnaSequence {
+    static_assert(is_nucleotide_like<T> && sizeof(T) == 1);
+
+  public:
+    DnaSequence() = default;
+    explicit DnaSequence(std::vector<T> dna) : dna_(std::move(dna)) {}  // :210-212
+
+    // TryFrom<&[u8]> / FromStr, :310-338: ' ' and '\t' are skipped, everything else validated
+    static DnaSequence from_str(std::string_view s) {
+        std::vector<T> v(s.size());
+        size_t k = 0;
+        qd_err e{};
+        Context& c = Context::current();
+        c.check(qd_parse(c.get(), strict_of<T>, reinterpret_cast<const uint8_t*>(s.data()), s.size(), reinterpret_cast<uint8_t*>(v.data()), &k, &e), e);
+        v.resize(k);
+        return DnaSequence(std::move(v));
+    }
+
+    size_t len() const { return dna_.size(); }
+    bool is_empty() const { return dna_.empty(); }
+    const std::vector<T>& as_slice() const { return dna_; }
+    void push(T n) { dna_.push_back(n); }  // :281-283
+    T operator[](size_t i) const { return dna_[i]; }
+    bool operator==(const DnaSequence& o) const { return dna_ == o.dna_; }
+    bool operator!=(const DnaSequence& o) const { return !(*this == o); }
+    std::string to_string() const {  // Display, :301-308
+        std::string s(dna_.size(), '?');
+        for (size_t i = 0; i < dna_.size(); i++) s[i] = to_ascii(dna_[i]);
+        return s;
+    }
+
+    // :216-219
+    ProteinSequence translate(TranslationTable table) const { return ProteinSequence(translate_dna(table, dna_.data(), dna_.size())); }
+
+    // :227-255 -- 3 frames if len >= 5, 2 if len == 4, 1 if len == 3, else none
+    std::vector<ProteinSequence> translate_self_frames(TranslationTable table) const { return frames(table, QD_FRAMES_SELF); }
+    // :263-270 -- forward frames then the frames of the reverse complement; one pass over the input
+    std::vector<ProteinSequence> translate_all_frames(TranslationTable table) const { return frames(table, QD_FRAMES_ALL); }
+
+    // :273-275
+    DnaSequence reverse_complement() const { return DnaSequence(quickdna::reverse_complement(dna_.data(), dna_.size())); }
+
+    // :277-279
+    std::vector<DnaSequence> windows(size_t length) const {
+        std::vector<DnaSequence> res;
+        if (length == 0 || dna_.size() < length) return res;
+        const size_t count = dna_.size() - length + 1;
+        std::vector<uint8_t> flat(count * length);
+        size_t got = 0;
+        Context& c = Context::current();
+        c.check(qd_windows(c.get(), bytes(), dna_.size(), length, flat.data(), &got), qd_err{});
+        res.reserve(got);
+        for (size_t i = 0; i < got; i++) {
+            const T* w = reinterpret_cast<const T*>(flat.data() + i * length);
+            res.emplace_back(std::vector<T>(w, w + length));
+        }
+        return res;
+    }
+
+    // :374-377 (DnaSequence<Nucleotide> only): min_lex(fw(seq), fw(reverse(seq))) under A<T<C<G
+    template <class U = T, class = std::enable_if_t<std::is_same_v<U, Nucleotide>>>
+    DnaSequence canonical() const {
+        std::vector<T> out(dna_.size());
+        qd_err e{};
+        Context& c = Context::current();
+        c.check(qd_canonical(c.get(), QD_ENC_MASK, 0, bytes(), dna_.size(), reinterpret_cast<uint8_t*>(out.data()), &e), e);
+        return DnaSequence(std::move(out));
+    }
+
+    // :385-387 (DnaSequence<NucleotideAmbiguous> only): every concrete expansion, lexicographic, materialised.
+    // size_hint() of the reference is `expansion_count()`; UINT64_MAX == (usize::MAX, None).
+    template <class U = T, class = std::enable_if_t<std::is_same_v<U, NucleotideAmbiguous>>>
+    uint64_t expansion_count() const {
+        if (dna_.empty()) return 1;
+        uint64_t count = 0, index[2] = {0, 0};
+        qd_err e{};
+        Context& c = Context::current();
+        c.check(qd_expansion_windows(c.get(), QD_ENC_MASK, bytes(), 1, dna_.size(), 0, &count, index, nullptr, &e), e);
+        return count;
+    }
+    template <class U = T, class = std::enable_if_t<std::is_same_v<U, NucleotideAmbiguous>>>
+    std::vector<DnaSequence<Nucleotide>> expansions(uint64_t max_expansions = uint64_t(1) << 24) const {
+        std::vector<DnaSequence<Nucleotide>> res;
+        if (dna_.empty()) {  // one empty expansion (src/expansions.rs:37-58 on an empty slice)
+            res.emplace_back();
+            return res;
+        }
+        uint64_t count = 0, index[2] = {0, 0};
+        qd_err e{};
+        Context& c = Context::current();
+        c.check(qd_expansion_windows(c.get(), QD_ENC_MASK, bytes(), 1, dna_.size(), max_expansions, &count, index, nullptr, &e), e);
+        if (count > max_expansions) throw std::length_error("quickdna: more expansions than max_expansions");
+        std::vector<uint8_t> flat(static_cast<size_t>(count) * dna_.size());
+        c.check(qd_expansion_windows(c.get(), QD_ENC_MASK, bytes(), 1, dna_.size(), max_expansions, &count, index, flat.data(), &e), e);
+        res.reserve(count);
+        for (uint64_t i = 0; i < count; i++) {
+            const Nucleotide* w = reinterpret_cast<const Nucleotide*>(flat.data() + i * dna_.size());
+            res.emplace_back(std::vector<Nucleotide>(w, w + dna_.size()));
+        }
+        return res;
+    }
+
+  private:
+    const uint8_t* bytes() const { return reinterpret_cast<const uint8_t*>(dna_.data()); }
+    std::vector<ProteinSequence> frames(TranslationTable table, int which) const {
+        const size_t n = dna_.size();
+        size_t cap = 0;
+        for (int k = 0; k < 3; k++) cap += qd_frame_len(n, k);
+        std::vector<uint8_t> buf((which == QD_FRAMES_ALL ? 2 : 1) * cap + 1);
+        size_t lens[6] = {0, 0, 0, 0, 0, 0};
+        int n_frames = 0;
+        qd_err e{};
+        Context& c = Context::current();
+        c.check(qd_translate_frames(c.get(), static_cast<int>(table), QD_ENC_MASK, 0, which, bytes(), n, buf.data(), lens, &n_frames, &e), e);
+        std::vector<ProteinSequence> res;
+        size_t off = 0;
+        for (size_t l : lens)
+            if (l) {
+                res.emplace_back(std::vector<uint8_t>(buf.begin() + off, buf.begin() + off + l));
+                off += l;
+            }
+        return res;
+    }
+    std::vector<T> dna_;
+};
+
+using DnaSequenceStrict = DnaSequence<Nucleotide>;              // src/rust_api.rs:163
+using DnaSequenceAmbiguous = DnaSequence<NucleotideAmbiguous>;  // src/rust_api.rs:164
+
+}  // namespace quickdna

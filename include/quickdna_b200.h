@@ -152,12 +152,24 @@ int qd_translate_frames_batch_uniform(qd_ctx *ctx, int table, int enc, int stric
                                       const uint8_t *dna, size_t n_seq, size_t seq_len,
                                       uint8_t *out, qd_err *err);
 
+/* TryFrom<&[u8]> / FromStr for DnaSequence<T>: src/rust_api.rs:310-338.  ASCII in, one mask byte per kept
+ * nucleotide out: ' ' and '\t' are dropped, every other byte must be a nucleotide letter of the alphabet
+ * (strict != 0: Nucleotide, else NucleotideAmbiguous).  masks: capacity n; *n_masks = masks written.
+ * On error `pos` is the index of the offending byte in the INPUT. */
+int qd_parse(qd_ctx *ctx, int strict, const uint8_t *ascii, size_t n, uint8_t *masks, size_t *n_masks,
+             qd_err *err);
+
 /* DnaSequence::<Nucleotide>::canonical over every length-w window: src/canonical.rs:17-55,
  * 71-118, 129-179 applied as in benches/canonical.rs:29-34.  Strict alphabet only.
  * forward_only != 0 gives ForwardCanonical.  out: (n-w+1)*w bytes (0 windows if n < w),
  * window i at out + i*w, same encoding as the input (ASCII output upper case). 1 <= w <= 64. */
 int qd_canonical_windows(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna, size_t n,
                          size_t w, uint8_t *out, qd_err *err);
+
+/* DnaSequence::<Nucleotide>::canonical of ONE sequence of any length: src/rust_api.rs:374-377 over
+ * src/canonical.rs:17-55 (min_lex(fw(seq), fw(reverse(seq))), A<T<C<G).  out: n bytes, input encoding. */
+int qd_canonical(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna, size_t n, uint8_t *out,
+                 qd_err *err);
 
 /* DnaSequence::<NucleotideAmbiguous>::expansions over a batch of n_win windows of w nt each
  * (benches/expansions.rs:126-130 shape): src/expansions.rs:35-108.
@@ -167,7 +179,7 @@ int qd_canonical_windows(qd_ctx *ctx, int enc, int forward_only, const uint8_t *
  *                    benches/expansions.rs:57-66 does); out_index[n_win] = total expansions
  *   out            = expansions in iteration order, w bytes each (strict alphabet, input encoding)
  * Call with out == NULL to get counts / out_index only.  out capacity:
- * out_index[n_win]*w, at most n_win*max_expansions*w.  1 <= w <= 64. */
+ * out_index[n_win]*w, at most n_win*max_expansions*w.  w >= 1 (n_win = 1, w = n is DnaSequence::expansions()). */
 int qd_expansion_windows(qd_ctx *ctx, int enc, const uint8_t *windows, size_t n_win, size_t w,
                          uint64_t max_expansions, uint64_t *counts, uint64_t *out_index,
                          uint8_t *out, qd_err *err);
@@ -214,6 +226,11 @@ int qd_translate_frames_batch_uniform_dev(qd_ctx *ctx, int table, int enc, int s
 int qd_translate_frames_batch_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
                                   const uint8_t *dna_dev, const uint64_t *offsets_dev,
                                   size_t n_seq, size_t total_nt, uint8_t *out_dev, void *stream);
+/* n_masks_dev: device uint64 receiving the mask count (may be NULL) */
+int qd_parse_dev(qd_ctx *ctx, int strict, const uint8_t *ascii_dev, size_t n, uint8_t *masks_dev,
+                 uint64_t *n_masks_dev, void *stream);
+int qd_canonical_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev, size_t n,
+                     uint8_t *out_dev, void *stream);
 int qd_canonical_windows_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev,
                              size_t n, size_t w, uint8_t *out_dev, void *stream);
 int qd_windows_dev(qd_ctx *ctx, const uint8_t *seq_dev, size_t n, size_t w, uint8_t *out_dev,

@@ -94,6 +94,10 @@ SIGNATURES = {
     "qd_windows_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "qd_launch_count": (C.c_uint64, [_vp]),
     "qd_ctx_set_big_tile_min_runs": (C.c_int, [_vp, C.c_uint64]),
+    "qd_canonical": (_i, [_vp, _i, _i, _vp, _sz, _vp, C.POINTER(QdErr)]),
+    "qd_canonical_dev": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
+    "qd_parse": (_i, [_vp, _i, _vp, _sz, _vp, C.POINTER(_sz), C.POINTER(QdErr)]),
+    "qd_parse_dev": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -109,6 +109,29 @@ def translate_frames_batch(
     return FramesBatch(out[:total], out_offsets, np.diff(offsets), frames)
 
 
+def parse(ascii_seq, strict: bool = False, ctx: Optional[N.Context] = None) -> np.ndarray:
+    """ASCII -> masks, dropping ' ' and '\\t' (TryFrom<&[u8]> for DnaSequence<T>, src/rust_api.rs:310-322)."""
+    ctx = ctx or N.default_context()
+    a = _u8(ascii_seq)
+    out = np.empty(max(a.size, 1), dtype=np.uint8)
+    k = C.c_size_t()
+    err = N.QdErr()
+    rc = N.lib().qd_parse(ctx.handle, int(strict), _p(a if a.size else np.zeros(1, np.uint8)), a.size, _p(out), C.byref(k), C.byref(err))
+    ctx.check(rc, err)
+    return out[: k.value]
+
+
+def canonical(dna, forward_only: bool = False, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None) -> np.ndarray:
+    """DnaSequence::<Nucleotide>::canonical of one sequence of any length (src/rust_api.rs:374-377)."""
+    ctx = ctx or N.default_context()
+    a = _u8(dna)
+    out = np.empty(max(a.size, 1), dtype=np.uint8)
+    err = N.QdErr()
+    rc = N.lib().qd_canonical(ctx.handle, enc, int(forward_only), _p(a if a.size else np.zeros(1, np.uint8)), a.size, _p(out), C.byref(err))
+    ctx.check(rc, err)
+    return out[: a.size]
+
+
 def canonical_windows(dna, w: int = 42, forward_only: bool = False, enc: int = N.ENC_ASCII,
                       ctx: Optional[N.Context] = None) -> np.ndarray:
     """Every length-w window of a strict sequence, canonicalised (src/canonical.rs; benches/canonical.rs:29-34)."""
@@ -239,6 +262,21 @@ def translate_frames_csr_dev(dna, offsets, out=None, table: int = 1, strict: boo
                                                _stream_ptr(torch))
     ctx.check(rc)
     return out
+
+
+def parse_dev(ascii_seq, out=None, strict: bool = False, ctx: Optional[N.Context] = None):
+    """qd_parse_dev on a torch uint8 CUDA tensor: returns (masks buffer, device int64[1] count)."""
+    import torch
+
+    ctx = ctx or N.default_context(ascii_seq.device.index or 0)
+    n = ascii_seq.numel()
+    if out is None:
+        out = torch.empty(n + 16, dtype=torch.uint8, device=ascii_seq.device)
+    count = torch.zeros(1, dtype=torch.int64, device=ascii_seq.device)
+    rc = N.lib().qd_parse_dev(ctx.handle, int(strict), C.c_void_p(ascii_seq.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                              C.c_void_p(count.data_ptr()), _stream_ptr(torch))
+    ctx.check(rc)
+    return out, count
 
 
 def dev_error_reset(ctx: Optional[N.Context] = None):

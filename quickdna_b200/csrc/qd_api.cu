@@ -74,7 +74,7 @@ struct qd_ctx {
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
-    DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums;
+    DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums, parse_counts, parse_offsets, canon_state;
     Pipe pipe[N_PIPE];
     size_t chunk_bytes = size_t(256) << 20;  // input bytes per pipeline chunk
     int occ_frames[6] = {0, 0, 0, 0, 0, 0};  // [tile size][frames]
@@ -99,6 +99,8 @@ enum {
     TAB_MASK_TO_ASCII_STRICT,
     TAB_TO_MASK_ASCII,
     TAB_TO_MASK_MASK,
+    TAB_PARSE,
+    TAB_PARSE_STRICT,
     TAB_COUNT
 };
 
@@ -413,6 +415,8 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         put(TAB_MASK_TO_ASCII_STRICT, T.mask_to_ascii[1]);
         put(TAB_TO_MASK_ASCII, T.to_mask_ascii);
         put(TAB_TO_MASK_MASK, T.to_mask_mask);
+        put(TAB_PARSE, T.parse[0]);
+        put(TAB_PARSE_STRICT, T.parse[1]);
         ok &= cudaMemcpy(c->d_tables, tabs.data(), tabs.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_lut, T.folded.data(), T.folded.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -431,7 +435,8 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&c->in, &c->out, &c->aux0, &c->aux1, &c->aux2, &c->aux3, &c->run_prefix, &c->tile_first, &c->block_sums}) b->release();
+    for (DevBuf* b : {&c->in, &c->out, &c->aux0, &c->aux1, &c->aux2, &c->aux3, &c->run_prefix, &c->tile_first, &c->block_sums, &c->parse_counts,
+                      &c->parse_offsets, &c->canon_state}) b->release();
     for (int i = 0; i < N_PIPE; i++) {
         Pipe& P = c->pipe[i];
         for (DevBuf* b : {&P.in, &P.out, &P.offsets, &P.run_prefix, &P.tile_first, &P.block_sums}) b->release();
@@ -645,6 +650,121 @@ extern "C" int qd_canonical_windows_dev(qd_ctx* c, int enc, int forward_only, co
     std::lock_guard<std::mutex> g(c->mu);
     QD_CUDA(c, cudaSetDevice(c->device));
     return canonical_dev(c, enc, forward_only, dna_dev, n, w, out_dev, pick_stream(c, stream));
+}
+
+// src/rust_api.rs:310-322 on device buffers: counts per 4 KiB block, scan, compacted write.
+// n_masks_dev receives the number of masks written (device uint64).
+static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
+                     cudaStream_t s) {
+    if (n == 0) {
+        if (n_masks_dev) QD_CUDA(c, cudaMemsetAsync(n_masks_dev, 0, 8, s));
+        return QD_OK;
+    }
+    const uint64_t span = (reinterpret_cast<uintptr_t>(ascii_dev) & 15) + n;  // from the aligned start
+    const uint64_t n_blocks = (span + PARSE_BLOCK_BYTES - 1) / PARSE_BLOCK_BYTES;
+    QD_CUDA(c, c->parse_counts.reserve(n_blocks * 8));
+    QD_CUDA(c, c->parse_offsets.reserve((n_blocks + 1) * 8));
+    ParseParams p{};
+    p.in = ascii_dev;
+    p.n = n;
+    p.table = tab(c, strict ? TAB_PARSE_STRICT : TAB_PARSE);
+    p.counts = c->parse_counts.as<uint64_t>();
+    p.offsets = c->parse_offsets.as<uint64_t>();
+    p.out = masks_dev;
+    p.err_key = c->d_err;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)c->sm_count * 8);
+    parse_count_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    if (int rc = device_exclusive_scan<1>(c, p.counts, n_blocks, c->parse_offsets.as<uint64_t>(), c->block_sums, s)) return rc;
+    parse_write_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    if (n_masks_dev) QD_CUDA(c, cudaMemcpyAsync(n_masks_dev, c->parse_offsets.as<uint64_t>() + n_blocks, 8, cudaMemcpyDeviceToDevice, s));
+    return QD_OK;
+}
+
+extern "C" int qd_parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
+                            void* stream) {
+    if (!c || (n && (!ascii_dev || !masks_dev))) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return parse_dev(c, strict, ascii_dev, n, masks_dev, n_masks_dev, pick_stream(c, stream));
+}
+
+extern "C" int qd_parse(qd_ctx* c, int strict, const uint8_t* ascii, size_t n, uint8_t* masks, size_t* n_masks, qd_err* err) {
+    clear_err(err);
+    if (n_masks) *n_masks = 0;
+    if (!c || (n && (!ascii || !masks))) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(n + 16));
+    QD_CUDA(c, c->aux0.reserve(8));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, ascii, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    if (int rc = parse_dev(c, strict, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), c->aux0.as<uint64_t>(), s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->aux0.p, 8, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
+    if (key != NO_ERROR_KEY) return report_single(QD_ENC_ASCII, strict, ascii, key, err);
+    const size_t k = (size_t)c->h_scratch[0];
+    QD_CUDA(c, cudaMemcpyAsync(masks, c->out.p, k, cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    if (n_masks) *n_masks = k;
+    return QD_OK;
+}
+
+static int canonical_seq_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, cudaStream_t s) {
+    if (n == 0) return QD_OK;
+    QD_CUDA(c, c->canon_state.reserve(9 * 8));
+    unsigned long long* st = c->canon_state.as<unsigned long long>();
+    QD_CUDA(c, cudaMemsetAsync(st, 0xff, 9 * 8, s));
+    QD_CUDA(c, cudaMemsetAsync(st + 4, 0, 4 * 8, s));
+    CanonSeqParams p{};
+    p.dna = dna_dev;
+    p.n = n;
+    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
+    p.forward_only = forward_only;
+    p.state = st;
+    p.out = out_dev;
+    p.err_key = c->d_err;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8));
+    canon_seq_scan_kernel<<<grid, 256, 0, s>>>(p);
+    if (!forward_only) canon_seq_diff_kernel<<<grid, 256, 0, s>>>(p);
+    canon_seq_write_kernel<<<grid, 256, 0, s>>>(p);
+    c->launches += forward_only ? 2 : 3;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, void* stream) {
+    if (!c || (n && (!dna_dev || !out_dev))) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return canonical_seq_dev(c, enc, forward_only, dna_dev, n, out_dev, pick_stream(c, stream));
+}
+
+extern "C" int qd_canonical(qd_ctx* c, int enc, int forward_only, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
+    clear_err(err);
+    if (!c || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(n + 16));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    if (int rc = canonical_seq_dev(c, enc, forward_only, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, n, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;
+    if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+    return QD_OK;
 }
 
 static int windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, uint8_t* out_dev, cudaStream_t s) {
@@ -871,7 +991,7 @@ extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const 
 extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, size_t n_win, size_t w, uint64_t max_expansions,
                                     uint64_t* counts, uint64_t* out_index, uint8_t* out, qd_err* err) {
     clear_err(err);
-    if (!c || w < 1 || w > 64) return QD_ERR_INVALID_ARGUMENT;
+    if (!c || w < 1 || w > 0xffffffffull) return QD_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(c->mu);
     QD_CUDA(c, cudaSetDevice(c->device));
     if (n_win == 0) {

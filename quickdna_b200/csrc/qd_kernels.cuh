@@ -980,4 +980,210 @@ __global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ASCII -> typed parse (src/rust_api.rs:310-322): drop ' ' and '\t', validate every other byte, emit one mask per
+// kept byte.  Stream compaction in two passes over the input: kept-byte counts per 4 KiB block -> device scan ->
+// compacted, coalesced write.
+// ------------------------------------------------------------------------------------------------
+constexpr int PARSE_THREADS = 256;
+constexpr int PARSE_BLOCK_BYTES = PARSE_THREADS * 16;  // one aligned 16-byte granule per thread
+constexpr uint32_t PARSE_SKIP = 0x80;                  // table value of ' ' and '\t' (0 = invalid, else the mask)
+
+struct ParseParams {
+    const uint8_t* in;
+    uint64_t n;
+    const uint8_t* table;        // 256 bytes: mask | PARSE_SKIP | 0
+    uint64_t* counts;            // kept bytes per block (pass 1 out)
+    const uint64_t* offsets;     // exclusive scan of counts, [n_blocks + 1] (pass 2 in)
+    uint8_t* out;
+    unsigned long long* err_key;
+};
+
+// granule `g` (16 bytes at the 16-byte-aligned address a) of the input as table values; bytes outside [in, in+n) skip
+__device__ __forceinline__ void parse_load(const ParseParams& p, const uint8_t* tab_s, uint64_t g, uint8_t (&v)[16], uint32_t& kept,
+                                           int& first_bad) {
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.in), hi = lo + p.n;
+    const uintptr_t a = (lo & ~(uintptr_t)15) + 16 * g;
+    uint32_t w[4];
+    if (a >= lo && a + 16 <= hi) {
+        const uint4 x = ldg_stream(reinterpret_cast<const void*>(a));
+        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uintptr_t b = a + 4 * q + k;
+                x |= ((b >= lo && b < hi) ? (uint32_t)*reinterpret_cast<const uint8_t*>(b) : 0x20u) << (8 * k);  // ' ' = skipped
+            }
+            w[q] = x;
+        }
+    }
+    kept = 0;
+    first_bad = -1;
+#pragma unroll
+    for (int k = 15; k >= 0; k--) {
+        const uint32_t t = tab_s[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+        v[k] = (uint8_t)t;
+        if (t == 0) first_bad = k;
+        kept += (t != 0 && t != PARSE_SKIP) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS) parse_count_kernel(const ParseParams p, uint64_t n_blocks) {
+    __shared__ uint8_t tab_s[256];
+    __shared__ uint64_t warp_sums[32];
+    tab_s[threadIdx.x] = __ldg(p.table + threadIdx.x);
+    __syncthreads();
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.in);
+    for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        uint8_t v[16];
+        uint32_t kept;
+        int bad;
+        const uint64_t g = blk * PARSE_THREADS + threadIdx.x;
+        parse_load(p, tab_s, g, v, kept, bad);
+        if (bad >= 0) atomicMin(p.err_key, (unsigned long long)(((lo & ~(uintptr_t)15) + 16 * g + bad) - lo));
+        uint64_t total;
+        block_exclusive_scan((uint64_t)kept, &total, warp_sums);
+        if (threadIdx.x == 0) p.counts[blk] = total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseParams p, uint64_t n_blocks) {
+    __shared__ uint8_t tab_s[256];
+    __shared__ uint64_t warp_sums[32];
+    __shared__ __align__(16) uint8_t stage[PARSE_BLOCK_BYTES + 16];
+    tab_s[threadIdx.x] = __ldg(p.table + threadIdx.x);
+    __syncthreads();
+    for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        uint8_t v[16];
+        uint32_t kept;
+        int bad;
+        parse_load(p, tab_s, blk * PARSE_THREADS + threadIdx.x, v, kept, bad);
+        uint64_t total;
+        const uint32_t off = (uint32_t)block_exclusive_scan((uint64_t)kept, &total, warp_sums);
+        const uint64_t out0 = p.offsets[blk];
+        uint8_t* gdst = p.out + out0;
+        const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
+        uint32_t at = phase + off;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (v[k] != 0 && v[k] != PARSE_SKIP) stage[at++] = v[k];
+        __syncthreads();
+        const uint32_t nbytes = (uint32_t)total;
+        const uint32_t head = min(nbytes, (16u - phase) & 15u);
+        const uint32_t body = (nbytes - head) >> 4;
+        if (threadIdx.x < head) gdst[threadIdx.x] = stage[phase + threadIdx.x];
+        for (uint32_t c = threadIdx.x; c < body; c += PARSE_THREADS)
+            stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(stage + phase + head + 16 * c));
+        const uint32_t done = head + 16 * body;
+        if (threadIdx.x < nbytes - done) gdst[done + threadIdx.x] = stage[phase + done + threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Canonical form of ONE sequence of any length (DnaSequence::canonical, src/rust_api.rs:374-377;
+// src/canonical.rs:17-55, 71-118, 129-179).  ForwardCanonical relabels bases by first occurrence, so the forward map
+// is fixed by the FIRST index of each base and the map of the reversed sequence by the LAST index of each base:
+//   pass 1  first / last occurrence of each base (+ strict validation)          -> state[0..7]
+//   pass 2  first i with fw[x[i]] != rv[x[n-1-i]] (LexicalMin decides there)     -> state[8]
+//   pass 3  write the winner
+// state: [0..3] first index of code c (~0 = absent), [4..7] last index + 1 (0 = absent), [8] first difference (~0 = none)
+// ------------------------------------------------------------------------------------------------
+struct CanonSeqParams {
+    const uint8_t* dna;
+    uint64_t n;
+    const uint8_t* decode;  // 256-byte table -> internal code (0..3 concrete)
+    uint32_t letters;       // output byte of A,T,C,G packed little-endian
+    int forward_only;
+    unsigned long long* state;  // 9 x u64
+    uint8_t* out;
+    unsigned long long* err_key;
+};
+
+__global__ void __launch_bounds__(256) canon_seq_scan_kernel(const CanonSeqParams p) {
+    unsigned long long first[4] = {~0ull, ~0ull, ~0ull, ~0ull}, last1[4] = {0, 0, 0, 0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = __ldg(p.decode + __ldg(p.dna + i));
+        if (c > 3) {
+            atomicMin(p.err_key, (unsigned long long)i);
+            continue;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (c == (uint32_t)b) {
+                first[b] = min(first[b], (unsigned long long)i);
+                last1[b] = max(last1[b], (unsigned long long)i + 1);
+            }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            first[b] = min(first[b], __shfl_xor_sync(0xffffffffu, first[b], o));
+            last1[b] = max(last1[b], __shfl_xor_sync(0xffffffffu, last1[b], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (first[b] != ~0ull) atomicMin(p.state + b, first[b]);
+            if (last1[b] != 0) atomicMax(p.state + 4 + b, last1[b]);
+        }
+    }
+}
+
+// relabelling maps (2 bits per code) from the occurrence indices: forward = rank by first index, reverse = rank by
+// descending last index; absent bases get rank 3 (never used)
+__device__ __forceinline__ void canon_seq_maps(const unsigned long long* state, uint32_t& fw, uint32_t& rv) {
+    unsigned long long f[4], l[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        f[b] = state[b];
+        l[b] = state[4 + b];
+    }
+    fw = 0;
+    rv = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        uint32_t rf = 0, rr = 0;
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            rf += (o != b && f[o] < f[b]) ? 1u : 0u;
+            rr += (o != b && l[o] > l[b]) ? 1u : 0u;
+        }
+        fw |= (f[b] == ~0ull ? 3u : rf) << (2 * b);
+        rv |= (l[b] == 0 ? 3u : rr) << (2 * b);
+    }
+}
+
+__global__ void __launch_bounds__(256) canon_seq_diff_kernel(const CanonSeqParams p) {
+    uint32_t fw, rv;
+    canon_seq_maps(p.state, fw, rv);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (i >= *reinterpret_cast<volatile unsigned long long*>(p.state + 8)) return;  // a smaller difference is known
+        const uint32_t a = __ldg(p.decode + __ldg(p.dna + i)) & 3u, b = __ldg(p.decode + __ldg(p.dna + (p.n - 1 - i))) & 3u;
+        if (((fw >> (2 * a)) & 3u) != ((rv >> (2 * b)) & 3u)) {
+            atomicMin(p.state + 8, (unsigned long long)i);
+            return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) canon_seq_write_kernel(const CanonSeqParams p) {
+    uint32_t fw, rv;
+    canon_seq_maps(p.state, fw, rv);
+    bool use_rev = false;
+    const unsigned long long d = p.state[8];
+    if (!p.forward_only && d != ~0ull) {
+        const uint32_t a = __ldg(p.decode + __ldg(p.dna + d)) & 3u, b = __ldg(p.decode + __ldg(p.dna + (p.n - 1 - d))) & 3u;
+        use_rev = ((rv >> (2 * b)) & 3u) < ((fw >> (2 * a)) & 3u);
+    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = __ldg(p.decode + __ldg(p.dna + (use_rev ? p.n - 1 - i : i))) & 3u;
+        const uint32_t y = ((use_rev ? rv : fw) >> (2 * c)) & 3u;
+        p.out[i] = (uint8_t)(p.letters >> (8 * y));
+    }
+}
+
 }  // namespace qd

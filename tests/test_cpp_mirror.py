@@ -1,0 +1,27 @@
+"""Runs the C++ mirror of the reference's Rust API (include/quickdna.hpp) against the reference's own
+Rust unit-test vectors, through the C ABI, on the GPU.  The binary is built by __graft_entry__.build()."""
+
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "test_rust_api_mirror")
+
+
+def test_mirror_binary_is_built():
+    import __graft_entry__ as g
+
+    g.build()
+    assert os.path.exists(BIN)
+
+
+@pytest.mark.gpu
+def test_rust_api_mirror_on_gpu():
+    import __graft_entry__ as g
+
+    g.build()
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout

@@ -348,6 +348,61 @@ def test_batch_chunked_pipeline_and_error_index(B, N, tiles):
         N.lib().qd_ctx_set_chunk_bytes(ctx.handle, 256 << 20)
 
 
+# ------------------------------------------------------------------ parse (src/rust_api.rs:310-322)
+
+
+def test_parse_vectors(B):
+    # accepted alphabet, case folding, space / tab skipping (src/rust_api.rs:421-457)
+    for text in ("", " ", "\t \t", "ACGT", "a c\tg t", "aAtTcCgGmMrRwWsSyYkKvVhHdDbBnN", " A", "A ", "AC GT" * 100):
+        got = B.parse(text.encode())
+        assert got.tobytes() == oracle.parse(text.encode()).tobytes(), text
+    assert B.parse(b"acgt ACGT", strict=True).tobytes() == bytes([1, 4, 8, 2, 1, 4, 8, 2])
+    for text, strict, kind, byte, pos in (("ABCD", True, 3, ord("B"), 1), ("AAAelephant", False, 2, ord("e"), 3),
+                                          ("AA\xc4\x8dCCG", False, 1, 0xC4, 2), ("AC\nGT", False, 2, 10, 2),
+                                          ("  \t- ", False, 2, ord("-"), 3)):
+        with pytest.raises(ValueError) as ei:
+            B.parse(text.encode("latin-1"), strict=strict)
+        assert (ei.value.kind, ei.value.byte, ei.value.pos) == (kind, byte, pos), text
+
+
+def test_parse_random(B):
+    rng = np.random.default_rng(21)
+    for trial in range(60):
+        n = int(rng.integers(0, 40000))
+        alphabet = b"ACGTacgt" if trial % 3 == 0 else IUPAC
+        a = np.frombuffer(_rand(rng, n, alphabet + b" \t" * int(rng.integers(0, 4))), dtype=np.uint8).copy()
+        strict = trial % 3 == 0
+        lead = int(rng.integers(0, 16))  # exercise every input alignment
+        buf = np.zeros(n + lead, dtype=np.uint8)
+        buf[lead:] = a
+        assert B.parse(buf[lead:], strict=strict).tobytes() == oracle.parse(a.tobytes(), strict=strict).tobytes(), trial
+        if n and trial % 2:
+            a[int(rng.integers(0, n))] = int(rng.choice(list(b"qZ-\n\x00\xff*")))
+            try:
+                oracle.parse(a.tobytes(), strict=strict)
+                raise AssertionError("oracle accepted a bad byte")
+            except oracle.OracleError as e:
+                with pytest.raises(ValueError) as ei:
+                    B.parse(a, strict=strict)
+                assert (ei.value.kind, ei.value.byte, ei.value.pos, str(ei.value)) == (e.kind, e.byte, e.pos, str(e))
+
+
+def test_parse_large_device(B, N):
+    import torch
+
+    n = 64_000_001
+    rng = np.random.default_rng(22)
+    a = np.frombuffer(b"ACGTNRY \t", dtype=np.uint8)[rng.integers(0, 9, n)]
+    x = torch.from_numpy(a).cuda()
+    B.dev_error_reset()
+    out, count = B.parse_dev(x)
+    assert B.dev_error_fetch(x) is None
+    want = oracle.parse(a.tobytes())
+    k = int(count.item())
+    assert k == want.size
+    assert out[:k].cpu().numpy().tobytes() == want.tobytes()
+
+
 # ------------------------------------------------------------------ windows / canonical / expansions
 
 
@@ -355,6 +410,30 @@ def test_batch_chunked_pipeline_and_error_index(B, N, tiles):
 def test_canonical_vectors(B, dna, canon):
     got = B.canonical_windows(dna.encode(), w=len(dna))
     assert got.shape == (1, len(dna)) and got[0].tobytes() == canon.encode()
+
+
+def test_canonical_whole_sequence(B):
+    # all inputs of length <= 3 (src/canonical.rs:216-404 enumerates them) and random longer ones, both variants
+    for n in range(0, 4):
+        for tup in itertools.product(b"ATCG", repeat=n):
+            s = bytes(tup)
+            m = oracle.masks_of(s) if n else np.zeros(0, np.uint8)
+            assert B.canonical(s).tobytes() == (oracle.ascii_of(oracle.canonical(m)) if n else b"")
+            assert B.canonical(s, forward_only=True).tobytes() == (oracle.ascii_of(oracle.forward_canonical(m)) if n else b"")
+    rng = np.random.default_rng(31)
+    for trial in range(80):
+        n = int(rng.integers(1, 200)) if trial < 50 else int(rng.integers(1000, 300000))
+        alphabet = [b"ACGT", b"AC", b"A", b"ACGTacgt", b"GT"][trial % 5]
+        s = _rand(rng, n, alphabet)
+        if trial % 7 == 0:  # palindromic under relabelling: the difference search runs to the end
+            s = s + s[::-1]
+        m = oracle.masks_of(s)
+        assert B.canonical(s).tobytes() == oracle.ascii_of(oracle.canonical(m)), trial
+        assert B.canonical(m, enc=1).tobytes() == oracle.canonical(m).tobytes(), trial
+        assert B.canonical(s, forward_only=True).tobytes() == oracle.ascii_of(oracle.forward_canonical(m)), trial
+    with pytest.raises(ValueError) as ei:
+        B.canonical(b"ACGTNACGT")
+    assert (ei.value.kind, ei.value.byte, ei.value.pos) == (3, ord("N"), 4)
 
 
 def test_canonical_windows_random(B):
