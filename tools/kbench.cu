@@ -160,6 +160,37 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
         printf("revcomp  thr %d unroll %d occ %d grid %u  %zu nt  %.4f ms  %.1f GB/s algorithmic  checksum %016llx\n", RCT, RC_UNROLL, occ_rc, g2, n_rc, ms, 2.0 * n_rc / ms / 1e6, acc);
     }
+    // canonical windows (w = 42) over one long sequence: n_cw windows, 42 bytes each
+    {
+        const size_t n_cw = std::min<size_t>(total, 40000000), w = 42, nwin = n_cw - w + 1;
+        if (out_bytes >= nwin * w) {
+            CanonParams q{};
+            q.dna = dna;
+            q.n = n_cw;
+            q.w = (uint32_t)w;
+            q.forward_only = 0;
+            q.out = out;
+            q.decode = d_decode;
+            q.letters = 'A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24);
+            q.err_key = d_err;
+            const size_t smem_c = ((CANON_THREADS + CANON_MAX_W + 15) & ~15) + 16 + (size_t)CANON_THREADS * w;
+            const uint64_t blocks = (nwin + CANON_THREADS - 1) / CANON_THREADS;
+            const unsigned gc = (unsigned)std::min<uint64_t>(blocks, (uint64_t)sms * 16);
+            canonical_windows_kernel<<<gc, CANON_THREADS, smem_c>>>(q);
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(e0));
+            for (int i = 0; i < 3; i++) canonical_windows_kernel<<<gc, CANON_THREADS, smem_c>>>(q);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            ms /= 3;
+            CK(cudaMemset(d_acc, 0, 8));
+            xorsum_kernel<<<sms * 8, 256>>>((const uint32_t*)out, nwin * w / 4, d_acc);
+            CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
+            printf("canonical_windows w=42  %zu windows  %.3f ms  %.1f GB/s algorithmic (43 B/window)  %.2f Gwin/s  checksum %016llx\n", nwin, ms,
+                   nwin * 43.0 / ms / 1e6, nwin / (double)ms / 1e6, acc);
+        }
+    }
     CK(cudaDeviceSynchronize());
     return 0;
 }
