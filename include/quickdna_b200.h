@@ -233,6 +233,10 @@ int qd_canonical_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_
                      uint8_t *out_dev, void *stream);
 int qd_canonical_windows_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev,
                              size_t n, size_t w, uint8_t *out_dev, void *stream);
+/* the same over n_seq sequences of seq_len nucleotides each (benches/canonical.rs shape scaled up): windows never
+ * span two sequences; out holds n_seq * (seq_len - w + 1) windows of w bytes, tightly packed */
+int qd_canonical_windows_batch_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev,
+                                   size_t n_seq, size_t seq_len, size_t w, uint8_t *out_dev, void *stream);
 int qd_windows_dev(qd_ctx *ctx, const uint8_t *seq_dev, size_t n, size_t w, uint8_t *out_dev,
                    void *stream);
 

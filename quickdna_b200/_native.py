@@ -96,6 +96,7 @@ SIGNATURES = {
     "qd_ctx_set_big_tile_min_runs": (C.c_int, [_vp, C.c_uint64]),
     "qd_canonical": (_i, [_vp, _i, _i, _vp, _sz, _vp, C.POINTER(QdErr)]),
     "qd_canonical_dev": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
+    "qd_canonical_windows_batch_dev": (_i, [_vp, _i, _i, _vp, _sz, _sz, _sz, _vp, _vp]),
     "qd_parse": (_i, [_vp, _i, _vp, _sz, _vp, C.POINTER(_sz), C.POINTER(QdErr)]),
     "qd_parse_dev": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _vp]),
 }

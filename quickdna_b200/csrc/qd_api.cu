@@ -622,26 +622,48 @@ extern "C" int qd_translate_frames_batch_dev(qd_ctx* c, int table, int enc, int 
                           c->block_sums, out_dev, pick_stream(c, stream));
 }
 
-static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, size_t w, uint8_t* out_dev,
-                         cudaStream_t s) {
+template <int NW>
+static int launch_canonical_windows(qd_ctx* c, const CanonParams& p, cudaStream_t s) {
+    auto kern = canonical_windows_kernel<NW>;
+    const size_t smem = 2 * (((size_t)CANON_THREADS * p.w + 127) & ~(size_t)127) + CANON_CODE_WORDS * 4 + 256 + 16;
+    QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t tiles = (p.n_seq * (p.seq_len - p.w + 1) + CANON_THREADS - 1) / CANON_THREADS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 6);
+    kern<<<grid, CANON_THREADS, smem, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+// every length-w window of each of n_seq sequences of seq_len nucleotides (n_seq = 1: one sequence)
+static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
+                         uint8_t* out_dev, cudaStream_t s) {
     if (w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
-    if (n < w) return QD_OK;
+    if (seq_len < w || n_seq == 0) return QD_OK;
     CanonParams p{};
     p.dna = dna_dev;
-    p.n = n;
+    p.n_seq = n_seq;
+    p.seq_len = seq_len;
     p.w = (uint32_t)w;
     p.forward_only = forward_only;
     p.out = out_dev;
     p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
     p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
     p.err_key = c->d_err;
-    const size_t smem = ((CANON_THREADS + CANON_MAX_W + 15) & ~15) + 16 + (size_t)CANON_THREADS * w;
-    const uint64_t blocks = ((n - w + 1) + CANON_THREADS - 1) / CANON_THREADS;
-    const unsigned grid = (unsigned)std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 16);
-    canonical_windows_kernel<<<grid, CANON_THREADS, smem, s>>>(p);
-    c->launches++;
-    QD_CUDA(c, cudaGetLastError());
-    return QD_OK;
+    switch ((2 * w + 31) / 32) {
+        case 1: return launch_canonical_windows<1>(c, p, s);
+        case 2: return launch_canonical_windows<2>(c, p, s);
+        case 3: return launch_canonical_windows<3>(c, p, s);
+        default: return launch_canonical_windows<4>(c, p, s);
+    }
+}
+
+extern "C" int qd_canonical_windows_batch_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len,
+                                              size_t w, uint8_t* out_dev, void* stream) {
+    if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return canonical_dev(c, enc, forward_only, dna_dev, n_seq, seq_len, w, out_dev, pick_stream(c, stream));
 }
 
 extern "C" int qd_canonical_windows_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, size_t w,
@@ -649,7 +671,7 @@ extern "C" int qd_canonical_windows_dev(qd_ctx* c, int enc, int forward_only, co
     if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(c->mu);
     QD_CUDA(c, cudaSetDevice(c->device));
-    return canonical_dev(c, enc, forward_only, dna_dev, n, w, out_dev, pick_stream(c, stream));
+    return canonical_dev(c, enc, forward_only, dna_dev, 1, n, w, out_dev, pick_stream(c, stream));
 }
 
 // src/rust_api.rs:310-322 on device buffers: counts per 4 KiB block, scan, compacted write.
@@ -980,7 +1002,7 @@ extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const 
     QD_CUDA(c, c->out.reserve(out_bytes + 16));
     QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
     if (int rc = reset_err_key(c, s)) return rc;
-    if (int rc = canonical_dev(c, enc, forward_only, c->in.as<uint8_t>(), n, w, c->out.as<uint8_t>(), s)) return rc;
+    if (int rc = canonical_dev(c, enc, forward_only, c->in.as<uint8_t>(), 1, n, w, c->out.as<uint8_t>(), s)) return rc;
     QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;

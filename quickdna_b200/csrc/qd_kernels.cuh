@@ -699,99 +699,248 @@ __global__ void origin_kernel(uint64_t* __restrict__ out, uint64_t count, int ki
 
 // ------------------------------------------------------------------------------------------------
 // Canonical windows (strict alphabet): per window, min_lex(fw(window), fw(reverse(window)))
+// (src/canonical.rs:17-55, 71-118, 129-179 applied per window as benches/canonical.rs:29-34 does).
+//
+// Bit-parallel: a window is w 2-bit codes (A,T,C,G = 0..3, the reference's order) in NW 32-bit words, nucleotide j at
+// bits 2j.  Relabelling by first occurrence sends the first three distinct codes c0, c1, c2 (and the fourth, which is
+// c0^c1^c2) to 0, 1, 2, 3.  Every permutation of {0..3} is AFFINE over GF(2)^2, so the relabelling is
+// y = M (x ^ c0) with a 2x2 bit matrix built from u = c0^c1, v = c0^c2 -- three LOP3 per word on the packed window
+// instead of a loop over nucleotides.  The reversed window goes through the same code after a 2-bit-group reversal.
+// Output bytes are produced 4 at a time (PRMT through a 4-letter register), staged in shared memory in output order
+// and written by one TMA bulk store per tile.
 // ------------------------------------------------------------------------------------------------
 struct CanonParams {
-    const uint8_t* dna;
-    uint64_t n;
+    const uint8_t* dna;      // n_seq sequences of seq_len nucleotides, back to back
+    uint64_t n_seq;
+    uint64_t seq_len;
     uint32_t w;
     int forward_only;
-    uint8_t* out;            // n_windows * w bytes, 16-byte aligned
+    uint8_t* out;            // n_seq * (seq_len - w + 1) windows, w bytes each, tightly packed, 16-byte aligned
     const uint8_t* decode;   // 256-byte table -> internal code (0..3 concrete)
     uint32_t letters;        // output byte of codes 0..3 packed little-endian (ASCII "ATCG" or masks 1,2,4,8)
     unsigned long long* err_key;
 };
 
-constexpr int CANON_THREADS = 128;  // windows per CTA
+constexpr int CANON_THREADS = 256;  // windows per tile (a multiple of 16: tile outputs stay 16-byte aligned)
 constexpr int CANON_MAX_W = 64;
+constexpr int CANON_CODE_WORDS = (CANON_THREADS * CANON_MAX_W) / 16 + 8;  // packed codes of the widest possible tile span
 
-// Relabel by first occurrence (src/canonical.rs:95-118) on 2-bit codes held in two 64-bit words
-// (nucleotide j at bits 2j of lo for j < 32, of hi otherwise).
-__device__ __forceinline__ void fw_canon_packed(uint64_t lo, uint64_t hi, uint32_t w, uint64_t& olo, uint64_t& ohi) {
-    uint32_t perm = 0, seen = 0, next = 0;
-    olo = 0; ohi = 0;
-    for (uint32_t j = 0; j < w; j++) {
-        const uint32_t x = (uint32_t)(((j < 32) ? (lo >> (2 * j)) : (hi >> (2 * (j - 32)))) & 3u);
-        if (!((seen >> x) & 1u)) {
-            seen |= 1u << x;
-            perm |= next << (2 * x);
-            next++;
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// first word (ascending) of m[] that is non-zero, with the matching word of x[]; returns false if all are zero
+template <int NW>
+__device__ __forceinline__ bool first_nonzero(const uint32_t (&m)[NW], const uint32_t (&x)[NW], uint32_t& msel, uint32_t& xsel) {
+    msel = m[NW - 1];
+    xsel = x[NW - 1];
+#pragma unroll
+    for (int k = NW - 2; k >= 0; k--)
+        if (m[k]) {
+            msel = m[k];
+            xsel = x[k];
         }
-        const uint64_t y = (perm >> (2 * x)) & 3u;
-        if (j < 32) olo |= y << (2 * j); else ohi |= y << (2 * (j - 32));
-    }
+    return msel != 0;
 }
 
-__global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const CanonParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: codes[CANON_THREADS + CANON_MAX_W] | stage[16 + CANON_THREADS * w]
-    uint8_t* codes = smem_raw;
-    uint8_t* stage = smem_raw + ((CANON_THREADS + CANON_MAX_W + 15) & ~15);
-    const int tid = threadIdx.x;
-    const uint32_t w = p.w;
-    const uint64_t n_windows = p.n - w + 1;
-    for (uint64_t blk = blockIdx.x; blk * CANON_THREADS < n_windows; blk += gridDim.x) {
-        const uint64_t i0 = blk * CANON_THREADS;
-        const uint32_t nwin = (uint32_t)min((uint64_t)CANON_THREADS, n_windows - i0);
-        const uint32_t nnt = nwin + w - 1;
-        __syncthreads();
-        for (uint32_t t = tid; t < nnt; t += CANON_THREADS) {
-            const uint32_t c = __ldg(p.decode + __ldg(p.dna + i0 + t));
-            if (c > 3) atomicMin(p.err_key, (unsigned long long)(i0 + t));
-            codes[t] = (uint8_t)(c & 3u);
-        }
-        __syncthreads();
-        const uint64_t out0 = i0 * w;                 // byte offset of this block's first window
-        const uint32_t phase = (uint32_t)(out0 & 15u);  // stage mirrors the output's 16-byte phase
-        if (tid < (int)nwin) {
-            uint64_t lo = 0, hi = 0, rlo = 0, rhi = 0;
-            for (uint32_t j = 0; j < w; j++) {
-                const uint64_t x = codes[tid + j];
-                if (j < 32) lo |= x << (2 * j); else hi |= x << (2 * (j - 32));
-                const uint32_t jr = w - 1 - j;
-                if (jr < 32) rlo |= x << (2 * jr); else rhi |= x << (2 * (jr - 32));
-            }
-            uint64_t flo, fhi;
-            fw_canon_packed(lo, hi, w, flo, fhi);
-            if (!p.forward_only) {
-                uint64_t glo, ghi;
-                fw_canon_packed(rlo, rhi, w, glo, ghi);
-                // lexical order, first nucleotide most significant, under A<T<C<G == code order
-                bool rev_less = false;
-                for (uint32_t j = 0; j < w; j++) {
-                    const uint32_t a = (uint32_t)(((j < 32) ? (flo >> (2 * j)) : (fhi >> (2 * (j - 32)))) & 3u);
-                    const uint32_t b = (uint32_t)(((j < 32) ? (glo >> (2 * j)) : (ghi >> (2 * (j - 32)))) & 3u);
-                    if (a != b) { rev_less = b < a; break; }
-                }
-                if (rev_less) { flo = glo; fhi = ghi; }
-            }
-            uint8_t* dst = stage + phase + (size_t)tid * w;
-            for (uint32_t j = 0; j < w; j++) {
-                const uint32_t y = (uint32_t)(((j < 32) ? (flo >> (2 * j)) : (fhi >> (2 * (j - 32)))) & 3u);
-                dst[j] = (uint8_t)(p.letters >> (8 * y));
-            }
-        }
-        __syncthreads();
-        // coalesced copy-out: head bytes to the first 16-byte boundary, aligned uint4 body, tail bytes
-        const uint32_t nbytes = nwin * w;
-        uint8_t* gdst = p.out + out0;
-        const uint32_t head = min(nbytes, (16u - phase) & 15u);
-        const uint32_t body = (nbytes - head) >> 4;
-        if (tid < (int)head) gdst[tid] = stage[phase + tid];
-        for (uint32_t c = tid; c < body; c += CANON_THREADS)
-            stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(stage + phase + head + 16 * c));
-        const uint32_t done = head + 16 * body;
-        if (tid < (int)(nbytes - done)) gdst[done + tid] = stage[phase + done + tid];
+// fw(x): relabel the packed window by first occurrence.  V[k] = 0x55555555 restricted to the window's positions.
+template <int NW>
+__device__ __forceinline__ void forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW]) {
+    const uint32_t c0 = x[0] & 3u;
+    const uint32_t C0 = c0 * 0x55555555u;
+    uint32_t ne1[NW], msel, xsel;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t e = x[k] ^ C0;
+        ne1[k] = (e | (e >> 1)) & V[k];  // positions whose code differs from c0
     }
+    uint32_t u = 1u, v = 2u;  // a window with one base: any invertible map sending c0 to 0
+    if (first_nonzero<NW>(ne1, x, msel, xsel)) {
+        const uint32_t c1 = (xsel >> (__ffs(msel) - 1)) & 3u;
+        u = c0 ^ c1;
+        v = u == 1u ? 2u : 1u;  // two bases: any v that keeps the map invertible
+        const uint32_t C1 = c1 * 0x55555555u;
+        uint32_t ne2[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const uint32_t e = x[k] ^ C1;
+            ne2[k] = ne1[k] & (e | (e >> 1));  // ... and from c1
+        }
+        if (first_nonzero<NW>(ne2, x, msel, xsel)) v = c0 ^ ((xsel >> (__ffs(msel) - 1)) & 3u);
+    }
+    // k = M^-1 (x ^ c0), M = [u v] as columns:  k0 = v1 z0 ^ v0 z1,  k1 = u1 z0 ^ u0 z1   (z = x ^ c0)
+    const uint32_t v0 = v & 1u, v1 = v >> 1, u0 = u & 1u, u1 = u >> 1, c00 = c0 & 1u, c01 = c0 >> 1;
+    const uint32_t P = v1 * 0x55555555u | u0 * 0xaaaaaaaau;               // applied to x in place
+    const uint32_t Q = v0 * 0x55555555u;                                  // applied to x >> 1 (hi bit moved to the lo plane)
+    const uint32_t R = u1 * 0xaaaaaaaau;                                  // applied to x << 1 (lo bit moved to the hi plane)
+    const uint32_t T = ((v1 & c00) ^ (v0 & c01)) * 0x55555555u | ((u1 & c00) ^ (u0 & c01)) * 0xaaaaaaaau;
+#pragma unroll
+    for (int k = 0; k < NW; k++) y[k] = (((x[k] & P) ^ T) ^ ((x[k] >> 1) & Q) ^ ((x[k] << 1) & R)) & (V[k] * 3u);
+}
+
+// reverse the order of the w 2-bit groups of x (nucleotide j <-> w-1-j)
+template <int NW>
+__device__ __forceinline__ void reverse_pairs(const uint32_t (&x)[NW], uint32_t w, uint32_t (&r)[NW]) {
+    uint32_t t[NW + 1];
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t b = __brev(x[NW - 1 - k]);
+        t[k] = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
+    }
+    t[NW] = 0;
+    // the reversed window now ends at bit 32*NW: move it down by 32*NW - 2w bits (< 32: NW is the smallest that fits w)
+    const uint32_t sh = 32u * NW - 2u * w;
+#pragma unroll
+    for (int k = 0; k < NW; k++) r[k] = __funnelshift_r(t[k], t[k + 1], sh);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const CanonParams p) {
+    extern __shared__ __align__(128) unsigned char canon_smem[];
+    // layout: stage[2][CANON_THREADS * w] | codes[CANON_CODE_WORDS] | decode[256] | tile origin
+    const uint32_t w = p.w;
+    const uint32_t tile_bytes = CANON_THREADS * w;
+    uint8_t* stage = canon_smem;
+    uint32_t* codes = reinterpret_cast<uint32_t*>(canon_smem + 2 * ((tile_bytes + 127) & ~127u));
+    uint8_t* decode_s = reinterpret_cast<uint8_t*>(codes + CANON_CODE_WORDS);
+    unsigned long long* origin = reinterpret_cast<unsigned long long*>(decode_s + 256);  // [0] sequence, [1] window in it
+    const int tid = threadIdx.x;
+    const uint64_t nw = p.seq_len - w + 1;       // windows per sequence
+    const uint64_t total = p.n_seq * nw;         // windows in the batch
+    const uint64_t n_tiles = (total + CANON_THREADS - 1) / CANON_THREADS;
+    decode_s[tid] = __ldg(p.decode + tid);
+    uint32_t V[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const int left = (int)w - 16 * k;
+        V[k] = left >= 16 ? 0x55555555u : (left <= 0 ? 0u : (0x55555555u & ((1u << (2 * left)) - 1u)));
+    }
+    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna);
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint64_t g0 = tile * CANON_THREADS;
+        const uint32_t cnt = (uint32_t)min((uint64_t)CANON_THREADS, total - g0);
+        if (tid == 0) {
+            origin[0] = g0 / nw;
+            origin[1] = g0 - origin[0] * nw;
+        }
+        __syncthreads();  // also: the previous tile's readers of codes[] are done
+        const uint64_t s0 = origin[0], i0 = origin[1];
+        // my window: sequence s, index i in it
+        uint64_t s = s0, i = i0 + (uint32_t)min((uint32_t)tid, cnt - 1);
+        if (i >= nw) {
+            if (nw >= CANON_THREADS) { i -= nw; s++; }
+            else { s += i / nw; i %= nw; }
+        }
+        const uint64_t flat_lo = s0 * p.seq_len + i0;
+        // span of input the tile touches: up to the end of its last window
+        uint64_t sl = s0, il = i0 + (cnt - 1);
+        if (il >= nw) {
+            if (nw >= CANON_THREADS) { il -= nw; sl++; }
+            else { sl += il / nw; il %= nw; }
+        }
+        const uint64_t flat_hi = sl * p.seq_len + il + w;
+        // ---- decode the span into 2-bit codes, 16 per word, word 0 starting at the 16-byte granule of flat_lo ----
+        const uintptr_t a0 = (dna_lo + flat_lo) & ~(uintptr_t)15;
+        const uint32_t n_gran = (uint32_t)((dna_lo + flat_hi - a0 + 15) >> 4);
+        for (uint32_t gidx = tid; gidx < n_gran; gidx += CANON_THREADS) {
+            const uintptr_t a = a0 + 16 * (uintptr_t)gidx;
+            uint32_t word = 0;
+            if (a >= dna_lo + flat_lo && a + 16 <= dna_lo + flat_hi) {
+                const uint4 q = ldg_stream(reinterpret_cast<const void*>(a));
+                const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int t = 15; t >= 0; t--) {
+                    const uint32_t c = decode_s[(ws[t >> 2] >> (8 * (t & 3))) & 0xffu];
+                    if (c > 3u) atomicMin(p.err_key, (unsigned long long)(a + t - dna_lo));
+                    word = (word << 2) | (c & 3u);
+                }
+            } else {
+#pragma unroll
+                for (int t = 15; t >= 0; t--) {
+                    const uintptr_t b = a + t;
+                    uint32_t c = 0;
+                    if (b >= dna_lo + flat_lo && b < dna_lo + flat_hi) {
+                        c = decode_s[*reinterpret_cast<const uint8_t*>(b)];
+                        if (c > 3u) atomicMin(p.err_key, (unsigned long long)(b - dna_lo));
+                    }
+                    word = (word << 2) | (c & 3u);
+                }
+            }
+            codes[gidx] = word;
+        }
+        if (tid == 0) codes[n_gran] = 0;
+        __syncthreads();
+        // ---- my window, canonicalised -------------------------------------------------------------
+        uint8_t* const st = stage + (it & 1u) * ((tile_bytes + 127) & ~127u);
+        if (tid < (int)cnt) {
+            const uint32_t o = (uint32_t)(dna_lo + s * p.seq_len + i - a0);  // nucleotide offset inside codes[]
+            const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
+            uint32_t x[NW], y[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) x[k] = __funnelshift_r(codes[wi + k], codes[wi + k + 1], sh) & (V[k] * 3u);
+            forward_canonical_packed<NW>(x, V, y);
+            if (!p.forward_only) {
+                uint32_t xr[NW], yr[NW];
+                reverse_pairs<NW>(x, w, xr);
+                forward_canonical_packed<NW>(xr, V, yr);
+                // lexical order: the lowest differing 2-bit group decides (first nucleotide = bits 0..1)
+                uint32_t d[NW], dsel, ysel;
+#pragma unroll
+                for (int k = 0; k < NW; k++) d[k] = y[k] ^ yr[k];
+                if (first_nonzero<NW>(d, y, dsel, ysel)) {
+                    const uint32_t pos = (__ffs(dsel) - 1) & ~1u;
+                    const uint32_t a = (ysel >> pos) & 3u, b = ((ysel ^ dsel) >> pos) & 3u;
+                    if (b < a) {
+#pragma unroll
+                        for (int k = 0; k < NW; k++) y[k] = yr[k];
+                    }
+                }
+            }
+            // ---- 2-bit codes -> bytes, 4 at a time: spread to nibble selectors, permute the 4-letter register ----
+            uint8_t* dst = st + (size_t)tid * w;
+            const bool even = (w & 1u) == 0;  // every window then starts at an even offset: 16-bit stores
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t j = 16 * k + 4 * q;  // first nucleotide of this group
+                    if (j < w) {
+                        uint32_t t = (y[k] >> (8 * q)) & 0xffu;
+                        t = (t | (t << 4)) & 0x0f0fu;
+                        t = (t | (t << 2)) & 0x3333u;
+                        const uint32_t four = __byte_perm(p.letters, 0, t);
+                        const uint32_t left = w - j;
+                        if (even) {
+                            *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)four;
+                            if (left > 2) *reinterpret_cast<uint16_t*>(dst + j + 2) = (uint16_t)(four >> 16);
+                        } else {
+                            dst[j] = (uint8_t)four;
+                            if (left > 1) dst[j + 1] = (uint8_t)(four >> 8);
+                            if (left > 2) dst[j + 2] = (uint8_t)(four >> 16);
+                            if (left > 3) dst[j + 3] = (uint8_t)(four >> 24);
+                        }
+                    }
+                }
+            }
+        }
+        fence_proxy_async_smem();  // my generic-proxy stores to `st` before the bulk store reads them
+        __syncthreads();
+        // ---- one bulk store per tile (the tail of the whole batch, if not a multiple of 16 bytes, by plain stores) ----
+        const uint32_t nbytes = cnt * w;
+        uint8_t* gdst = p.out + g0 * w;
+        const uint32_t body = nbytes & ~15u;
+        if (tid == 0) {
+            if (body) bulk_s2g(gdst, st, body);
+            bulk_commit();
+            bulk_wait_read_1();  // the OTHER stage buffer (next tile's) is no longer being read
+        }
+        if (tid < (int)(nbytes - body)) gdst[body + tid] = st[body + tid];
+    }
+    if (tid == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------

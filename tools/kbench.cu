@@ -166,20 +166,25 @@ int main(int argc, char** argv) {
         if (out_bytes >= nwin * w) {
             CanonParams q{};
             q.dna = dna;
-            q.n = n_cw;
+            q.n_seq = 1;
+            q.seq_len = n_cw;
             q.w = (uint32_t)w;
             q.forward_only = 0;
             q.out = out;
             q.decode = d_decode;
             q.letters = 'A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24);
             q.err_key = d_err;
-            const size_t smem_c = ((CANON_THREADS + CANON_MAX_W + 15) & ~15) + 16 + (size_t)CANON_THREADS * w;
+            const size_t smem_c = 2 * (((size_t)CANON_THREADS * w + 127) & ~(size_t)127) + CANON_CODE_WORDS * 4 + 256 + 16;
+            CK(cudaFuncSetAttribute(canonical_windows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
             const uint64_t blocks = (nwin + CANON_THREADS - 1) / CANON_THREADS;
-            const unsigned gc = (unsigned)std::min<uint64_t>(blocks, (uint64_t)sms * 16);
-            canonical_windows_kernel<<<gc, CANON_THREADS, smem_c>>>(q);
+#ifndef KB_CW_OCC
+#define KB_CW_OCC 6
+#endif
+            const unsigned gc = (unsigned)std::min<uint64_t>(blocks, (uint64_t)sms * KB_CW_OCC);
+            canonical_windows_kernel<3><<<gc, CANON_THREADS, smem_c>>>(q);
             CK(cudaDeviceSynchronize());
             CK(cudaEventRecord(e0));
-            for (int i = 0; i < 3; i++) canonical_windows_kernel<<<gc, CANON_THREADS, smem_c>>>(q);
+            for (int i = 0; i < 3; i++) canonical_windows_kernel<3><<<gc, CANON_THREADS, smem_c>>>(q);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             CK(cudaEventElapsedTime(&ms, e0, e1));
