@@ -77,7 +77,7 @@ void *qd_ctx_stream(const qd_ctx *ctx); /* the context's cudaStream_t */
 int qd_ctx_sm_count(const qd_ctx *ctx);
 const char *qd_last_cuda_error(const qd_ctx *ctx);
 int qd_abi_version(void);
-/* input bytes per chunk of the host batch pipeline (default 256 MiB) */
+/* input bytes per chunk of the host batch pipeline (default 64 MiB) */
 int qd_ctx_set_chunk_bytes(qd_ctx *ctx, size_t bytes);
 /* tuning / test knob: frame launches of at least `runs` 48-nt runs use the 1024-thread tile
  * (default 2 * 1024 * SM count); 0 = always, UINT64_MAX = never */

@@ -76,7 +76,7 @@ struct qd_ctx {
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
     DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums, parse_counts, parse_offsets, canon_state;
     Pipe pipe[N_PIPE];
-    size_t chunk_bytes = size_t(256) << 20;  // input bytes per pipeline chunk
+    size_t chunk_bytes = size_t(64) << 20;   // input bytes per pipeline chunk
     int occ_frames[6] = {0, 0, 0, 0, 0, 0};  // [tile size][frames]
     uint64_t big_tile_min_runs = 0;           // launches with at least this many runs use 1024-thread tiles
     int occ_revcomp[2] = {0, 0};  // [small, big tile]

@@ -345,7 +345,7 @@ def test_batch_chunked_pipeline_and_error_index(B, N, tiles):
             B.translate_frames_batch(reads, table=1, frames=6)
         assert (ei.value.seq_index, ei.value.pos, str(ei.value)) == (123, 50, "bad nucleotide: '-'")
     finally:
-        N.lib().qd_ctx_set_chunk_bytes(ctx.handle, 256 << 20)
+        N.lib().qd_ctx_set_chunk_bytes(ctx.handle, 64 << 20)
 
 
 # ------------------------------------------------------------------ parse (src/rust_api.rs:310-322)
