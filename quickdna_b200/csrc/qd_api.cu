@@ -71,6 +71,7 @@ struct qd_ctx {
     uint8_t* d_tables = nullptr;  // 256-byte tables, see TAB_* offsets
     uint16_t* d_pair = nullptr;   // [encoding][strict][PAIR_ENTRIES]
     uint16_t* d_rc_pair = nullptr;  // [RC_PAIR_COUNT][PAIR_ENTRIES]
+    uint8_t* d_canon_pair = nullptr;  // [encoding][PAIR_ENTRIES]
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
@@ -395,6 +396,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_tables, 256 * TAB_COUNT) == cudaSuccess;
     ok &= cudaMalloc(&c->d_pair, sizeof(T.pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_rc_pair, sizeof(T.rc_pair)) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_canon_pair, sizeof(T.canon_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
@@ -421,6 +423,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         ok &= cudaMemcpy(c->d_lut, T.folded.data(), T.folded.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_rc_pair, T.rc_pair, sizeof(T.rc_pair), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(c->d_canon_pair, T.canon_pair, sizeof(T.canon_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemset(c->d_err, 0xff, sizeof(unsigned long long)) == cudaSuccess;
     }
     if (!ok) {
@@ -446,6 +449,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->d_pair) cudaFree(c->d_pair);
     if (c->d_rc_pair) cudaFree(c->d_rc_pair);
+    if (c->d_canon_pair) cudaFree(c->d_canon_pair);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -625,10 +629,12 @@ extern "C" int qd_translate_frames_batch_dev(qd_ctx* c, int table, int enc, int 
 template <int NW>
 static int launch_canonical_windows(qd_ctx* c, const CanonParams& p, cudaStream_t s) {
     auto kern = canonical_windows_kernel<NW>;
-    const size_t smem = 2 * (((size_t)CANON_THREADS * p.w + 127) & ~(size_t)127) + CANON_CODE_WORDS * 4 + 256 + 16;
+    const size_t smem = (size_t)CanonWarpLayout(p.w).total_bytes * CANON_WARPS + PAIR_ENTRIES;
     QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t tiles = (p.n_seq * (p.seq_len - p.w + 1) + CANON_THREADS - 1) / CANON_THREADS;
-    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 6);
+    int occ = 0;
+    QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CANON_THREADS, smem));
+    const uint64_t tiles = (p.n_seq * (p.seq_len - p.w + 1) + CANON_WPT * CANON_WARPS - 1) / (CANON_WPT * CANON_WARPS);
+    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * std::max(1, occ));
     kern<<<grid, CANON_THREADS, smem, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
@@ -647,8 +653,14 @@ static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dn
     p.w = (uint32_t)w;
     p.forward_only = forward_only;
     p.out = out_dev;
-    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
-    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
+    const bool ascii = enc == QD_ENC_ASCII;
+    p.decode = tab(c, ascii ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    p.pair = c->d_canon_pair + (ascii ? 0 : PAIR_ENTRIES);
+    p.pair_coef = 1u | ((ascii ? PAIR_K1_ASCII : PAIR_K1_MASK) << 16);
+    p.and_need = ascii ? 0x40404040u : 0u;
+    p.or_forbid = ascii ? 0x80808080u : 0xe0e0e0e0u;
+    p.filler = ascii ? 0x41u : 0x01u;
+    p.letters = ascii ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
     p.err_key = c->d_err;
     switch ((2 * w + 31) / 32) {
         case 1: return launch_canonical_windows<1>(c, p, s);

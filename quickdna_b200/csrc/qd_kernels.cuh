@@ -716,14 +716,16 @@ struct CanonParams {
     uint32_t w;
     int forward_only;
     uint8_t* out;            // n_seq * (seq_len - w + 1) windows, w bytes each, tightly packed, 16-byte aligned
-    const uint8_t* decode;   // 256-byte table -> internal code (0..3 concrete)
+    const uint8_t* decode;   // 256-byte table -> internal code (0..3 concrete); exact error search only
+    const uint8_t* pair;     // PAIR_ENTRIES bytes: letter pair -> code0 | code1 << 4, | 0x88 if either is not a concrete base
+    uint32_t pair_coef;      // dp2a coefficients {1, k1} (byte entries)
+    uint32_t and_need, or_forbid, filler;  // as in the frame / reverse-complement kernels
     uint32_t letters;        // output byte of codes 0..3 packed little-endian (ASCII "ATCG" or masks 1,2,4,8)
     unsigned long long* err_key;
 };
 
 constexpr int CANON_THREADS = 256;  // windows per tile (a multiple of 16: tile outputs stay 16-byte aligned)
 constexpr int CANON_MAX_W = 64;
-constexpr int CANON_CODE_WORDS = (CANON_THREADS * CANON_MAX_W) / 16 + 8;  // packed codes of the widest possible tile span
 
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
@@ -748,7 +750,7 @@ __device__ __forceinline__ bool first_nonzero(const uint32_t (&m)[NW], const uin
 
 // fw(x): relabel the packed window by first occurrence.  V[k] = 0x55555555 restricted to the window's positions.
 template <int NW>
-__device__ __forceinline__ void forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW]) {
+__device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW]) {
     const uint32_t c0 = x[0] & 3u;
     const uint32_t C0 = c0 * 0x55555555u;
     uint32_t ne1[NW], msel, xsel;
@@ -779,6 +781,8 @@ __device__ __forceinline__ void forward_canonical_packed(const uint32_t (&x)[NW]
     const uint32_t T = ((v1 & c00) ^ (v0 & c01)) * 0x55555555u | ((u1 & c00) ^ (u0 & c01)) * 0xaaaaaaaau;
 #pragma unroll
     for (int k = 0; k < NW; k++) y[k] = (((x[k] & P) ^ T) ^ ((x[k] >> 1) & Q) ^ ((x[k] << 1) & R)) & (V[k] * 3u);
+    // the map itself, applied to the codes 0,1,2,3 (0xe4): 2 bits per code
+    return (((0xe4u & P) ^ T) ^ ((0xe4u >> 1) & Q) ^ ((0xe4u << 1) & R)) & 0xffu;
 }
 
 // reverse the order of the w 2-bit groups of x (nucleotide j <-> w-1-j)
@@ -797,123 +801,176 @@ __device__ __forceinline__ void reverse_pairs(const uint32_t (&x)[NW], uint32_t 
     for (int k = 0; k < NW; k++) r[k] = __funnelshift_r(t[k], t[k + 1], sh);
 }
 
+// Warp-independent tiles: a warp owns CANON_WPT consecutive windows (of the whole batch) per iteration and shares
+// nothing with the other warps of its CTA -- no block barrier anywhere.  Per warp-tile:
+//   decode   the <= CANON_WPT + w - 1 (+ sequence seams) nucleotides the tile touches, 4 per lane and step, two letters
+//            per shared-memory lookup (same dp2a pair index as the frame kernel), into three streams in shared memory:
+//            2-bit packed codes (for the relabelling arithmetic), and the codes as NIBBLES in forward and in reversed
+//            order (PRMT selectors for the output: a window's bytes are 4 per PRMT through a 4-letter register that
+//            already holds the window's relabelling, read from whichever of the two streams won)
+//   window   CANON_WPT / 32 per lane: fw(x), fw(reverse(x)), lexical minimum, 11 PRMT for 42 bytes
+//   copy-out the tile's staged bytes with coalesced 128-bit stores
+constexpr int CANON_WPT = 64;  // windows per warp-tile
+// per-warp shared memory, sized by w: c2 (16 codes per word) | nib_f (8 codes per word, ascending) | nib_r (the same
+// nucleotides in descending order) | stage (the tile's output bytes)
+struct CanonWarpLayout {
+    uint32_t c2_words, nib_words, stage_bytes, total_bytes;
+    __host__ __device__ explicit CanonWarpLayout(uint32_t w) {
+        const uint32_t gran = (CANON_WPT * w + 15) / 16 + 2;  // granules a warp-tile can touch
+        c2_words = (gran + 2 + 3) & ~3u;
+        nib_words = (2 * gran + 2 + 3) & ~3u;
+        stage_bytes = (CANON_WPT * w + 15) & ~15u;
+        total_bytes = 4 * (c2_words + 2 * nib_words) + stage_bytes;
+    }
+};
+struct CanonWarpSmem {
+    uint32_t* c2;
+    uint32_t* nib_f;
+    uint32_t* nib_r;
+    uint8_t* stage;
+};
+constexpr int CANON_WARPS = CANON_THREADS / 32;
+
 template <int NW>
 __global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const CanonParams p) {
     extern __shared__ __align__(128) unsigned char canon_smem[];
-    // layout: stage[2][CANON_THREADS * w] | codes[CANON_CODE_WORDS] | decode[256] | tile origin
     const uint32_t w = p.w;
-    const uint32_t tile_bytes = CANON_THREADS * w;
-    uint8_t* stage = canon_smem;
-    uint32_t* codes = reinterpret_cast<uint32_t*>(canon_smem + 2 * ((tile_bytes + 127) & ~127u));
-    uint8_t* decode_s = reinterpret_cast<uint8_t*>(codes + CANON_CODE_WORDS);
-    unsigned long long* origin = reinterpret_cast<unsigned long long*>(decode_s + 256);  // [0] sequence, [1] window in it
-    const int tid = threadIdx.x;
-    const uint64_t nw = p.seq_len - w + 1;       // windows per sequence
-    const uint64_t total = p.n_seq * nw;         // windows in the batch
-    const uint64_t n_tiles = (total + CANON_THREADS - 1) / CANON_THREADS;
-    decode_s[tid] = __ldg(p.decode + tid);
+    const CanonWarpLayout lay(w);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    CanonWarpSmem S;
+    S.c2 = reinterpret_cast<uint32_t*>(canon_smem + (size_t)warp * lay.total_bytes);
+    S.nib_f = S.c2 + lay.c2_words;
+    S.nib_r = S.nib_f + lay.nib_words;
+    S.stage = reinterpret_cast<uint8_t*>(S.nib_r + lay.nib_words);
+    uint8_t* const pair_s = canon_smem + (size_t)CANON_WARPS * lay.total_bytes;  // PAIR_ENTRIES bytes
+    for (int i = tid; i < (int)PAIR_ENTRIES; i += CANON_THREADS) pair_s[i] = __ldg(p.pair + i);
+    __syncthreads();
+    const uint64_t nw = p.seq_len - w + 1;  // windows per sequence
+    const uint64_t total = p.n_seq * nw;    // windows in the batch
+    const uint64_t n_tiles = (total + CANON_WPT - 1) / CANON_WPT;
     uint32_t V[NW];
 #pragma unroll
     for (int k = 0; k < NW; k++) {
         const int left = (int)w - 16 * k;
         V[k] = left >= 16 ? 0x55555555u : (left <= 0 ? 0u : (0x55555555u & ((1u << (2 * left)) - 1u)));
     }
-    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna);
-    uint32_t it = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint64_t g0 = tile * CANON_THREADS;
-        const uint32_t cnt = (uint32_t)min((uint64_t)CANON_THREADS, total - g0);
-        if (tid == 0) {
-            origin[0] = g0 / nw;
-            origin[1] = g0 - origin[0] * nw;
-        }
-        __syncthreads();  // also: the previous tile's readers of codes[] are done
-        const uint64_t s0 = origin[0], i0 = origin[1];
-        // my window: sequence s, index i in it
-        uint64_t s = s0, i = i0 + (uint32_t)min((uint32_t)tid, cnt - 1);
-        if (i >= nw) {
-            if (nw >= CANON_THREADS) { i -= nw; s++; }
-            else { s += i / nw; i %= nw; }
-        }
-        const uint64_t flat_lo = s0 * p.seq_len + i0;
-        // span of input the tile touches: up to the end of its last window
-        uint64_t sl = s0, il = i0 + (cnt - 1);
+    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.n_seq * p.seq_len;
+    const uint32_t pair_base = smem_u32(pair_s);
+    // tile t of this warp: first window g0 = CANON_WPT t, in sequence s0 at index i0; advanced incrementally
+    const uint64_t warps_total = (uint64_t)gridDim.x * CANON_WARPS;
+    uint64_t tile = (uint64_t)blockIdx.x * CANON_WARPS + warp;
+    uint64_t s0 = (tile * CANON_WPT) / nw, i0 = (tile * CANON_WPT) % nw;
+    const uint64_t step_s = (warps_total * CANON_WPT) / nw, step_i = (warps_total * CANON_WPT) % nw;
+    for (; tile < n_tiles; tile += warps_total) {
+        const uint64_t g0 = tile * CANON_WPT;
+        const uint32_t cnt = (uint32_t)min((uint64_t)CANON_WPT, total - g0);
+        uint64_t sl = s0, il = i0 + (cnt - 1);  // the tile's last window
         if (il >= nw) {
-            if (nw >= CANON_THREADS) { il -= nw; sl++; }
+            if (nw >= CANON_WPT) { il -= nw; sl++; }
             else { sl += il / nw; il %= nw; }
         }
-        const uint64_t flat_hi = sl * p.seq_len + il + w;
-        // ---- decode the span into 2-bit codes, 16 per word, word 0 starting at the 16-byte granule of flat_lo ----
+        const uint64_t flat_lo = s0 * p.seq_len + i0, flat_hi = sl * p.seq_len + il + w;
         const uintptr_t a0 = (dna_lo + flat_lo) & ~(uintptr_t)15;
         const uint32_t n_gran = (uint32_t)((dna_lo + flat_hi - a0 + 15) >> 4);
-        for (uint32_t gidx = tid; gidx < n_gran; gidx += CANON_THREADS) {
-            const uintptr_t a = a0 + 16 * (uintptr_t)gidx;
-            uint32_t word = 0;
-            if (a >= dna_lo + flat_lo && a + 16 <= dna_lo + flat_hi) {
-                const uint4 q = ldg_stream(reinterpret_cast<const void*>(a));
-                const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int t = 15; t >= 0; t--) {
-                    const uint32_t c = decode_s[(ws[t >> 2] >> (8 * (t & 3))) & 0xffu];
-                    if (c > 3u) atomicMin(p.err_key, (unsigned long long)(a + t - dna_lo));
-                    word = (word << 2) | (c & 3u);
-                }
-            } else {
-#pragma unroll
-                for (int t = 15; t >= 0; t--) {
+        // ---- decode: item = one aligned 32-bit word of input (4 nucleotides) -------------------------------
+        for (uint32_t item = lane; item < 4 * n_gran; item += 32) {
+            const uintptr_t a = a0 + 4 * (uintptr_t)item;
+            uint32_t x;
+            if (a >= dna_lo && a + 4 <= dna_hi) {
+                // bytes of the word outside this tile's span belong to a neighbouring tile (or sequence) and are
+                // validated there too, so looking at them here changes nothing
+                x = __ldg(reinterpret_cast<const uint32_t*>(a));
+            } else {  // the words straddling the ends of the whole buffer: bytes outside it read as a valid filler
+                x = 0;
+#pragma unroll 1
+                for (int t = 0; t < 4; t++) {
                     const uintptr_t b = a + t;
-                    uint32_t c = 0;
-                    if (b >= dna_lo + flat_lo && b < dna_lo + flat_hi) {
-                        c = decode_s[*reinterpret_cast<const uint8_t*>(b)];
-                        if (c > 3u) atomicMin(p.err_key, (unsigned long long)(b - dna_lo));
-                    }
-                    word = (word << 2) | (c & 3u);
+                    x |= ((b >= dna_lo && b < dna_hi) ? (uint32_t)*reinterpret_cast<const uint8_t*>(b) : (p.filler & 0xffu)) << (8 * t);
                 }
             }
-            codes[gidx] = word;
+            const uint32_t m = x & 0x1f1f1f1fu;
+            uint32_t e0 = lds_u8(dp2a_lo(p.pair_coef, m, pair_base)), e1 = lds_u8(dp2a_hi(p.pair_coef, m, pair_base));
+            if (((e0 | e1) & 0x88u) | ((x & p.and_need) ^ p.and_need) | (x & p.or_forbid)) {
+                // exact: first byte of this word that is not a concrete base
+#pragma unroll 1
+                for (int t = 0; t < 4; t++) {
+                    const uintptr_t b = a + t;
+                    if (b >= dna_lo && b < dna_hi && __ldg(p.decode + *reinterpret_cast<const uint8_t*>(b)) > 3u) {
+                        atomicMin(p.err_key, (unsigned long long)(b - dna_lo));
+                        break;
+                    }
+                }
+                e0 &= 0x33u;
+                e1 &= 0x33u;
+            }
+            reinterpret_cast<uint16_t*>(S.nib_f)[item] = (uint16_t)(e0 | (e1 << 8));
+            // reversed stream: the same four nibbles in descending order at the mirrored half-word
+            const uint32_t r0 = ((e1 >> 4) | (e1 << 4)) & 0xffu, r1 = ((e0 >> 4) | (e0 << 4)) & 0xffu;
+            reinterpret_cast<uint16_t*>(S.nib_r)[4 * n_gran - 1 - item] = (uint16_t)(r0 | (r1 << 8));
+            reinterpret_cast<uint8_t*>(S.c2)[item] = (uint8_t)((e0 & 3u) | ((e0 >> 2) & 0xcu) | ((e1 & 3u) << 4) | ((e1 << 2) & 0xc0u));
         }
-        if (tid == 0) codes[n_gran] = 0;
-        __syncthreads();
-        // ---- my window, canonicalised -------------------------------------------------------------
-        uint8_t* const st = stage + (it & 1u) * ((tile_bytes + 127) & ~127u);
-        if (tid < (int)cnt) {
-            const uint32_t o = (uint32_t)(dna_lo + s * p.seq_len + i - a0);  // nucleotide offset inside codes[]
-            const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
+        if (lane == 0) {
+            S.c2[n_gran] = 0;
+            S.nib_f[2 * n_gran] = 0;
+            S.nib_r[2 * n_gran] = 0;
+        }
+        __syncwarp();
+        // ---- my windows ----------------------------------------------------------------------------------
+#pragma unroll 1
+        for (uint32_t l = lane; l < cnt; l += 32) {
+            uint64_t s = s0, i = i0 + l;
+            if (i >= nw) {
+                if (nw >= CANON_WPT) { i -= nw; s++; }
+                else { s += i / nw; i %= nw; }
+            }
+            const uint32_t o = (uint32_t)(dna_lo + s * p.seq_len + i - a0);  // nucleotide offset inside the streams
             uint32_t x[NW], y[NW];
+            {
+                const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
 #pragma unroll
-            for (int k = 0; k < NW; k++) x[k] = __funnelshift_r(codes[wi + k], codes[wi + k + 1], sh) & (V[k] * 3u);
-            forward_canonical_packed<NW>(x, V, y);
+                for (int k = 0; k < NW; k++) x[k] = __funnelshift_r(S.c2[wi + k], S.c2[wi + k + 1], sh) & (V[k] * 3u);
+            }
+            uint32_t perm = forward_canonical_packed<NW>(x, V, y);  // perm: the relabelling of codes 0..3, 2 bits each
+            bool use_rev = false;
             if (!p.forward_only) {
                 uint32_t xr[NW], yr[NW];
                 reverse_pairs<NW>(x, w, xr);
-                forward_canonical_packed<NW>(xr, V, yr);
+                const uint32_t perm_r = forward_canonical_packed<NW>(xr, V, yr);
                 // lexical order: the lowest differing 2-bit group decides (first nucleotide = bits 0..1)
                 uint32_t d[NW], dsel, ysel;
 #pragma unroll
                 for (int k = 0; k < NW; k++) d[k] = y[k] ^ yr[k];
                 if (first_nonzero<NW>(d, y, dsel, ysel)) {
                     const uint32_t pos = (__ffs(dsel) - 1) & ~1u;
-                    const uint32_t a = (ysel >> pos) & 3u, b = ((ysel ^ dsel) >> pos) & 3u;
-                    if (b < a) {
-#pragma unroll
-                        for (int k = 0; k < NW; k++) y[k] = yr[k];
-                    }
+                    use_rev = (((ysel ^ dsel) >> pos) & 3u) < ((ysel >> pos) & 3u);
                 }
+                if (use_rev) perm = perm_r;
             }
-            // ---- 2-bit codes -> bytes, 4 at a time: spread to nibble selectors, permute the 4-letter register ----
-            uint8_t* dst = st + (size_t)tid * w;
+            // the window's letters: T[code] = letters[perm[code]]
+            uint32_t t = (perm | (perm << 4)) & 0x0f0fu;
+            t = (t | (t << 2)) & 0x3333u;
+            const uint32_t T = __byte_perm(p.letters, 0, t);
+            // selectors: the window's raw codes as nibbles, from the forward or the reversed stream
+            const uint32_t* stream = use_rev ? S.nib_r : S.nib_f;
+            const uint32_t on = use_rev ? 16u * n_gran - o - w : o;
+            const uint32_t wi = on >> 3, sh = (on & 7u) * 4u;
+            constexpr int NN = 2 * NW;  // nibble words of a window
+            uint32_t N[NN + 1];
+#pragma unroll
+            for (int k = 0; k <= NN; k++) N[k] = stream[wi + k];
+            uint8_t* dst = S.stage + (size_t)l * w;
             const bool even = (w & 1u) == 0;  // every window then starts at an even offset: 16-bit stores
 #pragma unroll
-            for (int k = 0; k < NW; k++) {
+            for (int k = 0; k < NN; k++) {
+                const uint32_t sel = __funnelshift_r(N[k], N[k + 1], sh);  // nucleotides 8k .. 8k+7
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t j = 16 * k + 4 * q;  // first nucleotide of this group
-                    if (j < w) {
-                        uint32_t t = (y[k] >> (8 * q)) & 0xffu;
-                        t = (t | (t << 4)) & 0x0f0fu;
-                        t = (t | (t << 2)) & 0x3333u;
-                        const uint32_t four = __byte_perm(p.letters, 0, t);
-                        const uint32_t left = w - j;
+                for (int q = 0; q < 2; q++) {
+                    const uint32_t j = 8 * k + 4 * q;
+                    // groups below 16 (NW - 1) are complete for every w this instantiation serves
+                    const bool surely_full = j + 4 <= 16 * (NW - 1);
+                    if (surely_full || j < w) {
+                        const uint32_t four = __byte_perm(T, 0, q ? (sel >> 16) : sel);
+                        const uint32_t left = surely_full ? 4u : w - j;
                         if (even) {
                             *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)four;
                             if (left > 2) *reinterpret_cast<uint16_t*>(dst + j + 2) = (uint16_t)(four >> 16);
@@ -927,20 +984,19 @@ __global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const 
                 }
             }
         }
-        fence_proxy_async_smem();  // my generic-proxy stores to `st` before the bulk store reads them
-        __syncthreads();
-        // ---- one bulk store per tile (the tail of the whole batch, if not a multiple of 16 bytes, by plain stores) ----
-        const uint32_t nbytes = cnt * w;
-        uint8_t* gdst = p.out + g0 * w;
-        const uint32_t body = nbytes & ~15u;
-        if (tid == 0) {
-            if (body) bulk_s2g(gdst, st, body);
-            bulk_commit();
-            bulk_wait_read_1();  // the OTHER stage buffer (next tile's) is no longer being read
+        __syncwarp();
+        // ---- copy-out: cnt * w contiguous bytes at out + g0 * w (16-byte aligned: g0 is a multiple of 64) ----
+        {
+            const uint32_t nbytes = cnt * w, body = nbytes >> 4;
+            uint8_t* gdst = p.out + g0 * w;
+            for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + 16 * c, *reinterpret_cast<const uint4*>(S.stage + 16 * c));
+            for (uint32_t b = 16 * body + lane; b < nbytes; b += 32) gdst[b] = S.stage[b];
         }
-        if (tid < (int)(nbytes - body)) gdst[body + tid] = st[body + tid];
+        __syncwarp();
+        s0 += step_s;
+        i0 += step_i;
+        if (i0 >= nw) { i0 -= nw; s0++; }
     }
-    if (tid == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------

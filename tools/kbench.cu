@@ -172,15 +172,29 @@ int main(int argc, char** argv) {
             q.forward_only = 0;
             q.out = out;
             q.decode = d_decode;
+            uint8_t* d_cp;
+            CK(cudaMalloc(&d_cp, PAIR_ENTRIES));
+            CK(cudaMemcpy(d_cp, T.canon_pair[0], PAIR_ENTRIES, cudaMemcpyHostToDevice));
+            q.pair = d_cp;
+            q.pair_coef = 1u | (PAIR_K1_ASCII << 16);
+            q.and_need = 0x40404040u;
+            q.or_forbid = 0x80808080u;
+            q.filler = 0x41u;
             q.letters = 'A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24);
             q.err_key = d_err;
-            const size_t smem_c = 2 * (((size_t)CANON_THREADS * w + 127) & ~(size_t)127) + CANON_CODE_WORDS * 4 + 256 + 16;
+            const size_t smem_c = (size_t)CanonWarpLayout((uint32_t)w).total_bytes * CANON_WARPS + PAIR_ENTRIES;
             CK(cudaFuncSetAttribute(canonical_windows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
             const uint64_t blocks = (nwin + CANON_THREADS - 1) / CANON_THREADS;
 #ifndef KB_CW_OCC
-#define KB_CW_OCC 6
+#define KB_CW_OCC 4
 #endif
-            const unsigned gc = (unsigned)std::min<uint64_t>(blocks, (uint64_t)sms * KB_CW_OCC);
+            int occ_c = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, canonical_windows_kernel<3>, CANON_THREADS, smem_c));
+#ifdef KB_CW_OCC_FORCE
+            occ_c = KB_CW_OCC_FORCE;
+#endif
+            const unsigned gc = (unsigned)std::min<uint64_t>(blocks, (uint64_t)sms * occ_c);
+            printf("canonical occ %d smem %zu\n", occ_c, smem_c);
             canonical_windows_kernel<3><<<gc, CANON_THREADS, smem_c>>>(q);
             CK(cudaDeviceSynchronize());
             CK(cudaEventRecord(e0));
