@@ -279,6 +279,22 @@ def parse_dev(ascii_seq, out=None, strict: bool = False, ctx: Optional[N.Context
     return out, count
 
 
+def canonical_windows_batch_dev(dna, n_seq: int, seq_len: int, w: int = 42, out=None, forward_only: bool = False,
+                                enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    """Every length-w window of each of n_seq sequences of seq_len nucleotides (torch uint8 CUDA tensor, back to back);
+    returns a uint8 tensor [n_seq * (seq_len - w + 1), w] (benches/canonical.rs shape, batched)."""
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    nw = max(0, seq_len - w + 1)
+    if out is None:
+        out = torch.empty(max(n_seq * nw * w, 16), dtype=torch.uint8, device=dna.device)
+    rc = N.lib().qd_canonical_windows_batch_dev(ctx.handle, enc, int(forward_only), C.c_void_p(dna.data_ptr()), n_seq, seq_len, w,
+                                                C.c_void_p(out.data_ptr()), _stream_ptr(torch))
+    ctx.check(rc)
+    return out[: n_seq * nw * w].view(n_seq * nw, w) if nw else out[:0].view(0, w)
+
+
 def dev_error_reset(ctx: Optional[N.Context] = None):
     import torch
 

@@ -436,6 +436,33 @@ def test_canonical_whole_sequence(B):
     assert (ei.value.kind, ei.value.byte, ei.value.pos) == (3, ord("N"), 4)
 
 
+def test_canonical_windows_batch(B):
+    """Batched form: windows never span two sequences; tiles of 64 windows cross sequence seams."""
+    import torch
+
+    rng = np.random.default_rng(33)
+    for n_seq, seq_len, w in ((1, 5000, 42), (7, 1000, 42), (300, 50, 42), (500, 42, 42), (64, 43, 42), (33, 99, 17),
+                              (10, 700, 64), (20, 333, 33), (5, 2000, 1), (3, 100, 16), (9, 257, 48), (2, 99999, 42)):
+        a = np.frombuffer(_rand(rng, n_seq * seq_len, b"ACGTacgt"), dtype=np.uint8).reshape(n_seq, seq_len)
+        x = torch.from_numpy(a.copy()).cuda()
+        B.dev_error_reset()
+        got = B.canonical_windows_batch_dev(x, n_seq, seq_len, w).cpu().numpy()
+        assert B.dev_error_fetch(x, uniform_len=seq_len, strict=True) is None
+        nw = seq_len - w + 1
+        assert got.shape == (n_seq * nw, w)
+        for s in range(n_seq):
+            want = oracle.ascii_of(oracle.canonical_windows(oracle.masks_of(a[s]), w).reshape(-1))
+            assert got[s * nw:(s + 1) * nw].tobytes() == want, (n_seq, seq_len, w, s)
+    # an invalid base anywhere in the batch is reported with its sequence and position
+    a = np.frombuffer(_rand(rng, 40 * 500, b"ACGT"), dtype=np.uint8).reshape(40, 500).copy()
+    a[17, 321] = ord("N")
+    x = torch.from_numpy(a).cuda()
+    B.dev_error_reset()
+    B.canonical_windows_batch_dev(x, 40, 500, 42)
+    err = B.dev_error_fetch(x, uniform_len=500, strict=True)
+    assert err is not None and (err.seq_index, err.pos, err.kind, err.byte) == (17, 321, 3, ord("N"))
+
+
 def test_canonical_windows_random(B):
     rng = np.random.default_rng(9)
     for n, w in ((10042 - 1, 42), (500, 1), (500, 7), (3000, 33), (1000, 64), (41, 42), (42, 42), (300, 20)):
