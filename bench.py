@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=0)
     ap.add_argument("--revcomp-nt", type=int, default=250_000_000)
+    ap.add_argument("--canon-seqs", type=int, default=4000, help="99 999-nt sequences per GPU in the canonical-window leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -275,6 +276,41 @@ def main():
                             "roofline": {"bound": "hbm", "achieved": rc_gbs, "peak": peak, "unit": "GB/s", "frac": rc_gbs / peak,
                                          "traffic": ncu_traffic("revcomp_kernel", nt=n_rc), "kernel": "revcomp_kernel<1024>",
                                          "algorithmic_bytes_per_launch": 2 * n_rc}}
+
+    # ---- extra: canonical 42-nt windows (config 5 shape: 99 999-nt strict sequences), device-resident
+    if not args.no_extra:
+        seq_len, w = 99_999, 42
+        n_seq = min(args.canon_seqs, total_nt // seq_len, out.numel() // ((seq_len - w + 1) * w))
+        if n_seq > 0:
+            nwin = n_seq * (seq_len - w + 1)
+            for _ in range(2):
+                B.canonical_windows_batch_dev(x, n_seq, seq_len, w, out=out, ctx=ctx)
+            barrier()
+            reps = 5
+            ev0.record()
+            for _ in range(reps):
+                B.canonical_windows_batch_dev(x, n_seq, seq_len, w, out=out, ctx=ctx)
+            ev1.record()
+            barrier()
+            cw_ms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
+            cw_gbs = nwin * (1 + w) / (cw_ms * 1e-3) / 1e9
+            extra["canonical_windows"] = {
+                "workload": f"canonical 42-nt windows of {n_seq} x {seq_len}-nt ACGT sequences per GPU (benches/canonical.rs shape)",
+                "windows_per_s": world * nwin / (cw_ms * 1e-3), "ms": cw_ms,
+                "roofline": {"bound": "hbm", "achieved": cw_gbs, "peak": peak, "unit": "GB/s", "frac": cw_gbs / peak, "traffic": None,
+                             "kernel": "canonical_windows_kernel<3>", "algorithmic_bytes_per_launch": nwin * (1 + w),
+                             "note": "ALU-bound (about 500 thread-instructions per 42-byte window), not HBM-bound"}}
+            if rank == 0 and world == 1 and not args.no_cpu:
+                import oracle
+
+                m = oracle.masks_of(x[: seq_len].cpu().numpy())
+                t0 = time.perf_counter()
+                n_rep = 0
+                while time.perf_counter() - t0 < 2.0:
+                    oracle.canonical_windows(m, w)
+                    n_rep += 1
+                extra["canonical_windows"]["cpu_port"] = {"windows_per_s": n_rep * (seq_len - w + 1) / (time.perf_counter() - t0), "cores": 1,
+                                                          "sample": f"{n_rep} x one {seq_len}-nt sequence, oracle/qd_oracle.c"}
 
     # ---- e2e: the host-pointer C-ABI call on pinned host buffers (H2D + kernels + D2H timed)
     e2e = None
