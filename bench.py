@@ -277,6 +277,73 @@ def main():
                                          "traffic": ncu_traffic("revcomp_kernel", nt=n_rc), "kernel": "revcomp_kernel<1024>",
                                          "algorithmic_bytes_per_launch": 2 * n_rc}}
 
+    # ---- extra: the other forms of the frame kernel on the same resident data (a few launches each)
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        barrier()
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1)) / reps
+
+    if not args.no_extra:
+        def leg(name, workload, ms, nt, algo_bytes, kernel):
+            gbs = algo_bytes / (ms * 1e-3) / 1e9
+            extra[name] = {"workload": workload, "nt_per_s": world * nt / (ms * 1e-3), "ms": ms,
+                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                                        "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes}}
+
+        n_v = min(n_reads, 4_000_000)
+        nt_v = n_v * READ_LEN
+        f1 = sum([(READ_LEN - 0) // 3])
+        f3 = sum((READ_LEN - k) // 3 for k in range(3))
+        ms1 = timed(lambda: B.translate_frames_uniform_dev(x[:nt_v], n_v, READ_LEN, out=out, table=args.table, frames=1, ctx=ctx))
+        leg("translate_1_frame", f"translate (1 frame) on {n_v} x {READ_LEN}-nt reads per GPU", ms1, nt_v, n_v * (READ_LEN + f1),
+            "translate_frames_kernel<1, 1024>")
+        ms3 = timed(lambda: B.translate_frames_uniform_dev(x[:nt_v], n_v, READ_LEN, out=out, table=args.table, frames=3, ctx=ctx))
+        leg("translate_self_frames", f"translate_self_frames (3 frames) on {n_v} x {READ_LEN}-nt reads per GPU", ms3, nt_v,
+            n_v * (READ_LEN + f3), "translate_frames_kernel<3, 1024>")
+        mss = timed(lambda: B.translate_frames_uniform_dev(x[:nt_v], n_v, READ_LEN, out=out, table=args.table, frames=6, strict=True, ctx=ctx))
+        leg("all_frames_strict", f"translate_all_frames, strict alphabet check, {n_v} x {READ_LEN}-nt ACGT reads per GPU", mss, nt_v,
+            n_v * ALGO_BYTES_PER_READ, "translate_frames_kernel<6, 1024>")
+        # variable-length batch (lengths uniform in 500..1500, seed 4): CSR offsets on the device, scan + tile map included
+        g = torch.Generator(device="cpu").manual_seed(4 + rank)
+        lens = torch.randint(500, 1501, (n_v,), generator=g, dtype=torch.int64)
+        offs = torch.zeros(n_v + 1, dtype=torch.int64)
+        offs[1:] = torch.cumsum(lens, 0)
+        keep = int(torch.searchsorted(offs, torch.tensor([min(nt_v, total_nt)]), right=True).item()) - 1
+        offs_d = offs[: keep + 1].to(dev)
+        tot_v = int(offs[keep].item())
+        runs_v = int(((lens[:keep] + 47) // 48).sum().item())
+        algo_v = int((lens[:keep] + 2 * ((lens[:keep]) // 3 + (lens[:keep] - 1) // 3 + (lens[:keep] - 2) // 3)).sum().item())
+        launches_v0 = ctx.launch_count
+        msv = timed(lambda: B.translate_frames_csr_dev(x[:tot_v], offs_d, out=out[: runs_v * 96], table=args.table, frames=6, ctx=ctx))
+        leg("all_frames_variable_length", f"translate_all_frames on {keep} reads of 500..1500 nt (CSR offsets, prefix scan and tile map "
+            "kernels inside the timed region)", msv, tot_v, algo_v, "translate_frames_kernel<6, 1024> + scan/tile-map")
+        extra["all_frames_variable_length"]["launches_per_call"] = (ctx.launch_count - launches_v0) // 7
+        # IUPAC-ambiguous, mixed-case input (config 4): 5 % ambiguity codes, tables 1 / 11 / 22
+        from quickdna_b200.synth import synth_iupac_np
+
+        base = torch.from_numpy(synth_iupac_np(5, rank * 50_000_000, 50_000 * READ_LEN)).to(dev)
+        n_a = 1_000_000
+        xa = base.repeat(n_a // 50_000)
+        for tbl in (1, 11, 22):
+            msa = timed(lambda: B.translate_frames_uniform_dev(xa, n_a, READ_LEN, out=out, table=tbl, frames=6, ctx=ctx), reps=3)
+            leg(f"all_frames_iupac_t{tbl}", f"translate_all_frames, NCBI table {tbl}, {n_a} x {READ_LEN}-nt reads with 5 % IUPAC "
+                "ambiguity codes, 50 % lower case, non-strict", msa, n_a * READ_LEN, n_a * ALGO_BYTES_PER_READ,
+                "translate_frames_kernel<6, 1024>")
+        assert B.dev_error_fetch(xa, uniform_len=READ_LEN, ctx=ctx) is None
+        B.dev_error_reset(ctx)
+        B.translate_frames_uniform_dev(xa, n_a, READ_LEN, out=out, table=1, frames=6, strict=True, ctx=ctx)
+        e = B.dev_error_fetch(xa, uniform_len=READ_LEN, strict=True, ctx=ctx)
+        extra["all_frames_iupac_strict_error"] = None if e is None else {"kind": e.kind, "byte": chr(e.byte), "seq_index": e.seq_index,
+                                                                       "pos": e.pos, "message": str(e)}
+        B.dev_error_reset(ctx)
+        del xa, base
+
     # ---- extra: canonical 42-nt windows (config 5 shape: 99 999-nt strict sequences), device-resident
     if not args.no_extra:
         seq_len, w = 99_999, 42

@@ -205,7 +205,8 @@ int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_sl
     return QD_OK;
 }
 
-// p.n_tiles must have been computed with tile_runs_for(c, total_runs)
+// p.n_tiles must match the tile size: big -> BIG_THREADS runs per tile, else SMALL_THREADS
+// (two 512-thread CTAs per SM were measured for variable-length batches too: no better than one 1024-thread CTA)
 int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s, bool big) {
     if (big) {
         switch (frames) {
@@ -282,12 +283,18 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     const uint64_t tile_runs = big ? BIG_THREADS : SMALL_THREADS;
     const size_t n_tiles = (size_t)((runs_upper_bound(total_nt, n_seq) + tile_runs - 1) / tile_runs);
     QD_CUDA(c, run_prefix.reserve((n_seq + 1) * sizeof(uint64_t)));
-    QD_CUDA(c, tile_first.reserve((n_tiles + 1) * sizeof(TileInfo)));
+    // one buffer: the tile map, then the 32-run map
+    const size_t warp_map_off = ((n_tiles + 1) * sizeof(TileInfo) + 15) & ~(size_t)15;
+    const uint64_t n_q = runs_upper_bound(total_nt, n_seq) / 32 + 1;
+    QD_CUDA(c, tile_first.reserve(warp_map_off + n_q * sizeof(uint32_t)));
     int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, run_prefix.as<uint64_t>(), block_sums, s);
     if (rc) return rc;
     const unsigned g = (unsigned)std::min<uint64_t>((n_seq + 255) / 256, (uint64_t)c->sm_count * 8);
     tile_info_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), offsets_dev, flat_base, n_seq, tile_first.as<TileInfo>(), n_tiles, tile_runs);
-    c->launches++;
+    uint32_t* warp_first = reinterpret_cast<uint32_t*>(tile_first.as<uint8_t>() + warp_map_off);
+    const unsigned gq = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_q + 255) / 256, (uint64_t)c->sm_count * 8));
+    warp_map_kernel<<<gq, 256, 0, s>>>(run_prefix.as<uint64_t>(), n_seq, tile_first.as<TileInfo>(), tile_runs, warp_first);
+    c->launches += 2;
     QD_CUDA(c, cudaGetLastError());
     FramesParams p{};
     p.dna = dna_dev;
@@ -295,6 +302,7 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     p.offsets = offsets_dev;
     p.run_prefix = run_prefix.as<uint64_t>();
     p.tiles = tile_first.as<TileInfo>();
+    p.warp_first = warp_first;
     p.n_seq = n_seq;
     p.n_tiles = (uint32_t)n_tiles;
     p.out = out_dev;

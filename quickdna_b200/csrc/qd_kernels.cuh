@@ -30,7 +30,7 @@ struct TileGeom {
     static constexpr int MAX_BYTES = RUNS * RUN_NT + 2 + 15 + 15;  // span + halo + alignment slack
     static constexpr int MAX_CHUNKS = (MAX_BYTES + 15) / 16 + 1;
     static constexpr int RAW_BYTES = MAX_CHUNKS * 16 + 64;         // one staged tile (+ slack: a run reads 80 B)
-    static constexpr int SEARCH_CAP = 2 * THREADS;                 // sequences of one tile whose run prefix is cached in smem
+    static constexpr int SEARCH_CAP = THREADS;                     // sequences of one tile whose geometry is cached in smem
     static constexpr int CTAS_PER_SM = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 4);
 };
 
@@ -137,6 +137,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -165,6 +173,7 @@ struct FramesParams {
     const uint64_t* offsets;     // CSR offsets [n_seq+1] or nullptr (uniform batch / single sequence)
     const uint64_t* run_prefix;  // exclusive prefix of ceil(len/48) [n_seq+1] or nullptr (uniform)
     const TileInfo* tiles;       // per tile (variable mode), or nullptr (uniform: closed form)
+    const uint32_t* warp_first;  // variable mode: sequence holding run 32 q, for every q (bounds each thread's search to 32 entries)
     uint64_t n_seq;
     uint64_t uniform_len;        // sequence length in uniform mode
     uint64_t uniform_magic;      // ceil(2^64 / uniform_runs): g / uniform_runs == umul64hi(g, magic) for g < 2^32
@@ -228,7 +237,11 @@ struct FramesSmem {
     alignas(128) uint8_t raw[STAGES][TileGeom<THREADS>::RAW_BYTES];  // multi-buffered raw input of a tile, 2-nt halo included
     alignas(8) uint64_t full[STAGES];             // mbarriers: raw[b] has landed
     uint64_t span[STAGES][2];                     // flat [start, end) of the input span staged in raw[b]
-    uint32_t search[TileGeom<THREADS>::SEARCH_CAP + 1];
+    // variable-length batches: run prefix and CSR offsets of the sequences a tile touches, prefetched one tile ahead
+    // with cp.async so that no dependent global load sits between two tiles (one CTA per SM: nothing else hides it)
+    alignas(8) uint64_t rp_cache[2][TileGeom<THREADS>::SEARCH_CAP + 2];
+    alignas(8) uint64_t off_cache[2][TileGeom<THREADS>::SEARCH_CAP + 2];
+    uint32_t warp_first[2][THREADS / 32];
 };
 
 static_assert(offsetof(FramesSmem<SMALL_THREADS>, lut) == 0 && (2 * 14 + PAIR_FLAG) * (1 + LUT_K1 + LUT_K2) + 2 <= sizeof(FramesSmem<SMALL_THREADS>),
@@ -274,6 +287,29 @@ __device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesPara
     }
 }
 
+// variable-length batches: start the asynchronous copy of the geometry window of the tile whose first sequence is r_first
+template <int THREADS>
+__device__ __forceinline__ void issue_geometry_window(FramesSmem<THREADS>& S, const FramesParams& p, uint64_t tile, uint64_t total_runs,
+                                                      uint32_t r_first, int b) {
+    constexpr int CAP = TileGeom<THREADS>::SEARCH_CAP;
+    if (threadIdx.x < THREADS / 32) {
+        const uint64_t q = tile * (TileGeom<THREADS>::RUNS / 32) + threadIdx.x;
+        if (q * 32 < total_runs) cp_async_4(&S.warp_first[b][threadIdx.x], p.warp_first + q);
+        else S.warp_first[b][threadIdx.x] = r_first;
+    }
+    for (uint32_t i = threadIdx.x; i <= (uint32_t)CAP + 1; i += THREADS) {
+        const uint64_t r = (uint64_t)r_first + i;
+        if (r <= p.n_seq) {
+            cp_async_8(&S.rp_cache[b][i], p.run_prefix + r);
+            cp_async_8(&S.off_cache[b][i], p.offsets + r);
+        } else {
+            S.rp_cache[b][i] = ~0ull;  // never <= a run index
+            S.off_cache[b][i] = 0;
+        }
+    }
+    cp_async_commit();
+}
+
 template <int FRAMES, int THREADS>
 __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) translate_frames_kernel(const FramesParams p) {
     constexpr int TILE_THREADS = THREADS, TILE_RUNS = TileGeom<THREADS>::RUNS, SEARCH_CAP = TileGeom<THREADS>::SEARCH_CAP;
@@ -309,6 +345,12 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
     const uint32_t lut_base = smem_u32(S.lut);
     const uint32_t pair_base = smem_u32(S.pair);
     const uint32_t pair_coef = p.pair_coef;
+    uint32_t first_cur = 0, first_nxt = 0;  // first sequence of this CTA's current / next tile (variable-length batches)
+    if (!uniform) {
+        if (blockIdx.x < n_tiles) first_cur = p.tiles[blockIdx.x].first_seq;
+        if (blockIdx.x < n_tiles) issue_geometry_window<THREADS>(S, p, blockIdx.x, total_runs, p.tiles[blockIdx.x].first_seq, 0);
+        if (blockIdx.x + (uint64_t)gridDim.x < n_tiles) first_nxt = p.tiles[blockIdx.x + (uint64_t)gridDim.x].first_seq;
+    }
     __syncthreads();
 
     uint32_t it = 0;
@@ -332,34 +374,38 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
             rd.flat_start = (uint64_t)r * p.uniform_len + in_seq;
             rd.out_base = (uint64_t)r * ((uint64_t)p.uniform_runs * (16u * FRAMES));
         } else {
-            // cache the run prefix of the sequences this tile touches, then upper_bound in smem
-            const uint32_t r_first = p.tiles[tile].first_seq;
-            for (uint32_t i = tid; i <= SEARCH_CAP; i += TILE_THREADS) {
-                uint64_t r = (uint64_t)r_first + i;
-                uint64_t v = (r <= p.n_seq) ? p.run_prefix[r] : ~0ull;
-                uint64_t rel = v >= g0 ? v - g0 : 0;
-                S.search[i] = rel > 0xffffffffull ? 0xffffffffu : (uint32_t)rel;
-            }
+            // the geometry window of this tile was requested one tile ago
+            cp_async_wait_all();
             __syncthreads();
+            const uint64_t* rpc = S.rp_cache[buf];
             const uint32_t gl = active ? tid : 0;  // run index relative to g0
-            uint32_t lo = 0, hi = SEARCH_CAP;      // largest i with search[i] <= gl
-            while (lo < hi) {
-                uint32_t mid = (lo + hi + 1) >> 1;
-                if (S.search[mid] <= gl) lo = mid; else hi = mid - 1;
+            const uint64_t g = g0 + gl;
+            // largest i with run_prefix[r_first + i] <= g: it is at or after the sequence of my warp's first run, and at most
+            // 32 entries further unless empty sequences intervene (then the whole window is searched)
+            uint32_t lo = 0, hi = SEARCH_CAP;
+            if (active) {
+                lo = S.warp_first[buf][tid >> 5] - first_cur;
+                const uint32_t near = min(lo + 32u, (uint32_t)SEARCH_CAP);
+                if (lo > (uint32_t)SEARCH_CAP) lo = SEARCH_CAP;  // window too small for this tile: global search below
+                else if (rpc[near] > g) hi = near;
             }
-            uint64_t r = (uint64_t)r_first + lo;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (rpc[mid] <= g) lo = mid; else hi = mid - 1;
+            }
+            uint64_t rp = rpc[lo], off_lo = S.off_cache[buf][lo], off_hi = S.off_cache[buf][lo + 1];
             if (lo == SEARCH_CAP) {  // more than SEARCH_CAP sequences start inside this tile: finish in global
-                uint64_t a = r, b = p.n_seq;  // invariant: run_prefix[a] <= g
-                const uint64_t g = g0 + gl;
+                uint64_t a = (uint64_t)first_cur + lo, b = p.n_seq;  // invariant: run_prefix[a] <= g
                 while (a < b) {
                     uint64_t mid = (a + b + 1) >> 1;
                     if (p.run_prefix[mid] <= g) a = mid; else b = mid - 1;
                 }
-                r = a;
+                rp = p.run_prefix[a];
+                off_lo = p.offsets[a];
+                off_hi = p.offsets[a + 1];
             }
-            const uint64_t rp = p.run_prefix[r];
-            const uint64_t o0 = p.offsets[r] - p.flat_base;
-            const uint64_t n = p.offsets[r + 1] - p.flat_base - o0;
+            const uint64_t o0 = off_lo - p.flat_base;
+            const uint64_t n = off_hi - off_lo;
             rd.m = (uint32_t)(g0 + gl - rp);
             rd.runs = (uint32_t)((n + RUN_NT - 1) / RUN_NT);
             rd.mod3 = (n >> 32) ? (uint32_t)(n % 3) : ((uint32_t)n % 3u);
@@ -402,6 +448,12 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
         }
         __syncthreads();  // every thread holds its bytes: raw[buf] can be refilled
         if (tid == 0 && tile + STAGES * (uint64_t)gridDim.x < n_tiles) stage_tile(S, p, tile + STAGES * (uint64_t)gridDim.x, total_runs, buf);
+        if (!uniform) {
+            // everyone is past this tile's geometry reads (barrier above) and past the previous tile's: refill the other window
+            if (tile + gridDim.x < n_tiles) issue_geometry_window<THREADS>(S, p, tile + gridDim.x, total_runs, first_nxt, buf ^ 1);
+            first_cur = first_nxt;
+            if (tile + 2 * (uint64_t)gridDim.x < n_tiles) first_nxt = p.tiles[tile + 2 * (uint64_t)gridDim.x].first_seq;
+        }
 
         // ---- phase 2: one run per thread: 48 codon starts -> 16 residues per frame per strand -----
         if (active) {
@@ -1182,6 +1234,22 @@ __global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t* __restri
             ti.pad_ = 0;
             tiles[t] = ti;
         }
+    }
+}
+
+// warp_first[q] = the sequence that holds run 32 q (largest r with run_prefix[r] <= 32 q), searched between the first
+// sequences of the enclosing tile and of the next one
+__global__ void __launch_bounds__(256) warp_map_kernel(const uint64_t* __restrict__ run_prefix, uint64_t n_seq, const TileInfo* __restrict__ tiles,
+                                                       uint64_t tile_runs, uint32_t* __restrict__ warp_first) {
+    const uint64_t total_runs = run_prefix[n_seq];
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 32 < total_runs; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = q * 32, t = g / tile_runs;
+        uint64_t lo = tiles[t].first_seq, hi = ((t + 1) * tile_runs < total_runs) ? tiles[t + 1].first_seq : n_seq - 1;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (run_prefix[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        warp_first[q] = (uint32_t)lo;
     }
 }
 
