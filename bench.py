@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=0)
     ap.add_argument("--revcomp-nt", type=int, default=250_000_000)
+    ap.add_argument("--expansion-windows", type=int, default=20_000_000, help="42-nt windows per GPU in the expansion leg")
     ap.add_argument("--canon-seqs", type=int, default=4000, help="99 999-nt sequences per GPU in the canonical-window leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -378,6 +379,34 @@ def main():
                     n_rep += 1
                 extra["canonical_windows"]["cpu_port"] = {"windows_per_s": n_rep * (seq_len - w + 1) / (time.perf_counter() - t0), "cores": 1,
                                                           "sample": f"{n_rep} x one {seq_len}-nt sequence, oracle/qd_oracle.c"}
+
+    # ---- extra: expansions of 42-nt windows with exactly two ambiguity codes, cap 16 (benches/expansions.rs:68-102 shape)
+    if not args.no_extra:
+        n_win, w = args.expansion_windows, 42
+        if n_win > 0 and n_win * w <= total_nt:
+            win = x[: n_win * w].clone().view(n_win, w)
+            g2 = torch.Generator(device=dev).manual_seed(11 + rank)
+            codes = torch.tensor(list(b"WMYHRKDSVBN"), dtype=torch.uint8, device=dev)
+            p1 = torch.randint(0, w, (n_win,), generator=g2, device=dev)
+            p2 = (p1 + 1 + torch.randint(0, w - 1, (n_win,), generator=g2, device=dev)) % w
+            rows_idx = torch.arange(n_win, device=dev)
+            win[rows_idx, p1] = codes[torch.randint(0, 11, (n_win,), generator=g2, device=dev)]
+            win[rows_idx, p2] = codes[torch.randint(0, 11, (n_win,), generator=g2, device=dev)]
+            del p1, p2, rows_idx
+            B.dev_error_reset(ctx)
+            c_d, oi_d, _ = B.expansion_windows_dev(win, 16, out=out, ctx=ctx)
+            n_rows = int(oi_d[n_win].item())
+            assert B.dev_error_fetch(win.view(-1), ctx=ctx) is None and n_rows * w <= out.numel()
+            ex_ms = timed(lambda: B.expansion_windows_dev(win, 16, out=out, ctx=ctx))
+            ex_bytes = n_win * (w + 16) + n_rows * w
+            ex_gbs = ex_bytes / (ex_ms * 1e-3) / 1e9
+            extra["expansion_windows"] = {
+                "workload": f"expansions of {n_win} 42-nt windows with exactly 2 ambiguity codes, cap 16, per GPU: {n_rows} rows "
+                            "(size_hint kernel + scan + write kernel per call)",
+                "rows_per_s": world * n_rows / (ex_ms * 1e-3), "windows_per_s": world * n_win / (ex_ms * 1e-3), "ms": ex_ms,
+                "roofline": {"bound": "hbm", "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak, "traffic": None,
+                             "kernel": "expansion_count_kernel + expansion_write_tiles_kernel", "algorithmic_bytes_per_launch": ex_bytes}}
+            del win, c_d, oi_d
 
     # ---- e2e: the host-pointer C-ABI call on pinned host buffers (H2D + kernels + D2H timed)
     e2e = None

@@ -237,6 +237,12 @@ int qd_canonical_windows_dev(qd_ctx *ctx, int enc, int forward_only, const uint8
  * span two sequences; out holds n_seq * (seq_len - w + 1) windows of w bytes, tightly packed */
 int qd_canonical_windows_batch_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev,
                                    size_t n_seq, size_t seq_len, size_t w, uint8_t *out_dev, void *stream);
+/* expansions on device buffers (w <= 64, max_expansions < 128): counts_dev[n_win], out_index_dev[n_win + 1] (device
+ * uint64; skipped windows repeat the next index), rows into out_dev while they fit out_capacity_rows
+ * (out_index_dev[n_win] tells how many there are).  out_dev may be NULL: counts and indices only. */
+int qd_expansion_windows_dev(qd_ctx *ctx, int enc, const uint8_t *windows_dev, size_t n_win, size_t w,
+                             uint64_t max_expansions, uint64_t *counts_dev, uint64_t *out_index_dev,
+                             uint8_t *out_dev, uint64_t out_capacity_rows, void *stream);
 int qd_windows_dev(qd_ctx *ctx, const uint8_t *seq_dev, size_t n, size_t w, uint8_t *out_dev,
                    void *stream);
 

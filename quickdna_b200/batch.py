@@ -295,6 +295,24 @@ def canonical_windows_batch_dev(dna, n_seq: int, seq_len: int, w: int = 42, out=
     return out[: n_seq * nw * w].view(n_seq * nw, w) if nw else out[:0].view(0, w)
 
 
+def expansion_windows_dev(windows, max_expansions: int = 16, out=None, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    """qd_expansion_windows_dev on a torch uint8 CUDA tensor [n_win, w]: returns (counts, out_index, rows buffer); rows are
+    written while they fit `out` (default: the worst case n_win * max_expansions rows)."""
+    import torch
+
+    ctx = ctx or N.default_context(windows.device.index or 0)
+    n_win, w = windows.shape
+    counts = torch.empty(n_win, dtype=torch.int64, device=windows.device)
+    out_index = torch.empty(n_win + 1, dtype=torch.int64, device=windows.device)
+    if out is None:
+        out = torch.empty(max(n_win * max_expansions * w, 16), dtype=torch.uint8, device=windows.device)
+    rc = N.lib().qd_expansion_windows_dev(ctx.handle, enc, C.c_void_p(windows.data_ptr()), n_win, w, max_expansions,
+                                          C.c_void_p(counts.data_ptr()), C.c_void_p(out_index.data_ptr()), C.c_void_p(out.data_ptr()),
+                                          out.numel() // w, _stream_ptr(torch))
+    ctx.check(rc)
+    return counts, out_index, out
+
+
 def dev_error_reset(ctx: Optional[N.Context] = None):
     import torch
 

@@ -1030,6 +1030,62 @@ extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const 
     return QD_OK;
 }
 
+static bool expansion_fast_path(size_t w, uint64_t max_expansions) { return w <= 64 && max_expansions < (uint64_t(1) << (EXP_DESC_MAX + 1)); }
+
+static ExpandParams expansion_params(qd_ctx* c, int enc, const uint8_t* windows_dev, size_t n_win, size_t w, uint64_t max_expansions,
+                                     uint64_t* counts_dev, uint64_t* emit_dev, uint64_t* out_index_dev, uint64_t* desc_dev) {
+    ExpandParams p{};
+    p.windows = windows_dev;
+    p.n_win = n_win;
+    p.w = (uint32_t)w;
+    p.max_expansions = max_expansions;
+    p.to_mask = tab(c, enc == QD_ENC_ASCII ? TAB_TO_MASK_ASCII : TAB_TO_MASK_MASK);
+    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
+    p.counts = counts_dev;
+    p.emit = emit_dev;
+    p.out_index = out_index_dev;
+    p.desc = desc_dev;
+    p.err_key = c->d_err;
+    return p;
+}
+
+// size_hint per window + exclusive scan of the rows each window emits
+static int expansion_count_dev(qd_ctx* c, const ExpandParams& p, cudaStream_t s) {
+    const unsigned grid = (unsigned)std::min<uint64_t>((p.n_win + 255) / 256, (uint64_t)c->sm_count * 16);
+    expansion_count_kernel<<<grid, 256, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return device_exclusive_scan<1>(c, p.emit, p.n_win, const_cast<uint64_t*>(p.out_index), c->block_sums, s);
+}
+
+static int expansion_write_tiles_dev(qd_ctx* c, ExpandParams p, uint8_t* out_dev, uint64_t row_cap, cudaStream_t s) {
+    p.out = out_dev;
+    p.row_cap = row_cap;
+    const uint64_t tiles = (p.n_win + 31) / 32;
+    const unsigned grid = (unsigned)std::min<uint64_t>((tiles + EXP_WARPS - 1) / EXP_WARPS, (uint64_t)c->sm_count * 6);
+    expansion_write_tiles_kernel<<<grid, 32 * EXP_WARPS, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_expansion_windows_dev(qd_ctx* c, int enc, const uint8_t* windows_dev, size_t n_win, size_t w, uint64_t max_expansions,
+                                        uint64_t* counts_dev, uint64_t* out_index_dev, uint8_t* out_dev, uint64_t out_capacity_rows,
+                                        void* stream) {
+    if (!c || w < 1 || !expansion_fast_path(w, max_expansions) || !counts_dev || !out_index_dev) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n_win == 0) return QD_OK;
+    cudaStream_t s = pick_stream(c, stream);
+    QD_CUDA(c, c->aux1.reserve(n_win * 8));  // emit
+    QD_CUDA(c, c->aux3.reserve(n_win * 8));  // descriptors
+    ExpandParams p = expansion_params(c, enc, windows_dev, n_win, w, max_expansions, counts_dev, c->aux1.as<uint64_t>(), out_index_dev,
+                                      c->aux3.as<uint64_t>());
+    if (int rc = expansion_count_dev(c, p, s)) return rc;
+    if (out_dev) return expansion_write_tiles_dev(c, p, out_dev, out_capacity_rows, s);
+    return QD_OK;
+}
+
 extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, size_t n_win, size_t w, uint64_t max_expansions,
                                     uint64_t* counts, uint64_t* out_index, uint8_t* out, qd_err* err) {
     clear_err(err);
@@ -1042,28 +1098,17 @@ extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, 
     }
     cudaStream_t s = c->stream;
     const size_t in_bytes = n_win * w;
+    const bool fast = expansion_fast_path(w, max_expansions);
     QD_CUDA(c, c->in.reserve(in_bytes + 16));
     QD_CUDA(c, c->aux0.reserve(n_win * 8));        // counts
     QD_CUDA(c, c->aux1.reserve(n_win * 8));        // emit
     QD_CUDA(c, c->aux2.reserve((n_win + 1) * 8));  // out_index
+    if (fast) QD_CUDA(c, c->aux3.reserve(n_win * 8));  // descriptors
     QD_CUDA(c, cudaMemcpyAsync(c->in.p, windows, in_bytes, cudaMemcpyHostToDevice, s));
     if (int rc = reset_err_key(c, s)) return rc;
-    ExpandParams p{};
-    p.windows = c->in.as<uint8_t>();
-    p.n_win = n_win;
-    p.w = (uint32_t)w;
-    p.max_expansions = max_expansions;
-    p.to_mask = tab(c, enc == QD_ENC_ASCII ? TAB_TO_MASK_ASCII : TAB_TO_MASK_MASK);
-    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
-    p.counts = c->aux0.as<uint64_t>();
-    p.emit = c->aux1.as<uint64_t>();
-    p.out_index = c->aux2.as<uint64_t>();
-    p.err_key = c->d_err;
-    const unsigned grid = (unsigned)std::min<uint64_t>((n_win + 255) / 256, (uint64_t)c->sm_count * 16);
-    expansion_count_kernel<<<grid, 256, 0, s>>>(p);
-    c->launches++;
-    QD_CUDA(c, cudaGetLastError());
-    if (int rc = device_exclusive_scan<1>(c, c->aux1.as<uint64_t>(), n_win, c->aux2.as<uint64_t>(), c->block_sums, s)) return rc;
+    ExpandParams p = expansion_params(c, enc, c->in.as<uint8_t>(), n_win, w, max_expansions, c->aux0.as<uint64_t>(), c->aux1.as<uint64_t>(),
+                                      c->aux2.as<uint64_t>(), fast ? c->aux3.as<uint64_t>() : nullptr);
+    if (int rc = expansion_count_dev(c, p, s)) return rc;
     QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->aux2.as<uint64_t>() + n_win, 8, cudaMemcpyDeviceToHost, s));
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
@@ -1083,11 +1128,15 @@ extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, 
     if (out_index) QD_CUDA(c, cudaMemcpyAsync(out_index, c->aux2.p, (n_win + 1) * 8, cudaMemcpyDeviceToHost, s));
     if (out && total_rows) {
         QD_CUDA(c, c->out.reserve(total_rows * w + 16));
-        p.out = c->out.as<uint8_t>();
-        const unsigned g2 = (unsigned)std::min<uint64_t>((total_rows + 255) / 256, (uint64_t)c->sm_count * 16);
-        expansion_write_kernel<<<g2, 256, 0, s>>>(p, total_rows);
-        c->launches++;
-        QD_CUDA(c, cudaGetLastError());
+        if (fast) {
+            if (int rc = expansion_write_tiles_dev(c, p, c->out.as<uint8_t>(), total_rows, s)) return rc;
+        } else {  // any w, any cap: one thread per row
+            p.out = c->out.as<uint8_t>();
+            const unsigned g2 = (unsigned)std::min<uint64_t>((total_rows + 255) / 256, (uint64_t)c->sm_count * 16);
+            expansion_write_kernel<<<g2, 256, 0, s>>>(p, total_rows);
+            c->launches++;
+            QD_CUDA(c, cudaGetLastError());
+        }
         QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, total_rows * w, cudaMemcpyDeviceToHost, s));
     }
     QD_CUDA(c, cudaStreamSynchronize(s));

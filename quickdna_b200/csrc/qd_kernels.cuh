@@ -1064,20 +1064,30 @@ struct ExpandParams {
     uint64_t* counts;        // size_hint per window, UINT64_MAX on overflow
     uint64_t* emit;          // expansions this window writes (0 if skipped)
     const uint64_t* out_index;  // exclusive scan of emit (phase 2)
+    uint64_t* desc;          // per window: its ambiguous positions, packed (fast path, see expansion_write_tiles_kernel)
+    uint64_t row_cap;        // rows `out` can hold (fast path: rows past it are not written)
     uint8_t* out;
     unsigned long long* err_key;
 };
+
+constexpr uint32_t EXP_DESC_MAX = 6;  // ambiguous positions a 64-bit descriptor holds: 6 x (6-bit position, 4-bit mask) + count
 
 // size_hint for a fresh iterator: prod(popcount) with checked arithmetic (src/expansions.rs:96-107)
 __global__ void __launch_bounds__(256) expansion_count_kernel(const ExpandParams p) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_win; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint8_t* win = p.windows + i * p.w;
-        uint64_t size = 0;
+        uint64_t size = 0, desc = 0;
+        uint32_t n_amb = 0;
         bool overflow = false;
-        for (uint32_t j = 0; j < p.w; j++) {
+        for (uint32_t jj = 0; jj < p.w; jj++) {
+            const uint32_t j = p.w - 1 - jj;  // last ambiguity first: it is the fastest odometer digit
             const uint32_t m = __ldg(p.to_mask + __ldg(win + j));
             if (m == 0) atomicMin(p.err_key, (unsigned long long)(i * p.w + j));
             const uint64_t states = (uint64_t)__popc(m);
+            if (states > 1) {
+                if (n_amb < EXP_DESC_MAX) desc |= (uint64_t)((j & 63u) | (m << 6)) << (10 * n_amb);
+                n_amb++;
+            }
             if (states > 1 && !overflow) {
                 if (size != 0 && states > 0xffffffffffffffffull / size) overflow = true;
                 else {
@@ -1091,6 +1101,7 @@ __global__ void __launch_bounds__(256) expansion_count_kernel(const ExpandParams
         const uint64_t count = overflow ? 0xffffffffffffffffull : size + 1;
         p.counts[i] = count;
         p.emit[i] = (count <= p.max_expansions) ? count : 0;
+        if (p.desc) p.desc[i] = desc | ((uint64_t)min(n_amb, 15u) << 60);
     }
 }
 
@@ -1119,6 +1130,82 @@ __global__ void __launch_bounds__(256) expansion_write_kernel(const ExpandParams
             const uint32_t base = __ffs(mm) - 1;  // 0..3 = A,T,C,G
             dst[j] = (uint8_t)(p.letters >> (8 * base));
         }
+    }
+}
+
+// Fast path (w <= 64, at most EXP_DESC_MAX ambiguous positions per emitted window): a warp owns 32 consecutive windows,
+// keeps their bytes in shared memory, and produces their rows 32 at a time -- one row per lane: copy the window
+// upper-cased (concrete positions are already final), patch the ambiguous positions with this row's odometer digits,
+// then drain the 32 staged rows with aligned 128-bit stores (head / tail bytes of the chunk individually).
+constexpr int EXP_WARPS = 8;
+struct ExpWarpSmem {
+    alignas(16) uint8_t win[32 * 64 + 16];
+    alignas(16) uint8_t stage[32 * 64 + 32];
+    uint64_t first_row[33];
+    uint64_t desc[32];
+};
+
+__global__ void __launch_bounds__(32 * EXP_WARPS) expansion_write_tiles_kernel(const ExpandParams p) {
+    __shared__ ExpWarpSmem SM[EXP_WARPS];
+    const int lane = threadIdx.x & 31;
+    ExpWarpSmem& S = SM[threadIdx.x >> 5];
+    const uint32_t w = p.w;
+    const uint64_t n_tiles = (p.n_win + 31) / 32;
+    for (uint64_t tile = (uint64_t)blockIdx.x * EXP_WARPS + (threadIdx.x >> 5); tile < n_tiles; tile += (uint64_t)gridDim.x * EXP_WARPS) {
+        const uint64_t i0 = tile * 32;
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, p.n_win - i0);
+        // geometry of my window, the tile's windows into shared memory
+        S.first_row[lane] = p.out_index[min(i0 + lane, p.n_win)];
+        if (lane == 0) S.first_row[32] = p.out_index[min(i0 + 32, p.n_win)];
+        S.desc[lane] = lane < (int)cnt ? p.desc[i0 + lane] : 0;
+        const uint8_t* src = p.windows + i0 * w;  // 32 w is a multiple of 32, but `windows` itself may be unaligned: bytes
+        for (uint32_t b = lane; b < cnt * w; b += 32) S.win[b] = __ldg(src + b);
+        __syncwarp();
+        const uint64_t row_lo = S.first_row[0], row_hi = S.first_row[cnt];
+        for (uint64_t r0 = row_lo; r0 < row_hi; r0 += 32) {
+            const uint32_t nrows = (uint32_t)min((uint64_t)32, row_hi - r0);
+            uint8_t* gdst = p.out + r0 * w;
+            const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
+            if (r0 + nrows > p.row_cap) break;  // caller's buffer is too small: out_index[n_win] tells how much was needed
+            if (lane < (int)nrows) {
+                const uint64_t row = r0 + lane;
+                uint32_t lo = 0, hi = cnt - 1;  // window of this row: largest j with first_row[j] <= row (skipped windows repeat)
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (S.first_row[mid] <= row) lo = mid; else hi = mid - 1;
+                }
+                uint64_t k = row - S.first_row[lo];
+                const uint64_t d = S.desc[lo];
+                const uint8_t* wsrc = S.win + lo * w;
+                uint8_t* dst = S.stage + phase + lane * w;
+                // upper case (masks are unchanged); two bytes at a time when every row starts at an even address
+                if (((w | phase) & 1u) == 0) {
+                    for (uint32_t j = 0; j < w; j += 2)
+                        *reinterpret_cast<uint16_t*>(dst + j) = *reinterpret_cast<const uint16_t*>(wsrc + j) & (uint16_t)0xdfdf;
+                } else {
+                    for (uint32_t j = 0; j < w; j++) dst[j] = wsrc[j] & 0xdfu;
+                }
+                const uint32_t n_amb = (uint32_t)(d >> 60);
+                for (uint32_t e = 0; e < n_amb; e++) {
+                    const uint32_t f = (uint32_t)(d >> (10 * e)) & 0x3ffu, pos = f & 63u, m = f >> 6;
+                    const uint32_t states = __popc(m);
+                    const uint32_t digit = (uint32_t)(k % states);
+                    k /= states;
+                    uint32_t mm = m;  // digit-th set bit of m, ascending (possibilities() order A,T,C,G)
+                    for (uint32_t t = 0; t < digit; t++) mm &= mm - 1;
+                    dst[pos] = (uint8_t)(p.letters >> (8 * (__ffs(mm) - 1)));
+                }
+            }
+            __syncwarp();
+            const uint32_t nbytes = nrows * w;
+            const uint32_t head = min(nbytes, (16u - phase) & 15u), body = (nbytes - head) >> 4;
+            if (lane < (int)head) gdst[lane] = S.stage[phase + lane];
+            for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(S.stage + phase + head + 16 * c));
+            const uint32_t done = head + 16 * body;
+            if (lane < (int)(nbytes - done)) gdst[done + lane] = S.stage[phase + done + lane];
+            __syncwarp();
+        }
+        __syncwarp();
     }
 }
 

@@ -521,6 +521,50 @@ def test_expansion_windows_random(B):
     assert int(B.expansion_windows(big)[0][0]) == V.SIZE_HINT_BIG[1]
 
 
+def test_expansion_windows_paths(B):
+    """Tiled fast path (w <= 64, cap < 128), generic path (larger caps / longer windows), both encodings, device API."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    codes = np.frombuffer(b"WMYHRKDSVBNwmyhrkdsvbn", dtype=np.uint8)
+    for n_win, w, cap, max_amb in ((257, 42, 16, 4), (100, 41, 100, 5), (64, 64, 127, 7), (50, 7, 16, 3), (33, 1, 4, 1),
+                                   (70, 42, 1000, 6), (20, 100, 64, 4), (300, 42, 1, 2)):
+        a = np.frombuffer(_rand(rng, n_win * w, b"ACGTacgt"), dtype=np.uint8).reshape(n_win, w).copy()
+        for i in range(n_win):
+            k = int(rng.integers(0, min(max_amb, w) + 1))
+            for j in rng.choice(w, size=k, replace=False):
+                a[i, j] = codes[rng.integers(0, len(codes))]
+        masks = np.stack([oracle.masks_of(a[i]) for i in range(n_win)])
+        for enc, arr in ((0, a), (1, masks)):
+            counts, out_index, rows = B.expansion_windows(arr, max_expansions=cap, enc=enc)
+            at = 0
+            for i in range(n_win):
+                hint = oracle.expansions_size_hint(masks[i])
+                assert int(counts[i]) == hint, (n_win, w, cap, enc, i)
+                if hint <= cap:
+                    assert int(out_index[i]) == at
+                    want = oracle.expansions(masks[i])
+                    want = oracle.ascii_of(want.reshape(-1)) if enc == 0 else want.tobytes()
+                    assert rows[at:at + hint].tobytes() == want, (n_win, w, cap, enc, i)
+                    at += hint
+                else:
+                    assert int(out_index[i]) == 2 ** 64 - 1
+            assert at == len(rows) == int(out_index[n_win])
+        if w <= 64 and cap < 128:
+            x = torch.from_numpy(a).cuda()
+            B.dev_error_reset()
+            c_d, oi_d, out_d = B.expansion_windows_dev(x, max_expansions=cap)
+            assert B.dev_error_fetch(x.view(-1)) is None
+            counts, out_index, rows = B.expansion_windows(a, max_expansions=cap)
+            total = int(oi_d[n_win].item())
+            assert total == len(rows)
+            assert out_d[: total * w].cpu().numpy().tobytes() == rows.tobytes()
+            assert (c_d.cpu().numpy().astype(np.uint64) == counts).all()
+    with pytest.raises(ValueError) as ei:
+        B.expansion_windows(np.frombuffer(b"ACGTXACG", dtype=np.uint8).reshape(2, 4))
+    assert (ei.value.seq_index, ei.value.pos, ei.value.kind) == (1, 0, 2)
+
+
 def test_windows(B):
     seq, wins = V.WINDOWS_10
     got = B.windows(seq.encode(), 10)
