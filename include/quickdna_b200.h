@@ -159,6 +159,22 @@ int qd_translate_frames_batch_uniform(qd_ctx *ctx, int table, int enc, int stric
 int qd_parse(qd_ctx *ctx, int strict, const uint8_t *ascii, size_t n, uint8_t *masks, size_t *n_masks,
              qd_err *err);
 
+/* FastaParser::<DnaSequence<T>>::parse, src/fasta.rs:207-491 (the format feeding batches): header lines start with
+ * '>' or ';', lines end at '\n' (a '\r' right before it is dropped), content lines go through the parse above.
+ * masks: one mask per nucleotide of all records back to back (capacity n); records[i] = header bytes
+ * [header_begin, header_end) of `text` (first header line start to the end of the last header line; both UINT64_MAX
+ * for the headerless record made of content before the first header), masks [content_begin, content_end) -- so
+ * content_begin/_end are the CSR offsets the batch entry points take -- and line_range [line_begin, line_end).
+ * concatenate_headers / allow_preceding_comment: FastaParseSettings, src/fasta.rs:67-110 (defaults 1 / 0).
+ * Call with masks == records == NULL to get *n_masks and *n_records only.  On a content error err->pos is the byte
+ * offset in `text` and err->seq_index the 1-based line number (Located::line_number, src/errors.rs:8-15). */
+typedef struct qd_fasta_record {
+    uint64_t header_begin, header_end, content_begin, content_end, line_begin, line_end;
+} qd_fasta_record;
+int qd_fasta_scan(qd_ctx *ctx, int strict, int concatenate_headers, int allow_preceding_comment,
+                  const uint8_t *text, size_t n, uint8_t *masks, size_t *n_masks, qd_fasta_record *records,
+                  size_t max_records, size_t *n_records, qd_err *err);
+
 /* DnaSequence::<Nucleotide>::canonical over every length-w window: src/canonical.rs:17-55,
  * 71-118, 129-179 applied as in benches/canonical.rs:29-34.  Strict alphabet only.
  * forward_only != 0 gives ForwardCanonical.  out: (n-w+1)*w bytes (0 windows if n < w),

@@ -310,6 +310,52 @@ def windows_all(masks, w_dna: int = 42, w_aa: int = 20) -> Tuple[np.ndarray, np.
     return dna, aa, origin, cs
 
 
+class _FastaRecord(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("header_begin", "header_end", "content_begin", "content_end", "line_begin", "line_end")]
+
+
+class FastaError(OracleError):
+    """Located<FastaParseError::ParseError(TranslationError)> (src/fasta.rs:413-423, src/errors.rs:8-15)."""
+
+    def __init__(self, kind, byte, pos, line):
+        super().__init__(kind, byte, pos, err_message(kind, byte))
+        self.line = line
+
+    def located(self) -> str:
+        return f"on line {self.line}: error parsing record: {err_message(self.kind, self.byte)}"
+
+
+def header_text(text: bytes, begin: int, end: int) -> str:
+    """The header string of a record: its header lines without the leading '>' / ';', joined by newlines."""
+    if begin == 2 ** 64 - 1:
+        return ""
+    lines = text[begin:end].split(b"\n")
+    lines = [ln[:-1] if i + 1 < len(lines) and ln.endswith(b"\r") else ln for i, ln in enumerate(lines)]
+    return "\n".join(ln[1:].decode("utf-8", "replace") for ln in lines)
+
+
+def fasta_scan(text, strict: bool = False, concatenate_headers: bool = True, allow_preceding_comment: bool = False):
+    """[(header, masks, (line_begin, line_end))] like FastaParser::<DnaSequence<T>>::parse_str (src/fasta.rs:425-480)."""
+    raw = bytes(text) if not isinstance(text, str) else text.encode()
+    a = _as_u8(raw)
+    masks = np.empty(max(len(a), 1), dtype=np.uint8)
+    cap = raw.count(b">") + raw.count(b";") + 2
+    recs = (_FastaRecord * cap)()
+    n_masks, n_recs, line = C.c_size_t(), C.c_size_t(), C.c_uint64()
+    err = _Err()
+    L = lib()
+    L.qdo_fasta_scan.restype = C.c_int
+    rc = L.qdo_fasta_scan(int(strict), int(concatenate_headers), int(allow_preceding_comment), _ptr(a), C.c_size_t(len(a)), _ptr(masks),
+                          C.byref(n_masks), recs, C.c_size_t(cap), C.byref(n_recs), C.byref(err), C.byref(line))
+    if rc != 0:
+        raise FastaError(err.kind, err.byte, err.pos, line.value)
+    out = []
+    for r in recs[: n_recs.value]:
+        out.append((header_text(raw, r.header_begin, r.header_end), masks[r.content_begin:r.content_end].copy(),
+                    (int(r.line_begin), int(r.line_end))))
+    return out
+
+
 def bench_all_frames_batch(slot: int, dna: np.ndarray, n_reads: int, read_len: int, threads: int, reps: int = 1,
                            out: Optional[np.ndarray] = None) -> Tuple[float, np.ndarray]:
     a = _as_u8(dna)

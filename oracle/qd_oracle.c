@@ -348,6 +348,88 @@ int qdo_parse(int strict, const uint8_t *ascii, size_t n, uint8_t *masks, size_t
     return QDO_OK;
 }
 
+/* ---------------------------------------------------------------- FASTA ----------- */
+
+/* src/fasta.rs:207-415.  The three parser states carry: the record's first line, where its header text starts and
+ * ends in `text`, and where its content starts in `masks`. */
+enum { FA_START_OF_FILE, FA_IN_HEADER, FA_IN_RECORD };
+
+int qdo_fasta_scan(int strict, int concatenate_headers, int allow_preceding_comment, const uint8_t *text, size_t n,
+                   uint8_t *masks, size_t *n_masks, qdo_fasta_record *records, size_t max_records, size_t *n_records,
+                   qdo_err *err, uint64_t *err_line) {
+    size_t k = 0, n_rec = 0;
+    int state = FA_START_OF_FILE;
+    uint64_t start_line = 1, header_begin = UINT64_MAX, header_end = UINT64_MAX, content_begin = 0;
+    uint64_t line_number = 0;
+    size_t pos = 0;
+    err->kind = QDO_OK;
+#define FA_EMIT(line_end_)                                                                        \
+    do {                                                                                          \
+        if (n_rec < max_records) {                                                                \
+            qdo_fasta_record r = {header_begin, header_end, content_begin, k, start_line, (line_end_)}; \
+            records[n_rec] = r;                                                                   \
+        }                                                                                         \
+        n_rec++;                                                                                  \
+    } while (0)
+    while (pos < n) { /* BufRead::lines: one line per '\n'; a final line without '\n' still counts */
+        size_t eol = pos;
+        while (eol < n && text[eol] != '\n') eol++;
+        size_t line_end = eol; /* exclusive, before the line break */
+        if (eol < n && line_end > pos && text[line_end - 1] == '\r') line_end--; /* CRLF */
+        line_number++;
+        const int is_header = line_end > pos && (text[pos] == '>' || text[pos] == ';'); /* :482-491 */
+        if (is_header) {
+            if (state == FA_START_OF_FILE) { /* :240-262 */
+                if (!allow_preceding_comment && k > 0) FA_EMIT(line_number);
+                content_begin = k;
+                start_line = line_number, header_begin = pos, header_end = line_end, state = FA_IN_HEADER;
+            } else if (state == FA_IN_HEADER) { /* :276-304 */
+                if (concatenate_headers) {
+                    header_end = line_end;
+                } else {
+                    FA_EMIT(line_number);
+                    start_line = line_number, header_begin = pos, header_end = line_end;
+                }
+            } else { /* InRecord: :322-340 */
+                FA_EMIT(line_number);
+                content_begin = k;
+                start_line = line_number, header_begin = pos, header_end = line_end, state = FA_IN_HEADER;
+            }
+        } else {
+            /* StartOfFile keeps content only if it may be emitted (:265-272); InHeader -> InRecord (:306-320);
+             * InRecord extends (:342-358) */
+            if (!(state == FA_START_OF_FILE && allow_preceding_comment)) {
+                for (size_t i = pos; i < line_end; i++) {
+                    const uint8_t b = text[i];
+                    if (b == ' ' || b == '\t') continue; /* src/rust_api.rs:316 */
+                    uint8_t m = 0, payload = 0;
+                    const int rc = qdo_decode_byte(b, strict, &m, &payload);
+                    if (rc != QDO_OK) {
+                        err->kind = rc;
+                        err->byte = payload;
+                        err->pos = i;
+                        *err_line = line_number;
+                        return rc;
+                    }
+                    masks[k++] = m;
+                }
+            }
+            if (state == FA_IN_HEADER) state = FA_IN_RECORD;
+        }
+        pos = eol < n ? eol + 1 : n;
+    }
+    /* advance_eof, :372-411 */
+    if (state == FA_START_OF_FILE) {
+        if (!allow_preceding_comment && k > 0) FA_EMIT(line_number + 1);
+    } else {
+        FA_EMIT(line_number + 1);
+    }
+#undef FA_EMIT
+    *n_masks = k;
+    *n_records = n_rec;
+    return QDO_OK;
+}
+
 /* ---------------------------------------------------------------- canonical ------- */
 
 /* src/canonical.rs:95-118: streaming first-occurrence relabelling. `step` = +1 / -1 walks the

@@ -108,6 +108,22 @@ size_t qdo_windows(const uint8_t *seq, size_t n, size_t w, uint8_t *out);
 size_t qdo_windows_all(const uint8_t *masks, size_t n, size_t w_dna, size_t w_aa, uint8_t *dna_out,
                        uint8_t *aa_out, uint64_t *origin, size_t counts[8]);
 
+/* FASTA ---------------------------------------------------------------------------- */
+/* FastaParser::<DnaSequence<T>>::parse, src/fasta.rs:207-415 (state machine) + :425-480 (driver): lines split as
+ * BufRead::lines does ('\n', with one '\r' before it dropped), header lines start with '>' or ';' (:482-491),
+ * content lines go through TryFrom<&[u8]> for DnaSequence (src/rust_api.rs:310-322).
+ * A record: header text bytes [header_begin, header_end) of `text` (first header line start to the end of the
+ * last header line, line break excluded; header_begin == header_end == UINT64_MAX for the headerless record made of
+ * preceding content), masks [content_begin, content_end) of `masks`, line_range [line_begin, line_end) 1-based.
+ * On a content error: err->pos = byte offset in `text`, *err_line = its 1-based line number.
+ * Returns the number of records (records beyond max_records are counted, not stored). */
+typedef struct {
+    uint64_t header_begin, header_end, content_begin, content_end, line_begin, line_end;
+} qdo_fasta_record;
+int qdo_fasta_scan(int strict, int concatenate_headers, int allow_preceding_comment, const uint8_t *text, size_t n,
+                   uint8_t *masks, size_t *n_masks, qdo_fasta_record *records, size_t max_records, size_t *n_records,
+                   qdo_err *err, uint64_t *err_line);
+
 /* Timed CPU baseline helpers (bench.py cpu_baseline / --impl reference) ------------ */
 /* Batch of n_reads reads of read_len ASCII nts each: per read, the Rust-API work of
  * src/rust_api.rs:263-270 after the parse of :310-322 (decode, 3 passes, materialised

@@ -121,6 +121,67 @@ def parse(ascii_seq, strict: bool = False, ctx: Optional[N.Context] = None) -> n
     return out[: k.value]
 
 
+class FastaRecordC(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("header_begin", "header_end", "content_begin", "content_end", "line_begin", "line_end")]
+
+
+class FastaScan:
+    """Result of fasta_scan: all records' nucleotides as masks back to back + CSR offsets (what the batch entry points
+    take), and per record its header text and line range (FastaRecord of src/fasta.rs:17-29)."""
+
+    def __init__(self, text: bytes, masks: np.ndarray, records):
+        self.masks = masks
+        self.offsets = np.array([r.content_begin for r in records] + [records[-1].content_end if records else 0], dtype=np.uint64)
+        self.line_ranges = [(int(r.line_begin), int(r.line_end)) for r in records]
+        self.headers = [self._header(text, r) for r in records]
+
+    @staticmethod
+    def _header(text: bytes, r) -> str:
+        if r.header_begin == 2 ** 64 - 1:
+            return ""
+        lines = text[r.header_begin:r.header_end].split(b"\n")
+        lines = [ln[:-1] if i + 1 < len(lines) and ln.endswith(b"\r") else ln for i, ln in enumerate(lines)]
+        return "\n".join(ln[1:].decode("utf-8", "replace") for ln in lines)
+
+    def __len__(self) -> int:
+        return len(self.headers)
+
+    def record(self, i: int):
+        """(header, masks, line_range) of record i."""
+        return self.headers[i], self.masks[int(self.offsets[i]):int(self.offsets[i + 1])], self.line_ranges[i]
+
+
+class FastaError(N.TranslationError):
+    """Located<FastaParseError::ParseError(TranslationError)> (src/fasta.rs:413-423): `.line` is the 1-based line."""
+
+    def located(self) -> str:
+        return f"on line {self.line}: error parsing record: {self}"
+
+
+def fasta_scan(text, strict: bool = False, concatenate_headers: bool = True, allow_preceding_comment: bool = False,
+               ctx: Optional[N.Context] = None) -> FastaScan:
+    """FastaParser::<DnaSequence<T>>::parse_str (src/fasta.rs:425-480) on the GPU."""
+    ctx = ctx or N.default_context()
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    a = _u8(raw)
+    L = N.lib()
+    n_masks, n_records = C.c_size_t(), C.c_size_t()
+    err = N.QdErr()
+    args = (ctx.handle, int(strict), int(concatenate_headers), int(allow_preceding_comment), _p(a if a.size else np.zeros(1, np.uint8)), a.size)
+    rc = L.qd_fasta_scan(*args, None, C.byref(n_masks), None, 0, C.byref(n_records), C.byref(err))
+    if rc in (1, 2, 3):
+        e = N.make_error(err)
+        fe = FastaError(str(e), e.kind, e.byte, e.pos, 0)
+        fe.line = int(err.seq_index)
+        raise fe
+    ctx.check(rc, err)
+    masks = np.empty(max(n_masks.value, 1), dtype=np.uint8)
+    recs = (FastaRecordC * max(n_records.value, 1))()
+    rc = L.qd_fasta_scan(*args, _p(masks), C.byref(n_masks), recs, n_records.value, C.byref(n_records), C.byref(err))
+    ctx.check(rc, err)
+    return FastaScan(raw, masks[: n_masks.value], list(recs[: n_records.value]))
+
+
 def canonical(dna, forward_only: bool = False, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None) -> np.ndarray:
     """DnaSequence::<Nucleotide>::canonical of one sequence of any length (src/rust_api.rs:374-377)."""
     ctx = ctx or N.default_context()

@@ -75,7 +75,7 @@ struct qd_ctx {
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
-    DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums, parse_counts, parse_offsets, canon_state;
+    DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums, parse_counts, parse_offsets, canon_state, fasta_scratch;
     Pipe pipe[N_PIPE];
     size_t chunk_bytes = size_t(64) << 20;   // input bytes per pipeline chunk
     int occ_frames[6] = {0, 0, 0, 0, 0, 0};  // [tile size][frames]
@@ -255,13 +255,13 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     return launch_frames(c, frames, p, s, big);
 }
 
-template <int MODE>
+template <int MODE, int OP = 0>
 int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* dst, DevBuf& block_sums, cudaStream_t s) {
     const uint64_t n_blocks = std::max<uint64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
     QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
-    scan_block_sums_kernel<MODE><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>());
-    scan_spine_kernel<<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks);
-    scan_finish_kernel<MODE><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst);
+    scan_block_sums_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>());
+    scan_spine_kernel<OP><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks);
+    scan_finish_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst);
     c->launches += 3;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
@@ -447,7 +447,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&c->in, &c->out, &c->aux0, &c->aux1, &c->aux2, &c->aux3, &c->run_prefix, &c->tile_first, &c->block_sums, &c->parse_counts,
-                      &c->parse_offsets, &c->canon_state}) b->release();
+                      &c->parse_offsets, &c->canon_state, &c->fasta_scratch}) b->release();
     for (int i = 0; i < N_PIPE; i++) {
         Pipe& P = c->pipe[i];
         for (DevBuf* b : {&P.in, &P.out, &P.offsets, &P.run_prefix, &P.tile_first, &P.block_sums}) b->release();
@@ -806,6 +806,131 @@ extern "C" int qd_canonical(qd_ctx* c, int enc, int forward_only, const uint8_t*
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;
     if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+    return QD_OK;
+}
+
+// ---- FASTA record scanner (src/fasta.rs:207-491) ------------------------------------------------------------------
+static_assert(sizeof(qd_fasta_record) == sizeof(FastaRecord), "qd_fasta_record and the kernel's record must agree");
+
+namespace {
+struct FastaRun {
+    FastaParams p{};
+    uint64_t* pre_base = nullptr;  // device: blk_last | blk_state | cnt x3 | pre x3
+};
+}  // namespace
+
+// passes 1-2 and the scans; totals stay on the device (p.pre_*[n_blocks], p.scalars)
+static int fasta_count_dev(qd_ctx* c, int strict, int concat, int allow, const uint8_t* text_dev, size_t n, FastaRun& R, cudaStream_t s) {
+    FastaParams& p = R.p;
+    p.text = text_dev;
+    p.n = n;
+    p.table = tab(c, strict ? TAB_PARSE_STRICT : TAB_PARSE);
+    p.concatenate_headers = concat;
+    p.allow_preceding_comment = allow;
+    const uint64_t span = (reinterpret_cast<uintptr_t>(text_dev) & 15) + n;
+    p.n_blocks = std::max<uint64_t>(1, (span + FA_BLOCK_BYTES - 1) / FA_BLOCK_BYTES);
+    const uint64_t nb1 = p.n_blocks + 1;
+    QD_CUDA(c, c->fasta_scratch.reserve((8 * nb1 + 2) * 8));
+    uint64_t* base = c->fasta_scratch.as<uint64_t>();
+    p.scalars = reinterpret_cast<unsigned long long*>(base);
+    p.blk_last = base + 2;
+    uint64_t* blk_state = base + 2 + nb1;
+    p.blk_state = blk_state;
+    p.cnt_kept = base + 2 + 2 * nb1;
+    p.cnt_recs = base + 2 + 3 * nb1;
+    p.cnt_nl = base + 2 + 4 * nb1;
+    uint64_t* pre_kept = base + 2 + 5 * nb1;
+    uint64_t* pre_recs = base + 2 + 6 * nb1;
+    uint64_t* pre_nl = base + 2 + 7 * nb1;
+    p.pre_kept = pre_kept;
+    p.pre_recs = pre_recs;
+    p.pre_nl = pre_nl;
+    p.err_key = c->d_err;
+    QD_CUDA(c, cudaMemsetAsync(p.scalars, 0xff, 8, s));
+    QD_CUDA(c, cudaMemsetAsync(p.scalars + 1, 0, 8, s));
+    const unsigned grid = (unsigned)std::min<uint64_t>(p.n_blocks, (uint64_t)c->sm_count * 8);
+    fasta_lines_kernel<<<grid, FA_THREADS, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    if (int rc = device_exclusive_scan<1, 1>(c, p.blk_last, p.n_blocks, blk_state, c->block_sums, s)) return rc;
+    fasta_pass_kernel<false><<<grid, FA_THREADS, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    if (int rc = device_exclusive_scan<1>(c, p.cnt_kept, p.n_blocks, pre_kept, c->block_sums, s)) return rc;
+    if (int rc = device_exclusive_scan<1>(c, p.cnt_recs, p.n_blocks, pre_recs, c->block_sums, s)) return rc;
+    if (int rc = device_exclusive_scan<1>(c, p.cnt_nl, p.n_blocks, pre_nl, c->block_sums, s)) return rc;
+    return QD_OK;
+}
+
+static int fasta_write_dev(qd_ctx* c, FastaRun& R, uint8_t* masks_dev, FastaRecord* records_dev, uint64_t max_records, uint64_t n_records,
+                           uint64_t shift, cudaStream_t s) {
+    FastaParams& p = R.p;
+    p.masks = masks_dev;
+    p.records = records_dev;
+    p.max_records = max_records;
+    const unsigned grid = (unsigned)std::min<uint64_t>(p.n_blocks, (uint64_t)c->sm_count * 8);
+    fasta_pass_kernel<true><<<grid, FA_THREADS, 0, s>>>(p);
+    c->launches++;
+    if (n_records) {
+        const unsigned g4 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_records + 255) / 256, (uint64_t)c->sm_count * 8));
+        fasta_finish_kernel<<<g4, 256, 0, s>>>(p, n_records, shift);
+        c->launches++;
+    }
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int allow_preceding_comment, const uint8_t* text, size_t n,
+                             uint8_t* masks, size_t* n_masks, qd_fasta_record* records, size_t max_records, size_t* n_records, qd_err* err) {
+    clear_err(err);
+    if (n_masks) *n_masks = 0;
+    if (n_records) *n_records = 0;
+    if (!c || (n && !text)) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, text, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    FastaRun R;
+    if (int rc = fasta_count_dev(c, strict, concatenate_headers, allow_preceding_comment, c->in.as<uint8_t>(), n, R, s)) return rc;
+    const FastaParams& p = R.p;
+    // totals: kept bytes, record starts, first header position, kept before it inside its block
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch + 0, p.pre_kept + p.n_blocks, 8, cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch + 1, p.pre_recs + p.n_blocks, 8, cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch + 2, p.scalars, 16, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
+    if (key != NO_ERROR_KEY) {
+        uint64_t line = 1;  // Located::line_number (src/errors.rs:8-15): lines are counted as BufRead::lines does
+        for (size_t i = 0; i < key; i++) line += text[i] == '\n';
+        uint8_t payload = 0;
+        int kind = classify_byte(QD_ENC_ASCII, strict, text[key], &payload);
+        if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+        return set_err(err, kind, payload, key, line);
+    }
+    const uint64_t total_kept = c->h_scratch[0], rec_starts = c->h_scratch[1], first_header = c->h_scratch[2];
+    uint64_t before = total_kept;
+    if (first_header != FA_NONE) {
+        const uint64_t blk = ((reinterpret_cast<uintptr_t>(p.text) & 15) + first_header) / FA_BLOCK_BYTES;
+        uint64_t pre = 0;
+        QD_CUDA(c, cudaMemcpyAsync(&pre, p.pre_kept + blk, 8, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        before = pre + c->h_scratch[3];
+    }
+    const uint64_t shift = (!allow_preceding_comment && before > 0) ? 1 : 0;
+    const uint64_t total_records = rec_starts + shift;
+    if (n_masks) *n_masks = (size_t)total_kept;
+    if (n_records) *n_records = (size_t)total_records;
+    if (!masks && !records) return QD_OK;  // counting call
+    if (!masks || (total_records && !records) || max_records < total_records) return QD_ERR_INVALID_ARGUMENT;
+    QD_CUDA(c, c->out.reserve(total_kept + 16));
+    QD_CUDA(c, c->aux0.reserve((total_records + 1) * sizeof(FastaRecord)));
+    if (int rc = fasta_write_dev(c, R, c->out.as<uint8_t>(), c->aux0.as<FastaRecord>(), total_records, total_records, shift, s)) return rc;
+    if (total_kept) QD_CUDA(c, cudaMemcpyAsync(masks, c->out.p, total_kept, cudaMemcpyDeviceToHost, s));
+    if (total_records) QD_CUDA(c, cudaMemcpyAsync(records, c->aux0.p, total_records * sizeof(FastaRecord), cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaStreamSynchronize(s));
     return QD_OK;
 }
 

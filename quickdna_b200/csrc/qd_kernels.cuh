@@ -1217,13 +1217,18 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;  // items per thread
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
 
-__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* warp_sums) {
+// OP 0: sum, OP 1: max (identity 0 for both)
+template <int OP>
+__device__ __forceinline__ uint64_t scan_comb(uint64_t a, uint64_t b) { return OP ? (a > b ? a : b) : a + b; }
+
+template <int OP>
+__device__ __forceinline__ uint64_t block_exclusive_scan_op(uint64_t v, uint64_t* total, uint64_t* warp_sums) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
+        if (lane >= o) x = scan_comb<OP>(x, y);
     }
     if (lane == 31) warp_sums[wid] = x;
     __syncthreads();
@@ -1232,14 +1237,19 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* t
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint64_t y = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += y;
+            if (lane >= o) s = scan_comb<OP>(s, y);
         }
         warp_sums[lane] = s;  // inclusive
     }
     __syncthreads();
     const uint64_t warp_off = wid ? warp_sums[wid - 1] : 0;
     *total = warp_sums[(blockDim.x >> 5) - 1];
-    return warp_off + x - v;
+    uint64_t prev = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) prev = 0;
+    return scan_comb<OP>(warp_off, prev);
+}
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* warp_sums) {
+    return block_exclusive_scan_op<0>(v, total, warp_sums);
 }
 
 // value(i): 0 = runs of sequence i from CSR offsets (ceil(len/48)); 1 = raw uint64 values
@@ -1249,20 +1259,21 @@ __device__ __forceinline__ uint64_t scan_value(const uint64_t* src, uint64_t i) 
     return src[i];
 }
 
-template <int MODE>
+template <int MODE, int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint64_t* src, uint64_t n, uint64_t* block_sums) {
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) s += scan_value<MODE>(src, base + k);
+        if (base + k < n) s = scan_comb<OP>(s, scan_value<MODE>(src, base + k));
     uint64_t total;
-    block_exclusive_scan(s, &total, warp_sums);
+    block_exclusive_scan_op<OP>(s, &total, warp_sums);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
 // single CTA: exclusive scan of the block sums in place
+template <int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* block_sums, uint64_t n_blocks) {
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
@@ -1272,17 +1283,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* bloc
         const uint64_t i = base + threadIdx.x;
         const uint64_t v = i < n_blocks ? block_sums[i] : 0;
         uint64_t total;
-        const uint64_t ex = block_exclusive_scan(v, &total, warp_sums);
+        const uint64_t ex = block_exclusive_scan_op<OP>(v, &total, warp_sums);
         const uint64_t carry = carry_s;
-        if (i < n_blocks) block_sums[i] = carry + ex;
+        if (i < n_blocks) block_sums[i] = scan_comb<OP>(carry, ex);
         __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
+        if (threadIdx.x == 0) carry_s = scan_comb<OP>(carry, total);
         __syncthreads();
     }
 }
 
 // dst[0..n] = exclusive scan (dst[n] = grand total)
-template <int MODE>
+template <int MODE, int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_t* src, uint64_t n, const uint64_t* block_sums,
                                                                    uint64_t* dst) {
     __shared__ uint64_t warp_sums[32];
@@ -1292,14 +1303,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         v[k] = (base + k < n) ? scan_value<MODE>(src, base + k) : 0;
-        s += v[k];
+        s = scan_comb<OP>(s, v[k]);
     }
     uint64_t total;
-    uint64_t ex = block_exclusive_scan(s, &total, warp_sums) + block_sums[blockIdx.x];
+    uint64_t ex = scan_comb<OP>(block_exclusive_scan_op<OP>(s, &total, warp_sums), block_sums[blockIdx.x]);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         if (base + k < n) dst[base + k] = ex;
-        ex += v[k];
+        ex = scan_comb<OP>(ex, v[k]);
         if (base + k + 1 == n) dst[n] = ex;
     }
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) dst[0] = 0;
@@ -1543,6 +1554,253 @@ __global__ void __launch_bounds__(256) canon_seq_write_kernel(const CanonSeqPara
         const uint32_t c = __ldg(p.decode + __ldg(p.dna + (use_rev ? p.n - 1 - i : i))) & 3u;
         const uint32_t y = ((use_rev ? rv : fw) >> (2 * c)) & 3u;
         p.out[i] = (uint8_t)(p.letters >> (8 * y));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FASTA record scanner (FastaParser::<DnaSequence<T>>::parse, src/fasta.rs:207-491): the line state machine of the
+// reference as data-parallel passes over the text.
+//   line type   a line is a header iff its first byte is '>' or ';'; the type of the line a byte belongs to is that of
+//               the last line start at or before it -> "last writer wins" = a MAX scan over (position, type)
+//   records     a header line starts a record unless headers are concatenated and the previous line is a header too;
+//               content before the first header is a headerless record (or dropped, unvalidated, when a preceding
+//               comment is allowed)
+//   content     bytes of non-header lines minus line breaks ('\n', and a '\r' right before it), ' ' and '\t', each
+//               validated and turned into a mask (src/rust_api.rs:310-322) -> stream compaction
+// pass 1: last line start per 4 KiB block + first header position.  max-scan over blocks.
+// pass 2: per block kept bytes / record starts / line breaks (+ first error).  three sum scans.
+// pass 3: compacted masks + one entry per record.  pass 4: per record, the *_end fields and the header extent.
+// ------------------------------------------------------------------------------------------------
+struct FastaRecord {  // == qd_fasta_record
+    uint64_t header_begin, header_end, content_begin, content_end, line_begin, line_end;
+};
+constexpr int FA_THREADS = 256;
+constexpr int FA_BLOCK_BYTES = FA_THREADS * 16;
+constexpr uint64_t FA_NONE = ~0ull;
+
+struct FastaParams {
+    const uint8_t* text;
+    uint64_t n;
+    const uint8_t* table;  // 256 bytes: mask | PARSE_SKIP | 0 (the parse table of the chosen alphabet)
+    int concatenate_headers, allow_preceding_comment;
+    uint64_t n_blocks;
+    uint64_t* blk_last;         // pass 1: ((position + 1) << 2 | type) of the block's last line start, 0 if none
+    const uint64_t* blk_state;  // exclusive max scan of blk_last
+    unsigned long long* scalars;  // [0] position of the first header line (FA_NONE if none), [1] kept bytes before it
+                                  // inside its own block
+    uint64_t* cnt_kept;
+    uint64_t* cnt_recs;
+    uint64_t* cnt_nl;
+    const uint64_t* pre_kept;  // exclusive sum scans, [n_blocks + 1]
+    const uint64_t* pre_recs;
+    const uint64_t* pre_nl;
+    uint8_t* masks;
+    FastaRecord* records;
+    uint64_t max_records;
+    unsigned long long* err_key;
+};
+
+__device__ __forceinline__ bool fa_is_header_byte(uint32_t c) { return c == '>' || c == ';'; }
+
+// the 16 bytes of granule g (bytes outside [text, text + n) come back as 0 with in_range false), the byte before and
+// the byte after
+struct FaGranule {
+    uint8_t b[16];
+    uint64_t i0;        // text index of b[0] (may be "negative" = wrapped when the granule starts before the text)
+    uint32_t lo, hi;    // valid k range [lo, hi)
+    uint32_t prev, next;  // text[i0 + lo - 1] ('\n' at the file start), text[i0 + hi] (0 at the end)
+};
+__device__ __forceinline__ void fa_load(const FastaParams& p, uint64_t g, FaGranule& G) {
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.text), hi = lo + p.n;
+    const uintptr_t a = (lo & ~(uintptr_t)15) + 16 * g;
+    G.i0 = (uint64_t)(a - lo);
+    G.lo = a < lo ? (uint32_t)(lo - a) : 0u;
+    G.hi = a + 16 <= hi ? 16u : (a < hi ? (uint32_t)(hi - a) : 0u);
+    if (G.lo == 0 && G.hi == 16) {
+        const uint4 x = ldg_cached(reinterpret_cast<const void*>(a));
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) G.b[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) G.b[k] = (k >= (int)G.lo && k < (int)G.hi) ? *reinterpret_cast<const uint8_t*>(a + k) : (uint8_t)0;
+    }
+    G.prev = '\n';
+    G.next = 0;
+    if (G.lo < G.hi) {
+        if (a + G.lo > lo) G.prev = *reinterpret_cast<const uint8_t*>(a + G.lo - 1);
+        if (a + G.hi < hi) G.next = *reinterpret_cast<const uint8_t*>(a + G.hi);
+    }
+}
+
+// ((position + 1) << 2 | type) of the last line start among the granule's bytes, 0 if none; type 3 = header, 2 = other
+__device__ __forceinline__ uint64_t fa_last_line_start(const FaGranule& G, unsigned long long* first_header) {
+    uint64_t last = 0;
+    uint32_t prevc = G.prev;
+    for (uint32_t k = G.lo; k < G.hi; k++) {
+        const uint32_t c = G.b[k];
+        if (prevc == '\n') {
+            const bool h = fa_is_header_byte(c);
+            last = ((G.i0 + k + 1) << 2) | (h ? 3u : 2u);
+            if (h && first_header) atomicMin(first_header, (unsigned long long)(G.i0 + k));
+        }
+        prevc = c;
+    }
+    return last;
+}
+
+__global__ void __launch_bounds__(FA_THREADS) fasta_lines_kernel(const FastaParams p) {
+    __shared__ uint64_t warp_sums[32];
+    for (uint64_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
+        FaGranule G;
+        fa_load(p, blk * FA_THREADS + threadIdx.x, G);
+        const uint64_t last = fa_last_line_start(G, p.scalars);
+        uint64_t total;
+        block_exclusive_scan_op<1>(last, &total, warp_sums);
+        if (threadIdx.x == 0) p.blk_last[blk] = total;
+        __syncthreads();
+    }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(FA_THREADS) fasta_pass_kernel(const FastaParams p) {
+    __shared__ uint8_t tab_s[256];
+    __shared__ uint64_t warp_sums[32];
+    __shared__ __align__(16) uint8_t stage[FA_BLOCK_BYTES + 16];
+    tab_s[threadIdx.x] = __ldg(p.table + threadIdx.x);
+    __syncthreads();
+    const uint64_t first_header = p.scalars[0];
+    // records are shifted by one when content before the first header makes a headerless record
+    uint64_t shift = 0;
+    if (WRITE && !p.allow_preceding_comment) {
+        const uint64_t before = first_header == FA_NONE ? p.pre_kept[p.n_blocks]
+                                                        : p.pre_kept[(((reinterpret_cast<uintptr_t>(p.text) & 15) + first_header) / FA_BLOCK_BYTES)] + p.scalars[1];
+        shift = before > 0 ? 1 : 0;
+    }
+    for (uint64_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
+        FaGranule G;
+        fa_load(p, blk * FA_THREADS + threadIdx.x, G);
+        uint64_t total;
+        // type of the line my first byte's predecessor belongs to
+        const uint64_t mine = fa_last_line_start(G, nullptr);
+        uint64_t before = block_exclusive_scan_op<1>(mine, &total, warp_sums);
+        __syncthreads();
+        before = max(before, p.blk_state[blk]);
+        uint32_t cur_type = before ? (uint32_t)(before & 3u) : 2u;
+        // ---- walk my bytes: what is kept, where records start, how many lines end ----
+        uint8_t keep[16];
+        uint32_t n_keep = 0, n_rec = 0, n_nl = 0, rec_at[8], rec_keep[8], rec_nl[8];  // a record start needs >= 2 bytes: at most 8
+        uint32_t prevc = G.prev;
+        for (uint32_t k = G.lo; k < G.hi; k++) {
+            const uint32_t c = G.b[k];
+            const uint64_t i = G.i0 + k;
+            if (prevc == '\n') {
+                const uint32_t prev_type = cur_type;
+                cur_type = fa_is_header_byte(c) ? 3u : 2u;
+                if (cur_type == 3u && (!p.concatenate_headers || prev_type != 3u)) {
+                    rec_at[n_rec] = k;
+                    rec_keep[n_rec] = n_keep;
+                    rec_nl[n_rec] = n_nl;
+                    n_rec++;
+                }
+            }
+            if (c == '\n') n_nl++;
+            else if (cur_type == 2u) {
+                const uint32_t nextc = k + 1 < G.hi ? (uint32_t)G.b[k + 1] : G.next;
+                const bool line_break_cr = c == '\r' && nextc == '\n';
+                const bool dropped_comment = p.allow_preceding_comment && i < first_header;
+                if (!line_break_cr && !dropped_comment) {
+                    const uint32_t t = tab_s[c];
+                    if (t == 0) { if (!WRITE) atomicMin(p.err_key, (unsigned long long)i); }
+                    else if (t != PARSE_SKIP) keep[n_keep++] = (uint8_t)t;
+                }
+            }
+            prevc = c;
+        }
+        // ---- block-level prefixes ----
+        const uint64_t ex_keep = block_exclusive_scan_op<0>(n_keep, &total, warp_sums);
+        const uint64_t blk_keep = total;
+        __syncthreads();
+        const uint64_t ex_rec = block_exclusive_scan_op<0>(n_rec, &total, warp_sums);
+        const uint64_t blk_rec = total;
+        __syncthreads();
+        const uint64_t ex_nl = block_exclusive_scan_op<0>(n_nl, &total, warp_sums);
+        const uint64_t blk_nl = total;
+        __syncthreads();
+        if (!WRITE) {
+            if (threadIdx.x == 0) {
+                p.cnt_kept[blk] = blk_keep;
+                p.cnt_recs[blk] = blk_rec;
+                p.cnt_nl[blk] = blk_nl;
+            }
+            // kept bytes of this block before the first header line (it is the first record start of its thread)
+            if (first_header != FA_NONE && first_header >= G.i0 + G.lo && first_header < G.i0 + G.hi && G.lo < G.hi) {
+                uint32_t kb = 0;
+                for (uint32_t r = 0; r < n_rec; r++)
+                    if (G.i0 + rec_at[r] == first_header) kb = rec_keep[r];
+                p.scalars[1] = ex_keep + kb;
+            }
+        } else {
+            const uint64_t out0 = p.pre_kept[blk];
+            uint8_t* gdst = p.masks + out0;
+            const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
+            for (uint32_t j = 0; j < n_keep; j++) stage[phase + ex_keep + j] = keep[j];
+            for (uint32_t r = 0; r < n_rec; r++) {
+                const uint64_t idx = shift + p.pre_recs[blk] + ex_rec + r;
+                if (idx < p.max_records) {
+                    FastaRecord rec;
+                    rec.header_begin = G.i0 + rec_at[r];
+                    rec.header_end = 0;
+                    rec.content_begin = out0 + ex_keep + rec_keep[r];
+                    rec.content_end = 0;
+                    rec.line_begin = p.pre_nl[blk] + ex_nl + rec_nl[r] + 1;
+                    rec.line_end = 0;
+                    p.records[idx] = rec;
+                }
+            }
+            __syncthreads();
+            const uint32_t nbytes = (uint32_t)blk_keep;
+            const uint32_t head = min(nbytes, (16u - phase) & 15u), body = (nbytes - head) >> 4;
+            if (threadIdx.x < head) gdst[threadIdx.x] = stage[phase + threadIdx.x];
+            for (uint32_t c = threadIdx.x; c < body; c += FA_THREADS)
+                stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(stage + phase + head + 16 * c));
+            const uint32_t done = head + 16 * body;
+            if (threadIdx.x < nbytes - done) gdst[done + threadIdx.x] = stage[phase + done + threadIdx.x];
+            __syncthreads();
+        }
+    }
+}
+
+// pass 4: one thread per record: where its content and its lines end (= where the next record's begin), and the extent
+// of its header lines in the text; record 0 is the headerless one when `shift` says so
+__global__ void __launch_bounds__(256) fasta_finish_kernel(const FastaParams p, uint64_t n_records, uint64_t shift) {
+    const uint64_t total_kept = p.pre_kept[p.n_blocks];
+    const uint64_t n_lines = p.pre_nl[p.n_blocks] + ((p.n > 0 && p.text[p.n - 1] != '\n') ? 1 : 0);
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_records && r < p.max_records; r += (uint64_t)gridDim.x * blockDim.x) {
+        const bool has_next = r + 1 < n_records && r + 1 < p.max_records;
+        const uint64_t next_content = has_next ? p.records[r + 1].content_begin : total_kept;
+        const uint64_t next_line = has_next ? p.records[r + 1].line_begin : n_lines + 1;
+        if (r == 0 && shift) {
+            FastaRecord rec = {FA_NONE, FA_NONE, 0, next_content, 1, next_line};
+            p.records[0].header_begin = rec.header_begin;
+            p.records[0].header_end = rec.header_end;
+            p.records[0].content_begin = 0;
+            p.records[0].content_end = rec.content_end;
+            p.records[0].line_begin = 1;
+            p.records[0].line_end = rec.line_end;
+            continue;
+        }
+        uint64_t pos = p.records[r].header_begin, header_end = pos;
+        for (;;) {  // the header line starting at pos, then (concatenated headers) the header lines right after it
+            uint64_t eol = pos;
+            while (eol < p.n && p.text[eol] != '\n') eol++;
+            header_end = (eol < p.n && eol > pos && p.text[eol - 1] == '\r') ? eol - 1 : eol;
+            if (!p.concatenate_headers || eol + 1 >= p.n || !fa_is_header_byte(p.text[eol + 1])) break;
+            pos = eol + 1;
+        }
+        p.records[r].header_end = header_end;
+        p.records[r].content_end = next_content;
+        p.records[r].line_end = next_line;
     }
 }
 

@@ -671,3 +671,88 @@ def test_device_api_six_frames_large_properties(B, N):
     B.translate_frames_uniform_dev(x, n_reads, L, out=out)
     e = B.dev_error_fetch(x, uniform_len=L)
     assert e is not None and (e.seq_index, e.pos, str(e)) == (123_456, 789, "bad nucleotide: '@'")
+
+
+# ------------------------------------------------------------------ FASTA record scanner (src/fasta.rs)
+
+
+def _fasta_same(B, text, strict, concat, allow):
+    try:
+        want = oracle.fasta_scan(text, strict=strict, concatenate_headers=concat, allow_preceding_comment=allow)
+        werr = None
+    except oracle.FastaError as e:
+        want, werr = None, e
+    if werr is not None:
+        with pytest.raises(ValueError) as ei:
+            B.fasta_scan(text, strict=strict, concatenate_headers=concat, allow_preceding_comment=allow)
+        assert (ei.value.kind, ei.value.byte, ei.value.pos, ei.value.line, ei.value.located()) == (
+            werr.kind, werr.byte, werr.pos, werr.line, werr.located())
+        return
+    got = B.fasta_scan(text, strict=strict, concatenate_headers=concat, allow_preceding_comment=allow)
+    assert len(got) == len(want)
+    for i, (h, m, lr) in enumerate(want):
+        gh, gm, glr = got.record(i)
+        assert (gh, gm.tobytes(), glr) == (h, m.tobytes(), lr), (i, concat, allow, strict)
+
+
+@pytest.mark.parametrize("text,settings,want", V.FASTA)
+def test_fasta_vectors(B, text, settings, want):
+    for concat, allow in settings:
+        got = B.fasta_scan(text, concatenate_headers=concat, allow_preceding_comment=allow)
+        assert [(got.record(i)[0], oracle.ascii_of(got.record(i)[1]).decode(), got.record(i)[2]) for i in range(len(got))] == want
+    for concat in (False, True):
+        for allow in (False, True):
+            _fasta_same(B, text, False, concat, allow)
+            _fasta_same(B, text, True, concat, allow)
+
+
+@pytest.mark.parametrize("text,strict,line,kind,byte,message", V.FASTA_ERRORS)
+def test_fasta_error_vectors(B, text, strict, line, kind, byte, message):
+    with pytest.raises(ValueError) as ei:
+        B.fasta_scan(text, strict=strict)
+    assert (ei.value.line, ei.value.kind, ei.value.byte, ei.value.located()) == (line, kind, byte, message)
+
+
+def test_fasta_random(B):
+    """Random files: line lengths 0..200 (plus a few multi-block lines), LF and CRLF, headers in runs, blanks, and an
+    occasional bad byte; every setting combination against the oracle."""
+    rng = np.random.default_rng(41)
+    for trial in range(40):
+        parts = []
+        n_lines = int(rng.integers(0, 400))
+        crlf = trial % 3 == 0
+        for _ in range(n_lines):
+            r = rng.random()
+            if r < 0.15:
+                line = (b">" if rng.random() < 0.7 else b";") + _rand(rng, int(rng.integers(0, 30)), b"abc xyz>;\t01")
+            elif r < 0.2:
+                line = b" \t"[: int(rng.integers(0, 3))]
+            else:
+                ln = int(rng.integers(0, 200)) if rng.random() < 0.97 else int(rng.integers(4000, 20000))
+                line = _rand(rng, ln, b"ACGTacgtNRY \t" if trial % 2 else b"ACGTacgt ")
+            parts.append(line + (b"\r\n" if crlf else b"\n"))
+        text = b"".join(parts)
+        if trial % 4 == 1 and text.endswith(b"\n"):
+            text = text[:-2] if crlf else text[:-1]  # no trailing line break
+        if trial % 5 == 2 and len(text) > 10:
+            t = bytearray(text)
+            t[int(rng.integers(0, len(t)))] = int(rng.choice(list(b"xQ-\r\x00\xc4")))
+            text = bytes(t)
+        lead = int(rng.integers(0, 16))  # input alignment
+        buf = np.frombuffer(b"\n" * lead + text, dtype=np.uint8)[lead:]
+        for concat in (False, True):
+            for allow in (False, True):
+                _fasta_same(B, bytes(buf), trial % 2 == 0 and b"N" not in text, concat, allow)
+
+
+def test_fasta_feeds_batch_translate(B):
+    """The scanner's CSR offsets are what the batch entry points consume."""
+    rng = np.random.default_rng(42)
+    seqs = [_rand(rng, int(n), b"ACGTN") for n in rng.integers(0, 3000, 50)]
+    text = b"".join(b">read%d some text\n" % i + b"\n".join(s[j:j + 70] for j in range(0, len(s), 70)) + b"\n" for i, s in enumerate(seqs))
+    scan = B.fasta_scan(text)
+    assert len(scan) == 50 and scan.headers[7] == "read7 some text"
+    res = B.translate_frames_batch([scan.record(i)[1] for i in range(50)], table=1, frames=6, enc=1)
+    for i, s in enumerate(seqs):
+        want = oracle.py_all_frames(1, s) if len(s) >= 3 else []
+        assert res.sequence_frames(i) == want

@@ -145,3 +145,46 @@ COVID = {
     "frame_lens": [9967, 9966, 9966, 9967, 9966, 9966],
     "frames_joined_sha256": "c050477ed99d645826c4e073904b843ee5fbf723a38dc7bc680c0518f4d75545",
 }
+
+
+# ---- FASTA (src/fasta.rs tests, restated with DNA content): (text, settings or None for all four, expected records)
+# a record = (header, content letters, (line_begin, line_end)); settings = (concatenate_headers, allow_preceding_comment)
+_ALL = [(c, a) for c in (False, True) for a in (False, True)]
+FASTA = [
+    ("", _ALL, []),                                                                  # :598-601
+    ("\n\n", _ALL, []),                                                              # :603-606
+    ("  \n\n \n  \t\t \t\n  \t \n", _ALL, []),                                       # :608-611 with the DNA-legal blanks
+    (">Virus\n", _ALL, [("Virus", "", (1, 2))]),                                     # :613-633
+    (";Virus\n", _ALL, [("Virus", "", (1, 2))]),
+    (">Virus\n\n", _ALL, [("Virus", "", (1, 3))]),                                   # :635-654
+    ("ACGT\nGGCC", [(False, True), (True, True)], []),                               # :656-663 preceding content dropped
+    ("ACGT\nGGCC", [(False, False), (True, False)], [("", "ACGTGGCC", (1, 3))]),     # :665-676
+    ("ACGT\nGGCC\n\n>Virus\n\n", [(False, True), (True, True)], [("Virus", "", (4, 6))]),  # :678-690
+    ("ACGT\nGGCC\n\n>Virus\n\n", [(False, False), (True, False)], [("", "ACGTGGCC", (1, 4)), ("Virus", "", (4, 6))]),  # :692-712
+    ("   \t\n\t\t   \n\n>Virus\n\n", _ALL, [("Virus", "", (4, 6))]),                # :714-724 (blank preceding content)
+    (">Virus\nCAAAGT\n", _ALL, [("Virus", "CAAAGT", (1, 3))]),                       # :726-746
+    (";Virus\nCAAAGT", _ALL, [("Virus", "CAAAGT", (1, 3))]),                         # :748-768 (no trailing newline)
+    (">Virus\nAAAA\nCCCC\nGGGG\n", _ALL, [("Virus", "AAAACCCCGGGG", (1, 5))]),       # :770-790
+    (">Virus1\nAAAA\n;Virus2\nCCCC\n", _ALL, [("Virus1", "AAAA", (1, 3)), ("Virus2", "CCCC", (3, 5))]),  # :792-853
+    (">Virus1\nAAAA\nAAAA\n>Virus2\nCCCC\nCCCC\n>Virus3\nCCCC\nCCCC\n", _ALL,
+     [("Virus1", "AAAAAAAA", (1, 4)), ("Virus2", "CCCCCCCC", (4, 7)), ("Virus3", "CCCCCCCC", (7, 10))]),  # :920-943
+    (">Virus1\nAAAA\nAAAA\n>Virus2\nCCCC\nCCCC\n>Virus3", _ALL,
+     [("Virus1", "AAAAAAAA", (1, 4)), ("Virus2", "CCCCCCCC", (4, 7)), ("Virus3", "", (7, 8))]),           # :945-968
+    (">a\n>b\ntcga", [(True, False), (True, True)], [("a\nb", "TCGA", (1, 4))]),     # :970-981
+    (">a\n>b\ntcga", [(False, False), (False, True)], [("a", "", (1, 2)), ("b", "TCGA", (2, 4))]),  # :983-1003
+    (">a\n>b", [(True, False), (True, True)], [("a\nb", "", (1, 3))]),               # :1005-1016
+    (">Virus1\r\nAC GT\r\n\r\n>V2 x\r\nTT\tT\r\n", _ALL, [("Virus1", "ACGT", (1, 4)), ("V2 x", "TTT", (4, 6))]),  # CRLF (BufRead::lines)
+    (">Virus1\nAAAA \n", _ALL, [("Virus1", "AAAA", (1, 3))]),                        # :1213-1222
+    (">Virus1\n  AAAA\tBCD \t\n", _ALL, [("Virus1", "AAAABCD", (1, 3))]),            # :1223-1231
+    (">Virus1\nAC\nT\n>Empty\n\n>Virus2\n>with many\n>comment lines\nC  AT", [(True, False)],
+     [("Virus1", "ACT", (1, 4)), ("Empty", "", (4, 6)), ("Virus2\nwith many\ncomment lines", "CAT", (6, 10))]),  # :1342-1358
+]
+# (text, strict, line, kind, byte, located message)
+FASTA_ERRORS = [
+    (">Virus1\nABCD", True, 2, 3, ord("B"), "on line 2: error parsing record: unexpected ambiguous nucleotide: 'B'"),   # :1157-1169
+    (">Virus1\nAAAelephant", False, 2, 2, ord("e"), "on line 2: error parsing record: bad nucleotide: 'e'"),           # :1233-1250
+    (">Virus1\nAAAA\n>Virus2\nAAAAelephant", True, 4, 2, ord("e"), "on line 4: error parsing record: bad nucleotide: 'e'"),  # :1252-1270
+    (">Virus1\nAAčCCG\n", False, 2, 1, 196, "on line 2: error parsing record: non-ascii byte: c4"),                # :1272-1290
+    (">Virus1\nAAA\nCCCxGGG", True, 3, 2, ord("x"), "on line 3: error parsing record: bad nucleotide: 'x'"),           # :1388-1396
+    ("AC\rGT\n>x\n", False, 1, 2, 13, "on line 1: error parsing record: bad nucleotide: '\\r'"),                        # a bare CR is content
+]
