@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <utility>
 #include <type_traits>
 #include <vector>
 
@@ -321,6 +322,82 @@ class DnaSequence {
         return res;
     }
     std::vector<T> dna_;
+};
+
+// ---- src/fasta.rs ------------------------------------------------------------------------------------
+
+// FastaParseSettings, src/fasta.rs:67-110
+struct FastaParseSettings {
+    bool concatenate_headers = true;
+    bool allow_preceding_comment = false;
+};
+
+// FastaRecord<DnaSequence<T>>, src/fasta.rs:17-29
+template <class T>
+struct FastaRecord {
+    std::string header;                      // without the leading '>' / ';'; concatenated header lines joined by '\n'
+    DnaSequence<T> contents;
+    std::pair<size_t, size_t> line_range;    // 1-based, end exclusive
+};
+
+// Located<FastaParseError::ParseError(TranslationError)>, src/fasta.rs:413-423 + src/errors.rs:8-15
+class FastaParseError : public TranslationError {
+  public:
+    FastaParseError(const qd_err& e, const std::string& msg)
+        : TranslationError(e, "on line " + std::to_string(e.seq_index) + ": error parsing record: " + msg), line_number(e.seq_index) {}
+    uint64_t line_number;
+};
+
+// FastaParser<DnaSequence<T>>, src/fasta.rs:425-480
+template <class T>
+class FastaParser {
+  public:
+    explicit FastaParser(FastaParseSettings settings = {}) : settings_(settings) {}
+    std::vector<FastaRecord<T>> parse_str(std::string_view s) const {
+        Context& c = Context::current();
+        const uint8_t* text = reinterpret_cast<const uint8_t*>(s.data());
+        size_t n_masks = 0, n_records = 0;
+        qd_err e{};
+        auto call = [&](uint8_t* masks, qd_fasta_record* recs, size_t cap) {
+            const int rc = qd_fasta_scan(c.get(), strict_of<T>, settings_.concatenate_headers, settings_.allow_preceding_comment, text, s.size(), masks,
+                                         &n_masks, recs, cap, &n_records, &e);
+            if (rc >= QD_ERR_NON_ASCII_BYTE && rc <= QD_ERR_UNEXPECTED_AMBIGUOUS) {
+                char buf[96];
+                qd_err_message(&e, buf, sizeof buf);
+                throw FastaParseError(e, buf);
+            }
+            c.check(rc, e);
+        };
+        call(nullptr, nullptr, 0);  // sizes
+        std::vector<uint8_t> masks(n_masks + 1);
+        std::vector<qd_fasta_record> recs(n_records + 1);
+        call(masks.data(), recs.data(), n_records);
+        std::vector<FastaRecord<T>> out;
+        out.reserve(n_records);
+        for (size_t i = 0; i < n_records; i++) {
+            const qd_fasta_record& r = recs[i];
+            FastaRecord<T> rec;
+            if (r.header_begin != UINT64_MAX) {  // header lines without their first byte, line breaks normalised to '\n'
+                size_t pos = r.header_begin;
+                while (pos < r.header_end) {
+                    size_t eol = pos;
+                    while (eol < r.header_end && s[eol] != '\n') eol++;
+                    size_t end = (eol < r.header_end && eol > pos && s[eol - 1] == '\r') ? eol - 1 : eol;
+                    if (!rec.header.empty() || pos != r.header_begin) rec.header.push_back('\n');
+                    rec.header.append(s.substr(pos + 1, end - pos - 1));
+                    pos = eol + 1;
+                }
+            }
+            const T* m = reinterpret_cast<const T*>(masks.data() + r.content_begin);
+            rec.contents = DnaSequence<T>(std::vector<T>(m, m + (r.content_end - r.content_begin)));
+            rec.line_range = {static_cast<size_t>(r.line_begin), static_cast<size_t>(r.line_end)};
+            out.push_back(std::move(rec));
+        }
+        return out;
+    }
+
+  private:
+    FastaParseSettings settings_;
 };
 
 using DnaSequenceStrict = DnaSequence<Nucleotide>;              // src/rust_api.rs:163

@@ -20,6 +20,7 @@ static int failures = 0;
         }                                                                    \
     } while (0)
 
+static std::pair<size_t, size_t> lr(size_t a, size_t b) { return {a, b}; }
 static DnaSequenceAmbiguous dna(const char* s) { return DnaSequenceAmbiguous::from_str(s); }
 static DnaSequenceStrict dna_strict(const char* s) { return DnaSequenceStrict::from_str(s); }
 static ProteinSequence protein(const char* s) { return ProteinSequence::from_str(s); }
@@ -161,6 +162,34 @@ int main() {
             CHECK(all[3 + k] == rev[k]);
         }
         CHECK(x.reverse_complement().reverse_complement() == x);
+    }
+    // FASTA (src/fasta.rs:1131-1210, 1342-1396)
+    {
+        auto recs = FastaParser<Nucleotide>().parse_str(">Virus1\nAAAA\nAAAA\n>Virus2\nCCCC\nCCCC\n");
+        CHECK(recs.size() == 2);
+        if (recs.size() == 2) {
+            CHECK(recs[0].header == "Virus1" && recs[0].contents == dna_strict("AAAAAAAA") && recs[0].line_range == lr(1, 4));
+            CHECK(recs[1].header == "Virus2" && recs[1].contents == dna_strict("CCCCCCCC") && recs[1].line_range == lr(4, 7));
+        }
+        auto many = FastaParser<Nucleotide>().parse_str(">Virus1\nAC\nT\n>Empty\n\n>Virus2\n>with many\n>comment lines\nC  AT");
+        CHECK(many.size() == 3);
+        if (many.size() == 3) {
+            CHECK(many[1].header == "Empty" && many[1].contents.is_empty());
+            CHECK(many[2].header == "Virus2\nwith many\ncomment lines" && many[2].contents == dna_strict("CAT"));
+        }
+        auto amb = FastaParser<NucleotideAmbiguous>().parse_str(">Virus1\n  AAAA\tBCD \t\n");
+        CHECK(amb.size() == 1 && amb[0].contents == dna("AAAABCD"));
+        auto noconcat = FastaParser<Nucleotide>(FastaParseSettings{false, false}).parse_str(">a\n>b\ntcga");
+        CHECK(noconcat.size() == 2 && noconcat[0].header == "a" && noconcat[0].contents.is_empty() && noconcat[1].contents == dna_strict("TCGA"));
+        auto pre = FastaParser<Nucleotide>().parse_str("ACGT\nGGCC\n\n>Virus\n\n");
+        CHECK(pre.size() == 2 && pre[0].header.empty() && pre[0].contents == dna_strict("ACGTGGCC") && pre[0].line_range == lr(1, 4));
+        bool threw = false;
+        try {
+            FastaParser<Nucleotide>().parse_str(">Virus1\nAAA\nCCCxGGG");
+        } catch (const FastaParseError& e) {
+            threw = e.line_number == 3 && std::string(e.what()) == "on line 3: error parsing record: bad nucleotide: 'x'";
+        }
+        CHECK(threw);
     }
     if (failures) {
         std::printf("%d check(s) failed\n", failures);
