@@ -195,6 +195,16 @@ def main():
         g.build()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    try:  # run (and allocate pinned memory) on the CPUs next to this rank's GPU: the e2e leg is PCIe / host-memory bound
+        import pynvml
+
+        pynvml.nvmlInit()
+        before_aff = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = {"cpus_before": before_aff, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as ex:  # not fatal: the numbers are simply taken without the binding
+        numa = {"error": type(ex).__name__}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -380,6 +390,36 @@ def main():
                 extra["canonical_windows"]["cpu_port"] = {"windows_per_s": n_rep * (seq_len - w + 1) / (time.perf_counter() - t0), "cores": 1,
                                                           "sample": f"{n_rep} x one {seq_len}-nt sequence, oracle/qd_oracle.c"}
 
+    # ---- extra: BASELINE config 1 shape (one 29 901-nt genome, translate table 1) through the Python drop-in API:
+    # latency of one call, host bytes in, host bytes out (launch + two copies; the reference's CPU path wins here)
+    if not args.no_extra and rank == 0:
+        import quickdna_b200 as qd
+        from quickdna_b200.synth import synth_np
+
+        genome = qd.DnaSequence(synth_np(1, 0, 29_901, b"acgt").tobytes())
+        for _ in range(20):
+            genome.translate(1)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            genome.translate(1)
+        lat_tr = (time.perf_counter() - t0) / 200
+        t0 = time.perf_counter()
+        for _ in range(200):
+            genome.reverse_complement()
+        lat_rc = (time.perf_counter() - t0) / 200
+        extra["covid_sized_calls"] = {"workload": "DnaSequence(29 901 nt).translate(1) / .reverse_complement(), Python API, host in / host out",
+                                      "translate_ms_per_call": lat_tr * 1e3, "reverse_complement_ms_per_call": lat_rc * 1e3,
+                                      "reference_readme_ms": {"translate": 0.02959, "reverse_complement": 0.02409,
+                                                              "note": "README.md:85,89, hardware unstated"}}
+        if world == 1 and not args.no_cpu:
+            import oracle
+
+            raw = genome.seq
+            t0 = time.perf_counter()
+            for _ in range(200):
+                oracle.translate_bytes(1, raw)
+            extra["covid_sized_calls"]["cpu_port_translate_ms_per_call"] = (time.perf_counter() - t0) / 200 * 1e3
+
     # ---- extra: expansions of 42-nt windows with exactly two ambiguity codes, cap 16 (benches/expansions.rs:68-102 shape)
     if not args.no_extra:
         n_win, w = args.expansion_windows, 42
@@ -440,7 +480,7 @@ def main():
         assert bytes(h_out[(er - 64) * per: er * per].numpy()) == bytes(tail.cpu().numpy())
         e2e = {"value": world * er * READ_LEN / e2e_s, "unit": UNIT, "h2d_bytes_per_step": er * READ_LEN,
                "d2h_bytes_per_step": er * per, "reads_per_step": er, "ms_per_step": e2e_s * 1e3,
-               "api": "qd_translate_frames_batch_uniform (host pointers, pinned)"}
+               "api": "qd_translate_frames_batch_uniform (host pointers, pinned)", "cpu_affinity": numa}
         del h_in, h_out
 
     # ---- CPU baseline beside it (rank 0, N=1 only): scalar port, one thread, bounded sample
