@@ -756,3 +756,43 @@ def test_fasta_feeds_batch_translate(B):
     for i, s in enumerate(seqs):
         want = oracle.py_all_frames(1, s) if len(s) >= 3 else []
         assert res.sequence_frames(i) == want
+
+
+# ------------------------------------------------------------------ threading contract
+
+
+def test_contexts_are_independent_across_threads(N):
+    """The reference's functions are pure and re-entrant; here: one context per thread, used concurrently, and one
+    shared context hammered from several threads (its entry points serialise on a mutex)."""
+    import threading
+
+    rng = np.random.default_rng(51)
+    inputs = [_rand(rng, int(n), IUPAC) for n in rng.integers(1000, 200000, 8)]
+    want = [(oracle.translate_bytes(11, d), oracle.revcomp_bytes(d)) for d in inputs]
+    L = N.lib()
+    errors = []
+
+    def work(ctx, idx, rounds):
+        try:
+            for _ in range(rounds):
+                d = inputs[idx]
+                out = C.create_string_buffer(max(len(d) // 3, 1))
+                rc_out = C.create_string_buffer(len(d))
+                err = N.QdErr()
+                assert L.qd_translate(ctx.handle, 11, 0, 0, d, len(d), out, C.byref(err)) == 0
+                assert L.qd_revcomp(ctx.handle, 0, 0, d, len(d), rc_out, C.byref(err)) == 0
+                assert out.raw[: len(d) // 3] == want[idx][0] and rc_out.raw == want[idx][1]
+        except BaseException as e:  # surfaced in the main thread
+            errors.append(e)
+
+    own = [N.Context(0) for _ in range(4)]
+    threads = [threading.Thread(target=work, args=(own[i], i, 10)) for i in range(4)]
+    shared = N.default_context()
+    threads += [threading.Thread(target=work, args=(shared, 4 + i, 10)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for c in own:
+        c.close()
+    assert not errors, errors[0]
