@@ -288,6 +288,51 @@ def main():
                                          "traffic": ncu_traffic("revcomp_kernel", nt=n_rc), "kernel": "revcomp_kernel<1024>",
                                          "algorithmic_bytes_per_launch": 2 * n_rc}}
 
+    # ---- extra: reverse-complement variants: misaligned length, strict alphabet, mask encoding
+    if not args.no_extra:
+        from quickdna_b200 import _native as _N
+
+        n_rc = args.revcomp_nt
+        variants = {}
+        for name, n_v, kw in (("n_plus_1", n_rc + 1, {}), ("n_minus_1", n_rc - 1, {}), ("strict", n_rc, {"strict": True})):
+            bufs = [(x[i * (n_rc + 16): i * (n_rc + 16) + n_v], out[i * (n_rc + 16): i * (n_rc + 16) + n_v]) for i in range(4)]
+            for i in range(4):
+                B.revcomp_dev(bufs[i][0], out=bufs[i][1], ctx=ctx, **kw)
+            barrier()
+            ev0.record()
+            for i in range(20):
+                B.revcomp_dev(bufs[i % 4][0], out=bufs[i % 4][1], ctx=ctx, **kw)
+            ev1.record()
+            barrier()
+            v_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 20
+            variants[name] = {"nt": n_v, "ms": v_ms, "GB/s": 2 * n_v / (v_ms * 1e-3) / 1e9}
+        assert B.dev_error_fetch(x, ctx=ctx) is None
+        # mask encoding (the typed Rust API: Vec<Nucleotide>): parse the ASCII once on the device, then reverse-complement masks
+        masks, cnt = B.parse_dev(x[:n_rc], ctx=ctx)
+        assert int(cnt.item()) == n_rc
+        mo = out[:n_rc]
+        for _ in range(3):
+            B.revcomp_dev(masks[:n_rc], out=mo, enc=_N.ENC_MASK, ctx=ctx)
+        barrier()
+        ev0.record()
+        for _ in range(10):
+            B.revcomp_dev(masks[:n_rc], out=mo, enc=_N.ENC_MASK, ctx=ctx)
+        ev1.record()
+        barrier()
+        v_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 10
+        variants["mask_encoding"] = {"nt": n_rc, "ms": v_ms, "GB/s": 2 * n_rc / (v_ms * 1e-3) / 1e9, "note": "one buffer set reused (partly L2-resident)"}
+        # ASCII -> mask parse itself (src/rust_api.rs:310-322), 2 B per input byte
+        ev0.record()
+        for _ in range(5):
+            B.parse_dev(x[:n_rc], out=masks, ctx=ctx)
+        ev1.record()
+        barrier()
+        v_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 5
+        extra["parse"] = {"workload": f"ASCII -> mask parse of {n_rc} nt (count pass + scan + compacting write pass)", "ms": v_ms,
+                          "nt_per_s": world * n_rc / (v_ms * 1e-3), "GB/s_algorithmic": 2 * n_rc / (v_ms * 1e-3) / 1e9}
+        extra["revcomp_variants"] = variants
+        del masks, cnt
+
     # ---- extra: the other forms of the frame kernel on the same resident data (a few launches each)
     def timed(fn, reps=5):
         for _ in range(2):

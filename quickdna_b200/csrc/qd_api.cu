@@ -72,6 +72,7 @@ struct qd_ctx {
     uint16_t* d_pair = nullptr;   // [encoding][strict][PAIR_ENTRIES]
     uint16_t* d_rc_pair = nullptr;  // [RC_PAIR_COUNT][PAIR_ENTRIES]
     uint8_t* d_canon_pair = nullptr;  // [encoding][PAIR_ENTRIES]
+    uint16_t* d_parse_pair = nullptr;  // [strict][PAIR_ENTRIES]
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
@@ -405,6 +406,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_pair, sizeof(T.pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_rc_pair, sizeof(T.rc_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_canon_pair, sizeof(T.canon_pair)) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_parse_pair, sizeof(T.parse_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
@@ -432,6 +434,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         ok &= cudaMemcpy(c->d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_rc_pair, T.rc_pair, sizeof(T.rc_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_canon_pair, T.canon_pair, sizeof(T.canon_pair), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(c->d_parse_pair, T.parse_pair, sizeof(T.parse_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemset(c->d_err, 0xff, sizeof(unsigned long long)) == cudaSuccess;
     }
     if (!ok) {
@@ -458,6 +461,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_pair) cudaFree(c->d_pair);
     if (c->d_rc_pair) cudaFree(c->d_rc_pair);
     if (c->d_canon_pair) cudaFree(c->d_canon_pair);
+    if (c->d_parse_pair) cudaFree(c->d_parse_pair);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -710,6 +714,8 @@ static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, 
     p.in = ascii_dev;
     p.n = n;
     p.table = tab(c, strict ? TAB_PARSE_STRICT : TAB_PARSE);
+    p.pair = c->d_parse_pair + (strict ? PAIR_ENTRIES : 0);
+    p.pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);
     p.counts = c->parse_counts.as<uint64_t>();
     p.offsets = c->parse_offsets.as<uint64_t>();
     p.out = masks_dev;

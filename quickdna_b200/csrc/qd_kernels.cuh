@@ -1359,11 +1359,14 @@ __global__ void __launch_bounds__(256) warp_map_kernel(const uint64_t* __restric
 constexpr int PARSE_THREADS = 256;
 constexpr int PARSE_BLOCK_BYTES = PARSE_THREADS * 16;  // one aligned 16-byte granule per thread
 constexpr uint32_t PARSE_SKIP = 0x80;                  // table value of ' ' and '\t' (0 = invalid, else the mask)
+constexpr uint32_t PARSE_PAIR_SLOW = 0x40;             // pair-table flag: the letter is not a nucleotide of the alphabet
 
 struct ParseParams {
     const uint8_t* in;
     uint64_t n;
     const uint8_t* table;        // 256 bytes: mask | PARSE_SKIP | 0
+    const uint16_t* pair;        // letter pair -> mask0 | mask1 << 8 (PARSE_PAIR_SLOW in a byte: not a plain nucleotide)
+    uint32_t pair_coef;
     uint64_t* counts;            // kept bytes per block (pass 1 out)
     const uint64_t* offsets;     // exclusive scan of counts, [n_blocks + 1] (pass 2 in)
     uint8_t* out;
@@ -1402,18 +1405,44 @@ __device__ __forceinline__ void parse_load(const ParseParams& p, const uint8_t* 
     }
 }
 
+// Fast path for a granule that lies wholly inside the input: two letters per lookup (the frame kernel's dp2a pair
+// index); returns false when any byte is whitespace, invalid or outside the letter range (then the byte path decides)
+__device__ __forceinline__ bool parse_granule_fast(const ParseParams& p, uint32_t pair_base, uint64_t g, uint4& masks) {
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.in), hi = lo + p.n;
+    const uintptr_t a = (lo & ~(uintptr_t)15) + 16 * g;
+    if (a < lo || a + 16 > hi) return false;
+    const uint4 x = ldg_stream(reinterpret_cast<const void*>(a));
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    uint32_t m[4], flags = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t u = w[q] & 0x1f1f1f1fu;
+        const uint32_t e_lo = lds_u16(dp2a_lo(p.pair_coef, u, pair_base)), e_hi = lds_u16(dp2a_hi(p.pair_coef, u, pair_base));
+        m[q] = e_hi * 65536u + e_lo;
+        flags |= m[q];
+    }
+    const uint32_t a_and = w[0] & w[1] & w[2] & w[3], a_or = w[0] | w[1] | w[2] | w[3];
+    if ((flags & (PARSE_PAIR_SLOW * 0x01010101u)) | ((a_and & 0x40404040u) ^ 0x40404040u) | (a_or & 0x80808080u)) return false;
+    masks = make_uint4(m[0], m[1], m[2], m[3]);
+    return true;
+}
+
 __global__ void __launch_bounds__(PARSE_THREADS) parse_count_kernel(const ParseParams p, uint64_t n_blocks) {
     __shared__ uint8_t tab_s[256];
     __shared__ uint64_t warp_sums[32];
+    __shared__ __align__(16) uint16_t pair_s[PAIR_ENTRIES];
     tab_s[threadIdx.x] = __ldg(p.table + threadIdx.x);
+    for (int i = threadIdx.x; i < (int)PAIR_ENTRIES; i += PARSE_THREADS) pair_s[i] = __ldg(p.pair + i);
     __syncthreads();
+    const uint32_t pair_base = smem_u32(pair_s);
     const uintptr_t lo = reinterpret_cast<uintptr_t>(p.in);
     for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         uint8_t v[16];
-        uint32_t kept;
-        int bad;
+        uint32_t kept = 16;
+        int bad = -1;
         const uint64_t g = blk * PARSE_THREADS + threadIdx.x;
-        parse_load(p, tab_s, g, v, kept, bad);
+        uint4 fast;
+        if (!parse_granule_fast(p, pair_base, g, fast)) parse_load(p, tab_s, g, v, kept, bad);
         if (bad >= 0) atomicMin(p.err_key, (unsigned long long)(((lo & ~(uintptr_t)15) + 16 * g + bad) - lo));
         uint64_t total;
         block_exclusive_scan((uint64_t)kept, &total, warp_sums);
@@ -1426,9 +1455,21 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseP
     __shared__ uint8_t tab_s[256];
     __shared__ uint64_t warp_sums[32];
     __shared__ __align__(16) uint8_t stage[PARSE_BLOCK_BYTES + 16];
+    __shared__ __align__(16) uint16_t pair_s[PAIR_ENTRIES];
     tab_s[threadIdx.x] = __ldg(p.table + threadIdx.x);
+    for (int i = threadIdx.x; i < (int)PAIR_ENTRIES; i += PARSE_THREADS) pair_s[i] = __ldg(p.pair + i);
     __syncthreads();
+    const uint32_t pair_base = smem_u32(pair_s);
     for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        // dense block (every byte a nucleotide: its output is as long as its input) landing on a 16-byte boundary:
+        // no compaction, no staging -- translate my granule and store it
+        if (p.offsets[blk + 1] - p.offsets[blk] == PARSE_BLOCK_BYTES && ((reinterpret_cast<uintptr_t>(p.out) + p.offsets[blk]) & 15u) == 0) {
+            uint4 fast;
+            if (parse_granule_fast(p, pair_base, blk * PARSE_THREADS + threadIdx.x, fast)) {  // always true here
+                stg_stream(p.out + p.offsets[blk] + 16 * threadIdx.x, fast);
+                continue;
+            }
+        }
         uint8_t v[16];
         uint32_t kept;
         int bad;
