@@ -465,6 +465,35 @@ def main():
                 oracle.translate_bytes(1, raw)
             extra["covid_sized_calls"]["cpu_port_translate_ms_per_call"] = (time.perf_counter() - t0) / 200 * 1e3
 
+    # ---- extra: FASTA record scanner (src/fasta.rs) through the host-pointer call: text in, masks + records out
+    if not args.no_extra and rank == 0 and world == 1:
+        import numpy as np
+
+        from quickdna_b200.synth import synth_np
+
+        n_rec, lines_per, width = 20_000, 143, 70  # ~10 kb records, 70-column lines, ~200 MB of text
+        body = synth_np(7, 0, n_rec * lines_per * width).reshape(n_rec, lines_per, width)
+        lines = np.concatenate([body, np.full((n_rec, lines_per, 1), 10, np.uint8)], axis=2).reshape(n_rec, -1)
+        hdr = np.frombuffer(b">synthetic record, 143 lines of 70 nt\n", dtype=np.uint8)
+        text = np.concatenate([np.broadcast_to(hdr, (n_rec, hdr.size)), lines], axis=1).reshape(-1).tobytes()
+        del body, lines
+        B.fasta_scan(text[: 1 << 20], ctx=ctx)
+        t0 = time.perf_counter()
+        scan = B.fasta_scan(text, ctx=ctx)
+        fa_s = time.perf_counter() - t0
+        assert len(scan) == n_rec and scan.masks.size == n_rec * lines_per * width
+        extra["fasta_scan"] = {"workload": f"{n_rec} records, {len(text)} bytes of FASTA text (70-column lines), host in / host out, "
+                                           "two qd_fasta_scan calls (sizes, then data) + Python record objects",
+                               "seconds": fa_s, "text_GB_per_s": len(text) / fa_s / 1e9}
+        if not args.no_cpu:
+            import oracle
+
+            t0 = time.perf_counter()
+            ref = oracle.fasta_scan(text[: len(text) // 10])
+            extra["fasta_scan"]["cpu_port_text_GB_per_s"] = (len(text) // 10) / (time.perf_counter() - t0) / 1e9
+            assert len(ref) >= n_rec // 10
+        del text, scan
+
     # ---- extra: expansions of 42-nt windows with exactly two ambiguity codes, cap 16 (benches/expansions.rs:68-102 shape)
     if not args.no_extra:
         n_win, w = args.expansion_windows, 42
