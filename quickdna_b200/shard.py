@@ -80,3 +80,30 @@ def chromosome_frame_ranges(n: int, start: int, end: int):
         top = qs_hi - ((qs_hi - k) % 3)
         res[3 + k] = (lo // 3, top // 3 + 1)
     return res
+
+
+def chromosome_shard_placement(n: int, start: int, end: int):
+    """Where the frames of ONE shard land in the frames of the whole n-nt sequence.
+
+    The shard [start, end) (start a multiple of 48; end a multiple of 48 or n) is translated as an ordinary
+    stand-alone sequence made of its nucleotides plus the 2-nt halo: piece = seq[start:min(n, end + 2)].  With
+    n_local = len(piece), every codon start of the whole sequence in [start, min(end, n - 2)) is a codon start of the
+    piece and vice versa, so nothing is exchanged between shards; only the frame NUMBERS and residue offsets differ:
+
+      forward local frame k  -> global frame k, first residue at index start // 3
+      reverse local frame k  -> global frame (k + d) % 3, first residue at local index 0 = global index (k + d) // 3,
+                                with d = n - (start + n_local)  (nucleotides of the sequence to the right of the piece)
+
+    Returns [(global_frame 0..5, global_first_index, length)] for local frames 0..5 (length 0 = frame absent).
+    """
+    read_end = min(n, end + 2)
+    n_local = read_end - start
+    d = n - read_end
+    out = []
+    for k in range(3):
+        ln = (n_local - k) // 3 if n_local > k else 0
+        out.append((k, start // 3, ln))
+    for k in range(3):
+        ln = (n_local - k) // 3 if n_local > k else 0
+        out.append((3 + (k + d) % 3, (k + d) // 3, ln))
+    return out

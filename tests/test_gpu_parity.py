@@ -796,3 +796,41 @@ def test_contexts_are_independent_across_threads(N):
     for c in own:
         c.close()
     assert not errors, errors[0]
+
+
+# ------------------------------------------------------------------ one long sequence cut into shards
+
+
+def test_chromosome_shards_stitch_to_the_unsharded_result(qd):
+    """Each shard is translated as an ordinary sequence (its nucleotides + a 2-nt halo); host-side placement alone
+    (quickdna_b200.shard) rebuilds the six frames and the reverse complement of the whole sequence."""
+    from quickdna_b200 import shard
+
+    rng = np.random.default_rng(61)
+    for n, world in ((100_003, 2), (1_000_001, 4), (48 * 7, 8), (50, 2), (999_999, 3), (5, 4), (3, 2), (97, 3), (49, 2)):
+        seq = _rand(rng, n, IUPAC)
+        def six(compact, length):  # the reference omits empty frames: put the returned ones back at their frame numbers
+            present = [k for k in range(3) if length > k and (length - k) // 3 > 0]
+            assert len(compact) == 2 * len(present)
+            full = [b""] * 6
+            for j, k in enumerate(present):
+                full[k], full[3 + k] = compact[j], compact[len(present) + j]
+            return full
+
+        whole = six([f.seq for f in qd.DnaSequence(seq).translate_all_frames(11)], n)
+        frames = [bytearray(len(f)) for f in whole]
+        seen = [0] * 6
+        rc = bytearray(n)
+        for s, e, read_end in shard.partition_chromosome(n, world):
+            if e <= s:
+                continue
+            piece = seq[s:read_end]
+            local = six([f.seq for f in qd.DnaSequence(piece).translate_all_frames(11)], len(piece))
+            for lf, (gf, first, ln) in enumerate(shard.chromosome_shard_placement(n, s, e)):
+                assert ln == len(local[lf])
+                frames[gf][first:first + ln] = local[lf]
+                seen[gf] += ln
+            rc[n - e:n - s] = qd.DnaSequence(seq[s:e]).reverse_complement().seq
+        assert [bytes(f) for f in frames] == whole, (n, world)
+        assert seen == [len(f) for f in whole]
+        assert bytes(rc) == qd.DnaSequence(seq).reverse_complement().seq

@@ -118,3 +118,34 @@ def test_partition_helpers():
         assert chrom[0][0] == 0 and chrom[-1][1] == 250_000_001
         for (s, e, r), nxt in zip(chrom, chrom[1:]):
             assert s % 48 == 0 and e % 48 == 0 and e == nxt[0] and r == e + 2
+
+
+def test_chromosome_shard_placement():
+    """A shard translated as a stand-alone sequence (its nucleotides + the 2-nt halo) lands in the whole sequence's
+    frames by host-side placement alone; checked here with the oracle standing in for the device path."""
+    rng = np.random.default_rng(61)
+    iupac = np.frombuffer(b"ACGTacgtWMRYSKBVDHNwmryskbvdhn", dtype=np.uint8)
+
+    def six(compact, length):  # the reference omits empty frames: put the returned ones back at their frame numbers
+        present = [k for k in range(3) if length > k and (length - k) // 3 > 0]
+        assert len(compact) == 2 * len(present)
+        full = [b""] * 6
+        for j, k in enumerate(present):
+            full[k], full[3 + k] = compact[j], compact[len(present) + j]
+        return full
+
+    for n, world in ((100_003, 2), (300_001, 4), (48 * 7, 8), (50, 2), (99_999, 3), (5, 4), (3, 2), (97, 3), (49, 2), (4, 1), (96, 2)):
+        seq = bytes(iupac[rng.integers(0, len(iupac), n)])
+        whole = six(oracle.py_all_frames(11, seq) if n >= 3 else [], n)
+        frames = [bytearray(len(f)) for f in whole]
+        seen = [0] * 6
+        for s, e, read_end in shard.partition_chromosome(n, world):
+            if e <= s:
+                continue
+            piece = seq[s:read_end]
+            local = six(oracle.py_all_frames(11, piece) if len(piece) >= 3 else [], len(piece))
+            for lf, (gf, first, ln) in enumerate(shard.chromosome_shard_placement(n, s, e)):
+                assert ln == len(local[lf])
+                frames[gf][first:first + ln] = local[lf]
+                seen[gf] += ln
+        assert [bytes(f) for f in frames] == whole and seen == [len(f) for f in whole], (n, world)
