@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -73,6 +74,7 @@ struct qd_ctx {
     uint16_t* d_rc_pair = nullptr;  // [RC_PAIR_COUNT][PAIR_ENTRIES]
     uint8_t* d_canon_pair = nullptr;  // [encoding][PAIR_ENTRIES]
     uint16_t* d_parse_pair = nullptr;  // [strict][PAIR_ENTRIES]
+    std::map<int, uint8_t*> d_direct;  // one-frame direct codon tables, built on first use: key = slot * 4 + ascii * 2 + strict
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
@@ -174,6 +176,24 @@ int check_table(int table, qd_err* err, int* slot) {
 
 bool valid_frames(int f) { return f == QD_FRAMES_ONE || f == QD_FRAMES_SELF || f == QD_FRAMES_ALL; }
 
+// direct codon table of the one-frame kernel for (slot, enc, strict), built and uploaded on first use
+int direct_table(qd_ctx* c, int slot, int enc, int strict, cudaStream_t s, const uint8_t** out) {
+    const bool ascii = enc == QD_ENC_ASCII;
+    const int key = slot * 4 + (ascii ? 2 : 0) + (strict ? 1 : 0);
+    auto it = c->d_direct.find(key);
+    if (it == c->d_direct.end()) {
+        std::vector<uint8_t> host;
+        build_direct_table(host_tables(), slot, ascii, strict != 0, host);
+        uint8_t* d = nullptr;
+        QD_CUDA(c, cudaMalloc(&d, DIRECT_ENTRIES));
+        QD_CUDA(c, cudaMemcpyAsync(d, host.data(), DIRECT_ENTRIES, cudaMemcpyHostToDevice, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));  // `host` goes away
+        it = c->d_direct.emplace(key, d).first;
+    }
+    *out = it->second;
+    return QD_OK;
+}
+
 void set_encoding(const qd_ctx* c, FramesParams& p, int enc, int strict) {
     const bool ascii = enc == QD_ENC_ASCII;
     p.decode = tab(c, ascii ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
@@ -182,6 +202,8 @@ void set_encoding(const qd_ctx* c, FramesParams& p, int enc, int strict) {
     p.pair_coef = 2u | ((2u * k1) << 16);
     p.and_need = ascii ? 0x40404040u : 0u;
     p.or_forbid = ascii ? 0x80808080u : 0xe0e0e0e0u;
+    p.direct_k1 = ascii ? DIRECT_K1_ASCII : DIRECT_K1_MASK;
+    p.direct_k2 = ascii ? DIRECT_K2_ASCII : DIRECT_K2_MASK;
     p.strict = strict;
 }
 
@@ -190,8 +212,9 @@ bool use_big_tiles(const qd_ctx* c, uint64_t total_runs) { return total_runs >= 
 
 template <int FRAMES, int THREADS>
 int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_slot) {
-    auto kern = translate_frames_kernel<FRAMES, THREADS>;
-    const size_t smem = sizeof(FramesSmem<THREADS>);
+    constexpr bool DIRECT = FRAMES == 1;  // the one-frame kernel looks codons up straight from the letters
+    auto kern = translate_frames_kernel<FRAMES, THREADS, DIRECT>;
+    const size_t smem = DIRECT ? ((sizeof(FramesSmem<THREADS>) + 127) & ~(size_t)127) + DIRECT_ENTRIES : sizeof(FramesSmem<THREADS>);
     if (c->occ_frames[occ_slot] == 0) {
         int occ = 0;
         QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -251,6 +274,8 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     p.out = out_dev;
     p.lut = c->d_lut + (size_t)slot * LUT_ENTRIES;
     set_encoding(c, p, enc, strict);
+    if (frames == QD_FRAMES_ONE)
+        if (int rc = direct_table(c, slot, enc, strict, s, &p.direct)) return rc;
     p.err_key = c->d_err;
     p.key_base = key_base;
     return launch_frames(c, frames, p, s, big);
@@ -309,6 +334,8 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     p.out = out_dev;
     p.lut = c->d_lut + (size_t)slot * LUT_ENTRIES;
     set_encoding(c, p, enc, strict);
+    if (frames == QD_FRAMES_ONE)
+        if (int rc = direct_table(c, slot, enc, strict, s, &p.direct)) return rc;
     p.err_key = c->d_err;
     p.flat_base = flat_base;
     p.key_base = key_base;
@@ -462,6 +489,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_rc_pair) cudaFree(c->d_rc_pair);
     if (c->d_canon_pair) cudaFree(c->d_canon_pair);
     if (c->d_parse_pair) cudaFree(c->d_parse_pair);
+    for (auto& kv : c->d_direct) cudaFree(kv.second);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);

@@ -185,6 +185,8 @@ struct FramesParams {
     const uint16_t* lut;         // LUT_ENTRIES entries of the selected table, lut_index() layout
     const uint8_t* decode;       // 256-byte ASCII (or mask) -> internal code table (exact error search only)
     const uint16_t* pair;        // PAIR_ENTRIES letter-pair entries for (encoding, strict)
+    const uint8_t* direct;       // one-frame kernel: DIRECT_ENTRIES bytes for (table, encoding, strict)
+    uint32_t direct_k1, direct_k2;
     uint32_t pair_coef;          // dp2a coefficients {2, 2 * k1} of the pair table
     uint32_t and_need;           // bits every input byte must have (ASCII letters: 0x40 per byte)
     uint32_t or_forbid;          // bits no input byte may have (ASCII: 0x80, mask: 0xe0 per byte)
@@ -210,6 +212,12 @@ struct RunDesc {
 // 16 distinct shared-memory banks (random ACGT never conflicts); 31 * (1 + k1) + 1 <= PAIR_ENTRIES.
 constexpr uint32_t PAIR_K1_ASCII = 40, PAIR_K1_MASK = 38;
 constexpr uint32_t PAIR_ENTRIES = 1280;
+// Direct codon table of the one-frame kernel: three 5-bit letters -> amino acid, at u0 + K1 u1 + K2 u2 (0x80 = a letter is
+// invalid / ambiguous in a strict table).  Strides found by search: injective on every valid codon, never aliasing an
+// invalid one, and about two shared-memory wavefronts per lookup on random ACGT.
+constexpr uint32_t DIRECT_K1_ASCII = 35, DIRECT_K2_ASCII = 1169, DIRECT_K1_MASK = 31, DIRECT_K2_MASK = 999;
+constexpr uint32_t DIRECT_ENTRIES = 37376;  // >= 31 * (1 + K1 + K2) + 1, a multiple of 16
+constexpr uint32_t DIRECT_INVALID = 0x80;
 // The flag sits above the doubled code (bits 1..4) so a flagged letter still forms an even, in-allocation LUT address
 // (its residue is garbage, but a flagged letter inside a validated range always ends in an error).
 constexpr uint32_t PAIR_FLAG = 0x20;
@@ -310,11 +318,13 @@ __device__ __forceinline__ void issue_geometry_window(FramesSmem<THREADS>& S, co
     cp_async_commit();
 }
 
-template <int FRAMES, int THREADS>
+template <int FRAMES, int THREADS, bool DIRECT = false>
 __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) translate_frames_kernel(const FramesParams p) {
+    static_assert(!DIRECT || FRAMES == 1, "the direct codon table serves the one-frame kernel only");
     constexpr int TILE_THREADS = THREADS, TILE_RUNS = TileGeom<THREADS>::RUNS, SEARCH_CAP = TileGeom<THREADS>::SEARCH_CAP;
     extern __shared__ __align__(128) unsigned char frames_smem_raw[];  // sizeof(FramesSmem<THREADS>) dynamic bytes
     FramesSmem<THREADS>& S = *reinterpret_cast<FramesSmem<THREADS>*>(frames_smem_raw);
+    uint8_t* const direct_s = frames_smem_raw + ((sizeof(FramesSmem<THREADS>) + 127) & ~(size_t)127);  // DIRECT only
     const int tid = threadIdx.x;
     const bool uniform = (p.offsets == nullptr);
     const uint64_t total_runs = uniform ? p.total_runs : p.run_prefix[p.n_seq];
@@ -327,17 +337,21 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
         for (int b = 0; b < STAGES; b++)
             if (blockIdx.x + b * (uint64_t)gridDim.x < n_tiles) stage_tile(S, p, blockIdx.x + b * (uint64_t)gridDim.x, total_runs, b);
     }
-    {
+    if (DIRECT) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.direct);
+        uint4* dst = reinterpret_cast<uint4*>(direct_s);
+        for (int i = tid; i < (int)(DIRECT_ENTRIES / 16); i += TILE_THREADS) dst[i] = ldg_cached(src + i);
+    } else {
         const uint4* src = reinterpret_cast<const uint4*>(p.lut);
         uint4* dst = reinterpret_cast<uint4*>(S.lut);
         for (int i = tid; i < (int)(LUT_ENTRIES * 2 / 16); i += TILE_THREADS) dst[i] = ldg_cached(src + i);
         const uint4* psrc = reinterpret_cast<const uint4*>(p.pair);
         uint4* pdst = reinterpret_cast<uint4*>(S.pair);
         for (int i = tid; i < (int)(PAIR_ENTRIES * 2 / 16); i += TILE_THREADS) pdst[i] = ldg_cached(psrc + i);
-        if (tid < 17) {
-            auto word = [](int k) { return k >= 4 ? 0xffffffffu : (k <= 0 ? 0u : (1u << (8 * k)) - 1u); };
-            S.lowmask[tid] = make_uint4(word(tid), word(tid - 4), word(tid - 8), word(tid - 12));
-        }
+    }
+    if (tid < 17) {
+        auto word = [](int k) { return k >= 4 ? 0xffffffffu : (k <= 0 ? 0u : (1u << (8 * k)) - 1u); };
+        S.lowmask[tid] = make_uint4(word(tid), word(tid - 4), word(tid - 8), word(tid - 12));
     }
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna);
     // shared-window addresses of the two tables: folded into the address-forming dot products as the accumulator,
@@ -456,7 +470,53 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
         }
 
         // ---- phase 2: one run per thread: 48 codon starts -> 16 residues per frame per strand -----
-        if (active) {
+        if (DIRECT && active) {
+            // one frame: 16 codons, each three letters -> ONE table byte; the index comes from two dp2a over the letters
+            // where they lie (codon e starts at byte 3e: within a word, or across two), no realignment, no code stage
+            const uint32_t dbase = smem_u32(direct_s);
+            const uint32_t c01 = 1u | (p.direct_k1 << 16), c2x = p.direct_k2, cx0 = 1u << 16, c12 = p.direct_k1 | (p.direct_k2 << 16);
+            uint32_t U[13], acc_and = 0xffffffffu, acc_or = 0u;
+#pragma unroll
+            for (int k = 0; k < 13; k++) {
+                if (k & 1) {
+                    acc_and &= W[k - 1] & W[k];
+                    acc_or |= W[k - 1] | W[k];
+                } else if (k == 12) {
+                    acc_and &= W[k];
+                    acc_or |= W[k];
+                }
+                U[k] = W[k] & 0x1f1f1f1fu;
+            }
+            uint32_t F[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t r4[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int j = 3 * (4 * q + e), wq = j >> 2, rb = j & 3;
+                    uint32_t a;
+                    if (rb == 0) a = dp2a_hi(c2x, U[wq], dp2a_lo(c01, U[wq], dbase));
+                    else if (rb == 1) a = dp2a_hi(c12, U[wq], dp2a_lo(cx0, U[wq], dbase));
+                    else if (rb == 2) a = dp2a_lo(c2x, U[wq + 1], dp2a_hi(c01, U[wq], dbase));
+                    else a = dp2a_lo(c12, U[wq + 1], dp2a_hi(cx0, U[wq], dbase));
+                    r4[e] = lds_u8(a);
+                }
+                F[q] = __byte_perm(__byte_perm(r4[0], r4[1], 0x0040), __byte_perm(r4[2], r4[3], 0x0040), 0x5410);
+            }
+            const bool suspicious = ((F[0] | F[1] | F[2] | F[3]) & (DIRECT_INVALID * 0x01010101u)) | ((acc_and & p.and_need) ^ p.and_need) | (acc_or & p.or_forbid);
+            if (suspicious) {
+                uint64_t vleft = rd.left_nt >= rd.mod3 ? rd.left_nt - rd.mod3 : 0;  // translate validates 3*floor(n/3) bytes
+                if (vleft) exact_check_run(p.dna + rd.flat_start, (int)min((uint64_t)RUN_NT, vleft), p.decode, p.strict, p.key_base + rd.flat_start, p.err_key);
+            }
+            uint4 fv = make_uint4(F[0], F[1], F[2], F[3]);
+            if (rd.left_nt < (uint64_t)(RUN_NT + 2)) {
+                const uint32_t keep = min(16u, ((uint32_t)rd.left_nt * 171u) >> 9);
+                const uint4 lm = S.lowmask[keep];
+                fv.x &= lm.x; fv.y &= lm.y; fv.z &= lm.z; fv.w &= lm.w;
+            }
+            stg_stream(p.out + rd.out_base + (size_t)rd.m * 16u, fv);
+        }
+        if (!DIRECT && active) {
             // letters -> doubled codes, two letters per table lookup; Bq[q] holds nucleotides 4q..4q+3
             uint32_t Bq[13];
             uint32_t acc_and = 0xffffffffu, acc_or = 0u;
