@@ -834,3 +834,59 @@ def test_chromosome_shards_stitch_to_the_unsharded_result(qd):
         assert [bytes(f) for f in frames] == whole, (n, world)
         assert seen == [len(f) for f in whole]
         assert bytes(rc) == qd.DnaSequence(seq).reverse_complement().seq
+
+
+# ------------------------------------------------------------------ beyond 2^32 nucleotides (64-bit offsets)
+
+
+def test_offsets_beyond_4g_nucleotides(B, N):
+    """A 4.4-G-nt buffer: as ONE sequence (reverse complement, six frames) and as a uniform batch; outputs are sampled
+    near the start, across 2^32 and at the very end, and compared with the oracle on the matching slices."""
+    import torch
+
+    from quickdna_b200.synth import synth_torch
+
+    dev = torch.device("cuda:0")
+    n = (1 << 32) + 100_000_007
+    x = synth_torch(13, 0, n, dev)
+    B.dev_error_reset()
+    # ---- reverse complement of one sequence: out[n-1-i] = comp(in[i])
+    out = torch.empty(n + 16, dtype=torch.uint8, device=dev)
+    B.revcomp_dev(x, out=out[:n])
+    for lo in (0, (1 << 32) - 50, n - 1000):
+        hi = min(n, lo + 1000)
+        want = oracle.revcomp_bytes(x[lo:hi].cpu().numpy().tobytes())
+        assert out[n - hi:n - lo].cpu().numpy().tobytes() == want, lo
+    del out
+    # ---- six frames of one sequence (slot layout): frame k, residues [a, b) <-> codon starts 3a+k ...
+    runs = B.runs(n)
+    out = torch.empty(max(runs * 16 * 6, (n // 1000) * 16 * B.runs(1000) * 6), dtype=torch.uint8, device=dev)
+    L = N.lib()
+    ctx = N.default_context()
+    rc = L.qd_translate_frames_dev(ctx.handle, 1, 0, 0, 6, C.c_void_p(x.data_ptr()), n, C.c_void_p(out.data_ptr()), B._stream_ptr(torch))
+    ctx.check(rc)
+    assert B.dev_error_fetch(x) is None
+    for p0 in (0, ((1 << 32) - 48) // 3 * 3, n - 3000 - (n - 3000) % 3):  # p0 multiple of 3
+        piece = x[p0:min(n, p0 + 999)].cpu().numpy().tobytes()
+        for k in range(3):
+            want = oracle.translate_bytes(1, piece[k:])
+            off = B.slot_frame_offset(n, 6, k) + p0 // 3
+            assert out[off:off + len(want)].cpu().numpy().tobytes() == want, (p0, k)
+    tail = x[n - 3000:].cpu().numpy().tobytes()
+    rc_tail = oracle.revcomp_bytes(tail)  # the reverse strand STARTS with the end of the sequence
+    for k in range(3):
+        want = oracle.translate_bytes(1, rc_tail[k:])[:900]
+        off = B.slot_frame_offset(n, 6, 3 + k)
+        assert out[off:off + len(want)].cpu().numpy().tobytes() == want, k
+    # ---- the same bytes as a uniform batch of 1000-nt reads: the last reads live beyond offset 2^32
+    n_reads = n // 1000
+    per = 16 * B.runs(1000) * 6
+    B.translate_frames_uniform_dev(x, n_reads, 1000, out=out[: n_reads * per])
+    assert B.dev_error_fetch(x, uniform_len=1000) is None
+    o = out[: n_reads * per].view(n_reads, per)
+    for i in (0, (1 << 32) // 1000, (1 << 32) // 1000 + 1, n_reads - 1):
+        r = x[i * 1000:(i + 1) * 1000].cpu().numpy().tobytes()
+        want = oracle.py_all_frames(1, r)
+        row = o[i].cpu().numpy()
+        got = [row[B.slot_frame_offset(1000, 6, f):B.slot_frame_offset(1000, 6, f) + B.frame_len(1000, f % 3)].tobytes() for f in range(6)]
+        assert got == want, i
