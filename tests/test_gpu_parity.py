@@ -154,6 +154,39 @@ def test_exhaustive_codons_all_tables(qd):
         assert qd.DnaSequence(dna.lower()).translate(table=table).seq == got
 
 
+def test_exhaustive_codons_mask_encoding_all_tables_all_frame_modes(N):
+    """All 15^3 codons, every table, typed (mask) input through the C ABI: one frame (direct codon table), three and
+    six frames (pair decode + folded LUT) must agree with the oracle and with each other."""
+    ctx = N.default_context()
+    L = N.lib()
+    masks = np.array([m for a in range(1, 16) for b in range(1, 16) for c in range(1, 16) for m in (a, b, c)], dtype=np.uint8)
+    n = masks.size
+    for table in V.ALL_ACCEPTED_TABLES:
+        slot = oracle.table_slot(table)
+        want1 = oracle.translate_masks(slot, masks)
+        want6 = oracle.all_frames_masks(slot, masks)
+        for frames, want in ((1, [want1]), (3, want6[:3]), (6, want6)):
+            out = np.zeros(2 * n + 16, dtype=np.uint8)
+            lens = (C.c_size_t * 6)()
+            nf = C.c_int()
+            err = N.QdErr()
+            rc = L.qd_translate_frames(ctx.handle, table, 1, 0, frames, masks.ctypes.data_as(C.c_void_p), n,
+                                       out.ctypes.data_as(C.c_void_p), lens, C.byref(nf), C.byref(err))
+            assert rc == 0
+            got, off = [], 0
+            for ln in lens:
+                if ln:
+                    got.append(out[off:off + ln].tobytes())
+                off += ln
+            assert got == want, (table, frames)
+        # strict: the first ambiguous mask is reported, kind UnexpectedAmbiguous
+        err = N.QdErr()
+        out = np.zeros(n, dtype=np.uint8)
+        rc = L.qd_translate(ctx.handle, table, 1, 1, masks.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), C.byref(err))
+        first_amb = int(np.argmax(np.array([bin(int(m)).count("1") > 1 for m in masks])))
+        assert (rc, err.kind, err.pos) == (3, 3, first_amb)
+
+
 def test_device_lut_image_matches_tables_dat(N):
     img = C.string_at(N.lib().qd_table_data(0), 27 * 4096)
     assert hashlib.sha256(img).hexdigest() == V.TABLES_DAT_SHA256
