@@ -145,6 +145,12 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -615,6 +621,9 @@ struct RevcompParams {
 #ifndef QD_RC_UNROLL
 #define QD_RC_UNROLL 2
 #endif
+#ifndef QD_RC_TMA_STORE
+#define QD_RC_TMA_STORE 0  // 1: stage a tile's output in shared memory and write it with one cp.async.bulk
+#endif
 constexpr int RC_BIG_THREADS = QD_RC_THREADS, RC_SMALL_THREADS = 256;
 constexpr int RC_UNROLL = QD_RC_UNROLL;  // 16-byte output granules per thread and tile
 constexpr uint32_t RC_INVALID = 0x80;    // complement-table flag (outputs are ASCII letters or masks: bit 7 is free)
@@ -625,6 +634,9 @@ struct RevcompSmem {
     static constexpr int RAW_BYTES = (TILE_CHUNKS + 1) * 16;       // + one granule for the source misalignment
     alignas(16) uint16_t pair[PAIR_ENTRIES];
     alignas(128) uint8_t raw[STAGES][RAW_BYTES];  // source bytes of a tile (TMA landing zone)
+#if QD_RC_TMA_STORE
+    alignas(128) uint8_t outb[2][TILE_CHUNKS * 16];  // a tile's output, drained by one bulk store
+#endif
     alignas(8) uint64_t full[STAGES];
 };
 
@@ -758,10 +770,26 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 4) revcomp_kern
                             }
                     }
                 }
+#if QD_RC_TMA_STORE
+                *reinterpret_cast<uint4*>(S.outb[it & 1] + 16 * l) = o;
+#else
                 stg_stream(p.out + 16 * j, o);
+#endif
             }
         }
+#if QD_RC_TMA_STORE
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(p.out + 16 * j0, S.outb[it & 1], cnt * 16);
+            bulk_commit();
+            bulk_wait_read_1();  // the other output buffer (next tile's) has been read out
+        }
+#endif
     }
+#if QD_RC_TMA_STORE
+    if (tid == 0) bulk_wait_all();
+#endif
     // tail: out[16*full, n) = in[0, n mod 16) reversed
     if (blockIdx.x == 0 && tid < (int)(n & 15u)) {
         const uint64_t i = tid;
@@ -839,12 +867,6 @@ struct CanonParams {
 constexpr int CANON_THREADS = 256;  // windows per tile (a multiple of 16: tile outputs stay 16-byte aligned)
 constexpr int CANON_MAX_W = 64;
 
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // first word (ascending) of m[] that is non-zero, with the matching word of x[]; returns false if all are zero
 template <int NW>
