@@ -308,12 +308,21 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     const bool big = use_big_tiles(c, total_nt / RUN_NT);
     const uint64_t tile_runs = big ? BIG_THREADS : SMALL_THREADS;
     const size_t n_tiles = (size_t)((runs_upper_bound(total_nt, n_seq) + tile_runs - 1) / tile_runs);
-    QD_CUDA(c, run_prefix.reserve((n_seq + 1) * sizeof(uint64_t)));
-    // one buffer: the tile map, then the 32-run map
-    const size_t warp_map_off = ((n_tiles + 1) * sizeof(TileInfo) + 15) & ~(size_t)15;
+    // The frame kernel bulk-copies windows of run_prefix / offsets (TMA: 16-byte aligned sources, reads up to a window
+    // past the last entry), so both live in one own buffer: [run_prefix | pad of ~0][copy of the offsets | pad]
+    constexpr size_t PAD = BIG_THREADS + 8;
+    const size_t arr_entries = (n_seq + 1 + PAD + 1) & ~(size_t)1;  // even: the second array stays 16-byte aligned
+    QD_CUDA(c, run_prefix.reserve(2 * arr_entries * sizeof(uint64_t)));
+    uint64_t* const rp_dev = run_prefix.as<uint64_t>();
+    uint64_t* const off_pad = rp_dev + arr_entries;
+    QD_CUDA(c, cudaMemsetAsync(rp_dev + n_seq + 1, 0xff, (arr_entries - n_seq - 1) * sizeof(uint64_t), s));
+    QD_CUDA(c, cudaMemcpyAsync(off_pad, offsets_dev, (n_seq + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    QD_CUDA(c, cudaMemsetAsync(off_pad + n_seq + 1, 0xff, (arr_entries - n_seq - 1) * sizeof(uint64_t), s));
+    // one buffer: the tile map, then the 32-run map (padded by one tile's worth of entries)
+    const size_t warp_map_off = ((n_tiles + 1) * sizeof(TileInfo) + 127) & ~(size_t)127;
     const uint64_t n_q = runs_upper_bound(total_nt, n_seq) / 32 + 1;
-    QD_CUDA(c, tile_first.reserve(warp_map_off + n_q * sizeof(uint32_t)));
-    int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, run_prefix.as<uint64_t>(), block_sums, s);
+    QD_CUDA(c, tile_first.reserve(warp_map_off + (n_q + BIG_THREADS / 32 + 8) * sizeof(uint32_t)));
+    int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, rp_dev, block_sums, s);
     if (rc) return rc;
     const unsigned g = (unsigned)std::min<uint64_t>((n_seq + 255) / 256, (uint64_t)c->sm_count * 8);
     tile_info_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), offsets_dev, flat_base, n_seq, tile_first.as<TileInfo>(), n_tiles, tile_runs);
@@ -325,8 +334,8 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     FramesParams p{};
     p.dna = dna_dev;
     p.total_nt = total_nt;
-    p.offsets = offsets_dev;
-    p.run_prefix = run_prefix.as<uint64_t>();
+    p.offsets = off_pad;
+    p.run_prefix = rp_dev;
     p.tiles = tile_first.as<TileInfo>();
     p.warp_first = warp_first;
     p.n_seq = n_seq;

@@ -251,11 +251,12 @@ struct FramesSmem {
     alignas(128) uint8_t raw[STAGES][TileGeom<THREADS>::RAW_BYTES];  // multi-buffered raw input of a tile, 2-nt halo included
     alignas(8) uint64_t full[STAGES];             // mbarriers: raw[b] has landed
     uint64_t span[STAGES][2];                     // flat [start, end) of the input span staged in raw[b]
-    // variable-length batches: run prefix and CSR offsets of the sequences a tile touches, prefetched one tile ahead
-    // with cp.async so that no dependent global load sits between two tiles (one CTA per SM: nothing else hides it)
-    alignas(8) uint64_t rp_cache[2][TileGeom<THREADS>::SEARCH_CAP + 2];
-    alignas(8) uint64_t off_cache[2][TileGeom<THREADS>::SEARCH_CAP + 2];
-    uint32_t warp_first[2][THREADS / 32];
+    // variable-length batches: run prefix and CSR offsets of the sequences a tile touches and the per-warp sequence map,
+    // bulk-copied together with the tile's bytes (same mbarrier), so no dependent global load sits between two tiles
+    alignas(16) uint64_t rp_cache[2][TileGeom<THREADS>::SEARCH_CAP + 6];
+    alignas(16) uint64_t off_cache[2][TileGeom<THREADS>::SEARCH_CAP + 6];
+    alignas(16) uint32_t warp_first[2][THREADS / 32];
+    uint32_t first_seq[2];  // first sequence of the tile staged in buffer b
 };
 
 static_assert(offsetof(FramesSmem<SMALL_THREADS>, lut) == 0 && (2 * 14 + PAIR_FLAG) * (1 + LUT_K1 + LUT_K2) + 2 <= sizeof(FramesSmem<SMALL_THREADS>),
@@ -292,36 +293,26 @@ __device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesPara
 #pragma unroll 1
         for (uintptr_t a = max(t1, a0); a < a1; a++) S.raw[b][a - a0] = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : (uint8_t)0;
     }
-    if (t1 > t0) {
-        const uint32_t bytes = (uint32_t)(t1 - t0);
+    const uint32_t bytes = t1 > t0 ? (uint32_t)(t1 - t0) : 0u;
+    if (p.tiles) {
+        // geometry of a variable-length tile: windows of run_prefix / offsets starting at the tile's first sequence (the host
+        // keeps 16-byte aligned, ~0-padded copies of both arrays, so an even index is an aligned source) and the tile's
+        // slice of the 32-run sequence map
+        constexpr uint32_t CAP = TileGeom<THREADS>::SEARCH_CAP;
+        const uint32_t r_first = p.tiles[t].first_seq, rs = r_first & 1u;
+        constexpr uint32_t WIN_BYTES = (CAP + 4) * 8, MAP_BYTES = (THREADS / 32) * 4;
+        S.first_seq[b] = r_first;
+        mbar_expect_tx(&S.full[b], bytes + 2 * WIN_BYTES + MAP_BYTES);  // release: plain stores above are visible with the phase
+        tma_bulk_g2s(S.rp_cache[b], p.run_prefix + (r_first - rs), WIN_BYTES, &S.full[b]);
+        tma_bulk_g2s(S.off_cache[b], p.offsets + (r_first - rs), WIN_BYTES, &S.full[b]);
+        tma_bulk_g2s(S.warp_first[b], p.warp_first + t * (THREADS / 32), MAP_BYTES, &S.full[b]);
+        if (bytes) tma_bulk_g2s(S.raw[b] + (t0 - a0), reinterpret_cast<const void*>(t0), bytes, &S.full[b]);
+    } else if (bytes) {
         mbar_expect_tx(&S.full[b], bytes);  // release: the byte stores above are visible to whoever observes the phase
         tma_bulk_g2s(S.raw[b] + (t0 - a0), reinterpret_cast<const void*>(t0), bytes, &S.full[b]);
     } else {
         mbar_arrive(&S.full[b]);
     }
-}
-
-// variable-length batches: start the asynchronous copy of the geometry window of the tile whose first sequence is r_first
-template <int THREADS>
-__device__ __forceinline__ void issue_geometry_window(FramesSmem<THREADS>& S, const FramesParams& p, uint64_t tile, uint64_t total_runs,
-                                                      uint32_t r_first, int b) {
-    constexpr int CAP = TileGeom<THREADS>::SEARCH_CAP;
-    if (threadIdx.x < THREADS / 32) {
-        const uint64_t q = tile * (TileGeom<THREADS>::RUNS / 32) + threadIdx.x;
-        if (q * 32 < total_runs) cp_async_4(&S.warp_first[b][threadIdx.x], p.warp_first + q);
-        else S.warp_first[b][threadIdx.x] = r_first;
-    }
-    for (uint32_t i = threadIdx.x; i <= (uint32_t)CAP + 1; i += THREADS) {
-        const uint64_t r = (uint64_t)r_first + i;
-        if (r <= p.n_seq) {
-            cp_async_8(&S.rp_cache[b][i], p.run_prefix + r);
-            cp_async_8(&S.off_cache[b][i], p.offsets + r);
-        } else {
-            S.rp_cache[b][i] = ~0ull;  // never <= a run index
-            S.off_cache[b][i] = 0;
-        }
-    }
-    cp_async_commit();
 }
 
 template <int FRAMES, int THREADS, bool DIRECT = false>
@@ -365,12 +356,6 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
     const uint32_t lut_base = smem_u32(S.lut);
     const uint32_t pair_base = smem_u32(S.pair);
     const uint32_t pair_coef = p.pair_coef;
-    uint32_t first_cur = 0, first_nxt = 0;  // first sequence of this CTA's current / next tile (variable-length batches)
-    if (!uniform) {
-        if (blockIdx.x < n_tiles) first_cur = p.tiles[blockIdx.x].first_seq;
-        if (blockIdx.x < n_tiles) issue_geometry_window<THREADS>(S, p, blockIdx.x, total_runs, p.tiles[blockIdx.x].first_seq, 0);
-        if (blockIdx.x + (uint64_t)gridDim.x < n_tiles) first_nxt = p.tiles[blockIdx.x + (uint64_t)gridDim.x].first_seq;
-    }
     __syncthreads();
 
     uint32_t it = 0;
@@ -394,10 +379,11 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
             rd.flat_start = (uint64_t)r * p.uniform_len + in_seq;
             rd.out_base = (uint64_t)r * ((uint64_t)p.uniform_runs * (16u * FRAMES));
         } else {
-            // the geometry window of this tile was requested one tile ago
-            cp_async_wait_all();
-            __syncthreads();
-            const uint64_t* rpc = S.rp_cache[buf];
+            // the geometry windows of this tile arrived with its bytes (same mbarrier)
+            mbar_wait(&S.full[buf], (it / STAGES) & 1);
+            const uint32_t first_cur = S.first_seq[buf];
+            const uint64_t* rpc = S.rp_cache[buf] + (first_cur & 1u);
+            const uint64_t* offc = S.off_cache[buf] + (first_cur & 1u);
             const uint32_t gl = active ? tid : 0;  // run index relative to g0
             const uint64_t g = g0 + gl;
             // largest i with run_prefix[r_first + i] <= g: it is at or after the sequence of my warp's first run, and at most
@@ -413,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
                 const uint32_t mid = (lo + hi + 1) >> 1;
                 if (rpc[mid] <= g) lo = mid; else hi = mid - 1;
             }
-            uint64_t rp = rpc[lo], off_lo = S.off_cache[buf][lo], off_hi = S.off_cache[buf][lo + 1];
+            uint64_t rp = rpc[lo], off_lo = offc[lo], off_hi = offc[lo + 1];
             if (lo == SEARCH_CAP) {  // more than SEARCH_CAP sequences start inside this tile: finish in global
                 uint64_t a = (uint64_t)first_cur + lo, b = p.n_seq;  // invariant: run_prefix[a] <= g
                 while (a < b) {
@@ -426,13 +412,21 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
             }
             const uint64_t o0 = off_lo - p.flat_base;
             const uint64_t n = off_hi - off_lo;
-            rd.m = (uint32_t)(g0 + gl - rp);
-            rd.runs = (uint32_t)((n + RUN_NT - 1) / RUN_NT);
-            rd.mod3 = (n >> 32) ? (uint32_t)(n % 3) : ((uint32_t)n % 3u);
+            rd.m = (uint32_t)(g - rp);
+            if ((n >> 32) == 0) {  // the usual case: 32-bit arithmetic
+                const uint32_t n32 = (uint32_t)n, in_seq = rd.m * RUN_NT;
+                rd.runs = (n32 + RUN_NT - 1) / RUN_NT;
+                rd.mod3 = n32 % 3u;
+                rd.left_nt = n32 - in_seq;
+                rd.flat_start = o0 + in_seq;
+            } else {
+                const uint64_t in_seq = (uint64_t)rd.m * RUN_NT;
+                rd.runs = (uint32_t)((n + RUN_NT - 1) / RUN_NT);
+                rd.mod3 = (uint32_t)(n % 3);
+                rd.left_nt = n - in_seq;
+                rd.flat_start = o0 + in_seq;
+            }
             rd.tiny = n < 3;
-            const uint64_t in_seq = (uint64_t)rd.m * RUN_NT;
-            rd.left_nt = n - in_seq;
-            rd.flat_start = o0 + in_seq;
             rd.out_base = rp * (16u * FRAMES);
         }
 
@@ -468,12 +462,6 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
         }
         __syncthreads();  // every thread holds its bytes: raw[buf] can be refilled
         if (tid == 0 && tile + STAGES * (uint64_t)gridDim.x < n_tiles) stage_tile(S, p, tile + STAGES * (uint64_t)gridDim.x, total_runs, buf);
-        if (!uniform) {
-            // everyone is past this tile's geometry reads (barrier above) and past the previous tile's: refill the other window
-            if (tile + gridDim.x < n_tiles) issue_geometry_window<THREADS>(S, p, tile + gridDim.x, total_runs, first_nxt, buf ^ 1);
-            first_cur = first_nxt;
-            if (tile + 2 * (uint64_t)gridDim.x < n_tiles) first_nxt = p.tiles[tile + 2 * (uint64_t)gridDim.x].first_seq;
-        }
 
         // ---- phase 2: one run per thread: 48 codon starts -> 16 residues per frame per strand -----
         if (DIRECT && active) {
