@@ -872,8 +872,10 @@ __device__ __forceinline__ bool first_nonzero(const uint32_t (&m)[NW], const uin
 
 // fw(x): relabel the packed window by first occurrence.  V[k] = 0x55555555 restricted to the window's positions.
 template <int NW>
-__device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW]) {
+__device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW],
+                                                             bool* three_found = nullptr) {
     const uint32_t c0 = x[0] & 3u;
+    bool found3 = false;
     const uint32_t C0 = c0 * 0x55555555u;
     uint32_t ne1[NW], msel, xsel;
 #pragma unroll
@@ -893,8 +895,12 @@ __device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)
             const uint32_t e = x[k] ^ C1;
             ne2[k] = ne1[k] & (e | (e >> 1));  // ... and from c1
         }
-        if (first_nonzero<NW>(ne2, x, msel, xsel)) v = c0 ^ ((xsel >> (__ffs(msel) - 1)) & 3u);
+        if (first_nonzero<NW>(ne2, x, msel, xsel)) {
+            v = c0 ^ ((xsel >> (__ffs(msel) - 1)) & 3u);
+            found3 = true;
+        }
     }
+    if (three_found) *three_found = found3;  // three distinct bases seen: the map is final even if x is only a prefix
     // k = M^-1 (x ^ c0), M = [u v] as columns:  k0 = v1 z0 ^ v0 z1,  k1 = u1 z0 ^ u0 z1   (z = x ^ c0)
     const uint32_t v0 = v & 1u, v1 = v >> 1, u0 = u & 1u, u1 = u >> 1, c00 = c0 & 1u, c01 = c0 >> 1;
     const uint32_t P = v1 * 0x55555555u | u0 * 0xaaaaaaaau;               // applied to x in place
@@ -1046,27 +1052,60 @@ __global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const 
                 else { s += i / nw; i %= nw; }
             }
             const uint32_t o = (uint32_t)(dna_lo + s * p.seq_len + i - a0);  // nucleotide offset inside the streams
-            uint32_t x[NW], y[NW];
-            {
-                const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
-#pragma unroll
-                for (int k = 0; k < NW; k++) x[k] = __funnelshift_r(S.c2[wi + k], S.c2[wi + k + 1], sh) & (V[k] * 3u);
-            }
-            uint32_t perm = forward_canonical_packed<NW>(x, V, y);  // perm: the relabelling of codes 0..3, 2 bits each
-            bool use_rev = false;
-            if (!p.forward_only) {
-                uint32_t xr[NW], yr[NW];
-                reverse_pairs<NW>(x, w, xr);
-                const uint32_t perm_r = forward_canonical_packed<NW>(xr, V, yr);
-                // lexical order: the lowest differing 2-bit group decides (first nucleotide = bits 0..1)
-                uint32_t d[NW], dsel, ysel;
-#pragma unroll
-                for (int k = 0; k < NW; k++) d[k] = y[k] ^ yr[k];
-                if (first_nonzero<NW>(d, y, dsel, ysel)) {
-                    const uint32_t pos = (__ffs(dsel) - 1) & ~1u;
-                    use_rev = (((ysel ^ dsel) >> pos) & 3u) < ((ysel >> pos) & 3u);
+            uint32_t perm = 0;
+            bool use_rev = false, decided = false;
+            if (NW > 1) {
+                // Fast path: the relabelling is fixed by the first three distinct bases and the lexical minimum by the first
+                // differing position -- for all but low-complexity windows both lie within the first 16 nucleotides of the
+                // window and of its reverse.  One word from each end; anything unresolved takes the full-width path below.
+                const uint32_t V16[1] = {0x55555555u};
+                uint32_t h[1], t[1], yh[1], yt[1];
+                {
+                    const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
+                    h[0] = __funnelshift_r(S.c2[wi], S.c2[wi + 1], sh);
+                    const uint32_t ot = o + w - 16u, wt = ot >> 4, st = (ot & 15u) * 2u;
+                    const uint32_t tail = __brev(__funnelshift_r(S.c2[wt], S.c2[wt + 1], st));  // last 16 nucleotides ...
+                    t[0] = ((tail >> 1) & 0x55555555u) | ((tail & 0x55555555u) << 1);             // ... in reversed order
                 }
-                if (use_rev) perm = perm_r;
+                bool f3 = false, r3 = false;
+                const uint32_t pf = forward_canonical_packed<1>(h, V16, yh, &f3);
+                if (p.forward_only) {
+                    decided = f3;
+                    perm = pf;
+                } else {
+                    const uint32_t pr = forward_canonical_packed<1>(t, V16, yt, &r3);
+                    const uint32_t d = yh[0] ^ yt[0];
+                    if (f3 && r3 && d) {
+                        const uint32_t pos = (__ffs(d) - 1) & ~1u;
+                        use_rev = ((yt[0] >> pos) & 3u) < ((yh[0] >> pos) & 3u);
+                        perm = use_rev ? pr : pf;
+                        decided = true;
+                    }
+                }
+            }
+            if (!decided) {
+                uint32_t x[NW], y[NW];
+                {
+                    const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
+#pragma unroll
+                    for (int k = 0; k < NW; k++) x[k] = __funnelshift_r(S.c2[wi + k], S.c2[wi + k + 1], sh) & (V[k] * 3u);
+                }
+                perm = forward_canonical_packed<NW>(x, V, y);  // perm: the relabelling of codes 0..3, 2 bits each
+                use_rev = false;
+                if (!p.forward_only) {
+                    uint32_t xr[NW], yr[NW];
+                    reverse_pairs<NW>(x, w, xr);
+                    const uint32_t perm_r = forward_canonical_packed<NW>(xr, V, yr);
+                    // lexical order: the lowest differing 2-bit group decides (first nucleotide = bits 0..1)
+                    uint32_t d[NW], dsel, ysel;
+#pragma unroll
+                    for (int k = 0; k < NW; k++) d[k] = y[k] ^ yr[k];
+                    if (first_nonzero<NW>(d, y, dsel, ysel)) {
+                        const uint32_t pos = (__ffs(dsel) - 1) & ~1u;
+                        use_rev = (((ysel ^ dsel) >> pos) & 3u) < ((ysel >> pos) & 3u);
+                    }
+                    if (use_rev) perm = perm_r;
+                }
             }
             // the window's letters: T[code] = letters[perm[code]]
             uint32_t t = (perm | (perm << 4)) & 0x0f0fu;
