@@ -237,8 +237,9 @@ int qd_translate_frames_dev(qd_ctx *ctx, int table, int enc, int strict, int fra
 int qd_translate_frames_batch_uniform_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
                                           const uint8_t *dna_dev, size_t n_seq, size_t seq_len,
                                           uint8_t *out_dev, void *stream);
-/* variable lengths: CSR offsets on the device (absolute, offsets_dev[0] corresponds to dna_dev[0]);
- * the run prefix / tile map the kernel needs are built on `stream` in context-owned scratch. */
+/* variable lengths: CSR offsets on the device, offsets_dev[0] == 0 (sequence i is dna_dev[offsets[i] .. offsets[i+1]));
+ * the run prefix, the padded offsets copy and the tile maps the kernel needs are built on `stream` in context-owned
+ * scratch. */
 int qd_translate_frames_batch_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
                                   const uint8_t *dna_dev, const uint64_t *offsets_dev,
                                   size_t n_seq, size_t total_nt, uint8_t *out_dev, void *stream);
