@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=0)
     ap.add_argument("--revcomp-nt", type=int, default=250_000_000)
     ap.add_argument("--expansion-windows", type=int, default=20_000_000, help="42-nt windows per GPU in the expansion leg")
+    ap.add_argument("--windows-all-seqs", type=int, default=1000, help="99 999-nt sequences per GPU in the all_windows leg")
     ap.add_argument("--canon-seqs", type=int, default=4000, help="99 999-nt sequences per GPU in the canonical-window leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -434,6 +435,29 @@ def main():
                     n_rep += 1
                 extra["canonical_windows"]["cpu_port"] = {"windows_per_s": n_rep * (seq_len - w + 1) / (time.perf_counter() - t0), "cores": 1,
                                                           "sample": f"{n_rep} x one {seq_len}-nt sequence, oracle/qd_oracle.c"}
+
+    # ---- extra: the all_windows shape (benches/all_windows.rs: 42-nt DNA windows of both strands + 20-aa windows of the
+    # six frames) materialised for a batch of 99 999-nt sequences: 124 output bytes per nucleotide
+    if not args.no_extra:
+        seq_len, n_sw = 99_999, min(args.windows_all_seqs, total_nt // 99_999)
+        if n_sw > 0:
+            counts = (__import__("ctypes").c_size_t * 8)()
+            L.qd_windows_all_batch_counts(seq_len, 42, 20, counts)
+            cs = list(counts)
+            dna_bytes, aa_bytes = 2 * n_sw * cs[0] * 42, n_sw * sum(cs[2:]) * 20
+            if dna_bytes + aa_bytes + 64 <= out.numel():
+                d_out, a_out = out[:dna_bytes], out[(dna_bytes + 15) // 16 * 16:(dna_bytes + 15) // 16 * 16 + aa_bytes]
+                B.dev_error_reset(ctx)
+                wa_ms = timed(lambda: B.windows_all_batch_dev(x, n_sw, seq_len, 42, 20, dna_out=d_out, aa_out=a_out, ctx=ctx), reps=3)
+                assert B.dev_error_fetch(x, uniform_len=seq_len, strict=True, ctx=ctx) is None
+                wa_bytes = n_sw * seq_len + dna_bytes + aa_bytes
+                gbs = wa_bytes / (wa_ms * 1e-3) / 1e9
+                extra["windows_all"] = {
+                    "workload": f"all_windows shape for {n_sw} x {seq_len}-nt strict sequences per GPU: {n_sw * sum(cs)} windows "
+                                "(six-frame kernel + 2 DNA-window launches + 6 amino-acid-window launches)",
+                    "nt_per_s": world * n_sw * seq_len / (wa_ms * 1e-3), "windows_per_s": world * n_sw * sum(cs) / (wa_ms * 1e-3), "ms": wa_ms,
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                                 "kernel": "windows_batch_kernel (+ translate_frames_kernel<6>)", "algorithmic_bytes_per_launch": wa_bytes}}
 
     # ---- extra: BASELINE config 1 shape (one 29 901-nt genome, translate table 1) through the Python drop-in API:
     # latency of one call, host bytes in, host bytes out (launch + two copies; the reference's CPU path wins here)

@@ -260,6 +260,26 @@ int qd_canonical_windows_batch_dev(qd_ctx *ctx, int enc, int forward_only, const
 int qd_expansion_windows_dev(qd_ctx *ctx, int enc, const uint8_t *windows_dev, size_t n_win, size_t w,
                              uint64_t max_expansions, uint64_t *counts_dev, uint64_t *out_index_dev,
                              uint8_t *out_dev, uint64_t out_capacity_rows, void *stream);
+/* windows of a batch: n_seq sequences of seq_len bytes back to back; out_dev = [n_seq][seq_len - w + 1][w], tightly packed.
+ * mode: what a window's bytes are -- */
+enum {
+    QD_WIN_COPY = 0,          /* the bytes as they are (ProteinSequence::windows, typed DnaSequence::windows)      */
+    QD_WIN_DNA_ASCII = 1,     /* strict DNA letters -> upper-case letters (benches/all_windows.rs:84-86)           */
+    QD_WIN_DNA_ASCII_RC = 2,  /* windows of the reverse complement (:87-92), never materialised: window i, byte j =
+                                 complement(seq[len - 1 - i - j])                                                   */
+    QD_WIN_MASK_ASCII = 3,    /* strict masks -> letters                                                            */
+    QD_WIN_MASK_ASCII_RC = 4
+};
+int qd_windows_batch_dev(qd_ctx *ctx, const uint8_t *seq_dev, size_t n_seq, size_t seq_len, size_t w, int mode,
+                         uint8_t *out_dev, void *stream);
+/* benches/all_windows.rs:78-102 (SequenceWindows::from_dna, table Ncbi1) for a batch of strict sequences:
+ *   dna_out_dev = [forward windows: n_seq x counts[0] x w_dna][reverse-complement windows: same size]
+ *   aa_out_dev  = six blocks, block f (frame order fwd0..2, rc0..2) = [n_seq][counts[2+f]][w_aa]
+ * counts come from qd_windows_all_batch_counts (returns their sum); the origin index of every window is the closed
+ * form of benches/all_windows.rs:39-75 (see qd_windows_all).  Either output may be NULL. */
+size_t qd_windows_all_batch_counts(size_t seq_len, size_t w_dna, size_t w_aa, size_t counts[8]);
+int qd_windows_all_batch_dev(qd_ctx *ctx, int enc, const uint8_t *dna_dev, size_t n_seq, size_t seq_len, size_t w_dna,
+                             size_t w_aa, uint8_t *dna_out_dev, uint8_t *aa_out_dev, void *stream);
 int qd_windows_dev(qd_ctx *ctx, const uint8_t *seq_dev, size_t n, size_t w, uint8_t *out_dev,
                    void *stream);
 

@@ -374,6 +374,41 @@ def expansion_windows_dev(windows, max_expansions: int = 16, out=None, enc: int 
     return counts, out_index, out
 
 
+def windows_batch_dev(seq, n_seq: int, seq_len: int, w: int, mode: int = 0, out=None, ctx: Optional[N.Context] = None):
+    """qd_windows_batch_dev: every length-w window of each of n_seq sequences (torch uint8 CUDA tensor) -> [n_seq * count, w].
+    mode: 0 copy, 1 strict DNA letters upper-cased, 2 windows of the reverse complement, 3 / 4 the same from masks."""
+    import torch
+
+    ctx = ctx or N.default_context(seq.device.index or 0)
+    nw = max(0, seq_len - w + 1)
+    if out is None:
+        out = torch.empty(max(n_seq * nw * w, 16), dtype=torch.uint8, device=seq.device)
+    rc = N.lib().qd_windows_batch_dev(ctx.handle, C.c_void_p(seq.data_ptr()), n_seq, seq_len, w, mode, C.c_void_p(out.data_ptr()),
+                                      _stream_ptr(torch))
+    ctx.check(rc)
+    return out[: n_seq * nw * w].view(n_seq * nw, w) if nw else out[:0].view(0, w)
+
+
+def windows_all_batch_dev(dna, n_seq: int, seq_len: int, w_dna: int = 42, w_aa: int = 20, enc: int = N.ENC_ASCII, dna_out=None,
+                          aa_out=None, ctx: Optional[N.Context] = None):
+    """benches/all_windows.rs SequenceWindows::from_dna for a batch (table Ncbi1): returns (counts[8], dna windows
+    [forward block, reverse-complement block], aa windows [six frame blocks])."""
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    counts = (C.c_size_t * 8)()
+    N.lib().qd_windows_all_batch_counts(seq_len, w_dna, w_aa, counts)
+    cs = list(counts)
+    if dna_out is None:
+        dna_out = torch.empty(max(2 * n_seq * cs[0] * w_dna, 16), dtype=torch.uint8, device=dna.device)
+    if aa_out is None:
+        aa_out = torch.empty(max(n_seq * sum(cs[2:]) * w_aa, 16), dtype=torch.uint8, device=dna.device)
+    rc = N.lib().qd_windows_all_batch_dev(ctx.handle, enc, C.c_void_p(dna.data_ptr()), n_seq, seq_len, w_dna, w_aa,
+                                          C.c_void_p(dna_out.data_ptr()), C.c_void_p(aa_out.data_ptr()), _stream_ptr(torch))
+    ctx.check(rc)
+    return cs, dna_out, aa_out
+
+
 def dev_error_reset(ctx: Optional[N.Context] = None):
     import torch
 

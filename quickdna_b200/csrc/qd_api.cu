@@ -989,6 +989,82 @@ static int windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, ui
     return QD_OK;
 }
 
+// windows of n_seq sequences (sequence s at src + s * stride, `len` bytes each), see windows_batch_kernel
+static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride, size_t n_seq, size_t len, size_t w, int mode,
+                             uint8_t* out_dev, uint64_t key_stride, cudaStream_t s) {
+    if (w < 1 || w > 64 || len > 0xffffffffull || mode < QD_WIN_COPY || mode > QD_WIN_MASK_ASCII_RC) return QD_ERR_INVALID_ARGUMENT;
+    if (len < w || n_seq == 0) return QD_OK;
+    static const int map_tab[5] = {-1, TAB_UPPER_ASCII_STRICT, TAB_RC_ASCII_STRICT, TAB_MASK_TO_ASCII_STRICT, TAB_RC_MASK_TO_ASCII_STRICT};
+    WindowsBatchParams p{};
+    p.src = src_dev;
+    p.src_stride = stride;
+    p.n_seq = n_seq;
+    p.len = (uint32_t)len;
+    p.w = (uint32_t)w;
+    p.reverse = (mode == QD_WIN_DNA_ASCII_RC || mode == QD_WIN_MASK_ASCII_RC) ? 1 : 0;
+    p.map = map_tab[mode] < 0 ? nullptr : tab(c, map_tab[mode]);
+    p.out = out_dev;
+    p.key_stride = key_stride;
+    p.err_key = c->d_err;
+    const uint64_t tiles = (uint64_t)n_seq * ((len - w + 1 + WIN_WPT - 1) / WIN_WPT);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + WIN_WARPS - 1) / WIN_WARPS, (uint64_t)c->sm_count * 6));
+    windows_batch_kernel<<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_windows_batch_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n_seq, size_t seq_len, size_t w, int mode, uint8_t* out_dev,
+                                    void* stream) {
+    if (!c) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return windows_batch_dev(c, seq_dev, seq_len, n_seq, seq_len, w, mode, out_dev, seq_len, pick_stream(c, stream));
+}
+
+extern "C" size_t qd_windows_all_batch_counts(size_t seq_len, size_t w_dna, size_t w_aa, size_t counts[8]) {
+    auto nwin = [](size_t len, size_t w) { return len + 1 - std::min(w, len + 1); };  // benches/all_windows.rs:209-211
+    size_t total = 0;
+    counts[0] = counts[1] = nwin(seq_len, w_dna);
+    for (int f = 0; f < 6; f++) {
+        const size_t fl = qd_frame_len(seq_len, f % 3);
+        counts[2 + f] = fl ? nwin(fl, w_aa) : 0;
+    }
+    for (int i = 0; i < 8; i++) total += counts[i];
+    return total;
+}
+
+extern "C" int qd_windows_all_batch_dev(qd_ctx* c, int enc, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w_dna, size_t w_aa,
+                                        uint8_t* dna_out_dev, uint8_t* aa_out_dev, void* stream) {
+    if (!c || w_dna < 1 || w_aa < 1 || w_dna > 64 || w_aa > 64) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n_seq == 0 || seq_len == 0) return QD_OK;
+    cudaStream_t s = pick_stream(c, stream);
+    size_t counts[8];
+    qd_windows_all_batch_counts(seq_len, w_dna, w_aa, counts);
+    // forward and reverse-complement DNA windows straight from the input (strict alphabet: anything else is an error)
+    const int fwd_mode = enc == QD_ENC_ASCII ? QD_WIN_DNA_ASCII : QD_WIN_MASK_ASCII;
+    if (dna_out_dev && counts[0]) {
+        if (int rc = windows_batch_dev(c, dna_dev, seq_len, n_seq, seq_len, w_dna, fwd_mode, dna_out_dev, seq_len, s)) return rc;
+        if (int rc = windows_batch_dev(c, dna_dev, seq_len, n_seq, seq_len, w_dna, fwd_mode + 1, dna_out_dev + n_seq * counts[0] * w_dna, seq_len, s)) return rc;
+    }
+    if (aa_out_dev) {
+        // six frames (table Ncbi1, as SequenceWindows::from_dna does) into context scratch, then their windows
+        const size_t slots = qd_slots_bytes(seq_len, 6);
+        QD_CUDA(c, c->aux2.reserve(n_seq * slots + 16));
+        if (int rc = frames_uniform_dev(c, 0, enc, 1, QD_FRAMES_ALL, dna_dev, n_seq, seq_len, c->aux2.as<uint8_t>(), s)) return rc;
+        size_t at = 0;
+        for (int f = 0; f < 6; f++) {
+            if (!counts[2 + f]) continue;
+            const uint8_t* frame0 = c->aux2.as<uint8_t>() + qd_slot_frame_offset(seq_len, 6, f);
+            if (int rc = windows_batch_dev(c, frame0, slots, n_seq, qd_frame_len(seq_len, f % 3), w_aa, QD_WIN_COPY, aa_out_dev + at, seq_len, s)) return rc;
+            at += n_seq * counts[2 + f] * w_aa;
+        }
+    }
+    return QD_OK;
+}
+
 extern "C" int qd_windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, uint8_t* out_dev, void* stream) {
     if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(c->mu);

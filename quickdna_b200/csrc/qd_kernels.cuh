@@ -810,6 +810,115 @@ __global__ void __launch_bounds__(256) windows_kernel(const uint8_t* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Windows of a batch (DnaSequence::windows / ProteinSequence::windows over many sequences, and the DNA / amino-acid
+// window sets of benches/all_windows.rs:78-102): out[s][i][j] = map(seq_s[i + j]), or with REVERSE the windows of the
+// reverse complement, out[s][i][j] = map(seq_s[len - 1 - i - j]) -- taken straight from the forward strand, the reverse
+// complement is never materialised.  `map` is a 256-byte table (identity when NULL; 0 = reject, for the strict DNA
+// alphabets).  Sequence s starts at src + s * src_stride and has `len` bytes.
+// A warp owns 64 consecutive windows of ONE sequence: the <= 64 + w - 1 source bytes go through the table into shared
+// memory once (reversed if REVERSE), every lane re-aligns its window with funnel shifts and stores it into a staging
+// row, and the staged rows leave with aligned 128-bit stores.
+// ------------------------------------------------------------------------------------------------
+struct WindowsBatchParams {
+    const uint8_t* src;
+    uint64_t src_stride;
+    uint64_t n_seq;
+    uint32_t len;  // bytes per sequence (<= 2^32 - 1)
+    uint32_t w;    // 1 <= w <= 64
+    int reverse;
+    const uint8_t* map;  // 256-byte table or NULL
+    uint8_t* out;        // n_seq * (len - w + 1) * w bytes
+    uint64_t key_stride;  // error key of byte i of sequence s = s * key_stride + i
+    unsigned long long* err_key;
+};
+constexpr int WIN_WPT = 64, WIN_WARPS = 8;
+struct WinWarpSmem {
+    alignas(16) uint8_t srcb[4 + WIN_WPT + 64 + 16];
+    alignas(16) uint8_t stage[WIN_WPT * 64 + 32];
+};
+
+__global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const WindowsBatchParams p) {
+    __shared__ WinWarpSmem SM[WIN_WARPS];
+    __shared__ uint8_t map_s[256];
+    for (int i = threadIdx.x; i < 256; i += 32 * WIN_WARPS) map_s[i] = p.map ? __ldg(p.map + i) : (uint8_t)i;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    WinWarpSmem& S = SM[threadIdx.x >> 5];
+    const uint32_t w = p.w, nw = p.len - w + 1;
+    const uint32_t tiles_per_seq = (nw + WIN_WPT - 1) / WIN_WPT;
+    const uint64_t n_tiles = p.n_seq * tiles_per_seq;
+    const uint64_t warps_total = (uint64_t)gridDim.x * WIN_WARPS;
+    uint64_t tile = (uint64_t)blockIdx.x * WIN_WARPS + (threadIdx.x >> 5);
+    uint64_t s = tile / tiles_per_seq;
+    uint32_t t = (uint32_t)(tile % tiles_per_seq);
+    const uint64_t step_s = warps_total / tiles_per_seq;
+    const uint32_t step_t = (uint32_t)(warps_total % tiles_per_seq);
+    for (; tile < n_tiles; tile += warps_total) {
+        const uint32_t i0 = t * WIN_WPT, cnt = min((uint32_t)WIN_WPT, nw - i0), span = cnt + w - 1;
+        const uint8_t* seq = p.src + s * p.src_stride;
+        // source bytes of the tile, mapped, in window order: srcb[k] = map(seq[i0 + k]) or map(seq[len - 1 - i0 - k])
+        for (uint32_t k = lane; k < span; k += 32) {
+            const uint32_t at = p.reverse ? p.len - 1 - i0 - k : i0 + k;
+            const uint32_t v = map_s[__ldg(seq + at)];
+            if (v == 0 && p.map) atomicMin(p.err_key, (unsigned long long)(s * p.key_stride + at));
+            S.srcb[4 + k] = (uint8_t)v;  // 4-byte front pad: a row's first destination word may start before its window
+        }
+        __syncwarp();
+        const uint64_t out0 = (s * nw + i0) * (uint64_t)w;
+        uint8_t* gdst = p.out + out0;
+        const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
+#pragma unroll 1
+        for (uint32_t l = lane; l < cnt; l += 32) {
+            // window l = src[l .. l + w) -> stage row at D = phase + l * w.  Words are formed ALIGNED TO THE DESTINATION:
+            // destination word m (bytes D0 + 4m ..) holds source bytes l - a + 4m .., a = D & 3; the middle words are whole
+            // 32-bit stores, only the first and the last word of a row can be partial
+            const uint32_t D = phase + l * w, a = D & 3u;
+            const uint32_t b0 = l + 4u - a;  // source offset of destination word 0, in srcb coordinates (4-byte front pad)
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.srcb) + (b0 >> 2);
+            const uint32_t sh = (b0 & 3u) * 8u;
+            uint32_t* dw = reinterpret_cast<uint32_t*>(S.stage + (D & ~3u));
+            const uint32_t n_words = (a + w + 3u) >> 2, tail = (a + w) & 3u, whole_end = (a + w) >> 2;
+            uint32_t prev = sw[0], m = 0;
+            if (a != 0) {  // first word: bytes a .. min(4, a + w) - 1
+                const uint32_t next = sw[1];
+                const uint32_t word = __funnelshift_r(prev, next, sh);
+                prev = next;
+                uint8_t* db = reinterpret_cast<uint8_t*>(dw);
+                const uint32_t hi = min(4u, a + w);
+                if (a <= 1 && hi > 1) db[1] = (uint8_t)(word >> 8);
+                if (a <= 2 && hi > 2) db[2] = (uint8_t)(word >> 16);
+                if (hi > 3) db[3] = (uint8_t)(word >> 24);
+                m = 1;
+            }
+#pragma unroll 4
+            for (; m < whole_end; m++) {  // whole words
+                const uint32_t next = sw[m + 1];
+                dw[m] = __funnelshift_r(prev, next, sh);
+                prev = next;
+            }
+            if (tail != 0 && (a == 0 || n_words > 1)) {  // last word: bytes 0 .. tail - 1
+                const uint32_t word = __funnelshift_r(prev, sw[m + 1], sh);
+                uint8_t* db = reinterpret_cast<uint8_t*>(dw + m);
+                db[0] = (uint8_t)word;
+                if (tail > 1) db[1] = (uint8_t)(word >> 8);
+                if (tail > 2) db[2] = (uint8_t)(word >> 16);
+            }
+        }
+        __syncwarp();
+        const uint32_t nbytes = cnt * w;
+        const uint32_t head = min(nbytes, (16u - phase) & 15u), body = (nbytes - head) >> 4;
+        if (lane < (int)head) gdst[lane] = S.stage[phase + lane];
+        for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(S.stage + phase + head + 16 * c));
+        const uint32_t done = head + 16 * body;
+        if (lane < (int)(nbytes - done)) gdst[done + lane] = S.stage[phase + done + lane];
+        __syncwarp();
+        s += step_s;
+        t += step_t;
+        if (t >= tiles_per_seq) { t -= tiles_per_seq; s++; }
+    }
+}
+
 // origin indices of benches/all_windows.rs:39-75 for one segment of windows
 //   kind 0: i ; kind 1: count-1-i ; kind 2: 3*i + f ; kind 3: L - ((i + w_aa)*3 + f)
 __global__ void origin_kernel(uint64_t* __restrict__ out, uint64_t count, int kind, uint64_t f, uint64_t L, uint64_t w_aa) {

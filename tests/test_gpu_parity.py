@@ -923,3 +923,60 @@ def test_offsets_beyond_4g_nucleotides(B, N):
         row = o[i].cpu().numpy()
         got = [row[B.slot_frame_offset(1000, 6, f):B.slot_frame_offset(1000, 6, f) + B.frame_len(1000, f % 3)].tobytes() for f in range(6)]
         assert got == want, i
+
+
+# ------------------------------------------------------------------ batched windows / all_windows shape
+
+
+def test_windows_batch_and_windows_all_batch(B):
+    """Batched windows (copy / strict DNA / reverse-complement windows taken from the forward strand) and the
+    benches/all_windows.rs window sets for a batch, against the oracle sequence by sequence."""
+    import torch
+
+    rng = np.random.default_rng(71)
+    for n_seq, L, w_dna, w_aa in ((3, 999, 42, 20), (40, 100, 42, 20), (7, 42, 42, 20), (5, 300, 17, 5), (2, 5000, 64, 33), (9, 61, 1, 1),
+                                  (4, 130, 63, 64)):
+        a = np.frombuffer(_rand(rng, n_seq * L, b"ACGTacgt"), dtype=np.uint8).reshape(n_seq, L).copy()
+        x = torch.from_numpy(a).cuda()
+        B.dev_error_reset()
+        # plain copy windows (ProteinSequence::windows shape)
+        got = B.windows_batch_dev(x, n_seq, L, w_aa, mode=0).cpu().numpy()
+        nw = L - w_aa + 1
+        for s in range(n_seq):
+            assert got[s * nw:(s + 1) * nw].tobytes() == oracle.windows(a[s], w_aa).tobytes(), (n_seq, L, s)
+        counts, dna_w, aa_w = B.windows_all_batch_dev(x, n_seq, L, w_dna, w_aa)
+        assert B.dev_error_fetch(x, uniform_len=L, strict=True) is None
+        dna_w, aa_w = dna_w.cpu().numpy(), aa_w.cpu().numpy()
+        nd = counts[0]
+        aa_base = 0
+        want_all = [oracle.windows_all(oracle.masks_of(a[s]), w_dna, w_aa) for s in range(n_seq)]
+        for s in range(n_seq):
+            wd, wa, _origin, cs = want_all[s]
+            assert cs[:2] == counts[:2] and [c for c in cs[2:] if c] == [c for c in counts[2:] if c]
+            assert dna_w[(s * nd) * w_dna:((s + 1) * nd) * w_dna].tobytes() == wd[:nd].tobytes(), ("fwd", n_seq, L, s)
+            assert dna_w[(n_seq * nd + s * nd) * w_dna:(n_seq * nd + (s + 1) * nd) * w_dna].tobytes() == wd[nd:].tobytes(), ("rc", n_seq, L, s)
+        for f in range(6):
+            cf = counts[2 + f]
+            if not cf:
+                continue
+            for s in range(n_seq):
+                wa, cs = want_all[s][1], want_all[s][3]
+                present = [c for c in cs[2:]]
+                lo = sum(present[:f])
+                got_f = aa_w[(aa_base + s * cf) * w_aa:(aa_base + (s + 1) * cf) * w_aa]
+                assert got_f.tobytes() == wa[lo:lo + cf].tobytes(), ("aa", f, n_seq, L, s)
+            aa_base += n_seq * cf
+    # masks in, and an ambiguity code is an error with its sequence and position
+    a = np.frombuffer(_rand(rng, 6 * 200, b"ACGT"), dtype=np.uint8).reshape(6, 200).copy()
+    m = np.stack([oracle.masks_of(a[s]) for s in range(6)])
+    xm = torch.from_numpy(m).cuda()
+    got = B.windows_batch_dev(xm, 6, 200, 42, mode=4).cpu().numpy()
+    for s in range(6):
+        rc = np.frombuffer(oracle.revcomp_bytes(a[s].tobytes()), dtype=np.uint8)
+        assert got[s * 159:(s + 1) * 159].tobytes() == oracle.windows(rc, 42).tobytes()
+    a[4, 77] = ord("N")
+    x = torch.from_numpy(a).cuda()
+    B.dev_error_reset()
+    B.windows_batch_dev(x, 6, 200, 42, mode=1)
+    e = B.dev_error_fetch(x, uniform_len=200, strict=True)
+    assert e is not None and (e.seq_index, e.pos, e.kind, e.byte) == (4, 77, 3, ord("N"))
