@@ -675,9 +675,9 @@ extern "C" int qd_translate_frames_batch_dev(qd_ctx* c, int table, int enc, int 
                           c->block_sums, out_dev, pick_stream(c, stream));
 }
 
-template <int NW>
+template <int NW, int W = 0>
 static int launch_canonical_windows(qd_ctx* c, const CanonParams& p, cudaStream_t s) {
-    auto kern = canonical_windows_kernel<NW>;
+    auto kern = canonical_windows_kernel<NW, W>;
     const size_t smem = (size_t)CanonWarpLayout(p.w).total_bytes * CANON_WARPS + PAIR_ENTRIES;
     QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -711,6 +711,7 @@ static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dn
     p.filler = ascii ? 0x41u : 0x01u;
     p.letters = ascii ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
     p.err_key = c->d_err;
+    if (w == 42) return launch_canonical_windows<3, 42>(c, p, s);  // the window length of benches/canonical.rs: unrolled
     switch ((2 * w + 31) / 32) {
         case 1: return launch_canonical_windows<1>(c, p, s);
         case 2: return launch_canonical_windows<2>(c, p, s);

@@ -1099,10 +1099,12 @@ struct CanonWarpSmem {
 };
 constexpr int CANON_WARPS = CANON_THREADS / 32;
 
-template <int NW>
+// W: the window length when it is a compile-time constant (42: benches/canonical.rs), 0 = p.w
+template <int NW, int W = 0>
 __global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const CanonParams p) {
+    static_assert(W == 0 || (2 * W + 31) / 32 == NW, "NW must be the word count of W");
     extern __shared__ __align__(128) unsigned char canon_smem[];
-    const uint32_t w = p.w;
+    const uint32_t w = W ? (uint32_t)W : p.w;
     const CanonWarpLayout lay(w);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     CanonWarpSmem S;
@@ -1184,8 +1186,11 @@ __global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const 
         }
         __syncwarp();
         // ---- my windows ----------------------------------------------------------------------------------
+        // lane handles windows 2 * lane and 2 * lane + 1: for even w all rows of one pass share their alignment in the stage
 #pragma unroll 1
-        for (uint32_t l = lane; l < cnt; l += 32) {
+        for (uint32_t pass = 0; pass < CANON_WPT / 32; pass++) {
+            const uint32_t l = (CANON_WPT / 32) * lane + pass;
+            if (l >= cnt) continue;
             uint64_t s = s0, i = i0 + l;
             if (i >= nw) {
                 if (nw >= CANON_WPT) { i -= nw; s++; }
@@ -1260,27 +1265,45 @@ __global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const 
 #pragma unroll
             for (int k = 0; k <= NN; k++) N[k] = stream[wi + k];
             uint8_t* dst = S.stage + (size_t)l * w;
-            const bool even = (w & 1u) == 0;  // every window then starts at an even offset: 16-bit stores
+            // the row's letters, four per PRMT
+            uint32_t Lw[2 * NN];
 #pragma unroll
             for (int k = 0; k < NN; k++) {
                 const uint32_t sel = __funnelshift_r(N[k], N[k + 1], sh);  // nucleotides 8k .. 8k+7
+                Lw[2 * k] = __byte_perm(T, 0, sel);
+                Lw[2 * k + 1] = __byte_perm(T, 0, sel >> 16);
+            }
+            if ((w & 1u) == 0) {
+                // even w: a row starts 4-byte aligned or 2 bytes past; whole 32-bit stores in between.  The alignment is the
+                // same for every row of this pass, so the branch does not diverge.
+                if (((l * w) & 2u) == 0) {
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const uint32_t j = 8 * k + 4 * q;
-                    // groups below 16 (NW - 1) are complete for every w this instantiation serves
-                    const bool surely_full = j + 4 <= 16 * (NW - 1);
-                    if (surely_full || j < w) {
-                        const uint32_t four = __byte_perm(T, 0, q ? (sel >> 16) : sel);
-                        const uint32_t left = surely_full ? 4u : w - j;
-                        if (even) {
-                            *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)four;
-                            if (left > 2) *reinterpret_cast<uint16_t*>(dst + j + 2) = (uint16_t)(four >> 16);
-                        } else {
-                            dst[j] = (uint8_t)four;
-                            if (left > 1) dst[j + 1] = (uint8_t)(four >> 8);
-                            if (left > 2) dst[j + 2] = (uint8_t)(four >> 16);
-                            if (left > 3) dst[j + 3] = (uint8_t)(four >> 24);
-                        }
+                    for (int m = 0; m < 2 * NN; m++) {
+                        const uint32_t j = 4 * m;
+                        if ((W ? j + 4 <= (uint32_t)W : j + 4 <= 16 * (NW - 1)) || j + 4 <= w) *reinterpret_cast<uint32_t*>(dst + j) = Lw[m];
+                        else if (j < w) *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)Lw[m];  // w % 4 == 2: the last two bytes
+                    }
+                } else {
+                    *reinterpret_cast<uint16_t*>(dst) = (uint16_t)Lw[0];
+#pragma unroll
+                    for (int m = 0; m + 1 < 2 * NN; m++) {
+                        const uint32_t j = 4 * m + 2;  // row bytes j .. j+3 sit in one aligned stage word
+                        const uint32_t word = __funnelshift_r(Lw[m], Lw[m + 1], 16);
+                        if ((W ? j + 4 <= (uint32_t)W : j + 4 <= 16 * (NW - 1)) || j + 4 <= w) *reinterpret_cast<uint32_t*>(dst + j) = word;
+                        else if (j < w) *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)word;
+                    }
+                    if (8 * NN - 2 < w) *reinterpret_cast<uint16_t*>(dst + 8 * NN - 2) = (uint16_t)(Lw[2 * NN - 1] >> 16);  // w == 16 NW
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 2 * NN; m++) {
+                    const uint32_t j = 4 * m;
+                    if (j < w) {
+                        const uint32_t four = Lw[m], left = w - j;
+                        dst[j] = (uint8_t)four;
+                        if (left > 1) dst[j + 1] = (uint8_t)(four >> 8);
+                        if (left > 2) dst[j + 2] = (uint8_t)(four >> 16);
+                        if (left > 3) dst[j + 3] = (uint8_t)(four >> 24);
                     }
                 }
             }

@@ -183,22 +183,22 @@ int main(int argc, char** argv) {
             q.letters = 'A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24);
             q.err_key = d_err;
             const size_t smem_c = (size_t)CanonWarpLayout((uint32_t)w).total_bytes * CANON_WARPS + PAIR_ENTRIES;
-            CK(cudaFuncSetAttribute(canonical_windows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+            CK(cudaFuncSetAttribute(canonical_windows_kernel<3, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
             const uint64_t blocks = (nwin + CANON_THREADS - 1) / CANON_THREADS;
 #ifndef KB_CW_OCC
 #define KB_CW_OCC 4
 #endif
             int occ_c = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, canonical_windows_kernel<3>, CANON_THREADS, smem_c));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, canonical_windows_kernel<3, 42>, CANON_THREADS, smem_c));
 #ifdef KB_CW_OCC_FORCE
             occ_c = KB_CW_OCC_FORCE;
 #endif
             const unsigned gc = (unsigned)std::min<uint64_t>(blocks, (uint64_t)sms * occ_c);
             printf("canonical occ %d smem %zu\n", occ_c, smem_c);
-            canonical_windows_kernel<3><<<gc, CANON_THREADS, smem_c>>>(q);
+            canonical_windows_kernel<3, 42><<<gc, CANON_THREADS, smem_c>>>(q);
             CK(cudaDeviceSynchronize());
             CK(cudaEventRecord(e0));
-            for (int i = 0; i < 3; i++) canonical_windows_kernel<3><<<gc, CANON_THREADS, smem_c>>>(q);
+            for (int i = 0; i < 3; i++) canonical_windows_kernel<3, 42><<<gc, CANON_THREADS, smem_c>>>(q);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             CK(cudaEventElapsedTime(&ms, e0, e1));
