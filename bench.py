@@ -468,6 +468,7 @@ def main():
         genome = qd.DnaSequence(synth_np(1, 0, 29_901, b"acgt").tobytes())
         for _ in range(20):
             genome.translate(1)
+            genome.reverse_complement()
         t0 = time.perf_counter()
         for _ in range(200):
             genome.translate(1)

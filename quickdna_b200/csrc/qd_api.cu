@@ -52,6 +52,9 @@ struct DevBuf {
 };
 
 constexpr int N_PIPE = 3;  // streams / buffer sets of the chunked host pipeline
+// host calls whose device result is at most this big come back as ONE device->host copy [result | error key] into pinned
+// memory (the reference's typical call is a 30-kb genome: launch and copy count is what it costs here)
+constexpr size_t SMALL_CALL_BYTES = size_t(2) << 20;
 
 struct Pipe {
     cudaStream_t stream = nullptr;
@@ -78,6 +81,7 @@ struct qd_ctx {
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
+    uint8_t* h_stage = nullptr;           // pinned staging for small host calls: [result | error key] in ONE copy
     DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums, parse_counts, parse_offsets, canon_state, fasta_scratch;
     Pipe pipe[N_PIPE];
     size_t chunk_bytes = size_t(64) << 20;   // input bytes per pipeline chunk
@@ -248,7 +252,7 @@ int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s, 
 
 // uniform batch (also the single-sequence case n_seq = 1) on device buffers
 int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna_dev, size_t n_seq,
-                       size_t seq_len, uint8_t* out_dev, cudaStream_t s, uint64_t key_base = 0) {
+                       size_t seq_len, uint8_t* out_dev, cudaStream_t s, uint64_t key_base = 0, unsigned long long* err_key = nullptr) {
     if (n_seq == 0 || seq_len == 0) return QD_OK;
     const uint64_t runs = (seq_len + RUN_NT - 1) / RUN_NT;
     const uint64_t total_runs = runs * n_seq;
@@ -276,7 +280,7 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     set_encoding(c, p, enc, strict);
     if (frames == QD_FRAMES_ONE)
         if (int rc = direct_table(c, slot, enc, strict, s, &p.direct)) return rc;
-    p.err_key = c->d_err;
+    p.err_key = err_key ? err_key : c->d_err;
     p.key_base = key_base;
     return launch_frames(c, frames, p, s, big);
 }
@@ -370,7 +374,8 @@ int launch_revcomp_t(qd_ctx* c, const RevcompParams& p, cudaStream_t s, int occ_
 }
 
 // `which` = one of RC_PAIR_*: selects the complement table (256-byte form and letter-pair form)
-int revcomp_dev_table(qd_ctx* c, int which, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, cudaStream_t s) {
+int revcomp_dev_table(qd_ctx* c, int which, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, cudaStream_t s,
+                      unsigned long long* err_key = nullptr) {
     if (n == 0) return QD_OK;
     static const int byte_tab[RC_PAIR_COUNT] = {TAB_RC_ASCII, TAB_RC_ASCII_STRICT, TAB_RC_MASK, TAB_RC_MASK_STRICT,
                                                 TAB_RC_MASK_TO_ASCII, TAB_RC_MASK_TO_ASCII_STRICT};
@@ -385,7 +390,7 @@ int revcomp_dev_table(qd_ctx* c, int which, const uint8_t* dna_dev, size_t n, ui
     p.and_need = ascii_in ? 0x40404040u : 0u;
     p.or_forbid = ascii_in ? 0x80808080u : 0xe0e0e0e0u;
     p.filler = ascii_in ? 0x41u : 0x01u;
-    p.err_key = c->d_err;
+    p.err_key = err_key ? err_key : c->d_err;
     // big tiles once every SM gets two of them
     const bool big = (n >> 4) >= (uint64_t)2 * RevcompSmem<RC_BIG_THREADS>::TILE_CHUNKS * (uint64_t)c->sm_count && c->big_tile_min_runs != ~0ull;
     if (big || c->big_tile_min_runs == 0) return launch_revcomp_t<RC_BIG_THREADS>(c, p, s, 1);
@@ -446,6 +451,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
+    ok &= cudaHostAlloc(&c->h_stage, SMALL_CALL_BYTES + 64, cudaHostAllocDefault) == cudaSuccess;
     if (ok) {
         std::vector<uint8_t> tabs(256 * TAB_COUNT);
         auto put = [&](int which, const uint8_t* src) { memcpy(tabs.data() + 256 * which, src, 256); };
@@ -502,6 +508,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1100,15 +1107,40 @@ extern "C" int qd_translate_frames(qd_ctx* c, int table, int enc, int strict, in
     QD_CUDA(c, cudaSetDevice(c->device));
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
+    const size_t slot_bytes = qd_slots_bytes(n, frames);
     QD_CUDA(c, c->in.reserve(n + 16));
-    QD_CUDA(c, c->out.reserve(qd_slots_bytes(n, frames)));
+    QD_CUDA(c, c->out.reserve(slot_bytes + 16));
     QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
+    if (slot_bytes <= SMALL_CALL_BYTES) {
+        // small call: the error key lives right behind the slots, so result and key come back in one copy
+        unsigned long long* key_dev = reinterpret_cast<unsigned long long*>(c->out.as<uint8_t>() + slot_bytes);  // 16-byte aligned
+        QD_CUDA(c, cudaMemsetAsync(key_dev, 0xff, 8, s));
+        if (int rc = frames_uniform_dev(c, slot, enc, strict, frames, c->in.as<uint8_t>(), 1, n, c->out.as<uint8_t>(), s, 0, key_dev)) return rc;
+        QD_CUDA(c, cudaMemcpyAsync(c->h_stage, c->out.p, slot_bytes + 8, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        unsigned long long key;
+        memcpy(&key, c->h_stage + slot_bytes, 8);
+        if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+        size_t off = 0;
+        int nf = 0;
+        for (int f = 0; f < n_slots; f++) {
+            const size_t len = qd_frame_len(n, f % 3);
+            if (out_len) out_len[f] = len;
+            if (len) {
+                memcpy(out + off, c->h_stage + qd_slot_frame_offset(n, frames, f), len);
+                off += len;
+                nf++;
+            }
+        }
+        if (n_frames) *n_frames = nf;
+        return QD_OK;
+    }
     if (int rc = reset_err_key(c, s)) return rc;
     if (int rc = frames_uniform_dev(c, slot, enc, strict, frames, c->in.as<uint8_t>(), 1, n, c->out.as<uint8_t>(), s)) return rc;
     // gather the frames tightly: f0|f1|f2[|r0|r1|r2]
     size_t off = 0;
     int nf = 0;
-    const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
     for (int f = 0; f < n_slots; f++) {
         const size_t len = qd_frame_len(n, f % 3);
         if (out_len) out_len[f] = len;
@@ -1135,8 +1167,22 @@ extern "C" int qd_revcomp(qd_ctx* c, int enc, int strict, const uint8_t* dna, si
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(n + 16));
     QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
-    if (int rc = reset_err_key(c, s)) return rc;
     const int which = enc == QD_ENC_ASCII ? (strict ? RC_PAIR_ASCII_STRICT : RC_PAIR_ASCII) : (strict ? RC_PAIR_MASK_STRICT : RC_PAIR_MASK);
+    if (n <= SMALL_CALL_BYTES) {  // small call: [result | error key] in one copy through pinned memory
+        const size_t key_off = (n + 15) & ~(size_t)15;
+        QD_CUDA(c, c->out.reserve(key_off + 16));
+        unsigned long long* key_dev = reinterpret_cast<unsigned long long*>(c->out.as<uint8_t>() + key_off);
+        QD_CUDA(c, cudaMemsetAsync(key_dev, 0xff, 8, s));
+        if (int rc = revcomp_dev_table(c, which, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s, key_dev)) return rc;
+        QD_CUDA(c, cudaMemcpyAsync(c->h_stage, c->out.p, key_off + 8, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        unsigned long long key;
+        memcpy(&key, c->h_stage + key_off, 8);
+        if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+        memcpy(out, c->h_stage, n);
+        return QD_OK;
+    }
+    if (int rc = reset_err_key(c, s)) return rc;
     if (int rc = revcomp_dev_table(c, which, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s)) return rc;
     QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, n, cudaMemcpyDeviceToHost, s));
     unsigned long long key = 0;
