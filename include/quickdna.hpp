@@ -324,6 +324,169 @@ class DnaSequence {
     std::vector<T> dna_;
 };
 
+// ---- src/iter.rs, src/trans_table.rs:165-174: per-element lazy adaptors ----------------------------------------
+//
+// The reference's `NucleotideIter` extension trait composes adaptors over any nucleotide iterator; every use it has is
+// over a slice, so the mirror is a pair of O(1) views over a BORROWED span (no copies, no allocation per element):
+// `NucleotideView` (a strand: forward / reversed, plain / complemented) and `CodonsView` (one reading frame of it).
+// They are host-side by nature -- one element per call, exactly like the Rust iterators -- and exist for API parity;
+// anything that walks a whole sequence should call DnaSequence::translate / translate_*_frames / reverse_complement,
+// which are one kernel launch.  `to_fn` reads the same 27 x 4096-byte LUT image the device tables are built from.
+
+// N::Codon, src/nucleotide.rs:354, 396
+template <class T>
+struct Codon {
+    T n[3];
+    bool operator==(const Codon& o) const { return n[0] == o.n[0] && n[1] == o.n[1] && n[2] == o.n[2]; }
+    bool operator!=(const Codon& o) const { return !(*this == o); }
+    std::string to_string() const { return {to_ascii(n[0]), to_ascii(n[1]), to_ascii(n[2])}; }  // Display, :380-384
+};
+
+// TranslationTable::to_fn, src/trans_table.rs:165-174: codon -> amino acid over one 4096-byte slice,
+// index (m0 << 8) | (m1 << 4) | m2 (CodonIdx, :75-103)
+inline auto to_fn(TranslationTable table) {
+    const uint8_t* slice = qd_table_data(qd_table_slot(static_cast<int>(table)));
+    return [slice](const auto& codon) -> uint8_t {
+        return slice[(static_cast<unsigned>(codon.n[0]) << 8) | (static_cast<unsigned>(codon.n[1]) << 4) | static_cast<unsigned>(codon.n[2])];
+    };
+}
+
+template <class T>
+class CodonsView;
+
+template <class T>
+class NucleotideView {
+    static_assert(is_nucleotide_like<T>);
+
+  public:
+    NucleotideView() = default;
+    NucleotideView(const T* p, size_t n) : p_(p), n_(n) {}
+    explicit NucleotideView(const std::vector<T>& v) : p_(v.data()), n_(v.size()) {}
+    explicit NucleotideView(const DnaSequence<T>& s) : NucleotideView(s.as_slice()) {}
+
+    size_t len() const { return n_; }
+    bool is_empty() const { return n_ == 0; }
+    T operator[](size_t j) const {
+        const T v = p_[rev_ ? n_ - 1 - j : j];
+        return comp_ ? quickdna::complement(v) : v;
+    }
+    // iter.rs:148-157
+    NucleotideView complement() const {
+        NucleotideView r = *this;
+        r.comp_ = !comp_;
+        return r;
+    }
+    // iter.rs:171-177 (`self.rev().complement()`)
+    NucleotideView reverse_complement() const {
+        NucleotideView r = *this;
+        r.rev_ = !rev_;
+        r.comp_ = !comp_;
+        return r;
+    }
+    // `next()` k times / `next_back()` k times
+    NucleotideView skip(size_t k) const {
+        NucleotideView r = *this;
+        k = k < n_ ? k : n_;
+        if (!rev_) r.p_ += k;
+        r.n_ -= k;
+        return r;
+    }
+    NucleotideView skip_back(size_t k) const {
+        NucleotideView r = *this;
+        k = k < n_ ? k : n_;
+        if (rev_) r.p_ += k;
+        r.n_ -= k;
+        return r;
+    }
+    // trim_to_codon / trimmed_to_codon, iter.rs:253-283
+    NucleotideView trimmed_to_codon() const { return skip_back(n_ % 3); }
+    // iter.rs:125-134
+    CodonsView<T> codons() const;
+    // iter.rs:221-236: frames at offsets 0, 1, 2; empty ones dropped
+    std::vector<CodonsView<T>> self_reading_frames() const;
+    // iter.rs:75-103: forward frames, then the frames of the reverse complement; empty ones dropped
+    std::vector<CodonsView<T>> all_reading_frames() const;
+    std::vector<T> collect() const {
+        std::vector<T> v(n_);
+        for (size_t j = 0; j < n_; j++) v[j] = (*this)[j];
+        return v;
+    }
+
+  private:
+    const T* p_ = nullptr;
+    size_t n_ = 0;
+    bool rev_ = false, comp_ = false;
+};
+
+// Codons<N, I> / ForwardOrRcCodons<N, I>, iter.rs:292-448: one view type serves both, the strand is a property of the
+// NucleotideView underneath.  Double-ended like the reference: next() takes from the front, next_back() from the back
+// (after trimming the incomplete trailing codon, :322-323).
+template <class T>
+class CodonsView {
+  public:
+    CodonsView() = default;
+    explicit CodonsView(NucleotideView<T> v) : v_(v), front_(0), back_(v.len() / 3) {}
+    size_t len() const { return back_ - front_; }  // ExactSizeIterator, :335-343
+    bool is_empty() const { return len() == 0; }
+    Codon<T> operator[](size_t i) const {
+        const size_t j = 3 * (front_ + i);
+        return Codon<T>{{v_[j], v_[j + 1], v_[j + 2]}};
+    }
+    bool next(Codon<T>* out) {
+        if (front_ == back_) return false;
+        *out = (*this)[0];
+        front_++;
+        return true;
+    }
+    bool next_back(Codon<T>* out) {
+        if (front_ == back_) return false;
+        *out = (*this)[len() - 1];
+        back_--;
+        return true;
+    }
+    std::vector<Codon<T>> collect() const {
+        std::vector<Codon<T>> r;
+        r.reserve(len());
+        for (size_t i = 0; i < len(); i++) r.push_back((*this)[i]);
+        return r;
+    }
+    std::vector<Codon<T>> collect_rev() const {  // `.rev().collect()`
+        std::vector<Codon<T>> r;
+        r.reserve(len());
+        for (size_t i = len(); i-- > 0;) r.push_back((*this)[i]);
+        return r;
+    }
+    // `.map(f).collect()`, e.g. f = to_fn(table)
+    template <class F>
+    std::vector<uint8_t> map(F f) const {
+        std::vector<uint8_t> r(len());
+        for (size_t i = 0; i < len(); i++) r[i] = f((*this)[i]);
+        return r;
+    }
+
+  private:
+    NucleotideView<T> v_;
+    size_t front_ = 0, back_ = 0;
+};
+
+template <class T>
+CodonsView<T> NucleotideView<T>::codons() const {
+    return CodonsView<T>(*this);
+}
+template <class T>
+std::vector<CodonsView<T>> NucleotideView<T>::self_reading_frames() const {
+    std::vector<CodonsView<T>> frames;
+    for (size_t k = 0; k < 3; k++)
+        if (CodonsView<T> f = skip(k).codons(); f.len() > 0) frames.push_back(f);
+    return frames;
+}
+template <class T>
+std::vector<CodonsView<T>> NucleotideView<T>::all_reading_frames() const {
+    std::vector<CodonsView<T>> frames = self_reading_frames();
+    for (const CodonsView<T>& f : reverse_complement().self_reading_frames()) frames.push_back(f);
+    return frames;
+}
+
 // ---- src/fasta.rs ------------------------------------------------------------------------------------
 
 // FastaParseSettings, src/fasta.rs:67-110

@@ -17,6 +17,16 @@ def test_mirror_binary_is_built():
     assert os.path.exists(BIN)
 
 
+def test_lazy_adaptor_views_on_host():
+    """NucleotideView / CodonsView / to_fn (src/iter.rs, src/trans_table.rs:165-174): host-side views, no kernel."""
+    import __graft_entry__ as g
+
+    g.build()
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_iter_views")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
 @pytest.mark.gpu
 def test_rust_api_mirror_on_gpu():
     import __graft_entry__ as g
