@@ -424,6 +424,27 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": cw_gbs, "peak": peak, "unit": "GB/s", "frac": cw_gbs / peak, "traffic": None,
                              "kernel": "canonical_windows_kernel<3>", "algorithmic_bytes_per_launch": nwin * (1 + w),
                              "note": "ALU-bound (about 500 thread-instructions per 42-byte window), not HBM-bound"}}
+            # the same windows as fixed-width keys: 64-bit fingerprints, then lossless 16-byte packed windows (two bit planes)
+            keys = {}
+            for kind, label, kb in ((N.CANON_KEY_FP64, "fingerprint_64", 8), (N.CANON_KEY_PACKED, "packed_2bit", 16)):
+                kout = out.view(torch.int32)
+                for _ in range(2):
+                    B.canonical_window_keys_dev(x, n_seq, seq_len, w, kind=kind, out=kout, ctx=ctx)
+                barrier()
+                ev0.record()
+                for _ in range(reps):
+                    B.canonical_window_keys_dev(x, n_seq, seq_len, w, kind=kind, out=kout, ctx=ctx)
+                ev1.record()
+                barrier()
+                k_ms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
+                k_gbs = nwin * (1 + kb) / (k_ms * 1e-3) / 1e9
+                keys[label] = {"ms": k_ms, "windows_per_s": world * nwin / (k_ms * 1e-3), "key_bytes": kb,
+                               "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": None,
+                                            "kernel": f"canonical_keys_kernel<2, 42, {kind}>", "algorithmic_bytes_per_launch": nwin * (1 + kb),
+                                            "note": "ALU-bound (about 150 thread-instructions per window), not HBM-bound"}}
+            extra["canonical_window_keys"] = {
+                "workload": f"one key per canonical 42-nt window of the same {n_seq} x {seq_len}-nt sequences (SURVEY 8(f) rank 3)",
+                "speedup_vs_materialised_rows": {k: cw_ms / v["ms"] for k, v in keys.items()}, **keys}
             if rank == 0 and world == 1 and not args.no_cpu:
                 import oracle
 

@@ -254,6 +254,28 @@ int qd_canonical_windows_dev(qd_ctx *ctx, int enc, int forward_only, const uint8
  * span two sequences; out holds n_seq * (seq_len - w + 1) windows of w bytes, tightly packed */
 int qd_canonical_windows_batch_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev,
                                    size_t n_seq, size_t seq_len, size_t w, uint8_t *out_dev, void *stream);
+/* ---- canonical window KEYS ------------------------------------------------
+ * One fixed-width key per canonical window instead of its w materialised bytes -- the form a downstream
+ * set lookup (the consumer benches/all_windows.rs:15-102 was adapted from) wants, and 5x-42x fewer output
+ * bytes.  The window arithmetic is exactly qd_canonical_windows' (src/canonical.rs:17-55, 71-118, 129-179).
+ *   QD_CANON_KEY_PACKED  the canonical window itself, lossless, as two bit planes: PW = ceil(w / 32) uint32
+ *                        words with the LOW bit of each nucleotide's code (A, T, C, G = 0, 1, 2, 3: the
+ *                        reference's Ord; nucleotide j at bit j % 32 of word j / 32), then PW words with the
+ *                        HIGH bits; unused bits zero.  8 bytes per window for w <= 32, else 16.
+ *   QD_CANON_KEY_FP64    a 64-bit fingerprint of those words: h = 0x9e3779b97f4a7c15 * w; for k < PW:
+ *                        h = mix64(h ^ (lo[k] | (uint64) hi[k] << 32)), mix64 = the splitmix64 finaliser
+ *                        (z ^= z >> 30; z *= 0xbf58476d1ce4e5b9; z ^= z >> 27; z *= 0x94d049bb133111eb;
+ *                        z ^= z >> 31).  Injective for w <= 32.
+ * qd_canonical_key_bytes: bytes per key (0 = bad kind / w).  qd_canonical_fingerprint: the FP64 key of one
+ * PACKED key, on the host (what the kernel computes).  Keys are in window order, tightly packed; keys_dev
+ * 16-byte aligned.  Windows never span two sequences. */
+enum { QD_CANON_KEY_PACKED = 0, QD_CANON_KEY_FP64 = 1 };
+size_t qd_canonical_key_bytes(int kind, size_t w);
+uint64_t qd_canonical_fingerprint(const uint32_t *packed, size_t w);
+int qd_canonical_window_keys(qd_ctx *ctx, int enc, int forward_only, int kind, const uint8_t *dna, size_t n,
+                             size_t w, void *keys, qd_err *err);
+int qd_canonical_window_keys_dev(qd_ctx *ctx, int enc, int forward_only, int kind, const uint8_t *dna_dev,
+                                 size_t n_seq, size_t seq_len, size_t w, void *keys_dev, void *stream);
 /* expansions on device buffers (w <= 64, max_expansions < 128): counts_dev[n_win], out_index_dev[n_win + 1] (device
  * uint64; skipped windows repeat the next index), rows into out_dev while they fit out_capacity_rows
  * (out_index_dev[n_win] tells how many there are).  out_dev may be NULL: counts and indices only. */

@@ -27,6 +27,7 @@ ENC_ASCII = 0
 ENC_MASK = 1
 FRAMES_ONE = 1
 FRAMES_SELF = 3
+CANON_KEY_PACKED, CANON_KEY_FP64 = 0, 1
 FRAMES_ALL = 6
 
 
@@ -97,6 +98,10 @@ SIGNATURES = {
     "qd_canonical": (_i, [_vp, _i, _i, _vp, _sz, _vp, C.POINTER(QdErr)]),
     "qd_canonical_dev": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
     "qd_canonical_windows_batch_dev": (_i, [_vp, _i, _i, _vp, _sz, _sz, _sz, _vp, _vp]),
+    "qd_canonical_key_bytes": (_sz, [_i, _sz]),
+    "qd_canonical_fingerprint": (C.c_uint64, [_vp, _sz]),
+    "qd_canonical_window_keys": (_i, [_vp, _i, _i, _i, _vp, _sz, _sz, _vp, C.POINTER(QdErr)]),
+    "qd_canonical_window_keys_dev": (_i, [_vp, _i, _i, _i, _vp, _sz, _sz, _sz, _vp, _vp]),
     "qd_expansion_windows_dev": (_i, [_vp, _i, _vp, _sz, _sz, C.c_uint64, _vp, _vp, _vp, C.c_uint64, _vp]),
     "qd_fasta_scan": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz), C.POINTER(QdErr)]),
     "qd_windows_batch_dev": (_i, [_vp, _vp, _sz, _sz, _sz, _i, _vp, _vp]),

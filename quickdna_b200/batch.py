@@ -207,6 +207,25 @@ def canonical_windows(dna, w: int = 42, forward_only: bool = False, enc: int = N
     return out
 
 
+def canonical_window_keys(dna, w: int = 42, kind: int = N.CANON_KEY_FP64, forward_only: bool = False, enc: int = N.ENC_ASCII,
+                          ctx: Optional[N.Context] = None) -> np.ndarray:
+    """One fixed-width key per canonical window of a strict sequence: kind CANON_KEY_FP64 ->
+    uint64 [count]; CANON_KEY_PACKED -> uint32 [count, 2 * ceil(w / 32)], the canonical window as two bit planes (low bits of the codes, then high bits)."""
+    ctx = ctx or N.default_context()
+    a = _u8(dna)
+    count = max(0, a.size - w + 1)
+    words = N.lib().qd_canonical_key_bytes(kind, w) // 4
+    if words == 0:
+        raise ValueError("bad key kind or window length")
+    out = np.zeros(max(count, 1) * words, dtype=np.uint32)
+    err = N.QdErr()
+    rc = N.lib().qd_canonical_window_keys(ctx.handle, enc, int(forward_only), kind, _p(a if a.size else np.zeros(1, np.uint8)), a.size, w,
+                                          _p(out), C.byref(err))
+    ctx.check(rc, err)
+    out = out[: count * words]
+    return out.view(np.uint64) if kind == N.CANON_KEY_FP64 else out.reshape(count, words)
+
+
 def expansion_windows(windows, max_expansions: int = 16, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
     """Expansions of a batch of equal-length ambiguous windows (src/expansions.rs; benches/expansions.rs:126-130).
 
@@ -354,6 +373,26 @@ def canonical_windows_batch_dev(dna, n_seq: int, seq_len: int, w: int = 42, out=
                                                 C.c_void_p(out.data_ptr()), _stream_ptr(torch))
     ctx.check(rc)
     return out[: n_seq * nw * w].view(n_seq * nw, w) if nw else out[:0].view(0, w)
+
+
+def canonical_window_keys_dev(dna, n_seq: int, seq_len: int, w: int = 42, kind: int = N.CANON_KEY_FP64, out=None,
+                              forward_only: bool = False, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    """qd_canonical_window_keys_dev on a torch uint8 CUDA tensor of n_seq x seq_len nucleotides: an int64 tensor
+    [n_windows] (CANON_KEY_FP64; the bits are the unsigned key) or an int32 tensor [n_windows, 2 * ceil(w / 32)] (PACKED: bit planes)."""
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    nw = max(0, seq_len - w + 1)
+    words = N.lib().qd_canonical_key_bytes(kind, w) // 4
+    if words == 0:
+        raise ValueError("bad key kind or window length")
+    if out is None:
+        out = torch.empty(max(n_seq * nw * words, 4), dtype=torch.int32, device=dna.device)
+    rc = N.lib().qd_canonical_window_keys_dev(ctx.handle, enc, int(forward_only), kind, C.c_void_p(dna.data_ptr()), n_seq, seq_len, w,
+                                              C.c_void_p(out.data_ptr()), _stream_ptr(torch))
+    ctx.check(rc)
+    flat = out.view(torch.int32)[: n_seq * nw * words]
+    return flat.view(torch.int64) if kind == N.CANON_KEY_FP64 else flat.view(n_seq * nw, words)
 
 
 def expansion_windows_dev(windows, max_expansions: int = 16, out=None, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):

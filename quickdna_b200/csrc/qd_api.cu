@@ -76,6 +76,8 @@ struct qd_ctx {
     uint16_t* d_pair = nullptr;   // [encoding][strict][PAIR_ENTRIES]
     uint16_t* d_rc_pair = nullptr;  // [RC_PAIR_COUNT][PAIR_ENTRIES]
     uint8_t* d_canon_pair = nullptr;  // [encoding][PAIR_ENTRIES]
+    uint8_t* d_ckey_pair = nullptr;   // [encoding][PAIR_ENTRIES]
+    CanonKeyTables* d_ckey = nullptr;
     uint16_t* d_parse_pair = nullptr;  // [strict][PAIR_ENTRIES]
     std::map<int, uint8_t*> d_direct;  // one-frame direct codon tables, built on first use: key = slot * 4 + ascii * 2 + strict
     unsigned long long* d_err = nullptr;
@@ -447,6 +449,8 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_pair, sizeof(T.pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_rc_pair, sizeof(T.rc_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_canon_pair, sizeof(T.canon_pair)) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_ckey_pair, sizeof(T.ckey_pair)) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_ckey, sizeof(T.ckey)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_parse_pair, sizeof(T.parse_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
@@ -476,6 +480,8 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         ok &= cudaMemcpy(c->d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_rc_pair, T.rc_pair, sizeof(T.rc_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_canon_pair, T.canon_pair, sizeof(T.canon_pair), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(c->d_ckey_pair, T.ckey_pair, sizeof(T.ckey_pair), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(c->d_ckey, &T.ckey, sizeof(T.ckey), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_parse_pair, T.parse_pair, sizeof(T.parse_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemset(c->d_err, 0xff, sizeof(unsigned long long)) == cudaSuccess;
     }
@@ -503,6 +509,8 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_pair) cudaFree(c->d_pair);
     if (c->d_rc_pair) cudaFree(c->d_rc_pair);
     if (c->d_canon_pair) cudaFree(c->d_canon_pair);
+    if (c->d_ckey_pair) cudaFree(c->d_ckey_pair);
+    if (c->d_ckey) cudaFree(c->d_ckey);
     if (c->d_parse_pair) cudaFree(c->d_parse_pair);
     for (auto& kv : c->d_direct) cudaFree(kv.second);
     if (c->d_err) cudaFree(c->d_err);
@@ -697,11 +705,8 @@ static int launch_canonical_windows(qd_ctx* c, const CanonParams& p, cudaStream_
     return QD_OK;
 }
 
-// every length-w window of each of n_seq sequences of seq_len nucleotides (n_seq = 1: one sequence)
-static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
-                         uint8_t* out_dev, cudaStream_t s) {
-    if (w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
-    if (seq_len < w || n_seq == 0) return QD_OK;
+static CanonParams canonical_params(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
+                                    uint8_t* out_dev) {
     CanonParams p{};
     p.dna = dna_dev;
     p.n_seq = n_seq;
@@ -718,6 +723,15 @@ static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dn
     p.filler = ascii ? 0x41u : 0x01u;
     p.letters = ascii ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
     p.err_key = c->d_err;
+    return p;
+}
+
+// every length-w window of each of n_seq sequences of seq_len nucleotides (n_seq = 1: one sequence)
+static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
+                         uint8_t* out_dev, cudaStream_t s) {
+    if (w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
+    if (seq_len < w || n_seq == 0) return QD_OK;
+    const CanonParams p = canonical_params(c, enc, forward_only, dna_dev, n_seq, seq_len, w, out_dev);
     if (w == 42) return launch_canonical_windows<3, 42>(c, p, s);  // the window length of benches/canonical.rs: unrolled
     switch ((2 * w + 31) / 32) {
         case 1: return launch_canonical_windows<1>(c, p, s);
@@ -725,6 +739,70 @@ static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dn
         case 3: return launch_canonical_windows<3>(c, p, s);
         default: return launch_canonical_windows<4>(c, p, s);
     }
+}
+
+template <int PW, int W, int KIND>
+static int launch_canonical_keys(qd_ctx* c, CanonKeyParams kp, cudaStream_t s) {
+    auto kern = canonical_keys_kernel<PW, W, KIND>;
+    const CanonParams& p = kp.base;
+    const uint64_t nw = p.seq_len - p.w + 1;
+    // the largest warp-tile (a multiple of 32 windows) whose positions fit the per-warp budget; 448 + 41 + slack = 16 x 32
+    // positions for w = 42 is two rounds of the per-position pass
+    uint32_t wpt = 448;
+    while (wpt > 32 && ckey_span_bound(wpt, p.w, nw) > 2048) wpt -= 32;
+    kp.wpt = wpt;
+    kp.pos_cap = (uint32_t)((ckey_span_bound(wpt, p.w, nw) + 31) & ~(uint64_t)31);
+    const size_t smem = CKEY_SHARED_TABLE_BYTES + (size_t)CanonKeyLayout(kp.pos_cap).total_bytes * CKEY_WARPS;
+    QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CKEY_THREADS, smem));
+    const uint64_t tiles = (p.n_seq * nw + (uint64_t)wpt * CKEY_WARPS - 1) / ((uint64_t)wpt * CKEY_WARPS);
+    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * std::max(1, occ));
+    kern<<<grid, CKEY_THREADS, smem, s>>>(kp);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+template <int KIND>
+static int canonical_keys_kind(qd_ctx* c, const CanonKeyParams& kp, cudaStream_t s) {
+    if (kp.base.w == 42) return launch_canonical_keys<2, 42, KIND>(c, kp, s);
+    return kp.base.w <= 32 ? launch_canonical_keys<1, 0, KIND>(c, kp, s) : launch_canonical_keys<2, 0, KIND>(c, kp, s);
+}
+
+// one fixed-width key per canonical window
+static int canonical_keys_dev(qd_ctx* c, int enc, int forward_only, int kind, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
+                              void* keys_dev, cudaStream_t s) {
+    if (w < 1 || w > CANON_MAX_W || (kind != QD_CANON_KEY_PACKED && kind != QD_CANON_KEY_FP64)) return QD_ERR_INVALID_ARGUMENT;
+    if (seq_len < w || n_seq == 0) return QD_OK;
+    CanonKeyParams kp{};
+    kp.base = canonical_params(c, enc, forward_only, dna_dev, n_seq, seq_len, w, static_cast<uint8_t*>(keys_dev));
+    kp.base.pair = c->d_ckey_pair + (enc == QD_ENC_ASCII ? 0 : PAIR_ENTRIES);
+    kp.tables = c->d_ckey;
+    return kind == QD_CANON_KEY_FP64 ? canonical_keys_kind<CKEY_FP64>(c, kp, s) : canonical_keys_kind<CKEY_PACKED>(c, kp, s);
+}
+
+extern "C" size_t qd_canonical_key_bytes(int kind, size_t w) {
+    if (w < 1 || w > CANON_MAX_W) return 0;
+    return kind == QD_CANON_KEY_FP64 ? 8 : (kind == QD_CANON_KEY_PACKED ? 8 * ((w + 31) / 32) : 0);
+}
+
+extern "C" uint64_t qd_canonical_fingerprint(const uint32_t* packed, size_t w) {
+    if (!packed || w < 1 || w > CANON_MAX_W) return 0;
+    if (w <= 32) {  // the same template the kernel instantiates
+        const uint32_t lo[1] = {packed[0]}, hi[1] = {packed[1]};
+        return canon_fingerprint<1>(lo, hi, (uint32_t)w);
+    }
+    const uint32_t lo[2] = {packed[0], packed[1]}, hi[2] = {packed[2], packed[3]};
+    return canon_fingerprint<2>(lo, hi, (uint32_t)w);
+}
+
+extern "C" int qd_canonical_window_keys_dev(qd_ctx* c, int enc, int forward_only, int kind, const uint8_t* dna_dev, size_t n_seq,
+                                            size_t seq_len, size_t w, void* keys_dev, void* stream) {
+    if (!c || (reinterpret_cast<uintptr_t>(keys_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    return canonical_keys_dev(c, enc, forward_only, kind, dna_dev, n_seq, seq_len, w, keys_dev, pick_stream(c, stream));
 }
 
 extern "C" int qd_canonical_windows_batch_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len,
@@ -1318,6 +1396,28 @@ extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const 
     if (int rc = reset_err_key(c, s)) return rc;
     if (int rc = canonical_dev(c, enc, forward_only, c->in.as<uint8_t>(), 1, n, w, c->out.as<uint8_t>(), s)) return rc;
     QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;
+    if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+    return QD_OK;
+}
+
+extern "C" int qd_canonical_window_keys(qd_ctx* c, int enc, int forward_only, int kind, const uint8_t* dna, size_t n, size_t w, void* keys,
+                                        qd_err* err) {
+    clear_err(err);
+    const size_t key_bytes = qd_canonical_key_bytes(kind, w);
+    if (!c || key_bytes == 0) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(c->mu);
+    QD_CUDA(c, cudaSetDevice(c->device));
+    if (n < w) return QD_OK;
+    cudaStream_t s = c->stream;
+    const size_t out_bytes = (n - w + 1) * key_bytes;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(out_bytes + 16));
+    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = reset_err_key(c, s)) return rc;
+    if (int rc = canonical_keys_dev(c, enc, forward_only, kind, c->in.as<uint8_t>(), 1, n, w, c->out.p, s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(keys, c->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;
     if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);

@@ -93,6 +93,21 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 
 // d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1   (.hi: b.byte2, b.byte3) -- 16-bit coefficients, 8-bit data
 __device__ __forceinline__ uint32_t dp2a_lo(uint32_t coef, uint32_t data, uint32_t acc) {
@@ -1010,10 +1025,17 @@ __device__ __forceinline__ bool first_nonzero(const uint32_t (&m)[NW], const uin
     return msel != 0;
 }
 
-// fw(x): relabel the packed window by first occurrence.  V[k] = 0x55555555 restricted to the window's positions.
+// The relabelling of one window as an affine map over GF(2)^2 applied to packed codes: y = ((x & P) ^ T) ^ ((x >> 1) & Q) ^ ((x << 1) & R)
+struct CanonMap {
+    uint32_t P, Q, R, T;
+};
+__device__ __forceinline__ uint32_t canon_apply(const CanonMap& m, uint32_t xk, uint32_t keep) {
+    return (((xk & m.P) ^ m.T) ^ ((xk >> 1) & m.Q) ^ ((xk << 1) & m.R)) & keep;
+}
+
+// The map of fw(x): relabel by first occurrence.  V[k] = 0x55555555 restricted to the window's positions.
 template <int NW>
-__device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW],
-                                                             bool* three_found = nullptr) {
+__device__ __forceinline__ CanonMap canon_find_map(const uint32_t (&x)[NW], const uint32_t (&V)[NW], bool* three_found) {
     const uint32_t c0 = x[0] & 3u;
     bool found3 = false;
     const uint32_t C0 = c0 * 0x55555555u;
@@ -1043,14 +1065,22 @@ __device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)
     if (three_found) *three_found = found3;  // three distinct bases seen: the map is final even if x is only a prefix
     // k = M^-1 (x ^ c0), M = [u v] as columns:  k0 = v1 z0 ^ v0 z1,  k1 = u1 z0 ^ u0 z1   (z = x ^ c0)
     const uint32_t v0 = v & 1u, v1 = v >> 1, u0 = u & 1u, u1 = u >> 1, c00 = c0 & 1u, c01 = c0 >> 1;
-    const uint32_t P = v1 * 0x55555555u | u0 * 0xaaaaaaaau;               // applied to x in place
-    const uint32_t Q = v0 * 0x55555555u;                                  // applied to x >> 1 (hi bit moved to the lo plane)
-    const uint32_t R = u1 * 0xaaaaaaaau;                                  // applied to x << 1 (lo bit moved to the hi plane)
-    const uint32_t T = ((v1 & c00) ^ (v0 & c01)) * 0x55555555u | ((u1 & c00) ^ (u0 & c01)) * 0xaaaaaaaau;
+    CanonMap m;
+    m.P = v1 * 0x55555555u | u0 * 0xaaaaaaaau;  // applied to x in place
+    m.Q = v0 * 0x55555555u;                      // applied to x >> 1 (hi bit moved to the lo plane)
+    m.R = u1 * 0xaaaaaaaau;                      // applied to x << 1 (lo bit moved to the hi plane)
+    m.T = ((v1 & c00) ^ (v0 & c01)) * 0x55555555u | ((u1 & c00) ^ (u0 & c01)) * 0xaaaaaaaau;
+    return m;
+}
+
+// fw(x) into y; returns the map itself applied to the codes 0,1,2,3 (0xe4): 2 bits per code
+template <int NW>
+__device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW],
+                                                             bool* three_found = nullptr) {
+    const CanonMap m = canon_find_map<NW>(x, V, three_found);
 #pragma unroll
-    for (int k = 0; k < NW; k++) y[k] = (((x[k] & P) ^ T) ^ ((x[k] >> 1) & Q) ^ ((x[k] << 1) & R)) & (V[k] * 3u);
-    // the map itself, applied to the codes 0,1,2,3 (0xe4): 2 bits per code
-    return (((0xe4u & P) ^ T) ^ ((0xe4u >> 1) & Q) ^ ((0xe4u << 1) & R)) & 0xffu;
+    for (int k = 0; k < NW; k++) y[k] = canon_apply(m, x[k], V[k] * 3u);
+    return canon_apply(m, 0xe4u, 0xffu);
 }
 
 // reverse the order of the w 2-bit groups of x (nucleotide j <-> w-1-j)
@@ -1315,6 +1345,360 @@ __global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const 
             uint8_t* gdst = p.out + g0 * w;
             for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + 16 * c, *reinterpret_cast<const uint4*>(S.stage + 16 * c));
             for (uint32_t b = 16 * body + lane; b < nbytes; b += 32) gdst[b] = S.stage[b];
+        }
+        __syncwarp();
+        s0 += step_s;
+        i0 += step_i;
+        if (i0 >= nw) { i0 -= nw; s0++; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Canonical window KEYS (a fixed-width key per canonical window for a downstream set lookup,
+// instead of 42 materialised bytes; the window arithmetic is src/canonical.rs:17-55, 71-118, 129-179 as above).
+//
+//   QD_CANON_KEY_PACKED  the canonical window itself, lossless, as two BIT PLANES: PW = ceil(w / 32) words holding the low
+//                        bit of each nucleotide's code (A, T, C, G = 0..3, the reference's order; nucleotide j at bit j % 32
+//                        of word j / 32), then PW words holding the high bits; unused bits zero
+//   QD_CANON_KEY_FP64    canon_fingerprint() of those words: 64 bits
+//
+// Bit planes make the relabelling two LOP3 per 32 nucleotides (new_lo = (lo & A) ^ (hi & B) ^ T0, new_hi likewise) and the
+// reversal one BREV per word.  What is left, finding the relabelling itself, is shared between windows: the order in
+// which the four codes first occur reading FORWARD from position j is the same for every window that starts at j, and
+// follows from the order at j + 1 by moving code[j] to the front; the order reading BACKWARD from j serves every window
+// that ends at j.  (Codes that do not occur inside a window may sit anywhere in the order: they are never relabelled.)
+// So after the decode a warp runs one pass over its tile's positions -- each lane takes 8 consecutive positions, starts
+// from the order found directly in the 32 positions past its chunk, and steps through a 25 x 4 move-to-front table --
+// leaving one byte per position and direction; a window then needs two byte loads and two table rows (its six
+// coefficient masks each) instead of two searches.  Windows whose chunk start was not decided within 32 positions
+// (low-complexity sequence) search their own w positions.
+// Nothing is staged on the way out: a lane's key lives in registers and lanes write consecutive keys.
+// ------------------------------------------------------------------------------------------------
+constexpr int CKEY_THREADS = 256;
+constexpr int CKEY_WARPS = CKEY_THREADS / 32;
+constexpr int CKEY_PACKED = 0, CKEY_FP64 = 1;
+constexpr uint32_t CKEY_PAIR_FLAG = 0x80;
+constexpr uint32_t CKEY_RANKS = 25;  // 0 = not known, 1..24 = the orders of {0, 1, 2, 3} in lexicographic order
+constexpr uint32_t CKEY_PAD = 32;    // positions of zero padding in front of the plane streams (backward look-behind)
+
+struct CanonKeyTables {
+    uint8_t rank_of[64];            // c0 | c1 << 2 | c2 << 4 (pairwise distinct) -> rank of the order (c0, c1, c2, the fourth); else 0
+    uint8_t mtf[128];               // rank * 4 + code -> rank of the order with `code` moved to the front (rank 0 stays 0)
+    uint32_t masks[CKEY_RANKS + 7][8];  // rank -> A, B, C, D, T0, T1 (0 or ~0), 0, 0
+};
+
+// CTA-wide shared memory: the tables, the letter-pair image, and the coefficient masks once more in a conflict-free layout
+constexpr uint32_t CKEY_SHARED_TABLE_BYTES = ((uint32_t)(sizeof(CanonKeyTables) + PAIR_ENTRIES + 15) & ~15u) + 2 * CKEY_RANKS * 128;
+
+// per-warp shared memory for a tile of at most `pos_cap` positions (a multiple of 32)
+struct CanonKeyLayout {
+    uint32_t plane_words, cw_bytes, state_bytes, total_bytes;
+    __host__ __device__ explicit CanonKeyLayout(uint32_t pos_cap) {
+        plane_words = (pos_cap + CKEY_PAD) / 32 + 4;
+        cw_bytes = (pos_cap / 4 + 15) & ~15u;  // 2 bits per position
+        state_bytes = pos_cap;
+        total_bytes = 2 * 4 * plane_words + cw_bytes + 2 * state_bytes;
+        total_bytes = (total_bytes + 15) & ~15u;
+    }
+};
+// positions a warp-tile of `wpt` windows can touch: its windows, w - 1 more per sequence it reaches into, alignment slack
+__host__ __device__ inline uint64_t ckey_span_bound(uint64_t wpt, uint64_t w, uint64_t nw) {
+    const uint64_t seqs = (wpt - 1 + nw - 1) / nw + 1;
+    return wpt + seqs * (w - 1) + 32;
+}
+
+__host__ __device__ __forceinline__ uint64_t canon_mix64(uint64_t z) {  // the splitmix64 finaliser: a bijection of 64 bits
+    z ^= z >> 30;
+    z *= 0xbf58476d1ce4e5b9ull;
+    z ^= z >> 27;
+    z *= 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return z;
+}
+// h = GOLDEN * w;  for k < PW:  h = mix64(h ^ (lo[k] | hi[k] << 32)).
+// Every step is a bijection of h for a fixed pair and of the pair for a fixed h, so windows of w <= 32 never collide.
+template <int PW>
+__host__ __device__ __forceinline__ uint64_t canon_fingerprint(const uint32_t (&lo)[PW], const uint32_t (&hi)[PW], uint32_t w) {
+    static_assert(PW == 1 || PW == 2, "at most 64 nucleotides");
+    uint64_t h = 0x9e3779b97f4a7c15ull * w;
+    h = canon_mix64(h ^ ((uint64_t)lo[0] | (uint64_t)hi[0] << 32));
+    if (PW > 1) h = canon_mix64(h ^ ((uint64_t)lo[PW - 1] | (uint64_t)hi[PW - 1] << 32));
+    return h;
+}
+
+// The order in which codes first occur in a window given as bit planes (V = the window's positions), as the index
+// c0 | c1 << 2 | c2 << 4 of CanonKeyTables::rank_of.  A window with fewer than three distinct codes gets some valid order
+// (the missing codes are never relabelled) unless STRICT3, which then returns 0xff.
+template <int PW, bool STRICT3>
+__device__ __forceinline__ uint32_t ckey_first_three(const uint32_t (&lo)[PW], const uint32_t (&hi)[PW], const uint32_t (&V)[PW]) {
+    const uint32_t c0 = (lo[0] & 1u) | ((hi[0] & 1u) << 1);
+    const uint32_t a0 = 0u - (lo[0] & 1u), b0 = 0u - (hi[0] & 1u);
+    uint32_t ne1[PW];
+#pragma unroll
+    for (int k = 0; k < PW; k++) ne1[k] = ((lo[k] ^ a0) | (hi[k] ^ b0)) & V[k];  // positions whose code differs from c0
+    uint32_t nsel = ne1[PW - 1], lsel = lo[PW - 1], hsel = hi[PW - 1];
+    if (PW > 1 && ne1[0]) nsel = ne1[0], lsel = lo[0], hsel = hi[0];
+    if (nsel == 0) return STRICT3 ? 0xffu : (c0 | ((c0 ^ 1u) << 2) | ((c0 ^ 2u) << 4));
+    uint32_t bit = nsel & (0u - nsel);
+    const uint32_t c1 = ((lsel & bit) ? 1u : 0u) | ((hsel & bit) ? 2u : 0u);
+    const uint32_t a1 = 0u - (c1 & 1u), b1 = 0u - (c1 >> 1);
+    uint32_t ne2[PW];
+#pragma unroll
+    for (int k = 0; k < PW; k++) ne2[k] = ne1[k] & ((lo[k] ^ a1) | (hi[k] ^ b1));  // ... and from c1
+    nsel = ne2[PW - 1], lsel = lo[PW - 1], hsel = hi[PW - 1];
+    if (PW > 1 && ne2[0]) nsel = ne2[0], lsel = lo[0], hsel = hi[0];
+    if (nsel == 0) {
+        if (STRICT3) return 0xffu;
+        const uint32_t u = c0 ^ c1;
+        return c0 | (c1 << 2) | ((c0 ^ (u == 1u ? 2u : 1u)) << 4);
+    }
+    bit = nsel & (0u - nsel);
+    const uint32_t c2 = ((lsel & bit) ? 1u : 0u) | ((hsel & bit) ? 2u : 0u);
+    return c0 | (c1 << 2) | (c2 << 4);
+}
+
+struct CanonKeyParams {
+    CanonParams base;               // out = the keys; pair = the ckey_pair image of the encoding
+    const CanonKeyTables* tables;
+    uint32_t wpt;                   // windows per warp-tile (a multiple of 32)
+    uint32_t pos_cap;               // positions a warp-tile can touch, rounded up to 32 (sizes the shared memory)
+};
+
+template <int PW, int W, int KIND>
+__global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const CanonKeyParams kp) {
+    static_assert(W == 0 || (W + 31) / 32 == PW, "PW must be the plane word count of W");
+    extern __shared__ __align__(16) unsigned char ckey_smem[];
+    const CanonParams& p = kp.base;
+    const uint32_t w = W ? (uint32_t)W : p.w;
+    const CanonKeyLayout lay(kp.pos_cap);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // CTA-wide tables, then one private region per warp
+    CanonKeyTables* const tabs = reinterpret_cast<CanonKeyTables*>(ckey_smem);
+    uint8_t* const pair_s = ckey_smem + sizeof(CanonKeyTables);  // PAIR_ENTRIES bytes
+    // the coefficient masks again, one 128-byte line per rank and part -- (A, B, C, D) and (T0, T1, T0 & V_last, T1 & V_last),
+    // V_last = the positions of the window's last plane word -- replicated so that every lane of a quarter-warp reads its
+    // own bank group whatever its rank: no conflicts
+    uint32_t* const quad_s = reinterpret_cast<uint32_t*>(ckey_smem + CKEY_SHARED_TABLE_BYTES - 2 * CKEY_RANKS * 128);
+    uint32_t* const duo_s = quad_s + CKEY_RANKS * 32;
+    unsigned char* const mine = ckey_smem + CKEY_SHARED_TABLE_BYTES + (size_t)warp * lay.total_bytes;
+    uint32_t* const LO = reinterpret_cast<uint32_t*>(mine);
+    uint32_t* const HI = LO + lay.plane_words;
+    uint16_t* const CW = reinterpret_cast<uint16_t*>(HI + lay.plane_words);  // codes interleaved, 8 positions per half-word
+    uint8_t* const stF = reinterpret_cast<uint8_t*>(CW) + lay.cw_bytes;      // order reading forward from each position
+    uint8_t* const stB = stF + lay.state_bytes;                              // order reading backward from each position
+    for (int i = tid; i < (int)(sizeof(CanonKeyTables) / 4); i += CKEY_THREADS)
+        reinterpret_cast<uint32_t*>(tabs)[i] = __ldg(reinterpret_cast<const uint32_t*>(kp.tables) + i);
+    for (int i = tid; i < (int)PAIR_ENTRIES; i += CKEY_THREADS) pair_s[i] = __ldg(p.pair + i);
+    {
+        const uint32_t left = w - 32u * (PW - 1), v_last = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+        for (int i = tid; i < (int)CKEY_RANKS * 32; i += CKEY_THREADS) {
+            quad_s[i] = __ldg(&kp.tables->masks[i >> 5][i & 3]);
+            duo_s[i] = __ldg(&kp.tables->masks[i >> 5][4 + (i & 1)]) & ((i & 2) ? v_last : 0xffffffffu);
+        }
+    }
+    __syncthreads();
+    const uint64_t nw = p.seq_len - w + 1;  // windows per sequence
+    const uint64_t total = p.n_seq * nw;    // windows in the batch
+    const uint32_t WPT = kp.wpt;
+    const uint64_t n_tiles = (total + WPT - 1) / WPT;
+    uint32_t V[PW];
+#pragma unroll
+    for (int k = 0; k < PW; k++) {
+        const int left = (int)w - 32 * k;
+        V[k] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+    }
+    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.n_seq * p.seq_len;
+    const uint32_t pair_base = smem_u32(pair_s);
+    const uint32_t mtf_base = smem_u32(tabs->mtf), rank_base = smem_u32(tabs->rank_of);
+    const uint32_t quad_base = smem_u32(quad_s) + (lane & 7) * 16, duo_base = smem_u32(duo_s) + (lane & 7) * 16;
+    const uint32_t lo_base = smem_u32(LO), hi_delta = 4u * lay.plane_words, stF_base = smem_u32(stF), stB_base = smem_u32(stB) + w - 1u;
+    const bool long_seqs = nw >= WPT;  // a tile reaches into at most two sequences
+    const uint32_t V32[1] = {0xffffffffu};
+    const uint64_t warps_total = (uint64_t)gridDim.x * CKEY_WARPS;
+    uint64_t tile = (uint64_t)blockIdx.x * CKEY_WARPS + warp;
+    uint64_t s0 = (tile * WPT) / nw, i0 = (tile * WPT) % nw;
+    const uint64_t step_s = (warps_total * WPT) / nw, step_i = (warps_total * WPT) % nw;
+    for (; tile < n_tiles; tile += warps_total) {
+        const uint64_t g0 = tile * WPT;
+        const uint32_t cnt = (uint32_t)min((uint64_t)WPT, total - g0);
+        uint64_t sl = s0, il = i0 + (cnt - 1);  // the tile's last window
+        if (il >= nw) {
+            if (nw >= WPT) { il -= nw; sl++; }
+            else { sl += il / nw; il %= nw; }
+        }
+        const uint64_t flat_lo = s0 * p.seq_len + i0, flat_hi = sl * p.seq_len + il + w;
+        const uintptr_t a0 = (dna_lo + flat_lo) & ~(uintptr_t)15;
+        const uint32_t n_chunk = (uint32_t)((dna_lo + flat_hi - a0 + 7) >> 3);  // 8 positions each
+        const uint32_t o_first = (uint32_t)(dna_lo + flat_lo - a0);             // position of the tile's first window
+        const uint32_t l_seam = (uint32_t)min((uint64_t)WPT, nw - i0);          // the first window of the next sequence
+        // ---- decode: item = 8 nucleotides -> one byte per plane, one half-word of interleaved codes -------------
+        if (lane < 4) {
+            reinterpret_cast<uint8_t*>(LO)[lane] = 0;  // the padding in front
+            reinterpret_cast<uint8_t*>(HI)[lane] = 0;
+        }
+        for (uint32_t item = lane; item < n_chunk + 12; item += 32) {
+            uint32_t plane_lo = 0, plane_hi = 0, cw = 0;
+            if (item < n_chunk) {
+                const uintptr_t a = a0 + 8 * (uintptr_t)item;
+                uint32_t x0, x1;
+                if (a >= dna_lo && a + 8 <= dna_hi) {
+                    // bytes outside the tile's span are some other tile's: validated there too
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(a));
+                    x0 = v.x;
+                    x1 = v.y;
+                } else {  // the chunks straddling the ends of the whole buffer: bytes outside it read as a valid filler
+                    x0 = x1 = 0;
+#pragma unroll 1
+                    for (int t = 0; t < 8; t++) {
+                        const uintptr_t b = a + t;
+                        const uint32_t v = (b >= dna_lo && b < dna_hi) ? (uint32_t)*reinterpret_cast<const uint8_t*>(b) : (p.filler & 0xffu);
+                        if (t < 4) x0 |= v << (8 * t);
+                        else x1 |= v << (8 * (t - 4));
+                    }
+                }
+                const uint32_t m0 = x0 & 0x1f1f1f1fu, m1 = x1 & 0x1f1f1f1fu;
+                uint32_t e0 = lds_u8(dp2a_lo(p.pair_coef, m0, pair_base)), e1 = lds_u8(dp2a_hi(p.pair_coef, m0, pair_base));
+                uint32_t e2 = lds_u8(dp2a_lo(p.pair_coef, m1, pair_base)), e3 = lds_u8(dp2a_hi(p.pair_coef, m1, pair_base));
+                if (((e0 | e1 | e2 | e3) & CKEY_PAIR_FLAG) | (((x0 & x1) & p.and_need) ^ p.and_need) | ((x0 | x1) & p.or_forbid)) {
+#pragma unroll 1
+                    for (int t = 0; t < 8; t++) {  // exact: first byte of this chunk that is not a concrete base
+                        const uintptr_t b = a + t;
+                        if (b >= dna_lo && b < dna_hi && __ldg(p.decode + *reinterpret_cast<const uint8_t*>(b)) > 3u) {
+                            atomicMin(p.err_key, (unsigned long long)(b - dna_lo));
+                            break;
+                        }
+                    }
+                    e0 &= 0xfu, e1 &= 0xfu, e2 &= 0xfu, e3 &= 0xfu;
+                }
+                cw = e0 | (e1 << 4) | (e2 << 8) | (e3 << 12);  // code of position t at bits 2t
+                // even bits -> low plane byte, odd bits -> high plane byte (both halves of one word at once)
+                uint32_t z = (cw & 0x5555u) | (((cw >> 1) & 0x5555u) << 16);
+                z = (z | (z >> 1)) & 0x33333333u;
+                z = (z | (z >> 2)) & 0x0f0f0f0fu;
+                z = (z | (z >> 4)) & 0x00ff00ffu;
+                plane_lo = z & 0xffu;
+                plane_hi = z >> 16;
+            }
+            // items past the tile's end: zeros (the look-ahead of the last chunks reads them)
+            reinterpret_cast<uint8_t*>(LO)[CKEY_PAD / 8 + item] = (uint8_t)plane_lo;
+            reinterpret_cast<uint8_t*>(HI)[CKEY_PAD / 8 + item] = (uint8_t)plane_hi;
+            if (item < n_chunk) CW[item] = (uint16_t)cw;
+        }
+        __syncwarp();
+        // ---- orders: lane takes chunk ch; positions 8 ch .. 8 ch + 7 --------------------------------------------
+        for (uint32_t ch = lane; ch < n_chunk; ch += 32) {
+            const uint32_t cw = CW[ch];
+            {   // forward orders, from the back of the chunk to its front; start: the order found in positions 8 ch + 8 .. + 39
+                const uint32_t q = CKEY_PAD + 8 * ch + 8, wi = q >> 5, sh = q & 31u;
+                const uint32_t l[1] = {__funnelshift_r(LO[wi], LO[wi + 1], sh)}, h[1] = {__funnelshift_r(HI[wi], HI[wi + 1], sh)};
+                const uint32_t idx = ckey_first_three<1, true>(l, h, V32);
+                uint32_t r = idx == 0xffu ? 0u : lds_u8(rank_base + idx);
+                uint32_t pk0 = 0, pk1 = 0;
+#pragma unroll
+                for (int t = 7; t >= 0; t--) {
+                    r = lds_u8(mtf_base + r * 4u + ((cw >> (2 * t)) & 3u));
+                    if (t >= 4) pk1 |= r << (8 * (t - 4));
+                    else pk0 |= r << (8 * t);
+                }
+                *reinterpret_cast<uint2*>(stF + 8 * ch) = make_uint2(pk0, pk1);
+            }
+            {   // backward orders, front to back; start: the order found reading back from position 8 ch - 1
+                const uint32_t q = CKEY_PAD + 8 * ch - 32, wi = q >> 5, sh = q & 31u;
+                const uint32_t l[1] = {__brev(__funnelshift_r(LO[wi], LO[wi + 1], sh))}, h[1] = {__brev(__funnelshift_r(HI[wi], HI[wi + 1], sh))};
+                const uint32_t idx = ckey_first_three<1, true>(l, h, V32);
+                uint32_t r = idx == 0xffu ? 0u : lds_u8(rank_base + idx);
+                uint32_t pk0 = 0, pk1 = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    r = lds_u8(mtf_base + r * 4u + ((cw >> (2 * t)) & 3u));
+                    if (t >= 4) pk1 |= r << (8 * (t - 4));
+                    else pk0 |= r << (8 * t);
+                }
+                *reinterpret_cast<uint2*>(stB + 8 * ch) = make_uint2(pk0, pk1);
+            }
+        }
+        __syncwarp();
+        // ---- my windows: lane handles windows lane, lane + 32, ...: consecutive lanes write consecutive keys ----
+#pragma unroll 1
+        for (uint32_t l = lane; l < cnt; l += 32) {
+            uint32_t o;  // position inside the streams: every sequence seam before the window skips w - 1 positions
+            if (long_seqs) o = o_first + l + (l >= l_seam ? w - 1u : 0u);
+            else o = o_first + l + (((uint32_t)i0 + l) / (uint32_t)nw) * (w - 1u);  // nw < WPT here: 32-bit division
+            uint32_t rF = lds_u8(stF_base + o), rB = lds_u8(stB_base + o);
+            uint32_t xl[PW], xh[PW], rl[PW], rh[PW];
+            {
+                const uint32_t q = CKEY_PAD + o, wa = lo_base + ((q >> 5) << 2), sh = q & 31u;
+                uint32_t tl[PW + 1], th[PW + 1];
+#pragma unroll
+                for (int k = 0; k <= PW; k++) {
+                    tl[k] = lds_u32(wa + 4 * k);
+                    th[k] = lds_u32(wa + hi_delta + 4 * k);
+                }
+#pragma unroll
+                for (int k = 0; k < PW; k++) {
+                    xl[k] = __funnelshift_r(tl[k], tl[k + 1], sh) & V[k];
+                    xh[k] = __funnelshift_r(th[k], th[k + 1], sh) & V[k];
+                }
+            }
+            // the reversed window: position j <-> w - 1 - j
+            if constexpr (PW == 1) {
+                rl[0] = __brev(xl[0]) >> (32u - w);
+                rh[0] = __brev(xh[0]) >> (32u - w);
+            } else {
+                const uint32_t sh = 64u - w;  // < 32: PW is the smallest that fits w
+                const uint32_t bl0 = __brev(xl[PW - 1]), bl1 = __brev(xl[0]), bh0 = __brev(xh[PW - 1]), bh1 = __brev(xh[0]);
+                rl[0] = __funnelshift_r(bl0, bl1, sh);
+                rl[PW - 1] = bl1 >> sh;
+                rh[0] = __funnelshift_r(bh0, bh1, sh);
+                rh[PW - 1] = bh1 >> sh;
+            }
+            if (p.forward_only) rB = rF;
+            if (__any_sync(__activemask(), (rF == 0u) | (rB == 0u))) {  // rare: the whole warp takes the detour together
+                if (rF == 0) rF = lds_u8(rank_base + ckey_first_three<PW, false>(xl, xh, V));
+                if (rB == 0) rB = lds_u8(rank_base + ckey_first_three<PW, false>(rl, rh, V));
+            }
+            const uint4 mf0 = lds_u128(quad_base + rF * 128u);
+            const uint4 mf1 = lds_u128(duo_base + rF * 128u);  // T0, T1, and both restricted to the last word's positions
+            uint32_t yl[PW], yh[PW];
+#pragma unroll
+            for (int k = 0; k < PW; k++) {
+                yl[k] = (xl[k] & mf0.x) ^ (xh[k] & mf0.y) ^ (k == PW - 1 ? mf1.z : mf1.x);
+                yh[k] = (xl[k] & mf0.z) ^ (xh[k] & mf0.w) ^ (k == PW - 1 ? mf1.w : mf1.y);
+            }
+            if (!p.forward_only) {
+                const uint4 mr0 = lds_u128(quad_base + rB * 128u);
+                const uint4 mr1 = lds_u128(duo_base + rB * 128u);
+                uint32_t zl[PW], zh[PW], lose[PW];
+#pragma unroll
+                for (int k = 0; k < PW; k++) {
+                    zl[k] = (rl[k] & mr0.x) ^ (rh[k] & mr0.y) ^ (k == PW - 1 ? mr1.z : mr1.x);
+                    zh[k] = (rl[k] & mr0.z) ^ (rh[k] & mr0.w) ^ (k == PW - 1 ? mr1.w : mr1.y);
+                    // lexical order: the first differing position decides; there the smaller code wins, hi bit first.
+                    // lose = positions that differ AND where the reversed window holds the larger code
+                    const uint32_t d = (yl[k] ^ zl[k]) | (yh[k] ^ zh[k]);
+                    const uint32_t hd = yh[k] ^ zh[k];
+                    lose[k] = (d & (0u - d)) & ((hd & zh[k]) | (~hd & ~yl[k]));  // first differing position of this word, if lost there
+                }
+                bool use_rev;
+                if (PW == 1) {
+                    use_rev = lose[0] == 0;  // (equal windows: either)
+                } else {
+                    const uint32_t d0 = (yl[0] ^ zl[0]) | (yh[0] ^ zh[0]);
+                    use_rev = (d0 ? lose[0] : lose[PW - 1]) == 0;
+                }
+                if (use_rev) {
+#pragma unroll
+                    for (int k = 0; k < PW; k++) yl[k] = zl[k], yh[k] = zh[k];
+                }
+            }
+            const uint64_t g = g0 + l;
+            if (KIND == CKEY_FP64) {
+                reinterpret_cast<uint64_t*>(p.out)[g] = canon_fingerprint<PW>(yl, yh, w);
+            } else if (PW == 1) {
+                reinterpret_cast<uint2*>(p.out)[g] = make_uint2(yl[0], yh[0]);
+            } else {
+                reinterpret_cast<uint4*>(p.out)[g] = make_uint4(yl[0], yl[PW - 1], yh[0], yh[PW - 1]);
+            }
         }
         __syncwarp();
         s0 += step_s;

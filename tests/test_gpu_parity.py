@@ -516,6 +516,107 @@ def test_canonical_windows_random(B):
     assert (ei.value.kind, ei.value.pos, ei.value.byte) == (3, 4, ord("N"))
 
 
+def _pack_windows(win_masks: np.ndarray) -> np.ndarray:
+    """[count, w] masks {1, 2, 4, 8} -> [count, 2 * ceil(w / 32)] uint32: the QD_CANON_KEY_PACKED layout restated with numpy --
+    the low bits of the codes (A, T, C, G = 0..3; nucleotide j at bit j % 32 of word j / 32), then the high bits."""
+    count, w = win_masks.shape
+    code = np.zeros(16, np.uint64)
+    code[[1, 2, 4, 8]] = [0, 1, 2, 3]
+    pw = (w + 31) // 32
+    c = np.zeros((count, pw * 32), np.uint64)
+    c[:, :w] = code[win_masks]
+    shifts = np.arange(32, dtype=np.uint64)[None, None, :]
+    lo = ((c & np.uint64(1)).reshape(count, pw, 32) << shifts).sum(axis=2, dtype=np.uint64)
+    hi = ((c >> np.uint64(1)).reshape(count, pw, 32) << shifts).sum(axis=2, dtype=np.uint64)
+    return np.concatenate([lo, hi], axis=1).astype(np.uint32)
+
+
+def _fingerprint(packed: np.ndarray, w: int) -> np.ndarray:
+    """The QD_CANON_KEY_FP64 definition of include/quickdna_b200.h restated with numpy uint64 arithmetic."""
+    def mix(z):
+        z = z ^ (z >> np.uint64(30))
+        z = z * np.uint64(0xbf58476d1ce4e5b9)
+        z = z ^ (z >> np.uint64(27))
+        z = z * np.uint64(0x94d049bb133111eb)
+        return z ^ (z >> np.uint64(31))
+
+    count, words = packed.shape
+    pw = words // 2
+    p = packed.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = np.full(count, (0x9e3779b97f4a7c15 * w) & (2**64 - 1), dtype=np.uint64)
+        for k in range(pw):
+            h = mix(h ^ (p[:, k] | (p[:, pw + k] << np.uint64(32))))
+    return h
+
+
+def _want_windows(m: np.ndarray, w: int, fwd_only: bool) -> np.ndarray:
+    if not fwd_only:
+        return oracle.canonical_windows(m, w)
+    n = len(m)
+    return np.stack([oracle.forward_canonical(m[i:i + w]) for i in range(n - w + 1)]) if n >= w else np.empty((0, w), np.uint8)
+
+
+def test_canonical_window_keys_single_sequence(B, N):
+    """packed keys ARE the oracle's canonical windows at 2 bits per nucleotide; the fingerprint is
+    the documented function of them.  Low-complexity alphabets force the full-width decision path."""
+    rng = np.random.default_rng(77)
+    cases = [(3000, 42, b"ACGTacgt"), (700, 42, b"A"), (900, 42, b"AC"), (900, 42, b"ACG"), (500, 1, b"ACGT"), (500, 7, b"ACGT"),
+             (800, 16, b"ACGT"), (800, 17, b"GT"), (1000, 32, b"ACGT"), (1000, 33, b"ACGT"), (1200, 48, b"AACC"), (1500, 64, b"ACGT"),
+             (41, 42, b"ACGT"), (42, 42, b"ACGT"), (64, 64, b"TG"), (300, 20, b"ACGT")]
+    for n, w, alphabet in cases:
+        dna = _rand(rng, n, alphabet)
+        if alphabet == b"AACC":  # long runs, then a palindrome under relabelling
+            dna = dna[: n // 2] + dna[: n - n // 2][::-1]
+        m = oracle.masks_of(dna)
+        for fwd_only in (False, True):
+            want = _pack_windows(_want_windows(m, w, fwd_only))
+            got = B.canonical_window_keys(dna, w=w, kind=N.CANON_KEY_PACKED, forward_only=fwd_only)
+            assert got.shape == want.shape and (got == want).all(), (n, w, alphabet, fwd_only)
+            fp = B.canonical_window_keys(dna, w=w, kind=N.CANON_KEY_FP64, forward_only=fwd_only)
+            assert fp.dtype == np.uint64 and (fp == _fingerprint(want, w)).all(), (n, w, alphabet, fwd_only)
+        gm = B.canonical_window_keys(m, w=w, kind=N.CANON_KEY_PACKED, enc=1)
+        assert (gm == _pack_windows(oracle.canonical_windows(m, w))).all()
+    # the reference's own vectors (src/canonical.rs:200-214, 406-412; src/rust_api.rs:365-367) through the packed key
+    for dna, canon in V.CANONICAL[:-1]:
+        got = B.canonical_window_keys(dna.encode(), w=len(dna), kind=N.CANON_KEY_PACKED)
+        assert (got == _pack_windows(oracle.masks_of(canon.encode())[None, :])).all(), dna
+    with pytest.raises(ValueError) as ei:
+        B.canonical_window_keys(b"ACGTNACGT", w=4)
+    assert (ei.value.kind, ei.value.pos, ei.value.byte) == (3, 4, ord("N"))
+    with pytest.raises(ValueError):
+        B.canonical_window_keys(b"ACGT" * 40, w=65)
+
+
+def test_canonical_window_keys_batch(B, N):
+    """Batched device form: 256-window warp tiles cross sequence seams; keys equal the materialised canonical windows."""
+    import torch
+
+    rng = np.random.default_rng(78)
+    for n_seq, seq_len, w in ((1, 5000, 42), (7, 1000, 42), (300, 50, 42), (500, 42, 42), (64, 43, 42), (33, 99, 17), (10, 700, 64),
+                              (20, 333, 33), (5, 2000, 1), (3, 100, 16), (9, 257, 48), (2, 99999, 42), (1000, 297, 42), (4, 298, 42)):
+        a = np.frombuffer(_rand(rng, n_seq * seq_len, b"ACGTacgt"), dtype=np.uint8).reshape(n_seq, seq_len)
+        x = torch.from_numpy(a.copy()).cuda()
+        B.dev_error_reset()
+        packed = B.canonical_window_keys_dev(x, n_seq, seq_len, w, kind=N.CANON_KEY_PACKED).cpu().numpy().view(np.uint32)
+        fp = B.canonical_window_keys_dev(x, n_seq, seq_len, w, kind=N.CANON_KEY_FP64).cpu().numpy().view(np.uint64)
+        rows = B.canonical_windows_batch_dev(x, n_seq, seq_len, w).cpu().numpy()
+        assert B.dev_error_fetch(x, uniform_len=seq_len, strict=True) is None
+        nw = seq_len - w + 1
+        want = _pack_windows(oracle.masks_of(rows.reshape(-1)).reshape(n_seq * nw, w))  # rows are oracle-checked in test_canonical_windows_batch
+        assert packed.shape == want.shape and (packed == want).all(), (n_seq, seq_len, w)
+        assert (fp == _fingerprint(want, w)).all(), (n_seq, seq_len, w)
+        for s in range(0, n_seq, max(1, n_seq // 5)):  # and directly against the oracle on a few sequences
+            assert (packed[s * nw:(s + 1) * nw] == _pack_windows(oracle.canonical_windows(oracle.masks_of(a[s]), w))).all()
+    a = np.frombuffer(_rand(rng, 40 * 500, b"ACGT"), dtype=np.uint8).reshape(40, 500).copy()
+    a[17, 321] = ord("N")
+    x = torch.from_numpy(a).cuda()
+    B.dev_error_reset()
+    B.canonical_window_keys_dev(x, 40, 500, 42)
+    err = B.dev_error_fetch(x, uniform_len=500, strict=True)
+    assert err is not None and (err.seq_index, err.pos, err.kind, err.byte) == (17, 321, 3, ord("N"))
+
+
 @pytest.mark.parametrize("dna,exp", V.EXPANSIONS)
 def test_expansion_vectors(B, dna, exp):
     a = np.frombuffer(dna.encode(), dtype=np.uint8).reshape(1, -1)

@@ -144,3 +144,40 @@ def test_synthetic_generators_agree():
     x = synth_iupac_np(5, 0, 200_000)
     amb = np.isin(x, np.frombuffer(b"WMRYSKBVDHNwmryskbvdhn", dtype=np.uint8)).mean()
     assert 0.04 < amb < 0.06 and 0.45 < (x >= 97).mean() < 0.55
+
+
+def test_canonical_key_host_helpers():
+    """qd_canonical_key_bytes / qd_canonical_fingerprint are host-only: sizes, and the documented fingerprint function."""
+    import ctypes as C
+
+    import numpy as np
+
+    from quickdna_b200 import _native as N
+
+    L = N.lib()
+    assert [L.qd_canonical_key_bytes(N.CANON_KEY_PACKED, w) for w in (1, 16, 32, 33, 42, 64)] == [8, 8, 8, 16, 16, 16]
+    assert L.qd_canonical_key_bytes(N.CANON_KEY_FP64, 42) == 8
+    assert L.qd_canonical_key_bytes(N.CANON_KEY_PACKED, 0) == 0 and L.qd_canonical_key_bytes(N.CANON_KEY_PACKED, 65) == 0
+    assert L.qd_canonical_key_bytes(7, 42) == 0
+
+    def mix(z):
+        z ^= z >> 30
+        z = (z * 0xbf58476d1ce4e5b9) & (2**64 - 1)
+        z ^= z >> 27
+        z = (z * 0x94d049bb133111eb) & (2**64 - 1)
+        return z ^ (z >> 31)
+
+    rng = np.random.default_rng(5)
+    seen = set()
+    for w in (1, 5, 16, 17, 32, 33, 42, 64):
+        pw = (w + 31) // 32
+        for _ in range(50):
+            y = rng.integers(0, 2**32, 2 * pw, dtype=np.uint64)  # lo words, then hi words
+            h = (0x9e3779b97f4a7c15 * w) & (2**64 - 1)
+            for k in range(pw):
+                h = mix(h ^ (int(y[k]) | int(y[pw + k]) << 32))
+            arr = y.astype(np.uint32)
+            got = L.qd_canonical_fingerprint(arr.ctypes.data_as(C.c_void_p), w)
+            assert got == h, (w, y)
+            seen.add(got)
+    assert len(seen) == 8 * 50
