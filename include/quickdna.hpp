@@ -267,6 +267,21 @@ class DnaSequence {
         return DnaSequence(std::move(out));
     }
 
+    // Not in the reference: one fixed-width key per canonical length-`w` window, in window order --
+    // what a set lookup downstream of `windows(w)` + `canonical()` needs, without materialising the windows.
+    // kind = QD_CANON_KEY_FP64: one uint64 per window; QD_CANON_KEY_PACKED: qd_canonical_key_bytes(kind, w) / 8 uint64 per window.
+    template <class U = T, class = std::enable_if_t<std::is_same_v<U, Nucleotide>>>
+    std::vector<uint64_t> canonical_window_keys(size_t w, int kind = QD_CANON_KEY_FP64) const {
+        const size_t kb = qd_canonical_key_bytes(kind, w);
+        if (kb == 0) throw std::invalid_argument("quickdna: bad key kind or window length");
+        std::vector<uint64_t> keys(dna_.size() >= w ? (dna_.size() - w + 1) * (kb / 8) : 0);
+        qd_err e{};
+        Context& c = Context::current();
+        uint64_t none = 0;
+        c.check(qd_canonical_window_keys(c.get(), QD_ENC_MASK, 0, kind, bytes(), dna_.size(), w, keys.empty() ? &none : keys.data(), &e), e);
+        return keys;
+    }
+
     // :385-387 (DnaSequence<NucleotideAmbiguous> only): every concrete expansion, lexicographic, materialised.
     // size_hint() of the reference is `expansion_count()`; UINT64_MAX == (usize::MAX, None).
     template <class U = T, class = std::enable_if_t<std::is_same_v<U, NucleotideAmbiguous>>>

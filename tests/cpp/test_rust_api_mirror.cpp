@@ -120,6 +120,29 @@ int main() {
     CHECK(dna_strict("TGTT").canonical() == dna_strict("AATA"));
     CHECK(dna_strict("ATCGCCAT").canonical() == dna_strict("ATCCGCAT"));
     CHECK(dna_strict("").canonical() == dna_strict(""));
+    // canonical window keys (not in the reference: SURVEY 8(f) rank 3) agree with windows(w) + canonical()
+    {
+        const auto x = dna_strict("TGCGAGTGTAGCGAGATGTAGCGTAGAGTCTGAGATGCAGTACATTAGCATTAG");
+        for (size_t w : {size_t(6), size_t(33), size_t(42)}) {
+            const auto wins = x.windows(w);
+            const auto fp = x.canonical_window_keys(w);
+            const auto packed = x.canonical_window_keys(w, QD_CANON_KEY_PACKED);
+            const size_t pw = (w + 31) / 32;
+            CHECK(fp.size() == wins.size() && packed.size() == wins.size() * pw);
+            for (size_t i = 0; i < wins.size() && i < fp.size(); i++) {
+                const auto c = wins[i].canonical();
+                uint32_t words[4] = {0, 0, 0, 0};  // lo plane words, then hi plane words
+                for (size_t j = 0; j < w; j++) {
+                    const unsigned code = c[j] == Nucleotide::A ? 0 : c[j] == Nucleotide::T ? 1 : c[j] == Nucleotide::C ? 2 : 3;
+                    words[j / 32] |= (code & 1u) << (j % 32);
+                    words[pw + j / 32] |= (code >> 1) << (j % 32);
+                }
+                CHECK(fp[i] == qd_canonical_fingerprint(words, w));
+                CHECK(std::memcmp(&packed[i * pw], words, 8 * pw) == 0);
+            }
+        }
+        CHECK(dna_strict("ACG").canonical_window_keys(42).empty());
+    }
     {
         const DnaSequenceStrict x = dna_strict("GATTACAGATTACACATTAGGATCCAGTTTACGATCAGGACT"), rc = x.reverse_complement();
         CHECK(x.canonical() == rc.reverse_complement().canonical());
