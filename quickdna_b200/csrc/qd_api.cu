@@ -75,7 +75,6 @@ struct qd_ctx {
     uint8_t* d_tables = nullptr;  // 256-byte tables, see TAB_* offsets
     uint16_t* d_pair = nullptr;   // [encoding][strict][PAIR_ENTRIES]
     uint16_t* d_rc_pair = nullptr;  // [RC_PAIR_COUNT][PAIR_ENTRIES]
-    uint8_t* d_canon_pair = nullptr;  // [encoding][PAIR_ENTRIES]
     uint8_t* d_ckey_pair = nullptr;   // [encoding][PAIR_ENTRIES]
     CanonKeyTables* d_ckey = nullptr;
     uint16_t* d_parse_pair = nullptr;  // [strict][PAIR_ENTRIES]
@@ -448,7 +447,6 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_tables, 256 * TAB_COUNT) == cudaSuccess;
     ok &= cudaMalloc(&c->d_pair, sizeof(T.pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_rc_pair, sizeof(T.rc_pair)) == cudaSuccess;
-    ok &= cudaMalloc(&c->d_canon_pair, sizeof(T.canon_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_ckey_pair, sizeof(T.ckey_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_ckey, sizeof(T.ckey)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_parse_pair, sizeof(T.parse_pair)) == cudaSuccess;
@@ -479,7 +477,6 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
         ok &= cudaMemcpy(c->d_lut, T.folded.data(), T.folded.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_pair, T.pair, sizeof(T.pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_rc_pair, T.rc_pair, sizeof(T.rc_pair), cudaMemcpyHostToDevice) == cudaSuccess;
-        ok &= cudaMemcpy(c->d_canon_pair, T.canon_pair, sizeof(T.canon_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_ckey_pair, T.ckey_pair, sizeof(T.ckey_pair), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_ckey, &T.ckey, sizeof(T.ckey), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(c->d_parse_pair, T.parse_pair, sizeof(T.parse_pair), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -508,7 +505,6 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->d_pair) cudaFree(c->d_pair);
     if (c->d_rc_pair) cudaFree(c->d_rc_pair);
-    if (c->d_canon_pair) cudaFree(c->d_canon_pair);
     if (c->d_ckey_pair) cudaFree(c->d_ckey_pair);
     if (c->d_ckey) cudaFree(c->d_ckey);
     if (c->d_parse_pair) cudaFree(c->d_parse_pair);
@@ -690,21 +686,6 @@ extern "C" int qd_translate_frames_batch_dev(qd_ctx* c, int table, int enc, int 
                           c->block_sums, out_dev, pick_stream(c, stream));
 }
 
-template <int NW, int W = 0>
-static int launch_canonical_windows(qd_ctx* c, const CanonParams& p, cudaStream_t s) {
-    auto kern = canonical_windows_kernel<NW, W>;
-    const size_t smem = (size_t)CanonWarpLayout(p.w).total_bytes * CANON_WARPS + PAIR_ENTRIES;
-    QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CANON_THREADS, smem));
-    const uint64_t tiles = (p.n_seq * (p.seq_len - p.w + 1) + CANON_WPT * CANON_WARPS - 1) / (CANON_WPT * CANON_WARPS);
-    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * std::max(1, occ));
-    kern<<<grid, CANON_THREADS, smem, s>>>(p);
-    c->launches++;
-    QD_CUDA(c, cudaGetLastError());
-    return QD_OK;
-}
-
 static CanonParams canonical_params(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
                                     uint8_t* out_dev) {
     CanonParams p{};
@@ -716,7 +697,6 @@ static CanonParams canonical_params(qd_ctx* c, int enc, int forward_only, const 
     p.out = out_dev;
     const bool ascii = enc == QD_ENC_ASCII;
     p.decode = tab(c, ascii ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
-    p.pair = c->d_canon_pair + (ascii ? 0 : PAIR_ENTRIES);
     p.pair_coef = 1u | ((ascii ? PAIR_K1_ASCII : PAIR_K1_MASK) << 16);
     p.and_need = ascii ? 0x40404040u : 0u;
     p.or_forbid = ascii ? 0x80808080u : 0xe0e0e0e0u;
@@ -726,48 +706,58 @@ static CanonParams canonical_params(qd_ctx* c, int enc, int forward_only, const 
     return p;
 }
 
-// every length-w window of each of n_seq sequences of seq_len nucleotides (n_seq = 1: one sequence)
-static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
-                         uint8_t* out_dev, cudaStream_t s) {
-    if (w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
-    if (seq_len < w || n_seq == 0) return QD_OK;
-    const CanonParams p = canonical_params(c, enc, forward_only, dna_dev, n_seq, seq_len, w, out_dev);
-    if (w == 42) return launch_canonical_windows<3, 42>(c, p, s);  // the window length of benches/canonical.rs: unrolled
-    switch ((2 * w + 31) / 32) {
-        case 1: return launch_canonical_windows<1>(c, p, s);
-        case 2: return launch_canonical_windows<2>(c, p, s);
-        case 3: return launch_canonical_windows<3>(c, p, s);
-        default: return launch_canonical_windows<4>(c, p, s);
-    }
-}
-
-template <int PW, int W, int KIND>
-static int launch_canonical_keys(qd_ctx* c, CanonKeyParams kp, cudaStream_t s) {
-    auto kern = canonical_keys_kernel<PW, W, KIND>;
+// One launch of the tile kernel: rows (MODE = CTILE_ROWS) or keys.  The warp-tile is the largest multiple of 64 windows
+// whose positions (and, for rows, staged bytes) fit the per-warp shared-memory budget.
+template <int NW, int W, int MODE>
+static int launch_canonical_tiles(qd_ctx* c, CanonKeyParams kp, cudaStream_t s) {
+    auto kern = canonical_tile_kernel<NW, W, MODE>;
     const CanonParams& p = kp.base;
+    const bool rows = MODE == CTILE_ROWS;
     const uint64_t nw = p.seq_len - p.w + 1;
-    // the largest warp-tile (a multiple of 32 windows) whose positions fit the per-warp budget; 448 + 41 + slack = 16 x 32
-    // positions for w = 42 is two rounds of the per-position pass
-    uint32_t wpt = 448;
-    while (wpt > 32 && ckey_span_bound(wpt, p.w, nw) > 2048) wpt -= 32;
+    // keys: 448 + 41 + slack = 16 x 32 positions for w = 42 is two rounds of the per-position pass;
+    // rows: 192 + 41 + slack = 8 x 32 is one round (rows are staged and copied out 64 at a time)
+    uint32_t wpt = rows ? 192 : 448;
+    while (wpt > 64 && ckey_span_bound(wpt, p.w, nw) > 2048) wpt -= 64;
     kp.wpt = wpt;
     kp.pos_cap = (uint32_t)((ckey_span_bound(wpt, p.w, nw) + 31) & ~(uint64_t)31);
-    const size_t smem = CKEY_SHARED_TABLE_BYTES + (size_t)CanonKeyLayout(kp.pos_cap).total_bytes * CKEY_WARPS;
+    const size_t smem = CKEY_SHARED_TABLE_BYTES + (size_t)CanonTileLayout(kp.pos_cap, wpt, p.w, rows).total_bytes * CTILE_WARPS;
     QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CKEY_THREADS, smem));
-    const uint64_t tiles = (p.n_seq * nw + (uint64_t)wpt * CKEY_WARPS - 1) / ((uint64_t)wpt * CKEY_WARPS);
+    QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTILE_THREADS, smem));
+    const uint64_t tiles = (p.n_seq * nw + (uint64_t)wpt * CTILE_WARPS - 1) / ((uint64_t)wpt * CTILE_WARPS);
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * std::max(1, occ));
-    kern<<<grid, CKEY_THREADS, smem, s>>>(kp);
+    kern<<<grid, CTILE_THREADS, smem, s>>>(kp);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
 }
 
-template <int KIND>
-static int canonical_keys_kind(qd_ctx* c, const CanonKeyParams& kp, cudaStream_t s) {
-    if (kp.base.w == 42) return launch_canonical_keys<2, 42, KIND>(c, kp, s);
-    return kp.base.w <= 32 ? launch_canonical_keys<1, 0, KIND>(c, kp, s) : launch_canonical_keys<2, 0, KIND>(c, kp, s);
+template <int MODE>
+static int canonical_tiles_mode(qd_ctx* c, const CanonKeyParams& kp, cudaStream_t s) {
+    if (kp.base.w == 42) return launch_canonical_tiles<3, 42, MODE>(c, kp, s);  // the window length of benches/canonical.rs: unrolled
+    switch ((kp.base.w + 15) / 16) {
+        case 1: return launch_canonical_tiles<1, 0, MODE>(c, kp, s);
+        case 2: return launch_canonical_tiles<2, 0, MODE>(c, kp, s);
+        case 3: return launch_canonical_tiles<3, 0, MODE>(c, kp, s);
+        default: return launch_canonical_tiles<4, 0, MODE>(c, kp, s);
+    }
+}
+
+static CanonKeyParams canonical_tile_params(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
+                                            void* out_dev) {
+    CanonKeyParams kp{};
+    kp.base = canonical_params(c, enc, forward_only, dna_dev, n_seq, seq_len, w, static_cast<uint8_t*>(out_dev));
+    kp.base.pair = c->d_ckey_pair + (enc == QD_ENC_ASCII ? 0 : PAIR_ENTRIES);
+    kp.tables = c->d_ckey;
+    return kp;
+}
+
+// every length-w window of each of n_seq sequences of seq_len nucleotides (n_seq = 1: one sequence)
+static int canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w,
+                         uint8_t* out_dev, cudaStream_t s) {
+    if (w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
+    if (seq_len < w || n_seq == 0) return QD_OK;
+    return canonical_tiles_mode<CTILE_ROWS>(c, canonical_tile_params(c, enc, forward_only, dna_dev, n_seq, seq_len, w, out_dev), s);
 }
 
 // one fixed-width key per canonical window
@@ -775,11 +765,8 @@ static int canonical_keys_dev(qd_ctx* c, int enc, int forward_only, int kind, co
                               void* keys_dev, cudaStream_t s) {
     if (w < 1 || w > CANON_MAX_W || (kind != QD_CANON_KEY_PACKED && kind != QD_CANON_KEY_FP64)) return QD_ERR_INVALID_ARGUMENT;
     if (seq_len < w || n_seq == 0) return QD_OK;
-    CanonKeyParams kp{};
-    kp.base = canonical_params(c, enc, forward_only, dna_dev, n_seq, seq_len, w, static_cast<uint8_t*>(keys_dev));
-    kp.base.pair = c->d_ckey_pair + (enc == QD_ENC_ASCII ? 0 : PAIR_ENTRIES);
-    kp.tables = c->d_ckey;
-    return kind == QD_CANON_KEY_FP64 ? canonical_keys_kind<CKEY_FP64>(c, kp, s) : canonical_keys_kind<CKEY_PACKED>(c, kp, s);
+    const CanonKeyParams kp = canonical_tile_params(c, enc, forward_only, dna_dev, n_seq, seq_len, w, keys_dev);
+    return kind == QD_CANON_KEY_FP64 ? canonical_tiles_mode<CTILE_KEY_FP64>(c, kp, s) : canonical_tiles_mode<CTILE_KEY_PACKED>(c, kp, s);
 }
 
 extern "C" size_t qd_canonical_key_bytes(int kind, size_t w) {

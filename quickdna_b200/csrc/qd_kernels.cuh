@@ -93,6 +93,9 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -983,14 +986,6 @@ __global__ void origin_kernel(uint64_t* __restrict__ out, uint64_t count, int ki
 // ------------------------------------------------------------------------------------------------
 // Canonical windows (strict alphabet): per window, min_lex(fw(window), fw(reverse(window)))
 // (src/canonical.rs:17-55, 71-118, 129-179 applied per window as benches/canonical.rs:29-34 does).
-//
-// Bit-parallel: a window is w 2-bit codes (A,T,C,G = 0..3, the reference's order) in NW 32-bit words, nucleotide j at
-// bits 2j.  Relabelling by first occurrence sends the first three distinct codes c0, c1, c2 (and the fourth, which is
-// c0^c1^c2) to 0, 1, 2, 3.  Every permutation of {0..3} is AFFINE over GF(2)^2, so the relabelling is
-// y = M (x ^ c0) with a 2x2 bit matrix built from u = c0^c1, v = c0^c2 -- three LOP3 per word on the packed window
-// instead of a loop over nucleotides.  The reversed window goes through the same code after a 2-bit-group reversal.
-// Output bytes are produced 4 at a time (PRMT through a 4-letter register), staged in shared memory in output order
-// and written by one TMA bulk store per tile.
 // ------------------------------------------------------------------------------------------------
 struct CanonParams {
     const uint8_t* dna;      // n_seq sequences of seq_len nucleotides, back to back
@@ -1000,383 +995,44 @@ struct CanonParams {
     int forward_only;
     uint8_t* out;            // n_seq * (seq_len - w + 1) windows, w bytes each, tightly packed, 16-byte aligned
     const uint8_t* decode;   // 256-byte table -> internal code (0..3 concrete); exact error search only
-    const uint8_t* pair;     // PAIR_ENTRIES bytes: letter pair -> code0 | code1 << 4, | 0x88 if either is not a concrete base
+    const uint8_t* pair;     // PAIR_ENTRIES bytes: letter pair -> code0 | code1 << 2, | CKEY_PAIR_FLAG if either is not a concrete base
     uint32_t pair_coef;      // dp2a coefficients {1, k1} (byte entries)
     uint32_t and_need, or_forbid, filler;  // as in the frame / reverse-complement kernels
     uint32_t letters;        // output byte of codes 0..3 packed little-endian (ASCII "ATCG" or masks 1,2,4,8)
     unsigned long long* err_key;
 };
 
-constexpr int CANON_THREADS = 256;  // windows per tile (a multiple of 16: tile outputs stay 16-byte aligned)
 constexpr int CANON_MAX_W = 64;
 
-
-// first word (ascending) of m[] that is non-zero, with the matching word of x[]; returns false if all are zero
-template <int NW>
-__device__ __forceinline__ bool first_nonzero(const uint32_t (&m)[NW], const uint32_t (&x)[NW], uint32_t& msel, uint32_t& xsel) {
-    msel = m[NW - 1];
-    xsel = x[NW - 1];
-#pragma unroll
-    for (int k = NW - 2; k >= 0; k--)
-        if (m[k]) {
-            msel = m[k];
-            xsel = x[k];
-        }
-    return msel != 0;
-}
-
-// The relabelling of one window as an affine map over GF(2)^2 applied to packed codes: y = ((x & P) ^ T) ^ ((x >> 1) & Q) ^ ((x << 1) & R)
-struct CanonMap {
-    uint32_t P, Q, R, T;
-};
-__device__ __forceinline__ uint32_t canon_apply(const CanonMap& m, uint32_t xk, uint32_t keep) {
-    return (((xk & m.P) ^ m.T) ^ ((xk >> 1) & m.Q) ^ ((xk << 1) & m.R)) & keep;
-}
-
-// The map of fw(x): relabel by first occurrence.  V[k] = 0x55555555 restricted to the window's positions.
-template <int NW>
-__device__ __forceinline__ CanonMap canon_find_map(const uint32_t (&x)[NW], const uint32_t (&V)[NW], bool* three_found) {
-    const uint32_t c0 = x[0] & 3u;
-    bool found3 = false;
-    const uint32_t C0 = c0 * 0x55555555u;
-    uint32_t ne1[NW], msel, xsel;
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-        const uint32_t e = x[k] ^ C0;
-        ne1[k] = (e | (e >> 1)) & V[k];  // positions whose code differs from c0
-    }
-    uint32_t u = 1u, v = 2u;  // a window with one base: any invertible map sending c0 to 0
-    if (first_nonzero<NW>(ne1, x, msel, xsel)) {
-        const uint32_t c1 = (xsel >> (__ffs(msel) - 1)) & 3u;
-        u = c0 ^ c1;
-        v = u == 1u ? 2u : 1u;  // two bases: any v that keeps the map invertible
-        const uint32_t C1 = c1 * 0x55555555u;
-        uint32_t ne2[NW];
-#pragma unroll
-        for (int k = 0; k < NW; k++) {
-            const uint32_t e = x[k] ^ C1;
-            ne2[k] = ne1[k] & (e | (e >> 1));  // ... and from c1
-        }
-        if (first_nonzero<NW>(ne2, x, msel, xsel)) {
-            v = c0 ^ ((xsel >> (__ffs(msel) - 1)) & 3u);
-            found3 = true;
-        }
-    }
-    if (three_found) *three_found = found3;  // three distinct bases seen: the map is final even if x is only a prefix
-    // k = M^-1 (x ^ c0), M = [u v] as columns:  k0 = v1 z0 ^ v0 z1,  k1 = u1 z0 ^ u0 z1   (z = x ^ c0)
-    const uint32_t v0 = v & 1u, v1 = v >> 1, u0 = u & 1u, u1 = u >> 1, c00 = c0 & 1u, c01 = c0 >> 1;
-    CanonMap m;
-    m.P = v1 * 0x55555555u | u0 * 0xaaaaaaaau;  // applied to x in place
-    m.Q = v0 * 0x55555555u;                      // applied to x >> 1 (hi bit moved to the lo plane)
-    m.R = u1 * 0xaaaaaaaau;                      // applied to x << 1 (lo bit moved to the hi plane)
-    m.T = ((v1 & c00) ^ (v0 & c01)) * 0x55555555u | ((u1 & c00) ^ (u0 & c01)) * 0xaaaaaaaau;
-    return m;
-}
-
-// fw(x) into y; returns the map itself applied to the codes 0,1,2,3 (0xe4): 2 bits per code
-template <int NW>
-__device__ __forceinline__ uint32_t forward_canonical_packed(const uint32_t (&x)[NW], const uint32_t (&V)[NW], uint32_t (&y)[NW],
-                                                             bool* three_found = nullptr) {
-    const CanonMap m = canon_find_map<NW>(x, V, three_found);
-#pragma unroll
-    for (int k = 0; k < NW; k++) y[k] = canon_apply(m, x[k], V[k] * 3u);
-    return canon_apply(m, 0xe4u, 0xffu);
-}
-
-// reverse the order of the w 2-bit groups of x (nucleotide j <-> w-1-j)
-template <int NW>
-__device__ __forceinline__ void reverse_pairs(const uint32_t (&x)[NW], uint32_t w, uint32_t (&r)[NW]) {
-    uint32_t t[NW + 1];
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-        const uint32_t b = __brev(x[NW - 1 - k]);
-        t[k] = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
-    }
-    t[NW] = 0;
-    // the reversed window now ends at bit 32*NW: move it down by 32*NW - 2w bits (< 32: NW is the smallest that fits w)
-    const uint32_t sh = 32u * NW - 2u * w;
-#pragma unroll
-    for (int k = 0; k < NW; k++) r[k] = __funnelshift_r(t[k], t[k + 1], sh);
-}
-
-// Warp-independent tiles: a warp owns CANON_WPT consecutive windows (of the whole batch) per iteration and shares
-// nothing with the other warps of its CTA -- no block barrier anywhere.  Per warp-tile:
-//   decode   the <= CANON_WPT + w - 1 (+ sequence seams) nucleotides the tile touches, 4 per lane and step, two letters
-//            per shared-memory lookup (same dp2a pair index as the frame kernel), into three streams in shared memory:
-//            2-bit packed codes (for the relabelling arithmetic), and the codes as NIBBLES in forward and in reversed
-//            order (PRMT selectors for the output: a window's bytes are 4 per PRMT through a 4-letter register that
-//            already holds the window's relabelling, read from whichever of the two streams won)
-//   window   CANON_WPT / 32 per lane: fw(x), fw(reverse(x)), lexical minimum, 11 PRMT for 42 bytes
-//   copy-out the tile's staged bytes with coalesced 128-bit stores
-constexpr int CANON_WPT = 64;  // windows per warp-tile
-// per-warp shared memory, sized by w: c2 (16 codes per word) | nib_f (8 codes per word, ascending) | nib_r (the same
-// nucleotides in descending order) | stage (the tile's output bytes)
-struct CanonWarpLayout {
-    uint32_t c2_words, nib_words, stage_bytes, total_bytes;
-    __host__ __device__ explicit CanonWarpLayout(uint32_t w) {
-        const uint32_t gran = (CANON_WPT * w + 15) / 16 + 2;  // granules a warp-tile can touch
-        c2_words = (gran + 2 + 3) & ~3u;
-        nib_words = (2 * gran + 2 + 3) & ~3u;
-        stage_bytes = (CANON_WPT * w + 15) & ~15u;
-        total_bytes = 4 * (c2_words + 2 * nib_words) + stage_bytes;
-    }
-};
-struct CanonWarpSmem {
-    uint32_t* c2;
-    uint32_t* nib_f;
-    uint32_t* nib_r;
-    uint8_t* stage;
-};
-constexpr int CANON_WARPS = CANON_THREADS / 32;
-
-// W: the window length when it is a compile-time constant (42: benches/canonical.rs), 0 = p.w
-template <int NW, int W = 0>
-__global__ void __launch_bounds__(CANON_THREADS) canonical_windows_kernel(const CanonParams p) {
-    static_assert(W == 0 || (2 * W + 31) / 32 == NW, "NW must be the word count of W");
-    extern __shared__ __align__(128) unsigned char canon_smem[];
-    const uint32_t w = W ? (uint32_t)W : p.w;
-    const CanonWarpLayout lay(w);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    CanonWarpSmem S;
-    S.c2 = reinterpret_cast<uint32_t*>(canon_smem + (size_t)warp * lay.total_bytes);
-    S.nib_f = S.c2 + lay.c2_words;
-    S.nib_r = S.nib_f + lay.nib_words;
-    S.stage = reinterpret_cast<uint8_t*>(S.nib_r + lay.nib_words);
-    uint8_t* const pair_s = canon_smem + (size_t)CANON_WARPS * lay.total_bytes;  // PAIR_ENTRIES bytes
-    for (int i = tid; i < (int)PAIR_ENTRIES; i += CANON_THREADS) pair_s[i] = __ldg(p.pair + i);
-    __syncthreads();
-    const uint64_t nw = p.seq_len - w + 1;  // windows per sequence
-    const uint64_t total = p.n_seq * nw;    // windows in the batch
-    const uint64_t n_tiles = (total + CANON_WPT - 1) / CANON_WPT;
-    uint32_t V[NW];
-#pragma unroll
-    for (int k = 0; k < NW; k++) {
-        const int left = (int)w - 16 * k;
-        V[k] = left >= 16 ? 0x55555555u : (left <= 0 ? 0u : (0x55555555u & ((1u << (2 * left)) - 1u)));
-    }
-    const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.n_seq * p.seq_len;
-    const uint32_t pair_base = smem_u32(pair_s);
-    // tile t of this warp: first window g0 = CANON_WPT t, in sequence s0 at index i0; advanced incrementally
-    const uint64_t warps_total = (uint64_t)gridDim.x * CANON_WARPS;
-    uint64_t tile = (uint64_t)blockIdx.x * CANON_WARPS + warp;
-    uint64_t s0 = (tile * CANON_WPT) / nw, i0 = (tile * CANON_WPT) % nw;
-    const uint64_t step_s = (warps_total * CANON_WPT) / nw, step_i = (warps_total * CANON_WPT) % nw;
-    for (; tile < n_tiles; tile += warps_total) {
-        const uint64_t g0 = tile * CANON_WPT;
-        const uint32_t cnt = (uint32_t)min((uint64_t)CANON_WPT, total - g0);
-        uint64_t sl = s0, il = i0 + (cnt - 1);  // the tile's last window
-        if (il >= nw) {
-            if (nw >= CANON_WPT) { il -= nw; sl++; }
-            else { sl += il / nw; il %= nw; }
-        }
-        const uint64_t flat_lo = s0 * p.seq_len + i0, flat_hi = sl * p.seq_len + il + w;
-        const uintptr_t a0 = (dna_lo + flat_lo) & ~(uintptr_t)15;
-        const uint32_t n_gran = (uint32_t)((dna_lo + flat_hi - a0 + 15) >> 4);
-        // ---- decode: item = one aligned 32-bit word of input (4 nucleotides) -------------------------------
-        for (uint32_t item = lane; item < 4 * n_gran; item += 32) {
-            const uintptr_t a = a0 + 4 * (uintptr_t)item;
-            uint32_t x;
-            if (a >= dna_lo && a + 4 <= dna_hi) {
-                // bytes of the word outside this tile's span belong to a neighbouring tile (or sequence) and are
-                // validated there too, so looking at them here changes nothing
-                x = __ldg(reinterpret_cast<const uint32_t*>(a));
-            } else {  // the words straddling the ends of the whole buffer: bytes outside it read as a valid filler
-                x = 0;
-#pragma unroll 1
-                for (int t = 0; t < 4; t++) {
-                    const uintptr_t b = a + t;
-                    x |= ((b >= dna_lo && b < dna_hi) ? (uint32_t)*reinterpret_cast<const uint8_t*>(b) : (p.filler & 0xffu)) << (8 * t);
-                }
-            }
-            const uint32_t m = x & 0x1f1f1f1fu;
-            uint32_t e0 = lds_u8(dp2a_lo(p.pair_coef, m, pair_base)), e1 = lds_u8(dp2a_hi(p.pair_coef, m, pair_base));
-            if (((e0 | e1) & 0x88u) | ((x & p.and_need) ^ p.and_need) | (x & p.or_forbid)) {
-                // exact: first byte of this word that is not a concrete base
-#pragma unroll 1
-                for (int t = 0; t < 4; t++) {
-                    const uintptr_t b = a + t;
-                    if (b >= dna_lo && b < dna_hi && __ldg(p.decode + *reinterpret_cast<const uint8_t*>(b)) > 3u) {
-                        atomicMin(p.err_key, (unsigned long long)(b - dna_lo));
-                        break;
-                    }
-                }
-                e0 &= 0x33u;
-                e1 &= 0x33u;
-            }
-            reinterpret_cast<uint16_t*>(S.nib_f)[item] = (uint16_t)(e0 | (e1 << 8));
-            // reversed stream: the same four nibbles in descending order at the mirrored half-word
-            const uint32_t r0 = ((e1 >> 4) | (e1 << 4)) & 0xffu, r1 = ((e0 >> 4) | (e0 << 4)) & 0xffu;
-            reinterpret_cast<uint16_t*>(S.nib_r)[4 * n_gran - 1 - item] = (uint16_t)(r0 | (r1 << 8));
-            reinterpret_cast<uint8_t*>(S.c2)[item] = (uint8_t)((e0 & 3u) | ((e0 >> 2) & 0xcu) | ((e1 & 3u) << 4) | ((e1 << 2) & 0xc0u));
-        }
-        if (lane == 0) {
-            S.c2[n_gran] = 0;
-            S.nib_f[2 * n_gran] = 0;
-            S.nib_r[2 * n_gran] = 0;
-        }
-        __syncwarp();
-        // ---- my windows ----------------------------------------------------------------------------------
-        // lane handles windows 2 * lane and 2 * lane + 1: for even w all rows of one pass share their alignment in the stage
-#pragma unroll 1
-        for (uint32_t pass = 0; pass < CANON_WPT / 32; pass++) {
-            const uint32_t l = (CANON_WPT / 32) * lane + pass;
-            if (l >= cnt) continue;
-            uint64_t s = s0, i = i0 + l;
-            if (i >= nw) {
-                if (nw >= CANON_WPT) { i -= nw; s++; }
-                else { s += i / nw; i %= nw; }
-            }
-            const uint32_t o = (uint32_t)(dna_lo + s * p.seq_len + i - a0);  // nucleotide offset inside the streams
-            uint32_t perm = 0;
-            bool use_rev = false, decided = false;
-            if (NW > 1) {
-                // Fast path: the relabelling is fixed by the first three distinct bases and the lexical minimum by the first
-                // differing position -- for all but low-complexity windows both lie within the first 16 nucleotides of the
-                // window and of its reverse.  One word from each end; anything unresolved takes the full-width path below.
-                const uint32_t V16[1] = {0x55555555u};
-                uint32_t h[1], t[1], yh[1], yt[1];
-                {
-                    const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
-                    h[0] = __funnelshift_r(S.c2[wi], S.c2[wi + 1], sh);
-                    const uint32_t ot = o + w - 16u, wt = ot >> 4, st = (ot & 15u) * 2u;
-                    const uint32_t tail = __brev(__funnelshift_r(S.c2[wt], S.c2[wt + 1], st));  // last 16 nucleotides ...
-                    t[0] = ((tail >> 1) & 0x55555555u) | ((tail & 0x55555555u) << 1);             // ... in reversed order
-                }
-                bool f3 = false, r3 = false;
-                const uint32_t pf = forward_canonical_packed<1>(h, V16, yh, &f3);
-                if (p.forward_only) {
-                    decided = f3;
-                    perm = pf;
-                } else {
-                    const uint32_t pr = forward_canonical_packed<1>(t, V16, yt, &r3);
-                    const uint32_t d = yh[0] ^ yt[0];
-                    if (f3 && r3 && d) {
-                        const uint32_t pos = (__ffs(d) - 1) & ~1u;
-                        use_rev = ((yt[0] >> pos) & 3u) < ((yh[0] >> pos) & 3u);
-                        perm = use_rev ? pr : pf;
-                        decided = true;
-                    }
-                }
-            }
-            if (!decided) {
-                uint32_t x[NW], y[NW];
-                {
-                    const uint32_t wi = o >> 4, sh = (o & 15u) * 2u;
-#pragma unroll
-                    for (int k = 0; k < NW; k++) x[k] = __funnelshift_r(S.c2[wi + k], S.c2[wi + k + 1], sh) & (V[k] * 3u);
-                }
-                perm = forward_canonical_packed<NW>(x, V, y);  // perm: the relabelling of codes 0..3, 2 bits each
-                use_rev = false;
-                if (!p.forward_only) {
-                    uint32_t xr[NW], yr[NW];
-                    reverse_pairs<NW>(x, w, xr);
-                    const uint32_t perm_r = forward_canonical_packed<NW>(xr, V, yr);
-                    // lexical order: the lowest differing 2-bit group decides (first nucleotide = bits 0..1)
-                    uint32_t d[NW], dsel, ysel;
-#pragma unroll
-                    for (int k = 0; k < NW; k++) d[k] = y[k] ^ yr[k];
-                    if (first_nonzero<NW>(d, y, dsel, ysel)) {
-                        const uint32_t pos = (__ffs(dsel) - 1) & ~1u;
-                        use_rev = (((ysel ^ dsel) >> pos) & 3u) < ((ysel >> pos) & 3u);
-                    }
-                    if (use_rev) perm = perm_r;
-                }
-            }
-            // the window's letters: T[code] = letters[perm[code]]
-            uint32_t t = (perm | (perm << 4)) & 0x0f0fu;
-            t = (t | (t << 2)) & 0x3333u;
-            const uint32_t T = __byte_perm(p.letters, 0, t);
-            // selectors: the window's raw codes as nibbles, from the forward or the reversed stream
-            const uint32_t* stream = use_rev ? S.nib_r : S.nib_f;
-            const uint32_t on = use_rev ? 16u * n_gran - o - w : o;
-            const uint32_t wi = on >> 3, sh = (on & 7u) * 4u;
-            constexpr int NN = 2 * NW;  // nibble words of a window
-            uint32_t N[NN + 1];
-#pragma unroll
-            for (int k = 0; k <= NN; k++) N[k] = stream[wi + k];
-            uint8_t* dst = S.stage + (size_t)l * w;
-            // the row's letters, four per PRMT
-            uint32_t Lw[2 * NN];
-#pragma unroll
-            for (int k = 0; k < NN; k++) {
-                const uint32_t sel = __funnelshift_r(N[k], N[k + 1], sh);  // nucleotides 8k .. 8k+7
-                Lw[2 * k] = __byte_perm(T, 0, sel);
-                Lw[2 * k + 1] = __byte_perm(T, 0, sel >> 16);
-            }
-            if ((w & 1u) == 0) {
-                // even w: a row starts 4-byte aligned or 2 bytes past; whole 32-bit stores in between.  The alignment is the
-                // same for every row of this pass, so the branch does not diverge.
-                if (((l * w) & 2u) == 0) {
-#pragma unroll
-                    for (int m = 0; m < 2 * NN; m++) {
-                        const uint32_t j = 4 * m;
-                        if ((W ? j + 4 <= (uint32_t)W : j + 4 <= 16 * (NW - 1)) || j + 4 <= w) *reinterpret_cast<uint32_t*>(dst + j) = Lw[m];
-                        else if (j < w) *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)Lw[m];  // w % 4 == 2: the last two bytes
-                    }
-                } else {
-                    *reinterpret_cast<uint16_t*>(dst) = (uint16_t)Lw[0];
-#pragma unroll
-                    for (int m = 0; m + 1 < 2 * NN; m++) {
-                        const uint32_t j = 4 * m + 2;  // row bytes j .. j+3 sit in one aligned stage word
-                        const uint32_t word = __funnelshift_r(Lw[m], Lw[m + 1], 16);
-                        if ((W ? j + 4 <= (uint32_t)W : j + 4 <= 16 * (NW - 1)) || j + 4 <= w) *reinterpret_cast<uint32_t*>(dst + j) = word;
-                        else if (j < w) *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)word;
-                    }
-                    if (8 * NN - 2 < w) *reinterpret_cast<uint16_t*>(dst + 8 * NN - 2) = (uint16_t)(Lw[2 * NN - 1] >> 16);  // w == 16 NW
-                }
-            } else {
-#pragma unroll
-                for (int m = 0; m < 2 * NN; m++) {
-                    const uint32_t j = 4 * m;
-                    if (j < w) {
-                        const uint32_t four = Lw[m], left = w - j;
-                        dst[j] = (uint8_t)four;
-                        if (left > 1) dst[j + 1] = (uint8_t)(four >> 8);
-                        if (left > 2) dst[j + 2] = (uint8_t)(four >> 16);
-                        if (left > 3) dst[j + 3] = (uint8_t)(four >> 24);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- copy-out: cnt * w contiguous bytes at out + g0 * w (16-byte aligned: g0 is a multiple of 64) ----
-        {
-            const uint32_t nbytes = cnt * w, body = nbytes >> 4;
-            uint8_t* gdst = p.out + g0 * w;
-            for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + 16 * c, *reinterpret_cast<const uint4*>(S.stage + 16 * c));
-            for (uint32_t b = 16 * body + lane; b < nbytes; b += 32) gdst[b] = S.stage[b];
-        }
-        __syncwarp();
-        s0 += step_s;
-        i0 += step_i;
-        if (i0 >= nw) { i0 -= nw; s0++; }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Canonical window KEYS (a fixed-width key per canonical window for a downstream set lookup,
-// instead of 42 materialised bytes; the window arithmetic is src/canonical.rs:17-55, 71-118, 129-179 as above).
+// Canonical windows, tile kernel (src/canonical.rs:17-55, 71-118, 129-179 per window, as benches/canonical.rs:29-34 does).
+// One kernel body, three outputs:
+//   CTILE_ROWS        the canonical window's w bytes (letters or masks): qd_canonical_windows*
+//   CTILE_KEY_PACKED  the canonical window as two BIT PLANES, lossless: PW = ceil(w / 32) words holding the low bit of each
+//                     nucleotide's code (A, T, C, G = 0..3, the reference's order; nucleotide j at bit j % 32 of word j / 32),
+//                     then PW words holding the high bits; unused bits zero            
+//   CTILE_KEY_FP64    canon_fingerprint() of those words: 64 bits
 //
-//   QD_CANON_KEY_PACKED  the canonical window itself, lossless, as two BIT PLANES: PW = ceil(w / 32) words holding the low
-//                        bit of each nucleotide's code (A, T, C, G = 0..3, the reference's order; nucleotide j at bit j % 32
-//                        of word j / 32), then PW words holding the high bits; unused bits zero
-//   QD_CANON_KEY_FP64    canon_fingerprint() of those words: 64 bits
-//
-// Bit planes make the relabelling two LOP3 per 32 nucleotides (new_lo = (lo & A) ^ (hi & B) ^ T0, new_hi likewise) and the
-// reversal one BREV per word.  What is left, finding the relabelling itself, is shared between windows: the order in
-// which the four codes first occur reading FORWARD from position j is the same for every window that starts at j, and
-// follows from the order at j + 1 by moving code[j] to the front; the order reading BACKWARD from j serves every window
-// that ends at j.  (Codes that do not occur inside a window may sit anywhere in the order: they are never relabelled.)
+// Bit planes make the relabelling two LOP3 per 32 nucleotides (new_lo = (lo & A) ^ (hi & B) ^ T0, new_hi likewise: every
+// permutation of the four codes is affine over GF(2)^2) and the reversal one BREV per word.  What is left, finding the
+// relabelling itself, is shared between windows: the order in which the four codes first occur reading FORWARD from
+// position j is the same for every window that starts at j, and follows from the order at j + 1 by moving code[j] to
+// the front; the order reading BACKWARD from j serves every window that ends at j.  (Codes that do not occur inside a
+// window may sit anywhere in the order: they are never relabelled, so the scan need not stop at the window's end.)
 // So after the decode a warp runs one pass over its tile's positions -- each lane takes 8 consecutive positions, starts
 // from the order found directly in the 32 positions past its chunk, and steps through a 25 x 4 move-to-front table --
 // leaving one byte per position and direction; a window then needs two byte loads and two table rows (its six
 // coefficient masks each) instead of two searches.  Windows whose chunk start was not decided within 32 positions
 // (low-complexity sequence) search their own w positions.
-// Nothing is staged on the way out: a lane's key lives in registers and lanes write consecutive keys.
+//
+// Warps are independent (no block barrier after the tables are loaded): a warp owns `wpt` consecutive windows of the
+// whole batch per iteration.  Keys leave straight from registers, consecutive lanes -> consecutive keys.  Rows are
+// formed 4 bytes per PRMT from the RAW codes kept as nibbles (forward and reversed stream) through a 4-letter register
+// that holds the winning relabelling, staged in shared memory in output order, and copied out with 128-bit stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int CKEY_THREADS = 256;
-constexpr int CKEY_WARPS = CKEY_THREADS / 32;
-constexpr int CKEY_PACKED = 0, CKEY_FP64 = 1;
+constexpr int CTILE_THREADS = 256;
+constexpr int CTILE_WARPS = CTILE_THREADS / 32;
+constexpr int CTILE_KEY_PACKED = 0, CTILE_KEY_FP64 = 1, CTILE_ROWS = 2;
 constexpr uint32_t CKEY_PAIR_FLAG = 0x80;
 constexpr uint32_t CKEY_RANKS = 25;  // 0 = not known, 1..24 = the orders of {0, 1, 2, 3} in lexicographic order
 constexpr uint32_t CKEY_PAD = 32;    // positions of zero padding in front of the plane streams (backward look-behind)
@@ -1384,21 +1040,23 @@ constexpr uint32_t CKEY_PAD = 32;    // positions of zero padding in front of th
 struct CanonKeyTables {
     uint8_t rank_of[64];            // c0 | c1 << 2 | c2 << 4 (pairwise distinct) -> rank of the order (c0, c1, c2, the fourth); else 0
     uint8_t mtf[128];               // rank * 4 + code -> rank of the order with `code` moved to the front (rank 0 stays 0)
-    uint32_t masks[CKEY_RANKS + 7][8];  // rank -> A, B, C, D, T0, T1 (0 or ~0), 0, 0
+    uint32_t masks[CKEY_RANKS + 7][8];  // rank -> A, B, C, D, T0, T1 (0 or ~0), perm (2 bits per code: its place in the order), 0
 };
 
-// CTA-wide shared memory: the tables, the letter-pair image, and the coefficient masks once more in a conflict-free layout
-constexpr uint32_t CKEY_SHARED_TABLE_BYTES = ((uint32_t)(sizeof(CanonKeyTables) + PAIR_ENTRIES + 15) & ~15u) + 2 * CKEY_RANKS * 128;
+// CTA-wide shared memory: the tables, the letter-pair image, the coefficient masks once more in a conflict-free layout,
+// and the four output letters of every order
+constexpr uint32_t CKEY_SHARED_TABLE_BYTES = ((uint32_t)(sizeof(CanonKeyTables) + PAIR_ENTRIES + 15) & ~15u) + 2 * CKEY_RANKS * 128 + 128;
 
-// per-warp shared memory for a tile of at most `pos_cap` positions (a multiple of 32)
-struct CanonKeyLayout {
-    uint32_t plane_words, cw_bytes, state_bytes, total_bytes;
-    __host__ __device__ explicit CanonKeyLayout(uint32_t pos_cap) {
-        plane_words = (pos_cap + CKEY_PAD) / 32 + 4;
+// per-warp shared memory for a tile of `wpt` windows touching at most `pos_cap` positions (a multiple of 32)
+struct CanonTileLayout {
+    uint32_t plane_words, cw_bytes, state_bytes, nib_words, stage_bytes, total_bytes;
+    __host__ __device__ CanonTileLayout(uint32_t pos_cap, uint32_t wpt, uint32_t w, bool rows) {
+        plane_words = ((pos_cap + CKEY_PAD) / 32 + 4 + 3) & ~3u;  // every part a multiple of 16 bytes
         cw_bytes = (pos_cap / 4 + 15) & ~15u;  // 2 bits per position
         state_bytes = pos_cap;
-        total_bytes = 2 * 4 * plane_words + cw_bytes + 2 * state_bytes;
-        total_bytes = (total_bytes + 15) & ~15u;
+        nib_words = rows ? ((pos_cap / 8 + 16 + 3) & ~3u) : 0u;  // 4 bits per position: one pad word in front, + what a window's last load may touch
+        stage_bytes = rows ? ((64 * w + 15) & ~15u) : 0u;        // rows leave 64 at a time
+        total_bytes = (8 * plane_words + cw_bytes + 2 * state_bytes + 8 * nib_words + stage_bytes + 15) & ~15u;
     }
 };
 // positions a warp-tile of `wpt` windows can touch: its windows, w - 1 more per sequence it reaches into, alignment slack
@@ -1458,48 +1116,63 @@ __device__ __forceinline__ uint32_t ckey_first_three(const uint32_t (&lo)[PW], c
 }
 
 struct CanonKeyParams {
-    CanonParams base;               // out = the keys; pair = the ckey_pair image of the encoding
+    CanonParams base;               // out = the rows or keys; pair = the ckey_pair image of the encoding
     const CanonKeyTables* tables;
-    uint32_t wpt;                   // windows per warp-tile (a multiple of 32)
+    uint32_t wpt;                   // windows per warp-tile (a multiple of 64)
     uint32_t pos_cap;               // positions a warp-tile can touch, rounded up to 32 (sizes the shared memory)
 };
 
-template <int PW, int W, int KIND>
-__global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const CanonKeyParams kp) {
-    static_assert(W == 0 || (W + 31) / 32 == PW, "PW must be the plane word count of W");
-    extern __shared__ __align__(16) unsigned char ckey_smem[];
+// NW = ceil(w / 16) (the row emission works on 16-nucleotide units), W = the window length when it is a compile-time
+// constant (42: benches/canonical.rs), 0 = p.w
+template <int NW, int W, int MODE>
+__global__ void __launch_bounds__(CTILE_THREADS) canonical_tile_kernel(const CanonKeyParams kp) {
+    constexpr int PW = (NW + 1) / 2;  // plane words of a window
+    constexpr bool ROWS = MODE == CTILE_ROWS;
+    static_assert(W == 0 || (W + 15) / 16 == NW, "NW must be the 16-nucleotide unit count of W");
+    extern __shared__ __align__(16) unsigned char ctile_smem[];
     const CanonParams& p = kp.base;
     const uint32_t w = W ? (uint32_t)W : p.w;
-    const CanonKeyLayout lay(kp.pos_cap);
+    const uint32_t WPT = kp.wpt;
+    const CanonTileLayout lay(kp.pos_cap, WPT, w, ROWS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // CTA-wide tables, then one private region per warp
-    CanonKeyTables* const tabs = reinterpret_cast<CanonKeyTables*>(ckey_smem);
-    uint8_t* const pair_s = ckey_smem + sizeof(CanonKeyTables);  // PAIR_ENTRIES bytes
+    CanonKeyTables* const tabs = reinterpret_cast<CanonKeyTables*>(ctile_smem);
+    uint8_t* const pair_s = ctile_smem + sizeof(CanonKeyTables);  // PAIR_ENTRIES bytes
     // the coefficient masks again, one 128-byte line per rank and part -- (A, B, C, D) and (T0, T1, T0 & V_last, T1 & V_last),
     // V_last = the positions of the window's last plane word -- replicated so that every lane of a quarter-warp reads its
     // own bank group whatever its rank: no conflicts
-    uint32_t* const quad_s = reinterpret_cast<uint32_t*>(ckey_smem + CKEY_SHARED_TABLE_BYTES - 2 * CKEY_RANKS * 128);
+    uint32_t* const quad_s = reinterpret_cast<uint32_t*>(ctile_smem + CKEY_SHARED_TABLE_BYTES - 2 * CKEY_RANKS * 128 - 128);
     uint32_t* const duo_s = quad_s + CKEY_RANKS * 32;
-    unsigned char* const mine = ckey_smem + CKEY_SHARED_TABLE_BYTES + (size_t)warp * lay.total_bytes;
+    uint32_t* const letters_s = duo_s + CKEY_RANKS * 32;  // rank -> the output byte of raw code c at byte c
+    unsigned char* const mine = ctile_smem + CKEY_SHARED_TABLE_BYTES + (size_t)warp * lay.total_bytes;
     uint32_t* const LO = reinterpret_cast<uint32_t*>(mine);
     uint32_t* const HI = LO + lay.plane_words;
     uint16_t* const CW = reinterpret_cast<uint16_t*>(HI + lay.plane_words);  // codes interleaved, 8 positions per half-word
     uint8_t* const stF = reinterpret_cast<uint8_t*>(CW) + lay.cw_bytes;      // order reading forward from each position
     uint8_t* const stB = stF + lay.state_bytes;                              // order reading backward from each position
-    for (int i = tid; i < (int)(sizeof(CanonKeyTables) / 4); i += CKEY_THREADS)
+    uint32_t* const NF = reinterpret_cast<uint32_t*>(stB + lay.state_bytes); // raw codes as nibbles, ascending positions
+    uint32_t* const NR = NF + lay.nib_words;                                 // the same, descending
+    uint8_t* const stage = reinterpret_cast<uint8_t*>(NR + lay.nib_words);   // the tile's rows in output order
+    for (int i = tid; i < (int)(sizeof(CanonKeyTables) / 4); i += CTILE_THREADS)
         reinterpret_cast<uint32_t*>(tabs)[i] = __ldg(reinterpret_cast<const uint32_t*>(kp.tables) + i);
-    for (int i = tid; i < (int)PAIR_ENTRIES; i += CKEY_THREADS) pair_s[i] = __ldg(p.pair + i);
+    for (int i = tid; i < (int)PAIR_ENTRIES; i += CTILE_THREADS) pair_s[i] = __ldg(p.pair + i);
     {
         const uint32_t left = w - 32u * (PW - 1), v_last = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
-        for (int i = tid; i < (int)CKEY_RANKS * 32; i += CKEY_THREADS) {
+        for (int i = tid; i < (int)CKEY_RANKS * 32; i += CTILE_THREADS) {
             quad_s[i] = __ldg(&kp.tables->masks[i >> 5][i & 3]);
             duo_s[i] = __ldg(&kp.tables->masks[i >> 5][4 + (i & 1)]) & ((i & 2) ? v_last : 0xffffffffu);
+        }
+        if (tid < (int)CKEY_RANKS) {
+            // letters[c] = p.letters[place of raw code c in the order]
+            const uint32_t perm = __ldg(&kp.tables->masks[tid][6]);
+            uint32_t t = (perm | (perm << 4)) & 0x0f0fu;
+            t = (t | (t << 2)) & 0x3333u;
+            letters_s[tid] = __byte_perm(p.letters, 0, t);
         }
     }
     __syncthreads();
     const uint64_t nw = p.seq_len - w + 1;  // windows per sequence
     const uint64_t total = p.n_seq * nw;    // windows in the batch
-    const uint32_t WPT = kp.wpt;
     const uint64_t n_tiles = (total + WPT - 1) / WPT;
     uint32_t V[PW];
 #pragma unroll
@@ -1512,10 +1185,11 @@ __global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const Cano
     const uint32_t mtf_base = smem_u32(tabs->mtf), rank_base = smem_u32(tabs->rank_of);
     const uint32_t quad_base = smem_u32(quad_s) + (lane & 7) * 16, duo_base = smem_u32(duo_s) + (lane & 7) * 16;
     const uint32_t lo_base = smem_u32(LO), hi_delta = 4u * lay.plane_words, stF_base = smem_u32(stF), stB_base = smem_u32(stB) + w - 1u;
+    const uint32_t nf_base = smem_u32(NF), nr_base = smem_u32(NR), stage_base = smem_u32(stage), letters_base = smem_u32(letters_s);
     const bool long_seqs = nw >= WPT;  // a tile reaches into at most two sequences
     const uint32_t V32[1] = {0xffffffffu};
-    const uint64_t warps_total = (uint64_t)gridDim.x * CKEY_WARPS;
-    uint64_t tile = (uint64_t)blockIdx.x * CKEY_WARPS + warp;
+    const uint64_t warps_total = (uint64_t)gridDim.x * CTILE_WARPS;
+    uint64_t tile = (uint64_t)blockIdx.x * CTILE_WARPS + warp;
     uint64_t s0 = (tile * WPT) / nw, i0 = (tile * WPT) % nw;
     const uint64_t step_s = (warps_total * WPT) / nw, step_i = (warps_total * WPT) % nw;
     for (; tile < n_tiles; tile += warps_total) {
@@ -1531,11 +1205,12 @@ __global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const Cano
         const uint32_t n_chunk = (uint32_t)((dna_lo + flat_hi - a0 + 7) >> 3);  // 8 positions each
         const uint32_t o_first = (uint32_t)(dna_lo + flat_lo - a0);             // position of the tile's first window
         const uint32_t l_seam = (uint32_t)min((uint64_t)WPT, nw - i0);          // the first window of the next sequence
-        // ---- decode: item = 8 nucleotides -> one byte per plane, one half-word of interleaved codes -------------
+        // ---- decode: item = 8 nucleotides -> one byte per plane, one half-word of interleaved codes (+ 2 nibble words) ----
         if (lane < 4) {
             reinterpret_cast<uint8_t*>(LO)[lane] = 0;  // the padding in front
             reinterpret_cast<uint8_t*>(HI)[lane] = 0;
         }
+        if (ROWS && lane == 4) NF[0] = NR[0] = 0;
         for (uint32_t item = lane; item < n_chunk + 12; item += 32) {
             uint32_t plane_lo = 0, plane_hi = 0, cw = 0;
             if (item < n_chunk) {
@@ -1578,6 +1253,18 @@ __global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const Cano
                 z = (z | (z >> 4)) & 0x00ff00ffu;
                 plane_lo = z & 0xffu;
                 plane_hi = z >> 16;
+                if (ROWS) {
+                    // the eight codes as nibbles, and once more in reversed order at the mirrored word
+                    uint32_t n = (cw | (cw << 8)) & 0x00ff00ffu;
+                    n = (n | (n << 4)) & 0x0f0f0f0fu;
+                    n = (n | (n << 2)) & 0x33333333u;
+                    NF[1 + item] = n;
+                    const uint32_t b = __byte_perm(n, 0, 0x0123);
+                    NR[n_chunk - item] = ((b >> 4) & 0x0f0f0f0fu) | ((b & 0x0f0f0f0fu) << 4);
+                }
+            } else if (ROWS) {
+                NF[1 + item] = 0;  // the words past the end a window's last load may touch
+                NR[1 + item] = 0;
             }
             // items past the tile's end: zeros (the look-ahead of the last chunks reads them)
             reinterpret_cast<uint8_t*>(LO)[CKEY_PAD / 8 + item] = (uint8_t)plane_lo;
@@ -1618,9 +1305,15 @@ __global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const Cano
             }
         }
         __syncwarp();
-        // ---- my windows: lane handles windows lane, lane + 32, ...: consecutive lanes write consecutive keys ----
+        // ---- my windows ------------------------------------------------------------------------------------------
+        // keys: lane handles windows lane, lane + 32, ...: consecutive lanes write consecutive keys.
+        // rows: within every 64 windows lane handles 2 lane and 2 lane + 1: for even w all rows of one pass share their
+        //       alignment in the stage, and the rows of a pass are an odd number of words apart (no bank conflicts)
+        const uint32_t n_it = ROWS ? 2u * ((cnt + 63u) >> 6) : (cnt + 31u) >> 5;
 #pragma unroll 1
-        for (uint32_t l = lane; l < cnt; l += 32) {
+        for (uint32_t it = 0; it < n_it; it++) {
+            const uint32_t l = ROWS ? 64u * (it >> 1) + 2u * lane + (it & 1u) : 32u * it + lane;
+            if (l < cnt) {
             uint32_t o;  // position inside the streams: every sequence seam before the window skips w - 1 positions
             if (long_seqs) o = o_first + l + (l >= l_seam ? w - 1u : 0u);
             else o = o_first + l + (((uint32_t)i0 + l) / (uint32_t)nw) * (w - 1u);  // nw < WPT here: 32-bit division
@@ -1665,6 +1358,7 @@ __global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const Cano
                 yl[k] = (xl[k] & mf0.x) ^ (xh[k] & mf0.y) ^ (k == PW - 1 ? mf1.z : mf1.x);
                 yh[k] = (xl[k] & mf0.z) ^ (xh[k] & mf0.w) ^ (k == PW - 1 ? mf1.w : mf1.y);
             }
+            bool use_rev = false;
             if (!p.forward_only) {
                 const uint4 mr0 = lds_u128(quad_base + rB * 128u);
                 const uint4 mr1 = lds_u128(duo_base + rB * 128u);
@@ -1679,25 +1373,96 @@ __global__ void __launch_bounds__(CKEY_THREADS) canonical_keys_kernel(const Cano
                     const uint32_t hd = yh[k] ^ zh[k];
                     lose[k] = (d & (0u - d)) & ((hd & zh[k]) | (~hd & ~yl[k]));  // first differing position of this word, if lost there
                 }
-                bool use_rev;
                 if (PW == 1) {
                     use_rev = lose[0] == 0;  // (equal windows: either)
                 } else {
                     const uint32_t d0 = (yl[0] ^ zl[0]) | (yh[0] ^ zh[0]);
                     use_rev = (d0 ? lose[0] : lose[PW - 1]) == 0;
                 }
-                if (use_rev) {
+                if (!ROWS && use_rev) {
 #pragma unroll
                     for (int k = 0; k < PW; k++) yl[k] = zl[k], yh[k] = zh[k];
                 }
             }
-            const uint64_t g = g0 + l;
-            if (KIND == CKEY_FP64) {
-                reinterpret_cast<uint64_t*>(p.out)[g] = canon_fingerprint<PW>(yl, yh, w);
-            } else if (PW == 1) {
-                reinterpret_cast<uint2*>(p.out)[g] = make_uint2(yl[0], yh[0]);
+            if constexpr (!ROWS) {
+                const uint64_t g = g0 + l;
+                if (MODE == CTILE_KEY_FP64) {
+                    reinterpret_cast<uint64_t*>(p.out)[g] = canon_fingerprint<PW>(yl, yh, w);
+                } else if (PW == 1) {
+                    reinterpret_cast<uint2*>(p.out)[g] = make_uint2(yl[0], yh[0]);
+                } else {
+                    reinterpret_cast<uint4*>(p.out)[g] = make_uint4(yl[0], yl[PW - 1], yh[0], yh[PW - 1]);
+                }
             } else {
-                reinterpret_cast<uint4*>(p.out)[g] = make_uint4(yl[0], yl[PW - 1], yh[0], yh[PW - 1]);
+                // the window's letters: T[raw code] = the letter of its place in the winning order
+                const uint32_t T = lds_u32(letters_base + 4u * (use_rev ? rB : rF));
+                // selectors: the window's raw codes as nibbles, from the forward or the reversed stream (one pad word in front).
+                // A row of even length starts 4-byte aligned in the stage or 2 bytes past; in the second case the selectors
+                // start 2 nucleotides early, so every word formed is an aligned stage word either way -- and the case is the
+                // same for every row of a pass (rows 2 lane + pass), so the branch does not diverge.
+                const uint32_t row = 2u * lane + (it & 1u);
+                const uint32_t mis = (w & 1u) ? 0u : ((row * w) & 2u);
+                const uint32_t on = 8u + (use_rev ? 8u * n_chunk - o - w : o) - mis;
+                const uint32_t na = (use_rev ? nr_base : nf_base) + ((on >> 3) << 2), sh = (on & 7u) * 4u;
+                constexpr int NN = 2 * NW;                              // nibble words of a window
+                constexpr bool EXTRA = W == 0 || (W + 2 + 3) / 4 > 2 * NN;  // a misaligned row of 16 NW nucleotides reaches one word further
+                constexpr int NL = 2 * NN + (EXTRA ? 1 : 0);
+                uint32_t N[NN + 2];
+#pragma unroll
+                for (int k = 0; k <= NN + (EXTRA ? 1 : 0); k++) N[k] = lds_u32(na + 4 * k);
+                const uint32_t dst = stage_base + row * w - mis;  // 4-byte aligned for even w
+                uint32_t Lw[NL];  // the row's letters, four per PRMT
+#pragma unroll
+                for (int m = 0; m < NL; m += 2) {
+                    const uint32_t sel = __funnelshift_r(N[m >> 1], N[(m >> 1) + 1], sh);  // nucleotides 4m .. 4m + 7 (- mis)
+                    Lw[m] = __byte_perm(T, 0, sel);
+                    if (m + 1 < NL) Lw[m + 1] = __byte_perm(T, 0, sel >> 16);
+                }
+                if ((w & 1u) == 0) {
+                    if (mis == 0) {
+#pragma unroll
+                        for (int m = 0; m < NL; m++) {
+                            const uint32_t j = 4 * m;  // row bytes j .. j + 3
+                            if ((W && j + 4 <= (uint32_t)W) || j + 4 <= w) sts_u32(dst + j, Lw[m]);
+                            else if (j < w) sts_u16(dst + j, Lw[m]);  // w % 4 == 2: the last two bytes
+                        }
+                    } else {
+                        sts_u16(dst + 2, Lw[0] >> 16);  // row bytes 0, 1
+#pragma unroll
+                        for (int m = 1; m < NL; m++) {
+                            const uint32_t j = 4 * m - 2;  // row bytes j .. j + 3
+                            if ((W && j + 4 <= (uint32_t)W) || j + 4 <= w) sts_u32(dst + 4 * m, Lw[m]);
+                            else if (j < w) sts_u16(dst + 4 * m, Lw[m]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < NL; m++) {
+                        const uint32_t j = 4 * m;
+                        if (j < w) {
+                            const uint32_t four = Lw[m], left = w - j;
+                            sts_u8(dst + j, four);
+                            if (left > 1) sts_u8(dst + j + 1, four >> 8);
+                            if (left > 2) sts_u8(dst + j + 2, four >> 16);
+                            if (left > 3) sts_u8(dst + j + 3, four >> 24);
+                        }
+                    }
+                }
+            }
+            }  // l < cnt
+            if constexpr (ROWS) {
+                if ((it & 1u) != 0) {
+                    // ---- copy-out of 64 rows: contiguous bytes at out + (g0 + first) * w (16-byte aligned: 64 w is a multiple of 16) ----
+                    __syncwarp();
+                    const uint32_t first = 64u * (it >> 1), nbytes = min(64u, cnt - first) * w, body = nbytes >> 4;
+                    uint8_t* const gdst = p.out + (g0 + first) * w;
+                    uint4* gp = reinterpret_cast<uint4*>(gdst) + lane;
+                    uint32_t sa = stage_base + 16u * lane;
+#pragma unroll 2
+                    for (uint32_t c = lane; c < body; c += 32, gp += 32, sa += 512u) stg_stream(gp, lds_u128(sa));
+                    for (uint32_t b = 16 * body + lane; b < nbytes; b += 32) gdst[b] = stage[b];
+                    __syncwarp();
+                }
             }
         }
         __syncwarp();

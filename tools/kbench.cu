@@ -160,56 +160,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
         printf("revcomp  thr %d unroll %d occ %d grid %u  %zu nt  %.4f ms  %.1f GB/s algorithmic  checksum %016llx\n", RCT, RC_UNROLL, occ_rc, g2, n_rc, ms, 2.0 * n_rc / ms / 1e6, acc);
     }
-    // canonical windows (w = 42) over one long sequence: n_cw windows, 42 bytes each
-    {
-        const size_t n_cw = std::min<size_t>(total, 40000000), w = 42, nwin = n_cw - w + 1;
-        if (out_bytes >= nwin * w) {
-            CanonParams q{};
-            q.dna = dna;
-            q.n_seq = 1;
-            q.seq_len = n_cw;
-            q.w = (uint32_t)w;
-            q.forward_only = 0;
-            q.out = out;
-            q.decode = d_decode;
-            uint8_t* d_cp;
-            CK(cudaMalloc(&d_cp, PAIR_ENTRIES));
-            CK(cudaMemcpy(d_cp, T.canon_pair[0], PAIR_ENTRIES, cudaMemcpyHostToDevice));
-            q.pair = d_cp;
-            q.pair_coef = 1u | (PAIR_K1_ASCII << 16);
-            q.and_need = 0x40404040u;
-            q.or_forbid = 0x80808080u;
-            q.filler = 0x41u;
-            q.letters = 'A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24);
-            q.err_key = d_err;
-            const size_t smem_c = (size_t)CanonWarpLayout((uint32_t)w).total_bytes * CANON_WARPS + PAIR_ENTRIES;
-            CK(cudaFuncSetAttribute(canonical_windows_kernel<3, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-            const uint64_t blocks = (nwin + CANON_THREADS - 1) / CANON_THREADS;
-#ifndef KB_CW_OCC
-#define KB_CW_OCC 4
-#endif
-            int occ_c = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, canonical_windows_kernel<3, 42>, CANON_THREADS, smem_c));
-#ifdef KB_CW_OCC_FORCE
-            occ_c = KB_CW_OCC_FORCE;
-#endif
-            const unsigned gc = (unsigned)std::min<uint64_t>(blocks, (uint64_t)sms * occ_c);
-            printf("canonical occ %d smem %zu\n", occ_c, smem_c);
-            canonical_windows_kernel<3, 42><<<gc, CANON_THREADS, smem_c>>>(q);
-            CK(cudaDeviceSynchronize());
-            CK(cudaEventRecord(e0));
-            for (int i = 0; i < 3; i++) canonical_windows_kernel<3, 42><<<gc, CANON_THREADS, smem_c>>>(q);
-            CK(cudaEventRecord(e1));
-            CK(cudaEventSynchronize(e1));
-            CK(cudaEventElapsedTime(&ms, e0, e1));
-            ms /= 3;
-            CK(cudaMemset(d_acc, 0, 8));
-            xorsum_kernel<<<sms * 8, 256>>>((const uint32_t*)out, nwin * w / 4, d_acc);
-            CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
-            printf("canonical_windows w=42  %zu windows  %.3f ms  %.1f GB/s algorithmic (43 B/window)  %.2f Gwin/s  checksum %016llx\n", nwin, ms,
-                   nwin * 43.0 / ms / 1e6, nwin / (double)ms / 1e6, acc);
-        }
-    }
+    // (canonical windows / keys are timed through the library: tools/canon_keys_bench.py)
     CK(cudaDeviceSynchronize());
     return 0;
 }
