@@ -1310,9 +1310,9 @@ __global__ void __launch_bounds__(CTILE_THREADS) canonical_tile_kernel(const Can
         // rows: within every 64 windows lane handles 2 lane and 2 lane + 1: for even w all rows of one pass share their
         //       alignment in the stage, and the rows of a pass are an odd number of words apart (no bank conflicts)
         const uint32_t n_it = ROWS ? 2u * ((cnt + 63u) >> 6) : (cnt + 31u) >> 5;
+        uint32_t l = ROWS ? 2u * lane : lane;
 #pragma unroll 1
-        for (uint32_t it = 0; it < n_it; it++) {
-            const uint32_t l = ROWS ? 64u * (it >> 1) + 2u * lane + (it & 1u) : 32u * it + lane;
+        for (uint32_t it = 0; it < n_it; it++, l += ROWS ? ((it & 1u) ? 1u : 63u) : 32u) {
             if (l < cnt) {
             uint32_t o;  // position inside the streams: every sequence seam before the window skips w - 1 positions
             if (long_seqs) o = o_first + l + (l >= l_seam ? w - 1u : 0u);
@@ -1458,9 +1458,20 @@ __global__ void __launch_bounds__(CTILE_THREADS) canonical_tile_kernel(const Can
                     uint8_t* const gdst = p.out + (g0 + first) * w;
                     uint4* gp = reinterpret_cast<uint4*>(gdst) + lane;
                     uint32_t sa = stage_base + 16u * lane;
-#pragma unroll 2
-                    for (uint32_t c = lane; c < body; c += 32, gp += 32, sa += 512u) stg_stream(gp, lds_u128(sa));
-                    for (uint32_t b = 16 * body + lane; b < nbytes; b += 32) gdst[b] = stage[b];
+                    bool done = false;
+                    if constexpr (W != 0) {
+                        if (nbytes == 64u * (uint32_t)W) {  // a full group of a compile-time window length: 4 W granules, unrolled
+                            constexpr uint32_t BODY = 4u * (uint32_t)W;
+#pragma unroll
+                            for (uint32_t k = 0; k < (BODY + 31u) / 32u; k++)
+                                if (32u * k + 32u <= BODY || lane + 32u * k < BODY) stg_stream(gp + 32 * k, lds_u128(sa + 512u * k));
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        for (uint32_t c = lane; c < body; c += 32, gp += 32, sa += 512u) stg_stream(gp, lds_u128(sa));
+                        for (uint32_t b = 16 * body + lane; b < nbytes; b += 32) gdst[b] = stage[b];
+                    }
                     __syncwarp();
                 }
             }
