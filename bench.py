@@ -422,8 +422,8 @@ def main():
                 "workload": f"canonical 42-nt windows of {n_seq} x {seq_len}-nt ACGT sequences per GPU (benches/canonical.rs shape)",
                 "windows_per_s": world * nwin / (cw_ms * 1e-3), "ms": cw_ms,
                 "roofline": {"bound": "hbm", "achieved": cw_gbs, "peak": peak, "unit": "GB/s", "frac": cw_gbs / peak, "traffic": None,
-                             "kernel": "canonical_windows_kernel<3>", "algorithmic_bytes_per_launch": nwin * (1 + w),
-                             "note": "ALU-bound (about 500 thread-instructions per 42-byte window), not HBM-bound"}}
+                             "kernel": "canonical_tile_kernel<3, 42, rows>", "algorithmic_bytes_per_launch": nwin * (1 + w),
+                             "note": "issue-bound (about 280 thread-instructions per 42-byte window), not HBM-bound"}}
             # the same windows as fixed-width keys: 64-bit fingerprints, then lossless 16-byte packed windows (two bit planes)
             keys = {}
             for kind, label, kb in ((N.CANON_KEY_FP64, "fingerprint_64", 8), (N.CANON_KEY_PACKED, "packed_2bit", 16)):
@@ -440,7 +440,7 @@ def main():
                 k_gbs = nwin * (1 + kb) / (k_ms * 1e-3) / 1e9
                 keys[label] = {"ms": k_ms, "windows_per_s": world * nwin / (k_ms * 1e-3), "key_bytes": kb,
                                "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": None,
-                                            "kernel": f"canonical_keys_kernel<2, 42, {kind}>", "algorithmic_bytes_per_launch": nwin * (1 + kb),
+                                            "kernel": f"canonical_tile_kernel<3, 42, {kind}>", "algorithmic_bytes_per_launch": nwin * (1 + kb),
                                             "note": "ALU-bound (about 150 thread-instructions per window), not HBM-bound"}}
             extra["canonical_window_keys"] = {
                 "workload": f"one key per canonical 42-nt window of the same {n_seq} x {seq_len}-nt sequences (SURVEY 8(f) rank 3)",
