@@ -1431,9 +1431,16 @@ static ExpandParams expansion_params(qd_ctx* c, int enc, const uint8_t* windows_
 }
 
 // size_hint per window + exclusive scan of the rows each window emits
-static int expansion_count_dev(qd_ctx* c, const ExpandParams& p, cudaStream_t s) {
-    const unsigned grid = (unsigned)std::min<uint64_t>((p.n_win + 255) / 256, (uint64_t)c->sm_count * 16);
-    expansion_count_kernel<<<grid, 256, 0, s>>>(p);
+static int expansion_count_dev(qd_ctx* c, const ExpandParams& p, int enc, cudaStream_t s) {
+    if (p.desc && p.w <= 64) {  // fast path: warp tiles of 32 windows, four letters per step
+        const uint64_t tiles = (p.n_win + 31) / 32;
+        const unsigned grid = (unsigned)std::min<uint64_t>((tiles + EXP_WARPS - 1) / EXP_WARPS, (uint64_t)c->sm_count * 8);
+        if (enc == QD_ENC_ASCII) expansion_count_tiles_kernel<true><<<grid, 32 * EXP_WARPS, 0, s>>>(p, c->d_parse_pair);
+        else expansion_count_tiles_kernel<false><<<grid, 32 * EXP_WARPS, 0, s>>>(p, nullptr);
+    } else {
+        const unsigned grid = (unsigned)std::min<uint64_t>((p.n_win + 255) / 256, (uint64_t)c->sm_count * 16);
+        expansion_count_kernel<<<grid, 256, 0, s>>>(p);
+    }
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     return device_exclusive_scan<1>(c, p.emit, p.n_win, const_cast<uint64_t*>(p.out_index), c->block_sums, s);
@@ -1444,7 +1451,8 @@ static int expansion_write_tiles_dev(qd_ctx* c, ExpandParams p, uint8_t* out_dev
     p.row_cap = row_cap;
     const uint64_t tiles = (p.n_win + 31) / 32;
     const unsigned grid = (unsigned)std::min<uint64_t>((tiles + EXP_WARPS - 1) / EXP_WARPS, (uint64_t)c->sm_count * 6);
-    expansion_write_tiles_kernel<<<grid, 32 * EXP_WARPS, 0, s>>>(p);
+    if (p.w == 42) expansion_write_tiles_kernel<42><<<grid, 32 * EXP_WARPS, 0, s>>>(p);  // the window length of benches/expansions.rs: unrolled
+    else expansion_write_tiles_kernel<0><<<grid, 32 * EXP_WARPS, 0, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
@@ -1462,7 +1470,7 @@ extern "C" int qd_expansion_windows_dev(qd_ctx* c, int enc, const uint8_t* windo
     QD_CUDA(c, c->aux3.reserve(n_win * 8));  // descriptors
     ExpandParams p = expansion_params(c, enc, windows_dev, n_win, w, max_expansions, counts_dev, c->aux1.as<uint64_t>(), out_index_dev,
                                       c->aux3.as<uint64_t>());
-    if (int rc = expansion_count_dev(c, p, s)) return rc;
+    if (int rc = expansion_count_dev(c, p, enc, s)) return rc;
     if (out_dev) return expansion_write_tiles_dev(c, p, out_dev, out_capacity_rows, s);
     return QD_OK;
 }
@@ -1489,7 +1497,7 @@ extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, 
     if (int rc = reset_err_key(c, s)) return rc;
     ExpandParams p = expansion_params(c, enc, c->in.as<uint8_t>(), n_win, w, max_expansions, c->aux0.as<uint64_t>(), c->aux1.as<uint64_t>(),
                                       c->aux2.as<uint64_t>(), fast ? c->aux3.as<uint64_t>() : nullptr);
-    if (int rc = expansion_count_dev(c, p, s)) return rc;
+    if (int rc = expansion_count_dev(c, p, enc, s)) return rc;
     QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->aux2.as<uint64_t>() + n_win, 8, cudaMemcpyDeviceToHost, s));
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises

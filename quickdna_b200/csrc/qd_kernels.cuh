@@ -1565,75 +1565,238 @@ __global__ void __launch_bounds__(256) expansion_write_kernel(const ExpandParams
     }
 }
 
-// Fast path (w <= 64, at most EXP_DESC_MAX ambiguous positions per emitted window): a warp owns 32 consecutive windows,
-// keeps their bytes in shared memory, and produces their rows 32 at a time -- one row per lane: copy the window
-// upper-cased (concrete positions are already final), patch the ambiguous positions with this row's odometer digits,
-// then drain the 32 staged rows with aligned 128-bit stores (head / tail bytes of the chunk individually).
+constexpr uint32_t PARSE_PAIR_SLOW = 0x40;  // letter-pair table of the parse (qd_tables.hpp): the letter is not a nucleotide of the alphabet
+// ---- fast path (w <= 64, max_expansions < 128): warp tiles of 32 windows -------------------------------------------
 constexpr int EXP_WARPS = 8;
+
+// the tile's cnt * w source bytes into shared memory with aligned 128-bit loads; returns the offset of window 0 in `raw`
+// (bytes before / after the buffer read as `filler`, a valid concrete base, and are never looked at)
+__device__ __forceinline__ uint32_t expansion_stage_windows(const ExpandParams& p, uint64_t i0, uint32_t cnt, uint8_t* raw, int lane, uint32_t filler) {
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.windows), hi = lo + p.n_win * p.w;
+    const uintptr_t src = lo + i0 * p.w, a0 = src & ~(uintptr_t)15;
+    const uint32_t n_gran = (uint32_t)((src + (uintptr_t)cnt * p.w - a0 + 15) >> 4);
+    for (uint32_t c = lane; c < n_gran; c += 32) {
+        const uintptr_t a = a0 + 16 * (uintptr_t)c;
+        uint4 v;
+        if (a >= lo && a + 16 <= hi) {
+            v = ldg_stream(reinterpret_cast<const void*>(a));
+        } else {
+            uint32_t wds[4] = {0, 0, 0, 0};
+#pragma unroll 1
+            for (int t = 0; t < 16; t++) {
+                const uintptr_t b = a + t;
+                wds[t >> 2] |= ((b >= lo && b < hi) ? (uint32_t)*reinterpret_cast<const uint8_t*>(b) : filler) << (8 * (t & 3));
+            }
+            v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+        *reinterpret_cast<uint4*>(raw + 16 * c) = v;
+    }
+    return (uint32_t)(src - a0);
+}
+
+// size_hint, rows to emit and the ambiguity descriptor of every window (src/expansions.rs:96-107): lane = window.
+// Four letters per step: masks from the letter-pair table (ASCII) or the bytes themselves (MASK); a word without an
+// ambiguity code (m & (m - 1) == 0 in every byte) costs nothing more.
+template <bool ASCII>
+__global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(const ExpandParams p, const uint16_t* __restrict__ pair) {
+    __shared__ __align__(16) uint8_t raw_s[EXP_WARPS][32 * 64 + 48];
+    __shared__ __align__(16) uint16_t pair_s[ASCII ? PAIR_ENTRIES : 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ASCII) {
+        for (int i = threadIdx.x; i < (int)PAIR_ENTRIES; i += 32 * EXP_WARPS) pair_s[i] = __ldg(pair + i);
+        __syncthreads();
+    }
+    uint8_t* const raw = raw_s[warp];
+    const uint32_t w = p.w, n_words = (w + 3) >> 2;
+    const uint32_t pair_base = smem_u32(pair_s), pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);  // 16-bit entries
+    const uint32_t filler = ASCII ? 0x41u : 0x01u;
+    const uint64_t n_tiles = (p.n_win + 31) / 32;
+    for (uint64_t tile = (uint64_t)blockIdx.x * EXP_WARPS + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * EXP_WARPS) {
+        const uint64_t i0 = tile * 32;
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, p.n_win - i0);
+        const uint32_t off0 = expansion_stage_windows(p, i0, cnt, raw, lane, filler);
+        if (lane == 0) *reinterpret_cast<uint4*>(raw + ((off0 + cnt * w + 15) & ~15u)) = make_uint4(0, 0, 0, 0);  // the word past the last row
+        __syncwarp();
+        if (lane < (int)cnt) {
+            const uint32_t off = off0 + lane * w;
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(raw) + (off >> 2);
+            const uint32_t sh = (off & 3u) * 8u;
+            // phase A, the same instructions for every lane: a bit per position that holds an ambiguity code
+            uint32_t amb_lo = 0, amb_hi = 0;
+#pragma unroll 1
+            for (uint32_t k = 0; k < n_words; k++) {
+                uint32_t x = __funnelshift_r(sw[k], sw[k + 1], sh);
+                const uint32_t nb = min(4u, w - 4u * k);  // bytes of this word inside the window
+                if (nb < 4) x = (x & ((1u << (8 * nb)) - 1u)) | ((filler * 0x01010101u) << (8 * nb));
+                uint32_t m4;
+                bool bad;
+                if (ASCII) {
+                    const uint32_t u = x & 0x1f1f1f1fu;
+                    m4 = lds_u16(dp2a_lo(pair_coef, u, pair_base)) | (lds_u16(dp2a_hi(pair_coef, u, pair_base)) << 16);
+                    bad = ((m4 & (PARSE_PAIR_SLOW * 0x01010101u)) | ((x & 0x40404040u) ^ 0x40404040u) | (x & 0x80808080u)) != 0;
+                } else {
+                    m4 = x;
+                    bad = ((x & 0xf0f0f0f0u) | ((x - 0x01010101u) & ~x & 0x80808080u)) != 0;
+                }
+                if (bad) {  // exact: the first byte of this word that is not a nucleotide code
+                    for (uint32_t t = 0; t < nb; t++) {
+                        const uint32_t b = (x >> (8 * t)) & 0xffu;
+                        if (__ldg(p.to_mask + b) == 0) {
+                            atomicMin(p.err_key, (unsigned long long)((i0 + lane) * w + 4u * k + t));
+                            break;
+                        }
+                    }
+                    continue;  // (the call fails; the counts of this window do not matter)
+                }
+                // bytes with more than one bit -> one bit each -> a nibble
+                uint32_t t4 = m4 & (m4 - 0x01010101u) & 0x0f0f0f0fu;
+                t4 = (t4 | (t4 >> 1) | (t4 >> 2) | (t4 >> 3)) & 0x01010101u;
+                const uint32_t nib = (t4 * 0x10204080u) >> 28;  // byte t -> bit t
+                if (k < 8) amb_lo |= nib << (4 * k);
+                else amb_hi |= nib << (4 * (k - 8));
+            }
+            // phase B: the few ambiguous positions, last first (the fastest odometer digit)
+            uint64_t size = 1, desc = 0;
+            uint32_t n_amb = 0;
+            bool overflow = false;
+            while (amb_lo | amb_hi) {
+                const uint32_t j = amb_hi ? 63u - __clz(amb_hi) : 31u - __clz(amb_lo);
+                if (j >= 32) amb_hi &= ~(1u << (j - 32));
+                else amb_lo &= ~(1u << j);
+                const uint32_t m = __ldg(p.to_mask + raw[off + j]);
+                const uint32_t states = __popc(m);
+                if (n_amb < EXP_DESC_MAX) desc |= (uint64_t)((j & 63u) | (m << 6)) << (10 * n_amb);
+                n_amb++;
+                overflow |= __umul64hi(size, (uint64_t)states) != 0;
+                size *= states;
+            }
+            const uint64_t count = overflow ? 0xffffffffffffffffull : size;
+            p.counts[i0 + lane] = count;
+            p.emit[i0 + lane] = (count <= p.max_expansions) ? count : 0;
+            p.desc[i0 + lane] = desc | ((uint64_t)min(n_amb, 15u) << 60);
+        }
+        __syncwarp();
+    }
+}
+
+// Rows of the fast path.  A warp owns 32 consecutive windows: their bytes, descriptors and first rows go to shared memory
+// once; then 32 output rows at a time -- lane = row -- are copied from their window with whole 32-bit words aligned to the
+// DESTINATION (upper-cased on the way: concrete positions are then final), patched at the ambiguous positions with the
+// row's odometer digits, and drained with aligned 128-bit stores (head / tail bytes of the chunk individually).
+// The window of a row comes from two ballots over the tile's non-empty windows instead of a search, the digits from
+// 7-bit arithmetic (a row index inside a window is < 128).
 struct ExpWarpSmem {
-    alignas(16) uint8_t win[32 * 64 + 16];
+    alignas(16) uint8_t win[32 * 64 + 48];
     alignas(16) uint8_t stage[32 * 64 + 32];
-    uint64_t first_row[33];
     uint64_t desc[32];
+    uint32_t ne_first[32];  // first row (relative to the tile's first row) of the k-th window that emits rows
+    uint32_t ne_win[32];    // ... and which window that is
 };
 
+// W: the window length when it is a compile-time constant with W % 4 == 2 (42: benches/expansions.rs), 0 = p.w
+template <int W>
 __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_write_tiles_kernel(const ExpandParams p) {
+    static_assert(W == 0 || (W % 4 == 2 && W <= 64), "the unrolled row copy is written for W = 2 mod 4");
     __shared__ ExpWarpSmem SM[EXP_WARPS];
+    __shared__ uint8_t letter_of[64];  // mask * 4 + digit -> the letter of the digit-th base of the mask (possibilities() order A,T,C,G)
     const int lane = threadIdx.x & 31;
     ExpWarpSmem& S = SM[threadIdx.x >> 5];
-    const uint32_t w = p.w;
+    if (threadIdx.x < 64) {
+        uint32_t mm = threadIdx.x >> 2;
+        for (uint32_t t = 0; t < (threadIdx.x & 3u); t++) mm &= mm - 1u;
+        letter_of[threadIdx.x] = mm ? (uint8_t)(p.letters >> (8 * (__ffs(mm) - 1))) : (uint8_t)0;
+    }
+    __syncthreads();
+    const uint32_t w = W ? (uint32_t)W : p.w;
+    const uint32_t filler = 0x41u;
+    const uint32_t win_base = smem_u32(S.win), stage_base = smem_u32(S.stage), letter_base = smem_u32(letter_of);
     const uint64_t n_tiles = (p.n_win + 31) / 32;
     for (uint64_t tile = (uint64_t)blockIdx.x * EXP_WARPS + (threadIdx.x >> 5); tile < n_tiles; tile += (uint64_t)gridDim.x * EXP_WARPS) {
         const uint64_t i0 = tile * 32;
         const uint32_t cnt = (uint32_t)min((uint64_t)32, p.n_win - i0);
-        // geometry of my window, the tile's windows into shared memory
-        S.first_row[lane] = p.out_index[min(i0 + lane, p.n_win)];
-        if (lane == 0) S.first_row[32] = p.out_index[min(i0 + 32, p.n_win)];
+        // geometry: first rows relative to the tile's first row (a tile emits fewer than 32 * 128 rows)
+        const uint64_t my_first = p.out_index[min(i0 + lane, p.n_win)], my_next = p.out_index[min(i0 + lane + 1, p.n_win)];
+        const uint64_t row_lo = __shfl_sync(0xffffffffu, my_first, 0);
+        const uint32_t rel = (uint32_t)(my_first - row_lo), emit = lane < (int)cnt ? (uint32_t)(my_next - my_first) : 0u;
+        const uint32_t total = __shfl_sync(0xffffffffu, rel + emit, (int)cnt - 1);
+        const uint32_t ne = __ballot_sync(0xffffffffu, emit != 0);
+        const uint32_t m = __popc(ne);
+        if (emit != 0) {
+            const uint32_t k = __popc(ne & ((1u << lane) - 1u));
+            S.ne_first[k] = rel;
+            S.ne_win[k] = lane;
+        }
         S.desc[lane] = lane < (int)cnt ? p.desc[i0 + lane] : 0;
-        const uint8_t* src = p.windows + i0 * w;  // 32 w is a multiple of 32, but `windows` itself may be unaligned: bytes
-        for (uint32_t b = lane; b < cnt * w; b += 32) S.win[b] = __ldg(src + b);
+        const uint32_t off0 = expansion_stage_windows(p, i0, cnt, S.win, lane, filler);
         __syncwarp();
-        const uint64_t row_lo = S.first_row[0], row_hi = S.first_row[cnt];
-        for (uint64_t r0 = row_lo; r0 < row_hi; r0 += 32) {
-            const uint32_t nrows = (uint32_t)min((uint64_t)32, row_hi - r0);
-            uint8_t* gdst = p.out + r0 * w;
+        const uint32_t my_ne_first = lane < (int)m ? S.ne_first[lane] : 0xffffffffu;
+        uint8_t* gdst = p.out + row_lo * w;
+        for (uint32_t r0 = 0; r0 < total; r0 += 32, gdst += 32 * w) {
+            const uint32_t nrows = min(32u, total - r0);
+            if (row_lo + r0 + nrows > p.row_cap) break;  // caller's buffer is too small: out_index[n_win] tells how much was needed
             const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
-            if (r0 + nrows > p.row_cap) break;  // caller's buffer is too small: out_index[n_win] tells how much was needed
+            // the window of every row of the chunk: how many non-empty windows start at or before row r0, and a bit per
+            // window that starts inside the chunk
+            const uint32_t base_k = __popc(__ballot_sync(0xffffffffu, my_ne_first <= r0)) - 1u;
+            const uint32_t starts = __reduce_or_sync(0xffffffffu, (my_ne_first > r0 && my_ne_first < r0 + 32u) ? 1u << (my_ne_first - r0) : 0u);
             if (lane < (int)nrows) {
-                const uint64_t row = r0 + lane;
-                uint32_t lo = 0, hi = cnt - 1;  // window of this row: largest j with first_row[j] <= row (skipped windows repeat)
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi + 1) >> 1;
-                    if (S.first_row[mid] <= row) lo = mid; else hi = mid - 1;
-                }
-                uint64_t k = row - S.first_row[lo];
-                const uint64_t d = S.desc[lo];
-                const uint8_t* wsrc = S.win + lo * w;
-                uint8_t* dst = S.stage + phase + lane * w;
-                // upper case (masks are unchanged); two bytes at a time when every row starts at an even address
-                if (((w | phase) & 1u) == 0) {
-                    for (uint32_t j = 0; j < w; j += 2)
-                        *reinterpret_cast<uint16_t*>(dst + j) = *reinterpret_cast<const uint16_t*>(wsrc + j) & (uint16_t)0xdfdf;
+                const uint32_t kidx = base_k + __popc(starts & (0xffffffffu >> (31 - lane)));
+                const uint32_t j = S.ne_win[kidx];
+                uint32_t k = r0 + lane - S.ne_first[kidx];  // the row's index inside its window: < 128
+                const uint64_t d = S.desc[j];
+                const uint32_t s0 = off0 + j * w, d0 = phase + lane * w;
+                if (W != 0 && ((phase | off0) & 1u) == 0) {
+                    // rows and windows start at even addresses: the row is 10 aligned destination words plus one half-word,
+                    // at its front (row starts mid-word) or at its back
+                    const uint32_t hb = d0 & 2u, hpos = hb ? 0u : (uint32_t)W - 2u;
+                    sts_u16(stage_base + d0 + hpos, lds_u16(win_base + s0 + hpos) & 0xdfdfu);
+                    const uint32_t sb = s0 + hb, sh = (sb & 3u) * 8u, sa = win_base + (sb & ~3u), da = stage_base + d0 + hb;
+                    uint32_t prev = lds_u32(sa);
+#pragma unroll
+                    for (int q = 0; q < (W - 2) / 4; q++) {
+                        const uint32_t next = lds_u32(sa + 4 * q + 4);
+                        sts_u32(da + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                        prev = next;
+                    }
                 } else {
-                    for (uint32_t j = 0; j < w; j++) dst[j] = wsrc[j] & 0xdfu;
+                    // head bytes up to the first aligned destination word, whole words, tail bytes
+                    const uint32_t head = min(w, (4u - (d0 & 3u)) & 3u);
+                    for (uint32_t b = 0; b < head; b++) S.stage[d0 + b] = S.win[s0 + b] & 0xdfu;
+                    const uint32_t n_body = (w - head) >> 2, sb = s0 + head, sh = (sb & 3u) * 8u;
+                    const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.win) + (sb >> 2);
+                    uint32_t* dw = reinterpret_cast<uint32_t*>(S.stage + d0 + head);
+                    uint32_t prev = sw[0];
+#pragma unroll 1
+                    for (uint32_t q = 0; q < n_body; q++) {
+                        const uint32_t next = sw[q + 1];
+                        dw[q] = __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu;
+                        prev = next;
+                    }
+                    for (uint32_t b = head + 4u * n_body; b < w; b++) S.stage[d0 + b] = S.win[s0 + b] & 0xdfu;
                 }
                 const uint32_t n_amb = (uint32_t)(d >> 60);
-                for (uint32_t e = 0; e < n_amb; e++) {
-                    const uint32_t f = (uint32_t)(d >> (10 * e)) & 0x3ffu, pos = f & 63u, m = f >> 6;
-                    const uint32_t states = __popc(m);
-                    const uint32_t digit = (uint32_t)(k % states);
-                    k /= states;
-                    uint32_t mm = m;  // digit-th set bit of m, ascending (possibilities() order A,T,C,G)
-                    for (uint32_t t = 0; t < digit; t++) mm &= mm - 1;
-                    dst[pos] = (uint8_t)(p.letters >> (8 * (__ffs(mm) - 1)));
+#pragma unroll
+                for (uint32_t e = 0; e < EXP_DESC_MAX; e++) {
+                    if (e < n_amb) {
+                        const uint32_t f = (uint32_t)(d >> (10 * e)) & 0x3ffu, pos = f & 63u, mask = f >> 6;
+                        const uint32_t states = __popc(mask);
+                        const uint32_t quo = states == 2u ? k >> 1 : (states == 4u ? k >> 2 : (k * 171u) >> 9);  // k / 3 for k < 128
+                        const uint32_t digit = k - quo * states;
+                        k = quo;
+                        sts_u8(stage_base + d0 + pos, lds_u8(letter_base + mask * 4u + digit));
+                    }
                 }
             }
             __syncwarp();
             const uint32_t nbytes = nrows * w;
-            const uint32_t head = min(nbytes, (16u - phase) & 15u), body = (nbytes - head) >> 4;
-            if (lane < (int)head) gdst[lane] = S.stage[phase + lane];
-            for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(S.stage + phase + head + 16 * c));
-            const uint32_t done = head + 16 * body;
+            const uint32_t hd = min(nbytes, (16u - phase) & 15u), body = (nbytes - hd) >> 4;
+            if (lane < (int)hd) gdst[lane] = S.stage[phase + lane];
+            {
+                uint4* gp = reinterpret_cast<uint4*>(gdst + hd) + lane;
+                uint32_t sa = stage_base + phase + hd + 16u * lane;
+                for (uint32_t c = lane; c < body; c += 32, gp += 32, sa += 512u) stg_stream(gp, lds_u128(sa));
+            }
+            const uint32_t done = hd + 16 * body;
             if (lane < (int)(nbytes - done)) gdst[done + lane] = S.stage[phase + done + lane];
             __syncwarp();
         }
@@ -1791,7 +1954,6 @@ __global__ void __launch_bounds__(256) warp_map_kernel(const uint64_t* __restric
 constexpr int PARSE_THREADS = 256;
 constexpr int PARSE_BLOCK_BYTES = PARSE_THREADS * 16;  // one aligned 16-byte granule per thread
 constexpr uint32_t PARSE_SKIP = 0x80;                  // table value of ' ' and '\t' (0 = invalid, else the mask)
-constexpr uint32_t PARSE_PAIR_SLOW = 0x40;             // pair-table flag: the letter is not a nucleotide of the alphabet
 
 struct ParseParams {
     const uint8_t* in;
