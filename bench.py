@@ -565,7 +565,7 @@ def main():
                             "(size_hint kernel + scan + write kernel per call)",
                 "rows_per_s": world * n_rows / (ex_ms * 1e-3), "windows_per_s": world * n_win / (ex_ms * 1e-3), "ms": ex_ms,
                 "roofline": {"bound": "hbm", "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak, "traffic": None,
-                             "kernel": "expansion_count_kernel + expansion_write_tiles_kernel", "algorithmic_bytes_per_launch": ex_bytes}}
+                             "kernel": "expansion_count_tiles_kernel<ascii, 42> + scan + expansion_write_tiles_kernel<42>", "algorithmic_bytes_per_launch": ex_bytes}}
             del win, c_d, oi_d
 
     # ---- e2e: the host-pointer C-ABI call on pinned host buffers (H2D + kernels + D2H timed)

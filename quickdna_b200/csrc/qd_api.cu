@@ -1435,8 +1435,13 @@ static int expansion_count_dev(qd_ctx* c, const ExpandParams& p, int enc, cudaSt
     if (p.desc && p.w <= 64) {  // fast path: warp tiles of 32 windows, four letters per step
         const uint64_t tiles = (p.n_win + 31) / 32;
         const unsigned grid = (unsigned)std::min<uint64_t>((tiles + EXP_WARPS - 1) / EXP_WARPS, (uint64_t)c->sm_count * 8);
-        if (enc == QD_ENC_ASCII) expansion_count_tiles_kernel<true><<<grid, 32 * EXP_WARPS, 0, s>>>(p, c->d_parse_pair);
-        else expansion_count_tiles_kernel<false><<<grid, 32 * EXP_WARPS, 0, s>>>(p, nullptr);
+        if (enc == QD_ENC_ASCII) {
+            if (p.w == 42) expansion_count_tiles_kernel<true, 42><<<grid, 32 * EXP_WARPS, 0, s>>>(p, c->d_parse_pair);  // benches/expansions.rs: unrolled
+            else expansion_count_tiles_kernel<true, 0><<<grid, 32 * EXP_WARPS, 0, s>>>(p, c->d_parse_pair);
+        } else {
+            if (p.w == 42) expansion_count_tiles_kernel<false, 42><<<grid, 32 * EXP_WARPS, 0, s>>>(p, nullptr);
+            else expansion_count_tiles_kernel<false, 0><<<grid, 32 * EXP_WARPS, 0, s>>>(p, nullptr);
+        }
     } else {
         const unsigned grid = (unsigned)std::min<uint64_t>((p.n_win + 255) / 256, (uint64_t)c->sm_count * 16);
         expansion_count_kernel<<<grid, 256, 0, s>>>(p);

@@ -1597,7 +1597,8 @@ __device__ __forceinline__ uint32_t expansion_stage_windows(const ExpandParams& 
 // size_hint, rows to emit and the ambiguity descriptor of every window (src/expansions.rs:96-107): lane = window.
 // Four letters per step: masks from the letter-pair table (ASCII) or the bytes themselves (MASK); a word without an
 // ambiguity code (m & (m - 1) == 0 in every byte) costs nothing more.
-template <bool ASCII>
+// W: the window length when it is a compile-time constant (42: benches/expansions.rs), 0 = p.w
+template <bool ASCII, int W>
 __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(const ExpandParams p, const uint16_t* __restrict__ pair) {
     __shared__ __align__(16) uint8_t raw_s[EXP_WARPS][32 * 64 + 48];
     __shared__ __align__(16) uint16_t pair_s[ASCII ? PAIR_ENTRIES : 8];
@@ -1607,8 +1608,9 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(c
         __syncthreads();
     }
     uint8_t* const raw = raw_s[warp];
-    const uint32_t w = p.w, n_words = (w + 3) >> 2;
+    const uint32_t w = W ? (uint32_t)W : p.w, n_words = (w + 3) >> 2;
     const uint32_t pair_base = smem_u32(pair_s), pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);  // 16-bit entries
+    const uint32_t raw_base = smem_u32(raw);
     const uint32_t filler = ASCII ? 0x41u : 0x01u;
     const uint64_t n_tiles = (p.n_win + 31) / 32;
     for (uint64_t tile = (uint64_t)blockIdx.x * EXP_WARPS + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * EXP_WARPS) {
@@ -1619,13 +1621,17 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(c
         __syncwarp();
         if (lane < (int)cnt) {
             const uint32_t off = off0 + lane * w;
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(raw) + (off >> 2);
+            const uint32_t sa = raw_base + (off & ~3u);
             const uint32_t sh = (off & 3u) * 8u;
             // phase A, the same instructions for every lane: a bit per position that holds an ambiguity code
             uint32_t amb_lo = 0, amb_hi = 0;
-#pragma unroll 1
-            for (uint32_t k = 0; k < n_words; k++) {
-                uint32_t x = __funnelshift_r(sw[k], sw[k + 1], sh);
+            uint32_t prev = lds_u32(sa);
+#pragma unroll
+            for (uint32_t k = 0; k < (W ? (uint32_t)(W + 3) / 4 : 16u); k++) {
+                if (W == 0 && k >= n_words) break;
+                const uint32_t next = lds_u32(sa + 4 * k + 4);
+                uint32_t x = __funnelshift_r(prev, next, sh);
+                prev = next;
                 const uint32_t nb = min(4u, w - 4u * k);  // bytes of this word inside the window
                 if (nb < 4) x = (x & ((1u << (8 * nb)) - 1u)) | ((filler * 0x01010101u) << (8 * nb));
                 uint32_t m4;
