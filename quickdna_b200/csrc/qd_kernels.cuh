@@ -403,19 +403,44 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
             const uint64_t* rpc = S.rp_cache[buf] + (first_cur & 1u);
             const uint64_t* offc = S.off_cache[buf] + (first_cur & 1u);
             const uint32_t gl = active ? tid : 0;  // run index relative to g0
-            const uint64_t g = g0 + gl;
+            uint64_t g = g0 + gl;
             // largest i with run_prefix[r_first + i] <= g: it is at or after the sequence of my warp's first run, and at most
             // 32 entries further unless empty sequences intervene (then the whole window is searched)
             uint32_t lo = 0, hi = SEARCH_CAP;
-            if (active) {
-                lo = S.warp_first[buf][tid >> 5] - first_cur;
-                const uint32_t near = min(lo + 32u, (uint32_t)SEARCH_CAP);
-                if (lo > (uint32_t)SEARCH_CAP) lo = SEARCH_CAP;  // window too small for this tile: global search below
-                else if (rpc[near] > g) hi = near;
+            bool found = false;
+            if ((uint32_t)(tid & ~31) < cnt) {  // (warp-uniform) my warp has runs in this tile
+                // Together: lane L looks at the L-th sequence after the one holding the warp's first run.  Those that start
+                // inside the warp's 32 runs set a bit at their first run; my sequence is as many steps further as there are
+                // bits at or below my run.  (Empty sequences repeat a prefix value and would share a bit: search instead.)
+                const uint32_t lo0 = S.warp_first[buf][tid >> 5] - first_cur, lane = tid & 31;
+                if (lo0 + 33u <= (uint32_t)SEARCH_CAP) {
+                    const uint64_t gw = g0 + (uint32_t)(tid & ~31);
+                    const uint64_t v = rpc[lo0 + 1 + lane], vnext = rpc[lo0 + 2 + lane];  // all > gw: warp_first is the LAST sequence at or before run gw
+                    const bool inside = v <= gw + 31;
+                    const uint32_t repeats = __ballot_sync(0xffffffffu, inside && v == vnext);
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, inside ? 1u << (uint32_t)(v - gw) : 0u);
+                    const bool all_seen = __shfl_sync(0xffffffffu, inside ? 0 : 1, 31) != 0;  // the 32nd candidate starts past the warp's runs
+                    if (repeats == 0 && all_seen) {
+                        lo = lo0 + __popc(starts & (0xffffffffu >> (31u - lane)));
+                        if (!active) {  // lanes past the last run: the geometry of the warp's first run (nothing is written)
+                            lo = lo0;
+                            g = gw;
+                        }
+                        found = true;
+                    }
+                }
             }
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (rpc[mid] <= g) lo = mid; else hi = mid - 1;
+            if (!found) {
+                if (active) {
+                    lo = S.warp_first[buf][tid >> 5] - first_cur;
+                    const uint32_t near = min(lo + 32u, (uint32_t)SEARCH_CAP);
+                    if (lo > (uint32_t)SEARCH_CAP) lo = SEARCH_CAP;  // window too small for this tile: global search below
+                    else if (rpc[near] > g) hi = near;
+                }
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (rpc[mid] <= g) lo = mid; else hi = mid - 1;
+                }
             }
             uint64_t rp = rpc[lo], off_lo = offc[lo], off_hi = offc[lo + 1];
             if (lo == SEARCH_CAP) {  // more than SEARCH_CAP sequences start inside this tile: finish in global
