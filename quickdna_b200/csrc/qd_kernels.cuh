@@ -1979,8 +1979,8 @@ __global__ void __launch_bounds__(256) warp_map_kernel(const uint64_t* __restric
 
 // ------------------------------------------------------------------------------------------------
 // ASCII -> typed parse (src/rust_api.rs:310-322): drop ' ' and '\t', validate every other byte, emit one mask per
-// kept byte.  Stream compaction in two passes over the input: kept-byte counts per 4 KiB block -> device scan ->
-// compacted, coalesced write.
+// kept byte.  Stream compaction in two passes: kept-byte counts per 4 KiB block (+ an optimistic in-place store of
+// every clean granule) -> device scan -> compacted, coalesced write of the blocks the guess was wrong for.
 // ------------------------------------------------------------------------------------------------
 constexpr int PARSE_THREADS = 256;
 constexpr int PARSE_BLOCK_BYTES = PARSE_THREADS * 16;  // one aligned 16-byte granule per thread
@@ -2061,6 +2061,10 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_count_kernel(const ParseP
     __syncthreads();
     const uint32_t pair_base = smem_u32(pair_s);
     const uintptr_t lo = reinterpret_cast<uintptr_t>(p.in);
+    // Input without whitespace is the usual case, and then every mask lands where its letter was.  When input and output
+    // share their 16-byte phase this pass stores each clean granule there already; the second pass skips the blocks whose
+    // scanned offset confirms the guess and rewrites the rest, so the common case reads the input once.
+    const bool same_phase = ((reinterpret_cast<uintptr_t>(p.out) ^ lo) & 15u) == 0;
     for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         uint8_t v[16];
         uint32_t kept = 16;
@@ -2068,6 +2072,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_count_kernel(const ParseP
         const uint64_t g = blk * PARSE_THREADS + threadIdx.x;
         uint4 fast;
         if (!parse_granule_fast(p, pair_base, g, fast)) parse_load(p, tab_s, g, v, kept, bad);
+        else if (same_phase) stg_stream(p.out + (16 * g - (lo & 15)), fast);  // optimistic: right if nothing before it was dropped
         if (bad >= 0) atomicMin(p.err_key, (unsigned long long)(((lo & ~(uintptr_t)15) + 16 * g + bad) - lo));
         uint64_t total;
         block_exclusive_scan((uint64_t)kept, &total, warp_sums);
@@ -2085,9 +2090,15 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseP
     for (int i = threadIdx.x; i < (int)PAIR_ENTRIES; i += PARSE_THREADS) pair_s[i] = __ldg(p.pair + i);
     __syncthreads();
     const uint32_t pair_base = smem_u32(pair_s);
+    const uintptr_t in_lo = reinterpret_cast<uintptr_t>(p.in);
+    const bool same_phase = ((reinterpret_cast<uintptr_t>(p.out) ^ in_lo) & 15u) == 0;
     for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        // dense block (every byte a nucleotide: its output is as long as its input) landing on a 16-byte boundary:
-        // no compaction, no staging -- translate my granule and store it
+        // dense block (every byte a nucleotide: its output is as long as its input) that lands exactly where the first pass
+        // guessed (nothing was dropped before it): already written
+        if (same_phase && p.offsets[blk + 1] - p.offsets[blk] == PARSE_BLOCK_BYTES &&
+            p.offsets[blk] + (in_lo & 15) == blk * (uint64_t)PARSE_BLOCK_BYTES)
+            continue;
+        // dense block landing on a 16-byte boundary: no compaction, no staging -- translate my granule and store it
         if (p.offsets[blk + 1] - p.offsets[blk] == PARSE_BLOCK_BYTES && ((reinterpret_cast<uintptr_t>(p.out) + p.offsets[blk]) & 15u) == 0) {
             uint4 fast;
             if (parse_granule_fast(p, pair_base, blk * PARSE_THREADS + threadIdx.x, fast)) {  // always true here
