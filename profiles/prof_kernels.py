@@ -22,6 +22,12 @@ elif which == "frames1":
     out = torch.empty(n_reads * 16 * B.runs(L), dtype=torch.uint8, device=dev)
     for _ in range(4):
         B.translate_frames_uniform_dev(x, n_reads, L, out=out, frames=1)
+elif which == "frames3":
+    n_reads, L = 4_000_000, 1000
+    x = synth_torch(3, 0, n_reads * L, dev)
+    out = torch.empty(n_reads * 16 * B.runs(L) * 3, dtype=torch.uint8, device=dev)
+    for _ in range(4):
+        B.translate_frames_uniform_dev(x, n_reads, L, out=out, frames=3)
 elif which == "frames_iupac":
     from quickdna_b200.synth import synth_iupac_np
     import numpy as np

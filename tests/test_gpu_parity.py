@@ -436,6 +436,32 @@ def test_parse_large_device(B, N):
     assert out[:k].cpu().numpy().tobytes() == want.tobytes()
 
 
+def test_parse_dev_clean_blocks_then_dropped_bytes(B):
+    """The count pass stores clean 16-byte granules in place and the write pass skips the 4 KiB blocks that the scan
+    confirms: every mix of confirmed, shifted and compacted blocks, and inputs / outputs of different 16-byte phases."""
+    import torch
+
+    rng = np.random.default_rng(23)
+    n = 9 * 4096 + 123
+    for first_blank in (None, 0, 5, 4095, 4096, 3 * 4096 + 17, n - 1):
+        for in_lead, out_lead in ((0, 0), (0, 16), (3, 3), (3, 0), (16, 5), (7, 23)):
+            a = np.frombuffer(_rand(rng, n, b"ACGTacgtNRY"), dtype=np.uint8).copy()
+            if first_blank is not None:
+                a[first_blank] = 0x20
+                a[first_blank + 1:][rng.random(n - first_blank - 1) < 0.002] = 0x09
+            src = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
+            src[in_lead:in_lead + n] = torch.from_numpy(a).cuda()
+            dst = torch.full((n + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+            B.dev_error_reset()
+            out, count = B.parse_dev(src[in_lead:in_lead + n], out=dst[out_lead:out_lead + n])
+            assert B.dev_error_fetch(src[in_lead:in_lead + n]) is None
+            want = oracle.parse(a.tobytes())
+            k = int(count.item())
+            assert k == want.size, (first_blank, in_lead, out_lead)
+            assert out[:k].cpu().numpy().tobytes() == want.tobytes(), (first_blank, in_lead, out_lead)
+            assert (dst[:out_lead] == 0xEE).all() and (dst[out_lead + n:] == 0xEE).all()  # nothing outside the caller's n bytes
+
+
 # ------------------------------------------------------------------ windows / canonical / expansions
 
 
