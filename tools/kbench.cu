@@ -1,4 +1,4 @@
-// Kernel-only harness for tuning: runs translate_frames_kernel<6, KB_THREADS> on a uniform batch and revcomp_kernel on one
+// Kernel-only harness for tuning: runs translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT> on a uniform batch and revcomp_kernel on one
 // sequence, device-resident, CUDA-event timed.  Not product code, not a parity check (tests/ does that) --
 // it exists so kernel variants (compile-time -D knobs) can be compared back to back on ONE box.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/kbench tools/kbench.cu
@@ -74,7 +74,21 @@ int main(int argc, char** argv) {
 #ifndef KB_THREADS
 #define KB_THREADS 1024
 #endif
+#ifndef KB_FRAMES
+#define KB_FRAMES 6
+#endif
     constexpr int TILE_THREADS = KB_THREADS, TILE_RUNS = KB_THREADS;
+    constexpr bool KB_DIRECT = KB_FRAMES == 1;
+    if (KB_DIRECT) {
+        std::vector<uint8_t> host;
+        build_direct_table(T, 0, true, false, host);
+        uint8_t* d_direct;
+        CK(cudaMalloc(&d_direct, DIRECT_ENTRIES));
+        CK(cudaMemcpy(d_direct, host.data(), DIRECT_ENTRIES, cudaMemcpyHostToDevice));
+        p.direct = d_direct;
+        p.direct_k1 = DIRECT_K1_ASCII;
+        p.direct_k2 = DIRECT_K2_ASCII;
+    }
     p.n_tiles = (uint32_t)((p.total_runs + TILE_RUNS - 1) / TILE_RUNS);
     p.out = out;
     p.lut = d_lut;
@@ -85,9 +99,9 @@ int main(int argc, char** argv) {
     p.or_forbid = 0x80808080u;
     p.err_key = d_err;
     int occ = 0;
-    const size_t smem = sizeof(FramesSmem<KB_THREADS>);
-    CK(cudaFuncSetAttribute(translate_frames_kernel<6, KB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, translate_frames_kernel<6, KB_THREADS>, TILE_THREADS, smem));
+    const size_t smem = KB_DIRECT ? ((sizeof(FramesSmem<KB_THREADS>) + 127) & ~(size_t)127) + DIRECT_ENTRIES : sizeof(FramesSmem<KB_THREADS>);
+    CK(cudaFuncSetAttribute(translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT>, TILE_THREADS, smem));
 #ifdef KB_OCC
     occ = KB_OCC;
 #endif
@@ -95,22 +109,22 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; i++) translate_frames_kernel<6, KB_THREADS><<<grid, TILE_THREADS, smem>>>(p);
+    for (int i = 0; i < 3; i++) translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT><<<grid, TILE_THREADS, smem>>>(p);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < reps; i++) translate_frames_kernel<6, KB_THREADS><<<grid, TILE_THREADS, smem>>>(p);
+    for (int i = 0; i < reps; i++) translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT><<<grid, TILE_THREADS, smem>>>(p);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= reps;
     size_t algo = L;
-    for (int k = 0; k < 3; k++) algo += 2 * ((L - k) / 3);
+    for (int k = 0; k < (KB_FRAMES == 1 ? 1 : 3); k++) algo += (KB_FRAMES == 6 ? 2 : 1) * ((L - k) / 3);
     xorsum_kernel<<<sms * 8, 256>>>((const uint32_t*)out, out_bytes / 4, d_acc);
     unsigned long long acc = 0, err = 0;
     CK(cudaMemcpy(&acc, d_acc, 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&err, d_err, 8, cudaMemcpyDeviceToHost));
-    printf("frames6  occ %d grid %u  %zu x %zu  %.3f ms  %.1f GB/s algorithmic  %.3f Tnt/s  checksum %016llx err %llx\n", occ, grid, n_reads, L,
+    printf("frames%d thr %d occ %d grid %u  %zu x %zu  %.3f ms  %.1f GB/s algorithmic  %.3f Tnt/s  checksum %016llx err %llx\n", KB_FRAMES, KB_THREADS, occ, grid, n_reads, L,
            ms, n_reads * (double)algo / ms / 1e6, total / (double)ms / 1e9, acc, err);
 
     // reverse complement, rotating 4 buffer sets inside the big allocations
