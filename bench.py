@@ -523,14 +523,16 @@ def main():
         hdr = np.frombuffer(b">synthetic record, 143 lines of 70 nt\n", dtype=np.uint8)
         text = np.concatenate([np.broadcast_to(hdr, (n_rec, hdr.size)), lines], axis=1).reshape(-1).tobytes()
         del body, lines
-        B.fasta_scan(text[: 1 << 20], ctx=ctx)
+        t0 = time.perf_counter()
+        scan = B.fasta_scan(text, ctx=ctx)  # first call: the context's device buffers grow to this size
+        fa_first = time.perf_counter() - t0
         t0 = time.perf_counter()
         scan = B.fasta_scan(text, ctx=ctx)
         fa_s = time.perf_counter() - t0
         assert len(scan) == n_rec and scan.masks.size == n_rec * lines_per * width
-        extra["fasta_scan"] = {"workload": f"{n_rec} records, {len(text)} bytes of FASTA text (70-column lines), host in / host out, "
-                                           "two qd_fasta_scan calls (sizes, then data) + Python record objects",
-                               "seconds": fa_s, "text_GB_per_s": len(text) / fa_s / 1e9}
+        extra["fasta_scan"] = {"workload": f"{n_rec} records, {len(text)} bytes of FASTA text (70-column lines), host in / host out "
+                                           "(pageable memory), one qd_fasta_scan call + Python record objects",
+                               "seconds": fa_s, "text_GB_per_s": len(text) / fa_s / 1e9, "first_call_seconds": fa_first}
         if not args.no_cpu:
             import oracle
 

@@ -536,7 +536,7 @@ class FastaParser {
         const uint8_t* text = reinterpret_cast<const uint8_t*>(s.data());
         size_t n_masks = 0, n_records = 0;
         qd_err e{};
-        auto call = [&](uint8_t* masks, qd_fasta_record* recs, size_t cap) {
+        auto call = [&](uint8_t* masks, qd_fasta_record* recs, size_t cap) {  // false: `cap` records were not enough
             const int rc = qd_fasta_scan(c.get(), strict_of<T>, settings_.concatenate_headers, settings_.allow_preceding_comment, text, s.size(), masks,
                                          &n_masks, recs, cap, &n_records, &e);
             if (rc >= QD_ERR_NON_ASCII_BYTE && rc <= QD_ERR_UNEXPECTED_AMBIGUOUS) {
@@ -544,12 +544,18 @@ class FastaParser {
                 qd_err_message(&e, buf, sizeof buf);
                 throw FastaParseError(e, buf);
             }
+            if (rc == QD_ERR_INVALID_ARGUMENT && n_records > cap) return false;
             c.check(rc, e);
+            return true;
         };
-        call(nullptr, nullptr, 0);  // sizes
-        std::vector<uint8_t> masks(n_masks + 1);
-        std::vector<qd_fasta_record> recs(n_records + 1);
-        call(masks.data(), recs.data(), n_records);
+        // one call in the usual case: there are at most s.size() masks, and a record of ordinary FASTA is longer than 64 bytes;
+        // only a file of very short records needs the exact count (the refused call has reported it) and a second call
+        std::vector<uint8_t> masks(s.size() + 1);
+        std::vector<qd_fasta_record> recs(s.size() / 64 + 16);
+        if (!call(masks.data(), recs.data(), recs.size())) {
+            recs.resize(n_records + 1);
+            call(masks.data(), recs.data(), n_records);
+        }
         std::vector<FastaRecord<T>> out;
         out.reserve(n_records);
         for (size_t i = 0; i < n_records; i++) {

@@ -168,17 +168,28 @@ def fasta_scan(text, strict: bool = False, concatenate_headers: bool = True, all
     n_masks, n_records = C.c_size_t(), C.c_size_t()
     err = N.QdErr()
     args = (ctx.handle, int(strict), int(concatenate_headers), int(allow_preceding_comment), _p(a if a.size else np.zeros(1, np.uint8)), a.size)
-    rc = L.qd_fasta_scan(*args, None, C.byref(n_masks), None, 0, C.byref(n_records), C.byref(err))
-    if rc in (1, 2, 3):
-        e = N.make_error(err)
-        fe = FastaError(str(e), e.kind, e.byte, e.pos, 0)
-        fe.line = int(err.seq_index)
-        raise fe
+
+    def call(masks, recs, cap):
+        rc = L.qd_fasta_scan(*args, None if masks is None else _p(masks), C.byref(n_masks), recs, cap, C.byref(n_records), C.byref(err))
+        if rc in (1, 2, 3):
+            e = N.make_error(err)
+            fe = FastaError(str(e), e.kind, e.byte, e.pos, 0)
+            fe.line = int(err.seq_index)
+            raise fe
+        return rc
+
+    # one call in the usual case: there are at most n masks, and a record of ordinary FASTA is longer than 64 bytes; only a
+    # file of very short records needs the exact count (the failed call has reported it) and a second call
+    cap = a.size // 64 + 16
+    masks = np.empty(max(a.size, 1), dtype=np.uint8)
+    rec_bytes = np.empty(cap * C.sizeof(FastaRecordC), dtype=np.uint8)  # untouched pages cost nothing
+    rc = call(masks, C.c_void_p(rec_bytes.ctypes.data), cap)
+    if rc == N.QD_ERR_INVALID_ARGUMENT and n_records.value > cap:
+        cap = n_records.value
+        rec_bytes = np.empty(cap * C.sizeof(FastaRecordC), dtype=np.uint8)
+        rc = call(masks, C.c_void_p(rec_bytes.ctypes.data), cap)
     ctx.check(rc, err)
-    masks = np.empty(max(n_masks.value, 1), dtype=np.uint8)
-    recs = (FastaRecordC * max(n_records.value, 1))()
-    rc = L.qd_fasta_scan(*args, _p(masks), C.byref(n_masks), recs, n_records.value, C.byref(n_records), C.byref(err))
-    ctx.check(rc, err)
+    recs = (FastaRecordC * max(n_records.value, 1)).from_buffer(rec_bytes)
     return FastaScan(raw, masks[: n_masks.value], list(recs[: n_records.value]))
 
 

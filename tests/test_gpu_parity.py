@@ -905,6 +905,15 @@ def test_fasta_random(B):
                 _fasta_same(B, bytes(buf), trial % 2 == 0 and b"N" not in text, concat, allow)
 
 
+def test_fasta_many_tiny_records(B):
+    """More records than the wrapper's first guess (one per 64 bytes of text): the second, exactly sized call."""
+    text = b"".join(b">%d\nAC\n" % i for i in range(500))
+    for concat in (False, True):
+        _fasta_same(B, text, False, concat, False)
+    scan = B.fasta_scan(text)
+    assert len(scan) == 500 and scan.headers[499] == "499" and scan.record(3)[1].tobytes() == bytes([1, 4])
+
+
 def test_fasta_feeds_batch_translate(B):
     """The scanner's CSR offsets are what the batch entry points consume."""
     rng = np.random.default_rng(42)
