@@ -1050,9 +1050,14 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
     return QD_OK;
 }
 
+static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride, size_t n_seq, size_t len, size_t w, int mode,
+                             uint8_t* out_dev, uint64_t key_stride, cudaStream_t s);
+
 static int windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, uint8_t* out_dev, cudaStream_t s) {
     if (w == 0 || w > 0xffffffffull) return QD_ERR_INVALID_ARGUMENT;
     if (n < w) return QD_OK;
+    // windows of up to 64 bytes: the warp-tile kernel of the batch form (rows staged in shared memory, 128-bit stores)
+    if (w <= 64 && n <= 0xffffffffull) return windows_batch_dev(c, seq_dev, n, 1, n, w, QD_WIN_COPY, out_dev, n, s);
     const uint64_t n_windows = n - w + 1;
     const uint64_t chunks = (n_windows * w + 15) >> 4;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + 255) / 256, (uint64_t)c->sm_count * 16));
