@@ -166,7 +166,9 @@ int qd_parse(qd_ctx *ctx, int strict, const uint8_t *ascii, size_t n, uint8_t *m
  * for the headerless record made of content before the first header), masks [content_begin, content_end) -- so
  * content_begin/_end are the CSR offsets the batch entry points take -- and line_range [line_begin, line_end).
  * concatenate_headers / allow_preceding_comment: FastaParseSettings, src/fasta.rs:67-110 (defaults 1 / 0).
- * Call with masks == records == NULL to get *n_masks and *n_records only.  On a content error err->pos is the byte
+ * Call with masks == records == NULL to get *n_masks and *n_records only; a call whose max_records is too small stores
+ * the needed *n_records and returns QD_ERR_INVALID_ARGUMENT (so one call with masks[n] and a generous guess, e.g.
+ * n / 64 + 16 records, is the usual case).  On a content error err->pos is the byte
  * offset in `text` and err->seq_index the 1-based line number (Located::line_number, src/errors.rs:8-15). */
 typedef struct qd_fasta_record {
     uint64_t header_begin, header_end, content_begin, content_end, line_begin, line_end;
