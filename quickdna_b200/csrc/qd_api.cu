@@ -717,6 +717,7 @@ static int launch_canonical_tiles(qd_ctx* c, CanonKeyParams kp, cudaStream_t s) 
     // keys: 448 + 41 + slack = 16 x 32 positions for w = 42 is two rounds of the per-position pass;
     // rows: 192 + 41 + slack = 8 x 32 is one round (rows are staged and copied out 64 at a time)
     uint32_t wpt = rows ? 192 : 448;
+    if (const char* e = getenv(rows ? "QD_CTILE_WPT_ROWS" : "QD_CTILE_WPT_KEYS")) wpt = std::max(64, atoi(e) & ~63);  // tuning knob
     while (wpt > 64 && ckey_span_bound(wpt, p.w, nw) > 2048) wpt -= 64;
     kp.wpt = wpt;
     kp.pos_cap = (uint32_t)((ckey_span_bound(wpt, p.w, nw) + 31) & ~(uint64_t)31);

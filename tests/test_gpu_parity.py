@@ -643,6 +643,31 @@ def test_canonical_window_keys_batch(B, N):
     assert err is not None and (err.seq_index, err.pos, err.kind, err.byte) == (17, 321, 3, ord("N"))
 
 
+def test_canonical_window_keys_full_size_properties(B, N):
+    """src/canonical.rs:414-437 at full size, through the keys: the canonical form does not change when the sequence is
+    reversed or when its bases are renamed, so window i of x and window nw - 1 - i of reverse(x) share their key, and so
+    do x and any relabelling of x."""
+    import torch
+
+    from quickdna_b200.synth import synth_torch
+
+    n, w = 20_000_003, 42
+    x = synth_torch(9, 0, n, torch.device("cuda:0"))
+    B.dev_error_reset()
+    k = B.canonical_window_keys_dev(x, 1, n, w)
+    kr = B.canonical_window_keys_dev(torch.flip(x, dims=[0]).contiguous(), 1, n, w)
+    assert torch.equal(k, torch.flip(kr, dims=[0]))
+    table = torch.arange(256, dtype=torch.uint8, device=x.device)
+    for a, b in zip(b"ACGT", b"GTAC"):
+        table[a] = b
+    kp = B.canonical_window_keys_dev(table[x.long()], 1, n, w)
+    assert torch.equal(k, kp)
+    assert B.dev_error_fetch(x, uniform_len=n, strict=True) is None
+    # the packed key of the forward-only form starts with code 0 and is a restricted-growth string: its first nucleotide is A
+    pf = B.canonical_window_keys_dev(x, 1, n, w, kind=N.CANON_KEY_PACKED, forward_only=True)
+    assert int((pf[:, 0] & 1).sum()) == 0 and int((pf[:, 2] & 1).sum()) == 0
+
+
 @pytest.mark.parametrize("dna,exp", V.EXPANSIONS)
 def test_expansion_vectors(B, dna, exp):
     a = np.frombuffer(dna.encode(), dtype=np.uint8).reshape(1, -1)
