@@ -1,7 +1,8 @@
 // quickdna_b200 -- sm_100a kernels for the quickdna sequence hot path.
 //
-// All kernels are HBM-bound byte/integer work (no tensor cores).  Design, data layout and the
-// algorithmic bytes per unit are described in DESIGN.md; reference citations are relative to
+// Byte/integer streaming work throughout (no tensor cores): the frame and reverse-complement kernels are HBM-bound, the
+// window kernels issue- or shared-memory-bound.  Design, data layout and the algorithmic bytes per unit are described in
+// DESIGN.md; reference citations are relative to
 // the SecureDNA/quickdna checkout.
 #pragma once
 
