@@ -1085,7 +1085,8 @@ static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride,
     p.out = out_dev;
     p.key_stride = key_stride;
     p.err_key = c->d_err;
-    const uint64_t tiles = (uint64_t)n_seq * ((len - w + 1 + WIN_WPT - 1) / WIN_WPT);
+    const uint64_t wpt = w == 42 ? WinTile<42>::WPT : (w == 20 ? WinTile<20>::WPT : WinTile<0>::WPT);
+    const uint64_t tiles = (uint64_t)n_seq * ((len - w + 1 + wpt - 1) / wpt);
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + WIN_WARPS - 1) / WIN_WARPS, (uint64_t)c->sm_count * 6));
     // the two window lengths of benches/all_windows.rs get fully unrolled instantiations
     if (w == 42) windows_batch_kernel<42><<<grid, 32 * WIN_WARPS, 0, s>>>(p);

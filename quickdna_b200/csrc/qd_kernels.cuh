@@ -877,8 +877,15 @@ struct WindowsBatchParams {
     unsigned long long* err_key;
 };
 constexpr int WIN_WPT = 64, WIN_WARPS = 8;
+// windows per warp-tile: 64, or for a compile-time window length as many more groups of 64 (at most 4) as fit the stage,
+// which is sized for 64 windows of 64 bytes -- the fixed cost of a tile is spread over more bytes of short windows
+template <int W>
+struct WinTile {
+    static constexpr int GROUPS = W == 0 ? 1 : (64 / W < 1 ? 1 : (64 / W > 4 ? 4 : 64 / W));
+    static constexpr int WPT = GROUPS * WIN_WPT;
+};
 struct WinWarpSmem {
-    alignas(16) uint8_t srcb[4 + WIN_WPT + 64 + 24];
+    alignas(16) uint8_t srcb[4 + 4 * WIN_WPT + 64 + 24];
     alignas(16) uint8_t stage[WIN_WPT * 64 + 32];
 };
 
@@ -941,8 +948,9 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WinWarpSmem& S = SM[threadIdx.x >> 5];
+    constexpr uint32_t WPT = WinTile<W>::WPT;
     const uint32_t w = W ? (uint32_t)W : p.w, nw = p.len - w + 1;
-    const uint32_t tiles_per_seq = (nw + WIN_WPT - 1) / WIN_WPT;
+    const uint32_t tiles_per_seq = (nw + WPT - 1) / WPT;
     const uint64_t n_tiles = p.n_seq * tiles_per_seq;
     const uint64_t warps_total = (uint64_t)gridDim.x * WIN_WARPS;
     uint64_t tile = (uint64_t)blockIdx.x * WIN_WARPS + (threadIdx.x >> 5);
@@ -951,7 +959,7 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
     const uint64_t step_s = warps_total / tiles_per_seq;
     const uint32_t step_t = (uint32_t)(warps_total % tiles_per_seq);
     for (; tile < n_tiles; tile += warps_total) {
-        const uint32_t i0 = t * WIN_WPT, cnt = min((uint32_t)WIN_WPT, nw - i0), span = cnt + w - 1;
+        const uint32_t i0 = t * WPT, cnt = min(WPT, nw - i0), span = cnt + w - 1;
         const uint8_t* seq = p.src + s * p.src_stride;
         // source bytes of the tile, mapped, in window order: srcb[4 + k] = map(seq[i0 + k]) or map(seq[len - 1 - i0 - k])
         // (a word-granular version of this loop was measured slower: 3.4 vs 2.8 ms on the all_windows bench leg)
@@ -965,11 +973,11 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
         const uint64_t out0 = (s * nw + i0) * (uint64_t)w;
         uint8_t* gdst = p.out + out0;
         const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
-        // lane handles windows 2 * lane and 2 * lane + 1: for even w all rows of one pass share their alignment in the
-        // stage, so the switch below does not diverge
+        // within every 64 windows lane handles windows 2 * lane and 2 * lane + 1: for even w all rows of one pass share their
+        // alignment in the stage, so the switch below does not diverge
 #pragma unroll 1
-        for (uint32_t pass = 0; pass < 2; pass++) {
-            const uint32_t l = 2u * lane + pass;
+        for (uint32_t pass = 0; pass < WPT / 32; pass++) {
+            const uint32_t l = 64u * (pass >> 1) + 2u * lane + (pass & 1u);
             if (l < cnt) {
                 const uint32_t D = phase + l * w;
                 switch (D & 3u) {
