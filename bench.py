@@ -264,7 +264,7 @@ def main():
     achieved = n_reads * ALGO_BYTES_PER_READ / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic("translate_frames_kernel<6>", reads=n_reads, read_len=READ_LEN),
-                "kernel": "translate_frames_kernel<6, 1024>", "peak_source": peak_src,
+                "kernel": "translate_frames_kernel<6, 1024, 0>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": n_reads * ALGO_BYTES_PER_READ}
 
     # ---- extra: reverse complement of one 250 Mb sequence (config 2), device-resident
