@@ -125,3 +125,36 @@ def test_canonical_gpu_properties(dna):
     if len(raw) >= 20:
         w = 20
         assert B.canonical_windows(raw, w).tobytes() == oracle.ascii_of(oracle.canonical_windows(m, w).reshape(-1))
+
+
+@pytest.mark.gpu
+@settings(**COMMON)
+@given(st.text(alphabet="ATCG", min_size=1, max_size=300), st.integers(min_value=1, max_value=64), st.booleans())
+def test_canonical_window_keys_hypothesis(dna, w, forward_only):
+    """One key per canonical window: unpacking the bit planes gives the oracle's canonical windows,
+    for every window length the kernel takes; equal windows have equal fingerprints and (w <= 32) vice versa."""
+    from quickdna_b200 import _native as N
+    from quickdna_b200 import batch as B
+
+    raw = dna.encode()
+    m = oracle.masks_of(raw)
+    count = max(0, len(raw) - w + 1)
+    packed = B.canonical_window_keys(raw, w=w, kind=N.CANON_KEY_PACKED, forward_only=forward_only)
+    fp = B.canonical_window_keys(raw, w=w, kind=N.CANON_KEY_FP64, forward_only=forward_only)
+    pw = (w + 31) // 32
+    assert packed.shape == (count, 2 * pw) and fp.shape == (count,)
+    if count == 0:
+        return
+    want = (oracle.canonical_windows(m, w) if not forward_only
+            else np.stack([oracle.forward_canonical(m[i:i + w]) for i in range(count)]))
+    bits = (packed[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1   # [count, 2 pw, 32]
+    lo = bits[:, :pw].reshape(count, -1)[:, :w]
+    hi = bits[:, pw:].reshape(count, -1)[:, :w]
+    mask_of_code = np.array([1, 2, 4, 8], dtype=np.uint8)  # A, T, C, G
+    assert (mask_of_code[lo + 2 * hi] == want).all()
+    assert (bits[:, :pw].reshape(count, -1)[:, w:] == 0).all() and (bits[:, pw:].reshape(count, -1)[:, w:] == 0).all()
+    same_window = (want[:, None, :] == want[None, :, :]).all(axis=2)
+    same_key = fp[:, None] == fp[None, :]
+    assert (same_key[same_window]).all()
+    if w <= 32:
+        assert (same_window == same_key).all()
