@@ -170,6 +170,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -876,6 +877,9 @@ struct WindowsBatchParams {
     uint64_t key_stride;  // error key of byte i of sequence s = s * key_stride + i
     unsigned long long* err_key;
 };
+#ifndef QD_WIN_TMA_STORE
+#define QD_WIN_TMA_STORE 1
+#endif
 constexpr int WIN_WPT = 64, WIN_WARPS = 8;
 // windows per warp-tile: 64, or for a compile-time window length as many more groups of 64 (at most 4) as fit the stage,
 // which is sized for 64 windows of 64 bytes -- the fixed cost of a tile is spread over more bytes of short windows
@@ -949,6 +953,7 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
     const int lane = threadIdx.x & 31;
     WinWarpSmem& S = SM[threadIdx.x >> 5];
     constexpr uint32_t WPT = WinTile<W>::WPT;
+    constexpr bool TMA_OUT = QD_WIN_TMA_STORE && WinTile<W>::GROUPS > 1;  // bulk-copy the rows out when a tile is large enough to pay for it
     const uint32_t w = W ? (uint32_t)W : p.w, nw = p.len - w + 1;
     const uint32_t tiles_per_seq = (nw + WPT - 1) / WPT;
     const uint64_t n_tiles = p.n_seq * tiles_per_seq;
@@ -969,6 +974,7 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
             if (v == 0 && p.map) atomicMin(p.err_key, (unsigned long long)(s * p.key_stride + at));
             S.srcb[4 + k] = (uint8_t)v;  // 4-byte front pad: a row's first destination word may start before its window
         }
+        if (TMA_OUT && lane == 0) bulk_wait_read_0();  // the previous tile's rows have left the stage
         __syncwarp();
         const uint64_t out0 = (s * nw + i0) * (uint64_t)w;
         uint8_t* gdst = p.out + out0;
@@ -988,11 +994,21 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
                 }
             }
         }
+        if (TMA_OUT) fence_proxy_async_smem();  // my rows, written through the generic proxy, are visible to the bulk copy
         __syncwarp();
         const uint32_t nbytes = cnt * w;
         const uint32_t head = min(nbytes, (16u - phase) & 15u), body = (nbytes - head) >> 4;
         if (lane < (int)head) gdst[lane] = S.stage[phase + lane];
-        for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(S.stage + phase + head + 16 * c));
+        if (TMA_OUT) {
+            // the aligned body leaves as ONE bulk copy shared -> global: no per-granule LDS.128 / STG.128 through the LSU pipe,
+            // which is what bounds this kernel (measured: +8 % for 192-window tiles of 20 bytes, -13 % for 64-window tiles of 42)
+            if (lane == 0 && body) {
+                bulk_s2g(gdst + head, S.stage + phase + head, 16 * body);
+                bulk_commit();
+            }
+        } else {
+            for (uint32_t c = lane; c < body; c += 32) stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(S.stage + phase + head + 16 * c));
+        }
         const uint32_t done = head + 16 * body;
         if (lane < (int)(nbytes - done)) gdst[done + lane] = S.stage[phase + done + lane];
         __syncwarp();
@@ -1000,6 +1016,7 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
         t += step_t;
         if (t >= tiles_per_seq) { t -= tiles_per_seq; s++; }
     }
+    if (TMA_OUT && lane == 0) bulk_wait_all();  // shared memory must outlive the last copy
 }
 
 // origin indices of benches/all_windows.rs:39-75 for one segment of windows
