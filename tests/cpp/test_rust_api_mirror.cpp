@@ -213,6 +213,12 @@ int main() {
             threw = e.line_number == 3 && std::string(e.what()) == "on line 3: error parsing record: bad nucleotide: 'x'";
         }
         CHECK(threw);
+        // more records than the first capacity guess (one per 64 bytes of text): the exactly sized second call
+        std::string tiny;
+        for (int i = 0; i < 300; i++) tiny += ">" + std::to_string(i) + "\nAC\n";
+        auto many_tiny = FastaParser<Nucleotide>().parse_str(tiny);
+        CHECK(many_tiny.size() == 300 && many_tiny[299].header == "299" && many_tiny[7].contents == dna_strict("AC") &&
+              many_tiny[299].line_range == lr(599, 601));
     }
     if (failures) {
         std::printf("%d check(s) failed\n", failures);
