@@ -374,10 +374,10 @@ def main():
         return max_over_ranks(ev0.elapsed_time(ev1)) / reps
 
     if not args.no_extra:
-        def leg(name, workload, ms, nt, algo_bytes, kernel):
+        def leg(name, workload, ms, nt, algo_bytes, kernel, traffic=None):
             gbs = algo_bytes / (ms * 1e-3) / 1e9
             extra[name] = {"workload": workload, "nt_per_s": world * nt / (ms * 1e-3), "ms": ms,
-                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
                                         "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes}}
 
         n_v = min(n_reads, 4_000_000)
@@ -386,7 +386,7 @@ def main():
         f3 = sum((READ_LEN - k) // 3 for k in range(3))
         ms1 = timed(lambda: B.translate_frames_uniform_dev(x[:nt_v], n_v, READ_LEN, out=out, table=args.table, frames=1, ctx=ctx))
         leg("translate_1_frame", f"translate (1 frame) on {n_v} x {READ_LEN}-nt reads per GPU", ms1, nt_v, n_v * (READ_LEN + f1),
-            "translate_frames_kernel<1, 1024>")
+            "translate_frames_kernel<1, 1024, direct>", ncu_traffic("translate_frames_kernel<1,direct>", reads=n_v, read_len=READ_LEN))
         ms3 = timed(lambda: B.translate_frames_uniform_dev(x[:nt_v], n_v, READ_LEN, out=out, table=args.table, frames=3, ctx=ctx))
         leg("translate_self_frames", f"translate_self_frames (3 frames) on {n_v} x {READ_LEN}-nt reads per GPU", ms3, nt_v,
             n_v * (READ_LEN + f3), "translate_frames_kernel<3, 1024>")
@@ -593,7 +593,8 @@ def main():
                 "workload": f"expansions of {n_win} 42-nt windows with exactly 2 ambiguity codes, cap 16, per GPU: {n_rows} rows "
                             "(size_hint kernel + scan + write kernel per call)",
                 "rows_per_s": world * n_rows / (ex_ms * 1e-3), "windows_per_s": world * n_win / (ex_ms * 1e-3), "ms": ex_ms,
-                "roofline": {"bound": "hbm", "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak,
+                             "traffic": ncu_traffic("expansion_windows", windows=n_win, w=w),
                              "kernel": "expansion_count_tiles_kernel<ascii, 42> + scan + expansion_write_tiles_kernel<42>", "algorithmic_bytes_per_launch": ex_bytes}}
             del win, c_d, oi_d
 
