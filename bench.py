@@ -47,6 +47,31 @@ def ncu_traffic(kernel: str, **match):
     return None
 
 
+def fill_leg_traffic(extra: dict):
+    """roofline.traffic of the `extra` legs: dram bytes of ONE call of the leg (all its kernels) from the committed per-leg
+    ncu capture (profiles/traffic_r01.json "legs", taken with QD_BENCH_NCU_LEGS=1), when the capture was taken on the same
+    workload (same algorithmic bytes per call)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            legs = json.load(f).get("legs", {})
+    except Exception:
+        return
+
+    def visit(name, node):
+        if not isinstance(node, dict):
+            return
+        r = node.get("roofline")
+        e = legs.get(name)
+        if isinstance(r, dict) and r.get("traffic") is None and e and e.get("algorithmic_bytes_per_launch") == r.get("algorithmic_bytes_per_launch"):
+            r["traffic"] = e["dram_read"] + e["dram_write"]
+        for k, v in node.items():
+            if k != "roofline":
+                visit(f"{name}/{k}", v)
+
+    for k, v in extra.items():
+        visit(k, v)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -274,13 +299,16 @@ def main():
     sampler.start()
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.profiler.start()  # `ncu --profile-from-start off` lists exactly the timed region
+    ncu_legs = os.environ.get("QD_BENCH_NCU_LEGS") == "1"  # profile one launch of every `extra` leg instead of the timed region
+    if not ncu_legs:
+        torch.cuda.profiler.start()  # `ncu --profile-from-start off` lists exactly the timed region
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
-    torch.cuda.profiler.stop()
+    if not ncu_legs:
+        torch.cuda.profiler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = ctx.launch_count - launches0
     clocks = sampler.stop()
@@ -356,6 +384,11 @@ def main():
         ev1.record()
         barrier()
         v_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 5
+        if ncu_legs:
+            torch.cuda.profiler.start()
+            B.parse_dev(x[:n_rc], out=masks, ctx=ctx)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         extra["parse"] = {"workload": f"ASCII -> mask parse of {n_rc} nt (count pass + scan + compacting write pass)", "ms": v_ms,
                           "nt_per_s": world * n_rc / (v_ms * 1e-3), "GB/s_algorithmic": 2 * n_rc / (v_ms * 1e-3) / 1e9}
         extra["revcomp_variants"] = variants
@@ -371,7 +404,13 @@ def main():
             fn()
         ev1.record()
         barrier()
-        return max_over_ranks(ev0.elapsed_time(ev1)) / reps
+        t_ms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
+        if ncu_legs:  # one more call, alone inside a profiler range: `ncu --profile-from-start off` sees each leg's kernels in order
+            torch.cuda.profiler.start()
+            fn()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        return t_ms
 
     if not args.no_extra:
         def leg(name, workload, ms, nt, algo_bytes, kernel, traffic=None):
@@ -434,16 +473,7 @@ def main():
         n_seq = min(args.canon_seqs, total_nt // seq_len, out.numel() // ((seq_len - w + 1) * w))
         if n_seq > 0:
             nwin = n_seq * (seq_len - w + 1)
-            for _ in range(2):
-                B.canonical_windows_batch_dev(x, n_seq, seq_len, w, out=out, ctx=ctx)
-            barrier()
-            reps = 5
-            ev0.record()
-            for _ in range(reps):
-                B.canonical_windows_batch_dev(x, n_seq, seq_len, w, out=out, ctx=ctx)
-            ev1.record()
-            barrier()
-            cw_ms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
+            cw_ms = timed(lambda: B.canonical_windows_batch_dev(x, n_seq, seq_len, w, out=out, ctx=ctx))
             cw_gbs = nwin * (1 + w) / (cw_ms * 1e-3) / 1e9
             extra["canonical_windows"] = {
                 "workload": f"canonical 42-nt windows of {n_seq} x {seq_len}-nt ACGT sequences per GPU (benches/canonical.rs shape)",
@@ -455,15 +485,7 @@ def main():
             keys = {}
             for kind, label, kb in ((N.CANON_KEY_FP64, "fingerprint_64", 8), (N.CANON_KEY_PACKED, "packed_2bit", 16)):
                 kout = out.view(torch.int32)
-                for _ in range(2):
-                    B.canonical_window_keys_dev(x, n_seq, seq_len, w, kind=kind, out=kout, ctx=ctx)
-                barrier()
-                ev0.record()
-                for _ in range(reps):
-                    B.canonical_window_keys_dev(x, n_seq, seq_len, w, kind=kind, out=kout, ctx=ctx)
-                ev1.record()
-                barrier()
-                k_ms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
+                k_ms = timed(lambda: B.canonical_window_keys_dev(x, n_seq, seq_len, w, kind=kind, out=kout, ctx=ctx))
                 k_gbs = nwin * (1 + kb) / (k_ms * 1e-3) / 1e9
                 keys[label] = {"ms": k_ms, "windows_per_s": world * nwin / (k_ms * 1e-3), "key_bytes": kb,
                                "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": None,
@@ -646,6 +668,7 @@ def main():
                "sample": f"{n_cpu} reads x {READ_LEN} nt x {reps} reps ({s1:.1f} s), oracle/qd_oracle.c single thread",
                "all_threads": {"value": vN, "cores": threads, "seconds": sN}}
 
+    fill_leg_traffic(extra)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -1911,14 +1911,32 @@ __device__ __forceinline__ uint64_t scan_value(const uint64_t* src, uint64_t i) 
     return src[i];
 }
 
+// a thread's SCAN_ITEMS consecutive values (0 past n): 128-bit loads for raw values in an aligned array
+template <int MODE>
+__device__ __forceinline__ void scan_load_items(const uint64_t* src, uint64_t n, uint64_t base, uint64_t (&v)[SCAN_ITEMS]) {
+    static_assert(SCAN_ITEMS % 2 == 0, "pairs of values per 128-bit access");
+    if (MODE == 1 && base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k += 2) {
+            const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(src + base + k);
+            v[k] = x.x;
+            v[k + 1] = x.y;
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < n) ? scan_value<MODE>(src, base + k) : 0;
+}
+
 template <int MODE, int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint64_t* src, uint64_t n, uint64_t* block_sums) {
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint64_t v[SCAN_ITEMS];
+    scan_load_items<MODE>(src, n, base, v);
     uint64_t s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) s = scan_comb<OP>(s, scan_value<MODE>(src, base + k));
+    for (int k = 0; k < SCAN_ITEMS; k++) s = scan_comb<OP>(s, v[k]);
     uint64_t total;
     block_exclusive_scan_op<OP>(s, &total, warp_sums);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -1931,13 +1949,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* bloc
     __shared__ uint64_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (uint64_t base = 0; base < n_blocks; base += SCAN_THREADS) {
-        const uint64_t i = base + threadIdx.x;
-        const uint64_t v = i < n_blocks ? block_sums[i] : 0;
+    for (uint64_t base = 0; base < n_blocks; base += SCAN_BLOCK) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        uint64_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = i0 + k < n_blocks ? block_sums[i0 + k] : 0;
+            s = scan_comb<OP>(s, v[k]);
+        }
         uint64_t total;
-        const uint64_t ex = block_exclusive_scan_op<OP>(v, &total, warp_sums);
+        uint64_t ex = block_exclusive_scan_op<OP>(s, &total, warp_sums);
         const uint64_t carry = carry_s;
-        if (i < n_blocks) block_sums[i] = scan_comb<OP>(carry, ex);
+        ex = scan_comb<OP>(carry, ex);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (i0 + k < n_blocks) block_sums[i0 + k] = ex;
+            ex = scan_comb<OP>(ex, v[k]);
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = scan_comb<OP>(carry, total);
         __syncthreads();
@@ -1951,14 +1979,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS];
+    scan_load_items<MODE>(src, n, base, v);
     uint64_t s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = (base + k < n) ? scan_value<MODE>(src, base + k) : 0;
-        s = scan_comb<OP>(s, v[k]);
-    }
+    for (int k = 0; k < SCAN_ITEMS; k++) s = scan_comb<OP>(s, v[k]);
     uint64_t total;
     uint64_t ex = scan_comb<OP>(block_exclusive_scan_op<OP>(s, &total, warp_sums), block_sums[blockIdx.x]);
+    if (base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {  // whole group: 128-bit stores
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k += 2) {
+            ulonglong2 o;
+            o.x = ex;
+            ex = scan_comb<OP>(ex, v[k]);
+            o.y = ex;
+            ex = scan_comb<OP>(ex, v[k + 1]);
+            *reinterpret_cast<ulonglong2*>(dst + base + k) = o;
+        }
+        if (base + SCAN_ITEMS == n) dst[n] = ex;
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         if (base + k < n) dst[base + k] = ex;
@@ -2118,43 +2157,57 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseP
     const uint32_t pair_base = smem_u32(pair_s);
     const uintptr_t in_lo = reinterpret_cast<uintptr_t>(p.in);
     const bool same_phase = ((reinterpret_cast<uintptr_t>(p.out) ^ in_lo) & 15u) == 0;
-    for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        // dense block (every byte a nucleotide: its output is as long as its input) that lands exactly where the first pass
-        // guessed (nothing was dropped before it): already written
-        if (same_phase && p.offsets[blk + 1] - p.offsets[blk] == PARSE_BLOCK_BYTES &&
-            p.offsets[blk] + (in_lo & 15) == blk * (uint64_t)PARSE_BLOCK_BYTES)
-            continue;
-        // dense block landing on a 16-byte boundary: no compaction, no staging -- translate my granule and store it
-        if (p.offsets[blk + 1] - p.offsets[blk] == PARSE_BLOCK_BYTES && ((reinterpret_cast<uintptr_t>(p.out) + p.offsets[blk]) & 15u) == 0) {
-            uint4 fast;
-            if (parse_granule_fast(p, pair_base, blk * PARSE_THREADS + threadIdx.x, fast)) {  // always true here
-                stg_stream(p.out + p.offsets[blk] + 16 * threadIdx.x, fast);
-                continue;
-            }
+    // This CTA owns blocks blockIdx.x + k * gridDim.x.  Which of them the first pass already finished is decided for
+    // PARSE_THREADS of them at a time, one block per thread (a CTA-wide loop with the check inside pays one dependent
+    // global load per block: 57 us for 250 M clean letters, against 3 us this way).
+    __shared__ uint8_t todo_s[PARSE_THREADS];
+    for (uint64_t k0 = 0; blockIdx.x + k0 * gridDim.x < n_blocks; k0 += PARSE_THREADS) {
+        const uint64_t mine = blockIdx.x + (k0 + threadIdx.x) * gridDim.x;
+        bool todo = false;
+        if (mine < n_blocks) {
+            // dense block (every byte a nucleotide: its output is as long as its input) that lands exactly where the first
+            // pass guessed (nothing was dropped before it): already written
+            const uint64_t o0 = p.offsets[mine], o1 = p.offsets[mine + 1];
+            todo = !(same_phase && o1 - o0 == PARSE_BLOCK_BYTES && o0 + (in_lo & 15) == mine * (uint64_t)PARSE_BLOCK_BYTES);
         }
-        uint8_t v[16];
-        uint32_t kept;
-        int bad;
-        parse_load(p, tab_s, blk * PARSE_THREADS + threadIdx.x, v, kept, bad);
-        uint64_t total;
-        const uint32_t off = (uint32_t)block_exclusive_scan((uint64_t)kept, &total, warp_sums);
-        const uint64_t out0 = p.offsets[blk];
-        uint8_t* gdst = p.out + out0;
-        const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
-        uint32_t at = phase + off;
+        __syncthreads();  // the previous round no longer reads todo_s
+        todo_s[threadIdx.x] = todo ? 1 : 0;
+        if (!__syncthreads_or(todo ? 1 : 0)) continue;
+        for (int j = 0; j < PARSE_THREADS; j++) {
+            if (!todo_s[j]) continue;
+            const uint64_t blk = blockIdx.x + (k0 + j) * gridDim.x;
+            // dense block landing on a 16-byte boundary: no compaction, no staging -- translate my granule and store it
+            if (p.offsets[blk + 1] - p.offsets[blk] == PARSE_BLOCK_BYTES && ((reinterpret_cast<uintptr_t>(p.out) + p.offsets[blk]) & 15u) == 0) {
+                uint4 fast;
+                if (parse_granule_fast(p, pair_base, blk * PARSE_THREADS + threadIdx.x, fast)) {  // always true here
+                    stg_stream(p.out + p.offsets[blk] + 16 * threadIdx.x, fast);
+                    continue;
+                }
+            }
+            uint8_t v[16];
+            uint32_t kept;
+            int bad;
+            parse_load(p, tab_s, blk * PARSE_THREADS + threadIdx.x, v, kept, bad);
+            uint64_t total;
+            const uint32_t off = (uint32_t)block_exclusive_scan((uint64_t)kept, &total, warp_sums);
+            const uint64_t out0 = p.offsets[blk];
+            uint8_t* gdst = p.out + out0;
+            const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
+            uint32_t at = phase + off;
 #pragma unroll
-        for (int k = 0; k < 16; k++)
-            if (v[k] != 0 && v[k] != PARSE_SKIP) stage[at++] = v[k];
-        __syncthreads();
-        const uint32_t nbytes = (uint32_t)total;
-        const uint32_t head = min(nbytes, (16u - phase) & 15u);
-        const uint32_t body = (nbytes - head) >> 4;
-        if (threadIdx.x < head) gdst[threadIdx.x] = stage[phase + threadIdx.x];
-        for (uint32_t c = threadIdx.x; c < body; c += PARSE_THREADS)
-            stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(stage + phase + head + 16 * c));
-        const uint32_t done = head + 16 * body;
-        if (threadIdx.x < nbytes - done) gdst[done + threadIdx.x] = stage[phase + done + threadIdx.x];
-        __syncthreads();
+            for (int k = 0; k < 16; k++)
+                if (v[k] != 0 && v[k] != PARSE_SKIP) stage[at++] = v[k];
+            __syncthreads();
+            const uint32_t nbytes = (uint32_t)total;
+            const uint32_t head = min(nbytes, (16u - phase) & 15u);
+            const uint32_t body = (nbytes - head) >> 4;
+            if (threadIdx.x < head) gdst[threadIdx.x] = stage[phase + threadIdx.x];
+            for (uint32_t c = threadIdx.x; c < body; c += PARSE_THREADS)
+                stg_stream(gdst + head + 16 * c, *reinterpret_cast<const uint4*>(stage + phase + head + 16 * c));
+            const uint32_t done = head + 16 * body;
+            if (threadIdx.x < nbytes - done) gdst[done + threadIdx.x] = stage[phase + done + threadIdx.x];
+            __syncthreads();
+        }
     }
 }
 
