@@ -389,8 +389,11 @@ def main():
             B.parse_dev(x[:n_rc], out=masks, ctx=ctx)
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
+        p_gbs = 2 * n_rc / (v_ms * 1e-3) / 1e9
         extra["parse"] = {"workload": f"ASCII -> mask parse of {n_rc} nt (count pass + scan + compacting write pass)", "ms": v_ms,
-                          "nt_per_s": world * n_rc / (v_ms * 1e-3), "GB/s_algorithmic": 2 * n_rc / (v_ms * 1e-3) / 1e9}
+                          "nt_per_s": world * n_rc / (v_ms * 1e-3), "GB/s_algorithmic": p_gbs,
+                          "roofline": {"bound": "hbm", "achieved": p_gbs, "peak": peak, "unit": "GB/s", "frac": p_gbs / peak, "traffic": None,
+                                       "kernel": "parse_count_kernel + scan + parse_write_kernel", "algorithmic_bytes_per_launch": 2 * n_rc}}
         extra["revcomp_variants"] = variants
         del masks, cnt
 
@@ -425,7 +428,7 @@ def main():
         f3 = sum((READ_LEN - k) // 3 for k in range(3))
         ms1 = timed(lambda: B.translate_frames_uniform_dev(x[:nt_v], n_v, READ_LEN, out=out, table=args.table, frames=1, ctx=ctx))
         leg("translate_1_frame", f"translate (1 frame) on {n_v} x {READ_LEN}-nt reads per GPU", ms1, nt_v, n_v * (READ_LEN + f1),
-            "translate_frames_kernel<1, 1024, direct>", ncu_traffic("translate_frames_kernel<1,direct>", reads=n_v, read_len=READ_LEN))
+            "translate_frames_kernel<1, 1024, direct>")
         ms3 = timed(lambda: B.translate_frames_uniform_dev(x[:nt_v], n_v, READ_LEN, out=out, table=args.table, frames=3, ctx=ctx))
         leg("translate_self_frames", f"translate_self_frames (3 frames) on {n_v} x {READ_LEN}-nt reads per GPU", ms3, nt_v,
             n_v * (READ_LEN + f3), "translate_frames_kernel<3, 1024>")
@@ -615,8 +618,7 @@ def main():
                 "workload": f"expansions of {n_win} 42-nt windows with exactly 2 ambiguity codes, cap 16, per GPU: {n_rows} rows "
                             "(size_hint kernel + scan + write kernel per call)",
                 "rows_per_s": world * n_rows / (ex_ms * 1e-3), "windows_per_s": world * n_win / (ex_ms * 1e-3), "ms": ex_ms,
-                "roofline": {"bound": "hbm", "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak,
-                             "traffic": ncu_traffic("expansion_windows", windows=n_win, w=w),
+                "roofline": {"bound": "hbm", "achieved": ex_gbs, "peak": peak, "unit": "GB/s", "frac": ex_gbs / peak, "traffic": None,
                              "kernel": "expansion_count_tiles_kernel<ascii, 42> + scan + expansion_write_tiles_kernel<42>", "algorithmic_bytes_per_launch": ex_bytes}}
             del win, c_d, oi_d
 

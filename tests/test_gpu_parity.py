@@ -443,7 +443,7 @@ def test_parse_dev_clean_blocks_then_dropped_bytes(B):
 
     rng = np.random.default_rng(23)
     n = 9 * 4096 + 123
-    for first_blank in (None, 0, 5, 4095, 4096, 3 * 4096 + 17, n - 1):
+    for first_blank in (None, 0, 5, 4095, 4096, 3 * 4096 + 17, 16383, 16384, 2 * 16384 + 17, n - 1):
         for in_lead, out_lead in ((0, 0), (0, 16), (3, 3), (3, 0), (16, 5), (7, 23)):
             a = np.frombuffer(_rand(rng, n, b"ACGTacgtNRY"), dtype=np.uint8).copy()
             if first_blank is not None:
