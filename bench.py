@@ -378,12 +378,15 @@ def main():
         v_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 10
         variants["mask_encoding"] = {"nt": n_rc, "ms": v_ms, "GB/s": 2 * n_rc / (v_ms * 1e-3) / 1e9, "note": "one buffer set reused (partly L2-resident)"}
         # ASCII -> mask parse itself (src/rust_api.rs:310-322), 2 B per input byte
+        for _ in range(3):
+            B.parse_dev(x[:n_rc], out=masks, ctx=ctx)
+        barrier()
         ev0.record()
-        for _ in range(5):
+        for _ in range(20):
             B.parse_dev(x[:n_rc], out=masks, ctx=ctx)
         ev1.record()
         barrier()
-        v_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 5
+        v_ms = max_over_ranks(ev0.elapsed_time(ev1)) / 20
         if ncu_legs:
             torch.cuda.profiler.start()
             B.parse_dev(x[:n_rc], out=masks, ctx=ctx)
