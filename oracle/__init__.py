@@ -41,15 +41,50 @@ class _Err(C.Structure):
     _fields_ = [("kind", C.c_int32), ("byte", C.c_uint8), ("pos", C.c_uint64)]
 
 
+def _cpu_signature() -> str:
+    """What `-march=native` depends on: the library built on one host must not be loaded on another."""
+    import hashlib
+
+    model, flags = "", ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name") and not model:
+                    model = line.split(":", 1)[1].strip()
+                elif line.startswith("flags") and not flags:
+                    flags = " ".join(sorted(line.split(":", 1)[1].split()))
+                if model and flags:
+                    break
+    except OSError:
+        pass
+    with open(os.path.join(_HERE, "Makefile"), "rb") as f:
+        mk = f.read()
+    return hashlib.sha256((model + "|" + flags).encode() + mk).hexdigest()[:16]
+
+
 def build(force: bool = False) -> str:
-    """Compile the oracle with gcc (oracle/Makefile).  Building the checker is not using it."""
+    """Compile the oracle with gcc (oracle/Makefile).  Building the checker is not using it.
+
+    Rebuilt when a source is newer than the library or when the library was built for another CPU (the snapshot that
+    travels to the GPU box carries the library built in the development container)."""
     src = os.path.join(_HERE, "qd_oracle.c")
-    stale = (not os.path.exists(_LIB_PATH)) or any(
+    sig_path = os.path.join(_HERE, ".build_sig")
+    sig = _cpu_signature()
+    try:
+        with open(sig_path) as f:
+            built_for = f.read().strip()
+    except OSError:
+        built_for = ""
+    stale = (not os.path.exists(_LIB_PATH)) or built_for != sig or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("qd_oracle.c", "qd_oracle.h", "ncbi_codes.h")
+        for f in ("qd_oracle.c", "qd_oracle.h", "ncbi_codes.h", "Makefile")
     )
     if force or stale:
-        subprocess.run(["make", "-C", _HERE, "-B", "libqd_oracle.so"], check=True, capture_output=True)
+        r = subprocess.run(["make", "-C", _HERE, "-B", "libqd_oracle.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building oracle/libqd_oracle.so failed:\n" + r.stdout + r.stderr)
+        with open(sig_path, "w") as f:
+            f.write(sig + "\n")
     assert os.path.exists(src)
     return _LIB_PATH
 
@@ -97,6 +132,18 @@ def lib() -> C.CDLL:
         L.qdo_bench_all_frames_batch.restype = C.c_double
         L.qdo_bench_revcomp.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
         L.qdo_bench_revcomp.restype = C.c_double
+        L.qdo_synth.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_char_p, C.c_size_t, C.c_void_p]
+        L.qdo_synth.restype = None
+        L.qdo_checksum64.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
+        L.qdo_checksum64.restype = C.c_uint64
+        L.qdo_check_frames_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int]
+        L.qdo_check_frames_uniform.restype = C.c_uint64
+        L.qdo_check_revcomp.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+        L.qdo_check_revcomp.restype = C.c_uint64
+        L.qdo_check_windows.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+        L.qdo_check_windows.restype = C.c_uint64
+        L.qdo_check_expansions.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+        L.qdo_check_expansions.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -371,3 +418,48 @@ def bench_revcomp(dna: np.ndarray, threads: int, reps: int = 1) -> Tuple[float, 
     out = np.empty(a.size, dtype=np.uint8)
     secs = lib().qdo_bench_revcomp(_ptr(a), a.size, _ptr(out), threads, reps)
     return secs, out
+
+
+# --------------------------------------------------------------------------- synthetic configs as checksums
+
+
+def synth(seed: int, start: int, count: int, alphabet: bytes = b"ACGT") -> np.ndarray:
+    """quickdna_b200/synth.py synth_np, in C (the whole-config checks generate their input with it)."""
+    out = np.empty(count, dtype=np.uint8)
+    lib().qdo_synth(seed, start, count, alphabet, len(alphabet), _ptr(out))
+    return out
+
+
+def checksum64(buf, base: int = 0) -> int:
+    """The position-weighted linear checksum of qd_checksum64_dev: `buf` = bytes [base, base + len) of a stream."""
+    a = _as_u8(buf)
+    return int(lib().qdo_checksum64(_ptr(a), a.size, base))
+
+
+def check_frames_uniform(seed: int, first_read: int, n_reads: int, read_len: int, slot: int = 0, frames: int = 6, threads: int = 1) -> int:
+    return int(lib().qdo_check_frames_uniform(seed, first_read, n_reads, read_len, slot, frames, threads))
+
+
+def check_revcomp(seed: int, start: int, n: int, strict: bool = False, threads: int = 1) -> int:
+    return int(lib().qdo_check_revcomp(seed, start, n, int(strict), threads))
+
+
+def check_canonical_windows(dna, n_seq: int, seq_len: int, w: int = 42, threads: int = 1) -> int:
+    a = _as_u8(dna)
+    assert a.size == n_seq * seq_len
+    return int(lib().qdo_check_windows(0, _ptr(a), n_seq, seq_len, w, 0, threads))
+
+
+def check_windows_all(dna, n_seq: int, seq_len: int, w_dna: int = 42, w_aa: int = 20, threads: int = 1) -> int:
+    a = _as_u8(dna)
+    assert a.size == n_seq * seq_len
+    return int(lib().qdo_check_windows(1, _ptr(a), n_seq, seq_len, w_dna, w_aa, threads))
+
+
+def check_expansions(windows, cap: int = 16, threads: int = 1) -> Tuple[int, int]:
+    """(checksum of the expansion rows, number of rows) of a [n_win, w] uint8 array of ASCII windows."""
+    a = _as_u8(windows)
+    assert a.ndim == 2
+    rows = C.c_uint64()
+    s = lib().qdo_check_expansions(_ptr(a), a.shape[0], a.shape[1], cap, threads, C.byref(rows))
+    return int(s), int(rows.value)

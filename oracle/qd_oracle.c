@@ -19,77 +19,50 @@
 /* src/nucleotide.rs:20-28, 31-53: the in-memory value IS the 4-bit IUPAC set. */
 enum { M_A = 1, M_T = 2, M_C = 4, M_G = 8 };
 
-/* src/nucleotide.rs:66-101: ASCII -> mask, 0 = None. Upper and lower case both accepted. */
-static uint8_t ascii_to_mask(uint8_t b) {
-    switch (b) {
-        case 'a': case 'A': return M_A;
-        case 't': case 'T': return M_T;
-        case 'c': case 'C': return M_C;
-        case 'g': case 'G': return M_G;
-        case 'n': case 'N': return M_A | M_T | M_C | M_G;
-        case 'm': case 'M': return M_A | M_C;
-        case 'r': case 'R': return M_A | M_G;
-        case 'w': case 'W': return M_A | M_T;
-        case 's': case 'S': return M_C | M_G;
-        case 'y': case 'Y': return M_T | M_C;
-        case 'k': case 'K': return M_T | M_G;
-        case 'v': case 'V': return M_A | M_C | M_G;
-        case 'h': case 'H': return M_A | M_T | M_C;
-        case 'd': case 'D': return M_A | M_T | M_G;
-        case 'b': case 'B': return M_T | M_C | M_G;
-        default: return 0;
-    }
-}
+/* src/nucleotide.rs:66-101: ASCII -> mask, 0 = None, as the reference's 256-entry ASCII_TO_NUCLEOTIDE table
+ * (its PERF comment: 256 entries so that any u8 indexes it without a bounds check). */
+#define BOTH_CASES(ch, m) [ch] = (m), [(ch) + 32] = (m)
+static const uint8_t ASCII_TO_MASK[256] = {
+    BOTH_CASES('A', M_A), BOTH_CASES('T', M_T), BOTH_CASES('C', M_C), BOTH_CASES('G', M_G),
+    BOTH_CASES('N', M_A | M_T | M_C | M_G), BOTH_CASES('M', M_A | M_C), BOTH_CASES('R', M_A | M_G),
+    BOTH_CASES('W', M_A | M_T), BOTH_CASES('S', M_C | M_G), BOTH_CASES('Y', M_T | M_C),
+    BOTH_CASES('K', M_T | M_G), BOTH_CASES('V', M_A | M_C | M_G), BOTH_CASES('H', M_A | M_T | M_C),
+    BOTH_CASES('D', M_A | M_T | M_G), BOTH_CASES('B', M_T | M_C | M_G),
+};
+#undef BOTH_CASES
 
 /* src/nucleotide.rs:138-145, 219-237: always upper case. */
-uint8_t qdo_mask_to_ascii(uint8_t m) {
-    static const char LETTERS[16] = {'?', 'A', 'T', 'W', 'C', 'M', 'Y', 'H',
-                                     'G', 'R', 'K', 'D', 'S', 'V', 'B', 'N'};
-    return (uint8_t)LETTERS[m & 15];
-}
+static const uint8_t MASK_TO_ASCII[16] = {'?', 'A', 'T', 'W', 'C', 'M', 'Y', 'H', 'G', 'R', 'K', 'D', 'S', 'V', 'B', 'N'};
+static inline uint8_t mask_to_ascii(uint8_t m) { return MASK_TO_ASCII[m & 15]; }
+uint8_t qdo_mask_to_ascii(uint8_t m) { return mask_to_ascii(m); }
 
-/* src/nucleotide.rs:125-132, 195-213, written out as the reference's match. */
-uint8_t qdo_complement_mask(uint8_t m) {
-    switch (m) {
-        case 1: return 2;    /* A -> T */
-        case 2: return 1;    /* T -> A */
-        case 3: return 3;    /* W -> W */
-        case 4: return 8;    /* C -> G */
-        case 5: return 10;   /* M -> K */
-        case 6: return 9;    /* Y -> R */
-        case 7: return 11;   /* H -> D */
-        case 8: return 4;    /* G -> C */
-        case 9: return 6;    /* R -> Y */
-        case 10: return 5;   /* K -> M */
-        case 11: return 7;   /* D -> H */
-        case 12: return 12;  /* S -> S */
-        case 13: return 14;  /* V -> B */
-        case 14: return 13;  /* B -> V */
-        case 15: return 15;  /* N -> N */
-        default: return 0;
-    }
-}
+/* src/nucleotide.rs:125-132, 195-213: the reference's match (A<->T, C<->G, M<->K, R<->Y, H<->D, V<->B; W, S, N fixed)
+ * as the table a compiler makes of it; 0 for a byte that is no mask. */
+static const uint8_t COMPLEMENT[16] = {0, 2, 1, 3, 8, 10, 9, 11, 4, 6, 5, 7, 12, 14, 13, 15};
+static inline uint8_t complement_mask(uint8_t m) { return m < 16 ? COMPLEMENT[m] : 0; }
+uint8_t qdo_complement_mask(uint8_t m) { return complement_mask(m); }
 
-static int popcount4(uint8_t m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
+static inline int popcount4(uint8_t m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
 
 /* src/nucleotide.rs:285-299 (strict) / :301-315 (ambiguous) / :268-283 (ambiguous -> strict). */
-int qdo_decode_byte(uint8_t b, int strict, uint8_t *mask, uint8_t *payload) {
+static inline int decode_byte(uint8_t b, int strict, uint8_t *mask, uint8_t *payload) {
     if (b >= 128) {
         *payload = b;
         return QDO_NON_ASCII_BYTE;
     }
-    uint8_t m = ascii_to_mask(b);
+    uint8_t m = ASCII_TO_MASK[b];
     if (m == 0) {
         *payload = b; /* BadNucleotide(u.into()): the char as given, case preserved */
         return QDO_BAD_NUCLEOTIDE;
     }
-    if (strict && popcount4(m) > 1) {
-        *payload = qdo_mask_to_ascii(m); /* other.into(): upper-case letter of the code */
+    if (strict && (m & (m - 1))) {
+        *payload = mask_to_ascii(m); /* other.into(): upper-case letter of the code */
         return QDO_UNEXPECTED_AMBIGUOUS;
     }
     *mask = m;
     return QDO_OK;
 }
+int qdo_decode_byte(uint8_t b, int strict, uint8_t *mask, uint8_t *payload) { return decode_byte(b, strict, mask, payload); }
 
 /* Rust `{:?}` of a char (core::char::EscapeDebug) for ASCII inputs. */
 static int fmt_char_debug(uint8_t c, char *buf, size_t cap) {
@@ -224,7 +197,7 @@ int qdo_translate_bytes(int ncbi_id, int strict, const uint8_t *dna, size_t n, u
         uint8_t m[3];
         for (int j = 0; j < 3; j++) {
             uint8_t payload = 0;
-            int rc = qdo_decode_byte(dna[i + j], strict, &m[j], &payload);
+            int rc = decode_byte(dna[i + j], strict, &m[j], &payload);
             if (rc != QDO_OK) {
                 err->kind = rc;
                 err->byte = payload;
@@ -243,14 +216,14 @@ int qdo_revcomp_bytes(int strict, const uint8_t *dna, size_t n, uint8_t *out, qd
     memset(out, 0, n); /* vec![0u8; n] */
     for (size_t i = 0; i < n; i++) {
         uint8_t m = 0, payload = 0;
-        int rc = qdo_decode_byte(dna[i], strict, &m, &payload);
+        int rc = decode_byte(dna[i], strict, &m, &payload);
         if (rc != QDO_OK) {
             err->kind = rc;
             err->byte = payload;
             err->pos = i;
             return rc;
         }
-        out[n - 1 - i] = qdo_mask_to_ascii(qdo_complement_mask(m));
+        out[n - 1 - i] = mask_to_ascii(complement_mask(m));
     }
     err->kind = QDO_OK;
     return QDO_OK;
@@ -258,7 +231,7 @@ int qdo_revcomp_bytes(int strict, const uint8_t *dna, size_t n, uint8_t *out, qd
 
 /* src/trans_table.rs:284-286 */
 void qdo_revcomp_masks(const uint8_t *m, size_t n, uint8_t *out) {
-    for (size_t i = 0; i < n; i++) out[i] = qdo_complement_mask(m[n - 1 - i]);
+    for (size_t i = 0; i < n; i++) out[i] = complement_mask(m[n - 1 - i]);
 }
 
 /* src/rust_api.rs:227-255 */
@@ -333,7 +306,7 @@ int qdo_parse(int strict, const uint8_t *ascii, size_t n, uint8_t *masks, size_t
         uint8_t b = ascii[i];
         if (b != ' ' && b != '\t') {
             uint8_t m = 0, payload = 0;
-            int rc = qdo_decode_byte(b, strict, &m, &payload);
+            int rc = decode_byte(b, strict, &m, &payload);
             if (rc != QDO_OK) {
                 err->kind = rc;
                 err->byte = payload;
@@ -403,7 +376,7 @@ int qdo_fasta_scan(int strict, int concatenate_headers, int allow_preceding_comm
                     const uint8_t b = text[i];
                     if (b == ' ' || b == '\t') continue; /* src/rust_api.rs:316 */
                     uint8_t m = 0, payload = 0;
-                    const int rc = qdo_decode_byte(b, strict, &m, &payload);
+                    const int rc = decode_byte(b, strict, &m, &payload);
                     if (rc != QDO_OK) {
                         err->kind = rc;
                         err->byte = payload;
@@ -579,9 +552,9 @@ size_t qdo_windows_all(const uint8_t *m, size_t n, size_t w_dna, size_t w_aa, ui
     uint8_t *rc_ascii = (uint8_t *)malloc(n ? n : 1);
     uint8_t *aa = (uint8_t *)malloc(2 * n + 16);
     size_t lens[6];
-    for (size_t i = 0; i < n; i++) ascii[i] = qdo_mask_to_ascii(m[i]);
+    for (size_t i = 0; i < n; i++) ascii[i] = mask_to_ascii(m[i]);
     qdo_revcomp_masks(m, n, rc);
-    for (size_t i = 0; i < n; i++) rc_ascii[i] = qdo_mask_to_ascii(rc[i]);
+    for (size_t i = 0; i < n; i++) rc_ascii[i] = mask_to_ascii(rc[i]);
     int n_frames = qdo_all_frames_masks(0 /* Ncbi1 */, m, n, aa, lens);
 
     size_t total = 0;
@@ -633,6 +606,37 @@ size_t qdo_windows_all(const uint8_t *m, size_t n, size_t w_dna, size_t w_aa, ui
     return total;
 }
 
+/* ---------------------------------------------------------------- thread pool ----- */
+
+/* One set of threads per call: job k of n_jobs goes to thread k % threads (jobs are equal-sized by construction). */
+typedef void (*job_fn)(void *ctx, size_t job);
+typedef struct {
+    job_fn fn;
+    void *ctx;
+    size_t first, n_jobs, stride;
+} pool_arg;
+
+static void *pool_thread(void *a) {
+    pool_arg *p = (pool_arg *)a;
+    for (size_t j = p->first; j < p->n_jobs; j += p->stride) p->fn(p->ctx, j);
+    return NULL;
+}
+
+static void run_jobs(job_fn fn, void *ctx, size_t n_jobs, int threads) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n_jobs) threads = n_jobs ? (int)n_jobs : 1;
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    pool_arg *arg = (pool_arg *)malloc(sizeof(pool_arg) * (size_t)threads);
+    for (int t = 0; t < threads; t++) {
+        arg[t].fn = fn, arg[t].ctx = ctx, arg[t].first = (size_t)t, arg[t].n_jobs = n_jobs, arg[t].stride = (size_t)threads;
+        if (t) pthread_create(&tid[t], NULL, pool_thread, &arg[t]);
+    }
+    pool_thread(&arg[0]);
+    for (int t = 1; t < threads; t++) pthread_join(tid[t], NULL);
+    free(tid);
+    free(arg);
+}
+
 /* ---------------------------------------------------------------- timed baseline -- */
 
 static double now_s(void) {
@@ -642,91 +646,337 @@ static double now_s(void) {
 }
 
 typedef struct {
-    int slot;
+    int slot, threads, reps;
     const uint8_t *dna;
-    size_t r0, r1, read_len;
+    size_t n_reads, read_len;
     uint8_t *out;
 } frames_job;
 
-static void *frames_worker(void *arg) {
-    frames_job *j = (frames_job *)arg;
-    size_t L = j->read_len;
-    size_t out_per_read = L >= 2 ? 2 * (L - 2) : 0;
-    uint8_t *masks = (uint8_t *)malloc(L ? L : 1);
-    size_t lens[6];
-    for (size_t r = j->r0; r < j->r1; r++) {
-        const uint8_t *src = j->dna + r * L;
-        /* the parse of rust_api.rs:310-322 (validation lives here on the Rust path) */
-        qdo_err e;
-        size_t nm = 0;
-        if (qdo_parse(0, src, L, masks, &nm, &e) != QDO_OK) continue;
-        qdo_all_frames_masks(j->slot, masks, nm, j->out + r * out_per_read, lens);
-    }
+/* one thread's share of the batch, `reps` times over: per read the parse of rust_api.rs:310-322 (validation lives
+ * there on the Rust path), then translate_all_frames (:263-270).  Scratch is per thread, not per read (the reference
+ * allocates seven Vecs per read; none of that is charged here). */
+static void frames_worker(void *ctx, size_t t) {
+    const frames_job *j = (const frames_job *)ctx;
+    const size_t L = j->read_len, out_per_read = L >= 2 ? 2 * (L - 2) : 0;
+    const size_t r0 = j->n_reads * t / (size_t)j->threads, r1 = j->n_reads * (t + 1) / (size_t)j->threads;
+    const uint8_t *table = qdo_tables() + (size_t)j->slot * QDO_CODONS_PER_TABLE;
+    uint8_t *masks = (uint8_t *)malloc(2 * (L ? L : 1)), *rc = masks + (L ? L : 1);
+    for (int rep = 0; rep < j->reps; rep++)
+        for (size_t r = r0; r < r1; r++) {
+            qdo_err e;
+            size_t nm = 0;
+            if (qdo_parse(0, j->dna + r * L, L, masks, &nm, &e) != QDO_OK) continue;
+            uint8_t *o = j->out + r * out_per_read;
+            const int frames = nm >= 5 ? 3 : nm == 4 ? 2 : nm == 3 ? 1 : 0;
+            for (int k = 0; k < frames; k++)
+                for (size_t i = (size_t)k; i + 3 <= nm; i += 3) *o++ = table[codon_idx(masks[i], masks[i + 1], masks[i + 2])];
+            qdo_revcomp_masks(masks, nm, rc);
+            for (int k = 0; k < frames; k++)
+                for (size_t i = (size_t)k; i + 3 <= nm; i += 3) *o++ = table[codon_idx(rc[i], rc[i + 1], rc[i + 2])];
+        }
     free(masks);
-    return NULL;
 }
 
 double qdo_bench_all_frames_batch(int slot, const uint8_t *dna, size_t n_reads, size_t read_len,
                                   uint8_t *out, int threads, int reps) {
     if (threads < 1) threads = 1;
     qdo_tables();
-    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
-    frames_job *jobs = (frames_job *)malloc(sizeof(frames_job) * (size_t)threads);
-    double t0 = now_s();
-    for (int rep = 0; rep < reps; rep++) {
-        for (int t = 0; t < threads; t++) {
-            jobs[t].slot = slot;
-            jobs[t].dna = dna;
-            jobs[t].read_len = read_len;
-            jobs[t].out = out;
-            jobs[t].r0 = n_reads * (size_t)t / (size_t)threads;
-            jobs[t].r1 = n_reads * (size_t)(t + 1) / (size_t)threads;
-            pthread_create(&tid[t], NULL, frames_worker, &jobs[t]);
-        }
-        for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
-    }
-    double dt = now_s() - t0;
-    free(tid);
-    free(jobs);
-    return dt;
+    frames_job j = {slot, threads, reps, dna, n_reads, read_len, out};
+    const double t0 = now_s();
+    run_jobs(frames_worker, &j, (size_t)threads, threads);
+    return now_s() - t0;
 }
 
 typedef struct {
     const uint8_t *dna;
-    size_t n, i0, i1;
+    size_t n;
     uint8_t *out;
+    int threads, reps;
 } rc_job;
 
-/* one thread's share of the loop at src/trans_table.rs:273-276 */
-static void *rc_worker(void *arg) {
-    rc_job *j = (rc_job *)arg;
-    memset(j->out + (j->n - j->i1), 0, j->i1 - j->i0);
-    for (size_t i = j->i0; i < j->i1; i++) {
-        uint8_t m = 0, payload = 0;
-        if (qdo_decode_byte(j->dna[i], 0, &m, &payload) != QDO_OK) break;
-        j->out[j->n - 1 - i] = qdo_mask_to_ascii(qdo_complement_mask(m));
+/* one thread's share of the loop at src/trans_table.rs:273-276 (zero-filled Vec, then the reversed indexed store) */
+static void rc_worker(void *ctx, size_t t) {
+    const rc_job *j = (const rc_job *)ctx;
+    const size_t i0 = j->n * t / (size_t)j->threads, i1 = j->n * (t + 1) / (size_t)j->threads;
+    for (int rep = 0; rep < j->reps; rep++) {
+        memset(j->out + (j->n - i1), 0, i1 - i0);
+        for (size_t i = i0; i < i1; i++) {
+            uint8_t m = 0, payload = 0;
+            if (decode_byte(j->dna[i], 0, &m, &payload) != QDO_OK) break;
+            j->out[j->n - 1 - i] = mask_to_ascii(complement_mask(m));
+        }
     }
-    return NULL;
 }
 
 double qdo_bench_revcomp(const uint8_t *dna, size_t n, uint8_t *out, int threads, int reps) {
     if (threads < 1) threads = 1;
-    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
-    rc_job *jobs = (rc_job *)malloc(sizeof(rc_job) * (size_t)threads);
-    double t0 = now_s();
-    for (int rep = 0; rep < reps; rep++) {
-        for (int t = 0; t < threads; t++) {
-            jobs[t].dna = dna;
-            jobs[t].n = n;
-            jobs[t].out = out;
-            jobs[t].i0 = n * (size_t)t / (size_t)threads;
-            jobs[t].i1 = n * (size_t)(t + 1) / (size_t)threads;
-            pthread_create(&tid[t], NULL, rc_worker, &jobs[t]);
-        }
-        for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
+    rc_job j = {dna, n, out, threads, reps};
+    const double t0 = now_s();
+    run_jobs(rc_worker, &j, (size_t)threads, threads);
+    return now_s() - t0;
+}
+
+/* ---------------------------------------------------------------- synthetic input + checksum ------------------- */
+
+static inline uint64_t mix64(uint64_t z) { /* splitmix64 finaliser */
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+/* quickdna_b200/synth.py synth_np: nt[i] = alphabet[(mix64(seed * 0x1000003D + i + GOLD) >> 33) % alen] */
+void qdo_synth(uint64_t seed, uint64_t start, uint64_t count, const uint8_t *alphabet, size_t alen, uint8_t *out) {
+    const uint64_t off = seed * 0x1000003Dull + 0x9e3779b97f4a7c15ull + start;
+    if (alen == 4)
+        for (uint64_t i = 0; i < count; i++) out[i] = alphabet[(mix64(off + i) >> 33) & 3];
+    else
+        for (uint64_t i = 0; i < count; i++) out[i] = alphabet[(mix64(off + i) >> 33) % alen];
+}
+
+/* Position-weighted linear checksum (the one qd_checksum64_dev computes, include/quickdna_b200.h): the buffer is a
+ * piece of a byte stream starting at stream offset `base`; stream word J (bytes 8J..8J+7, little endian) weighs
+ * K(J) = mix64(J * GOLD + 1) | 1, and the checksum is sum_J word_J * K(J) mod 2^64.  Linear in the data, so pieces of
+ * any byte alignment add up to the checksum of the whole. */
+static inline uint64_t weight64(uint64_t word_index) { return mix64(word_index * 0x9e3779b97f4a7c15ull + 1) | 1; }
+
+uint64_t qdo_checksum64(const uint8_t *buf, size_t n, uint64_t base) {
+    uint64_t sum = 0;
+    size_t i = 0;
+    while (i < n && ((base + i) & 7)) { /* head: bytes of a partly covered word */
+        sum += ((uint64_t)buf[i] << (8 * ((base + i) & 7))) * weight64((base + i) >> 3);
+        i++;
     }
-    double dt = now_s() - t0;
-    free(tid);
-    free(jobs);
-    return dt;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, buf + i, 8);
+        sum += w * weight64((base + i) >> 3);
+    }
+    for (; i < n; i++) sum += ((uint64_t)buf[i] << (8 * ((base + i) & 7))) * weight64((base + i) >> 3);
+    return sum;
+}
+
+/* ---- whole-config checks: what the GPU path must produce for the synthetic configs, as a checksum ------------- */
+
+typedef struct {
+    uint64_t seed, first_read, n_reads;
+    size_t read_len;
+    int slot, frames, n_jobs;
+    uint64_t *partial;
+} chk_frames;
+
+/* frames of read r in the slot layout of include/quickdna_b200.h (R = ceil(n/48) runs, 16*R bytes per frame slot,
+ * forward frame k from the start of slot k, reverse frame k ending at the end of slot 3+k, zero padding) */
+static void chk_frames_job(void *ctx, size_t job) {
+    const chk_frames *c = (const chk_frames *)ctx;
+    const size_t L = c->read_len, R = (L + 47) / 48, slot_bytes = 16 * R, per_read = slot_bytes * (size_t)c->frames;
+    const uint64_t r0 = c->n_reads * job / (uint64_t)c->n_jobs, r1 = c->n_reads * (job + 1) / (uint64_t)c->n_jobs;
+    uint8_t *dna = (uint8_t *)malloc(3 * L + 2 * L + 16 + per_read), *masks = dna + L, *rc = masks + L, *aa = rc + L, *img = aa + 2 * L + 16;
+    uint64_t sum = 0;
+    for (uint64_t r = r0; r < r1; r++) {
+        qdo_synth(c->seed, (c->first_read + r) * L, L, (const uint8_t *)"ACGT", 4, dna);
+        qdo_err e;
+        size_t nm = 0, lens[6] = {0, 0, 0, 0, 0, 0};
+        if (qdo_parse(0, dna, L, masks, &nm, &e) != QDO_OK) continue;
+        if (c->frames == 1) {
+            qdo_translate_masks(c->slot, masks, nm, aa);
+            lens[0] = nm / 3;
+        } else if (c->frames == 3) {
+            qdo_self_frames_masks(c->slot, masks, nm, aa, lens);
+        } else {
+            qdo_all_frames_masks(c->slot, masks, nm, aa, lens);
+        }
+        memset(img, 0, per_read);
+        size_t off = 0;
+        for (int f = 0; f < c->frames; f++) {
+            if (f < 3) memcpy(img + (size_t)f * slot_bytes, aa + off, lens[f]);
+            else memcpy(img + (size_t)(f + 1) * slot_bytes - lens[f], aa + off, lens[f]);
+            off += lens[f];
+        }
+        sum += qdo_checksum64(img, per_read, r * per_read);
+    }
+    c->partial[job] = sum;
+    free(dna);
+}
+
+/* checksum of the slot-layout output of reads [first_read, first_read + n_reads) of the seed's uniform ACGT stream
+ * (read r = stream bytes [r * read_len, (r + 1) * read_len)); the output stream starts at read first_read */
+uint64_t qdo_check_frames_uniform(uint64_t seed, uint64_t first_read, uint64_t n_reads, size_t read_len, int slot, int frames,
+                                  int threads) {
+    qdo_tables();
+    const int n_jobs = threads < 1 ? 1 : threads * 8;
+    uint64_t *partial = (uint64_t *)calloc((size_t)n_jobs, 8);
+    chk_frames c = {seed, first_read, n_reads, read_len, slot, frames, n_jobs, partial};
+    run_jobs(chk_frames_job, &c, (size_t)n_jobs, threads);
+    uint64_t sum = 0;
+    for (int i = 0; i < n_jobs; i++) sum += partial[i];
+    free(partial);
+    return sum;
+}
+
+typedef struct {
+    uint64_t seed, start, n;
+    int n_jobs, strict;
+    uint64_t *partial;
+    int failed;
+} chk_rc;
+
+static void chk_rc_job(void *ctx, size_t job) {
+    chk_rc *c = (chk_rc *)ctx;
+    /* output range [o0, o1), cut at multiples of 64 bytes; input range [n - o1, n - o0) */
+    const uint64_t blocks = (c->n + 63) / 64;
+    uint64_t o0 = blocks * job / (uint64_t)c->n_jobs * 64, o1 = blocks * (job + 1) / (uint64_t)c->n_jobs * 64;
+    if (o1 > c->n) o1 = c->n;
+    uint64_t sum = 0;
+    const uint64_t step = 1 << 20;
+    uint8_t *in = (uint8_t *)malloc(2 * step), *out = in + step;
+    for (uint64_t o = o0; o < o1; o += step) {
+        const uint64_t len = o1 - o < step ? o1 - o : step;
+        qdo_synth(c->seed, c->start + c->n - (o + len), len, (const uint8_t *)"ACGT", 4, in);
+        qdo_err e;
+        if (qdo_revcomp_bytes(c->strict, in, len, out, &e) != QDO_OK) c->failed = 1;
+        sum += qdo_checksum64(out, len, o);
+    }
+    c->partial[job] = sum;
+    free(in);
+}
+
+/* checksum of reverse_complement_bytes of stream bytes [start, start + n) of the seed's uniform ACGT stream */
+uint64_t qdo_check_revcomp(uint64_t seed, uint64_t start, uint64_t n, int strict, int threads) {
+    const int n_jobs = threads < 1 ? 1 : threads * 4;
+    uint64_t *partial = (uint64_t *)calloc((size_t)n_jobs, 8);
+    chk_rc c = {seed, start, n, n_jobs, strict, partial, 0};
+    run_jobs(chk_rc_job, &c, (size_t)n_jobs, threads);
+    uint64_t sum = 0;
+    for (int i = 0; i < n_jobs; i++) sum += partial[i];
+    free(partial);
+    return c.failed ? ~sum : sum;
+}
+
+typedef struct {
+    const uint8_t *dna; /* ASCII, n_seq sequences of seq_len back to back */
+    size_t n_seq, seq_len, w, w_aa;
+    int kind; /* 0 canonical rows, 1 all_windows */
+    uint64_t *partial;
+} chk_win;
+
+static void chk_win_job(void *ctx, size_t s) {
+    const chk_win *c = (const chk_win *)ctx;
+    const size_t L = c->seq_len, w = c->w;
+    const uint8_t *src = c->dna + s * L;
+    uint8_t *masks = (uint8_t *)calloc(L ? L : 1, 1);
+    for (size_t i = 0; i < L; i++) masks[i] = ASCII_TO_MASK[src[i]];
+    uint64_t sum = 0;
+    if (c->kind == 0) {
+        /* qd_canonical_windows_batch_dev layout: [n_seq][n_win][w], input encoding (ASCII, upper case) */
+        const size_t nw = L >= w ? L - w + 1 : 0;
+        uint8_t row[64], asc[64];
+        for (size_t i = 0; i < nw; i++) {
+            qdo_canonical(masks + i, w, row);
+            for (size_t k = 0; k < w; k++) asc[k] = mask_to_ascii(row[k]);
+            sum += qdo_checksum64(asc, w, (uint64_t)(s * nw + i) * w);
+        }
+    } else {
+        /* qd_windows_all_batch_dev layout: dna_out = [fwd: n_seq x c0 x w][rc: n_seq x c0 x w];
+         * aa_out = six blocks [n_seq][c_f][w_aa]; the aa stream is checksummed after the dna stream */
+        size_t counts[8];
+        const size_t total = qdo_windows_all(masks, L, w, c->w_aa, NULL, NULL, NULL, counts);
+        (void)total;
+        uint8_t *dna_out = (uint8_t *)malloc((counts[0] + counts[1]) * w + 1);
+        size_t n_aa = 0;
+        for (int f = 0; f < 6; f++) n_aa += counts[2 + f];
+        uint8_t *aa_out = (uint8_t *)malloc(n_aa * c->w_aa + 1);
+        qdo_windows_all(masks, L, w, c->w_aa, dna_out, aa_out, NULL, counts);
+        const uint64_t fwd_block = (uint64_t)c->n_seq * counts[0] * w;
+        sum += qdo_checksum64(dna_out, counts[0] * w, (uint64_t)s * counts[0] * w);
+        sum += qdo_checksum64(dna_out + counts[0] * w, counts[1] * w, fwd_block + (uint64_t)s * counts[1] * w);
+        uint64_t aa_base = 2 * fwd_block;
+        size_t at = 0;
+        for (int f = 0; f < 6; f++) {
+            sum += qdo_checksum64(aa_out + at * c->w_aa, counts[2 + f] * c->w_aa, aa_base + (uint64_t)s * counts[2 + f] * c->w_aa);
+            aa_base += (uint64_t)c->n_seq * counts[2 + f] * c->w_aa;
+            at += counts[2 + f];
+        }
+        free(dna_out);
+        free(aa_out);
+    }
+    c->partial[s] = sum;
+    free(masks);
+}
+
+/* checksum of the canonical w-nt windows (kind 0) / the all_windows output (kind 1; w = DNA window, w_aa = amino-acid window)
+ * of n_seq strict ASCII sequences of seq_len each, in the layouts of qd_canonical_windows_batch_dev /
+ * qd_windows_all_batch_dev (dna_out stream followed by aa_out stream) */
+uint64_t qdo_check_windows(int kind, const uint8_t *dna, size_t n_seq, size_t seq_len, size_t w, size_t w_aa, int threads) {
+    qdo_tables();
+    if (w > 64 || w_aa > 64) return 0;
+    uint64_t *partial = (uint64_t *)calloc(n_seq ? n_seq : 1, 8);
+    chk_win c = {dna, n_seq, seq_len, w, w_aa, kind, partial};
+    run_jobs(chk_win_job, &c, n_seq, threads);
+    uint64_t sum = 0;
+    for (size_t i = 0; i < n_seq; i++) sum += partial[i];
+    free(partial);
+    return sum;
+}
+
+typedef struct {
+    const uint8_t *win; /* ASCII windows, n_win x w */
+    size_t n_win, w, n_jobs;
+    uint64_t cap;
+    uint64_t *rows, *sums; /* per job */
+} chk_exp;
+
+/* rows of job j are checksummed relative to the job's first row; qdo_check_expansions rebases them */
+static void chk_exp_job(void *ctx, size_t job) {
+    chk_exp *c = (chk_exp *)ctx;
+    const size_t i0 = c->n_win * job / c->n_jobs, i1 = c->n_win * (job + 1) / c->n_jobs, w = c->w;
+    uint8_t *masks = (uint8_t *)malloc(w + 1);
+    uint64_t n_rows = 0;
+    /* first pass: rows of this job (needed before positions are known) */
+    for (size_t i = i0; i < i1; i++) {
+        for (size_t k = 0; k < w; k++) masks[k] = ASCII_TO_MASK[c->win[i * w + k]];
+        uint64_t cnt = 0;
+        if (qdo_expansions_size_hint(masks, w, &cnt) && cnt <= c->cap) n_rows += cnt;
+    }
+    c->rows[job] = n_rows;
+    free(masks);
+}
+
+static void chk_exp_job2(void *ctx, size_t job) {
+    chk_exp *c = (chk_exp *)ctx;
+    const size_t i0 = c->n_win * job / c->n_jobs, i1 = c->n_win * (job + 1) / c->n_jobs, w = c->w;
+    uint8_t *masks = (uint8_t *)malloc(w + (size_t)c->cap * w * 2 + 1), *rows = masks + w, *asc = rows + (size_t)c->cap * w;
+    uint64_t row = c->rows[job]; /* exclusive prefix by now */
+    uint64_t sum = 0;
+    for (size_t i = i0; i < i1; i++) {
+        for (size_t k = 0; k < w; k++) masks[k] = ASCII_TO_MASK[c->win[i * w + k]];
+        uint64_t cnt = 0;
+        if (!(qdo_expansions_size_hint(masks, w, &cnt) && cnt <= c->cap)) continue; /* benches/expansions.rs:57-66 */
+        const size_t got = qdo_expansions(masks, w, rows, (size_t)cnt);
+        for (size_t k = 0; k < got * w; k++) asc[k] = mask_to_ascii(rows[k]);
+        sum += qdo_checksum64(asc, got * w, row * w);
+        row += got;
+    }
+    c->sums[job] = sum;
+    free(masks);
+}
+
+/* checksum of the expansion rows (ASCII, iteration order, windows with more than `cap` expansions skipped) of n_win
+ * ASCII windows of w nt; *total_rows receives the row count */
+uint64_t qdo_check_expansions(const uint8_t *windows, size_t n_win, size_t w, uint64_t cap, int threads, uint64_t *total_rows) {
+    const size_t n_jobs = (size_t)(threads < 1 ? 1 : threads * 4);
+    uint64_t *rows = (uint64_t *)calloc(2 * n_jobs, 8), *sums = rows + n_jobs;
+    chk_exp c = {windows, n_win, w, n_jobs, cap, rows, sums};
+    run_jobs(chk_exp_job, &c, n_jobs, threads);
+    uint64_t acc = 0;
+    for (size_t j = 0; j < n_jobs; j++) {
+        const uint64_t r = rows[j];
+        rows[j] = acc;
+        acc += r;
+    }
+    if (total_rows) *total_rows = acc;
+    run_jobs(chk_exp_job2, &c, n_jobs, threads);
+    uint64_t sum = 0;
+    for (size_t j = 0; j < n_jobs; j++) sum += sums[j];
+    free(rows);
+    return sum;
 }

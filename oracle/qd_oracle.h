@@ -133,6 +133,25 @@ double qdo_bench_all_frames_batch(int slot, const uint8_t *dna, size_t n_reads, 
                                   uint8_t *out, int threads, int reps);
 double qdo_bench_revcomp(const uint8_t *dna, size_t n, uint8_t *out, int threads, int reps);
 
+/* Synthetic input + whole-config checks (tests and bench.py's checksum asserts) ------------- */
+/* quickdna_b200/synth.py synth_np, byte for byte: the counter-based stream every config's input is cut from */
+void qdo_synth(uint64_t seed, uint64_t start, uint64_t count, const uint8_t *alphabet, size_t alen, uint8_t *out);
+/* The position-weighted linear checksum qd_checksum64_dev computes (include/quickdna_b200.h): `buf` holds bytes
+ * [base, base + n) of a byte stream; sum over stream words J of word_J * (mix64(J * GOLD + 1) | 1) mod 2^64. */
+uint64_t qdo_checksum64(const uint8_t *buf, size_t n, uint64_t base);
+/* What the GPU path must produce, as that checksum, computed with the functions above on `threads` threads:
+ *  - frames of uniform reads [first_read, first_read + n_reads) of the seed's ACGT stream, slot layout
+ *    (the output stream starts at read first_read);
+ *  - reverse_complement_bytes of stream bytes [start, start + n);
+ *  - canonical w-nt windows (kind 0) or the all_windows output (kind 1: dna_out stream then aa_out stream) of n_seq
+ *    strict ASCII sequences, in the layouts of qd_canonical_windows_batch_dev / qd_windows_all_batch_dev;
+ *  - expansion rows of n_win ASCII windows (windows with more than `cap` expansions skipped). */
+uint64_t qdo_check_frames_uniform(uint64_t seed, uint64_t first_read, uint64_t n_reads, size_t read_len, int slot, int frames,
+                                  int threads);
+uint64_t qdo_check_revcomp(uint64_t seed, uint64_t start, uint64_t n, int strict, int threads);
+uint64_t qdo_check_windows(int kind, const uint8_t *dna, size_t n_seq, size_t seq_len, size_t w, size_t w_aa, int threads);
+uint64_t qdo_check_expansions(const uint8_t *windows, size_t n_win, size_t w, uint64_t cap, int threads, uint64_t *total_rows);
+
 #ifdef __cplusplus
 }
 #endif
