@@ -69,7 +69,12 @@ typedef struct qd_err {
  * One context owns one device, one stream, the device-resident LUTs and grow-only scratch
  * buffers.  Entry points taking a context are serialised on an internal mutex (the
  * reference's functions are pure and re-entrant; use one context per thread to run in
- * parallel). */
+ * parallel).  Scratch and the device-side error key belong to the context, not to a stream:
+ * a device-pointer call leaves an event behind and the next call on the same context that
+ * runs on ANOTHER stream waits for it (host-pointer calls wait on the host), so calls on one
+ * context execute in the order they were issued whatever streams they use; work that should
+ * overlap needs contexts of its own.  Every entry point makes the context's device current
+ * for its duration and restores the caller's device before returning. */
 int qd_ctx_create(qd_ctx **out, int device);
 void qd_ctx_destroy(qd_ctx *ctx);
 int qd_ctx_device(const qd_ctx *ctx);
@@ -306,6 +311,72 @@ int qd_windows_all_batch_dev(qd_ctx *ctx, int enc, const uint8_t *dna_dev, size_
                              size_t w_aa, uint8_t *dna_out_dev, uint8_t *aa_out_dev, void *stream);
 int qd_windows_dev(qd_ctx *ctx, const uint8_t *seq_dev, size_t n, size_t w, uint8_t *out_dev,
                    void *stream);
+
+/* ======================= several GPUs of one box, one call (host pointers, synchronous) =======================
+ * north_star: "batches of sequences, or one long chromosome split at codon-aligned offsets with a halo, are partitioned
+ * by byte count across the GPUs of one box, each on its own stream; outputs are concatenated on the host" -- the
+ * caller loop over DnaSequence::translate_all_frames (src/rust_api.rs:263-270) / reverse_complement (:273-275).
+ * ctxs: n_ctx DISTINCT contexts, normally one per device (two contexts of one device also work).  One host thread per
+ * context drives that context's pipe streams; every device copies its results to the right offset of the ONE output
+ * buffer; nothing is exchanged between devices.  Results and errors are exactly those of the single-context calls
+ * (the first error in input order is the one reported).
+ *   _batch_multi : offsets != NULL -> qd_translate_frames_batch (cut at the sequence boundaries nearest k*total/n_ctx);
+ *                  offsets == NULL -> qd_translate_frames_batch_uniform with seq_len (cut by count)
+ *   _multi       : ONE sequence, qd_translate_frames: cut at multiples of 48, each piece read with a 2-nt halo and
+ *                  translated as a stand-alone sequence; forward local frame k = global frame k from residue start/3,
+ *                  reverse local frame k = global reverse frame (k + d) % 3 from residue (k + d) / 3, d = nucleotides
+ *                  to the right of the piece
+ *   qd_revcomp_multi : piece [a, b) lands at out[n - b, n - a)
+ * A single context already pipelines sequences of 8 MiB and more this way (chunks of n/16, 4 .. 64 MiB). */
+int qd_translate_frames_batch_multi(qd_ctx *const *ctxs, int n_ctx, int table, int enc, int strict, int frames, const uint8_t *dna,
+                                    const uint64_t *offsets, size_t n_seq, size_t seq_len, uint8_t *out, uint64_t *out_offsets,
+                                    qd_err *err);
+int qd_translate_frames_multi(qd_ctx *const *ctxs, int n_ctx, int table, int enc, int strict, int frames, const uint8_t *dna, size_t n,
+                              uint8_t *out, size_t out_len[6], int *n_frames, qd_err *err);
+int qd_revcomp_multi(qd_ctx *const *ctxs, int n_ctx, int enc, int strict, const uint8_t *dna, size_t n, uint8_t *out, qd_err *err);
+
+/* ---- checksum of a device buffer ---------------------------------------------------------------------------------
+ * Position-weighted LINEAR checksum: the buffer holds bytes [base, base + n) of a byte stream; stream word J (bytes
+ * 8J .. 8J+7, little endian) weighs K(J) = mix64(J * 0x9e3779b97f4a7c15 + 1) | 1 (mix64 = the splitmix64 finaliser above,
+ * qd_checksum64_weight returns K(J)); the checksum is sum_J word_J * K(J) mod 2^64 and is ADDED to *acc_dev.  Linear in
+ * the data: the chunks of an output ring, or the shards the GPUs of a box produced, add up to the checksum of the whole
+ * output whatever their byte alignment -- so a 336 GB window enumeration is checked without ever being resident.
+ * One HBM read of the buffer.  Any alignment of buf_dev. */
+int qd_checksum64_dev(qd_ctx *ctx, const uint8_t *buf_dev, size_t n, uint64_t base, uint64_t *acc_dev, void *stream);
+uint64_t qd_checksum64_weight(uint64_t word_index);
+
+/* ---- chunked ("ring") window enumeration ---------------------------------------------------------------------------
+ * The window kernels write 42 - 124 bytes per input byte (benches/canonical.rs:29-34, benches/all_windows.rs:78-102,
+ * benches/expansions.rs:126-130): the output of an 8 GB shard (336 GB of canonical rows) does not fit HBM.  These entry
+ * points walk the batch in chunks of `chunk_seqs` sequences (`chunk_windows` windows), chunk k written to slot
+ * k % n_slots of the caller's ring (n_slots = ring_bytes / slot size, slot size = the chunk's bytes rounded up to 256;
+ * sizes from the qd_*_chunk_bytes helpers).  After each chunk, on the same stream:
+ *   - checksums_dev[k] (optional, qd_chunk_count() entries) receives the chunk's qd_checksum64:
+ *       canonical   : base = first window of the chunk * w  (summing all chunks gives the checksum of the whole
+ *                     [n_seq][windows][w] output, whatever the chunking)
+ *       windows_all : chunk-relative -- the chunk's DNA windows [forward block][reverse block] at base 0, then its
+ *                     amino-acid windows (six frame blocks) at base = the DNA bytes of the chunk
+ *       expansions  : chunk-relative, base 0, over the chunk_rows_dev[k] rows the chunk produced
+ *   - `consume` (optional) is called on the host with the slot; whatever it enqueues on `stream` runs before the slot
+ *     is overwritten.  n_rows_dev is NULL unless the row count is only known on the device (expansions).
+ * Slot layout: canonical = qd_canonical_windows_batch_dev of the chunk; windows_all = dna_out at 0, aa_out at
+ * *aa_offset (qd_windows_all_chunk_bytes); expansions = rows, tightly packed. */
+typedef void (*qd_chunk_fn)(void *user, size_t chunk, size_t first_unit, size_t n_units, const uint8_t *slot_dev, size_t slot_bytes,
+                            const uint64_t *n_rows_dev, void *stream);
+size_t qd_chunk_count(size_t n_units, size_t chunk_units);
+size_t qd_canonical_chunk_bytes(size_t chunk_seqs, size_t seq_len, size_t w);
+size_t qd_windows_all_chunk_bytes(size_t chunk_seqs, size_t seq_len, size_t w_dna, size_t w_aa, size_t *aa_offset);
+size_t qd_expansion_chunk_bytes(size_t chunk_windows, size_t w, uint64_t max_expansions);
+int qd_canonical_windows_chunked_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev, size_t n_seq, size_t seq_len,
+                                     size_t w, uint8_t *ring_dev, size_t ring_bytes, size_t chunk_seqs, uint64_t *checksums_dev,
+                                     qd_chunk_fn consume, void *user, void *stream);
+int qd_windows_all_chunked_dev(qd_ctx *ctx, int enc, const uint8_t *dna_dev, size_t n_seq, size_t seq_len, size_t w_dna, size_t w_aa,
+                               uint8_t *ring_dev, size_t ring_bytes, size_t chunk_seqs, uint64_t *checksums_dev, qd_chunk_fn consume,
+                               void *user, void *stream);
+/* counts_dev: size_hint of every window (n_win entries) or NULL; chunk_rows_dev[k] = rows chunk k produced (required) */
+int qd_expansion_windows_chunked_dev(qd_ctx *ctx, int enc, const uint8_t *windows_dev, size_t n_win, size_t w, uint64_t max_expansions,
+                                     uint8_t *ring_dev, size_t ring_bytes, size_t chunk_windows, uint64_t *counts_dev,
+                                     uint64_t *chunk_rows_dev, uint64_t *checksums_dev, qd_chunk_fn consume, void *user, void *stream);
 
 /* Number of kernel launches this context has issued (bench.py's gpu_launches claim). */
 uint64_t qd_launch_count(const qd_ctx *ctx);

@@ -66,8 +66,8 @@ class BaseSequence:
         return type(self)(self._seq * by)
 
     def __repr__(self) -> str:
-        text = self._seq.decode("ascii")
-        shown = text[:30] + "..." if len(text) > 30 else text
+        # only the bytes that are shown get decoded (quickdna/__init__.py:70-76)
+        shown = self._seq[:30].decode("ascii") + "..." if len(self._seq) > 30 else self._seq.decode("ascii")
         return f"{type(self).__name__}(seq={shown!r})"
 
     def __str__(self) -> str:

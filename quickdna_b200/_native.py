@@ -109,7 +109,22 @@ SIGNATURES = {
     "qd_windows_all_batch_dev": (_i, [_vp, _i, _vp, _sz, _sz, _sz, _sz, _vp, _vp, _vp]),
     "qd_parse": (_i, [_vp, _i, _vp, _sz, _vp, C.POINTER(_sz), C.POINTER(QdErr)]),
     "qd_parse_dev": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _vp]),
+    "qd_translate_frames_batch_multi": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _vp, _vp, C.POINTER(QdErr)]),
+    "qd_translate_frames_multi": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, C.POINTER(_sz), C.POINTER(_i), C.POINTER(QdErr)]),
+    "qd_revcomp_multi": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, C.POINTER(QdErr)]),
+    "qd_checksum64_dev": (_i, [_vp, _vp, _sz, C.c_uint64, _vp, _vp]),
+    "qd_checksum64_weight": (C.c_uint64, [C.c_uint64]),
+    "qd_chunk_count": (_sz, [_sz, _sz]),
+    "qd_canonical_chunk_bytes": (_sz, [_sz, _sz, _sz]),
+    "qd_windows_all_chunk_bytes": (_sz, [_sz, _sz, _sz, _sz, C.POINTER(_sz)]),
+    "qd_expansion_chunk_bytes": (_sz, [_sz, _sz, C.c_uint64]),
+    "qd_canonical_windows_chunked_dev": (_i, [_vp, _i, _i, _vp, _sz, _sz, _sz, _vp, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "qd_windows_all_chunked_dev": (_i, [_vp, _i, _vp, _sz, _sz, _sz, _sz, _vp, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "qd_expansion_windows_chunked_dev": (_i, [_vp, _i, _vp, _sz, _sz, C.c_uint64, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
+
+# qd_chunk_fn: (user, chunk, first_unit, n_units, slot_dev, slot_bytes, n_rows_dev, stream)
+CHUNK_FN = C.CFUNCTYPE(None, _vp, _sz, _sz, _sz, _vp, _sz, _vp, _vp)
 
 _lib: Optional[C.CDLL] = None
 _lock = threading.Lock()
@@ -162,9 +177,11 @@ class Context:
         except Exception:
             pass
 
-    def check(self, rc: int, err: Optional[QdErr] = None):
+    def check(self, rc: int, err: Optional[QdErr] = None, table: Optional[int] = None):
         if rc == QD_OK:
             return
+        if rc == QD_ERR_BAD_TABLE and err is None and table is not None:
+            err = QdErr(rc, int(table) & 0xFF, 0, 0)  # device-pointer calls carry no qd_err: the id is the payload
         if rc == QD_ERR_CUDA:
             raise CudaError(lib().qd_last_cuda_error(self._h).decode())
         if rc == QD_ERR_INVALID_ARGUMENT:
@@ -189,6 +206,21 @@ def make_error(err: QdErr) -> TranslationError:
 
 _contexts = {}
 _ctx_lock = threading.Lock()
+
+
+def context_array(ctxs):
+    """qd_ctx*[] for the *_multi entry points."""
+    arr = (_vp * len(ctxs))(*[c.handle for c in ctxs])
+    return arr
+
+
+def device_contexts(devices=None):
+    """One default context per device (all visible devices when None)."""
+    if devices is None:
+        import torch
+
+        devices = range(torch.cuda.device_count())
+    return [default_context(int(d)) for d in devices]
 
 
 def default_context(device: int = 0) -> Context:

@@ -71,27 +71,49 @@ def translate_frames_batch(
     frames: int = N.FRAMES_ALL,
     enc: int = N.ENC_ASCII,
     ctx: Optional[N.Context] = None,
+    offsets=None,
+    devices=None,
 ) -> FramesBatch:
     """Translate every read of a batch.
 
-    reads: a 2-D uint8 array (n_reads x read_len, uniform batch), a (flat, offsets) pair
-    (CSR, offsets uint64 [n+1]), or a sequence of bytes objects.
+    reads: a 2-D uint8 array (n_reads x read_len, uniform batch), a sequence of bytes-like reads, or -- with
+    `offsets=` -- one flat uint8 buffer holding all reads back to back (CSR, offsets uint64 [n+1]).  A 2-tuple
+    (flat ndarray, integer ndarray) is still taken as the CSR pair; a tuple of reads is a sequence of reads.
+
+    devices: a list of device indices (or of Contexts): the batch is partitioned by bytes over them
+    (qd_translate_frames_batch_multi: one host thread and one set of streams per device, one output buffer).
     """
-    ctx = ctx or N.default_context()
     L = N.lib()
     err = N.QdErr()
+    ctxs = None
+    if devices is not None:
+        ctxs = [d if isinstance(d, N.Context) else N.default_context(int(d)) for d in devices]
+        ctx = ctxs[0]
+    ctx = ctx or N.default_context()
     if isinstance(reads, np.ndarray) and reads.ndim == 2:
         a = _u8(reads)
         n_seq, seq_len = a.shape
         per = 16 * runs(seq_len) * frames
         out = np.empty(n_seq * per, dtype=np.uint8)
-        rc = L.qd_translate_frames_batch_uniform(ctx.handle, table, enc, int(strict), frames, _p(a), n_seq, seq_len, _p(out),
-                                                 C.byref(err))
+        if ctxs is not None:
+            rc = L.qd_translate_frames_batch_multi(N.context_array(ctxs), len(ctxs), table, enc, int(strict), frames, _p(a), None, n_seq, seq_len,
+                                                   _p(out), None, C.byref(err))
+        else:
+            rc = L.qd_translate_frames_batch_uniform(ctx.handle, table, enc, int(strict), frames, _p(a), n_seq, seq_len, _p(out),
+                                                     C.byref(err))
         ctx.check(rc, err)
         return FramesBatch(out, np.arange(n_seq + 1, dtype=np.uint64) * np.uint64(per),
                            np.full(n_seq, seq_len, dtype=np.uint64), frames)
-    if isinstance(reads, tuple):
-        flat, offsets = _u8(reads[0]), np.ascontiguousarray(reads[1], dtype=np.uint64)
+    def _is_offsets(o) -> bool:
+        return isinstance(o, np.ndarray) and o.ndim == 1 and np.issubdtype(o.dtype, np.integer) and o.dtype != np.uint8
+
+    if offsets is None and isinstance(reads, tuple) and len(reads) == 2 and isinstance(reads[0], np.ndarray) and _is_offsets(reads[1]):
+        reads, offsets = reads
+    if offsets is not None:
+        flat, offsets = _u8(reads), np.ascontiguousarray(offsets, dtype=np.uint64)
+        if flat.ndim != 1 or offsets.ndim != 1 or offsets.size < 1 or int(offsets[0]) != 0 or int(offsets[-1]) != flat.size \
+                or (offsets.size > 1 and bool((np.diff(offsets.astype(np.int64)) < 0).any())):
+            raise ValueError("offsets must be a non-decreasing uint64 array [n_reads + 1] with offsets[0] == 0 and offsets[-1] == len(flat)")
     else:
         lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
         offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
@@ -103,10 +125,64 @@ def translate_frames_batch(
     out_offsets = np.empty(n_seq + 1, dtype=np.uint64)
     if flat.size == 0:
         flat = np.zeros(1, dtype=np.uint8)
-    rc = L.qd_translate_frames_batch(ctx.handle, table, enc, int(strict), frames, _p(flat), _p(offsets), n_seq, _p(out),
-                                     _p(out_offsets), C.byref(err))
+    if ctxs is not None:
+        rc = L.qd_translate_frames_batch_multi(N.context_array(ctxs), len(ctxs), table, enc, int(strict), frames, _p(flat), _p(offsets), n_seq, 0,
+                                               _p(out), _p(out_offsets), C.byref(err))
+    else:
+        rc = L.qd_translate_frames_batch(ctx.handle, table, enc, int(strict), frames, _p(flat), _p(offsets), n_seq, _p(out),
+                                         _p(out_offsets), C.byref(err))
     ctx.check(rc, err)
     return FramesBatch(out[:total], out_offsets, np.diff(offsets), frames)
+
+
+def translate_frames(dna, table: int = 1, strict: bool = False, frames: int = N.FRAMES_ALL, enc: int = N.ENC_ASCII,
+                     ctx: Optional[N.Context] = None, devices=None) -> List[bytes]:
+    """The frames of ONE sequence (qd_translate_frames; with `devices`, qd_translate_frames_multi: the sequence is cut
+    at multiples of 48 with a 2-nt halo and spread over the devices).  Returns the frames the reference returns."""
+    L = N.lib()
+    a = _u8(dna)
+    n = a.size
+    n_slots = 1 if frames == N.FRAMES_ONE else frames
+    out = np.empty(max(1, sum(frame_len(n, f % 3) for f in range(n_slots))), dtype=np.uint8)
+    lens = (C.c_size_t * 6)()
+    nf = C.c_int()
+    err = N.QdErr()
+    src = _p(a if n else np.zeros(1, np.uint8))
+    if devices is not None:
+        ctxs = [d if isinstance(d, N.Context) else N.default_context(int(d)) for d in devices]
+        ctx = ctxs[0]
+        rc = L.qd_translate_frames_multi(N.context_array(ctxs), len(ctxs), table, enc, int(strict), frames, src, n, _p(out), lens, C.byref(nf),
+                                         C.byref(err))
+    else:
+        ctx = ctx or N.default_context()
+        rc = L.qd_translate_frames(ctx.handle, table, enc, int(strict), frames, src, n, _p(out), lens, C.byref(nf), C.byref(err))
+    ctx.check(rc, err)
+    res, off = [], 0
+    for f in range(6):
+        if lens[f]:
+            res.append(out[off:off + lens[f]].tobytes())
+        off += lens[f]
+    assert len(res) == nf.value
+    return res
+
+
+def revcomp(dna, strict: bool = False, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None, devices=None, out=None) -> np.ndarray:
+    """Reverse complement of ONE sequence (qd_revcomp; with `devices`, qd_revcomp_multi over the devices)."""
+    L = N.lib()
+    a = _u8(dna)
+    if out is None:
+        out = np.empty(max(a.size, 1), dtype=np.uint8)
+    err = N.QdErr()
+    src = _p(a if a.size else np.zeros(1, np.uint8))
+    if devices is not None:
+        ctxs = [d if isinstance(d, N.Context) else N.default_context(int(d)) for d in devices]
+        ctx = ctxs[0]
+        rc = L.qd_revcomp_multi(N.context_array(ctxs), len(ctxs), enc, int(strict), src, a.size, _p(out), C.byref(err))
+    else:
+        ctx = ctx or N.default_context()
+        rc = L.qd_revcomp(ctx.handle, enc, int(strict), src, a.size, _p(out), C.byref(err))
+    ctx.check(rc, err)
+    return out[: a.size]
 
 
 def parse(ascii_seq, strict: bool = False, ctx: Optional[N.Context] = None) -> np.ndarray:
@@ -332,7 +408,7 @@ def translate_frames_uniform_dev(dna, n_seq: int, seq_len: int, out=None, table:
         out = torch.empty(n_seq * 16 * runs(seq_len) * frames, dtype=torch.uint8, device=dna.device)
     rc = N.lib().qd_translate_frames_batch_uniform_dev(ctx.handle, table, enc, int(strict), frames, C.c_void_p(dna.data_ptr()),
                                                        n_seq, seq_len, C.c_void_p(out.data_ptr()), _stream_ptr(torch))
-    ctx.check(rc)
+    ctx.check(rc, table=table)
     return out
 
 
@@ -351,7 +427,7 @@ def translate_frames_csr_dev(dna, offsets, out=None, table: int = 1, strict: boo
     rc = N.lib().qd_translate_frames_batch_dev(ctx.handle, table, enc, int(strict), frames, C.c_void_p(dna.data_ptr()),
                                                C.c_void_p(offsets.data_ptr()), n_seq, dna.numel(), C.c_void_p(out.data_ptr()),
                                                _stream_ptr(torch))
-    ctx.check(rc)
+    ctx.check(rc, table=table)
     return out
 
 
@@ -457,6 +533,96 @@ def windows_all_batch_dev(dna, n_seq: int, seq_len: int, w_dna: int = 42, w_aa: 
                                           C.c_void_p(dna_out.data_ptr()), C.c_void_p(aa_out.data_ptr()), _stream_ptr(torch))
     ctx.check(rc)
     return cs, dna_out, aa_out
+
+
+def checksum64_dev(buf, base: int = 0, acc=None, ctx: Optional[N.Context] = None):
+    """qd_checksum64_dev: adds the position-weighted linear checksum of a uint8 CUDA tensor (bytes [base, base + n) of a
+    stream) to `acc` (int64 device tensor [1], created zeroed when None) and returns it; int(acc.item()) & (2**64 - 1)
+    is the checksum."""
+    import torch
+
+    ctx = ctx or N.default_context(buf.device.index or 0)
+    if acc is None:
+        acc = torch.zeros(1, dtype=torch.int64, device=buf.device)
+    rc = N.lib().qd_checksum64_dev(ctx.handle, C.c_void_p(buf.data_ptr()), buf.numel(), base, C.c_void_p(acc.data_ptr()), _stream_ptr(torch))
+    ctx.check(rc)
+    return acc
+
+
+def u64(t) -> int:
+    """The unsigned value of a one-element int64 tensor."""
+    return int(t.item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def _consumer(consume):
+    if consume is None:
+        return None, None
+    cb = N.CHUNK_FN(lambda user, chunk, first, n_units, slot, nbytes, n_rows_dev, stream: consume(chunk, first, n_units, slot, nbytes, n_rows_dev, stream))
+    return cb, cb
+
+
+def canonical_windows_chunked_dev(dna, n_seq: int, seq_len: int, w: int, ring, chunk_seqs: int, checksums: bool = True,
+                                  forward_only: bool = False, enc: int = N.ENC_ASCII, consume=None, ctx: Optional[N.Context] = None):
+    """qd_canonical_windows_chunked_dev: canonical windows of a batch whose output does not fit HBM, chunk by chunk through
+    the uint8 CUDA tensor `ring`.  Returns the per-chunk checksums (int64 device tensor [n_chunks]; their sum mod 2**64 is
+    the checksum of the whole output) or None.  consume(chunk, first_seq, n_seq, slot_ptr, bytes, n_rows_dev, stream) is
+    called on the host after each chunk has been enqueued."""
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    L = N.lib()
+    n_chunks = L.qd_chunk_count(n_seq, chunk_seqs)
+    sums = torch.zeros(max(n_chunks, 1), dtype=torch.int64, device=dna.device) if checksums else None
+    cb, keep = _consumer(consume)
+    rc = L.qd_canonical_windows_chunked_dev(ctx.handle, enc, int(forward_only), C.c_void_p(dna.data_ptr()), n_seq, seq_len, w,
+                                            C.c_void_p(ring.data_ptr()), ring.numel(), chunk_seqs,
+                                            None if sums is None else C.c_void_p(sums.data_ptr()), C.cast(cb, C.c_void_p) if cb else None, None,
+                                            _stream_ptr(torch))
+    ctx.check(rc)
+    del keep
+    return None if sums is None else sums[:n_chunks]
+
+
+def windows_all_chunked_dev(dna, n_seq: int, seq_len: int, ring, chunk_seqs: int, w_dna: int = 42, w_aa: int = 20, checksums: bool = True,
+                            enc: int = N.ENC_ASCII, consume=None, ctx: Optional[N.Context] = None):
+    """qd_windows_all_chunked_dev: the all_windows shape of a batch, chunk by chunk through `ring`; returns the
+    chunk-relative per-chunk checksums or None."""
+    import torch
+
+    ctx = ctx or N.default_context(dna.device.index or 0)
+    L = N.lib()
+    n_chunks = L.qd_chunk_count(n_seq, chunk_seqs)
+    sums = torch.zeros(max(n_chunks, 1), dtype=torch.int64, device=dna.device) if checksums else None
+    cb, keep = _consumer(consume)
+    rc = L.qd_windows_all_chunked_dev(ctx.handle, enc, C.c_void_p(dna.data_ptr()), n_seq, seq_len, w_dna, w_aa, C.c_void_p(ring.data_ptr()),
+                                      ring.numel(), chunk_seqs, None if sums is None else C.c_void_p(sums.data_ptr()),
+                                      C.cast(cb, C.c_void_p) if cb else None, None, _stream_ptr(torch))
+    ctx.check(rc)
+    del keep
+    return None if sums is None else sums[:n_chunks]
+
+
+def expansion_windows_chunked_dev(windows, ring, chunk_windows: int, max_expansions: int = 16, checksums: bool = True, counts=None,
+                                  enc: int = N.ENC_ASCII, consume=None, ctx: Optional[N.Context] = None):
+    """qd_expansion_windows_chunked_dev on a [n_win, w] uint8 CUDA tensor: returns (rows per chunk, chunk-relative
+    checksums or None), both int64 device tensors [n_chunks]."""
+    import torch
+
+    ctx = ctx or N.default_context(windows.device.index or 0)
+    L = N.lib()
+    n_win, w = windows.shape
+    n_chunks = L.qd_chunk_count(n_win, chunk_windows)
+    rows = torch.zeros(max(n_chunks, 1), dtype=torch.int64, device=windows.device)
+    sums = torch.zeros(max(n_chunks, 1), dtype=torch.int64, device=windows.device) if checksums else None
+    cb, keep = _consumer(consume)
+    rc = L.qd_expansion_windows_chunked_dev(ctx.handle, enc, C.c_void_p(windows.data_ptr()), n_win, w, max_expansions,
+                                            C.c_void_p(ring.data_ptr()), ring.numel(), chunk_windows,
+                                            None if counts is None else C.c_void_p(counts.data_ptr()), C.c_void_p(rows.data_ptr()),
+                                            None if sums is None else C.c_void_p(sums.data_ptr()), C.cast(cb, C.c_void_p) if cb else None,
+                                            None, _stream_ptr(torch))
+    ctx.check(rc)
+    del keep
+    return rows[:n_chunks], (None if sums is None else sums[:n_chunks])
 
 
 def dev_error_reset(ctx: Optional[N.Context] = None):

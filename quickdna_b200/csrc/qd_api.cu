@@ -30,16 +30,21 @@ const HostTables& host_tables() {
     return *T;
 }
 
+// Grow-only scratch.  Growth is stream-ordered (cudaFreeAsync / cudaMallocAsync on the stream the buffer is about to be
+// used on): the old block is released only after the work already enqueued on that stream, nothing synchronises the
+// device, and a call whose buffers are warm allocates nothing.  `tls_stream` is the stream of the entry point running
+// on this thread (set by its Guard).
+thread_local cudaStream_t tls_stream = nullptr;
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, tls_stream);
         p = nullptr;
         cap = 0;
         size_t want = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);  // 1 MiB granules, >= 16 B slack
-        cudaError_t e = cudaMalloc(&p, want);
+        cudaError_t e = cudaMallocAsync(&p, want, tls_stream);
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -89,6 +94,14 @@ struct qd_ctx {
     int occ_frames[6] = {0, 0, 0, 0, 0, 0};  // [tile size][frames]
     uint64_t big_tile_min_runs = 0;           // launches with at least this many runs use 1024-thread tiles
     int occ_revcomp[2] = {0, 0};  // [small, big tile]
+    // Scratch and the error key are per context, not per stream: a device-pointer call leaves an event behind, and the
+    // next call that runs on ANOTHER stream waits for it first (host-pointer calls wait on the host), so two calls on one
+    // context are ordered whatever streams they use.
+    cudaEvent_t dev_done = nullptr;
+    cudaStream_t dev_stream = nullptr;
+    bool dev_pending = false;
+    std::map<uint64_t, int> occ_cache;  // (kernel id, smem bytes) -> resident CTAs per SM, attribute already set
+    uint32_t ctile_wpt[2] = {448, 192};  // canonical tile kernel: windows per warp-tile for keys / rows (QD_CTILE_WPT_* read once)
 };
 
 namespace {
@@ -121,6 +134,49 @@ enum {
             return QD_ERR_CUDA;                                                               \
         }                                                                                     \
     } while (0)
+
+// Every entry point: lock the context, make its device current (restored on return), clear the last error text, and
+// order this call after a pending device-pointer call that ran on another stream.
+struct Guard {
+    qd_ctx* c;
+    std::unique_lock<std::mutex> lk;
+    int prev = -1;
+    bool ok = true;
+    bool dev;
+    cudaStream_t s;
+    // host-pointer entry points: Guard(c);  device-pointer entry points: Guard(c, stream)
+    explicit Guard(qd_ctx* c_) : Guard(c_, nullptr, false) {}
+    Guard(qd_ctx* c_, cudaStream_t stream, bool dev_ = true) : c(c_), lk(c_->mu), dev(dev_), s(dev_ ? stream : c_->stream) {
+        c->last_error.clear();
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != c->device && cudaSetDevice(c->device) != cudaSuccess) {
+            fail("cudaSetDevice");
+            return;
+        }
+        tls_stream = s;
+        if (c->dev_pending && (!dev || c->dev_stream != s)) {
+            const cudaError_t e = dev ? cudaStreamWaitEvent(s, c->dev_done, 0) : cudaEventSynchronize(c->dev_done);
+            if (e != cudaSuccess) {
+                fail("waiting for the previous device-pointer call");
+                return;
+            }
+            if (!dev) c->dev_pending = false;
+        }
+    }
+    void fail(const char* what) {
+        ok = false;
+        c->last_error = std::string(what) + " failed";
+    }
+    ~Guard() {
+        if (ok && dev) {
+            if (cudaEventRecord(c->dev_done, s) == cudaSuccess) {
+                c->dev_pending = true;
+                c->dev_stream = s;
+            }
+        }
+        if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+    }
+};
 
 inline const uint8_t* tab(const qd_ctx* c, int which) { return c->d_tables + 256 * which; }
 
@@ -376,7 +432,7 @@ int launch_revcomp_t(qd_ctx* c, const RevcompParams& p, cudaStream_t s, int occ_
 
 // `which` = one of RC_PAIR_*: selects the complement table (256-byte form and letter-pair form)
 int revcomp_dev_table(qd_ctx* c, int which, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, cudaStream_t s,
-                      unsigned long long* err_key = nullptr) {
+                      unsigned long long* err_key = nullptr, uint64_t key_base = 0) {
     if (n == 0) return QD_OK;
     static const int byte_tab[RC_PAIR_COUNT] = {TAB_RC_ASCII, TAB_RC_ASCII_STRICT, TAB_RC_MASK, TAB_RC_MASK_STRICT,
                                                 TAB_RC_MASK_TO_ASCII, TAB_RC_MASK_TO_ASCII_STRICT};
@@ -392,6 +448,7 @@ int revcomp_dev_table(qd_ctx* c, int which, const uint8_t* dna_dev, size_t n, ui
     p.or_forbid = ascii_in ? 0x80808080u : 0xe0e0e0e0u;
     p.filler = ascii_in ? 0x41u : 0x01u;
     p.err_key = err_key ? err_key : c->d_err;
+    p.key_base = key_base;
     // big tiles once every SM gets two of them
     const bool big = (n >> 4) >= (uint64_t)2 * RevcompSmem<RC_BIG_THREADS>::TILE_CHUNKS * (uint64_t)c->sm_count && c->big_tile_min_runs != ~0ull;
     if (big || c->big_tile_min_runs == 0) return launch_revcomp_t<RC_BIG_THREADS>(c, p, s, 1);
@@ -429,6 +486,12 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     *out = nullptr;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return QD_ERR_CUDA;
+    int prev_dev = -1;
+    if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
+    struct Restore {
+        int prev, dev;
+        ~Restore() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+    } restore{prev_dev, device};
     if (cudaSetDevice(device) != cudaSuccess) return QD_ERR_CUDA;
     qd_ctx* c = new qd_ctx();
     c->device = device;
@@ -439,6 +502,9 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     }
     c->sm_count = prop.multiProcessorCount;
     c->big_tile_min_runs = (uint64_t)2 * BIG_THREADS * (uint64_t)c->sm_count;  // every SM gets two big tiles
+    // tuning knobs of the canonical tile kernel, read once per context (not on the launch path)
+    if (const char* e = getenv("QD_CTILE_WPT_KEYS")) c->ctile_wpt[0] = (uint32_t)std::max(64, atoi(e) & ~63);
+    if (const char* e = getenv("QD_CTILE_WPT_ROWS")) c->ctile_wpt[1] = (uint32_t)std::max(64, atoi(e) & ~63);
     const HostTables& T = host_tables();
     bool ok = true;
     ok &= cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -451,6 +517,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_ckey, sizeof(T.ckey)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_parse_pair, sizeof(T.parse_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&c->dev_done, cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_stage, SMALL_CALL_BYTES + 64, cudaHostAllocDefault) == cudaSuccess;
@@ -492,6 +559,8 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
 
 extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (!c) return;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&c->in, &c->out, &c->aux0, &c->aux1, &c->aux2, &c->aux3, &c->run_prefix, &c->tile_first, &c->block_sums, &c->parse_counts,
@@ -514,6 +583,8 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->dev_done) cudaEventDestroy(c->dev_done);
+    if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
     delete c;
 }
 
@@ -606,16 +677,16 @@ static cudaStream_t pick_stream(qd_ctx*, void* s) { return (cudaStream_t)s; }
 
 extern "C" int qd_dev_error_reset(qd_ctx* c, void* stream) {
     if (!c) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return reset_err_key(c, pick_stream(c, stream));
 }
 
 extern "C" int qd_dev_error_fetch(qd_ctx* c, void* stream, int enc, int strict, const uint8_t* dna_dev,
                                   const uint64_t* offsets_dev, size_t n_seq, size_t uniform_len, qd_err* err) {
     if (!c) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     clear_err(err);
     cudaStream_t s = pick_stream(c, stream);
     unsigned long long key = 0;
@@ -653,8 +724,8 @@ extern "C" int qd_dev_error_fetch(qd_ctx* c, void* stream, int enc, int strict, 
 
 extern "C" int qd_revcomp_dev(qd_ctx* c, int enc, int strict, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, void* stream) {
     if (!c || (n && (!dna_dev || !out_dev)) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     const int which = enc == QD_ENC_ASCII ? (strict ? RC_PAIR_ASCII_STRICT : RC_PAIR_ASCII) : (strict ? RC_PAIR_MASK_STRICT : RC_PAIR_MASK);
     return revcomp_dev_table(c, which, dna_dev, n, out_dev, pick_stream(c, stream));
 }
@@ -669,8 +740,8 @@ extern "C" int qd_translate_frames_batch_uniform_dev(qd_ctx* c, int table, int e
     if (!c || !valid_frames(frames) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
     int slot;
     if (check_table(table, nullptr, &slot)) return QD_ERR_BAD_TABLE;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return frames_uniform_dev(c, slot, enc, strict, frames, dna_dev, n_seq, seq_len, out_dev, pick_stream(c, stream));
 }
 
@@ -680,8 +751,8 @@ extern "C" int qd_translate_frames_batch_dev(qd_ctx* c, int table, int enc, int 
     if (!c || !valid_frames(frames) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
     int slot;
     if (check_table(table, nullptr, &slot)) return QD_ERR_BAD_TABLE;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return frames_csr_dev(c, slot, enc, strict, frames, dna_dev, total_nt, offsets_dev, n_seq, c->run_prefix, c->tile_first,
                           c->block_sums, out_dev, pick_stream(c, stream));
 }
@@ -716,15 +787,25 @@ static int launch_canonical_tiles(qd_ctx* c, CanonKeyParams kp, cudaStream_t s) 
     const uint64_t nw = p.seq_len - p.w + 1;
     // keys: 448 + 41 + slack = 16 x 32 positions for w = 42 is two rounds of the per-position pass;
     // rows: 192 + 41 + slack = 8 x 32 is one round (rows are staged and copied out 64 at a time)
-    uint32_t wpt = rows ? 192 : 448;
-    if (const char* e = getenv(rows ? "QD_CTILE_WPT_ROWS" : "QD_CTILE_WPT_KEYS")) wpt = std::max(64, atoi(e) & ~63);  // tuning knob
+    uint32_t wpt = c->ctile_wpt[rows ? 1 : 0];
     while (wpt > 64 && ckey_span_bound(wpt, p.w, nw) > 2048) wpt -= 64;
     kp.wpt = wpt;
     kp.pos_cap = (uint32_t)((ckey_span_bound(wpt, p.w, nw) + 31) & ~(uint64_t)31);
     const size_t smem = CKEY_SHARED_TABLE_BYTES + (size_t)CanonTileLayout(kp.pos_cap, wpt, p.w, rows).total_bytes * CTILE_WARPS;
-    QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTILE_THREADS, smem));
+    // occupancy once per (instantiation, shared-memory size); the kernel's dynamic shared-memory limit only ever grows
+    const uint64_t kern_key = ((uint64_t)(NW * 4 + MODE) << 40) | ((uint64_t)(W != 0) << 39);
+    int& smem_limit = c->occ_cache[kern_key | ((uint64_t)1 << 38)];
+    if ((int)smem > smem_limit) {
+        QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_limit = (int)smem;
+    }
+    auto occ_it = c->occ_cache.find(kern_key | (uint64_t)smem);
+    if (occ_it == c->occ_cache.end()) {
+        int o = 0;
+        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, CTILE_THREADS, smem));
+        occ_it = c->occ_cache.emplace(kern_key | (uint64_t)smem, o).first;
+    }
+    const int occ = occ_it->second;
     const uint64_t tiles = (p.n_seq * nw + (uint64_t)wpt * CTILE_WARPS - 1) / ((uint64_t)wpt * CTILE_WARPS);
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * std::max(1, occ));
     kern<<<grid, CTILE_THREADS, smem, s>>>(kp);
@@ -788,24 +869,24 @@ extern "C" uint64_t qd_canonical_fingerprint(const uint32_t* packed, size_t w) {
 extern "C" int qd_canonical_window_keys_dev(qd_ctx* c, int enc, int forward_only, int kind, const uint8_t* dna_dev, size_t n_seq,
                                             size_t seq_len, size_t w, void* keys_dev, void* stream) {
     if (!c || (reinterpret_cast<uintptr_t>(keys_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return canonical_keys_dev(c, enc, forward_only, kind, dna_dev, n_seq, seq_len, w, keys_dev, pick_stream(c, stream));
 }
 
 extern "C" int qd_canonical_windows_batch_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len,
                                               size_t w, uint8_t* out_dev, void* stream) {
     if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return canonical_dev(c, enc, forward_only, dna_dev, n_seq, seq_len, w, out_dev, pick_stream(c, stream));
 }
 
 extern "C" int qd_canonical_windows_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, size_t w,
                                         uint8_t* out_dev, void* stream) {
     if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return canonical_dev(c, enc, forward_only, dna_dev, 1, n, w, out_dev, pick_stream(c, stream));
 }
 
@@ -846,8 +927,8 @@ static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, 
 extern "C" int qd_parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
                             void* stream) {
     if (!c || (n && (!ascii_dev || !masks_dev))) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return parse_dev(c, strict, ascii_dev, n, masks_dev, n_masks_dev, pick_stream(c, stream));
 }
 
@@ -855,8 +936,8 @@ extern "C" int qd_parse(qd_ctx* c, int strict, const uint8_t* ascii, size_t n, u
     clear_err(err);
     if (n_masks) *n_masks = 0;
     if (!c || (n && (!ascii || !masks))) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
     QD_CUDA(c, c->in.reserve(n + 16));
@@ -902,16 +983,16 @@ static int canonical_seq_dev(qd_ctx* c, int enc, int forward_only, const uint8_t
 
 extern "C" int qd_canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, void* stream) {
     if (!c || (n && (!dna_dev || !out_dev))) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return canonical_seq_dev(c, enc, forward_only, dna_dev, n, out_dev, pick_stream(c, stream));
 }
 
 extern "C" int qd_canonical(qd_ctx* c, int enc, int forward_only, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
     clear_err(err);
     if (!c || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
     QD_CUDA(c, c->in.reserve(n + 16));
@@ -1003,8 +1084,8 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
     if (n_masks) *n_masks = 0;
     if (n_records) *n_records = 0;
     if (!c || (n && !text)) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
     QD_CUDA(c, c->in.reserve(n + 16));
@@ -1053,6 +1134,8 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
 
 static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride, size_t n_seq, size_t len, size_t w, int mode,
                              uint8_t* out_dev, uint64_t key_stride, cudaStream_t s);
+static int windows_all_batch_dev(qd_ctx* c, int enc, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w_dna, size_t w_aa,
+                                 uint8_t* dna_out_dev, uint8_t* aa_out_dev, cudaStream_t s);
 
 static int windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, uint8_t* out_dev, cudaStream_t s) {
     if (w == 0 || w > 0xffffffffull) return QD_ERR_INVALID_ARGUMENT;
@@ -1100,8 +1183,8 @@ static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride,
 extern "C" int qd_windows_batch_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n_seq, size_t seq_len, size_t w, int mode, uint8_t* out_dev,
                                     void* stream) {
     if (!c) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return windows_batch_dev(c, seq_dev, seq_len, n_seq, seq_len, w, mode, out_dev, seq_len, pick_stream(c, stream));
 }
 
@@ -1120,10 +1203,14 @@ extern "C" size_t qd_windows_all_batch_counts(size_t seq_len, size_t w_dna, size
 extern "C" int qd_windows_all_batch_dev(qd_ctx* c, int enc, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w_dna, size_t w_aa,
                                         uint8_t* dna_out_dev, uint8_t* aa_out_dev, void* stream) {
     if (!c || w_dna < 1 || w_aa < 1 || w_dna > 64 || w_aa > 64) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
+    return windows_all_batch_dev(c, enc, dna_dev, n_seq, seq_len, w_dna, w_aa, dna_out_dev, aa_out_dev, g.s);
+}
+
+static int windows_all_batch_dev(qd_ctx* c, int enc, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w_dna, size_t w_aa,
+                                 uint8_t* dna_out_dev, uint8_t* aa_out_dev, cudaStream_t s) {
     if (n_seq == 0 || seq_len == 0) return QD_OK;
-    cudaStream_t s = pick_stream(c, stream);
     size_t counts[8];
     qd_windows_all_batch_counts(seq_len, w_dna, w_aa, counts);
     // forward and reverse-complement DNA windows straight from the input (strict alphabet: anything else is an error)
@@ -1150,14 +1237,226 @@ extern "C" int qd_windows_all_batch_dev(qd_ctx* c, int enc, const uint8_t* dna_d
 
 extern "C" int qd_windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, uint8_t* out_dev, void* stream) {
     if (!c || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     return windows_dev(c, seq_dev, n, w, out_dev, pick_stream(c, stream));
+}
+
+// ---- checksum and chunked ("ring") window enumeration -----------------------------------------------------------
+static int checksum_dev(qd_ctx* c, const uint8_t* buf_dev, uint64_t n, const uint64_t* n_dev, uint64_t n_scale, uint64_t base,
+                        uint64_t* acc_dev, cudaStream_t s) {
+    if (n == 0 && !n_dev) return QD_OK;
+    ChecksumParams p{};
+    p.buf = buf_dev;
+    p.n = n;
+    p.n_dev = n_dev;
+    p.n_scale = n_scale;
+    p.base = base;
+    p.acc = reinterpret_cast<unsigned long long*>(acc_dev);
+    const uint64_t gran = (n >> 4) + 1;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((gran + CHECKSUM_THREADS - 1) / CHECKSUM_THREADS, (uint64_t)c->sm_count * 8));
+    checksum64_kernel<<<grid, CHECKSUM_THREADS, 0, s>>>(p);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_checksum64_dev(qd_ctx* c, const uint8_t* buf_dev, size_t n, uint64_t base, uint64_t* acc_dev, void* stream) {
+    if (!c || !acc_dev || (n && !buf_dev)) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
+    return checksum_dev(c, buf_dev, n, nullptr, 0, base, acc_dev, g.s);
+}
+
+extern "C" uint64_t qd_checksum64_weight(uint64_t word_index) { return checksum_weight(word_index); }
+
+extern "C" size_t qd_chunk_count(size_t n_units, size_t chunk_units) { return chunk_units ? (n_units + chunk_units - 1) / chunk_units : 0; }
+
+extern "C" size_t qd_canonical_chunk_bytes(size_t chunk_seqs, size_t seq_len, size_t w) {
+    return (seq_len >= w && w) ? chunk_seqs * (seq_len - w + 1) * w : 0;
+}
+
+extern "C" size_t qd_windows_all_chunk_bytes(size_t chunk_seqs, size_t seq_len, size_t w_dna, size_t w_aa, size_t* aa_offset) {
+    size_t counts[8];
+    qd_windows_all_batch_counts(seq_len, w_dna, w_aa, counts);
+    const size_t dna_bytes = 2 * chunk_seqs * counts[0] * w_dna;
+    size_t aa_bytes = 0;
+    for (int f = 0; f < 6; f++) aa_bytes += chunk_seqs * counts[2 + f] * w_aa;
+    const size_t aa_off = (dna_bytes + 15) & ~(size_t)15;
+    if (aa_offset) *aa_offset = aa_off;
+    return aa_off + aa_bytes;
+}
+
+namespace {
+struct Ring {
+    uint8_t* base;
+    size_t slot_bytes, n_slots;
+    uint8_t* slot(size_t chunk) const { return base + (chunk % n_slots) * slot_bytes; }
+};
+// slots of `need` bytes (rounded up to 256) cut from the caller's ring; false when not even one fits
+bool make_ring(uint8_t* ring_dev, size_t ring_bytes, size_t need, Ring* r) {
+    r->base = ring_dev;
+    r->slot_bytes = (need + 255) & ~(size_t)255;
+    r->n_slots = r->slot_bytes ? ring_bytes / r->slot_bytes : 0;
+    return ring_dev && r->n_slots >= 1 && (reinterpret_cast<uintptr_t>(ring_dev) & 15) == 0;
+}
+}  // namespace
+
+extern "C" int qd_canonical_windows_chunked_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n_seq, size_t seq_len,
+                                                size_t w, uint8_t* ring_dev, size_t ring_bytes, size_t chunk_seqs, uint64_t* checksums_dev,
+                                                qd_chunk_fn consume, void* user, void* stream) {
+    if (!c || w < 1 || w > CANON_MAX_W || chunk_seqs == 0) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n_seq == 0 || seq_len < w) return QD_OK;
+    Ring ring;
+    const size_t per_seq = (seq_len - w + 1) * w;
+    if (!make_ring(ring_dev, ring_bytes, std::min(chunk_seqs, n_seq) * per_seq, &ring)) {
+        c->last_error = "ring smaller than one chunk (qd_canonical_chunk_bytes) or not 16-byte aligned";
+        return QD_ERR_INVALID_ARGUMENT;
+    }
+    const size_t n_chunks = qd_chunk_count(n_seq, chunk_seqs);
+    if (checksums_dev) QD_CUDA(c, cudaMemsetAsync(checksums_dev, 0, n_chunks * 8, g.s));
+    for (size_t k = 0; k < n_chunks; k++) {
+        const size_t s0 = k * chunk_seqs, cnt = std::min(chunk_seqs, n_seq - s0);
+        uint8_t* out = ring.slot(k);
+        if (int rc = canonical_dev(c, enc, forward_only, dna_dev + s0 * seq_len, cnt, seq_len, w, out, g.s)) return rc;
+        // the error key of a chunk is relative to the chunk's first byte: callers that need positions run chunks of their own
+        if (checksums_dev)
+            if (int rc = checksum_dev(c, out, cnt * per_seq, nullptr, 0, (uint64_t)s0 * per_seq, checksums_dev + k, g.s)) return rc;
+        if (consume) consume(user, k, s0, cnt, out, cnt * per_seq, nullptr, (void*)g.s);
+    }
+    return QD_OK;
+}
+
+extern "C" int qd_windows_all_chunked_dev(qd_ctx* c, int enc, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w_dna, size_t w_aa,
+                                          uint8_t* ring_dev, size_t ring_bytes, size_t chunk_seqs, uint64_t* checksums_dev, qd_chunk_fn consume,
+                                          void* user, void* stream) {
+    if (!c || w_dna < 1 || w_aa < 1 || w_dna > 64 || w_aa > 64 || chunk_seqs == 0) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n_seq == 0 || seq_len == 0) return QD_OK;
+    Ring ring;
+    size_t aa_off = 0;
+    if (!make_ring(ring_dev, ring_bytes, qd_windows_all_chunk_bytes(std::min(chunk_seqs, n_seq), seq_len, w_dna, w_aa, &aa_off), &ring)) {
+        c->last_error = "ring smaller than one chunk (qd_windows_all_chunk_bytes) or not 16-byte aligned";
+        return QD_ERR_INVALID_ARGUMENT;
+    }
+    const size_t n_chunks = qd_chunk_count(n_seq, chunk_seqs);
+    if (checksums_dev) QD_CUDA(c, cudaMemsetAsync(checksums_dev, 0, n_chunks * 8, g.s));
+    for (size_t k = 0; k < n_chunks; k++) {
+        const size_t s0 = k * chunk_seqs, cnt = std::min(chunk_seqs, n_seq - s0);
+        size_t off = 0;
+        const size_t bytes = qd_windows_all_chunk_bytes(cnt, seq_len, w_dna, w_aa, &off);
+        uint8_t* out = ring.slot(k);
+        if (int rc = windows_all_batch_dev(c, enc, dna_dev + s0 * seq_len, cnt, seq_len, w_dna, w_aa, out, out + off, g.s)) return rc;
+        if (checksums_dev) {
+            // chunk-relative stream: the DNA windows, then (without the alignment gap) the amino-acid windows
+            size_t counts[8];
+            qd_windows_all_batch_counts(seq_len, w_dna, w_aa, counts);
+            const uint64_t dna_bytes = 2 * (uint64_t)cnt * counts[0] * w_dna;
+            if (int rc = checksum_dev(c, out, dna_bytes, nullptr, 0, 0, checksums_dev + k, g.s)) return rc;
+            if (int rc = checksum_dev(c, out + off, bytes - off, nullptr, 0, dna_bytes, checksums_dev + k, g.s)) return rc;
+        }
+        if (consume) consume(user, k, s0, cnt, out, bytes, nullptr, (void*)g.s);
+    }
+    return QD_OK;
 }
 
 // =================================================================================================
 // host-pointer entry points
 // =================================================================================================
+// ---- one long sequence through the pipe streams --------------------------------------------------------------------------
+// Chunk size for a sequence of n bytes: a multiple of 48 (whole runs, whole codons, whole 16-byte granules), small enough
+// that the pipeline fills quickly, at most the context's chunk size.
+static uint64_t long_chunk_nt(const qd_ctx* c, uint64_t n) {
+    uint64_t ch = std::min<uint64_t>(c->chunk_bytes, std::max<uint64_t>(uint64_t(4) << 20, n / 16));
+    return std::max<uint64_t>(RUN_NT, ch / RUN_NT * RUN_NT);
+}
+static bool long_call(const qd_ctx* c, uint64_t n) {
+    return n >= std::min<uint64_t>(uint64_t(8) << 20, 2 * (uint64_t)c->chunk_bytes) && n >= 2 * long_chunk_nt(c, n);
+}
+
+// Frames of the codon starts in [lo, hi) of ONE n-nt host sequence (lo a multiple of 48, hi a multiple of 48 or n), chunk by
+// chunk: a chunk [a, b) is translated as the stand-alone sequence dna[a, min(n, b + 2)) -- the 2-nt halo completes the codons
+// that start before b -- and its frames are copied to their place in the global frames: forward local frame k is global
+// frame k from residue a / 3 on; reverse local frame k is global reverse frame (k + d) % 3 from residue (k + d) / 3 on,
+// d = nucleotides to the right of the piece.  frame_at[f] = where global frame f starts in `out`.
+// Error keys are global positions.  The caller resets / fetches the error key and synchronises the pipe streams.
+static int frames_long_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna, uint64_t n, uint64_t lo, uint64_t hi,
+                                uint8_t* out, const size_t frame_at[6]) {
+    const uint64_t chunk = long_chunk_nt(c, n);
+    int turn = 0;
+    for (uint64_t a = lo; a < hi; a += chunk) {
+        const uint64_t b = std::min(hi, a + chunk), read_end = std::min<uint64_t>(n, b + 2), n_local = read_end - a, d = n - read_end;
+        Pipe& P = c->pipe[turn++ % N_PIPE];
+        cudaStream_t s = P.stream;
+        tls_stream = s;
+        const size_t slot_bytes = qd_slots_bytes(n_local, frames);
+        QD_CUDA(c, P.in.reserve(n_local + 16));
+        QD_CUDA(c, P.out.reserve(slot_bytes + 16));
+        QD_CUDA(c, cudaMemcpyAsync(P.in.p, dna + a, n_local, cudaMemcpyHostToDevice, s));
+        if (int rc = frames_uniform_dev(c, slot, enc, strict, frames, P.in.as<uint8_t>(), 1, n_local, P.out.as<uint8_t>(), s, a)) return rc;
+        const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
+        for (int f = 0; f < n_slots; f++) {
+            const size_t len = qd_frame_len(n_local, f % 3);
+            if (!len) continue;
+            const uint8_t* src = P.out.as<uint8_t>() + qd_slot_frame_offset(n_local, frames, f);
+            uint8_t* dst;
+            if (f < 3) dst = out + frame_at[f] + a / 3;
+            else dst = out + frame_at[3 + (f - 3 + d) % 3] + (f - 3 + d) / 3;
+            QD_CUDA(c, cudaMemcpyAsync(dst, src, len, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    tls_stream = c->stream;
+    return QD_OK;
+}
+
+// out[n - b, n - a) = reverse complement of dna[a, b) for the chunks [a, b) of [lo, hi)
+static int revcomp_long_pipeline(qd_ctx* c, int which, const uint8_t* dna, uint64_t n, uint64_t lo, uint64_t hi, uint8_t* out) {
+    const uint64_t chunk = long_chunk_nt(c, n);
+    int turn = 0;
+    for (uint64_t a = lo; a < hi; a += chunk) {
+        const uint64_t b = std::min(hi, a + chunk), len = b - a;
+        Pipe& P = c->pipe[turn++ % N_PIPE];
+        cudaStream_t s = P.stream;
+        tls_stream = s;
+        QD_CUDA(c, P.in.reserve(len + 16));
+        QD_CUDA(c, P.out.reserve(len + 16));
+        QD_CUDA(c, cudaMemcpyAsync(P.in.p, dna + a, len, cudaMemcpyHostToDevice, s));
+        if (int rc = revcomp_dev_table(c, which, P.in.as<uint8_t>(), len, P.out.as<uint8_t>(), s, nullptr, a)) return rc;
+        QD_CUDA(c, cudaMemcpyAsync(out + (n - b), P.out.p, len, cudaMemcpyDeviceToHost, s));
+    }
+    tls_stream = c->stream;
+    return QD_OK;
+}
+
+static int pipes_begin(qd_ctx* c) {
+    for (int i = 0; i < N_PIPE; i++) QD_CUDA(c, cudaStreamSynchronize(c->pipe[i].stream));
+    if (int rc = reset_err_key(c, c->stream)) return rc;
+    QD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QD_OK;
+}
+static int pipes_end(qd_ctx* c, unsigned long long* key) {
+    for (int i = 0; i < N_PIPE; i++) QD_CUDA(c, cudaStreamSynchronize(c->pipe[i].stream));
+    return fetch_err_key(c, c->stream, key);
+}
+
+// frame lengths / count / positions of the tight output f0|f1|f2[|r0|r1|r2] of an n-nt sequence
+static int tight_frames(size_t n, int frames, size_t frame_at[6], size_t out_len[6]) {
+    const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
+    size_t off = 0;
+    int nf = 0;
+    for (int f = 0; f < 6; f++) {
+        const size_t len = f < n_slots ? qd_frame_len(n, f % 3) : 0;
+        frame_at[f] = off;
+        if (out_len) out_len[f] = len;
+        off += len;
+        nf += len != 0;
+    }
+    return nf;
+}
+
 extern "C" int qd_translate(qd_ctx* c, int table, int enc, int strict, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
     size_t lens[6];
     int nf = 0;
@@ -1175,10 +1474,23 @@ extern "C" int qd_translate_frames(qd_ctx* c, int table, int enc, int strict, in
     for (int k = 0; k < 6; k++)
         if (out_len) out_len[k] = 0;
     if (n_frames) *n_frames = 0;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
+    if (long_call(c, n)) {
+        // a chromosome-sized sequence: chunks cut at multiples of 48 with a 2-nt halo, H2D / kernel / D2H overlapped on the
+        // pipe streams, each chunk's frames copied straight to their place in the caller's buffer
+        size_t frame_at[6];
+        const int nf = tight_frames(n, frames, frame_at, out_len);
+        if (int rc = pipes_begin(c)) return rc;
+        if (int rc = frames_long_pipeline(c, slot, enc, strict, frames, dna, n, 0, n, out, frame_at)) return rc;
+        unsigned long long key = 0;
+        if (int rc = pipes_end(c, &key)) return rc;
+        if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+        if (n_frames) *n_frames = nf;
+        return QD_OK;
+    }
     const size_t slot_bytes = qd_slots_bytes(n, frames);
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(slot_bytes + 16));
@@ -1232,14 +1544,22 @@ extern "C" int qd_translate_frames(qd_ctx* c, int table, int enc, int strict, in
 extern "C" int qd_revcomp(qd_ctx* c, int enc, int strict, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
     clear_err(err);
     if (!c || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
+    const int which = enc == QD_ENC_ASCII ? (strict ? RC_PAIR_ASCII_STRICT : RC_PAIR_ASCII) : (strict ? RC_PAIR_MASK_STRICT : RC_PAIR_MASK);
+    if (long_call(c, n)) {  // chromosome-sized: chunked, copies and kernels overlapped on the pipe streams
+        if (int rc = pipes_begin(c)) return rc;
+        if (int rc = revcomp_long_pipeline(c, which, dna, n, 0, n, out)) return rc;
+        unsigned long long key = 0;
+        if (int rc = pipes_end(c, &key)) return rc;
+        if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+        return QD_OK;
+    }
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(n + 16));
     QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
-    const int which = enc == QD_ENC_ASCII ? (strict ? RC_PAIR_ASCII_STRICT : RC_PAIR_ASCII) : (strict ? RC_PAIR_MASK_STRICT : RC_PAIR_MASK);
     if (n <= SMALL_CALL_BYTES) {  // small call: [result | error key] in one copy through pinned memory
         const size_t key_off = (n + 15) & ~(size_t)15;
         QD_CUDA(c, c->out.reserve(key_off + 16));
@@ -1312,7 +1632,7 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
         Pipe& P = c->pipe[turn % N_PIPE];
         turn++;
         cudaStream_t s = P.stream;
-        if (in_bytes > P.in.cap || out_bytes > P.out.cap) QD_CUDA(c, cudaStreamSynchronize(s));  // about to reallocate
+        tls_stream = s;  // this pipe's buffers grow on its own stream
         QD_CUDA(c, P.in.reserve(in_bytes + 16));
         QD_CUDA(c, P.out.reserve(out_bytes + 16));
         if (in_bytes) QD_CUDA(c, cudaMemcpyAsync(P.in.p, dna + (uniform ? in0 : in0 - offsets[0]), in_bytes, cudaMemcpyHostToDevice, s));
@@ -1320,7 +1640,6 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
         if (uniform) {
             rc = frames_uniform_dev(c, slot, enc, strict, frames, P.in.as<uint8_t>(), cnt, uniform_len, P.out.as<uint8_t>(), s, in0);
         } else {
-            if ((cnt + 1) * 8 > P.offsets.cap) QD_CUDA(c, cudaStreamSynchronize(s));
             QD_CUDA(c, P.offsets.reserve((cnt + 1) * sizeof(uint64_t)));
             QD_CUDA(c, cudaMemcpyAsync(P.offsets.p, offsets + r0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
             // the chunk's device buffer starts at the sequence whose offset is in0
@@ -1332,6 +1651,7 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
         r0 = r1;
     }
     for (int i = 0; i < N_PIPE; i++) QD_CUDA(c, cudaStreamSynchronize(c->pipe[i].stream));
+    tls_stream = c->stream;
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, c->stream, &key)) return rc;
     if (key != NO_ERROR_KEY) {
@@ -1358,8 +1678,8 @@ extern "C" int qd_translate_frames_batch(qd_ctx* c, int table, int enc, int stri
     if (!c || !valid_frames(frames) || !offsets) return QD_ERR_INVALID_ARGUMENT;
     int slot;
     if (int rc = check_table(table, err, &slot)) return rc;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     return batch_pipeline(c, slot, enc, strict, frames, dna, offsets, n_seq, 0, out, out_offsets, err);
 }
 
@@ -1369,8 +1689,8 @@ extern "C" int qd_translate_frames_batch_uniform(qd_ctx* c, int table, int enc, 
     if (!c || !valid_frames(frames)) return QD_ERR_INVALID_ARGUMENT;
     int slot;
     if (int rc = check_table(table, err, &slot)) return rc;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (seq_len == 0) return QD_OK;
     return batch_pipeline(c, slot, enc, strict, frames, dna, nullptr, n_seq, seq_len, out, nullptr, err);
 }
@@ -1379,8 +1699,8 @@ extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const 
                                     qd_err* err) {
     clear_err(err);
     if (!c || w < 1 || w > CANON_MAX_W) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n < w) return QD_OK;
     cudaStream_t s = c->stream;
     const size_t out_bytes = (n - w + 1) * w;
@@ -1401,8 +1721,8 @@ extern "C" int qd_canonical_window_keys(qd_ctx* c, int enc, int forward_only, in
     clear_err(err);
     const size_t key_bytes = qd_canonical_key_bytes(kind, w);
     if (!c || key_bytes == 0) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n < w) return QD_OK;
     cudaStream_t s = c->stream;
     const size_t out_bytes = (n - w + 1) * key_bytes;
@@ -1474,8 +1794,8 @@ extern "C" int qd_expansion_windows_dev(qd_ctx* c, int enc, const uint8_t* windo
                                         uint64_t* counts_dev, uint64_t* out_index_dev, uint8_t* out_dev, uint64_t out_capacity_rows,
                                         void* stream) {
     if (!c || w < 1 || !expansion_fast_path(w, max_expansions) || !counts_dev || !out_index_dev) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
     if (n_win == 0) return QD_OK;
     cudaStream_t s = pick_stream(c, stream);
     QD_CUDA(c, c->aux1.reserve(n_win * 8));  // emit
@@ -1487,12 +1807,51 @@ extern "C" int qd_expansion_windows_dev(qd_ctx* c, int enc, const uint8_t* windo
     return QD_OK;
 }
 
+extern "C" size_t qd_expansion_chunk_bytes(size_t chunk_windows, size_t w, uint64_t max_expansions) {
+    return chunk_windows * (size_t)max_expansions * w;
+}
+
+extern "C" int qd_expansion_windows_chunked_dev(qd_ctx* c, int enc, const uint8_t* windows_dev, size_t n_win, size_t w, uint64_t max_expansions,
+                                                uint8_t* ring_dev, size_t ring_bytes, size_t chunk_windows, uint64_t* counts_dev,
+                                                uint64_t* chunk_rows_dev, uint64_t* checksums_dev, qd_chunk_fn consume, void* user,
+                                                void* stream) {
+    if (!c || w < 1 || !expansion_fast_path(w, max_expansions) || chunk_windows == 0 || !chunk_rows_dev) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n_win == 0) return QD_OK;
+    Ring ring;
+    const size_t cw = std::min(chunk_windows, n_win);
+    if (!make_ring(ring_dev, ring_bytes, qd_expansion_chunk_bytes(cw, w, max_expansions), &ring)) {
+        c->last_error = "ring smaller than one chunk (qd_expansion_chunk_bytes) or not 16-byte aligned";
+        return QD_ERR_INVALID_ARGUMENT;
+    }
+    QD_CUDA(c, c->aux1.reserve(cw * 8));        // emit
+    QD_CUDA(c, c->aux2.reserve((cw + 1) * 8));  // row index of the chunk's windows
+    QD_CUDA(c, c->aux3.reserve(cw * 8));        // descriptors
+    if (!counts_dev) QD_CUDA(c, c->aux0.reserve(cw * 8));
+    const size_t n_chunks = qd_chunk_count(n_win, chunk_windows);
+    if (checksums_dev) QD_CUDA(c, cudaMemsetAsync(checksums_dev, 0, n_chunks * 8, g.s));
+    for (size_t k = 0; k < n_chunks; k++) {
+        const size_t i0 = k * chunk_windows, cnt = std::min(chunk_windows, n_win - i0);
+        uint8_t* out = ring.slot(k);
+        ExpandParams p = expansion_params(c, enc, windows_dev + i0 * w, cnt, w, max_expansions, counts_dev ? counts_dev + i0 : c->aux0.as<uint64_t>(),
+                                          c->aux1.as<uint64_t>(), c->aux2.as<uint64_t>(), c->aux3.as<uint64_t>());
+        if (int rc = expansion_count_dev(c, p, enc, g.s)) return rc;
+        if (int rc = expansion_write_tiles_dev(c, p, out, (uint64_t)cnt * max_expansions, g.s)) return rc;
+        QD_CUDA(c, cudaMemcpyAsync(chunk_rows_dev + k, c->aux2.as<uint64_t>() + cnt, 8, cudaMemcpyDeviceToDevice, g.s));
+        if (checksums_dev)
+            if (int rc = checksum_dev(c, out, 0, chunk_rows_dev + k, w, 0, checksums_dev + k, g.s)) return rc;
+        if (consume) consume(user, k, i0, cnt, out, (uint64_t)cnt * max_expansions * w, chunk_rows_dev + k, (void*)g.s);
+    }
+    return QD_OK;
+}
+
 extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, size_t n_win, size_t w, uint64_t max_expansions,
                                     uint64_t* counts, uint64_t* out_index, uint8_t* out, qd_err* err) {
     clear_err(err);
     if (!c || w < 1 || w > 0xffffffffull) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n_win == 0) {
         if (out_index) out_index[0] = 0;
         return QD_OK;
@@ -1553,8 +1912,8 @@ extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, 
 extern "C" int qd_windows(qd_ctx* c, const uint8_t* seq, size_t n, size_t w, uint8_t* out, size_t* n_windows) {
     if (n_windows) *n_windows = 0;
     if (!c || w == 0) return QD_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n < w) return QD_OK;
     cudaStream_t s = c->stream;
     const size_t count = n - w + 1;
@@ -1573,8 +1932,8 @@ extern "C" int qd_windows_all(qd_ctx* c, int enc, const uint8_t* dna, size_t n, 
     clear_err(err);
     if (!c || !counts || w_dna == 0 || w_aa == 0) return QD_ERR_INVALID_ARGUMENT;
     for (int i = 0; i < 8; i++) counts[i] = 0;
-    std::lock_guard<std::mutex> g(c->mu);
-    QD_CUDA(c, cudaSetDevice(c->device));
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
     auto nwin = [](size_t len, size_t w) { return len + 1 - std::min(w, len + 1); };  // benches/all_windows.rs:209-211
@@ -1650,5 +2009,180 @@ extern "C" int qd_windows_all(qd_ctx* c, int enc, const uint8_t* dna, size_t n, 
         QD_CUDA(c, cudaMemcpyAsync(origin, o, total * 8, cudaMemcpyDeviceToHost, s));
         QD_CUDA(c, cudaStreamSynchronize(s));
     }
+    return QD_OK;
+}
+
+// =================================================================================================
+// several GPUs of one box from one call: partition by bytes, one context / host thread / set of pipe
+// streams per device, every device copies its results to the right offset of the caller's ONE output buffer.  Nothing is
+// exchanged between devices (no collective).
+// =================================================================================================
+#include <thread>
+
+namespace {
+// the error with the lowest (sequence, position) wins -- what a serial pass over the batch would have hit first
+void keep_first_error(int rc, const qd_err& e, int* best_rc, qd_err* best) {
+    if (rc == QD_OK) return;
+    const bool data_err = rc >= QD_ERR_NON_ASCII_BYTE && rc <= QD_ERR_BAD_MASK;
+    const bool best_data = *best_rc >= QD_ERR_NON_ASCII_BYTE && *best_rc <= QD_ERR_BAD_MASK;
+    if (*best_rc == QD_OK || (!data_err && best_data) ||
+        (data_err == best_data && (e.seq_index < best->seq_index || (e.seq_index == best->seq_index && e.pos < best->pos)))) {
+        *best_rc = rc;
+        *best = e;
+    }
+}
+bool valid_ctxs(qd_ctx* const* ctxs, int n_ctx) {
+    if (!ctxs || n_ctx < 1 || n_ctx > 64) return false;
+    for (int i = 0; i < n_ctx; i++) {
+        if (!ctxs[i]) return false;
+        for (int j = 0; j < i; j++)
+            if (ctxs[j] == ctxs[i]) return false;
+    }
+    return true;
+}
+template <class F>
+void run_per_device(int n_ctx, F&& body) {
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_ctx; i++) th.emplace_back(body, i);
+    body(0);
+    for (auto& t : th) t.join();
+}
+}  // namespace
+
+extern "C" int qd_translate_frames_batch_multi(qd_ctx* const* ctxs, int n_ctx, int table, int enc, int strict, int frames, const uint8_t* dna,
+                                               const uint64_t* offsets, size_t n_seq, size_t seq_len, uint8_t* out, uint64_t* out_offsets,
+                                               qd_err* err) {
+    clear_err(err);
+    if (!valid_ctxs(ctxs, n_ctx) || !valid_frames(frames)) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (int rc = check_table(table, err, &slot)) return rc;
+    if (n_seq == 0 || (!offsets && seq_len == 0)) {
+        if (offsets && out_offsets) out_offsets[0] = 0;
+        return QD_OK;
+    }
+    const uint64_t stride = 16 * (uint64_t)frames;
+    // cut points: sequence boundaries, balanced by BYTES
+    std::vector<size_t> cut(n_ctx + 1, n_seq);
+    cut[0] = 0;
+    std::vector<uint64_t> own_oo;
+    if (offsets) {
+        const uint64_t total = offsets[n_seq] - offsets[0];
+        for (int k = 1; k < n_ctx; k++) {
+            const uint64_t target = offsets[0] + total / n_ctx * k + total % n_ctx * k / n_ctx;
+            size_t j = (size_t)(std::lower_bound(offsets, offsets + n_seq + 1, target) - offsets);  // first boundary >= target
+            if (j > 0 && target - offsets[j - 1] < offsets[std::min(j, n_seq)] - target) j--;        // ... or the nearer one before it
+            cut[k] = std::min(std::max(j, cut[k - 1]), n_seq);
+        }
+        if (!out_offsets) {
+            own_oo.resize(n_seq + 1);
+            out_offsets = own_oo.data();
+        }
+        uint64_t acc = 0;
+        for (size_t i = 0; i < n_seq; i++) {
+            out_offsets[i] = acc;
+            acc += stride * qd_runs((size_t)(offsets[i + 1] - offsets[i]));
+        }
+        out_offsets[n_seq] = acc;
+    } else {
+        for (int k = 1; k < n_ctx; k++) cut[k] = n_seq / n_ctx * k + n_seq % n_ctx * k / n_ctx;
+    }
+    std::vector<int> rcs(n_ctx, QD_OK);
+    std::vector<qd_err> errs(n_ctx);
+    const uint64_t uni_out = offsets ? 0 : stride * qd_runs(seq_len);
+    run_per_device(n_ctx, [&](int i) {
+        clear_err(&errs[i]);
+        const size_t r0 = cut[i], cnt = cut[i + 1] - cut[i];
+        if (cnt == 0) return;
+        qd_ctx* c = ctxs[i];
+        Guard g(c);
+        if (!g.ok) {
+            rcs[i] = QD_ERR_CUDA;
+            return;
+        }
+        if (offsets)
+            rcs[i] = batch_pipeline(c, slot, enc, strict, frames, dna + (offsets[r0] - offsets[0]), offsets + r0, cnt, 0, out + out_offsets[r0], nullptr,
+                                    &errs[i]);
+        else
+            rcs[i] = batch_pipeline(c, slot, enc, strict, frames, dna + (uint64_t)r0 * seq_len, nullptr, cnt, seq_len, out + (uint64_t)r0 * uni_out, nullptr,
+                                    &errs[i]);
+        errs[i].seq_index += r0;
+    });
+    int best_rc = QD_OK;
+    qd_err best{};
+    for (int i = 0; i < n_ctx; i++) keep_first_error(rcs[i], errs[i], &best_rc, &best);
+    if (best_rc != QD_OK && err) *err = best;
+    return best_rc;
+}
+
+// the 48-aligned cut points of an n-nt sequence over n_ctx devices
+static std::vector<uint64_t> chromosome_cuts(uint64_t n, int n_ctx) {
+    const uint64_t runs = (n + RUN_NT - 1) / RUN_NT;
+    std::vector<uint64_t> cut(n_ctx + 1);
+    for (int k = 0; k <= n_ctx; k++) cut[k] = std::min<uint64_t>(n, (runs / n_ctx * k + runs % n_ctx * k / n_ctx) * RUN_NT);
+    cut[n_ctx] = n;
+    return cut;
+}
+
+extern "C" int qd_translate_frames_multi(qd_ctx* const* ctxs, int n_ctx, int table, int enc, int strict, int frames, const uint8_t* dna, size_t n,
+                                         uint8_t* out, size_t out_len[6], int* n_frames, qd_err* err) {
+    clear_err(err);
+    if (!valid_ctxs(ctxs, n_ctx) || !valid_frames(frames) || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (int rc = check_table(table, err, &slot)) return rc;
+    size_t frame_at[6];
+    const int nf = tight_frames(n, frames, frame_at, out_len);
+    if (n_frames) *n_frames = 0;
+    if (n == 0) return QD_OK;
+    const std::vector<uint64_t> cut = chromosome_cuts(n, n_ctx);
+    std::vector<int> rcs(n_ctx, QD_OK);
+    std::vector<unsigned long long> keys(n_ctx, NO_ERROR_KEY);
+    run_per_device(n_ctx, [&](int i) {
+        if (cut[i] >= cut[i + 1]) return;
+        qd_ctx* c = ctxs[i];
+        Guard g(c);
+        if (!g.ok) {
+            rcs[i] = QD_ERR_CUDA;
+            return;
+        }
+        if ((rcs[i] = pipes_begin(c))) return;
+        if ((rcs[i] = frames_long_pipeline(c, slot, enc, strict, frames, dna, n, cut[i], cut[i + 1], out, frame_at))) return;
+        rcs[i] = pipes_end(c, &keys[i]);
+    });
+    unsigned long long key = NO_ERROR_KEY;
+    for (int i = 0; i < n_ctx; i++) {
+        if (rcs[i]) return rcs[i];
+        key = std::min(key, keys[i]);
+    }
+    if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+    if (n_frames) *n_frames = nf;
+    return QD_OK;
+}
+
+extern "C" int qd_revcomp_multi(qd_ctx* const* ctxs, int n_ctx, int enc, int strict, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
+    clear_err(err);
+    if (!valid_ctxs(ctxs, n_ctx) || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
+    if (n == 0) return QD_OK;
+    const int which = enc == QD_ENC_ASCII ? (strict ? RC_PAIR_ASCII_STRICT : RC_PAIR_ASCII) : (strict ? RC_PAIR_MASK_STRICT : RC_PAIR_MASK);
+    const std::vector<uint64_t> cut = chromosome_cuts(n, n_ctx);
+    std::vector<int> rcs(n_ctx, QD_OK);
+    std::vector<unsigned long long> keys(n_ctx, NO_ERROR_KEY);
+    run_per_device(n_ctx, [&](int i) {
+        if (cut[i] >= cut[i + 1]) return;
+        qd_ctx* c = ctxs[i];
+        Guard g(c);
+        if (!g.ok) {
+            rcs[i] = QD_ERR_CUDA;
+            return;
+        }
+        if ((rcs[i] = pipes_begin(c))) return;
+        if ((rcs[i] = revcomp_long_pipeline(c, which, dna, n, cut[i], cut[i + 1], out))) return;
+        rcs[i] = pipes_end(c, &keys[i]);
+    });
+    unsigned long long key = NO_ERROR_KEY;
+    for (int i = 0; i < n_ctx; i++) {
+        if (rcs[i]) return rcs[i];
+        key = std::min(key, keys[i]);
+    }
+    if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
     return QD_OK;
 }

@@ -646,6 +646,7 @@ struct RevcompParams {
     uint32_t or_forbid;      // bits no input byte may have
     uint32_t filler;         // a valid input byte replicated 4x: stands in for bytes outside the buffer in its edge granules
     unsigned long long* err_key;
+    uint64_t key_base;       // added to an input index to form the error key (chunks of a longer sequence)
 };
 
 #ifndef QD_RC_THREADS
@@ -795,10 +796,10 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 4) revcomp_kern
                 const uint32_t bad = ((o.x | o.y | o.z | o.w) & (RC_INVALID * 0x01010101u)) | ((a & p.and_need) ^ p.and_need) | (r & p.or_forbid);
                 if (bad) {  // exact: the lowest failing input index of this granule
                     const uint64_t i0 = n - 16 * j - 16;
-                    if ((unsigned long long)i0 < *reinterpret_cast<volatile unsigned long long*>(p.err_key)) {
+                    if ((unsigned long long)(p.key_base + i0) < *reinterpret_cast<volatile unsigned long long*>(p.err_key)) {
                         for (int t = 0; t < 16; t++)
                             if (__ldg(p.table + __ldg(p.dna + i0 + t)) == 0) {
-                                atomicMin(p.err_key, (unsigned long long)(i0 + t));
+                                atomicMin(p.err_key, (unsigned long long)(p.key_base + i0 + t));
                                 break;
                             }
                     }
@@ -827,7 +828,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 4) revcomp_kern
     if (blockIdx.x == 0 && tid < (int)(n & 15u)) {
         const uint64_t i = tid;
         const uint32_t v = __ldg(p.table + __ldg(p.dna + i));
-        if (v == 0) atomicMin(p.err_key, (unsigned long long)i);
+        if (v == 0) atomicMin(p.err_key, (unsigned long long)(p.key_base + i));
         p.out[n - 1 - i] = (uint8_t)v;
     }
 }
@@ -2557,6 +2558,70 @@ __global__ void __launch_bounds__(256) fasta_finish_kernel(const FastaParams p, 
         p.records[r].header_end = header_end;
         p.records[r].content_end = next_content;
         p.records[r].line_end = next_line;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Position-weighted linear checksum of a byte stream (qd_checksum64_dev): stream word J (bytes 8J .. 8J+7, little
+// endian) weighs K(J) = mix64(J * GOLDEN + 1) | 1; the checksum is sum_J word_J * K(J) mod 2^64.  Linear in the data, so
+// pieces of a stream -- the chunks of an output ring, the shards of the GPUs of a box -- add up to the checksum of the
+// whole whatever their byte alignment.  HBM-bound read (8 B per mix64).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t checksum_weight(uint64_t word_index) {
+    return canon_mix64(word_index * 0x9e3779b97f4a7c15ull + 1ull) | 1ull;
+}
+
+struct ChecksumParams {
+    const uint8_t* buf;
+    uint64_t n;                  // bytes (ignored when n_dev is set)
+    const uint64_t* n_dev;       // optional: element count on the device ...
+    uint64_t n_scale;            // ... times bytes per element
+    uint64_t base;               // stream offset of buf[0]
+    unsigned long long* acc;     // *acc += checksum
+};
+
+constexpr int CHECKSUM_THREADS = 256;
+__global__ void __launch_bounds__(CHECKSUM_THREADS) checksum64_kernel(const ChecksumParams p) {
+    const uint64_t n = p.n_dev ? *p.n_dev * p.n_scale : p.n;
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.buf), hi = lo + n;
+    const uintptr_t b0 = min(hi, (lo + 15) & ~(uintptr_t)15), b1 = max(b0, hi & ~(uintptr_t)15);  // aligned body [b0, b1)
+    uint64_t sum = 0;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (uint64_t)gridDim.x * blockDim.x;
+    // head and tail bytes (fewer than 32 in all)
+    if (gtid < 32) {
+        const uint64_t n_head = b0 - lo, n_tail = hi - b1;
+        if (gtid < n_head + n_tail) {
+            const uintptr_t a = gtid < n_head ? lo + gtid : b1 + (gtid - n_head);
+            const uint64_t g = p.base + (a - lo);
+            sum += ((uint64_t)*reinterpret_cast<const uint8_t*>(a) << (8 * (g & 7))) * checksum_weight(g >> 3);
+        }
+    }
+    const uint64_t g0 = p.base + (b0 - lo);       // stream offset of the body
+    const uint32_t sh = (uint32_t)(g0 & 7) * 8u;  // the same for every body word
+    const uint64_t n_gran = (b1 - b0) >> 4;
+    const uint4* body = reinterpret_cast<const uint4*>(b0);
+    for (uint64_t c = gtid; c < n_gran; c += gsize) {
+        const uint4 v = ldg_stream(body + c);
+        const uint64_t w0 = (uint64_t)v.x | ((uint64_t)v.y << 32), w1 = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        const uint64_t J = (g0 >> 3) + 2 * c;
+        const uint64_t k0 = checksum_weight(J), k1 = checksum_weight(J + 1);
+        if (sh == 0) {
+            sum += w0 * k0 + w1 * k1;
+        } else {
+            const uint64_t k2 = checksum_weight(J + 2);
+            sum += (w0 << sh) * k0 + ((w0 >> (64 - sh)) | (w1 << sh)) * k1 + (w1 >> (64 - sh)) * k2;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ unsigned long long warp_sum[CHECKSUM_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int i = 0; i < CHECKSUM_THREADS / 32; i++) s += warp_sum[i];
+        if (s) atomicAdd(p.acc, s);
     }
 }
 
