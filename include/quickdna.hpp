@@ -344,9 +344,12 @@ class DnaSequence {
 // The reference's `NucleotideIter` extension trait composes adaptors over any nucleotide iterator; every use it has is
 // over a slice, so the mirror is a pair of O(1) views over a BORROWED span (no copies, no allocation per element):
 // `NucleotideView` (a strand: forward / reversed, plain / complemented) and `CodonsView` (one reading frame of it).
-// They are host-side by nature -- one element per call, exactly like the Rust iterators -- and exist for API parity;
-// anything that walks a whole sequence should call DnaSequence::translate / translate_*_frames / reverse_complement,
-// which are one kernel launch.  `to_fn` reads the same 27 x 4096-byte LUT image the device tables are built from.
+// One element per call they are host-side by nature, exactly like the Rust iterators.  What the reference's callers
+// DO with them is collect a whole frame -- `frame.map(table.to_fn()).collect()` (iter.rs:21-74, benches/all_windows.rs:
+// 113-149) -- and those bulk forms run on the device in ONE launch: CodonsView::translate, NucleotideView::
+// translate_all_frames / translate_self_frames, translate_codons (to_fn over a slice of codons), and
+// NucleotideView::collect_bulk for the reverse-complement strand.  `to_fn` itself reads the same 27 x 4096-byte LUT image
+// the device tables are built from.
 
 // N::Codon, src/nucleotide.rs:354, 396
 template <class T>
@@ -368,6 +371,14 @@ inline auto to_fn(TranslationTable table) {
 
 template <class T>
 class CodonsView;
+
+// `codons.iter().map(table.to_fn()).collect()` over a slice of codons (src/trans_table.rs:165-174 applied in bulk): a
+// Codon is three mask bytes, so the slice IS a mask sequence of 3 n nucleotides -- one qd_translate launch.
+template <class T>
+std::vector<uint8_t> translate_codons(TranslationTable table, const std::vector<Codon<T>>& codons) {
+    static_assert(sizeof(Codon<T>) == 3);
+    return translate_dna(table, reinterpret_cast<const T*>(codons.data()), 3 * codons.size());
+}
 
 template <class T>
 class NucleotideView {
@@ -421,13 +432,53 @@ class NucleotideView {
     std::vector<CodonsView<T>> self_reading_frames() const;
     // iter.rs:75-103: forward frames, then the frames of the reverse complement; empty ones dropped
     std::vector<CodonsView<T>> all_reading_frames() const;
+    // `.collect()`, one element at a time on the host like the Rust iterator
     std::vector<T> collect() const {
         std::vector<T> v(n_);
         for (size_t j = 0; j < n_; j++) v[j] = (*this)[j];
         return v;
     }
+    // `.collect()` in bulk: the reverse-complement strand of a span is ONE qd_revcomp launch (src/trans_table.rs:284-286);
+    // the forward strand is a copy; the two one-sided adaptors (reversed only / complemented only) have no bulk form
+    std::vector<T> collect_bulk() const {
+        if (rev_ && comp_) return quickdna::reverse_complement(p_, n_);
+        return collect();
+    }
+    // `self_reading_frames().map(|f| f.map(table.to_fn()).collect())` / the same for all_reading_frames (iter.rs:75-103,
+    // 221-236) in ONE launch (qd_translate_frames); empty frames are dropped like the iterators drop them.
+    std::vector<std::vector<uint8_t>> translate_self_frames(TranslationTable table) const { return bulk_frames(table, QD_FRAMES_SELF); }
+    std::vector<std::vector<uint8_t>> translate_all_frames(TranslationTable table) const { return bulk_frames(table, QD_FRAMES_ALL); }
+    bool is_forward() const { return !rev_ && !comp_; }
+    bool is_reverse_complement() const { return rev_ && comp_; }
+    const T* data() const { return p_; }
 
   private:
+    std::vector<std::vector<uint8_t>> bulk_frames(TranslationTable table, int which) const {
+        // the strand as a contiguous mask buffer: the span itself, or (rc / one-sided views) its collected form
+        std::vector<T> own;
+        const T* src = p_;
+        if (!is_forward()) {
+            own = collect_bulk();
+            src = own.data();
+        }
+        size_t cap = 0;
+        for (int k = 0; k < 3; k++) cap += qd_frame_len(n_, k);
+        std::vector<uint8_t> buf((which == QD_FRAMES_ALL ? 2 : 1) * cap + 1);
+        size_t lens[6] = {0, 0, 0, 0, 0, 0};
+        int n_frames = 0;
+        qd_err e{};
+        Context& c = Context::current();
+        c.check(qd_translate_frames(c.get(), static_cast<int>(table), QD_ENC_MASK, 0, which, reinterpret_cast<const uint8_t*>(src), n_, buf.data(), lens,
+                                    &n_frames, &e), e);
+        std::vector<std::vector<uint8_t>> res;
+        size_t off = 0;
+        for (size_t l : lens)
+            if (l) {
+                res.emplace_back(buf.begin() + off, buf.begin() + off + l);
+                off += l;
+            }
+        return res;
+    }
     const T* p_ = nullptr;
     size_t n_ = 0;
     bool rev_ = false, comp_ = false;
@@ -471,12 +522,20 @@ class CodonsView {
         for (size_t i = len(); i-- > 0;) r.push_back((*this)[i]);
         return r;
     }
-    // `.map(f).collect()`, e.g. f = to_fn(table)
+    // `.map(f).collect()`, e.g. f = to_fn(table): per element on the host, as the Rust iterator does
     template <class F>
     std::vector<uint8_t> map(F f) const {
         std::vector<uint8_t> r(len());
         for (size_t i = 0; i < len(); i++) r[i] = f((*this)[i]);
         return r;
+    }
+    // `.map(table.to_fn()).collect()` in bulk: the frame's nucleotides are contiguous masks (the forward strand in place,
+    // any other strand collected first -- the reverse complement by one qd_revcomp launch), so it is one qd_translate launch
+    std::vector<uint8_t> translate(TranslationTable table) const {
+        const size_t n = 3 * len();
+        if (v_.is_forward()) return translate_dna(table, v_.data() + 3 * front_, n);
+        const std::vector<T> strand = v_.collect_bulk();
+        return translate_dna(table, strand.data() + 3 * front_, n);
     }
 
   private:

@@ -1253,7 +1253,7 @@ static int checksum_dev(qd_ctx* c, const uint8_t* buf_dev, uint64_t n, const uin
     p.n_scale = n_scale;
     p.base = base;
     p.acc = reinterpret_cast<unsigned long long*>(acc_dev);
-    const uint64_t gran = (n >> 4) + 1;
+    const uint64_t gran = ((n_dev ? n * n_scale : n) >> 4) + 1;  // with a device-side count, `n` is the caller's bound on it (sizes the grid only)
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((gran + CHECKSUM_THREADS - 1) / CHECKSUM_THREADS, (uint64_t)c->sm_count * 8));
     checksum64_kernel<<<grid, CHECKSUM_THREADS, 0, s>>>(p);
     c->launches++;
@@ -1840,7 +1840,7 @@ extern "C" int qd_expansion_windows_chunked_dev(qd_ctx* c, int enc, const uint8_
         if (int rc = expansion_write_tiles_dev(c, p, out, (uint64_t)cnt * max_expansions, g.s)) return rc;
         QD_CUDA(c, cudaMemcpyAsync(chunk_rows_dev + k, c->aux2.as<uint64_t>() + cnt, 8, cudaMemcpyDeviceToDevice, g.s));
         if (checksums_dev)
-            if (int rc = checksum_dev(c, out, 0, chunk_rows_dev + k, w, 0, checksums_dev + k, g.s)) return rc;
+            if (int rc = checksum_dev(c, out, (uint64_t)cnt * max_expansions, chunk_rows_dev + k, w, 0, checksums_dev + k, g.s)) return rc;
         if (consume) consume(user, k, i0, cnt, out, (uint64_t)cnt * max_expansions * w, chunk_rows_dev + k, (void*)g.s);
     }
     return QD_OK;

@@ -35,3 +35,15 @@ def test_rust_api_mirror_on_gpu():
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_lazy_adaptor_bulk_forms_on_gpu():
+    """a11 / a24: `frame.map(table.to_fn()).collect()` of every reading frame, to_fn over a slice of codons and the
+    reverse-complement strand as ONE launch each, equal to the per-element host views."""
+    import __graft_entry__ as g
+
+    g.build()
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_iter_gpu")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout

@@ -180,3 +180,36 @@ def test_calls_restore_the_callers_device(torch, B, N):
     assert torch.empty(1, device="cuda").device.index == 0
     B.translate_frames_batch([b"ACGTAC"], ctx=ctx1)
     assert torch.cuda.current_device() == 0
+
+
+def test_import_name_drop_in():
+    """`from quickdna import DnaSequence` (quickdna/__init__.py:6 of the reference) binds this implementation."""
+    import quickdna
+    from quickdna import DnaSequence, ProteinSequence
+    from quickdna.quickdna import _check_table, _reverse_complement, _reverse_complement_strict, _translate, _translate_strict
+
+    import quickdna_b200
+
+    assert DnaSequence is quickdna_b200.DnaSequence and quickdna.ProteinSequence is quickdna_b200.ProteinSequence
+    assert DnaSequence("AAAGGGAAA").translate(table=1) == ProteinSequence("KGK")
+    assert _translate(1, b"AAAGGGAAA") == b"KGK" and _translate_strict(1, b"AAAGGGAAA") == b"KGK"
+    assert _reverse_complement(b"AAAAABCCC") == b"GGGVTTTTT"
+    with pytest.raises(ValueError):
+        _reverse_complement_strict(b"AAAAABCCC")
+    with pytest.raises(ValueError, match="not a ncbi translation table: 17"):
+        _check_table(17)
+
+
+def test_reference_wrapper_tests_run_unchanged_when_present():
+    """The reference's own tests/test_wrapper.py against the shim package (only where the reference checkout exists)."""
+    import os
+    import subprocess
+    import sys
+
+    ref = "/root/reference/tests/test_wrapper.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present (GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", "/tmp", "-c", "/dev/null", ref],
+                       env=dict(os.environ, PYTHONPATH=root), capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0, r.stdout[-3000:]
