@@ -101,6 +101,7 @@ struct qd_ctx {
     cudaStream_t dev_stream = nullptr;
     bool dev_pending = false;
     std::map<uint64_t, int> occ_cache;  // (kernel id, smem bytes) -> resident CTAs per SM, attribute already set
+    bool aligned_tiles = true;  // QD_ALIGNED_TILES=0 turns the whole-sequence tiles of the frame kernels off (A/B measurements)
     uint32_t ctile_wpt[2] = {448, 192};  // canonical tile kernel: windows per warp-tile for keys / rows (QD_CTILE_WPT_* read once)
 };
 
@@ -332,6 +333,13 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     const bool big = use_big_tiles(c, total_runs);
     const uint64_t tile_runs = big ? BIG_THREADS : SMALL_THREADS;
     p.n_tiles = (uint32_t)((total_runs + tile_runs - 1) / tile_runs);
+    // short sequences: tiles of WHOLE sequences when that idles at most 1/16 of a tile's threads (32-bit geometry, no quotient)
+    const uint64_t k = tile_runs / runs;
+    if (c->aligned_tiles && k >= 1 && k * runs * 16 >= tile_runs * 15 && n_seq <= 0xffffffffull) {
+        p.seqs_per_tile = (uint32_t)k;
+        p.tile_magic = (uint32_t)(((1u << 20) + runs - 1) / runs);
+        p.n_tiles = (uint32_t)((n_seq + k - 1) / k);
+    }
     p.out = out_dev;
     p.lut = c->d_lut + (size_t)slot * LUT_ENTRIES;
     set_encoding(c, p, enc, strict);
@@ -503,6 +511,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     c->sm_count = prop.multiProcessorCount;
     c->big_tile_min_runs = (uint64_t)2 * BIG_THREADS * (uint64_t)c->sm_count;  // every SM gets two big tiles
     // tuning knobs of the canonical tile kernel, read once per context (not on the launch path)
+    if (const char* e = getenv("QD_ALIGNED_TILES")) c->aligned_tiles = atoi(e) != 0;
     if (const char* e = getenv("QD_CTILE_WPT_KEYS")) c->ctile_wpt[0] = (uint32_t)std::max(64, atoi(e) & ~63);
     if (const char* e = getenv("QD_CTILE_WPT_ROWS")) c->ctile_wpt[1] = (uint32_t)std::max(64, atoi(e) & ~63);
     const HostTables& T = host_tables();

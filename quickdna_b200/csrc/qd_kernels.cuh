@@ -206,6 +206,11 @@ struct FramesParams {
     uint32_t uniform_runs;       // ceil(uniform_len / 48)
     uint32_t uniform_mod3;       // uniform_len % 3
     uint64_t total_runs;         // uniform mode; variable mode reads run_prefix[n_seq]
+    // uniform mode, short sequences: a tile is `seqs_per_tile` WHOLE sequences (0 = a tile is TILE_RUNS consecutive runs of
+    // the batch).  Thread t of a tile then owns run t % runs of the tile's sequence t / runs -- 32-bit arithmetic, no
+    // 64-bit quotient -- at the price of TILE_RUNS - seqs_per_tile * runs idle threads (1.6 % for 1000-nt reads).
+    uint32_t seqs_per_tile;
+    uint32_t tile_magic;         // ceil(2^20 / uniform_runs): t / runs == (t * tile_magic) >> 20 for t < 1024
     uint32_t n_tiles;            // upper bound on tiles (tiles past total_runs exit)
     uint8_t* out;                // slot layout, 16-byte aligned
     const uint16_t* lut;         // LUT_ENTRIES entries of the selected table, lut_index() layout
@@ -286,6 +291,7 @@ static_assert(offsetof(FramesSmem<SMALL_THREADS>, lut) == 0 && (2 * 14 + PAIR_FL
 template <int THREADS>
 __device__ __forceinline__ uint64_t tile_flat_start(const FramesParams& p, uint64_t t) {
     if (p.tiles) return p.tiles[t].flat;
+    if (p.seqs_per_tile) return min(p.total_nt, t * p.seqs_per_tile * p.uniform_len);
     const uint32_t g = (uint32_t)(t * TileGeom<THREADS>::RUNS);
     const uint32_t r = p.uniform_runs == 1 ? g : (uint32_t)__umul64hi((uint64_t)g, p.uniform_magic);
     return (uint64_t)r * p.uniform_len + (uint64_t)(g - r * p.uniform_runs) * RUN_NT;
@@ -299,7 +305,8 @@ __device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesPara
     constexpr int TILE_RUNS = TileGeom<THREADS>::RUNS;
     const uint64_t lo = tile_flat_start<THREADS>(p, t);
     uint64_t hi = p.total_nt;
-    if ((t + 1) * TILE_RUNS < total_runs) hi = min(p.total_nt, tile_flat_start<THREADS>(p, t + 1) + 2);  // 2-nt halo
+    if (p.seqs_per_tile ? (t + 1) * p.seqs_per_tile < p.n_seq : (t + 1) * TILE_RUNS < total_runs)
+        hi = min(p.total_nt, tile_flat_start<THREADS>(p, t + 1) + 2);  // 2-nt halo
     S.span[b][0] = lo;
     S.span[b][1] = hi;
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.total_nt;
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
     const int tid = threadIdx.x;
     const bool uniform = (p.offsets == nullptr);
     const uint64_t total_runs = uniform ? p.total_runs : p.run_prefix[p.n_seq];
-    const uint64_t n_tiles = min((uint64_t)p.n_tiles, (total_runs + TILE_RUNS - 1) / TILE_RUNS);
+    const uint64_t n_tiles = (uniform && p.seqs_per_tile) ? (uint64_t)p.n_tiles : min((uint64_t)p.n_tiles, (total_runs + TILE_RUNS - 1) / TILE_RUNS);
 
     // Per-CTA tables (persistent CTA: loaded once, reused for every tile) and the first two bulk copies.
     if (tid == 0) {
@@ -381,13 +388,29 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it % STAGES;
+        const bool aligned_tiles = uniform && p.seqs_per_tile != 0;
         const uint64_t g0 = tile * TILE_RUNS;
-        const uint32_t cnt = (uint32_t)min((uint64_t)TILE_RUNS, total_runs - g0);
+        const uint32_t cnt = aligned_tiles ? (uint32_t)min((uint64_t)p.seqs_per_tile, p.n_seq - tile * p.seqs_per_tile) * p.uniform_runs
+                                           : (uint32_t)min((uint64_t)TILE_RUNS, total_runs - g0);
 
         // ---- phase 0: which run is mine --------------------------------------------------------
         RunDesc rd;
         const bool active = tid < (int)cnt;
-        if (uniform) {
+        if (aligned_tiles) {
+            // whole sequences per tile: everything is 32-bit (sequences here are at most 1024 runs = 49 152 nt long)
+            const uint32_t t = active ? (uint32_t)tid : 0u;
+            const uint32_t rl = (t * p.tile_magic) >> 20;
+            const uint32_t r = (uint32_t)tile * p.seqs_per_tile + rl;  // < n_seq < 2^32
+            const uint32_t len = (uint32_t)p.uniform_len;
+            rd.m = t - rl * p.uniform_runs;
+            rd.runs = p.uniform_runs;
+            rd.mod3 = p.uniform_mod3;
+            rd.tiny = len < 3u;
+            const uint32_t in_seq = rd.m * RUN_NT;
+            rd.left_nt = len - in_seq;
+            rd.flat_start = (uint64_t)r * len + in_seq;
+            rd.out_base = (uint64_t)r * (p.uniform_runs * (16u * FRAMES));
+        } else if (uniform) {
             const uint32_t g = (uint32_t)g0 + (active ? tid : 0);
             const uint32_t r = p.uniform_runs == 1 ? g : (uint32_t)__umul64hi((uint64_t)g, p.uniform_magic);
             rd.m = g - r * p.uniform_runs;
@@ -480,7 +503,18 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
         const uintptr_t a0 = (dna_lo + S.span[buf][0]) & ~(uintptr_t)15;
         const uint32_t o = (uint32_t)(dna_lo + rd.flat_start - a0);  // local byte offset of the run
         uint32_t W[13];
-        {
+        if (__all_sync(0xffffffffu, (o & 7u) == 0u)) {
+            // every run of the warp starts on an 8-byte boundary of the staged tile (sequences whose length is a multiple of
+            // 8 in an 8-byte aligned buffer -- 1000-nt reads): seven 64-bit loads, no realignment
+            const uint32_t sa = smem_u32(S.raw[buf]) + o;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const uint2 v = lds_u64(sa + 8 * k);
+                W[2 * k] = v.x;
+                W[2 * k + 1] = v.y;
+            }
+            W[12] = lds_u32(sa + 48);
+        } else {
             const uint4* src = reinterpret_cast<const uint4*>(S.raw[buf] + (o & ~15u));
             const uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
             const uint32_t w[20] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y,
