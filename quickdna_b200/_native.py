@@ -12,7 +12,7 @@ import threading
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libquickdna_b200.so")
+LIB_PATH = os.environ.get("QUICKDNA_B200_LIB") or os.path.join(_HERE, "libquickdna_b200.so")  # the override is for A/B builds of the same ABI
 
 QD_OK = 0
 QD_ERR_NON_ASCII_BYTE = 1

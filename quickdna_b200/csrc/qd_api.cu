@@ -276,10 +276,12 @@ template <int FRAMES, int THREADS>
 int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_slot) {
     constexpr bool DIRECT = FRAMES == 1;  // the one-frame kernel looks codons up straight from the letters
     auto kern = translate_frames_kernel<FRAMES, THREADS, DIRECT>;
-    const size_t smem = DIRECT ? ((sizeof(FramesSmem<THREADS>) + 127) & ~(size_t)127) + DIRECT_ENTRIES : sizeof(FramesSmem<THREADS>);
+    using Smem = FramesSmem<THREADS, frames_stages(FRAMES)>;
+    const size_t smem = DIRECT ? ((sizeof(Smem) + 127) & ~(size_t)127) + DIRECT_ENTRIES : sizeof(Smem);
     if (c->occ_frames[occ_slot] == 0) {
         int occ = 0;
         QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (const char* e = getenv("QD_CARVEOUT")) QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
         c->occ_frames[occ_slot] = std::max(1, std::min(occ, TileGeom<THREADS>::CTAS_PER_SM));
     }
@@ -291,7 +293,10 @@ int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_sl
     return QD_OK;
 }
 
-// p.n_tiles must match the tile size: big -> BIG_THREADS runs per tile, else SMALL_THREADS
+// runs per tile of a launch = threads of its CTAs
+static uint64_t tile_runs_of(int /*frames*/, bool big) { return big ? TileGeom<BIG_THREADS>::RUNS : TileGeom<SMALL_THREADS>::RUNS; }
+
+// p.n_tiles must match the tile size (tile_runs_of)
 // (two 512-thread CTAs per SM were measured for variable-length batches too: no better than one 1024-thread CTA)
 int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s, bool big) {
     if (big) {
@@ -331,7 +336,7 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
     p.uniform_mod3 = (uint32_t)(seq_len % 3);
     p.total_runs = total_runs;
     const bool big = use_big_tiles(c, total_runs);
-    const uint64_t tile_runs = big ? BIG_THREADS : SMALL_THREADS;
+    const uint64_t tile_runs = tile_runs_of(frames, big);
     p.n_tiles = (uint32_t)((total_runs + tile_runs - 1) / tile_runs);
     // short sequences: tiles of WHOLE sequences when that idles at most 1/16 of a tile's threads (32-bit geometry, no quotient)
     const uint64_t k = tile_runs / runs;
@@ -375,7 +380,8 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     }
     // the exact run count is only known on the device; the tile size is picked from its upper bound
     const bool big = use_big_tiles(c, total_nt / RUN_NT);
-    const uint64_t tile_runs = big ? BIG_THREADS : SMALL_THREADS;
+    const uint64_t tile_runs = tile_runs_of(frames, big);
+    const uint32_t wq_stride = big ? TileGeom<BIG_THREADS>::WQ_STRIDE : TileGeom<SMALL_THREADS>::WQ_STRIDE;
     const size_t n_tiles = (size_t)((runs_upper_bound(total_nt, n_seq) + tile_runs - 1) / tile_runs);
     // The frame kernel bulk-copies windows of run_prefix / offsets (TMA: 16-byte aligned sources, reads up to a window
     // past the last entry), so both live in one own buffer: [run_prefix | pad of ~0][copy of the offsets | pad]
@@ -389,15 +395,15 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     QD_CUDA(c, cudaMemsetAsync(off_pad + n_seq + 1, 0xff, (arr_entries - n_seq - 1) * sizeof(uint64_t), s));
     // one buffer: the tile map, then the 32-run map (padded by one tile's worth of entries)
     const size_t warp_map_off = ((n_tiles + 1) * sizeof(TileInfo) + 127) & ~(size_t)127;
-    const uint64_t n_q = runs_upper_bound(total_nt, n_seq) / 32 + 1;
-    QD_CUDA(c, tile_first.reserve(warp_map_off + (n_q + BIG_THREADS / 32 + 8) * sizeof(uint32_t)));
+    const uint64_t n_q = (uint64_t)(n_tiles + 1) * wq_stride;  // a slice of wq_stride entries per tile
+    QD_CUDA(c, tile_first.reserve(warp_map_off + (n_q + 8) * sizeof(uint32_t)));
     int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, rp_dev, block_sums, s);
     if (rc) return rc;
     const unsigned g = (unsigned)std::min<uint64_t>((n_seq + 255) / 256, (uint64_t)c->sm_count * 8);
     tile_info_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), offsets_dev, flat_base, n_seq, tile_first.as<TileInfo>(), n_tiles, tile_runs);
     uint32_t* warp_first = reinterpret_cast<uint32_t*>(tile_first.as<uint8_t>() + warp_map_off);
     const unsigned gq = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_q + 255) / 256, (uint64_t)c->sm_count * 8));
-    warp_map_kernel<<<gq, 256, 0, s>>>(run_prefix.as<uint64_t>(), n_seq, tile_first.as<TileInfo>(), tile_runs, warp_first);
+    warp_map_kernel<<<gq, 256, 0, s>>>(run_prefix.as<uint64_t>(), n_seq, tile_first.as<TileInfo>(), tile_runs, wq_stride, warp_first);
     c->launches += 2;
     QD_CUDA(c, cudaGetLastError());
     FramesParams p{};

@@ -19,19 +19,40 @@ constexpr int RUN_NT = 48;        // nucleotides per run: 16 residues per frame 
 #ifndef QD_ST_HINT
 #define QD_ST_HINT 0  // 0: st.global.L1::no_allocate, 1: st.global.cs, 2: st.global
 #endif
-// A tile = one run per thread of the CTA.  Measured on B200 (tools/kbench.cu): for the 1 read : 2 write mix of the
-// six-frame kernel, ONE 1024-thread CTA per SM (48 KB contiguous in, 96 KB out per tile) reaches 5.75 TB/s where four
-// 256-thread CTAs per SM reach 5.05 TB/s; small inputs use the 256-thread form so they still spread over the SMs.
+// A tile = one run per thread of the CTA.  Two pipeline forms (frames_decoupled()):
+//   lockstep   one __syncthreads per tile; thread 0 refills the landing buffer behind it (six frames)
+//   decoupled  no CTA-wide barrier in the steady state: a warp that holds its bytes of a landing buffer in registers
+//              counts itself off on the buffer, and the LAST warp to do so issues the buffer's next bulk copy -- no
+//              dedicated producer, nobody waits on an "empty" barrier, warps drift apart (one and three frames; r01:
+//              with a __syncthreads per tile "barrier" was the top stall reason of those kernels)
+// Measured on B200 (tools/kbench.cu): for the 1 read : 2 write mix of the six-frame kernel, ONE 1024-thread CTA per SM
+// (48 KB contiguous in, 96 KB out per tile) reaches 5.75 TB/s where four 256-thread CTAs per SM reach 5.05 TB/s; small
+// inputs use the 256-thread form so they still spread over the SMs.
 constexpr int BIG_THREADS = 1024;
 constexpr int SMALL_THREADS = 256;
-constexpr int STAGES = 2;  // TMA landing buffers per CTA (3 and 4 measured no better)
-template <int THREADS>
+// TMA landing buffers per CTA (three measured no better once the refill left the critical path; the one-frame kernel's
+// 37 KB codon table leaves no room for a third anyway)
+#ifndef QD_FRAME_STAGES
+#define QD_FRAME_STAGES 2
+#endif
+__host__ __device__ constexpr int frames_stages(int /*frames*/) { return QD_FRAME_STAGES; }
+// Which pipeline form a frame count uses: all of them the decoupled one.  Measured on B200, 4 M x 1000-nt reads, fraction of
+// the 6548.5 GB/s copy peak, lockstep -> decoupled (tools/kbench.cu, also after other kernels / idle time in between):
+// one frame 0.79 -> 0.86, three frames 0.77 -> 0.80, six frames 0.90 -> 0.93.  -DQD_FRAMES_LOCKSTEP=1 builds the lockstep
+// form for A/B runs.
+#ifndef QD_FRAMES_LOCKSTEP
+#define QD_FRAMES_LOCKSTEP 0
+#endif
+__host__ __device__ constexpr bool frames_decoupled(int /*frames*/) { return !QD_FRAMES_LOCKSTEP; }
+template <int THREADS, bool SPEC = false>
 struct TileGeom {
-    static constexpr int RUNS = THREADS;                           // runs per tile
+    static constexpr int RUNS = THREADS;                           // runs per tile: one per thread
+    static constexpr int WQ = RUNS / 32;                           // consumer warps
+    static constexpr int WQ_STRIDE = ((THREADS / 32) + 3) & ~3;    // entries of the 32-run map per tile (16-byte aligned slices)
     static constexpr int MAX_BYTES = RUNS * RUN_NT + 2 + 15 + 15;  // span + halo + alignment slack
     static constexpr int MAX_CHUNKS = (MAX_BYTES + 15) / 16 + 1;
     static constexpr int RAW_BYTES = MAX_CHUNKS * 16 + 64;         // one staged tile (+ slack: a run reads 80 B)
-    static constexpr int SEARCH_CAP = THREADS;                     // sequences of one tile whose geometry is cached in smem
+    static constexpr int SEARCH_CAP = RUNS;                        // sequences of one tile whose geometry is cached in smem
     static constexpr int CTAS_PER_SM = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 4);
 };
 
@@ -136,7 +157,38 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef QD_WAIT_MODE
+#define QD_WAIT_MODE 0  // 0: try_wait in a tight loop; 1: nanosleep back-off between polls; 2: try_wait with a suspend-time hint
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if QD_WAIT_MODE == 1
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+#elif QD_WAIT_MODE == 2
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -148,6 +200,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile(
@@ -225,6 +278,7 @@ struct FramesParams {
     uint64_t flat_base;          // value of offsets[] that corresponds to dna[0] (CSR chunks)
     uint64_t key_base;           // added to a flat offset to form the error key (chunked host calls)
     int strict;
+    unsigned long long* trace;   // diagnostics (tools/kbench.cu): per CTA 8 words {start ns, end ns, SM id, tiles done, producer wait-empty ns, stage ns, warp 0 / warp 16 wait-full ns}, or nullptr
 };
 
 struct RunDesc {
@@ -268,31 +322,47 @@ __device__ __noinline__ void exact_check_run(const uint8_t* __restrict__ run_byt
 
 // Shared memory of one CTA.  raw[] is the TMA landing zone: while tile T is translated, the bytes of the CTA's next
 // tiles stream into the other buffer (cp.async.bulk + mbarrier), so DRAM latency hides behind arithmetic.
-template <int THREADS>
+// what the next bulk copies into a landing buffer are (plan_tile / issue_tile)
+struct TilePlan {
+    uint64_t lo, hi;      // flat [start, end) of the tile's input span, 2-nt halo included
+    uint64_t tile;
+    uint32_t first_seq;   // variable-length batches: the tile's first sequence
+    uint32_t pad_;
+};
+
+template <int THREADS, int STAGES>
 struct FramesSmem {
     alignas(16) uint16_t lut[LUT_ENTRIES];   // codon -> (forward aa, reverse aa)
     alignas(16) uint16_t pair[PAIR_ENTRIES]; // letter pair -> two doubled codes
     alignas(16) uint4 lowmask[17];           // lowmask[k]: the first k bytes of a 16-byte vector are 0xff
     alignas(128) uint8_t raw[STAGES][TileGeom<THREADS>::RAW_BYTES];  // multi-buffered raw input of a tile, 2-nt halo included
     alignas(8) uint64_t full[STAGES];             // mbarriers: raw[b] has landed
+    uint32_t released[STAGES];                    // decoupled form: warps that hold their bytes of raw[b] in registers
+    alignas(16) TilePlan plan[STAGES];            // the refill of raw[b], planned by the first warp to release it
     uint64_t span[STAGES][2];                     // flat [start, end) of the input span staged in raw[b]
     // variable-length batches: run prefix and CSR offsets of the sequences a tile touches and the per-warp sequence map,
     // bulk-copied together with the tile's bytes (same mbarrier), so no dependent global load sits between two tiles
-    alignas(16) uint64_t rp_cache[2][TileGeom<THREADS>::SEARCH_CAP + 6];
-    alignas(16) uint64_t off_cache[2][TileGeom<THREADS>::SEARCH_CAP + 6];
-    alignas(16) uint32_t warp_first[2][THREADS / 32];
-    uint32_t first_seq[2];  // first sequence of the tile staged in buffer b
+    alignas(16) uint64_t rp_cache[STAGES][TileGeom<THREADS>::SEARCH_CAP + 6];
+    alignas(16) uint64_t off_cache[STAGES][TileGeom<THREADS>::SEARCH_CAP + 6];
+    alignas(16) uint32_t warp_first[STAGES][TileGeom<THREADS>::WQ_STRIDE];
+    uint32_t first_seq[STAGES];  // first sequence of the tile staged in buffer b
+    // The kernel parameters once more, for the (not inlined) staging function: handing it the __grid_constant__ struct by
+    // reference made every thread keep a 200-byte copy in LOCAL memory, and the staging thread read its fields back with a
+    // chain of local loads per tile -- L2 or DRAM round trips on the critical path of the TMA pipeline (ncu: the consumers
+    // starved on the full barriers, DRAM at 29 %; how bad depended on what L2 happened to hold).
+    alignas(16) FramesParams params;
 };
 
-static_assert(offsetof(FramesSmem<SMALL_THREADS>, lut) == 0 && (2 * 14 + PAIR_FLAG) * (1 + LUT_K1 + LUT_K2) + 2 <= sizeof(FramesSmem<SMALL_THREADS>),
+using FramesSmemSmallest = FramesSmem<SMALL_THREADS, 2>;
+static_assert(offsetof(FramesSmemSmallest, lut) == 0 && (2 * 14 + PAIR_FLAG) * (1 + LUT_K1 + LUT_K2) + 2 <= sizeof(FramesSmemSmallest),
               "a flagged codon must still address shared memory of this CTA");
 
 // flat offset of the first run of tile t (t * RUNS < total_runs)
-template <int THREADS>
+template <int THREADS, bool SPEC>
 __device__ __forceinline__ uint64_t tile_flat_start(const FramesParams& p, uint64_t t) {
     if (p.tiles) return p.tiles[t].flat;
     if (p.seqs_per_tile) return min(p.total_nt, t * p.seqs_per_tile * p.uniform_len);
-    const uint32_t g = (uint32_t)(t * TileGeom<THREADS>::RUNS);
+    const uint32_t g = (uint32_t)(t * TileGeom<THREADS, SPEC>::RUNS);
     const uint32_t r = p.uniform_runs == 1 ? g : (uint32_t)__umul64hi((uint64_t)g, p.uniform_magic);
     return (uint64_t)r * p.uniform_len + (uint64_t)(g - r * p.uniform_runs) * RUN_NT;
 }
@@ -300,13 +370,27 @@ __device__ __forceinline__ uint64_t tile_flat_start(const FramesParams& p, uint6
 // One thread: publish the span of tile t in S.span[b] and start its bulk copy into S.raw[b].
 // Whole 16-byte granules inside [dna, dna + total) are copied by TMA; the (at most two) granules that straddle the
 // ends of the whole buffer are copied byte-wise by this thread, so nothing outside the buffer is ever read.
-template <int THREADS>
-__device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesParams& p, uint64_t t, uint64_t total_runs, int b) {
-    constexpr int TILE_RUNS = TileGeom<THREADS>::RUNS;
-    const uint64_t lo = tile_flat_start<THREADS>(p, t);
+// Staging a tile has two halves.  plan_tile works out WHAT to copy (a 64-bit quotient or, for variable-length batches,
+// dependent global loads): anybody may do it at any time, it touches only S.plan[b].  issue_tile starts the copies
+// described by S.plan[b] into landing buffer b: a handful of instructions, to be run once the buffer is free.
+template <int THREADS, bool SPEC, int STAGES>
+__device__ __noinline__ void plan_tile(FramesSmem<THREADS, STAGES>& S, const FramesParams& p, uint64_t t, uint64_t total_runs, int b) {
+    constexpr int TILE_RUNS = TileGeom<THREADS, SPEC>::RUNS;
+    const uint64_t lo = tile_flat_start<THREADS, SPEC>(p, t);
     uint64_t hi = p.total_nt;
     if (p.seqs_per_tile ? (t + 1) * p.seqs_per_tile < p.n_seq : (t + 1) * TILE_RUNS < total_runs)
-        hi = min(p.total_nt, tile_flat_start<THREADS>(p, t + 1) + 2);  // 2-nt halo
+        hi = min(p.total_nt, tile_flat_start<THREADS, SPEC>(p, t + 1) + 2);  // 2-nt halo
+    TilePlan& P = S.plan[b];
+    P.lo = lo;
+    P.hi = hi;
+    P.tile = t;
+    P.first_seq = p.tiles ? p.tiles[t].first_seq : 0u;
+}
+
+template <int THREADS, bool SPEC, int STAGES>
+__device__ __forceinline__ void issue_tile(FramesSmem<THREADS, STAGES>& S, const FramesParams& p, int b) {
+    const TilePlan P = S.plan[b];
+    const uint64_t lo = P.lo, hi = P.hi;
     S.span[b][0] = lo;
     S.span[b][1] = hi;
     const uintptr_t dna_lo = reinterpret_cast<uintptr_t>(p.dna), dna_hi = dna_lo + p.total_nt;
@@ -314,7 +398,7 @@ __device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesPara
     const uintptr_t a1 = (dna_lo + hi + 15) & ~(uintptr_t)15;
     const uintptr_t t0 = max(a0, (dna_lo + 15) & ~(uintptr_t)15);
     const uintptr_t t1 = min(a1, dna_hi & ~(uintptr_t)15);
-    if (a0 < t0 || t1 < a1) {  // edge granules of the whole buffer
+    if (a0 < t0 || t1 < a1) {  // edge granules of the whole buffer (the first and the last tile of a launch only)
 #pragma unroll 1
         for (uintptr_t a = a0; a < min(t0, a1); a++) S.raw[b][a - a0] = (a >= dna_lo && a < dna_hi) ? *reinterpret_cast<const uint8_t*>(a) : (uint8_t)0;
 #pragma unroll 1
@@ -326,13 +410,14 @@ __device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesPara
         // keeps 16-byte aligned, ~0-padded copies of both arrays, so an even index is an aligned source) and the tile's
         // slice of the 32-run sequence map
         constexpr uint32_t CAP = TileGeom<THREADS>::SEARCH_CAP;
-        const uint32_t r_first = p.tiles[t].first_seq, rs = r_first & 1u;
-        constexpr uint32_t WIN_BYTES = (CAP + 4) * 8, MAP_BYTES = (THREADS / 32) * 4;
+        const uint32_t r_first = P.first_seq, rs = r_first & 1u;
+        constexpr uint32_t WIN_BYTES = (CAP + 4) * 8, MAP_BYTES = TileGeom<THREADS>::WQ_STRIDE * 4;
+        static_assert(WIN_BYTES % 16 == 0 && MAP_BYTES % 16 == 0, "bulk copies move whole 16-byte granules");
         S.first_seq[b] = r_first;
         mbar_expect_tx(&S.full[b], bytes + 2 * WIN_BYTES + MAP_BYTES);  // release: plain stores above are visible with the phase
         tma_bulk_g2s(S.rp_cache[b], p.run_prefix + (r_first - rs), WIN_BYTES, &S.full[b]);
         tma_bulk_g2s(S.off_cache[b], p.offsets + (r_first - rs), WIN_BYTES, &S.full[b]);
-        tma_bulk_g2s(S.warp_first[b], p.warp_first + t * (THREADS / 32), MAP_BYTES, &S.full[b]);
+        tma_bulk_g2s(S.warp_first[b], p.warp_first + P.tile * TileGeom<THREADS>::WQ_STRIDE, MAP_BYTES, &S.full[b]);
         if (bytes) tma_bulk_g2s(S.raw[b] + (t0 - a0), reinterpret_cast<const void*>(t0), bytes, &S.full[b]);
     } else if (bytes) {
         mbar_expect_tx(&S.full[b], bytes);  // release: the byte stores above are visible to whoever observes the phase
@@ -342,24 +427,47 @@ __device__ __noinline__ void stage_tile(FramesSmem<THREADS>& S, const FramesPara
     }
 }
 
+template <int THREADS, bool SPEC, int STAGES>
+__device__ __forceinline__ void stage_tile(FramesSmem<THREADS, STAGES>& S, const FramesParams& p, uint64_t t, uint64_t total_runs, int b) {
+    plan_tile<THREADS, SPEC, STAGES>(S, p, t, total_runs, b);
+    issue_tile<THREADS, SPEC, STAGES>(S, p, b);
+}
+
 template <int FRAMES, int THREADS, bool DIRECT = false>
 __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) translate_frames_kernel(const FramesParams p) {
     static_assert(!DIRECT || FRAMES == 1, "the direct codon table serves the one-frame kernel only");
-    constexpr int TILE_THREADS = THREADS, TILE_RUNS = TileGeom<THREADS>::RUNS, SEARCH_CAP = TileGeom<THREADS>::SEARCH_CAP;
-    extern __shared__ __align__(128) unsigned char frames_smem_raw[];  // sizeof(FramesSmem<THREADS>) dynamic bytes
-    FramesSmem<THREADS>& S = *reinterpret_cast<FramesSmem<THREADS>*>(frames_smem_raw);
-    uint8_t* const direct_s = frames_smem_raw + ((sizeof(FramesSmem<THREADS>) + 127) & ~(size_t)127);  // DIRECT only
+    constexpr bool SPEC = frames_decoupled(FRAMES);
+    constexpr int STAGES = frames_stages(FRAMES);
+    constexpr int TILE_THREADS = THREADS, TILE_RUNS = TileGeom<THREADS, SPEC>::RUNS, SEARCH_CAP = TileGeom<THREADS>::SEARCH_CAP;
+    extern __shared__ __align__(128) unsigned char frames_smem_raw[];  // sizeof(FramesSmem<THREADS, STAGES>) dynamic bytes
+    using Smem = FramesSmem<THREADS, frames_stages(FRAMES)>;
+    Smem& S = *reinterpret_cast<Smem*>(frames_smem_raw);
+    uint8_t* const direct_s = frames_smem_raw + ((sizeof(Smem) + 127) & ~(size_t)127);  // DIRECT only
     const int tid = threadIdx.x;
     const bool uniform = (p.offsets == nullptr);
+    if (p.trace && tid == 0) {
+        unsigned long long t0;
+        uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[8 * blockIdx.x] = t0;
+        p.trace[8 * blockIdx.x + 2] = smid;
+    }
     const uint64_t total_runs = uniform ? p.total_runs : p.run_prefix[p.n_seq];
     const uint64_t n_tiles = (uniform && p.seqs_per_tile) ? (uint64_t)p.n_tiles : min((uint64_t)p.n_tiles, (total_runs + TILE_RUNS - 1) / TILE_RUNS);
 
-    // Per-CTA tables (persistent CTA: loaded once, reused for every tile) and the first two bulk copies.
+    // Per-CTA tables (persistent CTA: loaded once, reused for every tile)
     if (tid == 0) {
-        for (int b = 0; b < STAGES; b++) mbar_init(&S.full[b], 1);
+        S.params = p;
+        for (int b = 0; b < STAGES; b++) {
+            mbar_init(&S.full[b], 1);
+            S.released[b] = 0;
+        }
         fence_barrier_init();
-        for (int b = 0; b < STAGES; b++)
-            if (blockIdx.x + b * (uint64_t)gridDim.x < n_tiles) stage_tile(S, p, blockIdx.x + b * (uint64_t)gridDim.x, total_runs, b);
+        {   // the first STAGES tiles
+            for (int b = 0; b < STAGES; b++)
+                if (blockIdx.x + b * (uint64_t)gridDim.x < n_tiles) stage_tile<THREADS, SPEC, STAGES>(S, S.params, blockIdx.x + b * (uint64_t)gridDim.x, total_runs, b);
+        }
     }
     if (DIRECT) {
         const uint4* src = reinterpret_cast<const uint4*>(p.direct);
@@ -383,7 +491,7 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
     const uint32_t lut_base = smem_u32(S.lut);
     const uint32_t pair_base = smem_u32(S.pair);
     const uint32_t pair_coef = p.pair_coef;
-    __syncthreads();
+    __syncthreads();  // the only CTA-wide barrier
 
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -499,7 +607,15 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
         }
 
         // ---- phase 1: my run's 52 raw bytes, from the staged tile into registers ------------------
+#ifdef QD_TRACE_DETAIL
+        unsigned long long tw0, tw1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
+#endif
         mbar_wait(&S.full[buf], (it / STAGES) & 1);
+#ifdef QD_TRACE_DETAIL
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
+        if (p.trace && (tid == 0 || tid == 512)) atomicAdd(&p.trace[8 * blockIdx.x + (tid ? 7 : 6)], tw1 - tw0);
+#endif
         const uintptr_t a0 = (dna_lo + S.span[buf][0]) & ~(uintptr_t)15;
         const uint32_t o = (uint32_t)(dna_lo + rd.flat_start - a0);  // local byte offset of the run
         uint32_t W[13];
@@ -539,8 +655,28 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
                     break;
             }
         }
-        __syncthreads();  // every thread holds its bytes: raw[buf] can be refilled
-        if (tid == 0 && tile + STAGES * (uint64_t)gridDim.x < n_tiles) stage_tile(S, p, tile + STAGES * (uint64_t)gridDim.x, total_runs, buf);
+        if (SPEC) {
+            // every lane holds its bytes (and is done with the tile's geometry windows): the warp counts itself off on raw[buf].
+            // A warp that finds the count still at zero PLANS the buffer's refill before it counts itself off (it is ahead of
+            // the others: the planning -- a 64-bit quotient, or dependent global loads for variable-length batches -- costs
+            // nobody anything; several early warps may plan, they write the same values); the LAST warp to count itself off
+            // knows the buffer is free and only has to issue the planned copies.  Release / acquire runs through the counter.
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                const uint64_t next = tile + STAGES * (uint64_t)gridDim.x;
+                if (next < n_tiles && *reinterpret_cast<volatile uint32_t*>(&S.released[buf]) == 0u)
+                    plan_tile<THREADS, SPEC, STAGES>(S, S.params, next, total_runs, buf);
+                uint32_t before;
+                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(before) : "r"(smem_u32(&S.released[buf])) : "memory");
+                if (before == (uint32_t)(THREADS / 32 - 1)) {
+                    S.released[buf] = 0;  // published with the refill's mbarrier phase
+                    if (next < n_tiles) issue_tile<THREADS, SPEC, STAGES>(S, S.params, buf);
+                }
+            }
+        } else {
+            __syncthreads();  // every thread holds its bytes: raw[buf] can be refilled
+            if (tid == 0 && tile + STAGES * (uint64_t)gridDim.x < n_tiles) stage_tile<THREADS, SPEC, STAGES>(S, S.params, tile + STAGES * (uint64_t)gridDim.x, total_runs, buf);
+        }
 
         // ---- phase 2: one run per thread: 48 codon starts -> 16 residues per frame per strand -----
         if (DIRECT && active) {
@@ -664,6 +800,12 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
             }
         }
     }
+    if (p.trace && tid == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        p.trace[8 * blockIdx.x + 1] = t1;
+        p.trace[8 * blockIdx.x + 3] = it;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -693,6 +835,7 @@ struct RevcompParams {
 #define QD_RC_TMA_STORE 0  // 1: stage a tile's output in shared memory and write it with one cp.async.bulk
 #endif
 constexpr int RC_BIG_THREADS = QD_RC_THREADS, RC_SMALL_THREADS = 256;
+constexpr int RC_STAGES = 2;  // TMA landing buffers of the reverse-complement kernel
 constexpr int RC_UNROLL = QD_RC_UNROLL;  // 16-byte output granules per thread and tile
 constexpr uint32_t RC_INVALID = 0x80;    // complement-table flag (outputs are ASCII letters or masks: bit 7 is free)
 
@@ -701,11 +844,12 @@ struct RevcompSmem {
     static constexpr int TILE_CHUNKS = THREADS * RC_UNROLL;        // 16-byte output granules per tile
     static constexpr int RAW_BYTES = (TILE_CHUNKS + 1) * 16;       // + one granule for the source misalignment
     alignas(16) uint16_t pair[PAIR_ENTRIES];
-    alignas(128) uint8_t raw[STAGES][RAW_BYTES];  // source bytes of a tile (TMA landing zone)
+    alignas(128) uint8_t raw[RC_STAGES][RAW_BYTES];  // source bytes of a tile (TMA landing zone)
 #if QD_RC_TMA_STORE
     alignas(128) uint8_t outb[2][TILE_CHUNKS * 16];  // a tile's output, drained by one bulk store
 #endif
-    alignas(8) uint64_t full[STAGES];
+    alignas(8) uint64_t full[RC_STAGES];
+    alignas(16) RevcompParams params;  // for the staging function (see FramesSmem::params)
 };
 
 // Tile t produces output granules [t*TILE_CHUNKS, ...): out[16j, 16j+16) = in[n-16j-16, n-16j) reversed and
@@ -757,10 +901,11 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 4) revcomp_kern
     const uint64_t full = n >> 4;  // full 16-byte output granules
     const uint64_t n_tiles = (full + TILE_CHUNKS - 1) / TILE_CHUNKS;
     if (tid == 0) {
-        for (int b = 0; b < STAGES; b++) mbar_init(&S.full[b], 1);
+        S.params = p;
+        for (int b = 0; b < RC_STAGES; b++) mbar_init(&S.full[b], 1);
         fence_barrier_init();
-        for (int b = 0; b < STAGES; b++)
-            if (blockIdx.x + b * (uint64_t)gridDim.x < n_tiles) rc_stage_tile(S, p, blockIdx.x + b * (uint64_t)gridDim.x, full, b);
+        for (int b = 0; b < RC_STAGES; b++)
+            if (blockIdx.x + b * (uint64_t)gridDim.x < n_tiles) rc_stage_tile(S, S.params, blockIdx.x + b * (uint64_t)gridDim.x, full, b);
     }
     {
         const uint4* psrc = reinterpret_cast<const uint4*>(p.pair);
@@ -775,10 +920,10 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 4) revcomp_kern
 
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it % STAGES;
+        const int buf = it % RC_STAGES;
         const uint64_t j0 = tile * TILE_CHUNKS;
         const uint32_t cnt = (uint32_t)min((uint64_t)TILE_CHUNKS, full - j0);
-        mbar_wait(&S.full[buf], (it / STAGES) & 1);
+        mbar_wait(&S.full[buf], (it / RC_STAGES) & 1);
         // ---- my granules' 16 source bytes each, into registers ----------------------------------------
         uint32_t x[RC_UNROLL][4];
 #pragma unroll
@@ -813,7 +958,7 @@ __global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 4) revcomp_kern
             }
         }
         __syncthreads();  // every thread holds its bytes: raw[buf] can be refilled
-        if (tid == 0 && tile + STAGES * (uint64_t)gridDim.x < n_tiles) rc_stage_tile(S, p, tile + STAGES * (uint64_t)gridDim.x, full, buf);
+        if (tid == 0 && tile + RC_STAGES * (uint64_t)gridDim.x < n_tiles) rc_stage_tile(S, S.params, tile + RC_STAGES * (uint64_t)gridDim.x, full, buf);
         // ---- complement + reverse + validate + store ----------------------------------------------------
 #pragma unroll
         for (int u = 0; u < RC_UNROLL; u++) {
@@ -2064,16 +2209,20 @@ __global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t* __restri
 // warp_first[q] = the sequence that holds run 32 q (largest r with run_prefix[r] <= 32 q), searched between the first
 // sequences of the enclosing tile and of the next one
 __global__ void __launch_bounds__(256) warp_map_kernel(const uint64_t* __restrict__ run_prefix, uint64_t n_seq, const TileInfo* __restrict__ tiles,
-                                                       uint64_t tile_runs, uint32_t* __restrict__ warp_first) {
-    const uint64_t total_runs = run_prefix[n_seq];
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 32 < total_runs; q += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t g = q * 32, t = g / tile_runs;
+                                                       uint64_t tile_runs, uint32_t wq_stride, uint32_t* __restrict__ warp_first) {
+    // slot t * wq_stride + j = the sequence holding run t * tile_runs + 32 j (tile_runs is a multiple of 32; wq_stride >=
+    // tile_runs / 32 is a multiple of 4 so that a tile's slice is a 16-byte aligned bulk-copy source)
+    const uint64_t total_runs = run_prefix[n_seq], wq = tile_runs / 32;
+    const uint64_t n_slots = ((total_runs + tile_runs - 1) / tile_runs) * wq;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_slots; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = q / wq, j = q - t * wq, g = t * tile_runs + 32 * j;
+        if (g >= total_runs) continue;
         uint64_t lo = tiles[t].first_seq, hi = ((t + 1) * tile_runs < total_runs) ? tiles[t + 1].first_seq : n_seq - 1;
         while (lo < hi) {
             const uint64_t mid = (lo + hi + 1) >> 1;
             if (run_prefix[mid] <= g) lo = mid; else hi = mid - 1;
         }
-        warp_first[q] = (uint32_t)lo;
+        warp_first[t * wq_stride + j] = (uint32_t)lo;
     }
 }
 

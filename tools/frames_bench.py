@@ -26,6 +26,9 @@ for L in lens:
     out = torch.empty(n * 16 * B.runs(L) * 6, dtype=torch.uint8, device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     variants = [("1 frame", dict(frames=1)), ("3 frames", dict(frames=3)), ("6 frames", dict(frames=6)), ("6 strict", dict(frames=6, strict=True))]
+    order = os.environ.get("QD_BENCH_ORDER")  # e.g. "2,1,0,3": which variants, in which order
+    if order:
+        variants = [variants[int(i)] for i in order.split(",")]
     for name, kw in variants:
         f = kw["frames"]
         algo = n * (L + (2 if f == 6 else 1) * sum((L - k) // 3 for k in range(1 if f == 1 else 3)))

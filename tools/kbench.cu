@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
+#include <algorithm>
+#include <vector>
 
 #include "../quickdna_b200/csrc/qd_kernels.cuh"
 #include "../quickdna_b200/csrc/qd_tables.hpp"
@@ -77,7 +80,7 @@ int main(int argc, char** argv) {
 #ifndef KB_FRAMES
 #define KB_FRAMES 6
 #endif
-    constexpr int TILE_THREADS = KB_THREADS, TILE_RUNS = KB_THREADS;
+    constexpr int TILE_THREADS = KB_THREADS, TILE_RUNS = TileGeom<KB_THREADS, frames_decoupled(KB_FRAMES)>::RUNS;
     constexpr bool KB_DIRECT = KB_FRAMES == 1;
     if (KB_DIRECT) {
         std::vector<uint8_t> host;
@@ -90,6 +93,13 @@ int main(int argc, char** argv) {
         p.direct_k2 = DIRECT_K2_ASCII;
     }
     p.n_tiles = (uint32_t)((p.total_runs + TILE_RUNS - 1) / TILE_RUNS);
+#ifndef KB_NO_ALIGNED_TILES
+    if (TILE_RUNS / runs >= 1 && (TILE_RUNS / runs) * runs * 16 >= (size_t)TILE_RUNS * 15) {  // whole sequences per tile, as frames_uniform_dev does
+        p.seqs_per_tile = (uint32_t)(TILE_RUNS / runs);
+        p.tile_magic = (uint32_t)(((1u << 20) + runs - 1) / runs);
+        p.n_tiles = (uint32_t)((n_reads + p.seqs_per_tile - 1) / p.seqs_per_tile);
+    }
+#endif
     p.out = out;
     p.lut = d_lut;
     p.decode = d_decode;
@@ -99,13 +109,18 @@ int main(int argc, char** argv) {
     p.or_forbid = 0x80808080u;
     p.err_key = d_err;
     int occ = 0;
-    const size_t smem = KB_DIRECT ? ((sizeof(FramesSmem<KB_THREADS>) + 127) & ~(size_t)127) + DIRECT_ENTRIES : sizeof(FramesSmem<KB_THREADS>);
+    using Smem = FramesSmem<KB_THREADS, frames_stages(KB_FRAMES)>;
+    const size_t smem = KB_DIRECT ? ((sizeof(Smem) + 127) & ~(size_t)127) + DIRECT_ENTRIES : sizeof(Smem);
     CK(cudaFuncSetAttribute(translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT>, TILE_THREADS, smem));
 #ifdef KB_OCC
     occ = KB_OCC;
 #endif
+#ifdef KB_GRID
+    const unsigned grid = KB_GRID;
+#else
     const unsigned grid = (unsigned)(sms * occ);
+#endif
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -118,6 +133,59 @@ int main(int argc, char** argv) {
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= reps;
+    if (getenv("KB_DISTURB")) {
+        // what does the kernel do after the GPU has idled / run something else?  per-CTA start, end and SM of one launch each
+        unsigned long long* d_trace;
+        CK(cudaMalloc(&d_trace, grid * 64));
+        std::vector<unsigned long long> h(grid * 8);
+        auto traced = [&](const char* label) {
+            p.trace = d_trace;
+            CK(cudaMemset(d_trace, 0, grid * 64));
+            CK(cudaEventRecord(e0));
+            translate_frames_kernel<KB_FRAMES, KB_THREADS, KB_DIRECT><<<grid, TILE_THREADS, smem>>>(p);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float t;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            CK(cudaMemcpy(h.data(), d_trace, grid * 64, cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull, t1 = 0, late = 0, dur_min = ~0ull, dur_max = 0;
+            std::vector<int> per_sm(256, 0);
+            for (unsigned b = 0; b < grid; b++) t0 = std::min(t0, h[8 * b]);
+            for (unsigned b = 0; b < grid; b++) {
+                t1 = std::max(t1, h[8 * b + 1]);
+                late += h[8 * b] - t0 > 100000;  // started more than 100 us after the first CTA
+                dur_min = std::min(dur_min, h[8 * b + 1] - h[8 * b]);
+                dur_max = std::max(dur_max, h[8 * b + 1] - h[8 * b]);
+                per_sm[h[8 * b + 2] & 255]++;
+            }
+            int sms_used = 0, max_per_sm = 0;
+            for (int v : per_sm) sms_used += v > 0, max_per_sm = std::max(max_per_sm, v);
+            printf("  %-28s %.3f ms  span %.3f ms  CTA time %.3f..%.3f ms  CTAs started late %llu  SMs used %d  max CTAs on one SM %d\n", label, t,
+                   (t1 - t0) * 1e-6, dur_min * 1e-6, dur_max * 1e-6, late, sms_used, max_per_sm);
+#ifdef QD_TRACE_DETAIL
+            for (unsigned b : {0u, 1u, 2u, 3u})
+                printf("    block %u sm %llu: %.3f ms, producer waited for empty %.3f ms, staging %.3f ms; consumer warp 0 waited for full %.3f ms, warp 16 %.3f ms\n", b,
+                       h[8 * b + 2], (h[8 * b + 1] - h[8 * b]) * 1e-6, h[8 * b + 4] * 1e-6, h[8 * b + 5] * 1e-6, h[8 * b + 6] * 1e-6, h[8 * b + 7] * 1e-6);
+#endif
+            if (getenv("KB_DISTURB_DETAIL") && dur_max > 1.5 * dur_min) {
+                printf("    slow CTAs (block:sm:ms):");
+                for (unsigned b = 0; b < grid; b++)
+                    if (h[8 * b + 1] - h[8 * b] > 1.3 * dur_min) printf(" %u:%llu:%.2f", b, h[8 * b + 2], (h[8 * b + 1] - h[8 * b]) * 1e-6);
+                printf("\n");
+            }
+            p.trace = nullptr;
+        };
+        traced("back to back");
+        traced("again");
+        usleep(500000);
+        traced("after 0.5 s idle");
+        traced("again");
+        void* big;
+        CK(cudaMalloc(&big, size_t(1) << 30));
+        CK(cudaMemset(big, 1, size_t(1) << 30));
+        traced("after cudaMemset 1 GB");
+        traced("again");
+    }
     size_t algo = L;
     for (int k = 0; k < (KB_FRAMES == 1 ? 1 : 3); k++) algo += (KB_FRAMES == 6 ? 2 : 1) * ((L - k) / 3);
     xorsum_kernel<<<sms * 8, 256>>>((const uint32_t*)out, out_bytes / 4, d_acc);
