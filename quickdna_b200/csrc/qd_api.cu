@@ -1805,6 +1805,35 @@ static int expansion_write_tiles_dev(qd_ctx* c, ExpandParams p, uint8_t* out_dev
     return QD_OK;
 }
 
+// one pass (device callers with an output buffer): size_hint, row index and rows from one read of the windows;
+// `state` = ticket counter + one status word per warp tile of the chained scan, zeroed here
+template <bool ASCII, int W>
+static int launch_expansion_fused(qd_ctx* c, const ExpandParams& p, uint64_t* state, cudaStream_t s, int kernel_id) {
+    auto kern = expansion_fused_tiles_kernel<ASCII, W>;
+    const size_t smem = sizeof(ExpPipeSmem<(W ? W : 64)>);
+    auto it = c->occ_cache.find(((uint64_t)0xE0 + kernel_id) << 40);
+    if (it == c->occ_cache.end()) {
+        int occ = 0;
+        QD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QD_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * EXP_FUSED_WARPS, smem));
+        it = c->occ_cache.emplace(((uint64_t)0xE0 + kernel_id) << 40, std::max(1, occ)).first;
+    }
+    const uint64_t tiles = (p.n_win + 31) / 32;
+    const unsigned grid = (unsigned)std::min<uint64_t>((tiles + EXP_FUSED_WARPS - 1) / EXP_FUSED_WARPS, (uint64_t)c->sm_count * it->second);
+    QD_CUDA(c, cudaMemsetAsync(state, 0, (tiles + 1) * 8, s));  // ticket counter + one status word per warp tile
+    kern<<<grid, 32 * EXP_FUSED_WARPS, smem, s>>>(p, ASCII ? c->d_parse_pair : nullptr, state);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+static int expansion_fused_dev(qd_ctx* c, ExpandParams p, int enc, uint8_t* out_dev, uint64_t row_cap, uint64_t* state, cudaStream_t s) {
+    p.out = out_dev;
+    p.row_cap = row_cap;
+    if (enc == QD_ENC_ASCII) return p.w == 42 ? launch_expansion_fused<true, 42>(c, p, state, s, 0) : launch_expansion_fused<true, 0>(c, p, state, s, 1);
+    return p.w == 42 ? launch_expansion_fused<false, 42>(c, p, state, s, 2) : launch_expansion_fused<false, 0>(c, p, state, s, 3);
+}
+
 extern "C" int qd_expansion_windows_dev(qd_ctx* c, int enc, const uint8_t* windows_dev, size_t n_win, size_t w, uint64_t max_expansions,
                                         uint64_t* counts_dev, uint64_t* out_index_dev, uint8_t* out_dev, uint64_t out_capacity_rows,
                                         void* stream) {
@@ -1813,13 +1842,9 @@ extern "C" int qd_expansion_windows_dev(qd_ctx* c, int enc, const uint8_t* windo
     if (!g.ok) return QD_ERR_CUDA;
     if (n_win == 0) return QD_OK;
     cudaStream_t s = pick_stream(c, stream);
-    QD_CUDA(c, c->aux1.reserve(n_win * 8));  // emit
-    QD_CUDA(c, c->aux3.reserve(n_win * 8));  // descriptors
-    ExpandParams p = expansion_params(c, enc, windows_dev, n_win, w, max_expansions, counts_dev, c->aux1.as<uint64_t>(), out_index_dev,
-                                      c->aux3.as<uint64_t>());
-    if (int rc = expansion_count_dev(c, p, enc, s)) return rc;
-    if (out_dev) return expansion_write_tiles_dev(c, p, out_dev, out_capacity_rows, s);
-    return QD_OK;
+    QD_CUDA(c, c->aux1.reserve(((n_win + 31) / 32 + 1) * 8));  // ticket counter + status word per warp tile
+    ExpandParams p = expansion_params(c, enc, windows_dev, n_win, w, max_expansions, counts_dev, nullptr, out_index_dev, nullptr);
+    return expansion_fused_dev(c, p, enc, out_dev, out_capacity_rows, c->aux1.as<uint64_t>(), s);
 }
 
 extern "C" size_t qd_expansion_chunk_bytes(size_t chunk_windows, size_t w, uint64_t max_expansions) {
@@ -1840,9 +1865,8 @@ extern "C" int qd_expansion_windows_chunked_dev(qd_ctx* c, int enc, const uint8_
         c->last_error = "ring smaller than one chunk (qd_expansion_chunk_bytes) or not 16-byte aligned";
         return QD_ERR_INVALID_ARGUMENT;
     }
-    QD_CUDA(c, c->aux1.reserve(cw * 8));        // emit
-    QD_CUDA(c, c->aux2.reserve((cw + 1) * 8));  // row index of the chunk's windows
-    QD_CUDA(c, c->aux3.reserve(cw * 8));        // descriptors
+    QD_CUDA(c, c->aux1.reserve(((cw + 31) / 32 + 1) * 8));  // ticket counter + status word per warp tile
+    QD_CUDA(c, c->aux2.reserve((cw + 1) * 8));          // row index of the chunk's windows
     if (!counts_dev) QD_CUDA(c, c->aux0.reserve(cw * 8));
     const size_t n_chunks = qd_chunk_count(n_win, chunk_windows);
     if (checksums_dev) QD_CUDA(c, cudaMemsetAsync(checksums_dev, 0, n_chunks * 8, g.s));
@@ -1850,9 +1874,8 @@ extern "C" int qd_expansion_windows_chunked_dev(qd_ctx* c, int enc, const uint8_
         const size_t i0 = k * chunk_windows, cnt = std::min(chunk_windows, n_win - i0);
         uint8_t* out = ring.slot(k);
         ExpandParams p = expansion_params(c, enc, windows_dev + i0 * w, cnt, w, max_expansions, counts_dev ? counts_dev + i0 : c->aux0.as<uint64_t>(),
-                                          c->aux1.as<uint64_t>(), c->aux2.as<uint64_t>(), c->aux3.as<uint64_t>());
-        if (int rc = expansion_count_dev(c, p, enc, g.s)) return rc;
-        if (int rc = expansion_write_tiles_dev(c, p, out, (uint64_t)cnt * max_expansions, g.s)) return rc;
+                                          nullptr, c->aux2.as<uint64_t>(), nullptr);
+        if (int rc = expansion_fused_dev(c, p, enc, out, (uint64_t)cnt * max_expansions, c->aux1.as<uint64_t>(), g.s)) return rc;
         QD_CUDA(c, cudaMemcpyAsync(chunk_rows_dev + k, c->aux2.as<uint64_t>() + cnt, 8, cudaMemcpyDeviceToDevice, g.s));
         if (checksums_dev)
             if (int rc = checksum_dev(c, out, (uint64_t)cnt * max_expansions, chunk_rows_dev + k, w, 0, checksums_dev + k, g.s)) return rc;

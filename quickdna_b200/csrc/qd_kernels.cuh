@@ -1825,10 +1825,90 @@ __device__ __forceinline__ uint32_t expansion_stage_windows(const ExpandParams& 
     return (uint32_t)(src - a0);
 }
 
-// size_hint, rows to emit and the ambiguity descriptor of every window (src/expansions.rs:96-107): lane = window.
-// Four letters per step: masks from the letter-pair table (ASCII) or the bytes themselves (MASK); a word without an
-// ambiguity code (m & (m - 1) == 0 in every byte) costs nothing more.
+// size_hint and the ambiguity descriptor of ONE window whose bytes sit at raw[off ..] in shared memory
+// (src/expansions.rs:96-107).  Four letters per step: masks from the letter-pair table (ASCII) or the bytes themselves
+// (MASK); a word without an ambiguity code (m & (m - 1) == 0 in every byte) costs nothing more.
 // W: the window length when it is a compile-time constant (42: benches/expansions.rs), 0 = p.w
+// WIDE: the descriptor is two words of 16-bit entries -- position | (states - 1) << 6 | mask << 8, four in desc_out, two more and
+// the count (bits 63:60) in desc_hi -- instead of one word of 10-bit entries (position | mask << 6) with the count on top
+template <bool ASCII, int W, bool WIDE = false>
+__device__ __forceinline__ void expansion_size_hint(const ExpandParams& p, const uint8_t* raw, uint32_t raw_base, uint32_t off, uint32_t pair_base,
+                                                    uint64_t window, uint64_t& count, uint64_t& desc_out, uint64_t& desc_hi) {
+    const uint32_t w = W ? (uint32_t)W : p.w, n_words = (w + 3) >> 2;
+    const uint32_t pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);  // 16-bit entries
+    const uint32_t filler = ASCII ? 0x41u : 0x01u;
+    const uint32_t sa = raw_base + (off & ~3u);
+    const uint32_t sh = (off & 3u) * 8u;
+    // phase A, the same instructions for every lane: a bit per position that holds an ambiguity code
+    uint32_t amb_lo = 0, amb_hi = 0;
+    uint32_t prev = lds_u32(sa);
+#pragma unroll
+    for (uint32_t k = 0; k < (W ? (uint32_t)(W + 3) / 4 : 16u); k++) {
+        if (W == 0 && k >= n_words) break;
+        const uint32_t next = lds_u32(sa + 4 * k + 4);
+        uint32_t x = __funnelshift_r(prev, next, sh);
+        prev = next;
+        const uint32_t nb = min(4u, w - 4u * k);  // bytes of this word inside the window
+        if (nb < 4) x = (x & ((1u << (8 * nb)) - 1u)) | ((filler * 0x01010101u) << (8 * nb));
+        uint32_t m4;
+        bool bad;
+        if (ASCII) {
+            const uint32_t u = x & 0x1f1f1f1fu;
+            m4 = lds_u16(dp2a_lo(pair_coef, u, pair_base)) | (lds_u16(dp2a_hi(pair_coef, u, pair_base)) << 16);
+            bad = ((m4 & (PARSE_PAIR_SLOW * 0x01010101u)) | ((x & 0x40404040u) ^ 0x40404040u) | (x & 0x80808080u)) != 0;
+        } else {
+            m4 = x;
+            bad = ((x & 0xf0f0f0f0u) | ((x - 0x01010101u) & ~x & 0x80808080u)) != 0;
+        }
+        if (bad) {  // exact: the first byte of this word that is not a nucleotide code
+            for (uint32_t t = 0; t < nb; t++) {
+                const uint32_t b = (x >> (8 * t)) & 0xffu;
+                if (__ldg(p.to_mask + b) == 0) {
+                    atomicMin(p.err_key, (unsigned long long)(window * w + 4u * k + t));
+                    break;
+                }
+            }
+            continue;  // (the call fails; the counts of this window do not matter)
+        }
+        // bytes with more than one bit -> one bit each -> a nibble
+        uint32_t t4 = m4 & (m4 - 0x01010101u) & 0x0f0f0f0fu;
+        t4 = (t4 | (t4 >> 1) | (t4 >> 2) | (t4 >> 3)) & 0x01010101u;
+        const uint32_t nib = (t4 * 0x10204080u) >> 28;  // byte t -> bit t
+        if (k < 8) amb_lo |= nib << (4 * k);
+        else amb_hi |= nib << (4 * (k - 8));
+    }
+    // phase B: the few ambiguous positions, last first (the fastest odometer digit)
+    uint64_t size = 1, desc = 0, hi = 0;
+    uint32_t n_amb = 0;
+    bool overflow = false;
+    while (amb_lo | amb_hi) {
+        const uint32_t j = amb_hi ? 63u - __clz(amb_hi) : 31u - __clz(amb_lo);
+        if (j >= 32) amb_hi &= ~(1u << (j - 32));
+        else amb_lo &= ~(1u << j);
+        const uint32_t m = __ldg(p.to_mask + raw[off + j]);
+        const uint32_t states = __popc(m);
+        if (WIDE) {
+            const uint64_t entry = (j & 63u) | ((states - 1u) << 6) | (m << 8);
+            if (n_amb < 4) desc |= entry << (16 * n_amb);
+            else if (n_amb < EXP_DESC_MAX) hi |= entry << (16 * (n_amb - 4));
+        } else if (n_amb < EXP_DESC_MAX) {
+            desc |= (uint64_t)((j & 63u) | (m << 6)) << (10 * n_amb);
+        }
+        n_amb++;
+        overflow |= __umul64hi(size, (uint64_t)states) != 0;
+        size *= states;
+    }
+    count = overflow ? 0xffffffffffffffffull : size;
+    if (WIDE) {
+        desc_out = desc;
+        desc_hi = hi | ((uint64_t)min(n_amb, 15u) << 60);
+    } else {
+        desc_out = desc | ((uint64_t)min(n_amb, 15u) << 60);
+    }
+}
+
+// size_hint, rows to emit and the ambiguity descriptor of every window: lane = window (two-pass form: the host entry
+// point needs the row total before it can size the output; device callers with a buffer use expansion_fused_tiles_kernel)
 template <bool ASCII, int W>
 __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(const ExpandParams p, const uint16_t* __restrict__ pair) {
     __shared__ __align__(16) uint8_t raw_s[EXP_WARPS][32 * 64 + 48];
@@ -1839,9 +1919,8 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(c
         __syncthreads();
     }
     uint8_t* const raw = raw_s[warp];
-    const uint32_t w = W ? (uint32_t)W : p.w, n_words = (w + 3) >> 2;
-    const uint32_t pair_base = smem_u32(pair_s), pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);  // 16-bit entries
-    const uint32_t raw_base = smem_u32(raw);
+    const uint32_t w = W ? (uint32_t)W : p.w;
+    const uint32_t pair_base = smem_u32(pair_s), raw_base = smem_u32(raw);
     const uint32_t filler = ASCII ? 0x41u : 0x01u;
     const uint64_t n_tiles = (p.n_win + 31) / 32;
     for (uint64_t tile = (uint64_t)blockIdx.x * EXP_WARPS + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * EXP_WARPS) {
@@ -1851,66 +1930,11 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(c
         if (lane == 0) *reinterpret_cast<uint4*>(raw + ((off0 + cnt * w + 15) & ~15u)) = make_uint4(0, 0, 0, 0);  // the word past the last row
         __syncwarp();
         if (lane < (int)cnt) {
-            const uint32_t off = off0 + lane * w;
-            const uint32_t sa = raw_base + (off & ~3u);
-            const uint32_t sh = (off & 3u) * 8u;
-            // phase A, the same instructions for every lane: a bit per position that holds an ambiguity code
-            uint32_t amb_lo = 0, amb_hi = 0;
-            uint32_t prev = lds_u32(sa);
-#pragma unroll
-            for (uint32_t k = 0; k < (W ? (uint32_t)(W + 3) / 4 : 16u); k++) {
-                if (W == 0 && k >= n_words) break;
-                const uint32_t next = lds_u32(sa + 4 * k + 4);
-                uint32_t x = __funnelshift_r(prev, next, sh);
-                prev = next;
-                const uint32_t nb = min(4u, w - 4u * k);  // bytes of this word inside the window
-                if (nb < 4) x = (x & ((1u << (8 * nb)) - 1u)) | ((filler * 0x01010101u) << (8 * nb));
-                uint32_t m4;
-                bool bad;
-                if (ASCII) {
-                    const uint32_t u = x & 0x1f1f1f1fu;
-                    m4 = lds_u16(dp2a_lo(pair_coef, u, pair_base)) | (lds_u16(dp2a_hi(pair_coef, u, pair_base)) << 16);
-                    bad = ((m4 & (PARSE_PAIR_SLOW * 0x01010101u)) | ((x & 0x40404040u) ^ 0x40404040u) | (x & 0x80808080u)) != 0;
-                } else {
-                    m4 = x;
-                    bad = ((x & 0xf0f0f0f0u) | ((x - 0x01010101u) & ~x & 0x80808080u)) != 0;
-                }
-                if (bad) {  // exact: the first byte of this word that is not a nucleotide code
-                    for (uint32_t t = 0; t < nb; t++) {
-                        const uint32_t b = (x >> (8 * t)) & 0xffu;
-                        if (__ldg(p.to_mask + b) == 0) {
-                            atomicMin(p.err_key, (unsigned long long)((i0 + lane) * w + 4u * k + t));
-                            break;
-                        }
-                    }
-                    continue;  // (the call fails; the counts of this window do not matter)
-                }
-                // bytes with more than one bit -> one bit each -> a nibble
-                uint32_t t4 = m4 & (m4 - 0x01010101u) & 0x0f0f0f0fu;
-                t4 = (t4 | (t4 >> 1) | (t4 >> 2) | (t4 >> 3)) & 0x01010101u;
-                const uint32_t nib = (t4 * 0x10204080u) >> 28;  // byte t -> bit t
-                if (k < 8) amb_lo |= nib << (4 * k);
-                else amb_hi |= nib << (4 * (k - 8));
-            }
-            // phase B: the few ambiguous positions, last first (the fastest odometer digit)
-            uint64_t size = 1, desc = 0;
-            uint32_t n_amb = 0;
-            bool overflow = false;
-            while (amb_lo | amb_hi) {
-                const uint32_t j = amb_hi ? 63u - __clz(amb_hi) : 31u - __clz(amb_lo);
-                if (j >= 32) amb_hi &= ~(1u << (j - 32));
-                else amb_lo &= ~(1u << j);
-                const uint32_t m = __ldg(p.to_mask + raw[off + j]);
-                const uint32_t states = __popc(m);
-                if (n_amb < EXP_DESC_MAX) desc |= (uint64_t)((j & 63u) | (m << 6)) << (10 * n_amb);
-                n_amb++;
-                overflow |= __umul64hi(size, (uint64_t)states) != 0;
-                size *= states;
-            }
-            const uint64_t count = overflow ? 0xffffffffffffffffull : size;
+            uint64_t count, desc, unused;
+            expansion_size_hint<ASCII, W>(p, raw, raw_base, off0 + lane * w, pair_base, i0 + lane, count, desc, unused);
             p.counts[i0 + lane] = count;
             p.emit[i0 + lane] = (count <= p.max_expansions) ? count : 0;
-            p.desc[i0 + lane] = desc | ((uint64_t)min(n_amb, 15u) << 60);
+            p.desc[i0 + lane] = desc;
         }
         __syncwarp();
     }
@@ -1922,31 +1946,152 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_count_tiles_kernel(c
 // row's odometer digits, and drained with aligned 128-bit stores (head / tail bytes of the chunk individually).
 // The window of a row comes from two ballots over the tile's non-empty windows instead of a search, the digits from
 // 7-bit arithmetic (a row index inside a window is < 128).
+// WMAX: bytes per window the buffers are sized for
+template <int WMAX>
 struct ExpWarpSmem {
-    alignas(16) uint8_t win[32 * 64 + 48];
-    alignas(16) uint8_t stage[32 * 64 + 32];
+    alignas(16) uint8_t win[(32 * WMAX + 48 + 15) & ~15];
+    alignas(16) uint8_t stage[(32 * WMAX + 32 + 15) & ~15];
     uint64_t desc[32];
     uint32_t ne_first[32];  // first row (relative to the tile's first row) of the k-th window that emits rows
     uint32_t ne_win[32];    // ... and which window that is
 };
 
+#ifndef QD_EXP_SKEW
+#define QD_EXP_SKEW 1  // 1: rows that start mid-word copy their second five words first (W = 42: no bank conflicts in the stage)
+#endif
+
+// the rows of one warp tile: S.win (window 0 at off0) and S.desc are filled; window `lane` emits `emit` rows, the first one
+// `rel` rows after the tile's first row `row_lo`
 // W: the window length when it is a compile-time constant with W % 4 == 2 (42: benches/expansions.rs), 0 = p.w
-template <int W>
-__global__ void __launch_bounds__(32 * EXP_WARPS) expansion_write_tiles_kernel(const ExpandParams p) {
-    static_assert(W == 0 || (W % 4 == 2 && W <= 64), "the unrolled row copy is written for W = 2 mod 4");
-    __shared__ ExpWarpSmem SM[EXP_WARPS];
-    __shared__ uint8_t letter_of[64];  // mask * 4 + digit -> the letter of the digit-th base of the mask (possibilities() order A,T,C,G)
-    const int lane = threadIdx.x & 31;
-    ExpWarpSmem& S = SM[threadIdx.x >> 5];
+template <int W, int WMAX>
+__device__ __forceinline__ void expansion_tile_rows(const ExpandParams& p, ExpWarpSmem<WMAX>& S, uint32_t letter_base, uint32_t off0, uint32_t cnt,
+                                                    uint64_t row_lo, uint32_t rel, uint32_t emit, int lane) {
+    static_assert(W == 0 || (W % 4 == 2 && W <= 64 && (W - 2) / 4 % 2 == 0), "the unrolled row copy is written for W = 2 mod 8");
+    const uint32_t w = W ? (uint32_t)W : p.w;
+    const uint32_t win_base = smem_u32(S.win), stage_base = smem_u32(S.stage);
+    const uint32_t total = __shfl_sync(0xffffffffu, rel + emit, (int)cnt - 1);
+    const uint32_t ne = __ballot_sync(0xffffffffu, emit != 0);
+    const uint32_t m = __popc(ne);
+    if (emit != 0) {
+        const uint32_t k = __popc(ne & ((1u << lane) - 1u));
+        S.ne_first[k] = rel;
+        S.ne_win[k] = lane;
+    }
+    __syncwarp();
+    const uint32_t my_ne_first = lane < (int)m ? S.ne_first[lane] : 0xffffffffu;
+    uint8_t* gdst = p.out + row_lo * w;
+    for (uint32_t r0 = 0; r0 < total; r0 += 32, gdst += 32 * w) {
+        const uint32_t nrows = min(32u, total - r0);
+        if (row_lo + r0 + nrows > p.row_cap) break;  // caller's buffer is too small: out_index[n_win] tells how much was needed
+        const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
+        // the window of every row of the chunk: how many non-empty windows start at or before row r0, and a bit per
+        // window that starts inside the chunk
+        const uint32_t base_k = __popc(__ballot_sync(0xffffffffu, my_ne_first <= r0)) - 1u;
+        const uint32_t starts = __reduce_or_sync(0xffffffffu, (my_ne_first > r0 && my_ne_first < r0 + 32u) ? 1u << (my_ne_first - r0) : 0u);
+        if (lane < (int)nrows) {
+            const uint32_t kidx = base_k + __popc(starts & (0xffffffffu >> (31 - lane)));
+            const uint32_t j = S.ne_win[kidx];
+            uint32_t k = r0 + lane - S.ne_first[kidx];  // the row's index inside its window: < 128
+            const uint64_t d = S.desc[j];
+            const uint32_t s0 = off0 + j * w, d0 = phase + lane * w;
+            if (W != 0 && ((phase | off0) & 1u) == 0) {
+                // rows and windows start at even addresses: the row is (W - 2) / 4 aligned destination words plus one
+                // half-word, at its front (row starts mid-word) or at its back
+                const uint32_t hb = d0 & 2u, hpos = hb ? 0u : (uint32_t)W - 2u;
+                sts_u16(stage_base + d0 + hpos, lds_u16(win_base + s0 + hpos) & 0xdfdfu);
+                const uint32_t sb = s0 + hb, sh = (sb & 3u) * 8u, sa = win_base + (sb & ~3u), da = stage_base + d0 + hb;
+                constexpr int NQ = (W - 2) / 4;
+                if (QD_EXP_SKEW) {
+                    // rows W bytes apart: a word-aligned row and the mid-word row three rows on share their banks word for
+                    // word; walking the halves of a row in opposite order keeps them apart
+                    constexpr uint32_t HALF = 4u * (NQ / 2);
+                    const uint32_t o1 = hb ? HALF : 0u, o2 = HALF - o1;
+                    uint32_t prev = lds_u32(sa + o1);
+#pragma unroll
+                    for (int q = 0; q < NQ / 2; q++) {
+                        const uint32_t next = lds_u32(sa + o1 + 4 * q + 4);
+                        sts_u32(da + o1 + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                        prev = next;
+                    }
+                    prev = lds_u32(sa + o2);
+#pragma unroll
+                    for (int q = 0; q < NQ / 2; q++) {
+                        const uint32_t next = lds_u32(sa + o2 + 4 * q + 4);
+                        sts_u32(da + o2 + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                        prev = next;
+                    }
+                } else {
+                    uint32_t prev = lds_u32(sa);
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const uint32_t next = lds_u32(sa + 4 * q + 4);
+                        sts_u32(da + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                        prev = next;
+                    }
+                }
+            } else {
+                // head bytes up to the first aligned destination word, whole words, tail bytes
+                const uint32_t head = min(w, (4u - (d0 & 3u)) & 3u);
+                for (uint32_t b = 0; b < head; b++) S.stage[d0 + b] = S.win[s0 + b] & 0xdfu;
+                const uint32_t n_body = (w - head) >> 2, sb = s0 + head, sh = (sb & 3u) * 8u;
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.win) + (sb >> 2);
+                uint32_t* dw = reinterpret_cast<uint32_t*>(S.stage + d0 + head);
+                uint32_t prev = sw[0];
+#pragma unroll 1
+                for (uint32_t q = 0; q < n_body; q++) {
+                    const uint32_t next = sw[q + 1];
+                    dw[q] = __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu;
+                    prev = next;
+                }
+                for (uint32_t b = head + 4u * n_body; b < w; b++) S.stage[d0 + b] = S.win[s0 + b] & 0xdfu;
+            }
+            const uint32_t n_amb = (uint32_t)(d >> 60);
+#pragma unroll
+            for (uint32_t e = 0; e < EXP_DESC_MAX; e++) {
+                if (e < n_amb) {
+                    const uint32_t f = (uint32_t)(d >> (10 * e)) & 0x3ffu, pos = f & 63u, mask = f >> 6;
+                    const uint32_t states = __popc(mask);
+                    const uint32_t quo = states == 2u ? k >> 1 : (states == 4u ? k >> 2 : (k * 171u) >> 9);  // k / 3 for k < 128
+                    const uint32_t digit = k - quo * states;
+                    k = quo;
+                    sts_u8(stage_base + d0 + pos, lds_u8(letter_base + mask * 4u + digit));
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t nbytes = nrows * w;
+        const uint32_t hd = min(nbytes, (16u - phase) & 15u), body = (nbytes - hd) >> 4;
+        if (lane < (int)hd) gdst[lane] = S.stage[phase + lane];
+        {
+            uint4* gp = reinterpret_cast<uint4*>(gdst + hd) + lane;
+            uint32_t sa = stage_base + phase + hd + 16u * lane;
+            for (uint32_t c = lane; c < body; c += 32, gp += 32, sa += 512u) stg_stream(gp, lds_u128(sa));
+        }
+        const uint32_t done = hd + 16 * body;
+        if (lane < (int)(nbytes - done)) gdst[done + lane] = S.stage[phase + done + lane];
+        __syncwarp();
+    }
+}
+
+// mask * 4 + digit -> the letter of the digit-th base of the mask (possibilities() order A,T,C,G); needs a __syncthreads after
+__device__ __forceinline__ void expansion_fill_letters(uint8_t* letter_of, uint32_t letters) {
     if (threadIdx.x < 64) {
         uint32_t mm = threadIdx.x >> 2;
         for (uint32_t t = 0; t < (threadIdx.x & 3u); t++) mm &= mm - 1u;
-        letter_of[threadIdx.x] = mm ? (uint8_t)(p.letters >> (8 * (__ffs(mm) - 1))) : (uint8_t)0;
+        letter_of[threadIdx.x] = mm ? (uint8_t)(letters >> (8 * (__ffs(mm) - 1))) : (uint8_t)0;
     }
+}
+
+// W: the window length when it is a compile-time constant (42: benches/expansions.rs), 0 = p.w
+template <int W>
+__global__ void __launch_bounds__(32 * EXP_WARPS) expansion_write_tiles_kernel(const ExpandParams p) {
+    __shared__ ExpWarpSmem<64> SM[EXP_WARPS];
+    __shared__ uint8_t letter_of[64];
+    const int lane = threadIdx.x & 31;
+    ExpWarpSmem<64>& S = SM[threadIdx.x >> 5];
+    expansion_fill_letters(letter_of, p.letters);
     __syncthreads();
     const uint32_t w = W ? (uint32_t)W : p.w;
-    const uint32_t filler = 0x41u;
-    const uint32_t win_base = smem_u32(S.win), stage_base = smem_u32(S.stage), letter_base = smem_u32(letter_of);
     const uint64_t n_tiles = (p.n_win + 31) / 32;
     for (uint64_t tile = (uint64_t)blockIdx.x * EXP_WARPS + (threadIdx.x >> 5); tile < n_tiles; tile += (uint64_t)gridDim.x * EXP_WARPS) {
         const uint64_t i0 = tile * 32;
@@ -1955,53 +2100,263 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_write_tiles_kernel(c
         const uint64_t my_first = p.out_index[min(i0 + lane, p.n_win)], my_next = p.out_index[min(i0 + lane + 1, p.n_win)];
         const uint64_t row_lo = __shfl_sync(0xffffffffu, my_first, 0);
         const uint32_t rel = (uint32_t)(my_first - row_lo), emit = lane < (int)cnt ? (uint32_t)(my_next - my_first) : 0u;
-        const uint32_t total = __shfl_sync(0xffffffffu, rel + emit, (int)cnt - 1);
-        const uint32_t ne = __ballot_sync(0xffffffffu, emit != 0);
-        const uint32_t m = __popc(ne);
-        if (emit != 0) {
-            const uint32_t k = __popc(ne & ((1u << lane) - 1u));
-            S.ne_first[k] = rel;
-            S.ne_win[k] = lane;
-        }
         S.desc[lane] = lane < (int)cnt ? p.desc[i0 + lane] : 0;
-        const uint32_t off0 = expansion_stage_windows(p, i0, cnt, S.win, lane, filler);
+        const uint32_t off0 = expansion_stage_windows(p, i0, cnt, S.win, lane, 0x41u);
+        __syncwarp();
+        expansion_tile_rows<W, 64>(p, S, smem_u32(letter_of), off0, cnt, row_lo, rel, emit, lane);
+        __syncwarp();
+    }
+    (void)w;
+}
+
+// ---- one pass: size_hint, row index and rows of a tile from ONE read of its windows ---------------------------------------
+// The first row of a warp tile (32 windows) is the number of rows all tiles before it emit: a chained scan with decoupled
+// look-back over one 64-bit status word per tile (bits 63:62 = 0 nothing yet, 1 the tile's own rows, 2 rows of all tiles
+// up to and including it).  Warps are independent (no CTA barrier in the loop) and take tiles from a ticket counter, so
+// a tile with a lower number was always started earlier, and the warp holding the lowest unpublished tile never waits:
+// no deadlock, whatever part of the grid is resident.  A warp counts the windows of its NEXT tile and publishes that
+// tile's rows before it looks back for the current one (two window buffers): by then -- a whole row phase later -- every
+// tile before it has long been published, and all but the last few hundred carry their inclusive sum.
+// `state` (ticket counter, then the status words) must be zero when the kernel starts.
+// Measured on the way (2*10^7 windows of 42 nt, 1.3*10^8 rows; two-pass form 2.15 ms): tiles handed out statically, look-
+// back right after the count: 2.99 ms (every warp walks back through hundreds of unfinished neighbours); CTA tiles of
+// 8 x 32 windows with two __syncthreads per tile: 2.37 ms, a third of all warp time spent at the barriers; the same
+// without barriers (flags in shared memory, count one tile ahead): 2.0 ms -- with tiles assigned statically the whole
+// grid advances at the pace of the slowest warp of each generation.
+#ifndef QD_EXP_FUSED_WARPS
+#define QD_EXP_FUSED_WARPS 8
+#endif
+constexpr int EXP_FUSED_WARPS = QD_EXP_FUSED_WARPS;
+constexpr uint64_t EXP_STATE_VALUE = (1ull << 62) - 1;
+#ifndef QD_EXP_LOOK
+#define QD_EXP_LOOK 4
+#endif
+constexpr int EXP_LOOK = QD_EXP_LOOK;  // status words per lane and look
+
+__device__ __forceinline__ uint64_t ld_relaxed_gpu_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int WMAX>
+struct ExpPipeWarpSmem {
+    alignas(16) uint8_t win[2][(32 * WMAX + 48 + 15) & ~15];    // windows of the current and of the next tile
+    alignas(16) uint8_t stage[2][(32 * WMAX + 32 + 15) & ~15];  // 32 rows on their way out, and the 32 before them
+    ulonglong2 desc[2][32];  // ambiguous positions of each window (expansion_size_hint, WIDE form)
+    uint16_t ne_first[32];   // first row (relative to the tile's first row) of the k-th window that emits rows
+    uint8_t ne_win[32];      // ... and which window that is
+};
+template <int WMAX>
+struct ExpPipeSmem {
+    ExpPipeWarpSmem<WMAX> warp[EXP_FUSED_WARPS];
+    alignas(16) uint16_t pair[PAIR_ENTRIES];
+    uint8_t letter_of[64];
+};
+
+// rows the tiles before `tile` emit; every lane returns the sum.  A tile's own rows fit 32 bits (one REDUX per 32 status
+// words); only the one inclusive word that ends the walk is 64 bits wide.
+__device__ __forceinline__ uint64_t expansion_look_back(const uint64_t* status, uint64_t tile, int lane) {
+    uint64_t acc = 0;
+    uint32_t own = 0;  // own rows of the tiles walked over since `acc` was last topped up (a tile emits at most 4064 rows)
+    int64_t idx = (int64_t)tile - 1 - lane;
+    for (;;) {
+        uint64_t v[EXP_LOOK];
+#pragma unroll
+        for (int g = 0; g < EXP_LOOK; g++) v[g] = idx - 32 * g >= 0 ? ld_relaxed_gpu_u64(status + idx - 32 * g) : 2ull << 62;  // in front of the first tile: nothing
+#pragma unroll
+        for (int g = 0; g < EXP_LOOK; g++) {
+            while ((v[g] >> 62) == 0) v[g] = ld_relaxed_gpu_u64(status + idx - 32 * g);
+        }
+        bool found = false;
+        uint64_t ends_with = 0;
+#pragma unroll
+        for (int g = 0; g < EXP_LOOK; g++) {
+            if (!found) {
+                const uint32_t done = __ballot_sync(0xffffffffu, (v[g] >> 62) == 2);
+                const int first = done ? __ffs(done) - 1 : 32;
+                own += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)v[g] : 0u);
+                if (done) {
+                    found = true;
+                    ends_with = __shfl_sync(0xffffffffu, v[g], first) & EXP_STATE_VALUE;
+                }
+            }
+        }
+        if (found) return acc + own + ends_with;
+        if (own >= 0x80000000u) {  // (a tile emits at most 4064 rows: EXP_LOOK * 32 of them stay far below 2^31)
+            acc += own;
+            own = 0;
+        }
+        idx -= 32 * EXP_LOOK;
+    }
+}
+
+// what a warp keeps of a tile between counting it and writing its rows
+struct ExpTileRegs {
+    uint64_t i0;
+    uint32_t cnt, off0, emit, rel;
+};
+
+// W: the window length when it is a compile-time constant (42: benches/expansions.rs), 0 = p.w
+template <bool ASCII, int W>
+__global__ void __launch_bounds__(32 * EXP_FUSED_WARPS, W ? 4 : 3) expansion_fused_tiles_kernel(const ExpandParams p, const uint16_t* __restrict__ pair, uint64_t* state) {
+    constexpr int WMAX = W ? W : 64;
+    constexpr int FW = EXP_FUSED_WARPS;
+    constexpr int WR = (W % 8 == 2) ? W : 0;  // the unrolled row copy exists for W = 2 mod 8
+    extern __shared__ __align__(16) uint8_t exp_smem_raw[];
+    ExpPipeSmem<WMAX>& SH = *reinterpret_cast<ExpPipeSmem<WMAX>*>(exp_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ExpPipeWarpSmem<WMAX>& S = SH.warp[warp];
+    if (ASCII)
+        for (int i = threadIdx.x; i < (int)PAIR_ENTRIES; i += 32 * FW) SH.pair[i] = __ldg(pair + i);
+    expansion_fill_letters(SH.letter_of, p.letters);
+    __syncthreads();
+    const uint32_t w = W ? (uint32_t)W : p.w;
+    const uint32_t pair_base = smem_u32(SH.pair), letter_base = smem_u32(SH.letter_of);
+    const uint32_t filler = ASCII ? 0x41u : 0x01u;
+    const uint64_t n_tiles = (p.n_win + 31) / 32;
+    uint64_t* const out_index = const_cast<uint64_t*>(p.out_index);
+    uint64_t* const status = state + 1;
+
+    auto take_tile = [&]() -> uint64_t {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(reinterpret_cast<unsigned long long*>(state), 1ull);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    // size_hint of the 32 windows of `tile` into buffer nb; publishes the rows the tile emits
+    auto count_tile = [&](uint64_t tile, uint32_t nb, ExpTileRegs& T) {
+        T.i0 = tile * 32;
+        T.cnt = (uint32_t)min((uint64_t)32, p.n_win - T.i0);
+        T.off0 = expansion_stage_windows(p, T.i0, T.cnt, S.win[nb], lane, filler);
+        if (lane == 0) *reinterpret_cast<uint4*>(S.win[nb] + ((T.off0 + T.cnt * w + 15) & ~15u)) = make_uint4(0, 0, 0, 0);  // the word past the last row
+        __syncwarp();
+        uint64_t count = 0, desc = 0, desc_hi = 0;
+        if (lane < (int)T.cnt) {
+            expansion_size_hint<ASCII, W, true>(p, S.win[nb], smem_u32(S.win[nb]), T.off0 + lane * w, pair_base, T.i0 + lane, count, desc, desc_hi);
+            p.counts[T.i0 + lane] = count;
+        }
+        T.emit = (lane < (int)T.cnt && count <= p.max_expansions) ? (uint32_t)count : 0u;
+        S.desc[nb][lane] = make_ulonglong2(desc, desc_hi);
+        uint32_t incl = T.emit;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        T.rel = incl - T.emit;
+        if (lane == 31) st_relaxed_gpu_u64(status + tile, ((tile == 0 ? 2ull : 1ull) << 62) | incl);
+    };
+
+    // Per iteration: draw a ticket, count and PUBLISH that tile, then look back for the current tile and write its rows.
+    // The order matters: a warp never sits in a look-back holding a tile it has drawn but not published.  (Drawing the
+    // ticket and starting the window loads one step earlier, so that their latency passes behind the look-back, was
+    // measured: publishes then queue behind look-backs that wait for other publishes -- 18.6 ms instead of 1.9.)
+    ExpTileRegs cur{}, nxt{};
+    uint32_t iter = 0, chunk_no = 0;
+    uint64_t t_next = take_tile();
+    if (t_next < n_tiles) count_tile(t_next, 0, nxt);
+    for (; t_next < n_tiles; iter++) {
+        const uint32_t b = iter & 1u;
+        const uint64_t tile = t_next;
+        cur = nxt;
+        t_next = take_tile();
+        if (t_next < n_tiles) count_tile(t_next, b ^ 1u, nxt);
+        const uint32_t total = __shfl_sync(0xffffffffu, cur.rel + cur.emit, 31);
+        uint64_t row_lo = 0;
+        if (tile != 0) {
+            row_lo = expansion_look_back(status, tile, lane);
+            if (lane == 0) st_relaxed_gpu_u64(status + tile, (2ull << 62) | (row_lo + total));
+        }
+        if (lane < (int)cur.cnt) out_index[cur.i0 + lane] = row_lo + cur.rel;
+        if (tile == n_tiles - 1 && lane == 0) out_index[p.n_win] = row_lo + total;
+        if (!p.out) continue;
+
+        // ---- rows of this warp tile: 32 at a time, lane = row ----
+        // A chunk of 32 rows is a multiple of 16 bytes, so all chunks of a tile sit at the same 16-byte phase of the output;
+        // the stage mirrors it.  The (phase) bytes a chunk leaves past its last whole granule are carried into the front
+        // of the next chunk's stage, so only a tile's first and last granule are written byte-wise; everything else
+        // leaves as one bulk copy per chunk (two stage buffers: the copy of chunk c reads while chunk c + 1 is built).
+        const uint32_t win_base = smem_u32(S.win[b]);
+        const uint32_t lim = (uint32_t)min((uint64_t)total, p.row_cap - min(p.row_cap, row_lo));  // rows the caller's buffer still holds
+        const uint32_t rows_out = total <= lim ? total : (lim & ~31u);  // caller's buffer too small: whole chunks only (out_index[n_win] tells how much was needed)
+        const uint32_t ne = __ballot_sync(0xffffffffu, cur.emit != 0);
+        const uint32_t m = __popc(ne);
+        if (cur.emit != 0) {
+            const uint32_t k = __popc(ne & ((1u << lane) - 1u));
+            S.ne_first[k] = (uint16_t)cur.rel;
+            S.ne_win[k] = (uint8_t)lane;
+        }
         __syncwarp();
         const uint32_t my_ne_first = lane < (int)m ? S.ne_first[lane] : 0xffffffffu;
-        uint8_t* gdst = p.out + row_lo * w;
-        for (uint32_t r0 = 0; r0 < total; r0 += 32, gdst += 32 * w) {
-            const uint32_t nrows = min(32u, total - r0);
-            if (row_lo + r0 + nrows > p.row_cap) break;  // caller's buffer is too small: out_index[n_win] tells how much was needed
-            const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
+        uint8_t* const gtile = p.out + row_lo * w;
+        const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gtile) & 15u);
+        uint8_t* galigned = gtile - phase;  // the granule the chunk's first row starts in
+        const uint32_t d0 = phase + lane * w;
+        const bool even = WR != 0 && ((phase | cur.off0) & 1u) == 0;
+        for (uint32_t r0 = 0; r0 < rows_out; r0 += 32, galigned += 32 * w, chunk_no++) {
+            const uint32_t nrows = min(32u, rows_out - r0);
+            uint8_t* const stage = S.stage[chunk_no & 1u];
+            const uint32_t stage_base = smem_u32(stage);
+            if (lane == 0) {
+                bulk_wait_read_1();  // the copy that last used this stage buffer has read it
+                if (r0 != 0 && phase != 0)  // the previous chunk's last, partial granule
+                    *reinterpret_cast<uint4*>(stage) = *reinterpret_cast<const uint4*>(S.stage[(chunk_no & 1u) ^ 1u] + 32 * w);
+            }
+            __syncwarp();
             // the window of every row of the chunk: how many non-empty windows start at or before row r0, and a bit per
             // window that starts inside the chunk
             const uint32_t base_k = __popc(__ballot_sync(0xffffffffu, my_ne_first <= r0)) - 1u;
             const uint32_t starts = __reduce_or_sync(0xffffffffu, (my_ne_first > r0 && my_ne_first < r0 + 32u) ? 1u << (my_ne_first - r0) : 0u);
+            uint32_t n_amb = 0, k = 0;
+            ulonglong2 dd = make_ulonglong2(0, 0);
             if (lane < (int)nrows) {
                 const uint32_t kidx = base_k + __popc(starts & (0xffffffffu >> (31 - lane)));
                 const uint32_t j = S.ne_win[kidx];
-                uint32_t k = r0 + lane - S.ne_first[kidx];  // the row's index inside its window: < 128
-                const uint64_t d = S.desc[j];
-                const uint32_t s0 = off0 + j * w, d0 = phase + lane * w;
-                if (W != 0 && ((phase | off0) & 1u) == 0) {
-                    // rows and windows start at even addresses: the row is 10 aligned destination words plus one half-word,
-                    // at its front (row starts mid-word) or at its back
-                    const uint32_t hb = d0 & 2u, hpos = hb ? 0u : (uint32_t)W - 2u;
+                k = r0 + lane - S.ne_first[kidx];  // the row's index inside its window: < 128
+                dd = S.desc[b][j];
+                n_amb = (uint32_t)(dd.y >> 60);
+                const uint32_t s0 = cur.off0 + j * w;
+                if (even) {
+                    // rows and windows start at even addresses: the row is (W - 2) / 4 aligned destination words plus one
+                    // half-word, at its front (row starts mid-word) or at its back
+                    const uint32_t hb = d0 & 2u, hpos = hb ? 0u : (uint32_t)WR - 2u;
                     sts_u16(stage_base + d0 + hpos, lds_u16(win_base + s0 + hpos) & 0xdfdfu);
                     const uint32_t sb = s0 + hb, sh = (sb & 3u) * 8u, sa = win_base + (sb & ~3u), da = stage_base + d0 + hb;
-                    uint32_t prev = lds_u32(sa);
+                    constexpr int NQ = (WR - 2) / 4;
+                    // rows W bytes apart: a word-aligned row and the mid-word row three rows on share their banks word for
+                    // word; walking the halves of a row in opposite order keeps them apart
+                    constexpr uint32_t HALF = 4u * (NQ / 2);
+                    const uint32_t o1 = (QD_EXP_SKEW && hb) ? HALF : 0u, o2 = HALF - o1;
+                    uint32_t prev = lds_u32(sa + o1);
 #pragma unroll
-                    for (int q = 0; q < (W - 2) / 4; q++) {
-                        const uint32_t next = lds_u32(sa + 4 * q + 4);
-                        sts_u32(da + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                    for (int q = 0; q < NQ / 2; q++) {
+                        const uint32_t next = lds_u32(sa + o1 + 4 * q + 4);
+                        sts_u32(da + o1 + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                        prev = next;
+                    }
+                    prev = lds_u32(sa + o2);
+#pragma unroll
+                    for (int q = 0; q < NQ / 2; q++) {
+                        const uint32_t next = lds_u32(sa + o2 + 4 * q + 4);
+                        sts_u32(da + o2 + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
                         prev = next;
                     }
                 } else {
                     // head bytes up to the first aligned destination word, whole words, tail bytes
+                    const uint8_t* const wsrc = S.win[b];
                     const uint32_t head = min(w, (4u - (d0 & 3u)) & 3u);
-                    for (uint32_t b = 0; b < head; b++) S.stage[d0 + b] = S.win[s0 + b] & 0xdfu;
+                    for (uint32_t q = 0; q < head; q++) stage[d0 + q] = wsrc[s0 + q] & 0xdfu;
                     const uint32_t n_body = (w - head) >> 2, sb = s0 + head, sh = (sb & 3u) * 8u;
-                    const uint32_t* sw = reinterpret_cast<const uint32_t*>(S.win) + (sb >> 2);
-                    uint32_t* dw = reinterpret_cast<uint32_t*>(S.stage + d0 + head);
+                    const uint32_t* sw = reinterpret_cast<const uint32_t*>(wsrc) + (sb >> 2);
+                    uint32_t* dw = reinterpret_cast<uint32_t*>(stage + d0 + head);
                     uint32_t prev = sw[0];
 #pragma unroll 1
                     for (uint32_t q = 0; q < n_body; q++) {
@@ -2009,36 +2364,44 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_write_tiles_kernel(c
                         dw[q] = __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu;
                         prev = next;
                     }
-                    for (uint32_t b = head + 4u * n_body; b < w; b++) S.stage[d0 + b] = S.win[s0 + b] & 0xdfu;
-                }
-                const uint32_t n_amb = (uint32_t)(d >> 60);
-#pragma unroll
-                for (uint32_t e = 0; e < EXP_DESC_MAX; e++) {
-                    if (e < n_amb) {
-                        const uint32_t f = (uint32_t)(d >> (10 * e)) & 0x3ffu, pos = f & 63u, mask = f >> 6;
-                        const uint32_t states = __popc(mask);
-                        const uint32_t quo = states == 2u ? k >> 1 : (states == 4u ? k >> 2 : (k * 171u) >> 9);  // k / 3 for k < 128
-                        const uint32_t digit = k - quo * states;
-                        k = quo;
-                        sts_u8(stage_base + d0 + pos, lds_u8(letter_base + mask * 4u + digit));
-                    }
+                    for (uint32_t q = head + 4u * n_body; q < w; q++) stage[d0 + q] = wsrc[s0 + q] & 0xdfu;
                 }
             }
-            __syncwarp();
-            const uint32_t nbytes = nrows * w;
-            const uint32_t hd = min(nbytes, (16u - phase) & 15u), body = (nbytes - hd) >> 4;
-            if (lane < (int)hd) gdst[lane] = S.stage[phase + lane];
-            {
-                uint4* gp = reinterpret_cast<uint4*>(gdst + hd) + lane;
-                uint32_t sa = stage_base + phase + hd + 16u * lane;
-                for (uint32_t c = lane; c < body; c += 32, gp += 32, sa += 512u) stg_stream(gp, lds_u128(sa));
+            // the row's odometer digits, fastest first: digit = k mod states, k /= states; states in {2, 3, 4} and
+            // k < 128, so the quotient is one multiply: k / 2 = k * 128 >> 8, k / 3 = k * 86 >> 8, k / 4 = k * 64 >> 8
+            const uint32_t max_amb = __reduce_max_sync(0xffffffffu, n_amb);
+            uint64_t d = dd.x;
+            const uint32_t patch_base = stage_base + d0;
+#pragma unroll 1
+            for (uint32_t e = 0; e < max_amb; e++) {
+                const uint32_t f = (uint32_t)d;
+                d = e == 3 ? dd.y : d >> 16;
+                if (e < n_amb) {
+                    const uint32_t recip = (0x40568000u >> ((f >> 3) & 0x18u)) & 0xffu;
+                    const uint32_t quo = (k * recip) >> 8;
+                    const uint32_t digit = k - quo - quo * ((f >> 6) & 3u);
+                    k = quo;
+                    sts_u8(patch_base + (f & 63u), lds_u8(letter_base + ((f >> 6) & 0x3cu) + digit));
+                }
             }
-            const uint32_t done = hd + 16 * body;
-            if (lane < (int)(nbytes - done)) gdst[done + lane] = S.stage[phase + done + lane];
+            fence_proxy_async_smem();  // my rows, written through the generic proxy, are visible to the bulk copy
             __syncwarp();
+            const bool last = r0 + 32u >= rows_out;
+            const uint32_t start_off = r0 == 0 ? ((phase + 15u) & ~15u) : 0u;  // a tile's first granule may belong to the tile before
+            const uint32_t end_off = phase + nrows * w, body_end = last ? (end_off & ~15u) : min(end_off & ~15u, 32u * w);
+            if (lane == 0) {
+                if (body_end > start_off) bulk_s2g(galigned + start_off, stage + start_off, body_end - start_off);
+                bulk_commit();
+            }
+            if (r0 == 0 && lane < (int)(min(start_off, end_off) - phase)) gtile[lane] = stage[phase + lane];
+            if (last) {
+                const uint32_t tail0 = max(body_end, start_off);  // (a tile shorter than a granule has no body)
+                if (tail0 + lane < end_off) galigned[tail0 + lane] = stage[tail0 + lane];
+            }
         }
         __syncwarp();
     }
+    if (lane == 0) bulk_wait_all();  // shared memory must outlive the last copy
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -185,6 +185,35 @@ def test_expansions_chunked_matches_oracle(torch, B, N):
     assert torch.equal(rows1, rows) and torch.equal(sums1, sums)
 
 
+@pytest.mark.parametrize("n_win,w,shift", [(300_011, 42, 0), (70_001, 42, 3), (50_000, 37, 0), (1, 42, 0), (33, 64, 1)])
+def test_expansions_one_pass_many_tiles(torch, B, n_win, w, shift):
+    """The one-pass kernel chains the first row of every warp tile through status words (decoupled look-back): more tiles
+    than resident warps, windows that are skipped, odd input alignment, both encodings -- row index = running sum of
+    the emitted counts, rows = the oracle's (whole-output checksum)."""
+    rng = np.random.default_rng(n_win + w)
+    win = _ambiguous_windows(rng, n_win, w=w, n_amb=3)
+    win[rng.integers(0, n_win, max(1, n_win // 50)), :4] = np.frombuffer(b"NNNN", dtype=np.uint8)  # >= 256 expansions: skipped at cap 100
+    cap = 100
+    for enc, arr in ((0, win), (1, oracle.masks_of(win.reshape(-1)).reshape(n_win, w))):
+        flat = torch.zeros(n_win * w + shift, dtype=torch.uint8, device="cuda")
+        flat[shift:] = _dev(torch, arr).view(-1)
+        d = flat[shift:].view(n_win, w)
+        B.dev_error_reset()
+        c_d, oi_d, out_d = B.expansion_windows_dev(d, cap, enc=enc)
+        assert B.dev_error_fetch(d.reshape(-1)) is None
+        counts = c_d.cpu().numpy().astype(np.uint64)
+        emit = np.where(counts <= cap, counts, 0).astype(np.uint64)
+        want_index = np.concatenate([[0], np.cumsum(emit)]).astype(np.uint64)
+        assert (oi_d.cpu().numpy().astype(np.uint64) == want_index).all()
+        total = int(want_index[-1])
+        want_sum, want_rows = oracle.check_expansions(win, cap, _threads())
+        assert total == want_rows
+        rows = out_d[: total * w].cpu().numpy()
+        if enc == 1:
+            rows = oracle.ascii_of(rows)
+        assert oracle.checksum64(rows, 0) == want_sum
+
+
 def test_two_streams_on_one_context_are_ordered(torch, B):
     """scratch and the error key are per context; calls on different streams must not race on them."""
     rng = np.random.default_rng(9)
