@@ -83,6 +83,8 @@ struct qd_ctx {
     uint8_t* d_ckey_pair = nullptr;   // [encoding][PAIR_ENTRIES]
     CanonKeyTables* d_ckey = nullptr;
     uint16_t* d_parse_pair = nullptr;  // [strict][PAIR_ENTRIES]
+    unsigned long long* d_gate = nullptr;  // generation of the last optimistic pass that failed (ParseParams::gate)
+    unsigned long long gate_gen = 0;
     std::map<int, uint8_t*> d_direct;  // one-frame direct codon tables, built on first use: key = slot * 4 + ascii * 2 + strict
     unsigned long long* d_err = nullptr;
     unsigned long long* h_err = nullptr;  // pinned
@@ -356,12 +358,13 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
 }
 
 template <int MODE, int OP = 0>
-int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* dst, DevBuf& block_sums, cudaStream_t s) {
+int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* dst, DevBuf& block_sums, cudaStream_t s,
+                          const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0) {
     const uint64_t n_blocks = std::max<uint64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
     QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
-    scan_block_sums_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>());
-    scan_spine_kernel<OP><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks);
-    scan_finish_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst);
+    scan_block_sums_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), gate, gate_gen);
+    scan_spine_kernel<OP><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, gate, gate_gen);
+    scan_finish_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst, gate, gate_gen);
     c->launches += 3;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
@@ -531,6 +534,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaMalloc(&c->d_ckey_pair, sizeof(T.ckey_pair)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_ckey, sizeof(T.ckey)) == cudaSuccess;
     ok &= cudaMalloc(&c->d_parse_pair, sizeof(T.parse_pair)) == cudaSuccess;
+    ok &= cudaMalloc(&c->d_gate, 8) == cudaSuccess && cudaMemset(c->d_gate, 0, 8) == cudaSuccess;
     ok &= cudaMalloc(&c->d_err, sizeof(unsigned long long)) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&c->dev_done, cudaEventDisableTiming) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
@@ -592,6 +596,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->d_ckey_pair) cudaFree(c->d_ckey_pair);
     if (c->d_ckey) cudaFree(c->d_ckey);
     if (c->d_parse_pair) cudaFree(c->d_parse_pair);
+    if (c->d_gate) cudaFree(c->d_gate);
     for (auto& kv : c->d_direct) cudaFree(kv.second);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
@@ -915,7 +920,11 @@ static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, 
     }
     const uint64_t span = (reinterpret_cast<uintptr_t>(ascii_dev) & 15) + n;  // from the aligned start
     const uint64_t n_blocks = (span + PARSE_BLOCK_BYTES - 1) / PARSE_BLOCK_BYTES;
-    QD_CUDA(c, c->parse_counts.reserve(n_blocks * 8));
+    // dropped bytes per block: all zero between calls (pass 1 adds, the compacting pass clears what it has used)
+    if (c->parse_counts.cap < n_blocks * 8) {
+        QD_CUDA(c, c->parse_counts.reserve(n_blocks * 8));
+        QD_CUDA(c, cudaMemsetAsync(c->parse_counts.p, 0, c->parse_counts.cap, s));
+    }
     QD_CUDA(c, c->parse_offsets.reserve((n_blocks + 1) * 8));
     ParseParams p{};
     p.in = ascii_dev;
@@ -927,15 +936,21 @@ static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, 
     p.offsets = c->parse_offsets.as<uint64_t>();
     p.out = masks_dev;
     p.err_key = c->d_err;
+    p.gate = c->d_gate;
+    p.gate_gen = ++c->gate_gen;
+    // One streaming pass finishes input without whitespace (when input and output share their 16-byte phase); the scan
+    // and the compacting pass behind it return at once unless that pass dropped a byte.
+    const bool same_phase = ((reinterpret_cast<uintptr_t>(ascii_dev) ^ reinterpret_cast<uintptr_t>(masks_dev)) & 15) == 0;
+    const uint64_t n_gran = (span + 15) / 16;
+    const uint64_t step = (uint64_t)PARSE_THREADS * PARSE_CLEAN_UNROLL;
+    const unsigned g1 = (unsigned)std::min<uint64_t>((n_gran + step - 1) / step, (uint64_t)c->sm_count * 8);
+    if (same_phase) parse_pass1_kernel<true><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
+    else parse_pass1_kernel<false><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
+    parse_scan_kernel<<<1, PARSE_SCAN_THREADS, 0, s>>>(p, n_blocks);
     const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)c->sm_count * 8);
-    parse_count_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks);
-    c->launches++;
+    parse_write_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks, n_masks_dev);
+    c->launches += 3;
     QD_CUDA(c, cudaGetLastError());
-    if (int rc = device_exclusive_scan<1>(c, p.counts, n_blocks, c->parse_offsets.as<uint64_t>(), c->block_sums, s)) return rc;
-    parse_write_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks);
-    c->launches++;
-    QD_CUDA(c, cudaGetLastError());
-    if (n_masks_dev) QD_CUDA(c, cudaMemcpyAsync(n_masks_dev, c->parse_offsets.as<uint64_t>() + n_blocks, 8, cudaMemcpyDeviceToDevice, s));
     return QD_OK;
 }
 

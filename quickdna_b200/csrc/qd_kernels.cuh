@@ -1802,6 +1802,8 @@ constexpr int EXP_WARPS = 8;
 
 // the tile's cnt * w source bytes into shared memory with aligned 128-bit loads; returns the offset of window 0 in `raw`
 // (bytes before / after the buffer read as `filler`, a valid concrete base, and are never looked at)
+// FOLD: clear bit 5 of every byte on the way (ASCII letters become upper case; no byte changes between valid and invalid)
+template <bool FOLD = false>
 __device__ __forceinline__ uint32_t expansion_stage_windows(const ExpandParams& p, uint64_t i0, uint32_t cnt, uint8_t* raw, int lane, uint32_t filler) {
     const uintptr_t lo = reinterpret_cast<uintptr_t>(p.windows), hi = lo + p.n_win * p.w;
     const uintptr_t src = lo + i0 * p.w, a0 = src & ~(uintptr_t)15;
@@ -1820,6 +1822,7 @@ __device__ __forceinline__ uint32_t expansion_stage_windows(const ExpandParams& 
             }
             v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
         }
+        if (FOLD) v = make_uint4(v.x & 0xdfdfdfdfu, v.y & 0xdfdfdfdfu, v.z & 0xdfdfdfdfu, v.w & 0xdfdfdfdfu);
         *reinterpret_cast<uint4*>(raw + 16 * c) = v;
     }
     return (uint32_t)(src - a0);
@@ -2235,7 +2238,7 @@ __global__ void __launch_bounds__(32 * EXP_FUSED_WARPS, W ? 4 : 3) expansion_fus
     auto count_tile = [&](uint64_t tile, uint32_t nb, ExpTileRegs& T) {
         T.i0 = tile * 32;
         T.cnt = (uint32_t)min((uint64_t)32, p.n_win - T.i0);
-        T.off0 = expansion_stage_windows(p, T.i0, T.cnt, S.win[nb], lane, filler);
+        T.off0 = expansion_stage_windows<ASCII>(p, T.i0, T.cnt, S.win[nb], lane, filler);  // upper case from here on
         if (lane == 0) *reinterpret_cast<uint4*>(S.win[nb] + ((T.off0 + T.cnt * w + 15) & ~15u)) = make_uint4(0, 0, 0, 0);  // the word past the last row
         __syncwarp();
         uint64_t count = 0, desc = 0, desc_hi = 0;
@@ -2328,7 +2331,7 @@ __global__ void __launch_bounds__(32 * EXP_FUSED_WARPS, W ? 4 : 3) expansion_fus
                     // rows and windows start at even addresses: the row is (W - 2) / 4 aligned destination words plus one
                     // half-word, at its front (row starts mid-word) or at its back
                     const uint32_t hb = d0 & 2u, hpos = hb ? 0u : (uint32_t)WR - 2u;
-                    sts_u16(stage_base + d0 + hpos, lds_u16(win_base + s0 + hpos) & 0xdfdfu);
+                    sts_u16(stage_base + d0 + hpos, lds_u16(win_base + s0 + hpos));
                     const uint32_t sb = s0 + hb, sh = (sb & 3u) * 8u, sa = win_base + (sb & ~3u), da = stage_base + d0 + hb;
                     constexpr int NQ = (WR - 2) / 4;
                     // rows W bytes apart: a word-aligned row and the mid-word row three rows on share their banks word for
@@ -2339,21 +2342,21 @@ __global__ void __launch_bounds__(32 * EXP_FUSED_WARPS, W ? 4 : 3) expansion_fus
 #pragma unroll
                     for (int q = 0; q < NQ / 2; q++) {
                         const uint32_t next = lds_u32(sa + o1 + 4 * q + 4);
-                        sts_u32(da + o1 + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                        sts_u32(da + o1 + 4 * q, __funnelshift_r(prev, next, sh));
                         prev = next;
                     }
                     prev = lds_u32(sa + o2);
 #pragma unroll
                     for (int q = 0; q < NQ / 2; q++) {
                         const uint32_t next = lds_u32(sa + o2 + 4 * q + 4);
-                        sts_u32(da + o2 + 4 * q, __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu);
+                        sts_u32(da + o2 + 4 * q, __funnelshift_r(prev, next, sh));
                         prev = next;
                     }
                 } else {
                     // head bytes up to the first aligned destination word, whole words, tail bytes
                     const uint8_t* const wsrc = S.win[b];
                     const uint32_t head = min(w, (4u - (d0 & 3u)) & 3u);
-                    for (uint32_t q = 0; q < head; q++) stage[d0 + q] = wsrc[s0 + q] & 0xdfu;
+                    for (uint32_t q = 0; q < head; q++) stage[d0 + q] = wsrc[s0 + q];
                     const uint32_t n_body = (w - head) >> 2, sb = s0 + head, sh = (sb & 3u) * 8u;
                     const uint32_t* sw = reinterpret_cast<const uint32_t*>(wsrc) + (sb >> 2);
                     uint32_t* dw = reinterpret_cast<uint32_t*>(stage + d0 + head);
@@ -2361,10 +2364,10 @@ __global__ void __launch_bounds__(32 * EXP_FUSED_WARPS, W ? 4 : 3) expansion_fus
 #pragma unroll 1
                     for (uint32_t q = 0; q < n_body; q++) {
                         const uint32_t next = sw[q + 1];
-                        dw[q] = __funnelshift_r(prev, next, sh) & 0xdfdfdfdfu;
+                        dw[q] = __funnelshift_r(prev, next, sh);
                         prev = next;
                     }
-                    for (uint32_t q = head + 4u * n_body; q < w; q++) stage[d0 + q] = wsrc[s0 + q] & 0xdfu;
+                    for (uint32_t q = head + 4u * n_body; q < w; q++) stage[d0 + q] = wsrc[s0 + q];
                 }
             }
             // the row's odometer digits, fastest first: digit = k mod states, k /= states; states in {2, 3, 4} and
@@ -2472,7 +2475,10 @@ __device__ __forceinline__ void scan_load_items(const uint64_t* src, uint64_t n,
 }
 
 template <int MODE, int OP = 0>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint64_t* src, uint64_t n, uint64_t* block_sums) {
+// gate / gate_gen: the kernel returns at once unless *gate == gate_gen (nullptr: always runs); see ParseParams
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint64_t* src, uint64_t n, uint64_t* block_sums,
+                                                                       const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0) {
+    if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS];
@@ -2487,7 +2493,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uin
 
 // single CTA: exclusive scan of the block sums in place
 template <int OP = 0>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* block_sums, uint64_t n_blocks) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* block_sums, uint64_t n_blocks, const unsigned long long* gate = nullptr,
+                                                                  unsigned long long gate_gen = 0) {
+    if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -2518,7 +2526,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* bloc
 // dst[0..n] = exclusive scan (dst[n] = grand total)
 template <int MODE, int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_t* src, uint64_t n, const uint64_t* block_sums,
-                                                                   uint64_t* dst) {
+                                                                   uint64_t* dst, const unsigned long long* gate = nullptr,
+                                                                   unsigned long long gate_gen = 0) {
+    if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS];
@@ -2608,7 +2618,15 @@ struct ParseParams {
     const uint64_t* offsets;     // exclusive scan of counts, [n_blocks + 1] (pass 2 in)
     uint8_t* out;
     unsigned long long* err_key;
+    // Input without whitespace whose masks land where the letters were is finished by ONE optimistic pass
+    // (parse_pass1_kernel); that pass writes `gate_gen` to *gate when it drops a byte, and only then do the
+    // scan and the compacting pass behind it run (gate == nullptr: they always run).
+    unsigned long long* gate;
+    unsigned long long gate_gen;
 };
+__device__ __forceinline__ bool parse_gate_closed(const unsigned long long* gate, unsigned long long gen) {
+    return gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gen;
+}
 
 // granule `g` (16 bytes at the 16-byte-aligned address a) of the input as table values; bytes outside [in, in+n) skip
 __device__ __forceinline__ void parse_load(const ParseParams& p, const uint8_t* tab_s, uint64_t g, uint8_t (&v)[16], uint32_t& kept,
@@ -2664,36 +2682,127 @@ __device__ __forceinline__ bool parse_granule_fast(const ParseParams& p, uint32_
     return true;
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS) parse_count_kernel(const ParseParams p, uint64_t n_blocks) {
+// Pass 1, a streaming kernel without barriers: every granule that is 16 plain nucleotide letters is translated and --
+// STORE: input and output share their 16-byte phase -- stored where it lands if nothing before it is dropped; granules
+// cut by the ends of the input go byte-wise.  Dropped bytes (blank, tab, invalid) are added to their 4-KiB block's
+// entry of `counts` (all zero when the kernel starts, and all zero again when the call is over), the first invalid byte
+// goes to the error key, and the gate opens for the scan and the compacting pass.  Input without whitespace is
+// finished here: one launch that does work, one read of the input.
+constexpr int PARSE_CLEAN_UNROLL = 4;
+template <bool STORE>
+__global__ void __launch_bounds__(PARSE_THREADS) parse_pass1_kernel(const ParseParams p, uint64_t n_gran, uint64_t* n_masks) {
     __shared__ uint8_t tab_s[256];
-    __shared__ uint64_t warp_sums[32];
     __shared__ __align__(16) uint16_t pair_s[PAIR_ENTRIES];
     tab_s[threadIdx.x] = __ldg(p.table + threadIdx.x);
     for (int i = threadIdx.x; i < (int)PAIR_ENTRIES; i += PARSE_THREADS) pair_s[i] = __ldg(p.pair + i);
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_masks) *n_masks = p.n;  // right unless the gate opens (then the compacting pass overwrites it)
     const uint32_t pair_base = smem_u32(pair_s);
-    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.in);
-    // Input without whitespace is the usual case, and then every mask lands where its letter was.  When input and output
-    // share their 16-byte phase this pass stores each clean granule there already; the second pass skips the blocks whose
-    // scanned offset confirms the guess and rewrites the rest, so the common case reads the input once.
-    const bool same_phase = ((reinterpret_cast<uintptr_t>(p.out) ^ lo) & 15u) == 0;
-    for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        uint8_t v[16];
-        uint32_t kept = 16;
-        int bad = -1;
-        const uint64_t g = blk * PARSE_THREADS + threadIdx.x;
-        uint4 fast;
-        if (!parse_granule_fast(p, pair_base, g, fast)) parse_load(p, tab_s, g, v, kept, bad);
-        else if (same_phase) stg_stream(p.out + (16 * g - (lo & 15)), fast);  // optimistic: right if nothing before it was dropped
-        if (bad >= 0) atomicMin(p.err_key, (unsigned long long)(((lo & ~(uintptr_t)15) + 16 * g + bad) - lo));
-        uint64_t total;
-        block_exclusive_scan((uint64_t)kept, &total, warp_sums);
-        if (threadIdx.x == 0) p.counts[blk] = total;
-        __syncthreads();
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p.in), hi = lo + p.n, a0 = lo & ~(uintptr_t)15;
+    uint8_t* const out0 = p.out - (lo & 15);  // granule g of the input lands at out0 + 16 g
+    bool dirty = !STORE;
+    constexpr uint64_t STEP = (uint64_t)PARSE_THREADS * PARSE_CLEAN_UNROLL;
+    for (uint64_t g0 = (uint64_t)blockIdx.x * STEP; g0 < n_gran; g0 += (uint64_t)gridDim.x * STEP) {
+        uint4 x[PARSE_CLEAN_UNROLL];
+        bool whole[PARSE_CLEAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PARSE_CLEAN_UNROLL; u++) {
+            const uint64_t g = g0 + (uint64_t)u * PARSE_THREADS + threadIdx.x;
+            const uintptr_t a = a0 + 16 * g;
+            whole[u] = g < n_gran && a >= lo && a + 16 <= hi;
+            if (whole[u]) x[u] = ldg_stream(reinterpret_cast<const void*>(a));
+        }
+#pragma unroll
+        for (int u = 0; u < PARSE_CLEAN_UNROLL; u++) {
+            const uint64_t g = g0 + (uint64_t)u * PARSE_THREADS + threadIdx.x;
+            uint32_t dropped = 0;
+            int first_bad = -1;
+            if (whole[u]) {
+                const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                uint32_t m[4], flags = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t t = w[q] & 0x1f1f1f1fu;
+                    m[q] = lds_u16(dp2a_hi(p.pair_coef, t, pair_base)) * 65536u + lds_u16(dp2a_lo(p.pair_coef, t, pair_base));
+                    flags |= m[q];
+                }
+                const uint32_t a_and = w[0] & w[1] & w[2] & w[3], a_or = w[0] | w[1] | w[2] | w[3];
+                if ((flags & (PARSE_PAIR_SLOW * 0x01010101u)) | ((a_and & 0x40404040u) ^ 0x40404040u) | (a_or & 0x80808080u)) {
+#pragma unroll
+                    for (int k = 15; k >= 0; k--) {
+                        const uint32_t t = tab_s[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+                        if (t == 0) first_bad = k;
+                        dropped += (t == 0 || t == PARSE_SKIP) ? 1u : 0u;
+                    }
+                    if (STORE && dropped == 0) stg_stream(out0 + 16 * g, make_uint4(m[0], m[1], m[2], m[3]));  // (letters the pair table leaves to the byte table)
+                } else if (STORE) {
+                    stg_stream(out0 + 16 * g, make_uint4(m[0], m[1], m[2], m[3]));
+                }
+            } else if (g < n_gran) {  // a granule cut by the start or the end of the input
+                for (int k = 15; k >= 0; k--) {
+                    const uintptr_t b = a0 + 16 * g + k;
+                    if (b < lo || b >= hi) continue;
+                    const uint32_t t = tab_s[*reinterpret_cast<const uint8_t*>(b)];
+                    if (t == 0) first_bad = k;
+                    if (t == 0 || t == PARSE_SKIP) dropped++;
+                    else if (STORE) out0[16 * g + k] = (uint8_t)t;
+                }
+            }
+            if (first_bad >= 0) atomicMin(p.err_key, (unsigned long long)((a0 + 16 * g + first_bad) - lo));
+            if (__any_sync(0xffffffffu, dropped != 0)) {  // a warp's 32 granules lie in one 4-KiB block
+                dirty = true;
+                const uint32_t sum = __reduce_add_sync(0xffffffffu, dropped);
+                if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + g / PARSE_THREADS), (unsigned long long)sum);
+            }
+        }
     }
+    if (dirty) *reinterpret_cast<volatile unsigned long long*>(p.gate) = p.gate_gen;
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseParams p, uint64_t n_blocks) {
+// offsets[0 .. n_blocks] = exclusive scan of the kept bytes per 4-KiB block (the block's bytes inside the input minus its
+// dropped bytes): one CTA, 8192 blocks per round -- only input with whitespace comes here
+constexpr int PARSE_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(PARSE_SCAN_THREADS) parse_scan_kernel(const ParseParams p, uint64_t n_blocks) {
+    if (parse_gate_closed(p.gate, p.gate_gen)) return;
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const uint64_t lead = reinterpret_cast<uintptr_t>(p.in) & 15, end = lead + p.n;  // the input in block coordinates
+    uint64_t* const offsets = const_cast<uint64_t*>(p.offsets);
+    constexpr int ITEMS = 8;
+    for (uint64_t base = 0; base < n_blocks; base += (uint64_t)PARSE_SCAN_THREADS * ITEMS) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * ITEMS;
+        uint64_t v[ITEMS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            const uint64_t i = i0 + k;
+            v[k] = 0;
+            if (i < n_blocks) {
+                const uint64_t b0 = max(i * PARSE_BLOCK_BYTES, lead), b1 = min((i + 1) * PARSE_BLOCK_BYTES, end);
+                v[k] = (b1 > b0 ? b1 - b0 : 0) - p.counts[i];
+            }
+            sum += v[k];
+        }
+        uint64_t total;
+        uint64_t ex = block_exclusive_scan(sum, &total, warp_sums);
+        const uint64_t carry = carry_s;
+        ex += carry;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            if (i0 + k < n_blocks) offsets[i0 + k] = ex;
+            ex += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n_blocks] = carry_s;
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseParams p, uint64_t n_blocks, uint64_t* n_masks) {
+    if (parse_gate_closed(p.gate, p.gate_gen)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_masks) *n_masks = p.offsets[n_blocks];
     __shared__ uint8_t tab_s[256];
     __shared__ uint64_t warp_sums[32];
     __shared__ __align__(16) uint8_t stage[PARSE_BLOCK_BYTES + 16];
@@ -2716,6 +2825,7 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseP
             // pass guessed (nothing was dropped before it): already written
             const uint64_t o0 = p.offsets[mine], o1 = p.offsets[mine + 1];
             todo = !(same_phase && o1 - o0 == PARSE_BLOCK_BYTES && o0 + (in_lo & 15) == mine * (uint64_t)PARSE_BLOCK_BYTES);
+            p.counts[mine] = 0;  // the scan has used it: all zero again for the next call
         }
         __syncthreads();  // the previous round no longer reads todo_s
         todo_s[threadIdx.x] = todo ? 1 : 0;
