@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=0)
     ap.add_argument("--revcomp-nt", type=int, default=250_000_000)
     ap.add_argument("--window-seqs", type=int, default=80_000, help="99 999-nt sequences per GPU in the config-5 legs (64 GB / 8 GPUs)")
+    ap.add_argument("--window-chunk-seqs", type=int, default=768, help="sequences per ring chunk of the canonical / all_windows legs")
+    ap.add_argument("--expansion-chunk", type=int, default=6_000_000, help="windows per ring chunk of the expansion leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -545,8 +547,8 @@ def main():
         if n_w > 0:
             nwin = seq_len - w + 1
             M = lambda t: sum(int(v) & M64 for v in t.cpu().tolist()) & M64  # noqa: E731
-            # canonical rows: 43 B per window, 336 GB of rows per GPU through two 1 GB slots
-            chunk_c = min(256, n_w)
+            # canonical rows: 43 B per window, 336 GB of rows per GPU through a two-slot ring
+            chunk_c = min(args.window_chunk_seqs, n_w)
             slot_c = (L.qd_canonical_chunk_bytes(chunk_c, seq_len, w) + 255) & ~255
             ring_c = out[: 2 * slot_c]
             B.dev_error_reset(ctx)
@@ -580,8 +582,8 @@ def main():
                 legs["canonical_keys_" + label] = {"ms": round(k_ms, 4), "GBps": round(k_gbs, 1), "frac": round(k_gbs / peak, 4)}
             extra["canonical_window_keys"] = {"workload": f"one key per canonical 42-nt window of {n_k} x {seq_len}-nt sequences per GPU (SURVEY 8(f) rank 3)",
                                               "speedup_vs_materialised_rows": {k: (cw_ms * n_k / n_w) / v["ms"] for k, v in keys.items()}, **keys}
-            # the all_windows shape: 124 output bytes per nucleotide, ~1 TB per GPU through two 3.2 GB slots
-            chunk_a = min(256, n_w)
+            # the all_windows shape: 124 output bytes per nucleotide, ~1 TB per GPU through a two-slot ring
+            chunk_a = min(args.window_chunk_seqs, 512, n_w)  # two 6.3 GB slots inside the 20 GB output buffer
             aa_off = C.c_size_t()
             slot_a = (L.qd_windows_all_chunk_bytes(chunk_a, seq_len, 42, 20, C.byref(aa_off)) + 255) & ~255
             ring_a = out[: 2 * slot_a]
@@ -617,7 +619,7 @@ def main():
             p1 = (p1 + 1 + torch.randint(0, w - 1, (n_win,), generator=g2, device=dev)) % w
             win[rows_idx, p1] = codes[torch.randint(0, 11, (n_win,), generator=g2, device=dev)]
             del p1, rows_idx
-            chunk_e = min(2_000_000, n_win)
+            chunk_e = min(args.expansion_chunk, n_win)
             slot_e = (L.qd_expansion_chunk_bytes(chunk_e, w, 16) + 255) & ~255
             ring_e = out[: 2 * slot_e]
             B.dev_error_reset(ctx)
@@ -631,8 +633,8 @@ def main():
             assert B.dev_error_fetch(win.view(-1), ctx=ctx) is None
             n_rows = int(holder["rows"].sum().item())
             r = leg("expansion_windows", f"expansions of {n_win} 42-nt windows with exactly 2 ambiguity codes, cap 16, per GPU (config 5): {n_rows} rows = "
-                    f"{n_rows * w / 1e9:.0f} GB through a ring of two {slot_e / 1e9:.2f} GB slots (per chunk: size_hint kernel + scan + row kernel)",
-                    ex_ms, n_win * w + n_rows * w, "expansion_count_tiles_kernel<ascii, 42> + scan + expansion_write_tiles_kernel<42>",
+                    f"{n_rows * w / 1e9:.0f} GB through a ring of two {slot_e / 1e9:.2f} GB slots (per chunk: ONE kernel -- size_hint, row index and rows from one read of the windows)",
+                    ex_ms, n_win * w + n_rows * w, "expansion_fused_tiles_kernel<ascii, 42>",
                     units={"rows": n_rows, "windows": n_win}, windows_per_gpu=n_win, chunk_windows=chunk_e)
             if do_checks:
                 t0 = time.perf_counter()
@@ -736,6 +738,33 @@ def main():
                 ok = all_ranks_true(got == want)
                 checks["e2e_all_host_output_bytes_equal_oracle"] = ok
                 assert ok
+        # the same call on PAGEABLE host memory (a Rust Vec<u8> / numpy array): staged through pinned buffers by host threads
+        # (default) and with the driver's own staged copies (staging off)
+        if rank == 0 and world == 1 and not args.no_extra:
+            p_in = h_in.numpy().copy()
+            p_out = np.empty(er * per, dtype=np.uint8)
+            pg = {}
+            for label, threads in (("staged_by_host_threads", -1), ("driver_staged", 0)):
+                assert L.qd_ctx_set_stage_threads(ctx.handle, threads) == 0
+
+                def p_step():
+                    rc = L.qd_translate_frames_batch_uniform(ctx.handle, args.table, N.ENC_ASCII, 0, 6, C.c_void_p(p_in.ctypes.data), er,
+                                                             READ_LEN, C.c_void_p(p_out.ctypes.data), C.byref(err))
+                    ctx.check(rc, err)
+
+                p_step()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    p_step()
+                dt = (time.perf_counter() - t0) / 2
+                pg[label] = {"value": er * READ_LEN / dt, "ms_per_step": dt * 1e3}
+                if label == "staged_by_host_threads":
+                    same = bool(np.array_equal(p_out, h_out.numpy()))
+                    checks["e2e_pageable_output_equals_pinned_output"] = same
+                    assert same
+            assert L.qd_ctx_set_stage_threads(ctx.handle, -1) == 0
+            e2e["pageable_host_memory"] = pg
+            del p_in, p_out
         # beside it: what the box itself delivers for this copy pattern, and ONE call driving all the GPUs
         host_barrier()
         if rank == 0:
@@ -777,8 +806,10 @@ def main():
             n_rc = min(args.revcomp_nt, h_in.numel())
             rc_out = h_out[:n_rc]
             res = {}
-            for label, src in (("pinned", h_in[:n_rc]), ("pageable", torch.from_numpy(h_in[:n_rc].numpy().copy()))):
+            pageable_src = torch.from_numpy(h_in[:n_rc].numpy().copy())
+            for label, src in (("pinned", h_in[:n_rc]), ("pageable", pageable_src), ("pageable_driver_staged", pageable_src)):
                 dst = rc_out if label == "pinned" else torch.empty(n_rc, dtype=torch.uint8)
+                assert L.qd_ctx_set_stage_threads(ctx.handle, 0 if label == "pageable_driver_staged" else -1) == 0
                 call = lambda: ctx.check(L.qd_revcomp(ctx.handle, N.ENC_ASCII, 0, C.c_void_p(src.data_ptr()), n_rc, C.c_void_p(dst.data_ptr()), C.byref(err)), err)  # noqa: E731
                 call()
                 t0 = time.perf_counter()
@@ -786,6 +817,9 @@ def main():
                     call()
                 dt = (time.perf_counter() - t0) / 3
                 res[label] = {"ms": dt * 1e3, "nt_per_s": n_rc / dt, "GBps_each_way": n_rc / dt / 1e9}
+                if label == "pageable":
+                    assert torch.equal(dst, rc_out)
+            assert L.qd_ctx_set_stage_threads(ctx.handle, -1) == 0
             if do_checks:
                 checks["config2_e2e_all_host_output_bytes_equal_oracle"] = oracle.checksum64(rc_out.numpy(), 0) == oracle.check_revcomp(3, rank * total_nt, n_rc, False, cpu_threads)
                 assert checks["config2_e2e_all_host_output_bytes_equal_oracle"]

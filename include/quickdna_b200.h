@@ -84,6 +84,12 @@ const char *qd_last_cuda_error(const qd_ctx *ctx);
 int qd_abi_version(void);
 /* input bytes per chunk of the host batch pipeline (default 64 MiB) */
 int qd_ctx_set_chunk_bytes(qd_ctx *ctx, size_t bytes);
+/* Host entry points take any host pointer.  Pageable buffers (a Rust Vec<u8>, Python bytes, a numpy array) of large calls
+ * (>= 32 MiB in + out) are staged through pinned buffers of the context, 16 MiB of input per chunk, filled and drained by
+ * `threads` persistent host threads, so the PCIe copies stay asynchronous; pinned (cudaHostAlloc / cudaHostRegister)
+ * buffers are copied from and to directly.  threads: -1 = half the host's hardware threads, between 2 and 8 (default);
+ * 0 = no staging (the driver's own staged copies). */
+int qd_ctx_set_stage_threads(qd_ctx *ctx, int threads);
 /* tuning / test knob: frame launches of at least `runs` 48-nt runs use the 1024-thread tile
  * (default 2 * 1024 * SM count); 0 = always, UINT64_MAX = never */
 int qd_ctx_set_big_tile_min_runs(qd_ctx *ctx, uint64_t runs);

@@ -8,9 +8,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/quickdna_b200.h"
@@ -61,9 +63,94 @@ constexpr int N_PIPE = 3;  // streams / buffer sets of the chunked host pipeline
 // memory (the reference's typical call is a 30-kb genome: launch and copy count is what it costs here)
 constexpr size_t SMALL_CALL_BYTES = size_t(2) << 20;
 
+// Pageable host memory (a Rust Vec<u8>, a Python bytes object, a numpy array) cannot be the source or target of an
+// asynchronous copy: the driver stages it through one internal buffer on the calling thread, and the chunk pipeline
+// serialises (250 M nt reverse-complemented host to host: 39 ms against 6.7 ms from pinned buffers).  Large calls on
+// pageable buffers therefore go through pinned staging buffers of the context, filled and drained by a few persistent
+// host threads (HostPool::copy), so the PCIe copies stay asynchronous and overlap with the host-side memcpy of other chunks.
+class HostPool {
+public:
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; i++) workers_.emplace_back([this, i, n] { loop(i, n); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        work_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // blocking memcpy, split over the workers
+    void copy(void* dst, const void* src, size_t n) {
+        if (n < (size_t(1) << 20) || workers_.empty()) {
+            memcpy(dst, src, n);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(m_);
+        dst_ = static_cast<uint8_t*>(dst);
+        src_ = static_cast<const uint8_t*>(src);
+        n_ = n;
+        pending_ = workers_.size();
+        gen_++;
+        work_.notify_all();
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void loop(int i, int n_workers) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+            uint8_t* const dst = dst_;
+            const uint8_t* const src = src_;
+            const size_t n = n_;
+            lk.unlock();
+            const size_t piece = ((n + n_workers - 1) / n_workers + 63) & ~size_t(63);
+            const size_t a = std::min(n, piece * i), b = std::min(n, a + piece);
+            if (b > a) memcpy(dst + a, src + a, b - a);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable work_, done_;
+    uint8_t* dst_ = nullptr;
+    const uint8_t* src_ = nullptr;
+    size_t n_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+struct PinBuf {  // grow-only pinned host buffer
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct Pipe {
     cudaStream_t stream = nullptr;
     DevBuf in, out, offsets, run_prefix, tile_first, block_sums;
+    PinBuf hin, hout;            // staging for pageable caller buffers
+    cudaEvent_t done = nullptr;  // the chunk last staged through hin / hout has left the device
 };
 
 }  // namespace
@@ -93,6 +180,9 @@ struct qd_ctx {
     DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums, parse_counts, parse_offsets, canon_state, fasta_scratch;
     Pipe pipe[N_PIPE];
     size_t chunk_bytes = size_t(64) << 20;   // input bytes per pipeline chunk
+    HostPool* pool = nullptr;                // host threads of the pageable staging path, started on first use
+    int stage_threads = -1;                  // -1: pick from the host's thread count; 0: no staging (plain copies)
+    size_t stage_chunk_bytes = size_t(16) << 20;  // input bytes per chunk when staging (bounds the pinned memory)
     int occ_frames[6] = {0, 0, 0, 0, 0, 0};  // [tile size][frames]
     uint64_t big_tile_min_runs = 0;           // launches with at least this many runs use 1024-thread tiles
     int occ_revcomp[2] = {0, 0};  // [small, big tile]
@@ -587,8 +677,12 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     for (int i = 0; i < N_PIPE; i++) {
         Pipe& P = c->pipe[i];
         for (DevBuf* b : {&P.in, &P.out, &P.offsets, &P.run_prefix, &P.tile_first, &P.block_sums}) b->release();
+        P.hin.release();
+        P.hout.release();
+        if (P.done) cudaEventDestroy(P.done);
         if (P.stream) cudaStreamDestroy(P.stream);
     }
+    delete c->pool;
     if (c->d_lut) cudaFree(c->d_lut);
     if (c->d_tables) cudaFree(c->d_tables);
     if (c->d_pair) cudaFree(c->d_pair);
@@ -621,6 +715,14 @@ extern "C" int qd_ctx_set_big_tile_min_runs(qd_ctx* c, uint64_t runs) {
 extern "C" int qd_ctx_set_chunk_bytes(qd_ctx* c, size_t bytes) {
     if (!c || bytes < (size_t(1) << 16)) return QD_ERR_INVALID_ARGUMENT;
     c->chunk_bytes = bytes;
+    return QD_OK;
+}
+extern "C" int qd_ctx_set_stage_threads(qd_ctx* c, int threads) {
+    if (!c || threads < -1 || threads > 64) return QD_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(c->mu);
+    delete c->pool;
+    c->pool = nullptr;
+    c->stage_threads = threads;
     return QD_OK;
 }
 
@@ -1041,6 +1143,148 @@ extern "C" int qd_canonical(qd_ctx* c, int enc, int forward_only, const uint8_t*
 static_assert(sizeof(qd_fasta_record) == sizeof(FastaRecord), "qd_fasta_record and the kernel's record must agree");
 
 namespace {
+// ---- pageable caller buffers: staging through pinned memory (see HostPool) --------------------------------------------------
+static bool host_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();  // (older drivers report unregistered memory as an error)
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static HostPool* stage_pool(qd_ctx* c) {
+    if (!c->pool) {
+        int t = c->stage_threads;
+        if (t < 0) t = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+        c->pool = new HostPool(t);
+    }
+    return c->pool;
+}
+static int pipe_event(qd_ctx* c, Pipe& P) {
+    if (!P.done) QD_CUDA(c, cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+    return QD_OK;
+}
+constexpr size_t STAGE_MIN_BYTES = size_t(32) << 20;  // smaller calls: the driver's own staging is as good
+
+// One chunked host call.  Per chunk on pipe p:  begin(p) -- the chunk this pipe staged before has left the device, its
+// output is copied to the caller --, h2d, kernels, d2h..., end(p).  finish() drains what is still staged.  With pinned
+// caller buffers (or staging off) every call is the plain asynchronous copy.
+struct Stager {
+    struct Seg {
+        uint8_t* dst;
+        size_t off, n;
+    };
+    qd_ctx* c;
+    bool in_staged = false, out_staged = false;
+    std::vector<Seg> segs[N_PIPE];
+    size_t out_used[N_PIPE] = {};
+    bool busy[N_PIPE] = {};
+    Stager(qd_ctx* c_, const void* in, const void* out, uint64_t total_bytes) : c(c_) {
+        const bool on = c->stage_threads != 0 && total_bytes >= STAGE_MIN_BYTES;
+        in_staged = on && in && host_pageable(in);
+        out_staged = on && out && host_pageable(out);
+    }
+    bool active() const { return in_staged || out_staged; }
+    size_t chunk_bytes() const { return active() ? std::min(c->chunk_bytes, c->stage_chunk_bytes) : c->chunk_bytes; }
+    int begin(int p) {
+        if (!busy[p]) return QD_OK;
+        QD_CUDA(c, cudaEventSynchronize(c->pipe[p].done));
+        for (const Seg& g : segs[p]) stage_pool(c)->copy(g.dst, c->pipe[p].hout.p + g.off, g.n);
+        segs[p].clear();
+        out_used[p] = 0;
+        busy[p] = false;
+        return QD_OK;
+    }
+    // the chunk's payload (once per chunk: the staging buffer holds one)
+    int h2d(int p, void* dev, const uint8_t* host, size_t n) {
+        Pipe& P = c->pipe[p];
+        if (in_staged) {
+            QD_CUDA(c, P.hin.reserve(n));
+            stage_pool(c)->copy(P.hin.p, host, n);
+            host = P.hin.p;
+        }
+        QD_CUDA(c, cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, P.stream));
+        return QD_OK;
+    }
+    int d2h_reserve(int p, size_t total, size_t pieces = 1) {
+        if (out_staged) QD_CUDA(c, c->pipe[p].hout.reserve(total + 64 * pieces));
+        return QD_OK;
+    }
+    int d2h(int p, uint8_t* host, const void* dev, size_t n) {
+        Pipe& P = c->pipe[p];
+        if (!out_staged) {
+            QD_CUDA(c, cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, P.stream));
+            return QD_OK;
+        }
+        QD_CUDA(c, cudaMemcpyAsync(P.hout.p + out_used[p], dev, n, cudaMemcpyDeviceToHost, P.stream));
+        segs[p].push_back({host, out_used[p], n});
+        out_used[p] += (n + 63) & ~size_t(63);
+        return QD_OK;
+    }
+    int end(int p) {
+        if (!active()) return QD_OK;
+        Pipe& P = c->pipe[p];
+        if (int rc = pipe_event(c, P)) return rc;
+        QD_CUDA(c, cudaEventRecord(P.done, P.stream));
+        busy[p] = true;
+        return QD_OK;
+    }
+    int finish(int next_turn) {
+        for (int k = 0; k < N_PIPE; k++)
+            if (int rc = begin((next_turn + k) % N_PIPE)) return rc;  // oldest chunk first
+        return QD_OK;
+    }
+};
+
+// one large buffer up / down on stream s through the pipes' staging buffers (plain copy when pinned or small)
+static int staged_upload(qd_ctx* c, void* dev, const uint8_t* host, size_t n, cudaStream_t s) {
+    if (c->stage_threads == 0 || n < STAGE_MIN_BYTES || !host_pageable(host)) {
+        QD_CUDA(c, cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, s));
+        return QD_OK;
+    }
+    const size_t chunk = c->stage_chunk_bytes;
+    int k = 0;
+    for (size_t off = 0; off < n; off += chunk, k++) {
+        Pipe& P = c->pipe[k % N_PIPE];
+        const size_t len = std::min(chunk, n - off);
+        if (int rc = pipe_event(c, P)) return rc;
+        if (k >= N_PIPE) QD_CUDA(c, cudaEventSynchronize(P.done));
+        QD_CUDA(c, P.hin.reserve(len));
+        stage_pool(c)->copy(P.hin.p, host + off, len);
+        QD_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(dev) + off, P.hin.p, len, cudaMemcpyHostToDevice, s));
+        QD_CUDA(c, cudaEventRecord(P.done, s));
+    }
+    return QD_OK;
+}
+// synchronises s
+static int staged_download(qd_ctx* c, uint8_t* host, const void* dev, size_t n, cudaStream_t s) {
+    if (c->stage_threads == 0 || n < STAGE_MIN_BYTES || !host_pageable(host)) {
+        QD_CUDA(c, cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        return QD_OK;
+    }
+    const size_t chunk = c->stage_chunk_bytes;
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    for (size_t k = 0; k < n_chunks + N_PIPE; k++) {
+        if (k >= N_PIPE) {  // drain chunk k - N_PIPE
+            Pipe& Q = c->pipe[k % N_PIPE];
+            const size_t off = (k - N_PIPE) * chunk;
+            QD_CUDA(c, cudaEventSynchronize(Q.done));
+            stage_pool(c)->copy(host + off, Q.hout.p, std::min(chunk, n - off));
+        }
+        if (k < n_chunks) {
+            Pipe& P = c->pipe[k % N_PIPE];
+            const size_t off = k * chunk, len = std::min(chunk, n - off);
+            if (int rc = pipe_event(c, P)) return rc;
+            QD_CUDA(c, P.hout.reserve(len));
+            QD_CUDA(c, cudaMemcpyAsync(P.hout.p, static_cast<const uint8_t*>(dev) + off, len, cudaMemcpyDeviceToHost, s));
+            QD_CUDA(c, cudaEventRecord(P.done, s));
+        }
+    }
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    return QD_OK;
+}
+
 struct FastaRun {
     FastaParams p{};
     uint64_t* pre_base = nullptr;  // device: blk_last | blk_state | cnt x3 | pre x3
@@ -1119,7 +1363,7 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
     QD_CUDA(c, c->in.reserve(n + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, text, n, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, text, n, s)) return rc;
     if (int rc = reset_err_key(c, s)) return rc;
     FastaRun R;
     if (int rc = fasta_count_dev(c, strict, concatenate_headers, allow_preceding_comment, c->in.as<uint8_t>(), n, R, s)) return rc;
@@ -1156,8 +1400,9 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
     QD_CUDA(c, c->out.reserve(total_kept + 16));
     QD_CUDA(c, c->aux0.reserve((total_records + 1) * sizeof(FastaRecord)));
     if (int rc = fasta_write_dev(c, R, c->out.as<uint8_t>(), c->aux0.as<FastaRecord>(), total_records, total_records, shift, s)) return rc;
-    if (total_kept) QD_CUDA(c, cudaMemcpyAsync(masks, c->out.p, total_kept, cudaMemcpyDeviceToHost, s));
     if (total_records) QD_CUDA(c, cudaMemcpyAsync(records, c->aux0.p, total_records * sizeof(FastaRecord), cudaMemcpyDeviceToHost, s));
+    if (total_kept)
+        if (int rc = staged_download(c, masks, c->out.p, total_kept, s)) return rc;
     QD_CUDA(c, cudaStreamSynchronize(s));
     return QD_OK;
 }
@@ -1399,8 +1644,8 @@ extern "C" int qd_windows_all_chunked_dev(qd_ctx* c, int enc, const uint8_t* dna
 // ---- one long sequence through the pipe streams --------------------------------------------------------------------------
 // Chunk size for a sequence of n bytes: a multiple of 48 (whole runs, whole codons, whole 16-byte granules), small enough
 // that the pipeline fills quickly, at most the context's chunk size.
-static uint64_t long_chunk_nt(const qd_ctx* c, uint64_t n) {
-    uint64_t ch = std::min<uint64_t>(c->chunk_bytes, std::max<uint64_t>(uint64_t(4) << 20, n / 16));
+static uint64_t long_chunk_nt(const qd_ctx* c, uint64_t n, uint64_t chunk_bytes = 0) {
+    uint64_t ch = std::min<uint64_t>(chunk_bytes ? chunk_bytes : c->chunk_bytes, std::max<uint64_t>(uint64_t(4) << 20, n / 16));
     return std::max<uint64_t>(RUN_NT, ch / RUN_NT * RUN_NT);
 }
 static bool long_call(const qd_ctx* c, uint64_t n) {
@@ -1415,19 +1660,23 @@ static bool long_call(const qd_ctx* c, uint64_t n) {
 // Error keys are global positions.  The caller resets / fetches the error key and synchronises the pipe streams.
 static int frames_long_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna, uint64_t n, uint64_t lo, uint64_t hi,
                                 uint8_t* out, const size_t frame_at[6]) {
-    const uint64_t chunk = long_chunk_nt(c, n);
+    Stager st(c, dna + lo, out, 2 * (hi - lo));
+    const uint64_t chunk = long_chunk_nt(c, n, st.chunk_bytes());
     int turn = 0;
     for (uint64_t a = lo; a < hi; a += chunk) {
         const uint64_t b = std::min(hi, a + chunk), read_end = std::min<uint64_t>(n, b + 2), n_local = read_end - a, d = n - read_end;
-        Pipe& P = c->pipe[turn++ % N_PIPE];
+        const int pi = turn++ % N_PIPE;
+        Pipe& P = c->pipe[pi];
         cudaStream_t s = P.stream;
         tls_stream = s;
+        if (int rc = st.begin(pi)) return rc;
         const size_t slot_bytes = qd_slots_bytes(n_local, frames);
         QD_CUDA(c, P.in.reserve(n_local + 16));
         QD_CUDA(c, P.out.reserve(slot_bytes + 16));
-        QD_CUDA(c, cudaMemcpyAsync(P.in.p, dna + a, n_local, cudaMemcpyHostToDevice, s));
+        if (int rc = st.h2d(pi, P.in.p, dna + a, n_local)) return rc;
         if (int rc = frames_uniform_dev(c, slot, enc, strict, frames, P.in.as<uint8_t>(), 1, n_local, P.out.as<uint8_t>(), s, a)) return rc;
         const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
+        if (int rc = st.d2h_reserve(pi, slot_bytes, 6)) return rc;
         for (int f = 0; f < n_slots; f++) {
             const size_t len = qd_frame_len(n_local, f % 3);
             if (!len) continue;
@@ -1435,30 +1684,36 @@ static int frames_long_pipeline(qd_ctx* c, int slot, int enc, int strict, int fr
             uint8_t* dst;
             if (f < 3) dst = out + frame_at[f] + a / 3;
             else dst = out + frame_at[3 + (f - 3 + d) % 3] + (f - 3 + d) / 3;
-            QD_CUDA(c, cudaMemcpyAsync(dst, src, len, cudaMemcpyDeviceToHost, s));
+            if (int rc = st.d2h(pi, dst, src, len)) return rc;
         }
+        if (int rc = st.end(pi)) return rc;
     }
     tls_stream = c->stream;
-    return QD_OK;
+    return st.finish(turn);
 }
 
 // out[n - b, n - a) = reverse complement of dna[a, b) for the chunks [a, b) of [lo, hi)
 static int revcomp_long_pipeline(qd_ctx* c, int which, const uint8_t* dna, uint64_t n, uint64_t lo, uint64_t hi, uint8_t* out) {
-    const uint64_t chunk = long_chunk_nt(c, n);
+    Stager st(c, dna + lo, out, 2 * (hi - lo));
+    const uint64_t chunk = long_chunk_nt(c, n, st.chunk_bytes());
     int turn = 0;
     for (uint64_t a = lo; a < hi; a += chunk) {
         const uint64_t b = std::min(hi, a + chunk), len = b - a;
-        Pipe& P = c->pipe[turn++ % N_PIPE];
+        const int pi = turn++ % N_PIPE;
+        Pipe& P = c->pipe[pi];
         cudaStream_t s = P.stream;
         tls_stream = s;
+        if (int rc = st.begin(pi)) return rc;
         QD_CUDA(c, P.in.reserve(len + 16));
         QD_CUDA(c, P.out.reserve(len + 16));
-        QD_CUDA(c, cudaMemcpyAsync(P.in.p, dna + a, len, cudaMemcpyHostToDevice, s));
+        if (int rc = st.h2d(pi, P.in.p, dna + a, len)) return rc;
         if (int rc = revcomp_dev_table(c, which, P.in.as<uint8_t>(), len, P.out.as<uint8_t>(), s, nullptr, a)) return rc;
-        QD_CUDA(c, cudaMemcpyAsync(out + (n - b), P.out.p, len, cudaMemcpyDeviceToHost, s));
+        if (int rc = st.d2h_reserve(pi, len)) return rc;
+        if (int rc = st.d2h(pi, out + (n - b), P.out.p, len)) return rc;
+        if (int rc = st.end(pi)) return rc;
     }
     tls_stream = c->stream;
-    return QD_OK;
+    return st.finish(turn);
 }
 
 static int pipes_begin(qd_ctx* c) {
@@ -1643,14 +1898,16 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
     size_t r0 = 0;
     int turn = 0;
     const uint64_t uni_out = uniform ? stride * qd_runs(uniform_len) : 0;
+    Stager st(c, dna, out, total_nt + (uniform ? (uint64_t)n_seq * uni_out : oo[n_seq]));
+    const size_t chunk_bytes = st.chunk_bytes();
     while (r0 < n_seq) {
         // pick [r0, r1): whole sequences, about chunk_bytes of input (at least one sequence)
         size_t r1;
         if (uniform) {
-            const size_t per = std::max<size_t>(1, uniform_len ? c->chunk_bytes / uniform_len : n_seq);
+            const size_t per = std::max<size_t>(1, uniform_len ? chunk_bytes / uniform_len : n_seq);
             r1 = std::min(n_seq, r0 + per);
         } else {
-            const uint64_t target = offsets[r0] + c->chunk_bytes;
+            const uint64_t target = offsets[r0] + chunk_bytes;
             r1 = (size_t)(std::upper_bound(offsets + r0 + 1, offsets + n_seq + 1, target) - offsets) - 1;
             r1 = std::min(n_seq, std::max(r1, r0 + 1));
         }
@@ -1659,13 +1916,16 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
         const uint64_t in_bytes = uniform ? (uint64_t)cnt * uniform_len : offsets[r1] - offsets[r0];
         const uint64_t out0 = uniform ? (uint64_t)r0 * uni_out : oo[r0];
         const uint64_t out_bytes = uniform ? (uint64_t)cnt * uni_out : oo[r1] - oo[r0];
-        Pipe& P = c->pipe[turn % N_PIPE];
+        const int pi = turn % N_PIPE;
+        Pipe& P = c->pipe[pi];
         turn++;
         cudaStream_t s = P.stream;
         tls_stream = s;  // this pipe's buffers grow on its own stream
+        if (int rc = st.begin(pi)) return rc;
         QD_CUDA(c, P.in.reserve(in_bytes + 16));
         QD_CUDA(c, P.out.reserve(out_bytes + 16));
-        if (in_bytes) QD_CUDA(c, cudaMemcpyAsync(P.in.p, dna + (uniform ? in0 : in0 - offsets[0]), in_bytes, cudaMemcpyHostToDevice, s));
+        if (in_bytes)
+            if (int rc = st.h2d(pi, P.in.p, dna + (uniform ? in0 : in0 - offsets[0]), in_bytes)) return rc;
         int rc;
         if (uniform) {
             rc = frames_uniform_dev(c, slot, enc, strict, frames, P.in.as<uint8_t>(), cnt, uniform_len, P.out.as<uint8_t>(), s, in0);
@@ -1677,9 +1937,14 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
                                 P.tile_first, P.block_sums, P.out.as<uint8_t>(), s, in0, in0 - offsets[0]);
         }
         if (rc) return rc;
-        if (out_bytes) QD_CUDA(c, cudaMemcpyAsync(out + out0, P.out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+        if (out_bytes) {
+            if (int rc2 = st.d2h_reserve(pi, out_bytes)) return rc2;
+            if (int rc2 = st.d2h(pi, out + out0, P.out.p, out_bytes)) return rc2;
+        }
+        if (int rc2 = st.end(pi)) return rc2;
         r0 = r1;
     }
+    if (int rc = st.finish(turn)) return rc;
     for (int i = 0; i < N_PIPE; i++) QD_CUDA(c, cudaStreamSynchronize(c->pipe[i].stream));
     tls_stream = c->stream;
     unsigned long long key = 0;

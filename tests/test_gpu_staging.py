@@ -1,0 +1,117 @@
+"""Pageable caller buffers: large host calls are staged through pinned buffers of the context by a few host threads
+(qd_ctx_set_stage_threads).  Every staged result must equal the result of the plain (driver-staged) copies and the
+oracle's, byte for byte.  Needs a B200: -m gpu."""
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def N():
+    from quickdna_b200 import _native
+
+    return _native
+
+
+@pytest.fixture(scope="module")
+def B():
+    from quickdna_b200 import batch
+
+    return batch
+
+
+@pytest.fixture()
+def ctx(N):
+    c = N.Context(0)
+    yield c
+    c.close()
+
+
+def _staged_and_plain(N, ctx, call):
+    """call() -> bytes-like result; run with staging on (3 threads), then off."""
+    L = N.lib()
+    assert L.qd_ctx_set_stage_threads(ctx.handle, 3) == 0
+    a = call()
+    assert L.qd_ctx_set_stage_threads(ctx.handle, 0) == 0
+    b = call()
+    assert L.qd_ctx_set_stage_threads(ctx.handle, -1) == 0
+    return a, b
+
+
+def test_uniform_batch_staged_equals_plain_and_oracle(N, B, ctx):
+    n_reads, L_ = 20_011, 1000  # 20 MB in + 40 MB out: above the staging threshold, several 16-MiB chunks
+    reads = oracle.synth(3, 0, n_reads * L_).reshape(n_reads, L_)  # pageable numpy memory
+    a, b = _staged_and_plain(N, ctx, lambda: B.translate_frames_batch(reads, table=1, frames=6, ctx=ctx).data.copy())
+    assert np.array_equal(a, b)
+    assert oracle.checksum64(a, 0) == oracle.check_frames_uniform(3, 0, n_reads, L_, 0, 6, _threads())
+
+
+def test_csr_batch_staged_equals_plain(N, B, ctx):
+    rng = np.random.default_rng(4)
+    lens = rng.integers(1, 3000, 16_000)
+    offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    flat = oracle.synth(5, 0, int(offs[-1]))
+    a, b = _staged_and_plain(N, ctx, lambda: B.translate_frames_batch((flat, offs), table=11, frames=6, ctx=ctx).data.copy())
+    assert np.array_equal(a, b)
+    res = B.translate_frames_batch((flat, offs), table=11, frames=6, ctx=ctx)
+    for i in (0, 1, 7777, len(lens) - 1):
+        assert res.sequence_frames(i) == oracle.py_all_frames(11, flat[int(offs[i]):int(offs[i + 1])].tobytes())
+
+
+@pytest.mark.parametrize("n", [40_000_000, 33_554_433])
+def test_long_revcomp_and_frames_staged(N, B, ctx, n):
+    dna = oracle.synth(3, 0, n)
+    a, b = _staged_and_plain(N, ctx, lambda: B.revcomp(dna, ctx=ctx).copy())
+    assert np.array_equal(a, b)
+    assert oracle.checksum64(a, 0) == oracle.check_revcomp(3, 0, n, False, _threads())
+    fa, fb = _staged_and_plain(N, ctx, lambda: B.translate_frames(dna, table=1, frames=6, ctx=ctx))
+    assert len(fa) == len(fb) == 6
+    for x, y in zip(fa, fb):
+        assert x == y
+    want = oracle.py_all_frames(1, dna[:30_000].tobytes())
+    assert bytes(fa[0][:9000]) == want[0][:9000]
+
+
+def test_error_position_through_the_staged_path(N, B, ctx):
+    n_reads, L_ = 40_000, 1000
+    reads = oracle.synth(3, 0, n_reads * L_).reshape(n_reads, L_).copy()
+    reads[31_337, 501] = ord("!")
+    assert N.lib().qd_ctx_set_stage_threads(ctx.handle, 2) == 0
+    with pytest.raises(ValueError) as ei:
+        B.translate_frames_batch(reads, table=1, frames=6, ctx=ctx)
+    assert (ei.value.seq_index, ei.value.pos, ei.value.kind) == (31_337, 501, 2)
+
+
+def test_fasta_text_staged(N, B, ctx):
+    rec = 20_000
+    lines = []
+    body = oracle.synth(7, 0, rec * 1960).reshape(rec, 28, 70)
+    for i in range(rec):
+        lines.append(b">r%d\n" % i)
+        lines.append(b"\n".join(body[i, k].tobytes() for k in range(28)) + b"\n")
+    text = b"".join(lines)  # ~ 40 MB
+    assert len(text) > (32 << 20)
+    L = N.lib()
+    assert L.qd_ctx_set_stage_threads(ctx.handle, 3) == 0
+    ra = B.fasta_scan(text, ctx=ctx)
+    assert L.qd_ctx_set_stage_threads(ctx.handle, 0) == 0
+    rb = B.fasta_scan(text, ctx=ctx)
+    assert len(ra) == len(rb) == rec
+    assert np.array_equal(ra.masks, rb.masks)
+    assert ra.masks.size == rec * 1960
+    assert oracle.ascii_of(ra.masks[:1960]) == body[0].tobytes()
