@@ -403,11 +403,15 @@ def main():
         barrier()
         t_ms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
         if ncu_legs:  # one more call, alone inside a profiler range: `ncu --profile-from-start off` sees each leg's kernels in order
+            before = ctx.launch_count
             torch.cuda.profiler.start()
             fn()
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
+            ncu_calls.append(ctx.launch_count - before)
         return t_ms
+
+    ncu_calls = []  # kernel launches of every call profiled under QD_BENCH_NCU_LEGS, in order (profiles/legs_traffic.py cuts the ncu list with it)
 
     def leg(name, workload, t_ms, algo_bytes, kernel, units=None, **more):
         """One leg: full record in `extra`, compact (ms, GB/s, frac of the measured HBM peak) in roofline.legs."""
@@ -418,6 +422,8 @@ def main():
         for k, v in (units or {}).items():
             rec[k + "_per_s"] = world * v / (t_ms * 1e-3)
         rec.update(more)
+        if ncu_legs and ncu_calls:
+            rec["ncu_call_index"] = len(ncu_calls) - 1  # the profiled call that belongs to this leg
         extra[name] = rec
         legs[name] = {"ms": round(t_ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
         return rec
@@ -576,6 +582,7 @@ def main():
                 k_ms = timed(lambda: B.canonical_window_keys_dev(x, n_k, seq_len, w, kind=kind, out=kout, ctx=ctx), reps=2, warm=1)
                 k_gbs = n_k * nwin * (1 + kb) / (k_ms * 1e-3) / 1e9
                 keys[label] = {"ms": k_ms, "windows_per_s": world * n_k * nwin / (k_ms * 1e-3), "key_bytes": kb, "sequences_per_gpu": n_k,
+                               **({"ncu_call_index": len(ncu_calls) - 1} if ncu_legs and ncu_calls else {}),
                                "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": None,
                                             "kernel": f"canonical_tile_kernel<3, 42, {kind}>", "algorithmic_bytes_per_launch": n_k * nwin * (1 + kb),
                                             "note": "ALU-bound, not HBM-bound"}}
@@ -839,6 +846,8 @@ def main():
                "sample": f"{n_cpu} of the {CONFIG3_READS} reads x {READ_LEN} nt x {reps} reps ({s1:.1f} s), oracle/qd_oracle.c (C port of the Rust loops), one thread",
                "all_threads": {"value": vN, "cores": threads_all, "seconds": sN}}
 
+    if ncu_legs:
+        extra["_ncu_calls"] = ncu_calls
     fill_leg_traffic(extra)
     roofline["legs"] = legs
     if rank == 0:
