@@ -1,5 +1,5 @@
 """bench.py pieces that need no GPU: the reference arm's JSON line, the cached synthetic CPU input, and the per-leg DRAM
-traffic table (profiles/traffic_r01.json) being picked up for legs measured on the captured workload."""
+traffic table (profiles/traffic_rNN.json, newest first) being picked up for legs measured on the captured workload."""
 import json
 import os
 import subprocess
@@ -41,8 +41,9 @@ def test_cpu_input_is_the_counter_based_stream_and_is_cached():
 
 
 def test_leg_traffic_is_filled_only_for_the_captured_workload():
-    with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-        legs = json.load(f)["legs"]
+    table, src = bench._traffic_table()  # the newest committed capture: what bench.py itself reads
+    assert src == "profiles/" + bench.TRAFFIC_FILES[0]
+    legs = table["legs"]
     name = "translate_self_frames"
     algo = legs[name]["algorithmic_bytes_per_launch"]
     extra = {name: {"roofline": {"traffic": None, "algorithmic_bytes_per_launch": algo}},
@@ -57,3 +58,6 @@ def test_leg_traffic_is_filled_only_for_the_captured_workload():
     for leg in ("translate_1_frame", "translate_self_frames", "all_frames_strict", "canonical_windows", "windows_all"):
         e = legs[leg]
         assert 0.95 < (e["dram_read"] + e["dram_write"]) / e["algorithmic_bytes_per_launch"] < 1.02, leg
+    # round 2: the expansion path reads its windows once (1.26 x algorithmic with the two-pass form)
+    e = legs["expansion_windows"]
+    assert (e["dram_read"] + e["dram_write"]) / e["algorithmic_bytes_per_launch"] < 1.05
