@@ -256,7 +256,9 @@ int qd_translate_frames_batch_uniform_dev(qd_ctx *ctx, int table, int enc, int s
 int qd_translate_frames_batch_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
                                   const uint8_t *dna_dev, const uint64_t *offsets_dev,
                                   size_t n_seq, size_t total_nt, uint8_t *out_dev, void *stream);
-/* n_masks_dev: device uint64 receiving the mask count (may be NULL) */
+/* n_masks_dev: device uint64 receiving the mask count (may be NULL).  Input without blanks and tabs whose output shares
+ * the input's 16-byte phase (both 16-byte aligned, say) is finished by one streaming pass; anything else runs the scan and
+ * the compacting pass behind it (three launches either way; the last two return at once when not needed). */
 int qd_parse_dev(qd_ctx *ctx, int strict, const uint8_t *ascii_dev, size_t n, uint8_t *masks_dev,
                  uint64_t *n_masks_dev, void *stream);
 int qd_canonical_dev(qd_ctx *ctx, int enc, int forward_only, const uint8_t *dna_dev, size_t n,
@@ -291,7 +293,9 @@ int qd_canonical_window_keys_dev(qd_ctx *ctx, int enc, int forward_only, int kin
                                  size_t n_seq, size_t seq_len, size_t w, void *keys_dev, void *stream);
 /* expansions on device buffers (w <= 64, max_expansions < 128): counts_dev[n_win], out_index_dev[n_win + 1] (device
  * uint64; skipped windows repeat the next index), rows into out_dev while they fit out_capacity_rows
- * (out_index_dev[n_win] tells how many there are).  out_dev may be NULL: counts and indices only. */
+ * (out_index_dev[n_win] tells how many there are).  out_dev may be NULL: counts and indices only.
+ * ONE kernel, one read of the windows: the row index is a chained scan over 32-window tiles inside the kernel that
+ * writes the rows (rows still land in window order, whatever order the tiles finish in). */
 int qd_expansion_windows_dev(qd_ctx *ctx, int enc, const uint8_t *windows_dev, size_t n_win, size_t w,
                              uint64_t max_expansions, uint64_t *counts_dev, uint64_t *out_index_dev,
                              uint8_t *out_dev, uint64_t out_capacity_rows, void *stream);
