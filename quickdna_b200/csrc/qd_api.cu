@@ -1429,7 +1429,7 @@ static int windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, ui
 // windows of n_seq sequences (sequence s at src + s * stride, `len` bytes each), see windows_batch_kernel
 static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride, size_t n_seq, size_t len, size_t w, int mode,
                              uint8_t* out_dev, uint64_t key_stride, cudaStream_t s) {
-    if (w < 1 || w > 64 || len > 0xffffffffull || mode < QD_WIN_COPY || mode > QD_WIN_MASK_ASCII_RC) return QD_ERR_INVALID_ARGUMENT;
+    if (w < 1 || w > 64 || len > 0xffffffffull || n_seq >= 0xffffffffull || mode < QD_WIN_COPY || mode > QD_WIN_MASK_ASCII_RC) return QD_ERR_INVALID_ARGUMENT;
     if (len < w || n_seq == 0) return QD_OK;
     static const int map_tab[5] = {-1, TAB_UPPER_ASCII_STRICT, TAB_RC_ASCII_STRICT, TAB_MASK_TO_ASCII_STRICT, TAB_RC_MASK_TO_ASCII_STRICT};
     WindowsBatchParams p{};
@@ -1444,7 +1444,7 @@ static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride,
     p.key_stride = key_stride;
     p.err_key = c->d_err;
     const uint64_t wpt = w == 42 ? WinTile<42>::WPT : (w == 20 ? WinTile<20>::WPT : WinTile<0>::WPT);
-    const uint64_t tiles = (uint64_t)n_seq * ((len - w + 1 + wpt - 1) / wpt);
+    const uint64_t tiles = (uint64_t)n_seq * (1 + (len - w + 1 + wpt - 1) / wpt);  // + the short first tile of every sequence
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + WIN_WARPS - 1) / WIN_WARPS, (uint64_t)c->sm_count * 6));
     // the two window lengths of benches/all_windows.rs get fully unrolled instantiations
     if (w == 42) windows_batch_kernel<42><<<grid, 32 * WIN_WARPS, 0, s>>>(p);

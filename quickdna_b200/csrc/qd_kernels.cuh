@@ -1124,8 +1124,25 @@ __device__ __forceinline__ void windows_copy_row(const uint8_t* srcb, uint8_t* s
     }
 }
 
+// where tiles start so that their rows fill whole 128-byte lines of the output (see the kernel)
+struct WinAlign {
+    uint32_t g_shift, A, P, inv;
+    __host__ __device__ constexpr explicit WinAlign(uint32_t w) : g_shift(0), A(0), P(0), inv(0) {
+        uint32_t g = 0;
+        while (g < 7 && ((w >> g) & 1u) == 0) g++;
+        g_shift = g;
+        A = (64u << g) < 128u ? (64u << g) : 128u;
+        P = A >> g;
+        const uint32_t x = w >> g;  // odd; its inverse modulo 2^12 by two Newton steps
+        uint32_t i = x;
+        i *= 2u - x * i;
+        i *= 2u - x * i;
+        inv = i;
+    }
+};
+
 template <int W>
-__global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const WindowsBatchParams p) {
+__global__ void __launch_bounds__(32 * WIN_WARPS, W ? 6 : 4) windows_batch_kernel(const WindowsBatchParams p) {
     __shared__ WinWarpSmem SM[WIN_WARPS];
     __shared__ uint8_t map_s[256];
     for (int i = threadIdx.x; i < 256; i += 32 * WIN_WARPS) map_s[i] = p.map ? __ldg(p.map + i) : (uint8_t)i;
@@ -1135,16 +1152,29 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
     constexpr uint32_t WPT = WinTile<W>::WPT;
     constexpr bool TMA_OUT = QD_WIN_TMA_STORE && WinTile<W>::GROUPS > 1;  // bulk-copy the rows out when a tile is large enough to pay for it
     const uint32_t w = W ? (uint32_t)W : p.w, nw = p.len - w + 1;
-    const uint32_t tiles_per_seq = (nw + WPT - 1) / WPT;
-    const uint64_t n_tiles = p.n_seq * tiles_per_seq;
-    const uint64_t warps_total = (uint64_t)gridDim.x * WIN_WARPS;
-    uint64_t tile = (uint64_t)blockIdx.x * WIN_WARPS + (threadIdx.x >> 5);
-    uint64_t s = tile / tiles_per_seq;
-    uint32_t t = (uint32_t)(tile % tiles_per_seq);
-    const uint64_t step_s = warps_total / tiles_per_seq;
-    const uint32_t step_t = (uint32_t)(warps_total % tiles_per_seq);
-    for (; tile < n_tiles; tile += warps_total) {
-        const uint32_t i0 = t * WPT, cnt = min(WPT, nw - i0), span = cnt + w - 1;
+    // Tiles are cut where the OUTPUT crosses a 128-byte line: window g of the batch starts at byte g * w, so every tile but a
+    // sequence's first starts at a batch-wide window index that is a multiple of P = A / gcd(w, A), A = 128 (64 for odd w:
+    // P must divide the tile); the first tile of a sequence takes the 0 .. P - 1 windows in front of that.  Then a tile's
+    // rows fill whole lines, nothing is written byte-wise but a sequence's first and last granule, and no two warps share
+    // a line.  Measured, w = 42, 512 x ~100 000 nt: 0.78-0.81 of the copy peak when tiles start wherever a sequence starts
+    // (or on 16-byte granules only), 0.88-0.89 when they start on lines.
+    //   (out + g * w) % A == 0  <=>  g = -(phase / G) * inverse(w / G)  mod P,  G = gcd(w, A) = 1 << g_shift -- when G divides
+    //   the phase of the buffer at all (else tiles start with the sequences)
+    // (compile-time constants for the unrolled window lengths: the kernel has no register to spare -- at 48 instead of 40
+    // registers, five instead of six CTAs per SM, w = 42 drops from 0.89 to 0.63 of the copy peak)
+    const WinAlign al = W ? WinAlign(W) : WinAlign(w);
+    const uint32_t g_shift = al.g_shift, A = al.A, P = al.P, inv = al.inv;
+    const uint32_t tiles_per_seq = 1u + (nw + WPT - 1) / WPT;  // the short first tile (may be empty) + the aligned ones (the last may be empty)
+    // (sequence, tile) of this warp's work, stepped by the number of warps in the grid; 32-bit: n_seq < 2^32 (checked by the host)
+    const uint32_t warps_total = gridDim.x * WIN_WARPS, first = blockIdx.x * WIN_WARPS + (threadIdx.x >> 5);
+    uint32_t s = first / tiles_per_seq, t = first % tiles_per_seq;
+    const uint32_t step_s = warps_total / tiles_per_seq, step_t = warps_total % tiles_per_seq, n_seq = (uint32_t)p.n_seq;
+    for (; s < n_seq;) {
+        // windows in front of the sequence's first line boundary
+        const uint32_t seq_phase = ((uint32_t)reinterpret_cast<uintptr_t>(p.out) + ((s * nw) & (A - 1u)) * w) & (A - 1u);
+        const uint32_t lead = (seq_phase & ((1u << g_shift) - 1u)) ? 0u : ((((A - seq_phase) >> g_shift) * inv) & (P - 1u));
+        const uint32_t i0 = t == 0 ? 0u : min(nw, lead + (t - 1u) * WPT), i1 = t == 0 ? min(nw, lead) : min(nw, lead + t * WPT);
+        const uint32_t cnt = i1 - i0, span = cnt ? cnt + w - 1 : 0u;  // (an empty tile runs through the code below without touching anything)
         const uint8_t* seq = p.src + s * p.src_stride;
         // source bytes of the tile, mapped, in window order: srcb[4 + k] = map(seq[i0 + k]) or map(seq[len - 1 - i0 - k])
         // (a word-granular version of this loop was measured slower: 3.4 vs 2.8 ms on the all_windows bench leg)
@@ -1156,7 +1186,7 @@ __global__ void __launch_bounds__(32 * WIN_WARPS) windows_batch_kernel(const Win
         }
         if (TMA_OUT && lane == 0) bulk_wait_read_0();  // the previous tile's rows have left the stage
         __syncwarp();
-        const uint64_t out0 = (s * nw + i0) * (uint64_t)w;
+        const uint64_t out0 = ((uint64_t)s * nw + i0) * (uint64_t)w;
         uint8_t* gdst = p.out + out0;
         const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);  // stage mirrors the output's 16-byte phase
         // within every 64 windows lane handles windows 2 * lane and 2 * lane + 1: for even w all rows of one pass share their
