@@ -1012,137 +1012,6 @@ extern "C" int qd_canonical_windows_dev(qd_ctx* c, int enc, int forward_only, co
     return canonical_dev(c, enc, forward_only, dna_dev, 1, n, w, out_dev, pick_stream(c, stream));
 }
 
-// src/rust_api.rs:310-322 on device buffers: counts per 4 KiB block, scan, compacted write.
-// n_masks_dev receives the number of masks written (device uint64).
-static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
-                     cudaStream_t s) {
-    if (n == 0) {
-        if (n_masks_dev) QD_CUDA(c, cudaMemsetAsync(n_masks_dev, 0, 8, s));
-        return QD_OK;
-    }
-    const uint64_t span = (reinterpret_cast<uintptr_t>(ascii_dev) & 15) + n;  // from the aligned start
-    const uint64_t n_blocks = (span + PARSE_BLOCK_BYTES - 1) / PARSE_BLOCK_BYTES;
-    // dropped bytes per block: all zero between calls (pass 1 adds, the compacting pass clears what it has used)
-    if (c->parse_counts.cap < n_blocks * 8) {
-        QD_CUDA(c, c->parse_counts.reserve(n_blocks * 8));
-        QD_CUDA(c, cudaMemsetAsync(c->parse_counts.p, 0, c->parse_counts.cap, s));
-    }
-    QD_CUDA(c, c->parse_offsets.reserve((n_blocks + 1) * 8));
-    ParseParams p{};
-    p.in = ascii_dev;
-    p.n = n;
-    p.table = tab(c, strict ? TAB_PARSE_STRICT : TAB_PARSE);
-    p.pair = c->d_parse_pair + (strict ? PAIR_ENTRIES : 0);
-    p.pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);
-    p.counts = c->parse_counts.as<uint64_t>();
-    p.offsets = c->parse_offsets.as<uint64_t>();
-    p.out = masks_dev;
-    p.err_key = c->d_err;
-    p.gate = c->d_gate;
-    p.gate_gen = ++c->gate_gen;
-    // One streaming pass finishes input without whitespace (when input and output share their 16-byte phase); the scan
-    // and the compacting pass behind it return at once unless that pass dropped a byte.
-    const bool same_phase = ((reinterpret_cast<uintptr_t>(ascii_dev) ^ reinterpret_cast<uintptr_t>(masks_dev)) & 15) == 0;
-    const uint64_t n_gran = (span + 15) / 16;
-    const uint64_t step = (uint64_t)PARSE_THREADS * PARSE_CLEAN_UNROLL;
-    const unsigned g1 = (unsigned)std::min<uint64_t>((n_gran + step - 1) / step, (uint64_t)c->sm_count * 8);
-    if (same_phase) parse_pass1_kernel<true><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
-    else parse_pass1_kernel<false><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
-    parse_scan_kernel<<<1, PARSE_SCAN_THREADS, 0, s>>>(p, n_blocks);
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)c->sm_count * 8);
-    parse_write_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks, n_masks_dev);
-    c->launches += 3;
-    QD_CUDA(c, cudaGetLastError());
-    return QD_OK;
-}
-
-extern "C" int qd_parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
-                            void* stream) {
-    if (!c || (n && (!ascii_dev || !masks_dev))) return QD_ERR_INVALID_ARGUMENT;
-    Guard g(c, pick_stream(c, stream));
-    if (!g.ok) return QD_ERR_CUDA;
-    return parse_dev(c, strict, ascii_dev, n, masks_dev, n_masks_dev, pick_stream(c, stream));
-}
-
-extern "C" int qd_parse(qd_ctx* c, int strict, const uint8_t* ascii, size_t n, uint8_t* masks, size_t* n_masks, qd_err* err) {
-    clear_err(err);
-    if (n_masks) *n_masks = 0;
-    if (!c || (n && (!ascii || !masks))) return QD_ERR_INVALID_ARGUMENT;
-    Guard g(c);
-    if (!g.ok) return QD_ERR_CUDA;
-    if (n == 0) return QD_OK;
-    cudaStream_t s = c->stream;
-    QD_CUDA(c, c->in.reserve(n + 16));
-    QD_CUDA(c, c->out.reserve(n + 16));
-    QD_CUDA(c, c->aux0.reserve(8));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, ascii, n, cudaMemcpyHostToDevice, s));
-    if (int rc = reset_err_key(c, s)) return rc;
-    if (int rc = parse_dev(c, strict, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), c->aux0.as<uint64_t>(), s)) return rc;
-    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->aux0.p, 8, cudaMemcpyDeviceToHost, s));
-    unsigned long long key = 0;
-    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
-    if (key != NO_ERROR_KEY) return report_single(QD_ENC_ASCII, strict, ascii, key, err);
-    const size_t k = (size_t)c->h_scratch[0];
-    QD_CUDA(c, cudaMemcpyAsync(masks, c->out.p, k, cudaMemcpyDeviceToHost, s));
-    QD_CUDA(c, cudaStreamSynchronize(s));
-    if (n_masks) *n_masks = k;
-    return QD_OK;
-}
-
-static int canonical_seq_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, cudaStream_t s) {
-    if (n == 0) return QD_OK;
-    QD_CUDA(c, c->canon_state.reserve(9 * 8));
-    unsigned long long* st = c->canon_state.as<unsigned long long>();
-    QD_CUDA(c, cudaMemsetAsync(st, 0xff, 9 * 8, s));
-    QD_CUDA(c, cudaMemsetAsync(st + 4, 0, 4 * 8, s));
-    CanonSeqParams p{};
-    p.dna = dna_dev;
-    p.n = n;
-    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
-    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
-    p.forward_only = forward_only;
-    p.state = st;
-    p.out = out_dev;
-    p.err_key = c->d_err;
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8));
-    canon_seq_scan_kernel<<<grid, 256, 0, s>>>(p);
-    if (!forward_only) canon_seq_diff_kernel<<<grid, 256, 0, s>>>(p);
-    canon_seq_write_kernel<<<grid, 256, 0, s>>>(p);
-    c->launches += forward_only ? 2 : 3;
-    QD_CUDA(c, cudaGetLastError());
-    return QD_OK;
-}
-
-extern "C" int qd_canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, void* stream) {
-    if (!c || (n && (!dna_dev || !out_dev))) return QD_ERR_INVALID_ARGUMENT;
-    Guard g(c, pick_stream(c, stream));
-    if (!g.ok) return QD_ERR_CUDA;
-    return canonical_seq_dev(c, enc, forward_only, dna_dev, n, out_dev, pick_stream(c, stream));
-}
-
-extern "C" int qd_canonical(qd_ctx* c, int enc, int forward_only, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
-    clear_err(err);
-    if (!c || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
-    Guard g(c);
-    if (!g.ok) return QD_ERR_CUDA;
-    if (n == 0) return QD_OK;
-    cudaStream_t s = c->stream;
-    QD_CUDA(c, c->in.reserve(n + 16));
-    QD_CUDA(c, c->out.reserve(n + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
-    if (int rc = reset_err_key(c, s)) return rc;
-    if (int rc = canonical_seq_dev(c, enc, forward_only, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s)) return rc;
-    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, n, cudaMemcpyDeviceToHost, s));
-    unsigned long long key = 0;
-    if (int rc = fetch_err_key(c, s, &key)) return rc;
-    if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
-    return QD_OK;
-}
-
-// ---- FASTA record scanner (src/fasta.rs:207-491) ------------------------------------------------------------------
-static_assert(sizeof(qd_fasta_record) == sizeof(FastaRecord), "qd_fasta_record and the kernel's record must agree");
-
-namespace {
 // ---- pageable caller buffers: staging through pinned memory (see HostPool) --------------------------------------------------
 static bool host_pageable(const void* p) {
     cudaPointerAttributes a;
@@ -1248,7 +1117,7 @@ static int staged_upload(qd_ctx* c, void* dev, const uint8_t* host, size_t n, cu
         Pipe& P = c->pipe[k % N_PIPE];
         const size_t len = std::min(chunk, n - off);
         if (int rc = pipe_event(c, P)) return rc;
-        if (k >= N_PIPE) QD_CUDA(c, cudaEventSynchronize(P.done));
+        QD_CUDA(c, cudaEventSynchronize(P.done));  // the copy that last read this staging buffer (none: returns at once)
         QD_CUDA(c, P.hin.reserve(len));
         stage_pool(c)->copy(P.hin.p, host + off, len);
         QD_CUDA(c, cudaMemcpyAsync(static_cast<uint8_t*>(dev) + off, P.hin.p, len, cudaMemcpyHostToDevice, s));
@@ -1285,6 +1154,136 @@ static int staged_download(qd_ctx* c, uint8_t* host, const void* dev, size_t n, 
     return QD_OK;
 }
 
+// src/rust_api.rs:310-322 on device buffers: counts per 4 KiB block, scan, compacted write.
+// n_masks_dev receives the number of masks written (device uint64).
+static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
+                     cudaStream_t s) {
+    if (n == 0) {
+        if (n_masks_dev) QD_CUDA(c, cudaMemsetAsync(n_masks_dev, 0, 8, s));
+        return QD_OK;
+    }
+    const uint64_t span = (reinterpret_cast<uintptr_t>(ascii_dev) & 15) + n;  // from the aligned start
+    const uint64_t n_blocks = (span + PARSE_BLOCK_BYTES - 1) / PARSE_BLOCK_BYTES;
+    // dropped bytes per block: all zero between calls (pass 1 adds, the compacting pass clears what it has used)
+    if (c->parse_counts.cap < n_blocks * 8) {
+        QD_CUDA(c, c->parse_counts.reserve(n_blocks * 8));
+        QD_CUDA(c, cudaMemsetAsync(c->parse_counts.p, 0, c->parse_counts.cap, s));
+    }
+    QD_CUDA(c, c->parse_offsets.reserve((n_blocks + 1) * 8));
+    ParseParams p{};
+    p.in = ascii_dev;
+    p.n = n;
+    p.table = tab(c, strict ? TAB_PARSE_STRICT : TAB_PARSE);
+    p.pair = c->d_parse_pair + (strict ? PAIR_ENTRIES : 0);
+    p.pair_coef = 2u | ((2u * PAIR_K1_ASCII) << 16);
+    p.counts = c->parse_counts.as<uint64_t>();
+    p.offsets = c->parse_offsets.as<uint64_t>();
+    p.out = masks_dev;
+    p.err_key = c->d_err;
+    p.gate = c->d_gate;
+    p.gate_gen = ++c->gate_gen;
+    // One streaming pass finishes input without whitespace (when input and output share their 16-byte phase); the scan
+    // and the compacting pass behind it return at once unless that pass dropped a byte.
+    const bool same_phase = ((reinterpret_cast<uintptr_t>(ascii_dev) ^ reinterpret_cast<uintptr_t>(masks_dev)) & 15) == 0;
+    const uint64_t n_gran = (span + 15) / 16;
+    const uint64_t step = (uint64_t)PARSE_THREADS * PARSE_CLEAN_UNROLL;
+    const unsigned g1 = (unsigned)std::min<uint64_t>((n_gran + step - 1) / step, (uint64_t)c->sm_count * 8);
+    if (same_phase) parse_pass1_kernel<true><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
+    else parse_pass1_kernel<false><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
+    parse_scan_kernel<<<1, PARSE_SCAN_THREADS, 0, s>>>(p, n_blocks);
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)c->sm_count * 8);
+    parse_write_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks, n_masks_dev);
+    c->launches += 3;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
+                            void* stream) {
+    if (!c || (n && (!ascii_dev || !masks_dev))) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
+    return parse_dev(c, strict, ascii_dev, n, masks_dev, n_masks_dev, pick_stream(c, stream));
+}
+
+extern "C" int qd_parse(qd_ctx* c, int strict, const uint8_t* ascii, size_t n, uint8_t* masks, size_t* n_masks, qd_err* err) {
+    clear_err(err);
+    if (n_masks) *n_masks = 0;
+    if (!c || (n && (!ascii || !masks))) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(n + 16));
+    QD_CUDA(c, c->aux0.reserve(8));
+    if (int rc = staged_upload(c, c->in.p, ascii, n, s)) return rc;
+    if (int rc = reset_err_key(c, s)) return rc;
+    if (int rc = parse_dev(c, strict, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), c->aux0.as<uint64_t>(), s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->aux0.p, 8, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
+    if (key != NO_ERROR_KEY) return report_single(QD_ENC_ASCII, strict, ascii, key, err);
+    const size_t k = (size_t)c->h_scratch[0];
+    if (int rc = staged_download(c, masks, c->out.p, k, s)) return rc;
+    if (n_masks) *n_masks = k;
+    return QD_OK;
+}
+
+static int canonical_seq_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, cudaStream_t s) {
+    if (n == 0) return QD_OK;
+    QD_CUDA(c, c->canon_state.reserve(9 * 8));
+    unsigned long long* st = c->canon_state.as<unsigned long long>();
+    QD_CUDA(c, cudaMemsetAsync(st, 0xff, 9 * 8, s));
+    QD_CUDA(c, cudaMemsetAsync(st + 4, 0, 4 * 8, s));
+    CanonSeqParams p{};
+    p.dna = dna_dev;
+    p.n = n;
+    p.decode = tab(c, enc == QD_ENC_ASCII ? TAB_DECODE_ASCII : TAB_DECODE_MASK);
+    p.letters = enc == QD_ENC_ASCII ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
+    p.forward_only = forward_only;
+    p.state = st;
+    p.out = out_dev;
+    p.err_key = c->d_err;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8));
+    canon_seq_scan_kernel<<<grid, 256, 0, s>>>(p);
+    if (!forward_only) canon_seq_diff_kernel<<<grid, 256, 0, s>>>(p);
+    canon_seq_write_kernel<<<grid, 256, 0, s>>>(p);
+    c->launches += forward_only ? 2 : 3;
+    QD_CUDA(c, cudaGetLastError());
+    return QD_OK;
+}
+
+extern "C" int qd_canonical_dev(qd_ctx* c, int enc, int forward_only, const uint8_t* dna_dev, size_t n, uint8_t* out_dev, void* stream) {
+    if (!c || (n && (!dna_dev || !out_dev))) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c, pick_stream(c, stream));
+    if (!g.ok) return QD_ERR_CUDA;
+    return canonical_seq_dev(c, enc, forward_only, dna_dev, n, out_dev, pick_stream(c, stream));
+}
+
+extern "C" int qd_canonical(qd_ctx* c, int enc, int forward_only, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
+    clear_err(err);
+    if (!c || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(n + 16));
+    if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
+    if (int rc = reset_err_key(c, s)) return rc;
+    if (int rc = canonical_seq_dev(c, enc, forward_only, c->in.as<uint8_t>(), n, c->out.as<uint8_t>(), s)) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, n, cudaMemcpyDeviceToHost, s));
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;
+    if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+    return QD_OK;
+}
+
+// ---- FASTA record scanner (src/fasta.rs:207-491) ------------------------------------------------------------------
+static_assert(sizeof(qd_fasta_record) == sizeof(FastaRecord), "qd_fasta_record and the kernel's record must agree");
+
+namespace {
 struct FastaRun {
     FastaParams p{};
     uint64_t* pre_base = nullptr;  // device: blk_last | blk_state | cnt x3 | pre x3
@@ -1779,7 +1778,7 @@ extern "C" int qd_translate_frames(qd_ctx* c, int table, int enc, int strict, in
     const size_t slot_bytes = qd_slots_bytes(n, frames);
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(slot_bytes + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
     const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
     if (slot_bytes <= SMALL_CALL_BYTES) {
         // small call: the error key lives right behind the slots, so result and key come back in one copy
@@ -1844,7 +1843,7 @@ extern "C" int qd_revcomp(qd_ctx* c, int enc, int strict, const uint8_t* dna, si
     }
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(n + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
     if (n <= SMALL_CALL_BYTES) {  // small call: [result | error key] in one copy through pinned memory
         const size_t key_off = (n + 15) & ~(size_t)15;
         QD_CUDA(c, c->out.reserve(key_off + 16));
@@ -2001,10 +2000,10 @@ extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const 
     const size_t out_bytes = (n - w + 1) * w;
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(out_bytes + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
     if (int rc = reset_err_key(c, s)) return rc;
     if (int rc = canonical_dev(c, enc, forward_only, c->in.as<uint8_t>(), 1, n, w, c->out.as<uint8_t>(), s)) return rc;
-    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (int rc = staged_download(c, out, c->out.p, out_bytes, s)) return rc;
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;
     if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
@@ -2023,10 +2022,10 @@ extern "C" int qd_canonical_window_keys(qd_ctx* c, int enc, int forward_only, in
     const size_t out_bytes = (n - w + 1) * key_bytes;
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(out_bytes + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
     if (int rc = reset_err_key(c, s)) return rc;
     if (int rc = canonical_keys_dev(c, enc, forward_only, kind, c->in.as<uint8_t>(), 1, n, w, c->out.p, s)) return rc;
-    QD_CUDA(c, cudaMemcpyAsync(keys, c->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (int rc = staged_download(c, static_cast<uint8_t*>(keys), c->out.p, out_bytes, s)) return rc;
     unsigned long long key = 0;
     if (int rc = fetch_err_key(c, s, &key)) return rc;
     if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
@@ -2182,7 +2181,7 @@ extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, 
     QD_CUDA(c, c->aux1.reserve(n_win * 8));        // emit
     QD_CUDA(c, c->aux2.reserve((n_win + 1) * 8));  // out_index
     if (fast) QD_CUDA(c, c->aux3.reserve(n_win * 8));  // descriptors
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, windows, in_bytes, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, windows, in_bytes, s)) return rc;
     if (int rc = reset_err_key(c, s)) return rc;
     ExpandParams p = expansion_params(c, enc, c->in.as<uint8_t>(), n_win, w, max_expansions, c->aux0.as<uint64_t>(), c->aux1.as<uint64_t>(),
                                       c->aux2.as<uint64_t>(), fast ? c->aux3.as<uint64_t>() : nullptr);
@@ -2215,7 +2214,7 @@ extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, 
             c->launches++;
             QD_CUDA(c, cudaGetLastError());
         }
-        QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, total_rows * w, cudaMemcpyDeviceToHost, s));
+        if (int rc = staged_download(c, out, c->out.p, total_rows * w, s)) return rc;
     }
     QD_CUDA(c, cudaStreamSynchronize(s));
     if (out_index) {
@@ -2237,10 +2236,9 @@ extern "C" int qd_windows(qd_ctx* c, const uint8_t* seq, size_t n, size_t w, uin
     const size_t count = n - w + 1;
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(count * w + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, seq, n, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, seq, n, s)) return rc;
     if (int rc = windows_dev(c, c->in.as<uint8_t>(), n, w, c->out.as<uint8_t>(), s)) return rc;
-    QD_CUDA(c, cudaMemcpyAsync(out, c->out.p, count * w, cudaMemcpyDeviceToHost, s));
-    QD_CUDA(c, cudaStreamSynchronize(s));
+    if (int rc = staged_download(c, out, c->out.p, count * w, s)) return rc;
     if (n_windows) *n_windows = count;
     return QD_OK;
 }
@@ -2279,7 +2277,7 @@ extern "C" int qd_windows_all(qd_ctx* c, int enc, const uint8_t* dna, size_t n, 
     QD_CUDA(c, c->aux2.reserve(qd_slots_bytes(n, 6) + 16));    // six frames
     QD_CUDA(c, c->out.reserve(std::max(2 * n_dna * w_dna, n_aa * w_aa) + 16));
     QD_CUDA(c, c->aux3.reserve(total * 8 + 16));
-    QD_CUDA(c, cudaMemcpyAsync(c->in.p, dna, n, cudaMemcpyHostToDevice, s));
+    if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
     if (int rc = reset_err_key(c, s)) return rc;
     // strict alphabet (DnaSequence<Nucleotide>): the strict tables reject everything else
     const int t_rc = enc == QD_ENC_ASCII ? RC_PAIR_ASCII_STRICT : RC_PAIR_MASK_TO_ASCII_STRICT;

@@ -115,3 +115,32 @@ def test_fasta_text_staged(N, B, ctx):
     assert np.array_equal(ra.masks, rb.masks)
     assert ra.masks.size == rec * 1960
     assert oracle.ascii_of(ra.masks[:1960]) == body[0].tobytes()
+
+
+def test_window_and_parse_calls_staged_equal_plain(N, B, ctx):
+    """The other host entry points move their large buffers through the same staging: windows (42 bytes out per byte in),
+    canonical windows and keys, the parse, the expansions."""
+    n = 2_000_003
+    dna = oracle.synth(3, 0, n)
+    a, b = _staged_and_plain(N, ctx, lambda: B.windows(dna, 42, ctx=ctx).copy())  # 84 MB out
+    assert np.array_equal(a, b) and a.shape == (n - 41, 42)
+    assert a[12345].tobytes() == dna[12345:12345 + 42].tobytes()
+    a, b = _staged_and_plain(N, ctx, lambda: B.canonical_windows(dna, 42, ctx=ctx).copy())
+    assert np.array_equal(a, b)
+    want = oracle.ascii_of(oracle.canonical_windows(oracle.masks_of(dna[:5000]), 42).reshape(-1))
+    assert a[: 5000 - 41].tobytes() == want
+    a, b = _staged_and_plain(N, ctx, lambda: B.canonical_window_keys(dna, 42, kind=N.CANON_KEY_PACKED, ctx=ctx).copy())  # 32 MB of keys
+    assert np.array_equal(a, b)
+    big = oracle.synth(2, 0, 40_000_000)
+    big[1000::61] = 0x20
+    a, b = _staged_and_plain(N, ctx, lambda: B.parse(big, ctx=ctx).copy())
+    assert np.array_equal(a, b)
+    assert np.array_equal(a[:5000], oracle.parse(big[:6000].tobytes())[:5000])
+    rng = np.random.default_rng(3)
+    win = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (400_000, 42))].copy()
+    win[np.arange(400_000), rng.integers(0, 42, 400_000)] = ord("N")
+    win[np.arange(400_000), rng.integers(0, 42, 400_000)] = ord("R")
+    (ca, ia, ra), (cb, ib, rb) = _staged_and_plain(N, ctx, lambda: B.expansion_windows(win, max_expansions=16, ctx=ctx))  # ~130 MB of rows
+    assert np.array_equal(ca, cb) and np.array_equal(ia, ib) and np.array_equal(ra, rb)
+    want_sum, want_rows = oracle.check_expansions(win, 16, _threads())
+    assert len(ra) == want_rows and oracle.checksum64(np.ascontiguousarray(ra).reshape(-1), 0) == want_sum
