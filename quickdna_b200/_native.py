@@ -69,6 +69,8 @@ SIGNATURES = {
     "qd_last_cuda_error": (C.c_char_p, [_vp]),
     "qd_ctx_set_chunk_bytes": (_i, [_vp, _sz]),
     "qd_ctx_set_stage_threads": (_i, [_vp, _i]),
+    "qd_host_alloc": (_vp, [_sz]),
+    "qd_host_free": (None, [_vp]),
     "qd_table_slot": (_i, [_i]),
     "qd_table_data": (_vp, [_i]),
     "qd_err_message": (_i, [C.POINTER(QdErr), C.c_char_p, _sz]),

@@ -644,3 +644,31 @@ def dev_error_fetch(dna, offsets=None, n_seq: int = 0, uniform_len: int = 0, str
     if rc in (N.QD_ERR_CUDA, N.QD_ERR_INVALID_ARGUMENT):
         ctx.check(rc)
     return None if rc == N.QD_OK else N.make_error(err)
+
+
+class _PinnedOwner:
+    """Keeps a qd_host_alloc block alive for the numpy array that views it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    def __del__(self):
+        try:
+            N.lib().qd_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """A numpy array in pinned (page-locked) host memory (qd_host_alloc): the host entry points copy from and to it directly,
+    without the staging that pageable arrays go through.  The memory is released when the array (and its views) are gone."""
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(1, count * dt.itemsize)
+    ptr = N.lib().qd_host_alloc(nbytes)
+    if not ptr:
+        raise MemoryError(f"qd_host_alloc({nbytes}) failed")
+    owner = _PinnedOwner(int(ptr), nbytes)
+    buf = (C.c_uint8 * nbytes).from_address(owner.ptr)
+    buf._owner = owner  # the ctypes buffer is the array's base: the block lives as long as any view of it
+    return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)

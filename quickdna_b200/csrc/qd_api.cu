@@ -717,6 +717,17 @@ extern "C" int qd_ctx_set_chunk_bytes(qd_ctx* c, size_t bytes) {
     c->chunk_bytes = bytes;
     return QD_OK;
 }
+extern "C" void* qd_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void qd_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
 extern "C" int qd_ctx_set_stage_threads(qd_ctx* c, int threads) {
     if (!c || threads < -1 || threads > 64) return QD_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(c->mu);

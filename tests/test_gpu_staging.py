@@ -144,3 +144,23 @@ def test_window_and_parse_calls_staged_equal_plain(N, B, ctx):
     assert np.array_equal(ca, cb) and np.array_equal(ia, ib) and np.array_equal(ra, rb)
     want_sum, want_rows = oracle.check_expansions(win, 16, _threads())
     assert len(ra) == want_rows and oracle.checksum64(np.ascontiguousarray(ra).reshape(-1), 0) == want_sum
+
+
+def test_pinned_arrays_take_the_direct_path(N, B, ctx):
+    """batch.pinned_empty: numpy arrays in page-locked memory; results equal the staged ones."""
+    n_reads, L_ = 20_011, 1000
+    reads = oracle.synth(3, 0, n_reads * L_).reshape(n_reads, L_)
+    pinned = B.pinned_empty((n_reads, L_))
+    pinned[:] = reads
+    attr_type = None
+    try:
+        import torch
+
+        attr_type = torch.cuda.cudart().cudaPointerGetAttributes(pinned.ctypes.data)[1].type  # 1 = host (pinned)
+    except Exception:
+        pass
+    a = B.translate_frames_batch(pinned, table=1, frames=6, ctx=ctx).data
+    b = B.translate_frames_batch(reads, table=1, frames=6, ctx=ctx).data
+    assert np.array_equal(a, b)
+    assert attr_type in (None, 1) or int(attr_type) == 1
+    del pinned  # releases the block
