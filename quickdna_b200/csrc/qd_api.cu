@@ -62,6 +62,10 @@ constexpr int N_PIPE = 3;  // streams / buffer sets of the chunked host pipeline
 // host calls whose device result is at most this big come back as ONE device->host copy [result | error key] into pinned
 // memory (the reference's typical call is a 30-kb genome: launch and copy count is what it costs here)
 constexpr size_t SMALL_CALL_BYTES = size_t(2) << 20;
+// Tiny host calls (the reference's typical call: one 30-kb genome) skip the copies altogether: the kernel reads its input from
+// and writes its result and error key to MAPPED pinned host memory of the context, so a call is one host memcpy in, ONE
+// launch, one synchronise and one memcpy out instead of five runtime calls (H2D, memset, launch, D2H, synchronise).
+constexpr size_t TINY_IN_BYTES = size_t(128) << 10, TINY_OUT_BYTES = size_t(288) << 10;  // input / result capacity of the mapped block
 
 // Pageable host memory (a Rust Vec<u8>, a Python bytes object, a numpy array) cannot be the source or target of an
 // asynchronous copy: the driver stages it through one internal buffer on the calling thread, and the chunk pipeline
@@ -177,6 +181,8 @@ struct qd_ctx {
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
     uint8_t* h_stage = nullptr;           // pinned staging for small host calls: [result | error key] in ONE copy
+    uint8_t* h_tiny = nullptr;            // mapped pinned block of the tiny-call path: [input | error key | result]
+    bool tiny_calls = true;               // QD_TINY_CALLS=0 turns the mapped path off (A/B measurements)
     DevBuf in, out, aux0, aux1, aux2, aux3, run_prefix, tile_first, block_sums, parse_counts, parse_offsets, canon_state, fasta_scratch;
     Pipe pipe[N_PIPE];
     size_t chunk_bytes = size_t(64) << 20;   // input bytes per pipeline chunk
@@ -630,6 +636,8 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     ok &= cudaHostAlloc(&c->h_err, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_scratch, 8 * sizeof(uint64_t), cudaHostAllocDefault) == cudaSuccess;
     ok &= cudaHostAlloc(&c->h_stage, SMALL_CALL_BYTES + 64, cudaHostAllocDefault) == cudaSuccess;
+    ok &= cudaHostAlloc(&c->h_tiny, TINY_IN_BYTES + 64 + TINY_OUT_BYTES + 64, cudaHostAllocMapped) == cudaSuccess;
+    if (const char* e = getenv("QD_TINY_CALLS")) c->tiny_calls = atoi(e) != 0;
     if (ok) {
         std::vector<uint8_t> tabs(256 * TAB_COUNT);
         auto put = [&](int which, const uint8_t* src) { memcpy(tabs.data() + 256 * which, src, 256); };
@@ -696,6 +704,7 @@ extern "C" void qd_ctx_destroy(qd_ctx* c) {
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_tiny) cudaFreeHost(c->h_tiny);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->dev_done) cudaEventDestroy(c->dev_done);
     if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
@@ -1787,10 +1796,35 @@ extern "C" int qd_translate_frames(qd_ctx* c, int table, int enc, int strict, in
         return QD_OK;
     }
     const size_t slot_bytes = qd_slots_bytes(n, frames);
+    const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
+    if (c->tiny_calls && n <= TINY_IN_BYTES && slot_bytes <= TINY_OUT_BYTES) {
+        // tiny call: input, error key and result in mapped host memory -- one launch, no copies
+        uint8_t* const h_in = c->h_tiny;
+        unsigned long long* const h_key = reinterpret_cast<unsigned long long*>(c->h_tiny + TINY_IN_BYTES + 16);
+        uint8_t* const h_out = c->h_tiny + TINY_IN_BYTES + 64;
+        memcpy(h_in, dna, n);
+        *h_key = NO_ERROR_KEY;
+        if (int rc = frames_uniform_dev(c, slot, enc, strict, frames, h_in, 1, n, h_out, s, 0, h_key)) return rc;
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        const unsigned long long key = *h_key;
+        if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+        size_t off = 0;
+        int nf = 0;
+        for (int f = 0; f < n_slots; f++) {
+            const size_t len = qd_frame_len(n, f % 3);
+            if (out_len) out_len[f] = len;
+            if (len) {
+                memcpy(out + off, h_out + qd_slot_frame_offset(n, frames, f), len);
+                off += len;
+                nf++;
+            }
+        }
+        if (n_frames) *n_frames = nf;
+        return QD_OK;
+    }
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(slot_bytes + 16));
     if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
-    const int n_slots = frames == QD_FRAMES_ONE ? 1 : frames;
     if (slot_bytes <= SMALL_CALL_BYTES) {
         // small call: the error key lives right behind the slots, so result and key come back in one copy
         unsigned long long* key_dev = reinterpret_cast<unsigned long long*>(c->out.as<uint8_t>() + slot_bytes);  // 16-byte aligned
@@ -1850,6 +1884,19 @@ extern "C" int qd_revcomp(qd_ctx* c, int enc, int strict, const uint8_t* dna, si
         unsigned long long key = 0;
         if (int rc = pipes_end(c, &key)) return rc;
         if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+        return QD_OK;
+    }
+    if (c->tiny_calls && n <= TINY_IN_BYTES) {  // tiny call: input, error key and result in mapped host memory, one launch
+        uint8_t* const h_in = c->h_tiny;
+        unsigned long long* const h_key = reinterpret_cast<unsigned long long*>(c->h_tiny + TINY_IN_BYTES + 16);
+        uint8_t* const h_out = c->h_tiny + TINY_IN_BYTES + 64;
+        memcpy(h_in, dna, n);
+        *h_key = NO_ERROR_KEY;
+        if (int rc = revcomp_dev_table(c, which, h_in, n, h_out, s, h_key)) return rc;
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        const unsigned long long key = *h_key;
+        if (key != NO_ERROR_KEY) return report_single(enc, strict, dna, key, err);
+        memcpy(out, h_out, n);
         return QD_OK;
     }
     QD_CUDA(c, c->in.reserve(n + 16));
