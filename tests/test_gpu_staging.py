@@ -164,3 +164,25 @@ def test_pinned_arrays_take_the_direct_path(N, B, ctx):
     assert np.array_equal(a, b)
     assert attr_type in (None, 1) or int(attr_type) == 1
     del pinned  # releases the block
+
+
+@pytest.mark.parametrize("n", [131_071, 131_072, 131_073, 700_001, 2_500_000])
+def test_single_sequence_size_classes(N, B, ctx, n):
+    """One sequence through every host path: tiny (mapped memory, <= 128 KiB), small (result + key in one copy, <= 2 MiB of
+    result), plain (separate copies), each against the oracle -- frames, reverse complement, and the first error."""
+    dna = oracle.synth(3, n, n)
+    got = B.translate_frames(dna, table=11, frames=6, ctx=ctx)
+    want = oracle.py_all_frames(11, dna.tobytes())
+    assert [bytes(f) for f in got] == want
+    assert B.revcomp(dna, ctx=ctx).tobytes() == oracle.revcomp_bytes(dna.tobytes())
+    one = B.translate_frames(dna, table=2, frames=N.FRAMES_ONE, ctx=ctx)
+    assert bytes(one[0]) == oracle.translate_bytes(2, dna.tobytes())
+    bad = dna.copy()
+    bad[n - 7] = ord("x")
+    bad[n // 2] = ord("B")
+    with pytest.raises(ValueError) as ei:
+        B.translate_frames(bad, table=1, frames=6, strict=True, ctx=ctx)
+    assert (ei.value.pos, ei.value.kind, chr(ei.value.byte)) == (n // 2, 3, "B")
+    with pytest.raises(ValueError) as ei:
+        B.revcomp(bad, ctx=ctx)
+    assert (ei.value.pos, ei.value.kind) == (n - 7, 2)
