@@ -1873,7 +1873,7 @@ __device__ __forceinline__ void expansion_size_hint(const ExpandParams& p, const
     const uint32_t sa = raw_base + (off & ~3u);
     const uint32_t sh = (off & 3u) * 8u;
     // phase A, the same instructions for every lane: a bit per position that holds an ambiguity code
-    uint32_t amb_lo = 0, amb_hi = 0;
+    uint32_t amb_lo = 0, amb_hi = 0, bad = 0;
     uint32_t prev = lds_u32(sa);
 #pragma unroll
     for (uint32_t k = 0; k < (W ? (uint32_t)(W + 3) / 4 : 16u); k++) {
@@ -1884,31 +1884,29 @@ __device__ __forceinline__ void expansion_size_hint(const ExpandParams& p, const
         const uint32_t nb = min(4u, w - 4u * k);  // bytes of this word inside the window
         if (nb < 4) x = (x & ((1u << (8 * nb)) - 1u)) | ((filler * 0x01010101u) << (8 * nb));
         uint32_t m4;
-        bool bad;
         if (ASCII) {
             const uint32_t u = x & 0x1f1f1f1fu;
             m4 = lds_u16(dp2a_lo(pair_coef, u, pair_base)) | (lds_u16(dp2a_hi(pair_coef, u, pair_base)) << 16);
-            bad = ((m4 & (PARSE_PAIR_SLOW * 0x01010101u)) | ((x & 0x40404040u) ^ 0x40404040u) | (x & 0x80808080u)) != 0;
+            bad |= (m4 & (PARSE_PAIR_SLOW * 0x01010101u)) | ((x & 0x40404040u) ^ 0x40404040u) | (x & 0x80808080u);
         } else {
             m4 = x;
-            bad = ((x & 0xf0f0f0f0u) | ((x - 0x01010101u) & ~x & 0x80808080u)) != 0;
+            bad |= (x & 0xf0f0f0f0u) | ((x - 0x01010101u) & ~x & 0x80808080u);
         }
-        if (bad) {  // exact: the first byte of this word that is not a nucleotide code
-            for (uint32_t t = 0; t < nb; t++) {
-                const uint32_t b = (x >> (8 * t)) & 0xffu;
-                if (__ldg(p.to_mask + b) == 0) {
-                    atomicMin(p.err_key, (unsigned long long)(window * w + 4u * k + t));
-                    break;
-                }
-            }
-            continue;  // (the call fails; the counts of this window do not matter)
-        }
-        // bytes with more than one bit -> one bit each -> a nibble
+        // bytes with more than one bit -> one bit each -> a nibble (of a word with an invalid byte: garbage, the call fails anyway)
         uint32_t t4 = m4 & (m4 - 0x01010101u) & 0x0f0f0f0fu;
         t4 = (t4 | (t4 >> 1) | (t4 >> 2) | (t4 >> 3)) & 0x01010101u;
         const uint32_t nib = (t4 * 0x10204080u) >> 28;  // byte t -> bit t
         if (k < 8) amb_lo |= nib << (4 * k);
         else amb_hi |= nib << (4 * (k - 8));
+    }
+    if (bad) {  // exact: the first byte of the window that is not a nucleotide code (one branch per window, not per word)
+        for (uint32_t j = 0; j < w; j++) {
+            if (__ldg(p.to_mask + raw[off + j]) == 0) {
+                atomicMin(p.err_key, (unsigned long long)(window * w + j));
+                break;
+            }
+        }
+        amb_lo = amb_hi = 0;  // (the call fails; the counts of this window do not matter)
     }
     // phase B: the few ambiguous positions, last first (the fastest odometer digit)
     uint64_t size = 1, desc = 0, hi = 0;
@@ -2402,20 +2400,22 @@ __global__ void __launch_bounds__(32 * EXP_FUSED_WARPS, W ? 4 : 3) expansion_fus
             }
             // the row's odometer digits, fastest first: digit = k mod states, k /= states; states in {2, 3, 4} and
             // k < 128, so the quotient is one multiply: k / 2 = k * 128 >> 8, k / 3 = k * 86 >> 8, k / 4 = k * 64 >> 8
-            const uint32_t max_amb = __reduce_max_sync(0xffffffffu, n_amb);
-            uint64_t d = dd.x;
             const uint32_t patch_base = stage_base + d0;
-#pragma unroll 1
-            for (uint32_t e = 0; e < max_amb; e++) {
-                const uint32_t f = (uint32_t)d;
-                d = e == 3 ? dd.y : d >> 16;
-                if (e < n_amb) {
-                    const uint32_t recip = (0x40568000u >> ((f >> 3) & 0x18u)) & 0xffu;
-                    const uint32_t quo = (k * recip) >> 8;
-                    const uint32_t digit = k - quo - quo * ((f >> 6) & 3u);
-                    k = quo;
-                    sts_u8(patch_base + (f & 63u), lds_u8(letter_base + ((f >> 6) & 0x3cu) + digit));
-                }
+            auto patch = [&](uint32_t f) {
+                const uint32_t recip = (0x40568000u >> ((f >> 3) & 0x18u)) & 0xffu;
+                const uint32_t quo = (k * recip) >> 8;
+                const uint32_t digit = k - quo - quo * ((f >> 6) & 3u);
+                k = quo;
+                sts_u8(patch_base + (f & 63u), lds_u8(letter_base + ((f >> 6) & 0x3cu) + digit));
+            };
+            // (benches/expansions.rs puts two ambiguity codes into a window: the first two digits are straight-line code)
+            if (n_amb > 0) patch((uint32_t)dd.x);
+            if (n_amb > 1) patch((uint32_t)(dd.x >> 16));
+            if (__any_sync(0xffffffffu, n_amb > 2)) {
+                if (n_amb > 2) patch((uint32_t)(dd.x >> 32));
+                if (n_amb > 3) patch((uint32_t)(dd.x >> 48));
+                if (n_amb > 4) patch((uint32_t)dd.y);
+                if (n_amb > 5) patch((uint32_t)(dd.y >> 16));
             }
             fence_proxy_async_smem();  // my rows, written through the generic proxy, are visible to the bulk copy
             __syncwarp();
