@@ -1932,6 +1932,27 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
     const uint64_t total_nt = uniform ? (uint64_t)n_seq * uniform_len : offsets[n_seq] - offsets[0];
     if (n_seq == 0) return QD_OK;
     const uint64_t stride = 16 * (uint64_t)frames;
+    if (uniform && c->tiny_calls && total_nt <= TINY_IN_BYTES && n_seq * stride * qd_runs(uniform_len) <= TINY_OUT_BYTES) {
+        // a tiny uniform batch: input, error key and slots in mapped host memory -- one launch, no copies (see TINY_IN_BYTES)
+        const size_t out_bytes = n_seq * stride * qd_runs(uniform_len);
+        uint8_t* const h_in = c->h_tiny;
+        unsigned long long* const h_key = reinterpret_cast<unsigned long long*>(c->h_tiny + TINY_IN_BYTES + 16);
+        uint8_t* const h_out = c->h_tiny + TINY_IN_BYTES + 64;
+        cudaStream_t s = c->stream;
+        memcpy(h_in, dna, total_nt);
+        *h_key = NO_ERROR_KEY;
+        if (int rc = frames_uniform_dev(c, slot, enc, strict, frames, h_in, n_seq, uniform_len, h_out, s, 0, h_key)) return rc;
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        const unsigned long long key = *h_key;
+        if (key != NO_ERROR_KEY) {
+            uint8_t payload = 0;
+            int kind = classify_byte(enc, strict, dna[key], &payload);
+            if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+            return set_err(err, kind, payload, key % uniform_len, key / uniform_len);
+        }
+        memcpy(out, h_out, out_bytes);
+        return QD_OK;
+    }
     // out_offsets (host) for the CSR form: 16*frames*prefix(runs)
     std::vector<uint64_t> own_offsets;
     const uint64_t* oo = out_offsets;
