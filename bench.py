@@ -703,6 +703,21 @@ def main():
             extra["fasta_scan"] = {"workload": f"{n_rec} records, {len(text)} bytes of FASTA text (70-column lines), host in / host out "
                                                "(pageable memory), one qd_fasta_scan call + Python record objects",
                                    "seconds": fa_s, "text_GB_per_s": len(text) / fa_s / 1e9, "first_call_seconds": fa_first}
+            # FASTA text in, six frames of every record out: one fused call (masks stay on the device) against scan + batch translate
+            B.fasta_translate_frames(text, ctx=ctx)
+            t0 = time.perf_counter()
+            fscan, fframes = B.fasta_translate_frames(text, ctx=ctx)
+            ff_s = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            two = B.translate_frames_batch((scan.masks, scan.offsets), frames=6, enc=N.ENC_MASK, ctx=ctx)
+            tb_s = time.perf_counter() - t0
+            same = bool(np.array_equal(two.data, fframes.data))
+            checks["fasta_translate_frames_equals_scan_then_translate"] = same
+            assert same and len(fscan) == n_rec
+            extra["fasta_translate_frames"] = {"workload": "the same text -> six frames of every record, host in / host out (pageable), one qd_fasta_translate_frames call",
+                                               "seconds": ff_s, "text_GB_per_s": len(text) / ff_s / 1e9, "nt_per_s": scan.masks.size / ff_s,
+                                               "scan_then_translate_seconds": fa_s + tb_s}
+            del fscan, fframes, two
             if not args.no_cpu:
                 t0 = time.perf_counter()
                 ref = oracle.fasta_scan(text[: len(text) // 10])

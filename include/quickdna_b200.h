@@ -193,6 +193,19 @@ int qd_fasta_scan(qd_ctx *ctx, int strict, int concatenate_headers, int allow_pr
                   const uint8_t *text, size_t n, uint8_t *masks, size_t *n_masks, qd_fasta_record *records,
                   size_t max_records, size_t *n_records, qd_err *err);
 
+/* FASTA text in, the frames of every record out: FastaParser::parse (src/fasta.rs:207-491) followed by
+ * translate / translate_self_frames / translate_all_frames (src/rust_api.rs:227-270) of every record, in one call.  The
+ * scanner's masks and CSR offsets feed the frame kernels on the device: only the text goes up, only records and frames
+ * come back.  records[i] as qd_fasta_scan (content_begin/_end = the record's nucleotide range); out = the slot layout of
+ * qd_translate_frames_batch over the records (record i at out_offsets[i], frames at qd_slot_frame_offset(len_i, frames, f)),
+ * out_offsets: max_records + 1 entries or NULL.  *out_bytes = bytes needed / written (at most
+ * 16 * frames * (n / 48 + n_records)).  Call with records == out == NULL for *n_records and *out_bytes only; too small a
+ * capacity stores the needed values and returns QD_ERR_INVALID_ARGUMENT.  Errors as qd_fasta_scan (table id first). */
+int qd_fasta_translate_frames(qd_ctx *ctx, int table, int strict, int frames, int concatenate_headers,
+                              int allow_preceding_comment, const uint8_t *text, size_t n, qd_fasta_record *records,
+                              size_t max_records, size_t *n_records, uint8_t *out, size_t out_capacity,
+                              uint64_t *out_offsets, size_t *out_bytes, qd_err *err);
+
 /* DnaSequence::<Nucleotide>::canonical over every length-w window: src/canonical.rs:17-55,
  * 71-118, 129-179 applied as in benches/canonical.rs:29-34.  Strict alphabet only.
  * forward_only != 0 gives ForwardCanonical.  out: (n-w+1)*w bytes (0 windows if n < w),

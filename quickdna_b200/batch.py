@@ -269,6 +269,53 @@ def fasta_scan(text, strict: bool = False, concatenate_headers: bool = True, all
     return FastaScan(raw, masks[: n_masks.value], list(recs[: n_records.value]))
 
 
+def fasta_translate_frames(text, table: int = 1, frames: int = N.FRAMES_ALL, strict: bool = False, concatenate_headers: bool = True,
+                           allow_preceding_comment: bool = False, ctx: Optional[N.Context] = None):
+    """FASTA text in, the frames of every record out, in ONE call (qd_fasta_translate_frames): the scanner's masks and CSR
+    offsets stay on the device and feed the frame kernels.  Returns (FastaScan without masks, FramesBatch): headers and
+    line ranges of the records, and their frames in the slot layout -- `frames.sequence_frames(i)` are the frames the
+    reference returns for record i (FastaParser::parse + translate_all_frames per record)."""
+    ctx = ctx or N.default_context()
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    a = _u8(raw)
+    L = N.lib()
+    n_records, out_bytes = C.c_size_t(), C.c_size_t()
+    err = N.QdErr()
+    head = (ctx.handle, table, int(strict), frames, int(concatenate_headers), int(allow_preceding_comment), _p(a if a.size else np.zeros(1, np.uint8)), a.size)
+
+    def call(recs, cap, out, out_cap, offs):
+        rc = L.qd_fasta_translate_frames(*head, recs, cap, C.byref(n_records), None if out is None else _p(out), out_cap,
+                                         None if offs is None else _p(offs), C.byref(out_bytes), C.byref(err))
+        if rc in (1, 2, 3):
+            e = N.make_error(err)
+            fe = FastaError(str(e), e.kind, e.byte, e.pos, 0)
+            fe.line = int(err.seq_index)
+            raise fe
+        return rc
+
+    # one call in the usual case: generous guesses for both capacities; the failed call reports what is needed
+    n_slots = 1 if frames == N.FRAMES_ONE else frames
+    cap = a.size // 64 + 16
+    out_cap = 16 * n_slots * (a.size // 48 + cap)
+    out = np.empty(max(out_cap, 1), dtype=np.uint8)  # untouched pages cost nothing
+    rec_bytes = np.empty(cap * C.sizeof(FastaRecordC), dtype=np.uint8)
+    offs = np.empty(cap + 1, dtype=np.uint64)
+    rc = call(C.c_void_p(rec_bytes.ctypes.data), cap, out, out_cap, offs)
+    if rc == N.QD_ERR_INVALID_ARGUMENT and (n_records.value > cap or out_bytes.value > out_cap):
+        cap, out_cap = max(cap, n_records.value), max(out_cap, out_bytes.value)
+        out = np.empty(max(out_cap, 1), dtype=np.uint8)
+        rec_bytes = np.empty(cap * C.sizeof(FastaRecordC), dtype=np.uint8)
+        offs = np.empty(cap + 1, dtype=np.uint64)
+        rc = call(C.c_void_p(rec_bytes.ctypes.data), cap, out, out_cap, offs)
+    ctx.check(rc, err, table)
+    k = n_records.value
+    recs = list((FastaRecordC * max(k, 1)).from_buffer(rec_bytes)[:k])
+    scan = FastaScan(raw, None, recs)
+    lengths = np.array([r.content_end - r.content_begin for r in recs], dtype=np.uint64)
+    out_offsets = offs[: k + 1].copy() if k else np.zeros(1, dtype=np.uint64)
+    return scan, FramesBatch(out[: out_bytes.value], out_offsets, lengths, frames)
+
+
 def canonical(dna, forward_only: bool = False, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None) -> np.ndarray:
     """DnaSequence::<Nucleotide>::canonical of one sequence of any length (src/rust_api.rs:374-377)."""
     ctx = ctx or N.default_context()

@@ -75,16 +75,14 @@ constexpr size_t TINY_IN_BYTES = size_t(128) << 10, TINY_OUT_BYTES = size_t(288)
 class HostPool {
 public:
     explicit HostPool(int n) {
-        for (int i = 0; i < n; i++) workers_.emplace_back([this, i, n] { loop(i, n); });
-    }
-    ~HostPool() {
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            stop_ = true;
+        try {
+            for (int i = 0; i < n; i++) workers_.emplace_back([this, i, n] { loop(i, n); });
+        } catch (...) {
+            shutdown();
+            throw;
         }
-        work_.notify_all();
-        for (auto& t : workers_) t.join();
     }
+    ~HostPool() { shutdown(); }
     // blocking memcpy, split over the workers
     void copy(void* dst, const void* src, size_t n) {
         if (n < (size_t(1) << 20) || workers_.empty()) {
@@ -102,6 +100,15 @@ public:
     }
 
 private:
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        work_.notify_all();
+        for (auto& t : workers_) t.join();
+        workers_.clear();
+    }
     void loop(int i, int n_workers) {
         uint64_t seen = 0;
         for (;;) {
@@ -1045,7 +1052,11 @@ static HostPool* stage_pool(qd_ctx* c) {
     if (!c->pool) {
         int t = c->stage_threads;
         if (t < 0) t = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 2));
-        c->pool = new HostPool(t);
+        try {
+            c->pool = new HostPool(t);
+        } catch (...) {  // no threads to be had: the calling thread copies alone (nothing may be thrown across the C ABI)
+            c->pool = new HostPool(0);
+        }
     }
     return c->pool;
 }
@@ -1371,21 +1382,9 @@ static int fasta_write_dev(qd_ctx* c, FastaRun& R, uint8_t* masks_dev, FastaReco
     return QD_OK;
 }
 
-extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int allow_preceding_comment, const uint8_t* text, size_t n,
-                             uint8_t* masks, size_t* n_masks, qd_fasta_record* records, size_t max_records, size_t* n_records, qd_err* err) {
-    clear_err(err);
-    if (n_masks) *n_masks = 0;
-    if (n_records) *n_records = 0;
-    if (!c || (n && !text)) return QD_ERR_INVALID_ARGUMENT;
-    Guard g(c);
-    if (!g.ok) return QD_ERR_CUDA;
-    if (n == 0) return QD_OK;
-    cudaStream_t s = c->stream;
-    QD_CUDA(c, c->in.reserve(n + 16));
-    if (int rc = staged_upload(c, c->in.p, text, n, s)) return rc;
-    if (int rc = reset_err_key(c, s)) return rc;
-    FastaRun R;
-    if (int rc = fasta_count_dev(c, strict, concatenate_headers, allow_preceding_comment, c->in.as<uint8_t>(), n, R, s)) return rc;
+// after fasta_count_dev: totals and the first content error (synchronises the stream).  `text` is the host copy of the input.
+static int fasta_totals(qd_ctx* c, int strict, int allow_preceding_comment, const uint8_t* text, const FastaRun& R, cudaStream_t s,
+                        uint64_t* total_kept, uint64_t* total_records, uint64_t* shift_out, qd_err* err) {
     const FastaParams& p = R.p;
     // totals: kept bytes, record starts, first header position, kept before it inside its block
     QD_CUDA(c, cudaMemcpyAsync(c->h_scratch + 0, p.pre_kept + p.n_blocks, 8, cudaMemcpyDeviceToHost, s));
@@ -1401,8 +1400,8 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
         if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
         return set_err(err, kind, payload, key, line);
     }
-    const uint64_t total_kept = c->h_scratch[0], rec_starts = c->h_scratch[1], first_header = c->h_scratch[2];
-    uint64_t before = total_kept;
+    const uint64_t kept = c->h_scratch[0], rec_starts = c->h_scratch[1], first_header = c->h_scratch[2];
+    uint64_t before = kept;
     if (first_header != FA_NONE) {
         const uint64_t blk = ((reinterpret_cast<uintptr_t>(p.text) & 15) + first_header) / FA_BLOCK_BYTES;
         uint64_t pre = 0;
@@ -1410,8 +1409,29 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
         QD_CUDA(c, cudaStreamSynchronize(s));
         before = pre + c->h_scratch[3];
     }
-    const uint64_t shift = (!allow_preceding_comment && before > 0) ? 1 : 0;
-    const uint64_t total_records = rec_starts + shift;
+    *shift_out = (!allow_preceding_comment && before > 0) ? 1 : 0;
+    *total_kept = kept;
+    *total_records = rec_starts + *shift_out;
+    return QD_OK;
+}
+
+extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int allow_preceding_comment, const uint8_t* text, size_t n,
+                             uint8_t* masks, size_t* n_masks, qd_fasta_record* records, size_t max_records, size_t* n_records, qd_err* err) {
+    clear_err(err);
+    if (n_masks) *n_masks = 0;
+    if (n_records) *n_records = 0;
+    if (!c || (n && !text)) return QD_ERR_INVALID_ARGUMENT;
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    if (int rc = staged_upload(c, c->in.p, text, n, s)) return rc;
+    if (int rc = reset_err_key(c, s)) return rc;
+    FastaRun R;
+    if (int rc = fasta_count_dev(c, strict, concatenate_headers, allow_preceding_comment, c->in.as<uint8_t>(), n, R, s)) return rc;
+    uint64_t total_kept = 0, total_records = 0, shift = 0;
+    if (int rc = fasta_totals(c, strict, allow_preceding_comment, text, R, s, &total_kept, &total_records, &shift, err)) return rc;
     if (n_masks) *n_masks = (size_t)total_kept;
     if (n_records) *n_records = (size_t)total_records;
     if (!masks && !records) return QD_OK;  // counting call
@@ -1422,6 +1442,64 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
     if (total_records) QD_CUDA(c, cudaMemcpyAsync(records, c->aux0.p, total_records * sizeof(FastaRecord), cudaMemcpyDeviceToHost, s));
     if (total_kept)
         if (int rc = staged_download(c, masks, c->out.p, total_kept, s)) return rc;
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    return QD_OK;
+}
+
+// FASTA text in, the frames of every record out: the scanner's masks and CSR offsets feed the frame kernels on the device,
+// nothing but the text goes up and nothing but records and frames comes back.
+extern "C" int qd_fasta_translate_frames(qd_ctx* c, int table, int strict, int frames, int concatenate_headers, int allow_preceding_comment,
+                                         const uint8_t* text, size_t n, qd_fasta_record* records, size_t max_records, size_t* n_records,
+                                         uint8_t* out, size_t out_capacity, uint64_t* out_offsets, size_t* out_bytes, qd_err* err) {
+    clear_err(err);
+    if (n_records) *n_records = 0;
+    if (out_bytes) *out_bytes = 0;
+    if (!c || !valid_frames(frames) || (n && !text)) return QD_ERR_INVALID_ARGUMENT;
+    int slot;
+    if (int rc = check_table(table, err, &slot)) return rc;  // table first, as everywhere
+    Guard g(c);
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n == 0) return QD_OK;
+    cudaStream_t s = c->stream;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    if (int rc = staged_upload(c, c->in.p, text, n, s)) return rc;
+    if (int rc = reset_err_key(c, s)) return rc;
+    FastaRun R;
+    if (int rc = fasta_count_dev(c, strict, concatenate_headers, allow_preceding_comment, c->in.as<uint8_t>(), n, R, s)) return rc;
+    uint64_t total_kept = 0, total_records = 0, shift = 0;
+    if (int rc = fasta_totals(c, strict, allow_preceding_comment, text, R, s, &total_kept, &total_records, &shift, err)) return rc;
+    if (n_records) *n_records = (size_t)total_records;
+    if (total_records == 0) return QD_OK;
+    // masks and records stay on the device
+    QD_CUDA(c, c->aux1.reserve(total_kept + 16));
+    QD_CUDA(c, c->aux0.reserve((total_records + 1) * sizeof(FastaRecord)));
+    QD_CUDA(c, c->aux2.reserve((total_records + 1) * sizeof(uint64_t)));
+    if (int rc = fasta_write_dev(c, R, c->aux1.as<uint8_t>(), c->aux0.as<FastaRecord>(), total_records, total_records, shift, s)) return rc;
+    const unsigned g1 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total_records + 256) / 256, (uint64_t)c->sm_count * 8));
+    fasta_offsets_kernel<<<g1, 256, 0, s>>>(c->aux0.as<FastaRecord>(), total_records, total_kept, c->aux2.as<uint64_t>());
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    // frames of all records (slot layout of qd_translate_frames_batch); the exact size is the run total the device finds
+    const uint64_t stride = 16 * (uint64_t)frames;
+    const uint64_t runs_bound = total_kept / RUN_NT + total_records;
+    QD_CUDA(c, c->out.reserve(runs_bound * stride + 16));
+    if (int rc = frames_csr_dev(c, slot, QD_ENC_MASK, strict, frames, c->aux1.as<uint8_t>(), total_kept, c->aux2.as<uint64_t>(), total_records,
+                                c->run_prefix, c->tile_first, c->block_sums, c->out.as<uint8_t>(), s))
+        return rc;
+    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->run_prefix.as<uint64_t>() + total_records, 8, cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    const uint64_t need = c->h_scratch[0] * stride;
+    if (out_bytes) *out_bytes = (size_t)need;
+    if (!out && !records) return QD_OK;  // sizing call
+    if (!out || !records || max_records < total_records || out_capacity < need) return QD_ERR_INVALID_ARGUMENT;
+    QD_CUDA(c, cudaMemcpyAsync(records, c->aux0.p, total_records * sizeof(FastaRecord), cudaMemcpyDeviceToHost, s));
+    if (out_offsets) {
+        QD_CUDA(c, cudaMemcpyAsync(out_offsets, c->run_prefix.p, (total_records + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        for (uint64_t i = 0; i <= total_records; i++) out_offsets[i] *= stride;
+    }
+    if (need)
+        if (int rc = staged_download(c, out, c->out.p, need, s)) return rc;
     QD_CUDA(c, cudaStreamSynchronize(s));
     return QD_OK;
 }

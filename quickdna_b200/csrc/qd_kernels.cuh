@@ -3252,6 +3252,14 @@ __global__ void __launch_bounds__(256) fasta_finish_kernel(const FastaParams p, 
 // endian) weighs K(J) = mix64(J * GOLDEN + 1) | 1; the checksum is sum_J word_J * K(J) mod 2^64.  Linear in the data, so
 // pieces of a stream -- the chunks of an output ring, the shards of the GPUs of a box -- add up to the checksum of the
 // whole whatever their byte alignment.  HBM-bound read (8 B per mix64).
+// CSR offsets of the records of a FASTA scan (what the batch entry points take): offsets[i] = records[i].content_begin,
+// offsets[n_records] = the number of masks
+__global__ void __launch_bounds__(256) fasta_offsets_kernel(const FastaRecord* __restrict__ records, uint64_t n_records, uint64_t total_kept,
+                                                            uint64_t* __restrict__ offsets) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_records; i += (uint64_t)gridDim.x * blockDim.x)
+        offsets[i] = i < n_records ? records[i].content_begin : total_kept;
+}
+
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t checksum_weight(uint64_t word_index) {
     return canon_mix64(word_index * 0x9e3779b97f4a7c15ull + 1ull) | 1ull;
