@@ -207,7 +207,7 @@ struct qd_ctx {
     bool dev_pending = false;
     std::map<uint64_t, int> occ_cache;  // (kernel id, smem bytes) -> resident CTAs per SM, attribute already set
     bool aligned_tiles = true;  // QD_ALIGNED_TILES=0 turns the whole-sequence tiles of the frame kernels off (A/B measurements)
-    uint32_t ctile_wpt[2] = {448, 192};  // canonical tile kernel: windows per warp-tile for keys / rows (QD_CTILE_WPT_* read once)
+    uint32_t ctile_wpt[2] = {960, 448};  // canonical tile kernel: windows per warp-tile for keys / rows (QD_CTILE_WPT_* read once)
 };
 
 namespace {
@@ -934,8 +934,10 @@ static int launch_canonical_tiles(qd_ctx* c, CanonKeyParams kp, cudaStream_t s) 
     const CanonParams& p = kp.base;
     const bool rows = MODE == CTILE_ROWS;
     const uint64_t nw = p.seq_len - p.w + 1;
-    // keys: 448 + 41 + slack = 16 x 32 positions for w = 42 is two rounds of the per-position pass;
-    // rows: 192 + 41 + slack = 8 x 32 is one round (rows are staged and copied out 64 at a time)
+    // 448 + 41 + slack = 16 x 32 positions for w = 42 is two full rounds of the per-position pass (192 and 704 fill one and
+    // three; anything between wastes lanes of the last round).  Rows are staged and copied out 64 at a time whatever the tile,
+    // so the larger tile only spreads the halo (w - 1 + look-ahead positions decoded per tile) over more windows: measured
+    // on 768 x 99 999 nt, rows: 192 -> 0.586, 256 -> 0.563, 448 -> 0.629, 704 -> 0.633, 1024 -> 0.606 of the copy peak.
     uint32_t wpt = c->ctile_wpt[rows ? 1 : 0];
     while (wpt > 64 && ckey_span_bound(wpt, p.w, nw) > 2048) wpt -= 64;
     kp.wpt = wpt;
