@@ -1190,7 +1190,7 @@ static int staged_download(qd_ctx* c, uint8_t* host, const void* dev, size_t n, 
 // src/rust_api.rs:310-322 on device buffers: counts per 4 KiB block, scan, compacted write.
 // n_masks_dev receives the number of masks written (device uint64).
 static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, uint8_t* masks_dev, uint64_t* n_masks_dev,
-                     cudaStream_t s) {
+                     cudaStream_t s, unsigned long long* err_key = nullptr) {
     if (n == 0) {
         if (n_masks_dev) QD_CUDA(c, cudaMemsetAsync(n_masks_dev, 0, 8, s));
         return QD_OK;
@@ -1212,7 +1212,7 @@ static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, 
     p.counts = c->parse_counts.as<uint64_t>();
     p.offsets = c->parse_offsets.as<uint64_t>();
     p.out = masks_dev;
-    p.err_key = c->d_err;
+    p.err_key = err_key ? err_key : c->d_err;
     p.gate = c->d_gate;
     p.gate_gen = ++c->gate_gen;
     // One streaming pass finishes input without whitespace (when input and output share their 16-byte phase); the scan
@@ -1247,6 +1247,24 @@ extern "C" int qd_parse(qd_ctx* c, int strict, const uint8_t* ascii, size_t n, u
     if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
     cudaStream_t s = c->stream;
+    if (c->tiny_calls && n <= TINY_IN_BYTES) {
+        // tiny call: letters, mask count, error key and masks in mapped host memory -- three launches, one synchronise, no copies
+        uint8_t* const h_in = c->h_tiny;
+        unsigned long long* const h_cnt = reinterpret_cast<unsigned long long*>(c->h_tiny + TINY_IN_BYTES);
+        unsigned long long* const h_key = reinterpret_cast<unsigned long long*>(c->h_tiny + TINY_IN_BYTES + 16);
+        uint8_t* const h_out = c->h_tiny + TINY_IN_BYTES + 64;
+        memcpy(h_in, ascii, n);
+        *h_key = NO_ERROR_KEY;
+        *h_cnt = 0;
+        if (int rc = parse_dev(c, strict, h_in, n, h_out, reinterpret_cast<uint64_t*>(h_cnt), s, h_key)) return rc;
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        const unsigned long long key = *h_key;
+        if (key != NO_ERROR_KEY) return report_single(QD_ENC_ASCII, strict, ascii, key, err);
+        const size_t k = (size_t)*h_cnt;
+        memcpy(masks, h_out, k);
+        if (n_masks) *n_masks = k;
+        return QD_OK;
+    }
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(n + 16));
     QD_CUDA(c, c->aux0.reserve(8));
