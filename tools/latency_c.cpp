@@ -1,0 +1,36 @@
+// Latency of the tiny host calls from C (no Python in the way): g++ -O2 -I include tools/latency_c.cpp -o tools/latency_c -L quickdna_b200 -lquickdna_b200 -Wl,-rpath,$PWD/quickdna_b200
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "quickdna_b200.h"
+
+int main() {
+    qd_ctx* c = nullptr;
+    if (qd_ctx_create(&c, 0) != 0) return 1;
+    const size_t n = 29901;
+    std::vector<uint8_t> dna(n), out(3 * n);
+    uint64_t x = 88172645463325252ull;
+    for (size_t i = 0; i < n; i++) {
+        x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+        dna[i] = "ACGT"[x & 3];
+    }
+    qd_err err;
+    size_t lens[6];
+    int nf;
+    auto time_it = [&](const char* name, auto fn) {
+        for (int i = 0; i < 50; i++) fn();
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < 2000; i++) fn();
+        double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / 2000;
+        printf("%-28s %7.2f us per call\n", name, us);
+    };
+    time_it("qd_translate", [&] { qd_translate(c, 1, QD_ENC_ASCII, 0, dna.data(), n, out.data(), &err); });
+    time_it("qd_revcomp", [&] { qd_revcomp(c, QD_ENC_ASCII, 0, dna.data(), n, out.data(), &err); });
+    time_it("qd_translate_frames (6)", [&] { qd_translate_frames(c, 1, QD_ENC_ASCII, 0, QD_FRAMES_ALL, dna.data(), n, out.data(), lens, &nf, &err); });
+    size_t k;
+    time_it("qd_parse", [&] { qd_parse(c, 0, dna.data(), n, out.data(), &k, &err); });
+    qd_ctx_destroy(c);
+    return 0;
+}
