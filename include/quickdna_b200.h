@@ -193,6 +193,15 @@ int qd_fasta_scan(qd_ctx *ctx, int strict, int concatenate_headers, int allow_pr
                   const uint8_t *text, size_t n, uint8_t *masks, size_t *n_masks, qd_fasta_record *records,
                   size_t max_records, size_t *n_records, qd_err *err);
 
+/* qd_fasta_scan on device buffers (asynchronous up to ONE synchronisation of `stream`: the totals of the first pass size the
+ * second): text_dev in; masks_dev (capacity n), records_dev (capacity max_records) and, optionally, offsets_dev
+ * (max_records + 1 entries: the CSR offsets qd_translate_frames_batch_dev takes with QD_ENC_MASK) out.  *n_masks / *n_records
+ * are host values.  masks_dev == records_dev == NULL counts only. */
+int qd_fasta_scan_dev(qd_ctx *ctx, int strict, int concatenate_headers, int allow_preceding_comment,
+                      const uint8_t *text_dev, size_t n, uint8_t *masks_dev, size_t *n_masks,
+                      qd_fasta_record *records_dev, size_t max_records, size_t *n_records, uint64_t *offsets_dev,
+                      qd_err *err, void *stream);
+
 /* FASTA text in, the frames of every record out: FastaParser::parse (src/fasta.rs:207-491) followed by
  * translate / translate_self_frames / translate_all_frames (src/rust_api.rs:227-270) of every record, in one call.  The
  * scanner's masks and CSR offsets feed the frame kernels on the device: only the text goes up, only records and frames

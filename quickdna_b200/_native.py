@@ -107,6 +107,7 @@ SIGNATURES = {
     "qd_canonical_window_keys_dev": (_i, [_vp, _i, _i, _i, _vp, _sz, _sz, _sz, _vp, _vp]),
     "qd_expansion_windows_dev": (_i, [_vp, _i, _vp, _sz, _sz, C.c_uint64, _vp, _vp, _vp, C.c_uint64, _vp]),
     "qd_fasta_scan": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz), C.POINTER(QdErr)]),
+    "qd_fasta_scan_dev": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz), _vp, C.POINTER(QdErr), _vp]),
     "qd_fasta_translate_frames": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz, C.POINTER(_sz), _vp, _sz, _vp, C.POINTER(_sz), C.POINTER(QdErr)]),
     "qd_windows_batch_dev": (_i, [_vp, _vp, _sz, _sz, _sz, _i, _vp, _vp]),
     "qd_windows_all_batch_counts": (_sz, [_sz, _sz, _sz, C.POINTER(_sz)]),

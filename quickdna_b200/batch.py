@@ -478,6 +478,42 @@ def translate_frames_csr_dev(dna, offsets, out=None, table: int = 1, strict: boo
     return out
 
 
+def fasta_scan_dev(text, strict: bool = False, concatenate_headers: bool = True, allow_preceding_comment: bool = False,
+                   max_records: Optional[int] = None, ctx: Optional[N.Context] = None):
+    """qd_fasta_scan_dev on a torch uint8 CUDA tensor holding FASTA text: returns (masks [n_masks] uint8, records [n_records, 6]
+    int64 -- header_begin, header_end, content_begin, content_end, line_begin, line_end --, offsets [n_records + 1] int64),
+    all on the device: masks and offsets are what translate_frames_csr_dev(enc=ENC_MASK) takes."""
+    import torch
+
+    ctx = ctx or N.default_context(text.device.index or 0)
+    n = text.numel()
+    cap = max_records if max_records is not None else n // 64 + 16
+    masks = torch.empty(max(n, 1), dtype=torch.uint8, device=text.device)
+    n_masks, n_records = C.c_size_t(), C.c_size_t()
+    err = N.QdErr()
+    L = N.lib()
+
+    def call(cap):
+        recs = torch.empty((cap, 6), dtype=torch.int64, device=text.device)
+        offs = torch.empty(cap + 1, dtype=torch.int64, device=text.device)
+        rc = L.qd_fasta_scan_dev(ctx.handle, int(strict), int(concatenate_headers), int(allow_preceding_comment), C.c_void_p(text.data_ptr()), n,
+                                 C.c_void_p(masks.data_ptr()), C.byref(n_masks), C.c_void_p(recs.data_ptr()), cap, C.byref(n_records),
+                                 C.c_void_p(offs.data_ptr()), C.byref(err), _stream_ptr(torch))
+        return rc, recs, offs
+
+    rc, recs, offs = call(cap)
+    if rc == N.QD_ERR_INVALID_ARGUMENT and n_records.value > cap:
+        rc, recs, offs = call(n_records.value)
+    if rc in (1, 2, 3):
+        e = N.make_error(err)
+        fe = FastaError(str(e), e.kind, e.byte, e.pos, 0)
+        fe.line = int(err.seq_index)
+        raise fe
+    ctx.check(rc, err)
+    k = n_records.value
+    return masks[: n_masks.value], recs[:k], offs[: k + 1]
+
+
 def parse_dev(ascii_seq, out=None, strict: bool = False, ctx: Optional[N.Context] = None):
     """qd_parse_dev on a torch uint8 CUDA tensor: returns (masks buffer, device int64[1] count)."""
     import torch

@@ -1466,6 +1466,53 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
     return QD_OK;
 }
 
+// the scanner on device buffers: text_dev in; masks_dev (capacity n), records_dev (capacity max_records) and offsets_dev
+// (capacity max_records + 1, optional) out.  Synchronises `stream` once (the totals size the second pass); on a content error
+// err->pos is the byte offset and err->seq_index the 1-based line number, counted on the device copy of the text.
+extern "C" int qd_fasta_scan_dev(qd_ctx* c, int strict, int concatenate_headers, int allow_preceding_comment, const uint8_t* text_dev, size_t n,
+                                 uint8_t* masks_dev, size_t* n_masks, qd_fasta_record* records_dev, size_t max_records, size_t* n_records,
+                                 uint64_t* offsets_dev, qd_err* err, void* stream) {
+    clear_err(err);
+    if (n_masks) *n_masks = 0;
+    if (n_records) *n_records = 0;
+    if (!c || (n && !text_dev)) return QD_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = pick_stream(c, stream);
+    Guard g(c, s);
+    if (!g.ok) return QD_ERR_CUDA;
+    if (n == 0) return QD_OK;
+    if (int rc = reset_err_key(c, s)) return rc;
+    FastaRun R;
+    if (int rc = fasta_count_dev(c, strict, concatenate_headers, allow_preceding_comment, text_dev, n, R, s)) return rc;
+    // the totals; a content error is located with the text still on the device: its byte, and the newlines in front of it
+    unsigned long long key = 0;
+    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
+    if (key != NO_ERROR_KEY) {
+        std::vector<uint8_t> head(key + 1);
+        QD_CUDA(c, cudaMemcpyAsync(head.data(), text_dev, key + 1, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        uint64_t line = 1;
+        for (size_t i = 0; i < key; i++) line += head[i] == '\n';
+        uint8_t payload = 0;
+        int kind = classify_byte(QD_ENC_ASCII, strict, head[key], &payload);
+        if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+        return set_err(err, kind, payload, key, line);
+    }
+    uint64_t total_kept = 0, total_records = 0, shift = 0;
+    if (int rc = fasta_totals(c, strict, allow_preceding_comment, nullptr, R, s, &total_kept, &total_records, &shift, err)) return rc;
+    if (n_masks) *n_masks = (size_t)total_kept;
+    if (n_records) *n_records = (size_t)total_records;
+    if (!masks_dev && !records_dev) return QD_OK;  // counting call
+    if (!masks_dev || (total_records && !records_dev) || max_records < total_records) return QD_ERR_INVALID_ARGUMENT;
+    if (int rc = fasta_write_dev(c, R, masks_dev, reinterpret_cast<FastaRecord*>(records_dev), total_records, total_records, shift, s)) return rc;
+    if (offsets_dev) {
+        const unsigned g1 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total_records + 256) / 256, (uint64_t)c->sm_count * 8));
+        fasta_offsets_kernel<<<g1, 256, 0, s>>>(reinterpret_cast<const FastaRecord*>(records_dev), total_records, total_kept, offsets_dev);
+        c->launches++;
+        QD_CUDA(c, cudaGetLastError());
+    }
+    return QD_OK;
+}
+
 // FASTA text in, the frames of every record out: the scanner's masks and CSR offsets feed the frame kernels on the device,
 // nothing but the text goes up and nothing but records and frames comes back.
 extern "C" int qd_fasta_translate_frames(qd_ctx* c, int table, int strict, int frames, int concatenate_headers, int allow_preceding_comment,

@@ -98,3 +98,32 @@ def test_fasta_translate_frames_large(B):
         assert fb.sequence_frames(i) == oracle.py_all_frames(1, oracle.ascii_of(two.record(i)[1]))
     fb2 = B.translate_frames_batch((two.masks, two.offsets), frames=6, enc=1)
     assert np.array_equal(fb.data, fb2.data)
+
+
+def test_fasta_scan_dev_chains_into_the_frame_kernels(B, N):
+    """Text resident on the device -> masks, records, CSR offsets on the device -> frames, nothing crossing PCIe in between."""
+    import torch
+
+    rng = np.random.default_rng(23)
+    text = _fasta(rng, 2_000, crlf=True, lo=0, hi=3000)
+    d = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).cuda()
+    masks, recs, offs = B.fasta_scan_dev(d)
+    host = B.fasta_scan(text)
+    assert np.array_equal(masks.cpu().numpy(), host.masks)
+    assert np.array_equal(offs.cpu().numpy().astype(np.uint64), host.offsets)
+    r = recs.cpu().numpy()
+    assert [(int(a), int(b)) for a, b in r[:, 4:6]] == host.line_ranges
+    out = B.translate_frames_csr_dev(masks, offs, table=1, frames=6, enc=N.ENC_MASK)
+    want = B.translate_frames_batch((host.masks, host.offsets), frames=6, enc=1)
+    assert np.array_equal(out.cpu().numpy(), want.data)
+    # too small a record capacity: the call reports the count, the wrapper retries
+    masks2, recs2, offs2 = B.fasta_scan_dev(d, max_records=10)
+    assert torch.equal(recs2, recs) and torch.equal(offs2, offs)
+    bad = bytearray(text)
+    bad[len(bad) // 2] = ord("!") if bad[len(bad) // 2] not in b">\r\n" else bad[len(bad) // 2]
+    if bytes(bad) != text:
+        with pytest.raises(ValueError) as ei:
+            B.fasta_scan_dev(torch.from_numpy(np.frombuffer(bytes(bad), dtype=np.uint8).copy()).cuda())
+        with pytest.raises(ValueError) as eh:
+            B.fasta_scan(bytes(bad))
+        assert (ei.value.line, ei.value.pos, ei.value.kind) == (eh.value.line, eh.value.pos, eh.value.kind)
