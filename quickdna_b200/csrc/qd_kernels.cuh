@@ -221,6 +221,19 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// one elected lane of a converged warp (the pattern ptxas recognises: a uniform-datapath instruction behind it needs no loop
+// over the lanes' operand values)
+__device__ __forceinline__ bool elect_one_lane() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -2159,6 +2172,9 @@ __global__ void __launch_bounds__(32 * EXP_WARPS) expansion_write_tiles_kernel(c
 #endif
 constexpr int EXP_FUSED_WARPS = QD_EXP_FUSED_WARPS;
 constexpr uint64_t EXP_STATE_VALUE = (1ull << 62) - 1;
+#ifndef QD_EXP_ELECT
+#define QD_EXP_ELECT 1
+#endif
 #ifndef QD_EXP_LOOK
 #define QD_EXP_LOOK 1  // 1 -> 1.74 ms, 2 -> 1.77, 4 -> 1.79, 8 -> 1.87 for 2e7 windows
 #endif
@@ -2422,11 +2438,27 @@ __global__ void __launch_bounds__(32 * EXP_FUSED_WARPS, W ? 4 : 3) expansion_fus
             const bool last = r0 + 32u >= rows_out;
             const uint32_t start_off = r0 == 0 ? ((phase + 15u) & ~15u) : 0u;  // a tile's first granule may belong to the tile before
             const uint32_t end_off = phase + nrows * w, body_end = last ? (end_off & ~15u) : min(end_off & ~15u, 32u * w);
+#if QD_EXP_ELECT
+            {
+                // warp-uniform operands through the uniform datapath (REDUX writes a uniform register)
+                const uint64_t gaddr = reinterpret_cast<uint64_t>(galigned + start_off);
+                const uint32_t g_lo = __reduce_max_sync(0xffffffffu, (uint32_t)gaddr), g_hi = __reduce_max_sync(0xffffffffu, (uint32_t)(gaddr >> 32));
+                const uint32_t s_at = __reduce_max_sync(0xffffffffu, stage_base + start_off);
+                const uint32_t n_at = __reduce_max_sync(0xffffffffu, body_end > start_off ? body_end - start_off : 0u);
+                if (elect_one_lane()) {
+                    if (n_at) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(((uint64_t)g_hi << 32) | g_lo), "r"(s_at), "r"(n_at) : "memory");
+                    bulk_commit();
+                }
+            }
+#else
             if (lane == 0) {
                 if (body_end > start_off) bulk_s2g(galigned + start_off, stage + start_off, body_end - start_off);
                 bulk_commit();
             }
-            if (r0 == 0 && lane < (int)(min(start_off, end_off) - phase)) gtile[lane] = stage[phase + lane];
+#endif
+            if (r0 == 0) {  // (a branch the whole warp takes or skips)
+                if (lane < (int)(min(start_off, end_off) - phase)) gtile[lane] = stage[phase + lane];
+            }
             if (last) {
                 const uint32_t tail0 = max(body_end, start_off);  // (a tile shorter than a granule has no body)
                 if (tail0 + lane < end_off) galigned[tail0 + lane] = stage[tail0 + lane];
