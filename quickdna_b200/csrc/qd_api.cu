@@ -1611,9 +1611,15 @@ static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride,
     const uint64_t tiles = (uint64_t)n_seq * (1 + (len - w + 1 + wpt - 1) / wpt);  // + the short first tile of every sequence
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + WIN_WARPS - 1) / WIN_WARPS, (uint64_t)c->sm_count * 6));
     // the two window lengths of benches/all_windows.rs get fully unrolled instantiations
-    if (w == 42) windows_batch_kernel<42><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
-    else if (w == 20) windows_batch_kernel<20><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
-    else windows_batch_kernel<0><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+    if (p.map) {
+        if (w == 42) windows_batch_kernel<42, true><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+        else if (w == 20) windows_batch_kernel<20, true><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+        else windows_batch_kernel<0, true><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+    } else {  // plain copies: no table lookup per byte
+        if (w == 42) windows_batch_kernel<42, false><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+        else if (w == 20) windows_batch_kernel<20, false><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+        else windows_batch_kernel<0, false><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+    }
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;

@@ -1154,11 +1154,12 @@ struct WinAlign {
     }
 };
 
-template <int W>
+// MAP: bytes go through the 256-byte table p.map (DNA letters: upper case / complement + validation); plain copies skip it
+template <int W, bool MAP = true>
 __global__ void __launch_bounds__(32 * WIN_WARPS, W ? 6 : 4) windows_batch_kernel(const WindowsBatchParams p) {
     __shared__ WinWarpSmem SM[WIN_WARPS];
     __shared__ uint8_t map_s[256];
-    for (int i = threadIdx.x; i < 256; i += 32 * WIN_WARPS) map_s[i] = p.map ? __ldg(p.map + i) : (uint8_t)i;
+    for (int i = threadIdx.x; i < 256; i += 32 * WIN_WARPS) map_s[i] = MAP ? __ldg(p.map + i) : (uint8_t)i;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WinWarpSmem& S = SM[threadIdx.x >> 5];
@@ -1193,8 +1194,11 @@ __global__ void __launch_bounds__(32 * WIN_WARPS, W ? 6 : 4) windows_batch_kerne
         // (a word-granular version of this loop was measured slower: 3.4 vs 2.8 ms on the all_windows bench leg)
         for (uint32_t k = lane; k < span; k += 32) {
             const uint32_t at = p.reverse ? p.len - 1 - i0 - k : i0 + k;
-            const uint32_t v = map_s[__ldg(seq + at)];
-            if (v == 0 && p.map) atomicMin(p.err_key, (unsigned long long)(s * p.key_stride + at));
+            uint32_t v = __ldg(seq + at);
+            if (MAP) {  // (plain copies -- amino-acid windows, typed windows -- skip the table: one shared-memory access less per byte)
+                v = map_s[v];
+                if (v == 0) atomicMin(p.err_key, (unsigned long long)(s * p.key_stride + at));
+            }
             S.srcb[4 + k] = (uint8_t)v;  // 4-byte front pad: a row's first destination word may start before its window
         }
         if (TMA_OUT && lane == 0) bulk_wait_read_0();  // the previous tile's rows have left the stage
