@@ -186,3 +186,36 @@ def test_single_sequence_size_classes(N, B, ctx, n):
     with pytest.raises(ValueError) as ei:
         B.revcomp(bad, ctx=ctx)
     assert (ei.value.pos, ei.value.kind) == (n - 7, 2)
+
+
+def test_tiny_and_small_call_paths_agree(N, B, monkeypatch):
+    """Inputs of at most 128 KiB run on mapped host memory (one launch); QD_TINY_CALLS=0 (read when a context is made)
+    sends them through the copying path instead.  Same bytes, same errors."""
+    monkeypatch.setenv("QD_TINY_CALLS", "0")
+    plain = N.Context(0)
+    monkeypatch.delenv("QD_TINY_CALLS")
+    tiny = N.Context(0)
+    try:
+        rng = np.random.default_rng(8)
+        for n in (1, 2, 3, 47, 48, 49, 1000, 29_901, 131_072):
+            dna = np.frombuffer(b"ACGTacgtNRYK", dtype=np.uint8)[rng.integers(0, 12, n)].copy()
+            for frames in (N.FRAMES_ONE, N.FRAMES_SELF, N.FRAMES_ALL):
+                assert B.translate_frames(dna, table=4, frames=frames, ctx=tiny) == B.translate_frames(dna, table=4, frames=frames, ctx=plain)
+            assert np.array_equal(B.revcomp(dna, ctx=tiny), B.revcomp(dna, ctx=plain))
+            spaced = dna.copy()
+            spaced[::17] = 0x20
+            assert np.array_equal(B.parse(spaced, ctx=tiny), B.parse(spaced, ctx=plain))
+            assert np.array_equal(B.parse(dna, ctx=tiny), oracle.parse(dna.tobytes()))
+        reads = oracle.synth(3, 0, 100 * 1000).reshape(100, 1000)
+        assert np.array_equal(B.translate_frames_batch(reads, ctx=tiny).data, B.translate_frames_batch(reads, ctx=plain).data)
+        bad = reads.copy()
+        bad[57, 123] = ord("@")
+        errs = []
+        for c in (tiny, plain):
+            with pytest.raises(ValueError) as ei:
+                B.translate_frames_batch(bad, ctx=c)
+            errs.append((ei.value.seq_index, ei.value.pos, ei.value.kind, ei.value.byte))
+        assert errs[0] == errs[1] == (57, 123, 2, ord("@"))
+    finally:
+        tiny.close()
+        plain.close()
