@@ -565,6 +565,29 @@ def canonical_window_keys_dev(dna, n_seq: int, seq_len: int, w: int = 42, kind: 
     return flat.view(torch.int64) if kind == N.CANON_KEY_FP64 else flat.view(n_seq * nw, words)
 
 
+def canonical_window_keys_csr_dev(dna, offsets, w: int = 42, kind: int = N.CANON_KEY_FP64, forward_only: bool = False,
+                                  enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
+    """One key per canonical window of a VARIABLE-LENGTH batch (the masks + CSR offsets of fasta_scan_dev, say), by flat
+    position: the batch is run as ONE sequence, so the key of window j of sequence i sits at index offsets[i] + j, and the
+    w - 1 positions in front of every sequence end hold the keys of windows that span two sequences -- to be skipped.
+    Returns (keys, valid): keys as canonical_window_keys_dev over total - w + 1 positions, valid a bool tensor of the same
+    length (position p is valid iff p + w <= the end of its sequence)."""
+    import torch
+
+    total = dna.numel()
+    keys = canonical_window_keys_dev(dna, 1, total, w, kind=kind, forward_only=forward_only, enc=enc, ctx=ctx)
+    n_pos = max(0, total - w + 1)
+    offs = offsets.to(torch.int64)
+    # +1 at a sequence's start, -1 at the first start that no longer fits it: valid = the running sum is 1
+    delta = torch.zeros(n_pos + w + 1, dtype=torch.int32, device=dna.device)
+    starts, ends = offs[:-1], offs[1:]
+    fits = (ends - starts) >= w
+    delta.index_add_(0, starts[fits], torch.ones(int(fits.sum()), dtype=torch.int32, device=dna.device))
+    delta.index_add_(0, (ends - w + 1)[fits], -torch.ones(int(fits.sum()), dtype=torch.int32, device=dna.device))
+    valid = torch.cumsum(delta, 0)[:n_pos] > 0
+    return keys, valid
+
+
 def expansion_windows_dev(windows, max_expansions: int = 16, out=None, enc: int = N.ENC_ASCII, ctx: Optional[N.Context] = None):
     """qd_expansion_windows_dev on a torch uint8 CUDA tensor [n_win, w]: returns (counts, out_index, rows buffer); rows are
     written while they fit `out` (default: the worst case n_win * max_expansions rows)."""

@@ -127,3 +127,27 @@ def test_fasta_scan_dev_chains_into_the_frame_kernels(B, N):
         with pytest.raises(ValueError) as eh:
             B.fasta_scan(bytes(bad))
         assert (ei.value.line, ei.value.pos, ei.value.kind) == (eh.value.line, eh.value.pos, eh.value.kind)
+
+
+def test_fasta_to_canonical_window_keys_on_the_device(B, N):
+    """FASTA text -> masks + offsets -> one packed key per canonical 42-nt window of every record, nothing leaving the device:
+    the variable-length batch runs as one sequence, keys are indexed by flat position, seam positions are flagged invalid."""
+    import torch
+
+    rng = np.random.default_rng(31)
+    text = _fasta(rng, 300, lo=0, hi=400, alphabet=b"ACGTacgt")
+    d = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).cuda()
+    masks, recs, offs = B.fasta_scan_dev(d, strict=True)
+    keys, valid = B.canonical_window_keys_csr_dev(masks, offs, 42, kind=N.CANON_KEY_PACKED, enc=N.ENC_MASK)
+    keys, valid, o = keys.cpu().numpy(), valid.cpu().numpy(), offs.cpu().numpy()
+    m = masks.cpu().numpy()
+    n_valid = 0
+    for i in range(len(o) - 1):
+        seq = m[o[i]:o[i + 1]]
+        nw = max(0, len(seq) - 41)
+        assert valid[o[i]:o[i] + nw].all() and not valid[o[i] + nw:min(o[i + 1], len(valid))].any(), i
+        n_valid += nw
+        if nw and i % 7 == 0:
+            alone = B.canonical_window_keys_dev(torch.from_numpy(seq.copy()).cuda(), 1, len(seq), 42, kind=N.CANON_KEY_PACKED, enc=N.ENC_MASK)
+            assert np.array_equal(alone.cpu().numpy(), keys[o[i]:o[i] + nw]), i
+    assert int(valid.sum()) == n_valid
