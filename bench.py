@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--revcomp-nt", type=int, default=250_000_000)
     ap.add_argument("--window-seqs", type=int, default=80_000, help="99 999-nt sequences per GPU in the config-5 legs (64 GB / 8 GPUs)")
     ap.add_argument("--window-chunk-seqs", type=int, default=768, help="sequences per ring chunk of the canonical / all_windows legs")
-    ap.add_argument("--expansion-chunk", type=int, default=6_000_000, help="windows per ring chunk of the expansion leg")
+    ap.add_argument("--expansion-chunk", type=int, default=12_000_000, help="windows per ring chunk of the expansion leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
