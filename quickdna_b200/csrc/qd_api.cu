@@ -496,21 +496,43 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     QD_CUDA(c, run_prefix.reserve(2 * arr_entries * sizeof(uint64_t)));
     uint64_t* const rp_dev = run_prefix.as<uint64_t>();
     uint64_t* const off_pad = rp_dev + arr_entries;
-    QD_CUDA(c, cudaMemsetAsync(rp_dev + n_seq + 1, 0xff, (arr_entries - n_seq - 1) * sizeof(uint64_t), s));
-    QD_CUDA(c, cudaMemcpyAsync(off_pad, offsets_dev, (n_seq + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
-    QD_CUDA(c, cudaMemsetAsync(off_pad + n_seq + 1, 0xff, (arr_entries - n_seq - 1) * sizeof(uint64_t), s));
-    // one buffer: the tile map, then the 32-run map (padded by one tile's worth of entries)
+    // one buffer: the tile map, then the 32-run map (padded by one tile's worth of entries), then the lists of long sequences
     const size_t warp_map_off = ((n_tiles + 1) * sizeof(TileInfo) + 127) & ~(size_t)127;
     const uint64_t n_q = (uint64_t)(n_tiles + 1) * wq_stride;  // a slice of wq_stride entries per tile
-    QD_CUDA(c, tile_first.reserve(warp_map_off + (n_q + 8) * sizeof(uint32_t)));
-    int rc = device_exclusive_scan<0>(c, offsets_dev, n_seq, rp_dev, block_sums, s);
-    if (rc) return rc;
-    const unsigned g = (unsigned)std::min<uint64_t>((n_seq + 255) / 256, (uint64_t)c->sm_count * 8);
-    tile_info_kernel<<<g, 256, 0, s>>>(run_prefix.as<uint64_t>(), offsets_dev, flat_base, n_seq, tile_first.as<TileInfo>(), n_tiles, tile_runs);
+    const size_t long_off = (warp_map_off + (n_q + 8) * sizeof(uint32_t) + 15) & ~(size_t)15;
+    const size_t mid_cap = (size_t)(runs_upper_bound(total_nt, n_seq) / CSR_THREAD_RUNS) + 1;
+    const size_t long_cap = (size_t)(runs_upper_bound(total_nt, n_seq) / CSR_WARP_RUNS) + 1;
+    QD_CUDA(c, tile_first.reserve(long_off + 16 + (mid_cap + long_cap) * sizeof(uint32_t)));
     uint32_t* warp_first = reinterpret_cast<uint32_t*>(tile_first.as<uint8_t>() + warp_map_off);
-    const unsigned gq = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_q + 255) / 256, (uint64_t)c->sm_count * 8));
-    warp_map_kernel<<<gq, 256, 0, s>>>(run_prefix.as<uint64_t>(), n_seq, tile_first.as<TileInfo>(), tile_runs, wq_stride, warp_first);
-    c->launches += 2;
+    // scan of the run counts; its last pass writes the prefix, the padded copy of the offsets and both maps (csr_finish_kernel)
+    CsrMapParams m{};
+    m.offsets = offsets_dev;
+    m.n_seq = n_seq;
+    m.flat_base = flat_base;
+    m.run_prefix = rp_dev;
+    m.off_copy = off_pad;
+    m.arr_entries = arr_entries;
+    m.tiles = tile_first.as<TileInfo>();
+    m.n_tiles_cap = n_tiles;
+    m.tile_shift = 0;
+    while ((uint64_t(1) << m.tile_shift) < tile_runs) m.tile_shift++;
+    if ((uint64_t(1) << m.tile_shift) != tile_runs) {
+        c->last_error = "tile size is not a power of two";
+        return QD_ERR_INVALID_ARGUMENT;
+    }
+    m.wq_stride = wq_stride;
+    m.warp_first = warp_first;
+    m.list_counts = reinterpret_cast<unsigned int*>(tile_first.as<uint8_t>() + long_off);
+    m.mid_list = reinterpret_cast<uint32_t*>(tile_first.as<uint8_t>() + long_off + 16);
+    m.long_list = m.mid_list + mid_cap;
+    QD_CUDA(c, cudaMemsetAsync(m.list_counts, 0, 2 * sizeof(unsigned int), s));
+    const uint64_t n_blocks = std::max<uint64_t>(1, (n_seq + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
+    scan_block_sums_kernel<0, 0><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(offsets_dev, n_seq, block_sums.as<uint64_t>(), nullptr, 0);
+    scan_spine_kernel<0><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, nullptr, 0);
+    csr_finish_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(m, block_sums.as<uint64_t>());
+    csr_listed_kernel<<<(unsigned)std::min<uint64_t>((mid_cap + 7) / 8 + long_cap, (uint64_t)c->sm_count * 4), 256, 0, s>>>(m);
+    c->launches += 4;
     QD_CUDA(c, cudaGetLastError());
     FramesParams p{};
     p.dna = dna_dev;

@@ -2626,42 +2626,136 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) dst[0] = 0;
 }
 
-// tiles[t] = {flat offset of run t*tile_runs, sequence containing it}
-__global__ void __launch_bounds__(256) tile_info_kernel(const uint64_t* __restrict__ run_prefix, const uint64_t* __restrict__ offsets,
-                                                        uint64_t flat_base, uint64_t n_seq, TileInfo* __restrict__ tiles,
-                                                        uint64_t n_tiles_cap, uint64_t tile_runs) {
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_seq; r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t a = run_prefix[r], b = run_prefix[r + 1];
-        if (b == a) continue;
-        const uint64_t o0 = offsets[r] - flat_base;
-        uint64_t t = (a + tile_runs - 1) / tile_runs;
-        for (; t * tile_runs < b && t < n_tiles_cap; t++) {
-            TileInfo ti;
-            ti.flat = o0 + (t * tile_runs - a) * RUN_NT;
-            ti.first_seq = (uint32_t)r;
-            ti.pad_ = 0;
-            tiles[t] = ti;
+// ------------------------------------------------------------------------------------------------
+// The maps a variable-length batch needs before the frame kernel, written by the LAST pass of the scan of its run
+// counts (one kernel instead of scan-finish + two map kernels + a copy of the offsets + two fills):
+//   run_prefix[r]           runs before sequence r (exclusive scan of ceil(len / 48)), [n_seq] = the total
+//   off_copy[r]             the offsets once more, next to the prefix (the frame kernel bulk-copies windows of both)
+//   both padded with ~0 up to arr_entries
+//   tiles[t]                {flat offset of run t * tile_runs, the sequence that holds it}
+//   warp_first[t * wq_stride + j]   the sequence that holds run t * tile_runs + 32 j
+// Every 32nd run g lies in exactly one sequence (a <= g < b, b > a), so the sequence's own thread writes the entry: no
+// search.  A sequence of up to CSR_THREAD_RUNS runs is mapped by its own thread; longer ones go on two lists and are mapped
+// by csr_listed_kernel: up to CSR_WARP_RUNS runs by one warp each, a chromosome among reads (163 k entries) by one CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t CSR_THREAD_RUNS = 512, CSR_WARP_RUNS = 65536;
+
+struct CsrMapParams {
+    const uint64_t* offsets;  // n_seq + 1, absolute
+    uint64_t n_seq;
+    uint64_t flat_base;       // offsets[0]: TileInfo::flat counts from here
+    uint64_t* run_prefix;
+    uint64_t* off_copy;
+    uint64_t arr_entries;     // entries of run_prefix / off_copy, pads included
+    TileInfo* tiles;
+    uint64_t n_tiles_cap;
+    uint32_t tile_shift;      // tile_runs = 1 << tile_shift (a multiple of 32)
+    uint32_t wq_stride;
+    uint32_t* warp_first;
+    uint32_t* mid_list;         // sequences of more than CSR_THREAD_RUNS runs
+    uint32_t* long_list;        // sequences of more than CSR_WARP_RUNS runs
+    unsigned int* list_counts;  // entries of the two lists; zeroed before the launch
+};
+
+// the entry of run g (a multiple of 32) of sequence r = runs [a, ...), first nucleotide at o0 past flat_base
+__device__ __forceinline__ void csr_map_entry(const CsrMapParams& p, uint64_t g, uint64_t a, uint64_t o0, uint32_t r) {
+    const uint64_t t = g >> p.tile_shift;
+    if (t >= p.n_tiles_cap) return;
+    const uint32_t j = (uint32_t)(g - (t << p.tile_shift)) >> 5;
+    p.warp_first[t * p.wq_stride + j] = r;
+    if (j == 0) {
+        TileInfo ti;
+        ti.flat = o0 + (g - a) * RUN_NT;
+        ti.first_seq = r;
+        ti.pad_ = 0;
+        p.tiles[t] = ti;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) csr_finish_kernel(const CsrMapParams p, const uint64_t* __restrict__ block_sums) {
+    __shared__ uint64_t warp_sums[32];
+    const uint64_t n = p.n_seq;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    const int lane = threadIdx.x & 31;
+    uint64_t o[SCAN_ITEMS + 1], v[SCAN_ITEMS], a[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k <= SCAN_ITEMS; k++) o[k] = base + k <= n ? p.offsets[base + k] : 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = base + k < n ? (o[k + 1] - o[k] + RUN_NT - 1) / RUN_NT : 0;
+        s += v[k];
+    }
+    uint64_t total;
+    uint64_t ex = block_exclusive_scan(s, &total, warp_sums) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        a[k] = ex;
+        ex += v[k];
+    }
+    if (base + SCAN_ITEMS <= n) {  // whole group: 128-bit stores (both arrays 16-byte aligned, base a multiple of 8)
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k += 2) {
+            *reinterpret_cast<ulonglong2*>(p.run_prefix + base + k) = make_ulonglong2(a[k], a[k + 1]);
+            *reinterpret_cast<ulonglong2*>(p.off_copy + base + k) = make_ulonglong2(o[k], o[k + 1]);
+        }
+        if (base + SCAN_ITEMS == n) {
+            p.run_prefix[n] = ex;
+            p.off_copy[n] = o[SCAN_ITEMS];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) {
+                p.run_prefix[base + k] = a[k];
+                p.off_copy[base + k] = o[k];
+                if (base + k + 1 == n) {
+                    p.run_prefix[n] = a[k] + v[k];
+                    p.off_copy[n] = o[k + 1];
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (uint64_t i = n + 1 + threadIdx.x; i < p.arr_entries; i += SCAN_THREADS) {
+            p.run_prefix[i] = ~0ull;
+            p.off_copy[i] = ~0ull;
+        }
+    }
+    // the maps
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t ak = a[k], vk = v[k], o0 = o[k] - p.flat_base;
+        const uint32_t r = (uint32_t)(base + k);
+        if (vk <= CSR_THREAD_RUNS) {
+            for (uint64_t g = (ak + 31) & ~(uint64_t)31; g < ak + vk; g += 32) csr_map_entry(p, g, ak, o0, r);
+        } else if (vk > CSR_WARP_RUNS) {
+            p.long_list[atomicAdd(p.list_counts + 1, 1u)] = r;
+        }
+        // the middle list can take most of a batch (long reads): one atomic per warp
+        const bool mid = vk > CSR_THREAD_RUNS && vk <= CSR_WARP_RUNS;
+        const uint32_t mm = __ballot_sync(0xffffffffu, mid);
+        if (mm) {
+            uint32_t at = 0;
+            if (lane == __ffs(mm) - 1) at = atomicAdd(p.list_counts, (unsigned int)__popc(mm));
+            at = __shfl_sync(0xffffffffu, at, __ffs(mm) - 1);
+            if (mid) p.mid_list[at + __popc(mm & ((1u << lane) - 1u))] = r;
         }
     }
 }
 
-// warp_first[q] = the sequence that holds run 32 q (largest r with run_prefix[r] <= 32 q), searched between the first
-// sequences of the enclosing tile and of the next one
-__global__ void __launch_bounds__(256) warp_map_kernel(const uint64_t* __restrict__ run_prefix, uint64_t n_seq, const TileInfo* __restrict__ tiles,
-                                                       uint64_t tile_runs, uint32_t wq_stride, uint32_t* __restrict__ warp_first) {
-    // slot t * wq_stride + j = the sequence holding run t * tile_runs + 32 j (tile_runs is a multiple of 32; wq_stride >=
-    // tile_runs / 32 is a multiple of 4 so that a tile's slice is a 16-byte aligned bulk-copy source)
-    const uint64_t total_runs = run_prefix[n_seq], wq = tile_runs / 32;
-    const uint64_t n_slots = ((total_runs + tile_runs - 1) / tile_runs) * wq;
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_slots; q += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t t = q / wq, j = q - t * wq, g = t * tile_runs + 32 * j;
-        if (g >= total_runs) continue;
-        uint64_t lo = tiles[t].first_seq, hi = ((t + 1) * tile_runs < total_runs) ? tiles[t + 1].first_seq : n_seq - 1;
-        while (lo < hi) {
-            const uint64_t mid = (lo + hi + 1) >> 1;
-            if (run_prefix[mid] <= g) lo = mid; else hi = mid - 1;
-        }
-        warp_first[t * wq_stride + j] = (uint32_t)lo;
+// the listed sequences: one warp each for the middle ones, one CTA each for the long ones
+__global__ void __launch_bounds__(256) csr_listed_kernel(const CsrMapParams p) {
+    const unsigned int n_mid = p.list_counts[0], n_long = p.list_counts[1];
+    const int lane = threadIdx.x & 31;
+    for (unsigned int i = blockIdx.x * 8u + (threadIdx.x >> 5); i < n_mid; i += gridDim.x * 8u) {
+        const uint32_t r = p.mid_list[i];
+        const uint64_t a = p.run_prefix[r], b = p.run_prefix[r + 1], o0 = p.off_copy[r] - p.flat_base;
+        for (uint64_t g = ((a + 31) & ~(uint64_t)31) + 32u * lane; g < b; g += 32u * 32u) csr_map_entry(p, g, a, o0, r);
+    }
+    for (unsigned int i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const uint32_t r = p.long_list[i];
+        const uint64_t a = p.run_prefix[r], b = p.run_prefix[r + 1], o0 = p.off_copy[r] - p.flat_base;
+        for (uint64_t g = ((a + 31) & ~(uint64_t)31) + 32u * threadIdx.x; g < b; g += 32u * 256u) csr_map_entry(p, g, a, o0, r);
     }
 }
 

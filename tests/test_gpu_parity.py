@@ -333,6 +333,25 @@ def test_batch_variable_lengths(B, tiles):
     _check_batch(B, [_rand(rng, n) for n in lens], 4, True, 6)
 
 
+def test_batch_long_sequences_among_reads(B, tiles):
+    """The 32-run map of a variable-length batch is written per sequence: by its thread (up to 512 runs of 48 nt), by a warp
+    (up to 65536 runs) or by a CTA (longer: a chromosome among reads) of a second kernel.  Lengths on every boundary."""
+    rng = np.random.default_rng(15)
+    lens = [5, 0, 48 * 65536 + 1, 17, 0, 120_000, 1000, 48 * 512 + 1, 48 * 512, 0, 48 * 65536, 3, 48 * 65536 + 4800, 64, 48 * 513, 999]
+    lens += [int(x) for x in rng.integers(20_000, 60_000, 70)]  # more than one warp's worth of list entries
+    reads = [_rand(rng, n) for n in lens]
+    for frames in (6, 1):
+        res = B.translate_frames_batch(reads, table=1, frames=frames)
+        for i, r in enumerate(reads):
+            want = (oracle.py_all_frames(1, r) if frames == 6 else [oracle.translate_bytes(1, r)]) if len(r) >= 3 else []
+            assert res.sequence_frames(i) == want, (i, len(r), frames)
+    bad = list(reads)
+    bad[12] = bad[12][:3_000_000] + b"!" + bad[12][3_000_001:]
+    with pytest.raises(ValueError) as ei:
+        B.translate_frames_batch(bad, table=1, frames=6)
+    assert (ei.value.seq_index, ei.value.pos) == (12, 3_000_000)
+
+
 def test_batch_many_tiny_reads(B, tiles):
     # more sequences starting inside one tile than the shared-memory search window holds
     rng = np.random.default_rng(6)
