@@ -506,8 +506,8 @@ def main():
         algo_v = int((lens[:keep] + 2 * ((lens[:keep]) // 3 + (lens[:keep] - 1) // 3 + (lens[:keep] - 2) // 3)).sum().item())
         launches_v0 = ctx.launch_count
         msv = timed(lambda: B.translate_frames_csr_dev(x[:tot_v], offs_d, out=out[: runs_v * 96], table=args.table, frames=6, ctx=ctx))
-        leg("all_frames_variable_length", f"translate_all_frames on {keep} reads of 500..1500 nt (CSR offsets; scan and tile-map kernels timed too)", msv, algo_v,
-            "translate_frames_kernel<6, 1024> + scan/tile-map", units={"nt": tot_v}, launches_per_call=(ctx.launch_count - launches_v0) // 7)
+        leg("all_frames_variable_length", f"translate_all_frames on {keep} reads of 500..1500 nt (CSR offsets; the scan and map kernels timed too)", msv, algo_v,
+            "translate_frames_kernel<6, 1024> + scan / csr_finish_kernel", units={"nt": tot_v}, launches_per_call=(ctx.launch_count - launches_v0) // 7)
         # IUPAC-ambiguous, mixed-case input (config 4): 5 % ambiguity codes, tables 1 / 11 / 22
         from quickdna_b200.synth import synth_iupac_np
 
