@@ -157,7 +157,8 @@ int qd_revcomp(qd_ctx *ctx, int enc, int strict, const uint8_t *dna, size_t n, u
  * (offsets[0] = 0): what a caller looping DnaSequence::translate* over a Vec of reads does,
  * in one call.  out: slot layout above, sequence i at out_offsets[i] = 16*frames*sum_{j<i}R_j;
  * out_offsets (n_seq+1 entries) is filled when non-NULL.  Capacity: qd_batch_out_bytes().
- * Work is pipelined in chunks of whole sequences (H2D, kernel, D2H overlap). */
+ * Work is pipelined in chunks of whole sequences (H2D, kernel, D2H overlap).
+ * Offsets that decrease: QD_ERR_INVALID_ARGUMENT, err->seq_index = the first such sequence, nothing is launched. */
 size_t qd_batch_out_bytes(const uint64_t *offsets, size_t n_seq, int frames);
 int qd_translate_frames_batch(qd_ctx *ctx, int table, int enc, int strict, int frames,
                               const uint8_t *dna, const uint64_t *offsets, size_t n_seq,
@@ -279,7 +280,10 @@ int qd_translate_frames_batch_uniform_dev(qd_ctx *ctx, int table, int enc, int s
                                           uint8_t *out_dev, void *stream);
 /* variable lengths: CSR offsets on the device, offsets_dev[0] == 0 (sequence i is dna_dev[offsets[i] .. offsets[i+1]));
  * the run prefix, the padded offsets copy and the tile maps the kernel needs are built on `stream` in context-owned
- * scratch. */
+ * scratch.  The host cannot look at device offsets, so the scan checks them: a sequence whose offsets decrease or point
+ * past total_nt is skipped (no byte outside dna_dev[0 .. total_nt) is read) and qd_dev_error_fetch returns
+ * QD_ERR_INVALID_ARGUMENT with err->seq_index = the first such sequence -- unless a bad nucleotide was found, which is
+ * reported first. */
 int qd_translate_frames_batch_dev(qd_ctx *ctx, int table, int enc, int strict, int frames,
                                   const uint8_t *dna_dev, const uint64_t *offsets_dev,
                                   size_t n_seq, size_t total_nt, uint8_t *out_dev, void *stream);

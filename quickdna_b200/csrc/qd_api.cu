@@ -509,6 +509,8 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     m.offsets = offsets_dev;
     m.n_seq = n_seq;
     m.flat_base = flat_base;
+    m.total_nt = total_nt;
+    m.err_key = c->d_err;
     m.run_prefix = rp_dev;
     m.off_copy = off_pad;
     m.arr_entries = arr_entries;
@@ -528,7 +530,7 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     QD_CUDA(c, cudaMemsetAsync(m.list_counts, 0, 2 * sizeof(unsigned int), s));
     const uint64_t n_blocks = std::max<uint64_t>(1, (n_seq + SCAN_BLOCK - 1) / SCAN_BLOCK);
     QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
-    scan_block_sums_kernel<0, 0><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(offsets_dev, n_seq, block_sums.as<uint64_t>(), nullptr, 0);
+    csr_block_sums_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(m, block_sums.as<uint64_t>());
     scan_spine_kernel<0><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, nullptr, 0);
     csr_finish_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(m, block_sums.as<uint64_t>());
     csr_listed_kernel<<<(unsigned)std::min<uint64_t>((mid_cap + 7) / 8 + long_cap, (uint64_t)c->sm_count * 4), 256, 0, s>>>(m);
@@ -864,6 +866,11 @@ extern "C" int qd_dev_error_fetch(qd_ctx* c, void* stream, int enc, int strict, 
     int rc = fetch_err_key(c, s, &key);
     if (rc) return rc;
     if (key == NO_ERROR_KEY) return QD_OK;
+    if (key & CSR_BAD_OFFSETS) {  // csr_finish_kernel: the offsets of this sequence decrease or leave the buffer
+        c->last_error = "offsets of sequence " + std::to_string(key & ~CSR_BAD_OFFSETS) + " decrease or point outside the buffer";
+        set_err(err, QD_ERR_INVALID_ARGUMENT, 0, 0, key & ~CSR_BAD_OFFSETS);
+        return QD_ERR_INVALID_ARGUMENT;
+    }
     uint8_t b = 0;
     QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, dna_dev + key, 1, cudaMemcpyDeviceToHost, s));
     QD_CUDA(c, cudaStreamSynchronize(s));
@@ -2098,6 +2105,18 @@ extern "C" int qd_revcomp(qd_ctx* c, int enc, int strict, const uint8_t* dna, si
     return QD_OK;
 }
 
+// CSR offsets of a host call must not decrease (the lengths are differences of unsigned values)
+static int check_host_offsets(qd_ctx* c, const uint64_t* offsets, size_t n_seq, qd_err* err) {
+    for (size_t i = 0; i < n_seq; i++) {
+        if (offsets[i + 1] < offsets[i]) {
+            if (c) c->last_error = "offsets of sequence " + std::to_string(i) + " decrease";
+            set_err(err, QD_ERR_INVALID_ARGUMENT, 0, 0, i);
+            return QD_ERR_INVALID_ARGUMENT;
+        }
+    }
+    return QD_OK;
+}
+
 // chunked H2D -> kernel -> D2H pipeline over whole sequences, N_PIPE streams deep
 static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna, const uint64_t* offsets,
                           size_t n_seq, size_t uniform_len, uint8_t* out, uint64_t* out_offsets, qd_err* err) {
@@ -2224,6 +2243,7 @@ extern "C" int qd_translate_frames_batch(qd_ctx* c, int table, int enc, int stri
     if (!c || !valid_frames(frames) || !offsets) return QD_ERR_INVALID_ARGUMENT;
     int slot;
     if (int rc = check_table(table, err, &slot)) return rc;
+    if (int rc = check_host_offsets(c, offsets, n_seq, err)) return rc;
     Guard g(c);
     if (!g.ok) return QD_ERR_CUDA;
     return batch_pipeline(c, slot, enc, strict, frames, dna, offsets, n_seq, 0, out, out_offsets, err);
@@ -2628,6 +2648,8 @@ extern "C" int qd_translate_frames_batch_multi(qd_ctx* const* ctxs, int n_ctx, i
         if (offsets && out_offsets) out_offsets[0] = 0;
         return QD_OK;
     }
+    if (offsets)
+        if (int rc = check_host_offsets(ctxs[0], offsets, n_seq, err)) return rc;
     const uint64_t stride = 16 * (uint64_t)frames;
     // cut points: sequence boundaries, balanced by BYTES
     std::vector<size_t> cut(n_ctx + 1, n_seq);

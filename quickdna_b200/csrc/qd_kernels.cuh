@@ -2652,10 +2652,38 @@ struct CsrMapParams {
     uint32_t tile_shift;      // tile_runs = 1 << tile_shift (a multiple of 32)
     uint32_t wq_stride;
     uint32_t* warp_first;
+    uint64_t total_nt;          // nucleotides in the buffer: every sequence must lie inside [flat_base, flat_base + total_nt]
+    unsigned long long* err_key;  // CSR_BAD_OFFSETS | sequence index for offsets that do not
     uint32_t* mid_list;         // sequences of more than CSR_THREAD_RUNS runs
     uint32_t* long_list;        // sequences of more than CSR_WARP_RUNS runs
     unsigned int* list_counts;  // entries of the two lists; zeroed before the launch
 };
+
+// Offsets come from the caller (device memory: the host cannot look at them): a sequence whose offsets decrease or leave the
+// buffer counts as empty -- the frame kernel never touches it -- and is reported through the error key, above every
+// nucleotide position (those keep precedence in the atomicMin) and below "no error".
+constexpr unsigned long long CSR_BAD_OFFSETS = 1ull << 63;
+__device__ __forceinline__ uint64_t csr_runs_checked(const CsrMapParams& p, uint64_t o0, uint64_t o1, bool& bad) {
+    bad = o1 < o0 || o0 - p.flat_base > p.total_nt || o1 - p.flat_base > p.total_nt;
+    return bad ? 0 : (o1 - o0 + RUN_NT - 1) / RUN_NT;
+}
+
+// first pass of the scan: runs per block of SCAN_BLOCK sequences
+__global__ void __launch_bounds__(SCAN_THREADS) csr_block_sums_kernel(const CsrMapParams p, uint64_t* __restrict__ block_sums) {
+    __shared__ uint64_t warp_sums[32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint64_t o[SCAN_ITEMS + 1], s = 0;
+#pragma unroll
+    for (int k = 0; k <= SCAN_ITEMS; k++) o[k] = base + k <= p.n_seq ? p.offsets[base + k] : 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        bool bad;
+        if (base + k < p.n_seq) s += csr_runs_checked(p, o[k], o[k + 1], bad);
+    }
+    uint64_t total;
+    block_exclusive_scan(s, &total, warp_sums);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
 
 // the entry of run g (a multiple of 32) of sequence r = runs [a, ...), first nucleotide at o0 past flat_base
 __device__ __forceinline__ void csr_map_entry(const CsrMapParams& p, uint64_t g, uint64_t a, uint64_t o0, uint32_t r) {
@@ -2682,7 +2710,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) csr_finish_kernel(const CsrMapPa
     for (int k = 0; k <= SCAN_ITEMS; k++) o[k] = base + k <= n ? p.offsets[base + k] : 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = base + k < n ? (o[k + 1] - o[k] + RUN_NT - 1) / RUN_NT : 0;
+        bool bad = false;
+        v[k] = base + k < n ? csr_runs_checked(p, o[k], o[k + 1], bad) : 0;
+        if (bad) atomicMin(p.err_key, CSR_BAD_OFFSETS | (base + k));
         s += v[k];
     }
     uint64_t total;

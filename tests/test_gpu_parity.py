@@ -352,6 +352,48 @@ def test_batch_long_sequences_among_reads(B, tiles):
     assert (ei.value.seq_index, ei.value.pos) == (12, 3_000_000)
 
 
+def test_batch_bad_offsets_are_refused(B, N):
+    """CSR offsets are caller data.  Host call: decreasing offsets -> invalid argument before anything runs.  Device call: the
+    scan skips sequences whose offsets decrease or leave the buffer (nothing outside it is read), the error fetch names the
+    first one; the context stays usable."""
+    import torch
+
+    ctx = N.default_context()
+    rng = np.random.default_rng(16)
+    reads = [_rand(rng, n) for n in (100, 200, 300, 400)]
+    flat = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    good = np.array([0, 100, 300, 600, 1000], dtype=np.uint64)
+    for bad, first in ((np.array([0, 100, 50, 600, 1000], dtype=np.uint64), 1),
+                       (np.array([0, 100, 300, 600, 2**40], dtype=np.uint64), 3),
+                       (np.array([0, 100, 300, 2**63 + 5, 1000], dtype=np.uint64), 2)):
+        d_flat, d_offs = torch.from_numpy(flat.copy()).cuda(), torch.from_numpy(bad.view(np.int64).copy()).cuda()
+        out = torch.zeros(int(N.lib().qd_batch_out_bytes(good.ctypes.data_as(C.POINTER(C.c_uint64)), 4, 6)) + 4096, dtype=torch.uint8, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        L = N.lib()
+        assert L.qd_dev_error_reset(ctx.handle, s) == 0
+        rc = L.qd_translate_frames_batch_dev(ctx.handle, 1, N.ENC_ASCII, 0, 6, d_flat.data_ptr(), d_offs.data_ptr(), 4, flat.size, out.data_ptr(), s)
+        assert rc == 0
+        err = N.QdErr()
+        rc = L.qd_dev_error_fetch(ctx.handle, s, N.ENC_ASCII, 0, d_flat.data_ptr(), d_offs.data_ptr(), 4, 0, C.byref(err))
+        assert rc == N.QD_ERR_INVALID_ARGUMENT and err.seq_index == first, (rc, err.seq_index, first)
+    # decreasing offsets on the host path
+    with pytest.raises(ValueError):
+        B.translate_frames_batch((flat, np.array([0, 100, 50, 600, 1000], dtype=np.uint64)), table=1, frames=6)
+    # a nucleotide error takes precedence over bad offsets; then a clean call works
+    dirty = flat.copy()
+    dirty[42] = ord("!")
+    d_flat, d_offs = torch.from_numpy(dirty).cuda(), torch.from_numpy(np.array([0, 100, 300, 200, 1000], dtype=np.int64)).cuda()
+    out = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    L = N.lib()
+    assert L.qd_dev_error_reset(ctx.handle, s) == 0
+    assert L.qd_translate_frames_batch_dev(ctx.handle, 1, N.ENC_ASCII, 0, 6, d_flat.data_ptr(), d_offs.data_ptr(), 4, dirty.size, out.data_ptr(), s) == 0
+    err = N.QdErr()
+    rc = L.qd_dev_error_fetch(ctx.handle, s, N.ENC_ASCII, 0, d_flat.data_ptr(), d_offs.data_ptr(), 4, 0, C.byref(err))
+    assert rc == N.QD_ERR_BAD_NUCLEOTIDE and (err.seq_index, err.pos) == (0, 42)
+    _check_batch(B, reads, 1, False, 6)
+
+
 def test_batch_many_tiny_reads(B, tiles):
     # more sequences starting inside one tile than the shared-memory search window holds
     rng = np.random.default_rng(6)
