@@ -522,7 +522,7 @@ def parse_dev(ascii_seq, out=None, strict: bool = False, ctx: Optional[N.Context
     n = ascii_seq.numel()
     if out is None:
         out = torch.empty(n + 16, dtype=torch.uint8, device=ascii_seq.device)
-    count = torch.zeros(1, dtype=torch.int64, device=ascii_seq.device)
+    count = torch.empty(1, dtype=torch.int64, device=ascii_seq.device)  # always written by the call (no fill kernel needed)
     rc = N.lib().qd_parse_dev(ctx.handle, int(strict), C.c_void_p(ascii_seq.data_ptr()), n, C.c_void_p(out.data_ptr()),
                               C.c_void_p(count.data_ptr()), _stream_ptr(torch))
     ctx.check(rc)

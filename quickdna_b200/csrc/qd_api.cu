@@ -206,6 +206,7 @@ struct qd_ctx {
     cudaStream_t dev_stream = nullptr;
     bool dev_pending = false;
     std::map<uint64_t, int> occ_cache;  // (kernel id, smem bytes) -> resident CTAs per SM, attribute already set
+    bool pdl = true;  // QD_PDL=0: plain launches for the short dependent kernels (A/B measurements)
     bool aligned_tiles = true;  // QD_ALIGNED_TILES=0 turns the whole-sequence tiles of the frame kernels off (A/B measurements)
     uint32_t ctile_wpt[2] = {960, 448};  // canonical tile kernel: windows per warp-tile for keys / rows (QD_CTILE_WPT_* read once)
 };
@@ -377,8 +378,25 @@ void set_encoding(const qd_ctx* c, FramesParams& p, int enc, int strict) {
 // Which CTA size a launch of `total_runs` runs uses: the 1024-thread tile once every SM gets at least two of them.
 bool use_big_tiles(const qd_ctx* c, uint64_t total_runs) { return total_runs >= c->big_tile_min_runs; }
 
+// launch with programmatic stream serialization: the kernel may become resident before its predecessor in the stream has
+// finished and calls pdl_wait() before it reads what the predecessor wrote (qd_kernels.cuh)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int FRAMES, int THREADS>
-int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_slot) {
+int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_slot, bool dependent) {
     constexpr bool DIRECT = FRAMES == 1;  // the one-frame kernel looks codons up straight from the letters
     auto kern = translate_frames_kernel<FRAMES, THREADS, DIRECT>;
     using Smem = FramesSmem<THREADS, frames_stages(FRAMES)>;
@@ -392,7 +410,8 @@ int launch_frames_t(qd_ctx* c, const FramesParams& p, cudaStream_t s, int occ_sl
     }
     if (p.n_tiles == 0) return QD_OK;
     const unsigned grid = (unsigned)std::min<uint64_t>(p.n_tiles, (uint64_t)c->sm_count * c->occ_frames[occ_slot]);
-    kern<<<grid, THREADS, smem, s>>>(p);
+    if (dependent && c->pdl) QD_CUDA(c, launch_pdl(kern, grid, THREADS, smem, s, p));
+    else kern<<<grid, THREADS, smem, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
@@ -403,18 +422,19 @@ static uint64_t tile_runs_of(int /*frames*/, bool big) { return big ? TileGeom<B
 
 // p.n_tiles must match the tile size (tile_runs_of)
 // (two 512-thread CTAs per SM were measured for variable-length batches too: no better than one 1024-thread CTA)
-int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s, bool big) {
+// dependent: launched behind kernels that trigger early (programmatic dependent launch, see launch_pdl)
+int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s, bool big, bool dependent = false) {
     if (big) {
         switch (frames) {
-            case QD_FRAMES_ONE: return launch_frames_t<1, BIG_THREADS>(c, p, s, 3);
-            case QD_FRAMES_SELF: return launch_frames_t<3, BIG_THREADS>(c, p, s, 4);
-            default: return launch_frames_t<6, BIG_THREADS>(c, p, s, 5);
+            case QD_FRAMES_ONE: return launch_frames_t<1, BIG_THREADS>(c, p, s, 3, dependent);
+            case QD_FRAMES_SELF: return launch_frames_t<3, BIG_THREADS>(c, p, s, 4, dependent);
+            default: return launch_frames_t<6, BIG_THREADS>(c, p, s, 5, dependent);
         }
     }
     switch (frames) {
-        case QD_FRAMES_ONE: return launch_frames_t<1, SMALL_THREADS>(c, p, s, 0);
-        case QD_FRAMES_SELF: return launch_frames_t<3, SMALL_THREADS>(c, p, s, 1);
-        default: return launch_frames_t<6, SMALL_THREADS>(c, p, s, 2);
+        case QD_FRAMES_ONE: return launch_frames_t<1, SMALL_THREADS>(c, p, s, 0, dependent);
+        case QD_FRAMES_SELF: return launch_frames_t<3, SMALL_THREADS>(c, p, s, 1, dependent);
+        default: return launch_frames_t<6, SMALL_THREADS>(c, p, s, 2, dependent);
     }
 }
 
@@ -466,8 +486,14 @@ int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* 
     const uint64_t n_blocks = std::max<uint64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
     QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
     scan_block_sums_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), gate, gate_gen);
-    scan_spine_kernel<OP><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, gate, gate_gen);
-    scan_finish_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst, gate, gate_gen);
+    if (c->pdl) {
+        QD_CUDA(c, launch_pdl(scan_spine_kernel<OP>, 1, SCAN_THREADS, 0, s, block_sums.as<uint64_t>(), n_blocks, gate, gate_gen));
+        QD_CUDA(c, launch_pdl(scan_finish_kernel<MODE, OP>, (unsigned)n_blocks, SCAN_THREADS, 0, s, src, n, (const uint64_t*)block_sums.as<uint64_t>(), dst, gate,
+                              gate_gen));
+    } else {
+        scan_spine_kernel<OP><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, gate, gate_gen);
+        scan_finish_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst, gate, gate_gen);
+    }
     c->launches += 3;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
@@ -531,9 +557,16 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     const uint64_t n_blocks = std::max<uint64_t>(1, (n_seq + SCAN_BLOCK - 1) / SCAN_BLOCK);
     QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
     csr_block_sums_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(m, block_sums.as<uint64_t>());
-    scan_spine_kernel<0><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, nullptr, 0);
-    csr_finish_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(m, block_sums.as<uint64_t>());
-    csr_listed_kernel<<<(unsigned)std::min<uint64_t>((mid_cap + 7) / 8 + long_cap, (uint64_t)c->sm_count * 4), 256, 0, s>>>(m);
+    const unsigned g_listed = (unsigned)std::min<uint64_t>((mid_cap + 7) / 8 + long_cap, (uint64_t)c->sm_count * 4);
+    if (c->pdl) {  // each kernel of the chain takes its place while the one before drains, and waits for it before it reads
+        QD_CUDA(c, launch_pdl(scan_spine_kernel<0>, 1, SCAN_THREADS, 0, s, block_sums.as<uint64_t>(), n_blocks, nullptr, 0ull));
+        QD_CUDA(c, launch_pdl(csr_finish_kernel, (unsigned)n_blocks, SCAN_THREADS, 0, s, m, block_sums.as<uint64_t>()));
+        QD_CUDA(c, launch_pdl(csr_listed_kernel, g_listed, 256, 0, s, m));
+    } else {
+        scan_spine_kernel<0><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, nullptr, 0);
+        csr_finish_kernel<<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(m, block_sums.as<uint64_t>());
+        csr_listed_kernel<<<g_listed, 256, 0, s>>>(m);
+    }
     c->launches += 4;
     QD_CUDA(c, cudaGetLastError());
     FramesParams p{};
@@ -553,7 +586,7 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     p.err_key = c->d_err;
     p.flat_base = flat_base;
     p.key_base = key_base;
-    return launch_frames(c, frames, p, s, big);
+    return launch_frames(c, frames, p, s, big, /*dependent=*/true);
 }
 
 template <int THREADS>
@@ -648,6 +681,7 @@ extern "C" int qd_ctx_create(qd_ctx** out, int device) {
     c->big_tile_min_runs = (uint64_t)2 * BIG_THREADS * (uint64_t)c->sm_count;  // every SM gets two big tiles
     // tuning knobs of the canonical tile kernel, read once per context (not on the launch path)
     if (const char* e = getenv("QD_ALIGNED_TILES")) c->aligned_tiles = atoi(e) != 0;
+    if (const char* e = getenv("QD_PDL")) c->pdl = atoi(e) != 0;
     if (const char* e = getenv("QD_CTILE_WPT_KEYS")) c->ctile_wpt[0] = (uint32_t)std::max(64, atoi(e) & ~63);
     if (const char* e = getenv("QD_CTILE_WPT_ROWS")) c->ctile_wpt[1] = (uint32_t)std::max(64, atoi(e) & ~63);
     const HostTables& T = host_tables();
@@ -1252,9 +1286,14 @@ static int parse_dev(qd_ctx* c, int strict, const uint8_t* ascii_dev, size_t n, 
     const unsigned g1 = (unsigned)std::min<uint64_t>((n_gran + step - 1) / step, (uint64_t)c->sm_count * 8);
     if (same_phase) parse_pass1_kernel<true><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
     else parse_pass1_kernel<false><<<g1, PARSE_THREADS, 0, s>>>(p, n_gran, n_masks_dev);
-    parse_scan_kernel<<<1, PARSE_SCAN_THREADS, 0, s>>>(p, n_blocks);
     const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)c->sm_count * 8);
-    parse_write_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks, n_masks_dev);
+    if (c->pdl) {
+        QD_CUDA(c, launch_pdl(parse_scan_kernel, 1, PARSE_SCAN_THREADS, 0, s, p, n_blocks));
+        QD_CUDA(c, launch_pdl(parse_write_kernel, grid, PARSE_THREADS, 0, s, p, n_blocks, n_masks_dev));
+    } else {
+        parse_scan_kernel<<<1, PARSE_SCAN_THREADS, 0, s>>>(p, n_blocks);
+        parse_write_kernel<<<grid, PARSE_THREADS, 0, s>>>(p, n_blocks, n_masks_dev);
+    }
     c->launches += 3;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;

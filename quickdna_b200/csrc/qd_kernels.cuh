@@ -253,6 +253,13 @@ constexpr unsigned long long NO_ERROR_KEY = ~0ull;
 // Frame translation (1, 3 or 6 frames from ONE read of the input)
 // ------------------------------------------------------------------------------------------------
 // Where a tile starts: flat offset of its first run, and the sequence that run belongs to.
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute (launch_pdl in
+// qd_api.cu) may become resident while its predecessor in the stream is still running -- after every CTA of the predecessor
+// has called pdl_trigger() or exited -- and must call pdl_wait() before it touches anything the predecessor wrote (the wait
+// returns once the predecessor has completed and its writes are visible).  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct TileInfo {
     uint64_t flat;
     uint32_t first_seq;
@@ -458,6 +465,7 @@ __global__ void __launch_bounds__(THREADS, TileGeom<THREADS>::CTAS_PER_SM) trans
     uint8_t* const direct_s = frames_smem_raw + ((sizeof(Smem) + 127) & ~(size_t)127);  // DIRECT only
     const int tid = threadIdx.x;
     const bool uniform = (p.offsets == nullptr);
+    pdl_wait();  // variable-length batches launch this kernel behind the map kernels as a dependent (no-op otherwise)
     if (p.trace && tid == 0) {
         unsigned long long t0;
         uint32_t smid;
@@ -2544,6 +2552,7 @@ template <int MODE, int OP = 0>
 // gate / gate_gen: the kernel returns at once unless *gate == gate_gen (nullptr: always runs); see ParseParams
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint64_t* src, uint64_t n, uint64_t* block_sums,
                                                                        const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0) {
+    pdl_trigger();
     if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
@@ -2561,6 +2570,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uin
 template <int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* block_sums, uint64_t n_blocks, const unsigned long long* gate = nullptr,
                                                                   unsigned long long gate_gen = 0) {
+    pdl_trigger();
+    pdl_wait();  // (a dependent launch: the block sums come from the kernel before)
     if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
@@ -2594,6 +2605,8 @@ template <int MODE, int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_t* src, uint64_t n, const uint64_t* block_sums,
                                                                    uint64_t* dst, const unsigned long long* gate = nullptr,
                                                                    unsigned long long gate_gen = 0) {
+    pdl_trigger();
+    pdl_wait();
     if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
@@ -2670,6 +2683,7 @@ __device__ __forceinline__ uint64_t csr_runs_checked(const CsrMapParams& p, uint
 
 // first pass of the scan: runs per block of SCAN_BLOCK sequences
 __global__ void __launch_bounds__(SCAN_THREADS) csr_block_sums_kernel(const CsrMapParams p, uint64_t* __restrict__ block_sums) {
+    pdl_trigger();
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t o[SCAN_ITEMS + 1], s = 0;
@@ -2701,6 +2715,8 @@ __device__ __forceinline__ void csr_map_entry(const CsrMapParams& p, uint64_t g,
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) csr_finish_kernel(const CsrMapParams p, const uint64_t* __restrict__ block_sums) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ uint64_t warp_sums[32];
     const uint64_t n = p.n_seq;
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
@@ -2775,6 +2791,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) csr_finish_kernel(const CsrMapPa
 
 // the listed sequences: one warp each for the middle ones, one CTA each for the long ones
 __global__ void __launch_bounds__(256) csr_listed_kernel(const CsrMapParams p) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned int n_mid = p.list_counts[0], n_long = p.list_counts[1];
     const int lane = threadIdx.x & 31;
     for (unsigned int i = blockIdx.x * 8u + (threadIdx.x >> 5); i < n_mid; i += gridDim.x * 8u) {
@@ -2886,6 +2904,7 @@ template <bool STORE>
 __global__ void __launch_bounds__(PARSE_THREADS) parse_pass1_kernel(const ParseParams p, uint64_t n_gran, uint64_t* n_masks) {
     __shared__ uint8_t tab_s[256];
     __shared__ __align__(16) uint16_t pair_s[PAIR_ENTRIES];
+    pdl_trigger();  // the gated passes behind this one may take their places early (they wait for this grid before they look at the gate)
     tab_s[threadIdx.x] = __ldg(p.table + threadIdx.x);
     for (int i = threadIdx.x; i < (int)PAIR_ENTRIES; i += PARSE_THREADS) pair_s[i] = __ldg(p.pair + i);
     __syncthreads();
@@ -2956,6 +2975,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_pass1_kernel(const ParseP
 // dropped bytes): one CTA, 8192 blocks per round -- only input with whitespace comes here
 constexpr int PARSE_SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(PARSE_SCAN_THREADS) parse_scan_kernel(const ParseParams p, uint64_t n_blocks) {
+    pdl_trigger();
+    pdl_wait();
     if (parse_gate_closed(p.gate, p.gate_gen)) return;
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
@@ -2994,6 +3015,7 @@ __global__ void __launch_bounds__(PARSE_SCAN_THREADS) parse_scan_kernel(const Pa
 }
 
 __global__ void __launch_bounds__(PARSE_THREADS) parse_write_kernel(const ParseParams p, uint64_t n_blocks, uint64_t* n_masks) {
+    pdl_wait();
     if (parse_gate_closed(p.gate, p.gate_gen)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_masks) *n_masks = p.offsets[n_blocks];
     __shared__ uint8_t tab_s[256];
