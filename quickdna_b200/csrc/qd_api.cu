@@ -440,7 +440,8 @@ int launch_frames(qd_ctx* c, int frames, const FramesParams& p, cudaStream_t s, 
 
 // uniform batch (also the single-sequence case n_seq = 1) on device buffers
 int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna_dev, size_t n_seq,
-                       size_t seq_len, uint8_t* out_dev, cudaStream_t s, uint64_t key_base = 0, unsigned long long* err_key = nullptr) {
+                       size_t seq_len, uint8_t* out_dev, cudaStream_t s, uint64_t key_base = 0, unsigned long long* err_key = nullptr,
+                       bool dependent = false) {
     if (n_seq == 0 || seq_len == 0) return QD_OK;
     const uint64_t runs = (seq_len + RUN_NT - 1) / RUN_NT;
     const uint64_t total_runs = runs * n_seq;
@@ -477,7 +478,7 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
         if (int rc = direct_table(c, slot, enc, strict, s, &p.direct)) return rc;
     p.err_key = err_key ? err_key : c->d_err;
     p.key_base = key_base;
-    return launch_frames(c, frames, p, s, big);
+    return launch_frames(c, frames, p, s, big, dependent);
 }
 
 template <int MODE, int OP = 0>
@@ -1640,7 +1641,7 @@ extern "C" int qd_fasta_translate_frames(qd_ctx* c, int table, int strict, int f
 }
 
 static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride, size_t n_seq, size_t len, size_t w, int mode,
-                             uint8_t* out_dev, uint64_t key_stride, cudaStream_t s);
+                             uint8_t* out_dev, uint64_t key_stride, cudaStream_t s, int dep = 0);
 static int windows_all_batch_dev(qd_ctx* c, int enc, const uint8_t* dna_dev, size_t n_seq, size_t seq_len, size_t w_dna, size_t w_aa,
                                  uint8_t* dna_out_dev, uint8_t* aa_out_dev, cudaStream_t s);
 
@@ -1659,8 +1660,18 @@ static int windows_dev(qd_ctx* c, const uint8_t* seq_dev, size_t n, size_t w, ui
 }
 
 // windows of n_seq sequences (sequence s at src + s * stride, `len` bytes each), see windows_batch_kernel
+// dep: DEP_NONE = a plain launch; DEP_FREE / DEP_WAIT = a programmatic dependent of the kernel before it in the stream that
+// may start while that kernel drains -- DEP_WAIT when it reads what that kernel wrote, DEP_FREE when everything it reads was
+// complete before the first kernel of the chain started (WindowsBatchParams::dep_wait)
+enum { DEP_NONE = 0, DEP_FREE = 1, DEP_WAIT = 2 };
+template <typename K>
+static cudaError_t launch_windows(qd_ctx* c, K kern, unsigned grid, cudaStream_t s, int dep, const WindowsBatchParams& p) {
+    if (dep != DEP_NONE && c->pdl) return launch_pdl(kern, grid, 32 * WIN_WARPS, 0, s, p);
+    kern<<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+    return cudaSuccess;
+}
 static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride, size_t n_seq, size_t len, size_t w, int mode,
-                             uint8_t* out_dev, uint64_t key_stride, cudaStream_t s) {
+                             uint8_t* out_dev, uint64_t key_stride, cudaStream_t s, int dep) {
     if (w < 1 || w > 64 || len > 0xffffffffull || n_seq >= 0xffffffffull || mode < QD_WIN_COPY || mode > QD_WIN_MASK_ASCII_RC) return QD_ERR_INVALID_ARGUMENT;
     if (len < w || n_seq == 0) return QD_OK;
     static const int map_tab[5] = {-1, TAB_UPPER_ASCII_STRICT, TAB_RC_ASCII_STRICT, TAB_MASK_TO_ASCII_STRICT, TAB_RC_MASK_TO_ASCII_STRICT};
@@ -1675,18 +1686,19 @@ static int windows_batch_dev(qd_ctx* c, const uint8_t* src_dev, uint64_t stride,
     p.out = out_dev;
     p.key_stride = key_stride;
     p.err_key = c->d_err;
+    p.dep_wait = (dep == DEP_WAIT && c->pdl) ? 1u : 0u;
     const uint64_t wpt = w == 42 ? WinTile<42>::WPT : (w == 20 ? WinTile<20>::WPT : WinTile<0>::WPT);
     const uint64_t tiles = (uint64_t)n_seq * (1 + (len - w + 1 + wpt - 1) / wpt);  // + the short first tile of every sequence
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((tiles + WIN_WARPS - 1) / WIN_WARPS, (uint64_t)c->sm_count * 6));
     // the two window lengths of benches/all_windows.rs get fully unrolled instantiations
     if (p.map) {
-        if (w == 42) windows_batch_kernel<42, true><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
-        else if (w == 20) windows_batch_kernel<20, true><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
-        else windows_batch_kernel<0, true><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+        if (w == 42) QD_CUDA(c, launch_windows(c, windows_batch_kernel<42, true>, grid, s, dep, p));
+        else if (w == 20) QD_CUDA(c, launch_windows(c, windows_batch_kernel<20, true>, grid, s, dep, p));
+        else QD_CUDA(c, launch_windows(c, windows_batch_kernel<0, true>, grid, s, dep, p));
     } else {  // plain copies: no table lookup per byte
-        if (w == 42) windows_batch_kernel<42, false><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
-        else if (w == 20) windows_batch_kernel<20, false><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
-        else windows_batch_kernel<0, false><<<grid, 32 * WIN_WARPS, 0, s>>>(p);
+        if (w == 42) QD_CUDA(c, launch_windows(c, windows_batch_kernel<42, false>, grid, s, dep, p));
+        else if (w == 20) QD_CUDA(c, launch_windows(c, windows_batch_kernel<20, false>, grid, s, dep, p));
+        else QD_CUDA(c, launch_windows(c, windows_batch_kernel<0, false>, grid, s, dep, p));
     }
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
@@ -1729,19 +1741,26 @@ static int windows_all_batch_dev(qd_ctx* c, int enc, const uint8_t* dna_dev, siz
     // forward and reverse-complement DNA windows straight from the input (strict alphabet: anything else is an error)
     const int fwd_mode = enc == QD_ENC_ASCII ? QD_WIN_DNA_ASCII : QD_WIN_MASK_ASCII;
     if (dna_out_dev && counts[0]) {
-        if (int rc = windows_batch_dev(c, dna_dev, seq_len, n_seq, seq_len, w_dna, fwd_mode, dna_out_dev, seq_len, s)) return rc;
-        if (int rc = windows_batch_dev(c, dna_dev, seq_len, n_seq, seq_len, w_dna, fwd_mode + 1, dna_out_dev + n_seq * counts[0] * w_dna, seq_len, s)) return rc;
+        // The eight window kernels and the frame kernel between them are one chain of programmatic dependents: each may
+        // take its place on the SMs while the one before drains.  The first launch is a plain one, so everything the chain
+        // reads from outside (the input; the scratch of the frames: no reader of an earlier call is left) is settled
+        // before it starts; only the first window kernel over the frames has to wait for the kernel before it.
+        if (int rc = windows_batch_dev(c, dna_dev, seq_len, n_seq, seq_len, w_dna, fwd_mode, dna_out_dev, seq_len, s, DEP_NONE)) return rc;
+        if (int rc = windows_batch_dev(c, dna_dev, seq_len, n_seq, seq_len, w_dna, fwd_mode + 1, dna_out_dev + n_seq * counts[0] * w_dna, seq_len, s, DEP_FREE)) return rc;
     }
     if (aa_out_dev) {
         // six frames (table Ncbi1, as SequenceWindows::from_dna does) into context scratch, then their windows
         const size_t slots = qd_slots_bytes(seq_len, 6);
         QD_CUDA(c, c->aux2.reserve(n_seq * slots + 16));
-        if (int rc = frames_uniform_dev(c, 0, enc, 1, QD_FRAMES_ALL, dna_dev, n_seq, seq_len, c->aux2.as<uint8_t>(), s)) return rc;
+        const bool chained = dna_out_dev && counts[0];  // (else the frame kernel is the plain first launch of the chain)
+        if (int rc = frames_uniform_dev(c, 0, enc, 1, QD_FRAMES_ALL, dna_dev, n_seq, seq_len, c->aux2.as<uint8_t>(), s, 0, nullptr, chained)) return rc;
         size_t at = 0;
+        int dep = DEP_WAIT;  // the first kernel over the frames waits for them; the others start behind it
         for (int f = 0; f < 6; f++) {
             if (!counts[2 + f]) continue;
             const uint8_t* frame0 = c->aux2.as<uint8_t>() + qd_slot_frame_offset(seq_len, 6, f);
-            if (int rc = windows_batch_dev(c, frame0, slots, n_seq, qd_frame_len(seq_len, f % 3), w_aa, QD_WIN_COPY, aa_out_dev + at, seq_len, s)) return rc;
+            if (int rc = windows_batch_dev(c, frame0, slots, n_seq, qd_frame_len(seq_len, f % 3), w_aa, QD_WIN_COPY, aa_out_dev + at, seq_len, s, dep)) return rc;
+            dep = DEP_FREE;
             at += n_seq * counts[2 + f] * w_aa;
         }
     }

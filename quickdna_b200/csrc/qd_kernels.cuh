@@ -1077,6 +1077,10 @@ struct WindowsBatchParams {
     uint8_t* out;        // n_seq * (len - w + 1) * w bytes
     uint64_t key_stride;  // error key of byte i of sequence s = s * key_stride + i
     unsigned long long* err_key;
+    // Launched as a programmatic dependent (launch_pdl): 1 = src was written by the kernel before, wait for it.  A launch
+    // with 0 here starts reading at once -- legal only when everything it reads was complete before the FIRST kernel of the
+    // chain of dependents started.  Dependents behind this kernel are released after that wait, never before it.
+    uint32_t dep_wait;
 };
 #ifndef QD_WIN_TMA_STORE
 #define QD_WIN_TMA_STORE 1
@@ -1168,6 +1172,8 @@ __global__ void __launch_bounds__(32 * WIN_WARPS, W ? 6 : 4) windows_batch_kerne
     __shared__ WinWarpSmem SM[WIN_WARPS];
     __shared__ uint8_t map_s[256];
     for (int i = threadIdx.x; i < 256; i += 32 * WIN_WARPS) map_s[i] = MAP ? __ldg(p.map + i) : (uint8_t)i;
+    if (p.dep_wait) pdl_wait();
+    pdl_trigger();
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WinWarpSmem& S = SM[threadIdx.x >> 5];
