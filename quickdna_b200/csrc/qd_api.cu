@@ -483,10 +483,12 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
 
 template <int MODE, int OP = 0>
 int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* dst, DevBuf& block_sums, cudaStream_t s,
-                          const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0) {
+                          const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0, bool dependent = false) {
     const uint64_t n_blocks = std::max<uint64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
     QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
-    scan_block_sums_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), gate, gate_gen);
+    // dependent: the kernel before this scan in the stream triggers early (every kernel of the scan waits for its predecessor)
+    if (dependent && c->pdl) QD_CUDA(c, launch_pdl(scan_block_sums_kernel<MODE, OP>, (unsigned)n_blocks, SCAN_THREADS, 0, s, src, n, block_sums.as<uint64_t>(), gate, gate_gen));
+    else scan_block_sums_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), gate, gate_gen);
     if (c->pdl) {
         QD_CUDA(c, launch_pdl(scan_spine_kernel<OP>, 1, SCAN_THREADS, 0, s, block_sums.as<uint64_t>(), n_blocks, gate, gate_gen));
         QD_CUDA(c, launch_pdl(scan_finish_kernel<MODE, OP>, (unsigned)n_blocks, SCAN_THREADS, 0, s, src, n, (const uint64_t*)block_sums.as<uint64_t>(), dst, gate,
@@ -1367,8 +1369,13 @@ static int canonical_seq_dev(qd_ctx* c, int enc, int forward_only, const uint8_t
     p.err_key = c->d_err;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8));
     canon_seq_scan_kernel<<<grid, 256, 0, s>>>(p);
-    if (!forward_only) canon_seq_diff_kernel<<<grid, 256, 0, s>>>(p);
-    canon_seq_write_kernel<<<grid, 256, 0, s>>>(p);
+    if (c->pdl) {  // the second and third pass take their places while the pass before drains, and wait for it
+        if (!forward_only) QD_CUDA(c, launch_pdl(canon_seq_diff_kernel, grid, 256, 0, s, p));
+        QD_CUDA(c, launch_pdl(canon_seq_write_kernel, grid, 256, 0, s, p));
+    } else {
+        if (!forward_only) canon_seq_diff_kernel<<<grid, 256, 0, s>>>(p);
+        canon_seq_write_kernel<<<grid, 256, 0, s>>>(p);
+    }
     c->launches += forward_only ? 2 : 3;
     QD_CUDA(c, cudaGetLastError());
     return QD_OK;
@@ -1443,13 +1450,15 @@ static int fasta_count_dev(qd_ctx* c, int strict, int concat, int allow, const u
     fasta_lines_kernel<<<grid, FA_THREADS, 0, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
-    if (int rc = device_exclusive_scan<1, 1>(c, p.blk_last, p.n_blocks, blk_state, c->block_sums, s)) return rc;
-    fasta_pass_kernel<false><<<grid, FA_THREADS, 0, s>>>(p);
+    // every kernel from here on is a programmatic dependent of the one before: it takes its place early and waits
+    if (int rc = device_exclusive_scan<1, 1>(c, p.blk_last, p.n_blocks, blk_state, c->block_sums, s, nullptr, 0, true)) return rc;
+    if (c->pdl) QD_CUDA(c, launch_pdl(fasta_pass_kernel<false>, grid, FA_THREADS, 0, s, p));
+    else fasta_pass_kernel<false><<<grid, FA_THREADS, 0, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
-    if (int rc = device_exclusive_scan<1>(c, p.cnt_kept, p.n_blocks, pre_kept, c->block_sums, s)) return rc;
-    if (int rc = device_exclusive_scan<1>(c, p.cnt_recs, p.n_blocks, pre_recs, c->block_sums, s)) return rc;
-    if (int rc = device_exclusive_scan<1>(c, p.cnt_nl, p.n_blocks, pre_nl, c->block_sums, s)) return rc;
+    if (int rc = device_exclusive_scan<1>(c, p.cnt_kept, p.n_blocks, pre_kept, c->block_sums, s, nullptr, 0, true)) return rc;
+    if (int rc = device_exclusive_scan<1>(c, p.cnt_recs, p.n_blocks, pre_recs, c->block_sums, s, nullptr, 0, true)) return rc;
+    if (int rc = device_exclusive_scan<1>(c, p.cnt_nl, p.n_blocks, pre_nl, c->block_sums, s, nullptr, 0, true)) return rc;
     return QD_OK;
 }
 
@@ -1460,11 +1469,12 @@ static int fasta_write_dev(qd_ctx* c, FastaRun& R, uint8_t* masks_dev, FastaReco
     p.records = records_dev;
     p.max_records = max_records;
     const unsigned grid = (unsigned)std::min<uint64_t>(p.n_blocks, (uint64_t)c->sm_count * 8);
-    fasta_pass_kernel<true><<<grid, FA_THREADS, 0, s>>>(p);
+    fasta_pass_kernel<true><<<grid, FA_THREADS, 0, s>>>(p);  // (behind a synchronisation: a plain launch)
     c->launches++;
     if (n_records) {
         const unsigned g4 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_records + 255) / 256, (uint64_t)c->sm_count * 8));
-        fasta_finish_kernel<<<g4, 256, 0, s>>>(p, n_records, shift);
+        if (c->pdl) QD_CUDA(c, launch_pdl(fasta_finish_kernel, g4, 256, 0, s, p, n_records, shift));
+        else fasta_finish_kernel<<<g4, 256, 0, s>>>(p, n_records, shift);
         c->launches++;
     }
     QD_CUDA(c, cudaGetLastError());
@@ -1575,7 +1585,8 @@ extern "C" int qd_fasta_scan_dev(qd_ctx* c, int strict, int concatenate_headers,
     if (int rc = fasta_write_dev(c, R, masks_dev, reinterpret_cast<FastaRecord*>(records_dev), total_records, total_records, shift, s)) return rc;
     if (offsets_dev) {
         const unsigned g1 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total_records + 256) / 256, (uint64_t)c->sm_count * 8));
-        fasta_offsets_kernel<<<g1, 256, 0, s>>>(reinterpret_cast<const FastaRecord*>(records_dev), total_records, total_kept, offsets_dev);
+        if (c->pdl) QD_CUDA(c, launch_pdl(fasta_offsets_kernel, g1, 256, 0, s, reinterpret_cast<const FastaRecord*>(records_dev), total_records, total_kept, offsets_dev));
+        else fasta_offsets_kernel<<<g1, 256, 0, s>>>(reinterpret_cast<const FastaRecord*>(records_dev), total_records, total_kept, offsets_dev);
         c->launches++;
         QD_CUDA(c, cudaGetLastError());
     }
@@ -1612,7 +1623,8 @@ extern "C" int qd_fasta_translate_frames(qd_ctx* c, int table, int strict, int f
     QD_CUDA(c, c->aux2.reserve((total_records + 1) * sizeof(uint64_t)));
     if (int rc = fasta_write_dev(c, R, c->aux1.as<uint8_t>(), c->aux0.as<FastaRecord>(), total_records, total_records, shift, s)) return rc;
     const unsigned g1 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total_records + 256) / 256, (uint64_t)c->sm_count * 8));
-    fasta_offsets_kernel<<<g1, 256, 0, s>>>(c->aux0.as<FastaRecord>(), total_records, total_kept, c->aux2.as<uint64_t>());
+    if (c->pdl) QD_CUDA(c, launch_pdl(fasta_offsets_kernel, g1, 256, 0, s, (const FastaRecord*)c->aux0.as<FastaRecord>(), total_records, total_kept, c->aux2.as<uint64_t>()));
+    else fasta_offsets_kernel<<<g1, 256, 0, s>>>(c->aux0.as<FastaRecord>(), total_records, total_kept, c->aux2.as<uint64_t>());
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
     // frames of all records (slot layout of qd_translate_frames_batch); the exact size is the run total the device finds

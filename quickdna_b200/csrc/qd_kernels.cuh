@@ -2559,6 +2559,7 @@ template <int MODE, int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint64_t* src, uint64_t n, uint64_t* block_sums,
                                                                        const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0) {
     pdl_trigger();
+    pdl_wait();  // (when launched as a dependent: src comes from the kernel before)
     if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
@@ -3110,6 +3111,7 @@ struct CanonSeqParams {
 };
 
 __global__ void __launch_bounds__(256) canon_seq_scan_kernel(const CanonSeqParams p) {
+    pdl_trigger();
     unsigned long long first[4] = {~0ull, ~0ull, ~0ull, ~0ull}, last1[4] = {0, 0, 0, 0};
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t c = __ldg(p.decode + __ldg(p.dna + i));
@@ -3163,6 +3165,8 @@ __device__ __forceinline__ void canon_seq_maps(const unsigned long long* state, 
 }
 
 __global__ void __launch_bounds__(256) canon_seq_diff_kernel(const CanonSeqParams p) {
+    pdl_trigger();
+    pdl_wait();
     uint32_t fw, rv;
     canon_seq_maps(p.state, fw, rv);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -3176,6 +3180,8 @@ __global__ void __launch_bounds__(256) canon_seq_diff_kernel(const CanonSeqParam
 }
 
 __global__ void __launch_bounds__(256) canon_seq_write_kernel(const CanonSeqParams p) {
+    pdl_trigger();
+    pdl_wait();
     uint32_t fw, rv;
     canon_seq_maps(p.state, fw, rv);
     bool use_rev = false;
@@ -3284,6 +3290,7 @@ __device__ __forceinline__ uint64_t fa_last_line_start(const FaGranule& G, unsig
 }
 
 __global__ void __launch_bounds__(FA_THREADS) fasta_lines_kernel(const FastaParams p) {
+    pdl_trigger();
     __shared__ uint64_t warp_sums[32];
     for (uint64_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
         FaGranule G;
@@ -3298,6 +3305,8 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_lines_kernel(const FastaPara
 
 template <bool WRITE>
 __global__ void __launch_bounds__(FA_THREADS) fasta_pass_kernel(const FastaParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ uint8_t tab_s[256];
     __shared__ uint64_t warp_sums[32];
     __shared__ __align__(16) uint8_t stage[FA_BLOCK_BYTES + 16];
@@ -3408,6 +3417,8 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_pass_kernel(const FastaParam
 // pass 4: one thread per record: where its content and its lines end (= where the next record's begin), and the extent
 // of its header lines in the text; record 0 is the headerless one when `shift` says so
 __global__ void __launch_bounds__(256) fasta_finish_kernel(const FastaParams p, uint64_t n_records, uint64_t shift) {
+    pdl_trigger();
+    pdl_wait();
     const uint64_t total_kept = p.pre_kept[p.n_blocks];
     const uint64_t n_lines = p.pre_nl[p.n_blocks] + ((p.n > 0 && p.text[p.n - 1] != '\n') ? 1 : 0);
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_records && r < p.max_records; r += (uint64_t)gridDim.x * blockDim.x) {
@@ -3447,6 +3458,8 @@ __global__ void __launch_bounds__(256) fasta_finish_kernel(const FastaParams p, 
 // offsets[n_records] = the number of masks
 __global__ void __launch_bounds__(256) fasta_offsets_kernel(const FastaRecord* __restrict__ records, uint64_t n_records, uint64_t total_kept,
                                                             uint64_t* __restrict__ offsets) {
+    pdl_trigger();
+    pdl_wait();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_records; i += (uint64_t)gridDim.x * blockDim.x)
         offsets[i] = i < n_records ? records[i].content_begin : total_kept;
 }
