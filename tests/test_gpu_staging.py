@@ -219,3 +219,49 @@ def test_tiny_and_small_call_paths_agree(N, B, monkeypatch):
     finally:
         tiny.close()
         plain.close()
+
+
+def test_dependent_launches_and_plain_launches_agree(N, B, monkeypatch):
+    """Chains of short kernels (parse, variable-length batches, the FASTA scanner, the whole-sequence canonical form, the nine
+    launches of an all_windows call) run as programmatic dependent launches; QD_PDL=0 (read when a context is made) launches
+    them plainly.  Same bytes either way, and equal to the oracle's."""
+    import torch
+
+    monkeypatch.setenv("QD_PDL", "0")
+    plain = N.Context(0)
+    monkeypatch.delenv("QD_PDL")
+    pdl = N.Context(0)
+    try:
+        rng = np.random.default_rng(21)
+        dna = oracle.synth(3, 0, 3_000_000)
+        spaced = dna.copy()
+        spaced[500::97] = 0x20
+        for src in (dna, spaced):
+            a, b = B.parse(src, ctx=pdl), B.parse(src, ctx=plain)
+            assert np.array_equal(a, b)
+            assert np.array_equal(a[:4000], oracle.parse(src[:5000].tobytes())[:4000])
+        lens = np.concatenate([rng.integers(0, 2500, 3000), [48 * 600, 48 * 65536 + 7, 0, 5]])
+        offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(lens)
+        flat = oracle.synth(5, 0, int(offs[-1]))
+        ra = B.translate_frames_batch((flat, offs), table=11, frames=6, ctx=pdl)
+        rb = B.translate_frames_batch((flat, offs), table=11, frames=6, ctx=plain)
+        assert np.array_equal(ra.data, rb.data)
+        for i in (0, 17, 2999, 3000, 3001, 3003):
+            assert ra.sequence_frames(i) == (oracle.py_all_frames(11, flat[int(offs[i]):int(offs[i + 1])].tobytes()) if lens[i] >= 3 else [])
+        text = b"".join(b">r%d\n" % i + oracle.synth(7, i * 700, 700).tobytes() + b"\n" for i in range(300))
+        sa, fa = B.fasta_translate_frames(text, ctx=pdl)
+        sb, fb = B.fasta_translate_frames(text, ctx=plain)
+        assert len(sa) == len(sb) == 300 and np.array_equal(fa.data, fb.data)
+        assert fa.sequence_frames(7) == oracle.py_all_frames(1, oracle.synth(7, 7 * 700, 700).tobytes())
+        assert np.array_equal(B.canonical(dna[:200_001], ctx=pdl), B.canonical(dna[:200_001], ctx=plain))
+        x = torch.from_numpy(dna[: 40 * 5000].reshape(40, 5000).copy()).cuda()
+        ca, da, aa = B.windows_all_batch_dev(x, 40, 5000, ctx=pdl)
+        cb, db, ab = B.windows_all_batch_dev(x, 40, 5000, ctx=plain)
+        torch.cuda.synchronize()
+        assert ca == cb and torch.equal(da, db) and torch.equal(aa, ab)
+        wd, wa, _o, _c = oracle.windows_all(oracle.masks_of(dna[:5000]), 42, 20)
+        assert da[: ca[0] * 42].cpu().numpy().tobytes() == wd[: ca[0]].tobytes()
+    finally:
+        pdl.close()
+        plain.close()
