@@ -381,9 +381,9 @@ bool use_big_tiles(const qd_ctx* c, uint64_t total_runs) { return total_runs >= 
 // launch with programmatic stream serialization: the kernel may become resident before its predecessor in the stream has
 // finished and calls pdl_wait() before it reads what the predecessor wrote (qd_kernels.cuh)
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -483,19 +483,22 @@ int frames_uniform_dev(qd_ctx* c, int slot, int enc, int strict, int frames, con
 
 template <int MODE, int OP = 0>
 int device_exclusive_scan(qd_ctx* c, const uint64_t* src, uint64_t n, uint64_t* dst, DevBuf& block_sums, cudaStream_t s,
-                          const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0, bool dependent = false) {
+                          const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0, bool dependent = false, unsigned batch = 1,
+                          uint64_t batch_stride = 0) {
+    // batch > 1: `batch` arrays of n values, array y at src / dst + y * batch_stride, scanned by the same three launches
     const uint64_t n_blocks = std::max<uint64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    QD_CUDA(c, block_sums.reserve(n_blocks * sizeof(uint64_t)));
+    QD_CUDA(c, block_sums.reserve(batch * n_blocks * sizeof(uint64_t)));
+    const dim3 grid((unsigned)n_blocks, batch);
+    uint64_t* const sums = block_sums.as<uint64_t>();
     // dependent: the kernel before this scan in the stream triggers early (every kernel of the scan waits for its predecessor)
-    if (dependent && c->pdl) QD_CUDA(c, launch_pdl(scan_block_sums_kernel<MODE, OP>, (unsigned)n_blocks, SCAN_THREADS, 0, s, src, n, block_sums.as<uint64_t>(), gate, gate_gen));
-    else scan_block_sums_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), gate, gate_gen);
+    if (dependent && c->pdl) QD_CUDA(c, launch_pdl(scan_block_sums_kernel<MODE, OP>, grid, SCAN_THREADS, 0, s, src, n, sums, gate, gate_gen, batch_stride));
+    else scan_block_sums_kernel<MODE, OP><<<grid, SCAN_THREADS, 0, s>>>(src, n, sums, gate, gate_gen, batch_stride);
     if (c->pdl) {
-        QD_CUDA(c, launch_pdl(scan_spine_kernel<OP>, 1, SCAN_THREADS, 0, s, block_sums.as<uint64_t>(), n_blocks, gate, gate_gen));
-        QD_CUDA(c, launch_pdl(scan_finish_kernel<MODE, OP>, (unsigned)n_blocks, SCAN_THREADS, 0, s, src, n, (const uint64_t*)block_sums.as<uint64_t>(), dst, gate,
-                              gate_gen));
+        QD_CUDA(c, launch_pdl(scan_spine_kernel<OP>, dim3(batch), SCAN_THREADS, 0, s, sums, n_blocks, gate, gate_gen));
+        QD_CUDA(c, launch_pdl(scan_finish_kernel<MODE, OP>, grid, SCAN_THREADS, 0, s, src, n, (const uint64_t*)sums, dst, gate, gate_gen, batch_stride));
     } else {
-        scan_spine_kernel<OP><<<1, SCAN_THREADS, 0, s>>>(block_sums.as<uint64_t>(), n_blocks, gate, gate_gen);
-        scan_finish_kernel<MODE, OP><<<(unsigned)n_blocks, SCAN_THREADS, 0, s>>>(src, n, block_sums.as<uint64_t>(), dst, gate, gate_gen);
+        scan_spine_kernel<OP><<<batch, SCAN_THREADS, 0, s>>>(sums, n_blocks, gate, gate_gen);
+        scan_finish_kernel<MODE, OP><<<grid, SCAN_THREADS, 0, s>>>(src, n, sums, dst, gate, gate_gen, batch_stride);
     }
     c->launches += 3;
     QD_CUDA(c, cudaGetLastError());
@@ -1456,9 +1459,8 @@ static int fasta_count_dev(qd_ctx* c, int strict, int concat, int allow, const u
     else fasta_pass_kernel<false><<<grid, FA_THREADS, 0, s>>>(p);
     c->launches++;
     QD_CUDA(c, cudaGetLastError());
-    if (int rc = device_exclusive_scan<1>(c, p.cnt_kept, p.n_blocks, pre_kept, c->block_sums, s, nullptr, 0, true)) return rc;
-    if (int rc = device_exclusive_scan<1>(c, p.cnt_recs, p.n_blocks, pre_recs, c->block_sums, s, nullptr, 0, true)) return rc;
-    if (int rc = device_exclusive_scan<1>(c, p.cnt_nl, p.n_blocks, pre_nl, c->block_sums, s, nullptr, 0, true)) return rc;
+    // kept bytes, record starts and line ends per block: three arrays nb1 entries apart, scanned by one set of launches
+    if (int rc = device_exclusive_scan<1>(c, p.cnt_kept, p.n_blocks, pre_kept, c->block_sums, s, nullptr, 0, true, 3, nb1)) return rc;
     return QD_OK;
 }
 

@@ -2556,11 +2556,16 @@ __device__ __forceinline__ void scan_load_items(const uint64_t* src, uint64_t n,
 
 template <int MODE, int OP = 0>
 // gate / gate_gen: the kernel returns at once unless *gate == gate_gen (nullptr: always runs); see ParseParams
+// batch_stride: blockIdx.y selects one of several arrays of n values scanned in the same launches (array y at src / dst +
+// y * batch_stride, its block sums at block_sums + y * blocks per array); 0 for a single array
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint64_t* src, uint64_t n, uint64_t* block_sums,
-                                                                       const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0) {
+                                                                       const unsigned long long* gate = nullptr, unsigned long long gate_gen = 0,
+                                                                       uint64_t batch_stride = 0) {
     pdl_trigger();
     pdl_wait();  // (when launched as a dependent: src comes from the kernel before)
     if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
+    src += blockIdx.y * batch_stride;
+    block_sums += (uint64_t)blockIdx.y * gridDim.x;
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS];
@@ -2580,6 +2585,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* bloc
     pdl_trigger();
     pdl_wait();  // (a dependent launch: the block sums come from the kernel before)
     if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
+    block_sums += (uint64_t)blockIdx.x * n_blocks;  // one CTA per array of a batch
     __shared__ uint64_t warp_sums[32];
     __shared__ uint64_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -2611,10 +2617,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(uint64_t* bloc
 template <int MODE, int OP = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(const uint64_t* src, uint64_t n, const uint64_t* block_sums,
                                                                    uint64_t* dst, const unsigned long long* gate = nullptr,
-                                                                   unsigned long long gate_gen = 0) {
+                                                                   unsigned long long gate_gen = 0, uint64_t batch_stride = 0) {
     pdl_trigger();
     pdl_wait();
     if (gate != nullptr && *reinterpret_cast<const volatile unsigned long long*>(gate) != gate_gen) return;
+    src += blockIdx.y * batch_stride;
+    dst += blockIdx.y * batch_stride;
+    block_sums += (uint64_t)blockIdx.y * gridDim.x;
     __shared__ uint64_t warp_sums[32];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS];
