@@ -1483,32 +1483,34 @@ static int fasta_write_dev(qd_ctx* c, FastaRun& R, uint8_t* masks_dev, FastaReco
     return QD_OK;
 }
 
-// after fasta_count_dev: totals and the first content error (synchronises the stream).  `text` is the host copy of the input.
+// after fasta_count_dev: totals and the first content error (synchronises the stream once).  `text` is the host copy of the
+// input, or NULL when it only exists on the device (text_dev): then the bytes in front of an error are fetched to count its line.
 static int fasta_totals(qd_ctx* c, int strict, int allow_preceding_comment, const uint8_t* text, const FastaRun& R, cudaStream_t s,
                         uint64_t* total_kept, uint64_t* total_records, uint64_t* shift_out, qd_err* err) {
     const FastaParams& p = R.p;
-    // totals: kept bytes, record starts, first header position, kept before it inside its block
-    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch + 0, p.pre_kept + p.n_blocks, 8, cudaMemcpyDeviceToHost, s));
-    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch + 1, p.pre_recs + p.n_blocks, 8, cudaMemcpyDeviceToHost, s));
-    QD_CUDA(c, cudaMemcpyAsync(c->h_scratch + 2, p.scalars, 16, cudaMemcpyDeviceToHost, s));
-    unsigned long long key = 0;
-    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
+    // one single-warp kernel writes the four numbers into mapped host memory: no copies, one synchronisation
+    unsigned long long* const h = reinterpret_cast<unsigned long long*>(c->h_tiny + TINY_IN_BYTES);
+    if (c->pdl) QD_CUDA(c, launch_pdl(fasta_totals_kernel, 1, 32, 0, s, p, h));
+    else fasta_totals_kernel<<<1, 32, 0, s>>>(p, h);
+    c->launches++;
+    QD_CUDA(c, cudaGetLastError());
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    const uint64_t kept = h[0], rec_starts = h[1], before = h[2];
+    const unsigned long long key = h[3];
     if (key != NO_ERROR_KEY) {
+        std::vector<uint8_t> head;
+        if (!text) {
+            head.resize(key + 1);
+            QD_CUDA(c, cudaMemcpyAsync(head.data(), p.text, key + 1, cudaMemcpyDeviceToHost, s));
+            QD_CUDA(c, cudaStreamSynchronize(s));
+            text = head.data();
+        }
         uint64_t line = 1;  // Located::line_number (src/errors.rs:8-15): lines are counted as BufRead::lines does
         for (size_t i = 0; i < key; i++) line += text[i] == '\n';
         uint8_t payload = 0;
         int kind = classify_byte(QD_ENC_ASCII, strict, text[key], &payload);
         if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
         return set_err(err, kind, payload, key, line);
-    }
-    const uint64_t kept = c->h_scratch[0], rec_starts = c->h_scratch[1], first_header = c->h_scratch[2];
-    uint64_t before = kept;
-    if (first_header != FA_NONE) {
-        const uint64_t blk = ((reinterpret_cast<uintptr_t>(p.text) & 15) + first_header) / FA_BLOCK_BYTES;
-        uint64_t pre = 0;
-        QD_CUDA(c, cudaMemcpyAsync(&pre, p.pre_kept + blk, 8, cudaMemcpyDeviceToHost, s));
-        QD_CUDA(c, cudaStreamSynchronize(s));
-        before = pre + c->h_scratch[3];
     }
     *shift_out = (!allow_preceding_comment && before > 0) ? 1 : 0;
     *total_kept = kept;
@@ -1537,6 +1539,19 @@ extern "C" int qd_fasta_scan(qd_ctx* c, int strict, int concatenate_headers, int
     if (n_records) *n_records = (size_t)total_records;
     if (!masks && !records) return QD_OK;  // counting call
     if (!masks || (total_records && !records) || max_records < total_records) return QD_ERR_INVALID_ARGUMENT;
+    // small results: masks and records next to each other on the device, ONE copy into pinned memory, two host copies out
+    const size_t rec_off = ((size_t)total_kept + 15) & ~(size_t)15, rec_bytes = (size_t)total_records * sizeof(FastaRecord);
+    if (rec_off + rec_bytes <= SMALL_CALL_BYTES) {
+        QD_CUDA(c, c->out.reserve(rec_off + rec_bytes + sizeof(FastaRecord)));
+        if (int rc = fasta_write_dev(c, R, c->out.as<uint8_t>(), reinterpret_cast<FastaRecord*>(c->out.as<uint8_t>() + rec_off), total_records, total_records,
+                                     shift, s))
+            return rc;
+        if (rec_off + rec_bytes) QD_CUDA(c, cudaMemcpyAsync(c->h_stage, c->out.p, rec_off + rec_bytes, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        if (total_kept) memcpy(masks, c->h_stage, total_kept);
+        if (rec_bytes) memcpy(records, c->h_stage + rec_off, rec_bytes);
+        return QD_OK;
+    }
     QD_CUDA(c, c->out.reserve(total_kept + 16));
     QD_CUDA(c, c->aux0.reserve((total_records + 1) * sizeof(FastaRecord)));
     if (int rc = fasta_write_dev(c, R, c->out.as<uint8_t>(), c->aux0.as<FastaRecord>(), total_records, total_records, shift, s)) return rc;
@@ -1565,19 +1580,6 @@ extern "C" int qd_fasta_scan_dev(qd_ctx* c, int strict, int concatenate_headers,
     FastaRun R;
     if (int rc = fasta_count_dev(c, strict, concatenate_headers, allow_preceding_comment, text_dev, n, R, s)) return rc;
     // the totals; a content error is located with the text still on the device: its byte, and the newlines in front of it
-    unsigned long long key = 0;
-    if (int rc = fetch_err_key(c, s, &key)) return rc;  // synchronises
-    if (key != NO_ERROR_KEY) {
-        std::vector<uint8_t> head(key + 1);
-        QD_CUDA(c, cudaMemcpyAsync(head.data(), text_dev, key + 1, cudaMemcpyDeviceToHost, s));
-        QD_CUDA(c, cudaStreamSynchronize(s));
-        uint64_t line = 1;
-        for (size_t i = 0; i < key; i++) line += head[i] == '\n';
-        uint8_t payload = 0;
-        int kind = classify_byte(QD_ENC_ASCII, strict, head[key], &payload);
-        if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
-        return set_err(err, kind, payload, key, line);
-    }
     uint64_t total_kept = 0, total_records = 0, shift = 0;
     if (int rc = fasta_totals(c, strict, allow_preceding_comment, nullptr, R, s, &total_kept, &total_records, &shift, err)) return rc;
     if (n_masks) *n_masks = (size_t)total_kept;

@@ -3423,6 +3423,20 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_pass_kernel(const FastaParam
     }
 }
 
+// after the count pass and its scans: what the host needs before it can size the second pass, gathered into five words (of
+// mapped host memory: no copy) -- kept bytes, record starts, kept bytes before the first header line, the first invalid byte
+__global__ void __launch_bounds__(32) fasta_totals_kernel(const FastaParams p, unsigned long long* __restrict__ out) {
+    pdl_wait();
+    if (threadIdx.x != 0) return;
+    const uint64_t kept = p.pre_kept[p.n_blocks], first_header = p.scalars[0];
+    uint64_t before = kept;
+    if (first_header != FA_NONE) before = p.pre_kept[((reinterpret_cast<uintptr_t>(p.text) & 15) + first_header) / FA_BLOCK_BYTES] + p.scalars[1];
+    out[0] = kept;
+    out[1] = p.pre_recs[p.n_blocks];
+    out[2] = before;
+    out[3] = *p.err_key;
+}
+
 // pass 4: one thread per record: where its content and its lines end (= where the next record's begin), and the extent
 // of its header lines in the text; record 0 is the headerless one when `shift` says so
 __global__ void __launch_bounds__(256) fasta_finish_kernel(const FastaParams p, uint64_t n_records, uint64_t shift) {

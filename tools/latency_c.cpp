@@ -31,6 +31,24 @@ int main() {
     time_it("qd_translate_frames (6)", [&] { qd_translate_frames(c, 1, QD_ENC_ASCII, 0, QD_FRAMES_ALL, dna.data(), n, out.data(), lens, &nf, &err); });
     size_t k;
     time_it("qd_parse", [&] { qd_parse(c, 0, dna.data(), n, out.data(), &k, &err); });
+    // a 30-kb FASTA file: one record, 70-column lines
+    std::vector<uint8_t> text;
+    for (const char* h = ">covid\n"; *h; h++) text.push_back((uint8_t)*h);
+    for (size_t i = 0; i < n; i++) {
+        text.push_back(dna[i]);
+        if (i % 70 == 69 || i + 1 == n) text.push_back('\n');
+    }
+    std::vector<uint8_t> masks(text.size());
+    std::vector<qd_fasta_record> recs(16);
+    std::vector<uint64_t> oo(17);
+    std::vector<uint8_t> frames(qd_slots_bytes(n, 6) + 4096);
+    size_t n_masks = 0, n_recs = 0, out_bytes = 0;
+    time_it("qd_fasta_scan", [&] { qd_fasta_scan(c, 0, 1, 0, text.data(), text.size(), masks.data(), &n_masks, recs.data(), recs.size(), &n_recs, &err); });
+    time_it("qd_fasta_translate_frames", [&] {
+        qd_fasta_translate_frames(c, 1, 0, QD_FRAMES_ALL, 1, 0, text.data(), text.size(), recs.data(), recs.size(), &n_recs, frames.data(), frames.size(),
+                                  oo.data(), &out_bytes, &err);
+    });
+    printf("records %zu masks %zu frame bytes %zu\n", n_recs, n_masks, out_bytes);
     qd_ctx_destroy(c);
     return 0;
 }
