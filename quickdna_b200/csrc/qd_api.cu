@@ -1638,6 +1638,24 @@ extern "C" int qd_fasta_translate_frames(qd_ctx* c, int table, int strict, int f
     if (int rc = frames_csr_dev(c, slot, QD_ENC_MASK, strict, frames, c->aux1.as<uint8_t>(), total_kept, c->aux2.as<uint64_t>(), total_records,
                                 c->run_prefix, c->tile_first, c->block_sums, c->out.as<uint8_t>(), s))
         return rc;
+    // small results: records, run prefix and frames (up to the bound) into pinned memory behind the kernels, ONE synchronisation
+    const size_t rec_bytes = (size_t)total_records * sizeof(FastaRecord), pre_off = (rec_bytes + 15) & ~(size_t)15;
+    const size_t fr_off = (pre_off + (size_t)(total_records + 1) * 8 + 15) & ~(size_t)15;
+    if (out && records && max_records >= total_records && fr_off + runs_bound * stride <= SMALL_CALL_BYTES) {
+        QD_CUDA(c, cudaMemcpyAsync(c->h_stage, c->aux0.p, rec_bytes, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaMemcpyAsync(c->h_stage + pre_off, c->run_prefix.p, (total_records + 1) * 8, cudaMemcpyDeviceToHost, s));
+        if (runs_bound) QD_CUDA(c, cudaMemcpyAsync(c->h_stage + fr_off, c->out.p, runs_bound * stride, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        const uint64_t* pre = reinterpret_cast<const uint64_t*>(c->h_stage + pre_off);
+        const uint64_t need = pre[total_records] * stride;
+        if (out_bytes) *out_bytes = (size_t)need;
+        if (out_capacity < need) return QD_ERR_INVALID_ARGUMENT;
+        memcpy(records, c->h_stage, rec_bytes);
+        if (out_offsets)
+            for (uint64_t i = 0; i <= total_records; i++) out_offsets[i] = pre[i] * stride;
+        memcpy(out, c->h_stage + fr_off, need);
+        return QD_OK;
+    }
     QD_CUDA(c, cudaMemcpyAsync(c->h_scratch, c->run_prefix.as<uint64_t>() + total_records, 8, cudaMemcpyDeviceToHost, s));
     QD_CUDA(c, cudaStreamSynchronize(s));
     const uint64_t need = c->h_scratch[0] * stride;
