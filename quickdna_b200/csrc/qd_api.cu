@@ -510,7 +510,7 @@ uint64_t runs_upper_bound(uint64_t total_nt, uint64_t n_seq) { return total_nt /
 // variable-length batch on device buffers; offsets_dev are absolute, `flat_base` = offsets[0]
 int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const uint8_t* dna_dev, uint64_t total_nt,
                    const uint64_t* offsets_dev, size_t n_seq, DevBuf& run_prefix, DevBuf& tile_first, DevBuf& block_sums,
-                   uint8_t* out_dev, cudaStream_t s, uint64_t flat_base = 0, uint64_t key_base = 0) {
+                   uint8_t* out_dev, cudaStream_t s, uint64_t flat_base = 0, uint64_t key_base = 0, unsigned long long* err_key = nullptr) {
     if (n_seq == 0) return QD_OK;
     if (n_seq >= 0xffffffffull || total_nt / RUN_NT + n_seq > 0xffffff00ull) {
         c->last_error = "batch too large for one launch";
@@ -542,7 +542,7 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     m.n_seq = n_seq;
     m.flat_base = flat_base;
     m.total_nt = total_nt;
-    m.err_key = c->d_err;
+    m.err_key = err_key ? err_key : c->d_err;
     m.run_prefix = rp_dev;
     m.off_copy = off_pad;
     m.arr_entries = arr_entries;
@@ -589,7 +589,7 @@ int frames_csr_dev(qd_ctx* c, int slot, int enc, int strict, int frames, const u
     set_encoding(c, p, enc, strict);
     if (frames == QD_FRAMES_ONE)
         if (int rc = direct_table(c, slot, enc, strict, s, &p.direct)) return rc;
-    p.err_key = c->d_err;
+    p.err_key = err_key ? err_key : c->d_err;
     p.flat_base = flat_base;
     p.key_base = key_base;
     return launch_frames(c, frames, p, s, big, /*dependent=*/true);
@@ -2252,6 +2252,33 @@ static int batch_pipeline(qd_ctx* c, int slot, int enc, int strict, int frames, 
         }
         out_offsets[n_seq] = acc;
         oo = out_offsets;
+        const size_t offs_at = ((size_t)total_nt + 15) & ~(size_t)15;
+        if (c->tiny_calls && offs_at + (n_seq + 1) * 8 <= TINY_IN_BYTES && acc <= TINY_OUT_BYTES) {
+            // a tiny variable-length batch: nucleotides, offsets, error key and slots in mapped host memory -- the scan, the
+            // map kernels and the frame kernel run on them as they are: no copies, one synchronisation
+            uint8_t* const h_in = c->h_tiny;
+            uint64_t* const h_offs = reinterpret_cast<uint64_t*>(c->h_tiny + offs_at);
+            unsigned long long* const h_key = reinterpret_cast<unsigned long long*>(c->h_tiny + TINY_IN_BYTES + 16);
+            uint8_t* const h_out = c->h_tiny + TINY_IN_BYTES + 64;
+            cudaStream_t s = c->stream;
+            memcpy(h_in, dna, total_nt);
+            for (size_t i = 0; i <= n_seq; i++) h_offs[i] = offsets[i] - offsets[0];
+            *h_key = NO_ERROR_KEY;
+            if (int rc = frames_csr_dev(c, slot, enc, strict, frames, h_in, total_nt, h_offs, n_seq, c->run_prefix, c->tile_first, c->block_sums, h_out, s,
+                                        0, 0, h_key))
+                return rc;
+            QD_CUDA(c, cudaStreamSynchronize(s));
+            const unsigned long long key = *h_key;
+            if (key != NO_ERROR_KEY) {
+                const uint64_t seq = (uint64_t)(std::upper_bound(offsets, offsets + n_seq + 1, (uint64_t)key + offsets[0]) - offsets) - 1;
+                uint8_t payload = 0;
+                int kind = classify_byte(enc, strict, dna[key], &payload);
+                if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+                return set_err(err, kind, payload, key + offsets[0] - offsets[seq], seq);
+            }
+            memcpy(out, h_out, acc);
+            return QD_OK;
+        }
     }
     for (int i = 0; i < N_PIPE; i++) QD_CUDA(c, cudaStreamSynchronize(c->pipe[i].stream));
     if (int rc = reset_err_key(c, c->stream)) return rc;

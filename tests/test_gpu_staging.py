@@ -216,6 +216,28 @@ def test_tiny_and_small_call_paths_agree(N, B, monkeypatch):
                 B.translate_frames_batch(bad, ctx=c)
             errs.append((ei.value.seq_index, ei.value.pos, ei.value.kind, ei.value.byte))
         assert errs[0] == errs[1] == (57, 123, 2, ord("@"))
+        # variable-length batches: nucleotides and offsets in mapped memory, the scan and map kernels run on them as they are
+        for lens in ([0, 1, 2, 3, 47, 48, 49, 300, 0, 1000, 5], rng.integers(0, 700, 150).tolist(), [100_000], [0, 0, 0], [2, 2]):
+            offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum(lens)
+            flat = np.frombuffer(b"ACGTacgtNRYK", dtype=np.uint8)[rng.integers(0, 12, max(int(offs[-1]), 1))].copy()[: int(offs[-1])]
+            for frames in (N.FRAMES_ONE, N.FRAMES_SELF, N.FRAMES_ALL):
+                a = B.translate_frames_batch((flat, offs), table=2, frames=frames, ctx=tiny)
+                b = B.translate_frames_batch((flat, offs), table=2, frames=frames, ctx=plain)
+                assert np.array_equal(a.data, b.data) and np.array_equal(a.out_offsets, b.out_offsets)
+                for i in range(0, len(lens), 7):
+                    assert a.sequence_frames(i) == b.sequence_frames(i)
+            if len(lens) > 9 and lens[9] == 1000:
+                r = flat[int(offs[9]):int(offs[10])].tobytes()
+                assert B.translate_frames_batch((flat, offs), table=2, frames=6, ctx=tiny).sequence_frames(9) == oracle.py_all_frames(2, r)
+                dirty = flat.copy()
+                dirty[int(offs[9]) + 77] = ord("#")
+                errs = []
+                for c in (tiny, plain):
+                    with pytest.raises(ValueError) as ei:
+                        B.translate_frames_batch((dirty, offs), table=2, frames=6, ctx=c)
+                    errs.append((ei.value.seq_index, ei.value.pos, ei.value.kind, ei.value.byte))
+                assert errs[0] == errs[1] == (9, 77, 2, ord("#"))
     finally:
         tiny.close()
         plain.close()

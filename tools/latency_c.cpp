@@ -31,6 +31,30 @@ int main() {
     time_it("qd_translate_frames (6)", [&] { qd_translate_frames(c, 1, QD_ENC_ASCII, 0, QD_FRAMES_ALL, dna.data(), n, out.data(), lens, &nf, &err); });
     size_t k;
     time_it("qd_parse", [&] { qd_parse(c, 0, dna.data(), n, out.data(), &k, &err); });
+    // the window calls on the same 30-kb genome
+    std::vector<uint8_t> rows((n - 41) * 42 + 64);
+    std::vector<uint64_t> keys(2 * (n - 41) + 8);
+    size_t nw = 0;
+    time_it("qd_canonical_windows (42)", [&] { qd_canonical_windows(c, QD_ENC_ASCII, 0, dna.data(), n, 42, rows.data(), &err); });
+    time_it("qd_canonical_window_keys", [&] { qd_canonical_window_keys(c, QD_ENC_ASCII, 0, 0, dna.data(), n, 42, keys.data(), &err); });
+    time_it("qd_canonical", [&] { qd_canonical(c, QD_ENC_ASCII, 0, dna.data(), n, out.data(), &err); });
+    time_it("qd_windows (42)", [&] { qd_windows(c, dna.data(), n, 42, rows.data(), &nw); });
+    {
+        const size_t n_win = 500;
+        std::vector<uint8_t> win(n_win * 42), ex(n_win * 16 * 42);
+        std::vector<uint64_t> counts(n_win), index(n_win + 1);
+        for (size_t i = 0; i < n_win * 42; i++) win[i] = dna[i];
+        for (size_t i = 0; i < n_win; i++) win[i * 42 + 7] = 'N', win[i * 42 + 30] = 'R';
+        time_it("qd_expansion_windows (500)", [&] { qd_expansion_windows(c, QD_ENC_ASCII, win.data(), n_win, 42, 16, counts.data(), index.data(), ex.data(), &err); });
+    }
+    {
+        const size_t n_seq = 100, len = 299;
+        std::vector<uint64_t> offs(n_seq + 1), oo2(n_seq + 1);
+        for (size_t i = 0; i <= n_seq; i++) offs[i] = i * len;
+        std::vector<uint8_t> fr(qd_batch_out_bytes(offs.data(), n_seq, 6) + 64);
+        time_it("qd_translate_frames_batch", [&] { qd_translate_frames_batch(c, 1, QD_ENC_ASCII, 0, QD_FRAMES_ALL, dna.data(), offs.data(), n_seq, fr.data(), oo2.data(), &err); });
+        time_it("qd_translate_frames_batch_u", [&] { qd_translate_frames_batch_uniform(c, 1, QD_ENC_ASCII, 0, QD_FRAMES_ALL, dna.data(), n_seq, len, fr.data(), &err); });
+    }
     // a 30-kb FASTA file: one record, 70-column lines
     std::vector<uint8_t> text;
     for (const char* h = ">covid\n"; *h; h++) text.push_back((uint8_t)*h);
