@@ -874,7 +874,9 @@ def main():
                        "reads_per_gpu": n_reads, "read_len": READ_LEN, "parallelism": f"{world} independent shards, no collective",
                        "l2": "inputs (10 GB) and outputs (20 GB) per step far exceed the 126 MB L2",
                        "checks": checks},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra,
+            # the long per-leg records first: a reader who keeps only the tail of the line still gets the roofline with
+            # its compact per-leg table (revcomp, parse, windows ...), the CPU baseline and the end-to-end numbers
+            "extra": extra, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
