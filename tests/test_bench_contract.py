@@ -61,3 +61,22 @@ def test_leg_traffic_is_filled_only_for_the_captured_workload():
     # round 2: the expansion path reads its windows once (1.26 x algorithmic with the two-pass form)
     e = legs["expansion_windows"]
     assert (e["dram_read"] + e["dram_write"]) / e["algorithmic_bytes_per_launch"] < 1.05
+
+
+def test_stored_bench_line_keeps_the_contract_and_ends_with_the_roofline_table():
+    """The committed N = 1 line (profiles/r02_bench_n1.json): every contract key, the whole-output checks all true, and the
+    roofline -- with its compact per-leg table -- as the LAST key, so that a reader of the tail of the line sees it."""
+    raw = open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")).read().strip().splitlines()[-1]
+    line = json.loads(raw)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["metric"] == bench.METRIC and line["unit"] == bench.UNIT and line["n_gpus"] == 1 and line["gpu_launches"] == line["steps"]
+    assert list(line)[-1] == "roofline" and raw.rfind('"roofline"') > len(raw) - 3000
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.85 < r["frac"] <= 1.0
+    assert {"revcomp", "parse", "canonical_windows", "windows_all", "expansion_windows"} <= set(r["legs"])
+    checks = line["config"]["checks"]
+    assert checks and all(v is True for v in checks.values() if isinstance(v, bool))
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and not line["clocks"]["reasons"]
