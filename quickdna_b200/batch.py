@@ -374,6 +374,12 @@ def expansion_windows(windows, max_expansions: int = 16, enc: int = N.ENC_ASCII,
     out_index = np.empty(n_win + 1, dtype=np.uint64)
     err = N.QdErr()
     L = N.lib()
+    if 0 < n_win and w <= 64 and max_expansions < 128 and n_win * max_expansions * w <= (1 << 19):
+        # small batches: one call with room for the cap (the library runs its one-pass kernel and copies back once)
+        room = np.empty((n_win * max_expansions, w), dtype=np.uint8)
+        rc = L.qd_expansion_windows(ctx.handle, enc, _p(a), n_win, w, max_expansions, _p(counts), _p(out_index), _p(room), C.byref(err))
+        ctx.check(rc, err)
+        return counts, out_index, room[: int(out_index[n_win])]
     rc = L.qd_expansion_windows(ctx.handle, enc, _p(a), n_win, w, max_expansions, _p(counts), _p(out_index), None, C.byref(err))
     ctx.check(rc, err)
     total = int(out_index[n_win])

@@ -2568,6 +2568,41 @@ extern "C" int qd_expansion_windows(qd_ctx* c, int enc, const uint8_t* windows, 
     const size_t in_bytes = n_win * w;
     const bool fast = expansion_fast_path(w, max_expansions);
     QD_CUDA(c, c->in.reserve(in_bytes + 16));
+    // Small calls (DnaSequence::expansions() of one window, a few hundred windows): the one-pass kernel writes rows, counts,
+    // row index and error key into ONE device buffer sized by the cap, which comes back in one copy through pinned memory --
+    // no synchronisation between a count and a write pass.
+    const size_t row_bound = n_win * (size_t)max_expansions * w;
+    const size_t off_c = (row_bound + 15) & ~(size_t)15, off_i = off_c + n_win * 8, off_k = off_i + (n_win + 1) * 8;
+    if (fast && out && off_k + 8 <= (size_t(1) << 20)) {
+        QD_CUDA(c, c->out.reserve(off_k + 16));
+        QD_CUDA(c, c->aux1.reserve(((n_win + 31) / 32 + 1) * 8));  // ticket counter + status word per warp tile
+        uint8_t* const d = c->out.as<uint8_t>();
+        if (int rc = staged_upload(c, c->in.p, windows, in_bytes, s)) return rc;
+        QD_CUDA(c, cudaMemsetAsync(d + off_k, 0xff, 8, s));
+        ExpandParams p = expansion_params(c, enc, c->in.as<uint8_t>(), n_win, w, max_expansions, reinterpret_cast<uint64_t*>(d + off_c), nullptr,
+                                          reinterpret_cast<uint64_t*>(d + off_i), nullptr);
+        p.err_key = reinterpret_cast<unsigned long long*>(d + off_k);
+        if (int rc = expansion_fused_dev(c, p, enc, d, n_win * max_expansions, c->aux1.as<uint64_t>(), s)) return rc;
+        QD_CUDA(c, cudaMemcpyAsync(c->h_stage, d, off_k + 8, cudaMemcpyDeviceToHost, s));
+        QD_CUDA(c, cudaStreamSynchronize(s));
+        unsigned long long key;
+        memcpy(&key, c->h_stage + off_k, 8);
+        if (key != NO_ERROR_KEY) {
+            uint8_t payload = 0;
+            int kind = classify_byte(enc, 0, windows[key], &payload);
+            if (kind == QD_OK) kind = QD_ERR_BAD_NUCLEOTIDE;
+            return set_err(err, kind, payload, key % w, key / w);
+        }
+        const uint64_t* h_counts = reinterpret_cast<const uint64_t*>(c->h_stage + off_c);
+        const uint64_t* h_index = reinterpret_cast<const uint64_t*>(c->h_stage + off_i);
+        if (counts) memcpy(counts, h_counts, n_win * 8);
+        if (out_index) {
+            for (size_t i = 0; i < n_win; i++) out_index[i] = h_counts[i] > max_expansions ? ~0ull : h_index[i];  // skipped windows are marked
+            out_index[n_win] = h_index[n_win];
+        }
+        memcpy(out, c->h_stage, (size_t)h_index[n_win] * w);
+        return QD_OK;
+    }
     QD_CUDA(c, c->aux0.reserve(n_win * 8));        // counts
     QD_CUDA(c, c->aux1.reserve(n_win * 8));        // emit
     QD_CUDA(c, c->aux2.reserve((n_win + 1) * 8));  // out_index
