@@ -185,6 +185,7 @@ struct qd_ctx {
     unsigned long long gate_gen = 0;
     std::map<int, uint8_t*> d_direct;  // one-frame direct codon tables, built on first use: key = slot * 4 + ascii * 2 + strict
     unsigned long long* d_err = nullptr;
+    unsigned long long* cur_err_key = nullptr;  // set by small_call for the length of one call: the key behind the result
     unsigned long long* h_err = nullptr;  // pinned
     uint64_t* h_scratch = nullptr;        // pinned, 8 x u64
     uint8_t* h_stage = nullptr;           // pinned staging for small host calls: [result | error key] in ONE copy
@@ -991,7 +992,7 @@ static CanonParams canonical_params(qd_ctx* c, int enc, int forward_only, const 
     p.or_forbid = ascii ? 0x80808080u : 0xe0e0e0e0u;
     p.filler = ascii ? 0x41u : 0x01u;
     p.letters = ascii ? ('A' | ('T' << 8) | ('C' << 16) | ((uint32_t)'G' << 24)) : (1u | (2u << 8) | (4u << 16) | (8u << 24));
-    p.err_key = c->d_err;
+    p.err_key = c->cur_err_key ? c->cur_err_key : c->d_err;
     return p;
 }
 
@@ -1369,7 +1370,7 @@ static int canonical_seq_dev(qd_ctx* c, int enc, int forward_only, const uint8_t
     p.forward_only = forward_only;
     p.state = st;
     p.out = out_dev;
-    p.err_key = c->d_err;
+    p.err_key = c->cur_err_key ? c->cur_err_key : c->d_err;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8));
     canon_seq_scan_kernel<<<grid, 256, 0, s>>>(p);
     if (c->pdl) {  // the second and third pass take their places while the pass before drains, and wait for it
@@ -1391,12 +1392,44 @@ extern "C" int qd_canonical_dev(qd_ctx* c, int enc, int forward_only, const uint
     return canonical_seq_dev(c, enc, forward_only, dna_dev, n, out_dev, pick_stream(c, stream));
 }
 
+// Small single-sequence host calls: result and error key lie next to each other on the device and come back in ONE copy
+// through pinned memory; launch(d_in, d_out, stream) enqueues the kernels, which report to the key behind the result.
+template <typename Launch>
+static int small_call(qd_ctx* c, const uint8_t* in, size_t n, uint8_t* out, size_t out_bytes, unsigned long long* key, Launch launch) {
+    cudaStream_t s = c->stream;
+    const size_t key_off = (out_bytes + 15) & ~(size_t)15;
+    QD_CUDA(c, c->in.reserve(n + 16));
+    QD_CUDA(c, c->out.reserve(key_off + 16));
+    uint8_t* const d = c->out.as<uint8_t>();
+    if (int rc = staged_upload(c, c->in.p, in, n, s)) return rc;
+    QD_CUDA(c, cudaMemsetAsync(d + key_off, 0xff, 8, s));
+    c->cur_err_key = reinterpret_cast<unsigned long long*>(d + key_off);
+    const int rc = launch(c->in.as<uint8_t>(), d, s);
+    c->cur_err_key = nullptr;
+    if (rc) return rc;
+    QD_CUDA(c, cudaMemcpyAsync(c->h_stage, d, key_off + 8, cudaMemcpyDeviceToHost, s));
+    QD_CUDA(c, cudaStreamSynchronize(s));
+    memcpy(key, c->h_stage + key_off, 8);
+    if (*key == NO_ERROR_KEY) memcpy(out, c->h_stage, out_bytes);
+    return QD_OK;
+}
+static bool small_result(size_t out_bytes) { return out_bytes + 32 <= SMALL_CALL_BYTES; }
+
 extern "C" int qd_canonical(qd_ctx* c, int enc, int forward_only, const uint8_t* dna, size_t n, uint8_t* out, qd_err* err) {
     clear_err(err);
     if (!c || (n && (!dna || !out))) return QD_ERR_INVALID_ARGUMENT;
     Guard g(c);
     if (!g.ok) return QD_ERR_CUDA;
     if (n == 0) return QD_OK;
+    if (small_result(n)) {
+        unsigned long long key = 0;
+        if (int rc = small_call(c, dna, n, out, n, &key, [&](const uint8_t* d_in, uint8_t* d_out, cudaStream_t st) {
+                return canonical_seq_dev(c, enc, forward_only, d_in, n, d_out, st);
+            }))
+            return rc;
+        if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+        return QD_OK;
+    }
     cudaStream_t s = c->stream;
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(n + 16));
@@ -2389,6 +2422,15 @@ extern "C" int qd_canonical_windows(qd_ctx* c, int enc, int forward_only, const 
     if (n < w) return QD_OK;
     cudaStream_t s = c->stream;
     const size_t out_bytes = (n - w + 1) * w;
+    if (small_result(out_bytes)) {
+        unsigned long long key = 0;
+        if (int rc = small_call(c, dna, n, out, out_bytes, &key, [&](const uint8_t* d_in, uint8_t* d_out, cudaStream_t st) {
+                return canonical_dev(c, enc, forward_only, d_in, 1, n, w, d_out, st);
+            }))
+            return rc;
+        if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+        return QD_OK;
+    }
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(out_bytes + 16));
     if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
@@ -2411,6 +2453,15 @@ extern "C" int qd_canonical_window_keys(qd_ctx* c, int enc, int forward_only, in
     if (n < w) return QD_OK;
     cudaStream_t s = c->stream;
     const size_t out_bytes = (n - w + 1) * key_bytes;
+    if (small_result(out_bytes)) {
+        unsigned long long key = 0;
+        if (int rc = small_call(c, dna, n, static_cast<uint8_t*>(keys), out_bytes, &key, [&](const uint8_t* d_in, uint8_t* d_out, cudaStream_t st) {
+                return canonical_keys_dev(c, enc, forward_only, kind, d_in, 1, n, w, d_out, st);
+            }))
+            return rc;
+        if (key != NO_ERROR_KEY) return report_single(enc, /*strict=*/1, dna, key, err);
+        return QD_OK;
+    }
     QD_CUDA(c, c->in.reserve(n + 16));
     QD_CUDA(c, c->out.reserve(out_bytes + 16));
     if (int rc = staged_upload(c, c->in.p, dna, n, s)) return rc;
