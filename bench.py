@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=0)
     ap.add_argument("--revcomp-nt", type=int, default=250_000_000)
     ap.add_argument("--window-seqs", type=int, default=80_000, help="99 999-nt sequences per GPU in the config-5 legs (64 GB / 8 GPUs)")
-    ap.add_argument("--window-chunk-seqs", type=int, default=768, help="sequences per ring chunk of the canonical / all_windows legs")
+    ap.add_argument("--window-chunk-seqs", type=int, default=2048, help="sequences per ring chunk of the canonical leg (two 8.6 GB slots; all_windows: at most 512, two 6.3 GB slots)")
     ap.add_argument("--expansion-chunk", type=int, default=12_000_000, help="windows per ring chunk of the expansion leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
